@@ -1,0 +1,267 @@
+/*
+ * gsfm_ra.h -- C ABI of the B200-native robust rotation-averaging solver.
+ *
+ * This is the drop-in boundary for ONE path of zhangganlin/GlobalSfMpy: the
+ * Ceres-based robust rotation averaging in
+ *   src/GSfM_nonlinear_rotation_estimator.cpp            (reference, all four entry points)
+ * reached through Theia's plugin interface
+ *   thirdparty/TheiaSfM/src/theia/sfm/global_pose_estimation/rotation_estimator.h:50-66
+ * and, from Python, through bind_src/GlobalSfMpy.cpp:534-548.
+ *
+ * Plain C: pointers and sizes only, no torch / Eigen / STL types.  Host buffers
+ * in, host buffers out (the library owns all device memory); a handle API keeps
+ * a problem resident in HBM across iterations.  Every function returns 0 on
+ * success and a negative gsfm_ra_status on failure; nothing aborts the process
+ * (the reference CHECK-aborts on null pointers, rotation_estimator.cpp:28,88,208).
+ * There is NO CPU fallback: without a CUDA device every compute entry point
+ * fails with GSFM_RA_ERR_NO_DEVICE.
+ *
+ * Conventions: view i has world->camera rotation
+ * R_i = Exp(omega_i); edge (i,j) carries omega_ij with R_j ~= R_ij * R_i
+ * (thirdparty/TheiaSfM/src/theia/sfm/twoview_info.h:123-126).  The residual of an
+ * edge is r = U * Log(R_j * R_i^T * R_ij^T) with U the 3x3 whitening / weight
+ * (include/pairwise_rotation_error_quat.hpp:215-247 and
+ *  theia/sfm/global_pose_estimation/pairwise_rotation_error.h:66-95).
+ */
+#ifndef GSFM_RA_H_
+#define GSFM_RA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSFM_RA_ABI_VERSION 1
+
+typedef enum {
+  GSFM_RA_OK = 0,
+  GSFM_RA_ERR_INVALID = -1,    /* bad argument / malformed problem                         */
+  GSFM_RA_ERR_NO_DEVICE = -2,  /* no CUDA device: the product path has no CPU fallback     */
+  GSFM_RA_ERR_CUDA = -3,       /* a CUDA runtime call or kernel failed                     */
+  GSFM_RA_ERR_UNSUPPORTED = -4,/* valid request this build does not implement              */
+  GSFM_RA_ERR_NUMERIC = -5     /* non-finite cost / linear solver breakdown                */
+} gsfm_ra_status;
+
+/* Same numeric values as theia::RotationErrorType,
+ * include/pairwise_rotation_error_quat.hpp:50-61. */
+typedef enum {
+  GSFM_RA_QUATERNION_NORM = 0,
+  GSFM_RA_ROTATION_MAT_FNORM = 1,
+  GSFM_RA_QUATERNION_COSINE = 2,
+  GSFM_RA_ANGLE_AXIS_COVARIANCE = 3,  /* U = chol((1e8*Sigma)^-1)^T   rotation_estimator.cpp:251-256 */
+  GSFM_RA_ANGLE_AXIS = 4,             /* U = I                         :257-259 */
+  GSFM_RA_ANGLE_AXIS_INLIERS = 5,     /* U = edge_weight * I           :260-264 (weight = #matches/100 from the host) */
+  GSFM_RA_ANGLE_AXIS_COV_INLIERS = 6, /* U = Lt * edge_weight          :265-274 */
+  GSFM_RA_ANGLE_AXIS_COVTRACE = 7,    /* U = sqrt(1/trace(1e8 Sigma)) I :275-282 */
+  GSFM_RA_ANGLE_AXIS_COVNORM = 8      /* U = sqrt(1/||1e8 Sigma||_F) I  :283-288 */
+} gsfm_ra_error_type;
+
+/* Robust losses of scripts/loss_functions.py (formulas at the cited lines). */
+typedef enum {
+  GSFM_RA_LOSS_TRIVIAL = 0,       /* :47   p: -                                */
+  GSFM_RA_LOSS_HUBER = 1,         /* :56   p[0]=a                              */
+  GSFM_RA_LOSS_SOFTLONE = 2,      /* :74   p[0]=a                              */
+  GSFM_RA_LOSS_CAUCHY = 3,        /* :88   p[0]=a                              */
+  GSFM_RA_LOSS_ARCTAN = 4,        /* :101  p[0]=a                              */
+  GSFM_RA_LOSS_TOLERANT = 5,      /* :114  p[0]=a p[1]=b                       */
+  GSFM_RA_LOSS_TUKEY = 6,         /* :167  p[0]=a                              */
+  GSFM_RA_LOSS_LONEHALF = 7,      /* :187  p[0]=a                              */
+  GSFM_RA_LOSS_LTWO = 8,          /* :216  p[0]=a                              */
+  GSFM_RA_LOSS_GEMANMCCLURE = 9,  /* :239  p[0]=a p[1]=sigma2                  */
+  GSFM_RA_LOSS_MAGSAC3 = 10,      /* :285  p[0]=sigma, flags bit0 = inverse    */
+  GSFM_RA_LOSS_MAGSAC4 = 11,      /* :344                                      */
+  GSFM_RA_LOSS_MAGSAC9 = 12       /* :402                                      */
+} gsfm_ra_loss_kind;
+
+#define GSFM_RA_LOSS_FLAG_INVERSE 1u
+
+typedef struct {
+  int32_t kind;     /* gsfm_ra_loss_kind                                            */
+  uint32_t flags;   /* GSFM_RA_LOSS_FLAG_*                                          */
+  double p[4];      /* parameters, see gsfm_ra_loss_kind                            */
+  double scale;     /* ScaledLoss factor 'a' (loss_functions.py:267-281); 1 = none  */
+} gsfm_ra_loss;
+
+/* One rotation-averaging problem, views densely renumbered 0..num_views-1 by the
+ * caller (the C++/Python shims do this from the reference's hash maps). All
+ * arrays are HOST memory and are only read.                                    */
+typedef struct {
+  uint32_t num_views;        /* N                                                   */
+  uint64_t num_edges;        /* E; (edge_i[k], edge_j[k]) unique unordered pairs,
+                                edge_i[k] != edge_j[k]                               */
+  const uint32_t* edge_i;    /* [E]                                                 */
+  const uint32_t* edge_j;    /* [E]   R_j ~= R_ij R_i                               */
+  const double* omega_ij;    /* [E][3] TwoViewInfo::rotation_2                       */
+  const double* cov6;        /* [E][6] C00 C11 C22 C01 C02 C12 (covariance_rot.txt
+                                order, src/uncertainty.cpp:200-229) or NULL          */
+  const double* edge_weight; /* [E] scalar weight or NULL (=1)                       */
+  int32_t error_type;        /* gsfm_ra_error_type                                  */
+  int32_t reserved;
+} gsfm_ra_problem;
+
+typedef enum {
+  GSFM_RA_SOLVER_PCG = 0,           /* block-Jacobi PCG on the block-3x3 CSR system   */
+  GSFM_RA_SOLVER_DENSE_CHOLESKY = 1 /* on-device dense LL^T, small problems only      */
+} gsfm_ra_linear_solver;
+
+/* Trust-region options: the Ceres 1.14 defaults the reference runs with
+ * (rotation_estimator.cpp:299-303 overrides only linear solver, 200 iterations,
+ * num_threads).  gsfm_ra_default_options() fills these.                        */
+typedef struct {
+  gsfm_ra_loss loss;
+  int32_t max_num_iterations;          /* 200                                       */
+  int32_t jacobi_scaling;              /* 1                                         */
+  double function_tolerance;           /* 1e-6                                      */
+  double gradient_tolerance;           /* 1e-10                                     */
+  double parameter_tolerance;          /* 1e-8                                      */
+  double initial_trust_region_radius;  /* 1e4                                       */
+  double max_trust_region_radius;      /* 1e16                                      */
+  double min_trust_region_radius;      /* 1e-32                                     */
+  double min_relative_decrease;        /* 1e-3                                      */
+  double min_lm_diagonal;              /* 1e-6                                      */
+  double max_lm_diagonal;              /* 1e32                                      */
+  int32_t linear_solver;               /* gsfm_ra_linear_solver                     */
+  int32_t pcg_max_iterations;          /* cap per linear solve                      */
+  double pcg_rtol;                     /* stop when ||b - Ax|| <= rtol * ||b||      */
+  int32_t num_threads;                 /* accepted for API parity (thread_num); unused */
+  int32_t device;                      /* CUDA ordinal; -1 = current device         */
+  int32_t verbose;                     /* 0 silent, 1 one line per iteration        */
+  int32_t reserved;
+} gsfm_ra_options;
+
+typedef enum {
+  GSFM_RA_TERM_NONE = 0,
+  GSFM_RA_TERM_FUNCTION_TOLERANCE = 1,
+  GSFM_RA_TERM_GRADIENT_TOLERANCE = 2,
+  GSFM_RA_TERM_PARAMETER_TOLERANCE = 3,
+  GSFM_RA_TERM_MAX_ITERATIONS = 4,
+  GSFM_RA_TERM_MIN_RADIUS = 5,
+  GSFM_RA_TERM_INVALID_STEPS = 6,
+  GSFM_RA_TERM_FAILURE = 7
+} gsfm_ra_termination;
+
+/* One row per trust-region iteration (iteration 0 = the initial evaluation). */
+typedef struct {
+  int32_t iteration;
+  int32_t step_is_successful;
+  int32_t step_is_valid;
+  int32_t linear_iterations;   /* PCG iterations of this step's solve            */
+  double cost;                 /* cost at the accepted point after this iteration */
+  double candidate_cost;
+  double cost_change;
+  double model_cost_change;
+  double relative_decrease;
+  double gradient_max_norm;
+  double step_norm;
+  double trust_region_radius;  /* radius after the update                        */
+  double linear_residual;      /* ||b-Ax||/||b|| reached by the solve            */
+} gsfm_ra_iteration;
+
+typedef struct {
+  int32_t termination;            /* gsfm_ra_termination                           */
+  int32_t num_iterations;         /* trust-region iterations executed (excl. it.0) */
+  int32_t num_successful_steps;
+  int32_t num_unsuccessful_steps;
+  int64_t total_linear_iterations;
+  double initial_cost;
+  double final_cost;
+  /* device time, CUDA events on the solver stream, milliseconds */
+  double ms_setup;     /* upload + CSR structure + whitening                        */
+  double ms_assemble;  /* K1: residual+Jacobian+loss+normal equations (all its.)    */
+  double ms_linear;    /* K2/K3: PCG incl. SpMV (all iterations)                    */
+  double ms_cost;      /* K1c: trial-point cost                                     */
+  double ms_total;     /* whole call, host wall clock                               */
+  int64_t kernel_launches; /* kernels launched by this call                         */
+  /* optional trace: caller-provided array of trace_capacity rows, may be NULL     */
+  gsfm_ra_iteration* trace;
+  int32_t trace_capacity;
+  int32_t trace_size;
+} gsfm_ra_summary;
+
+typedef struct gsfm_ra_solver gsfm_ra_solver; /* opaque, device-resident problem */
+
+/* ---- library ---------------------------------------------------------------*/
+int gsfm_ra_abi_version(void);
+/* Human-readable message of the last failure on the calling thread. */
+const char* gsfm_ra_last_error(void);
+/* Number of visible CUDA devices (0 if none / driver missing). */
+int gsfm_ra_device_count(void);
+void gsfm_ra_default_options(gsfm_ra_options* options);
+
+/* ---- one-shot solve: replaces ceres::Solve at rotation_estimator.cpp:76-77,
+ *      181-182, 304-305 for the angle-axis entry points.  omega_inout [N][3] is the
+ *      initial guess on entry and the estimate on exit (the reference updates the
+ *      caller's unordered_map<ViewId,Vector3d> in place).                      */
+int gsfm_ra_solve(const gsfm_ra_problem* problem, const gsfm_ra_options* options,
+                  double* omega_inout, gsfm_ra_summary* summary);
+
+/* ---- resident solver ---------------------------------------------------------*/
+int gsfm_ra_solver_create(const gsfm_ra_problem* problem, const gsfm_ra_options* options,
+                          gsfm_ra_solver** out);
+/* Row-sharded variant: this process owns the rows [row_begin,row_end) of the
+ * normal equations (all half-edges whose row view lies in the range).  peers are
+ * exchanged with gsfm_ra_solver_ipc_* below; world_size==1 is the plain solver. */
+int gsfm_ra_solver_create_sharded(const gsfm_ra_problem* problem, const gsfm_ra_options* options,
+                                  int32_t rank, int32_t world_size, gsfm_ra_solver** out);
+void gsfm_ra_solver_destroy(gsfm_ra_solver* solver);
+int gsfm_ra_solver_set_rotations(gsfm_ra_solver* solver, const double* omega /*[N][3] host*/);
+int gsfm_ra_solver_get_rotations(gsfm_ra_solver* solver, double* omega /*[N][3] host*/);
+/* Restart the trust region (radius, Jacobi scaling, iteration counter). */
+int gsfm_ra_solver_reset(gsfm_ra_solver* solver);
+/* Run at most num_iterations further trust-region iterations from the current
+ * state (stops earlier on convergence unless tolerances are <= 0).            */
+int gsfm_ra_solver_iterate(gsfm_ra_solver* solver, int32_t num_iterations, gsfm_ra_summary* summary);
+/* Peer-memory exchange for the sharded solver: each rank exports an opaque
+ * 64-byte handle; all ranks then import every rank's handle (world_size*64 B). */
+#define GSFM_RA_IPC_HANDLE_BYTES 128
+int gsfm_ra_solver_ipc_export(gsfm_ra_solver* solver, uint8_t* handle /*[GSFM_RA_IPC_HANDLE_BYTES]*/);
+int gsfm_ra_solver_ipc_import(gsfm_ra_solver* solver, const uint8_t* handles /*[world][GSFM_RA_IPC_HANDLE_BYTES]*/);
+/* Row range owned by this rank (load-balanced on half-edge count). */
+int gsfm_ra_solver_row_range(const gsfm_ra_solver* solver, uint32_t* row_begin, uint32_t* row_end);
+
+/* ---- kernel-level entry points (parity tests, profiling) ---------------------*/
+/* K1 per edge, at omega [N][3]: raw residual r [E][3], raw Jacobians
+ * d r/d omega_i, d r/d omega_j [E][9] row-major, and rho[E][3] = loss at |r|^2.
+ * Any output pointer may be NULL.  Replaces one AutoDiffCostFunction::Evaluate +
+ * LossFunction::Evaluate per edge (src/pairwise_rotation_error.cpp:75-85,
+ * bind_src/GlobalSfMpy.cpp:36-59).                                             */
+int gsfm_ra_eval_edges(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, const double* omega,
+                       double* r, double* jac_i, double* jac_j, double* rho, int32_t device);
+/* Whitening only: U [E][9] row-major upper-triangular (rotation_estimator.cpp:252-255). */
+int gsfm_ra_whiten(const gsfm_ra_problem* problem, double* U, int32_t device);
+/* K1 fused: robustified normal equations at omega. cost = sum 1/2 rho; gradient
+ * g [N][3] = J~^T r~; hdiag [N][9] diagonal blocks of J~^T J~ (row-major); the
+ * off-diagonal blocks in the solver's block-CSR order: rowptr [N+1], col [nnzb],
+ * val [nnzb][9] row-major (nnzb = 2E).  Any output may be NULL.  No Jacobi
+ * scaling, no damping.                                                          */
+int gsfm_ra_assemble(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, const double* omega,
+                     double* cost, double* gradient, double* hdiag,
+                     uint32_t* rowptr, uint32_t* col, double* val, int32_t device);
+/* K1c: cost only. */
+int gsfm_ra_cost(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, const double* omega,
+                 double* cost, int32_t device);
+/* K2 on the matrix assembled at omega: y = (H + diag(damping)) x, x,y,damping [N][3];
+ * damping may be NULL.                                                           */
+int gsfm_ra_spmv(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, const double* omega,
+                 const double* damping, const double* x, double* y, int32_t device);
+/* K2+K3: solve (H + diag(damping)) x = b with the production PCG; returns the
+ * iteration count in *iterations and the relative residual in *rel_residual.   */
+int gsfm_ra_pcg(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, const double* omega,
+                const double* damping, const double* b, double rtol, int32_t max_iterations,
+                double* x, int32_t* iterations, double* rel_residual, int32_t device);
+/* Loss table on the device: out [n][3] = (rho, rho', rho'') at s[i]. Replaces
+ * LossFunction::Evaluate of scripts/loss_functions.py.                          */
+int gsfm_ra_eval_loss(const gsfm_ra_loss* loss, const double* s, uint64_t n, double* out, int32_t device);
+
+/* ---- the step after the path: FilterViewPairsFromOrientation
+ *      (thirdparty/TheiaSfM/src/theia/sfm/filter_view_pairs_from_orientation.cc:55-118).
+ *      keep[k] = 1 iff |Log(R_ij^T R_j R_i^T)| <= max_degrees.                 */
+int gsfm_ra_filter_view_pairs(const gsfm_ra_problem* problem, const double* omega,
+                              double max_relative_rotation_difference_degrees,
+                              uint8_t* keep, double* angle_rad /*may be NULL*/, int32_t device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSFM_RA_H_ */
