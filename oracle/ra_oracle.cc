@@ -1,0 +1,910 @@
+/*
+ * ra_oracle.cc -- CPU ORACLE for the rotation-averaging hot path.  TEST INFRASTRUCTURE ONLY.
+ * See ra_oracle.h for who may load this library and for the parity status ("UNPINNED" for
+ * the converged solve: no Ceres binary can be built here, the trust-region loop restates
+ * Ceres Solver 1.14.0 from its published algorithm).
+ *
+ * Every function cites the reference lines it restates.  Paths are relative to the
+ * reference checkout; T/ = thirdparty/TheiaSfM/src/theia/.
+ *
+ * The residual/Jacobian evaluation deliberately mirrors HOW the reference computes them:
+ * forward-mode dual numbers ("jets", 6 infinitesimals = the two 3-vector parameter
+ * blocks) pushed through Rodrigues -> matrix products -> matrix->quaternion -> angle-axis,
+ * exactly the chain ceres::AutoDiffCostFunction<PairwiseRotationErrorAngleAxis,3,3,3>
+ * evaluates (src/pairwise_rotation_error.cpp:75-85).  The CUDA product uses closed-form
+ * SO(3) Jacobians instead; agreement of the two is what the parity tests check.
+ */
+#include "ra_oracle.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+/* ------------------------------------------------------------------------------------ */
+/* forward-mode dual numbers, the role ceres::Jet<double,6> plays in the reference       */
+/* ------------------------------------------------------------------------------------ */
+constexpr int kN = 6;
+struct Jet {
+  double a;
+  double v[kN];
+  Jet() : a(0) { for (int k = 0; k < kN; ++k) v[k] = 0; }
+  Jet(double x) : a(x) { for (int k = 0; k < kN; ++k) v[k] = 0; }  // NOLINT
+};
+inline Jet operator+(const Jet& x, const Jet& y) { Jet r; r.a = x.a + y.a; for (int k = 0; k < kN; ++k) r.v[k] = x.v[k] + y.v[k]; return r; }
+inline Jet operator-(const Jet& x, const Jet& y) { Jet r; r.a = x.a - y.a; for (int k = 0; k < kN; ++k) r.v[k] = x.v[k] - y.v[k]; return r; }
+inline Jet operator-(const Jet& x) { Jet r; r.a = -x.a; for (int k = 0; k < kN; ++k) r.v[k] = -x.v[k]; return r; }
+inline Jet operator*(const Jet& x, const Jet& y) { Jet r; r.a = x.a * y.a; for (int k = 0; k < kN; ++k) r.v[k] = x.a * y.v[k] + x.v[k] * y.a; return r; }
+inline Jet operator/(const Jet& x, const Jet& y) {
+  Jet r; const double inv = 1.0 / y.a; r.a = x.a * inv;
+  for (int k = 0; k < kN; ++k) r.v[k] = (x.v[k] - r.a * y.v[k]) * inv;
+  return r;
+}
+inline Jet sqrt(const Jet& x) { Jet r; r.a = std::sqrt(x.a); const double d = 1.0 / (2.0 * r.a); for (int k = 0; k < kN; ++k) r.v[k] = x.v[k] * d; return r; }
+inline Jet sin(const Jet& x) { Jet r; r.a = std::sin(x.a); const double c = std::cos(x.a); for (int k = 0; k < kN; ++k) r.v[k] = c * x.v[k]; return r; }
+inline Jet cos(const Jet& x) { Jet r; r.a = std::cos(x.a); const double s = -std::sin(x.a); for (int k = 0; k < kN; ++k) r.v[k] = s * x.v[k]; return r; }
+inline Jet atan2(const Jet& y, const Jet& x) {
+  Jet r; r.a = std::atan2(y.a, x.a); const double d = 1.0 / (x.a * x.a + y.a * y.a);
+  for (int k = 0; k < kN; ++k) r.v[k] = (x.a * y.v[k] - y.a * x.v[k]) * d;
+  return r;
+}
+inline double val(const Jet& x) { return x.a; }
+inline double val(double x) { return x; }
+using std::atan2;
+using std::cos;
+using std::sin;
+using std::sqrt;
+
+/* 3x3 stored M[r][c] */
+template <typename T>
+struct Mat3 { T m[3][3]; };
+
+/* ceres/rotation.h AngleAxisToRotationMatrix (Ceres 1.14):
+ * Rodrigues with a unit axis when theta^2 > DBL_EPSILON, first-order I+[w]x otherwise. */
+template <typename T>
+void AngleAxisToMatrix(const T* w, Mat3<T>* R) {
+  const T theta2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  if (val(theta2) > DBL_EPSILON) {
+    const T theta = sqrt(theta2);
+    const T wx = w[0] / theta, wy = w[1] / theta, wz = w[2] / theta;
+    const T c = cos(theta), s = sin(theta);
+    const T one_c = T(1.0) - c;
+    R->m[0][0] = c + wx * wx * one_c;
+    R->m[1][0] = wz * s + wx * wy * one_c;
+    R->m[2][0] = -wy * s + wx * wz * one_c;
+    R->m[0][1] = wx * wy * one_c - wz * s;
+    R->m[1][1] = c + wy * wy * one_c;
+    R->m[2][1] = wx * s + wy * wz * one_c;
+    R->m[0][2] = wy * s + wx * wz * one_c;
+    R->m[1][2] = -wx * s + wy * wz * one_c;
+    R->m[2][2] = c + wz * wz * one_c;
+  } else {
+    R->m[0][0] = T(1.0); R->m[1][0] = w[2];   R->m[2][0] = -w[1];
+    R->m[0][1] = -w[2];  R->m[1][1] = T(1.0); R->m[2][1] = w[0];
+    R->m[0][2] = w[1];   R->m[1][2] = -w[0];  R->m[2][2] = T(1.0);
+  }
+}
+
+/* ceres/rotation.h RotationMatrixToQuaternion + QuaternionToAngleAxis, which is what
+ * RotationMatrixToAngleAxis is in Ceres 1.14. */
+template <typename T>
+void MatrixToAngleAxis(const Mat3<T>& R, T* w) {
+  T q[4];
+  const T trace = R.m[0][0] + R.m[1][1] + R.m[2][2];
+  if (val(trace) >= 0.0) {
+    T t = sqrt(trace + T(1.0));
+    q[0] = T(0.5) * t;
+    t = T(0.5) / t;
+    q[1] = (R.m[2][1] - R.m[1][2]) * t;
+    q[2] = (R.m[0][2] - R.m[2][0]) * t;
+    q[3] = (R.m[1][0] - R.m[0][1]) * t;
+  } else {
+    int i = 0;
+    if (val(R.m[1][1]) > val(R.m[0][0])) i = 1;
+    if (val(R.m[2][2]) > val(R.m[i][i])) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    T t = sqrt(R.m[i][i] - R.m[j][j] - R.m[k][k] + T(1.0));
+    q[i + 1] = T(0.5) * t;
+    t = T(0.5) / t;
+    q[0] = (R.m[k][j] - R.m[j][k]) * t;
+    q[j + 1] = (R.m[j][i] + R.m[i][j]) * t;
+    q[k + 1] = (R.m[k][i] + R.m[i][k]) * t;
+  }
+  const T sin2 = q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  if (val(sin2) > 0.0) {
+    const T s = sqrt(sin2);
+    const T& c = q[0];
+    const T two_theta = T(2.0) * ((val(c) < 0.0) ? atan2(-s, -c) : atan2(s, c));
+    const T k = two_theta / s;
+    w[0] = q[1] * k; w[1] = q[2] * k; w[2] = q[3] * k;
+  } else {
+    const T k(2.0);
+    w[0] = q[1] * k; w[1] = q[2] * k; w[2] = q[3] * k;
+  }
+}
+
+/* The functor body of include/pairwise_rotation_error_quat.hpp:215-247 (U = Lt) and of
+ * T/sfm/global_pose_estimation/pairwise_rotation_error.h:66-95 (U = weight * I):
+ *   loop = R2 * R1^T ; err = loop * R12^T ; e = Log(err) ; residual = U * e            */
+template <typename T>
+void EdgeResidual(const T* w1, const T* w2, const double* w12, const double* U, T* res) {
+  Mat3<T> R1, R2;
+  Mat3<double> R12;
+  AngleAxisToMatrix(w1, &R1);
+  AngleAxisToMatrix(w2, &R2);
+  AngleAxisToMatrix(w12, &R12);
+  Mat3<T> loop, err;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      loop.m[r][c] = R2.m[r][0] * R1.m[c][0] + R2.m[r][1] * R1.m[c][1] + R2.m[r][2] * R1.m[c][2];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      err.m[r][c] = loop.m[r][0] * T(R12.m[c][0]) + loop.m[r][1] * T(R12.m[c][1]) + loop.m[r][2] * T(R12.m[c][2]);
+  T e[3];
+  MatrixToAngleAxis(err, e);
+  for (int r = 0; r < 3; ++r) res[r] = T(U[3 * r + 0]) * e[0] + T(U[3 * r + 1]) * e[1] + T(U[3 * r + 2]) * e[2];
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* MAGSAC constants, include/gamma_values.cpp:6-11, 384-389, 780-785 (numbers, not code)  */
+/* ------------------------------------------------------------------------------------ */
+struct MagsacConst { double nu, C, quantile, gamma_k; int table_size; };
+const MagsacConst kMagsac3 = {3.0, 4.029720004054876e-01, 3.368214175218727, 3.439485560754856e-03, 36843};
+const MagsacConst kMagsac4 = {4.0, 2.525252525252525e-01, 3.643721193503644e+00, 3.611260617758625e-03, 38683};
+const MagsacConst kMagsac9 = {9.0, 3.837828575290349e-03, 4.654674460524809e+00, 3.344206155099048e-02, 48553};
+constexpr double kGammaPrecision = 1000.0; /* precision_of_stored_gamma{3,4,9} */
+
+/* stored_gamma_values{nu}[i] = Gamma((nu-1)/2, i/1000) (upper incomplete); closed forms
+ * (verified against the table to <= 1e-14 abs in the golden test). */
+double GammaTable(int nu, int index) {
+  const double x = index / kGammaPrecision;
+  switch (nu) {
+    case 3: return std::exp(-x);
+    case 4: return 0.5 * std::sqrt(M_PI) * std::erfc(std::sqrt(x)) + std::sqrt(x) * std::exp(-x);
+    case 9: return std::exp(-x) * (((x + 3.0) * x + 6.0) * x + 6.0);
+  }
+  return NAN;
+}
+
+/* Python's round(): half to even (scripts/loss_functions.py:309 uses the builtin). */
+inline double RoundHalfEven(double x) { return std::nearbyint(x); /* default FE_TONEAREST */ }
+
+/* scripts/loss_functions.py:285-341 (nu=3), 344-400 (nu=4), 402-459 (nu=9). */
+void MagsacLoss(const MagsacConst& K, double sigma, bool inverse, double s_in, double* rho) {
+  const double squared_sigma = sigma * sigma;
+  const double squared_sigma_max_2 = 2.0 * squared_sigma;
+  const double cubed_sigma_max = squared_sigma * sigma;
+  const double dof_minus_one_per_two = (K.nu - 1.0) / 2.0;
+  const double C_times_two_ad_dof = K.C * std::pow(2.0, dof_minus_one_per_two);
+  const double one_over_sigma = C_times_two_ad_dof / sigma;
+  const double gamma_value = std::tgamma(dof_minus_one_per_two);
+  const double gamma_difference = gamma_value - K.gamma_k;
+  const double weight_zero = one_over_sigma * gamma_difference;
+
+  double squared_residual = s_in;
+  bool zero_derivative = false;
+  if (squared_residual > K.quantile * K.quantile * squared_sigma) {
+    squared_residual = K.quantile * K.quantile * squared_sigma;
+    zero_derivative = true;
+  }
+  double xr = RoundHalfEven(kGammaPrecision * squared_residual / squared_sigma_max_2);
+  if (K.table_size < xr) xr = K.table_size;
+  const int x = (int)xr;
+  double s = x * squared_sigma_max_2 / kGammaPrecision;
+  const double weight = one_over_sigma * (GammaTable((int)K.nu, x) - K.gamma_k);
+  const double expo = K.nu / 2 - 1.5;
+  /* Python: 0.0 ** 0.0 == 1.0, same as C pow */
+  const double weight_derivative =
+      -C_times_two_ad_dof * std::pow(s / squared_sigma_max_2, expo) * std::exp(-s / squared_sigma_max_2) / (2 * cubed_sigma_max);
+  if (s < 1e-7) s = 1e-7;
+  const double weight_second_derivative = 2.0 * C_times_two_ad_dof * std::pow(s / squared_sigma_max_2, expo) *
+                                          (1.0 / squared_sigma - (K.nu - 3) / s) * std::exp(-s / squared_sigma_max_2) /
+                                          (8 * cubed_sigma_max);
+  if (inverse) {
+    rho[0] = 1.0 / weight;
+    rho[1] = -1.0 / (weight * weight) * weight_derivative;
+    rho[2] = 2.0 / (weight * weight * weight) * weight_derivative * weight_derivative - weight_second_derivative / (weight * weight);
+    if (zero_derivative) { rho[1] = 0.00001; rho[2] = 0.0; }
+  } else {
+    rho[0] = weight_zero - weight;
+    rho[1] = -weight_derivative;
+    rho[2] = -weight_second_derivative;
+    if (rho[1] == 0) rho[1] = 0.00001;
+    if (zero_derivative) { rho[1] = 0.00001; rho[2] = 0.0; }
+  }
+}
+
+/* scripts/loss_functions.py, unscaled losses; lines per gsfm_ra_loss_kind in gsfm_ra.h. */
+void BaseLoss(const gsfm_ra_loss* L, double s, double* out) {
+  const double* p = L->p;
+  switch (L->kind) {
+    case GSFM_RA_LOSS_TRIVIAL: out[0] = s; out[1] = 1.0; out[2] = 0.0; return;                   /* :47-54 */
+    case GSFM_RA_LOSS_HUBER: {                                                                   /* :56-72 */
+      const double a = p[0], b = a * a;
+      if (s > b) { const double r = std::sqrt(s); out[0] = 2 * a * r - b; out[1] = std::max(a / r, DBL_MIN); out[2] = -out[1] / (2.0 * s); }
+      else { out[0] = s; out[1] = 1.0; out[2] = 0.0; }
+      return;
+    }
+    case GSFM_RA_LOSS_SOFTLONE: {                                                                /* :74-86 */
+      const double b = p[0] * p[0], c = 1.0 / b;
+      const double sum = 1.0 + s * c, tmp = std::sqrt(sum);
+      out[0] = 2.0 * b * (tmp - 1.0); out[1] = std::max(1.0 / tmp, DBL_MIN); out[2] = -(c * out[1]) / (2.0 * sum);
+      return;
+    }
+    case GSFM_RA_LOSS_CAUCHY: {                                                                  /* :88-99 */
+      const double b = p[0] * p[0], c = 1.0 / b;
+      const double sum = 1.0 + s * c, inv = 1.0 / sum;
+      out[0] = b * std::log(sum); out[1] = std::max(inv, DBL_MIN); out[2] = -c * (inv * inv);
+      return;
+    }
+    case GSFM_RA_LOSS_ARCTAN: {                                                                  /* :101-112 */
+      const double a = p[0], b = 1 / (a * a);
+      const double sum = 1 + s * s * b, inv = 1.0 / sum;
+      out[0] = a * std::atan2(s, a); out[1] = std::max(inv, DBL_MIN); out[2] = -2.0 * s * b * (inv * inv);
+      return;
+    }
+    case GSFM_RA_LOSS_TOLERANT: {                                                                /* :114-165 */
+      const double a = p[0], b = p[1], c = b * std::log(1 + std::exp(-a / b));
+      const double x = (s - a) / b;
+      if (x > 36.7) { out[0] = s - a - c; out[1] = 1.0; out[2] = 0.0; }
+      else { const double e_x = std::exp(x); out[0] = b * std::log(1.0 + e_x) - c; out[1] = std::max(e_x / (1.0 + e_x), DBL_MIN); out[2] = 0.5 / (b * (1.0 + std::cosh(x))); }
+      return;
+    }
+    case GSFM_RA_LOSS_TUKEY: {                                                                   /* :167-185 */
+      const double a2 = p[0] * p[0];
+      if (s <= a2) { const double v = 1.0 - s / a2, v2 = v * v; out[0] = a2 / 6.0 * (1.0 - v2 * v); out[1] = 0.5 * v2; out[2] = -1.0 / a2 * v; }
+      else { out[0] = a2 / 6.0; out[1] = 0.0; out[2] = 0.0; }
+      return;
+    }
+    case GSFM_RA_LOSS_LONEHALF: {                                                                /* :187-215 */
+      const double a = p[0], sa = std::sqrt(a);
+      out[0] = 2.0 * a * sa * std::pow(s, 0.25);
+      if (s < 0.01) s = 0.01;
+      out[1] = 0.5 * std::pow(a, -1.5) * std::pow(s, -0.75);
+      out[2] = -0.375 * a * sa * std::pow(s, -1.75);
+      return;
+    }
+    case GSFM_RA_LOSS_LTWO: {                                                                    /* :216-237 */
+      const double a2 = p[0] * p[0];
+      out[0] = s * s / (a2 * 2.0); out[1] = s / a2; out[2] = 1 / a2;
+      return;
+    }
+    case GSFM_RA_LOSS_GEMANMCCLURE: {                                                            /* :239-248 */
+      const double a2 = p[0] * p[0], sg = p[1];
+      out[0] = a2 * sg * s / (2.0 * (s + a2 * sg));
+      const double d = s / a2 + sg;
+      out[1] = (sg * sg) / (2.0 * d * d);
+      out[2] = -(sg * sg) / (a2 * d * d * d);
+      return;
+    }
+    case GSFM_RA_LOSS_MAGSAC3: MagsacLoss(kMagsac3, p[0], (L->flags & GSFM_RA_LOSS_FLAG_INVERSE) != 0, s, out); return;
+    case GSFM_RA_LOSS_MAGSAC4: MagsacLoss(kMagsac4, p[0], (L->flags & GSFM_RA_LOSS_FLAG_INVERSE) != 0, s, out); return;
+    case GSFM_RA_LOSS_MAGSAC9: MagsacLoss(kMagsac9, p[0], (L->flags & GSFM_RA_LOSS_FLAG_INVERSE) != 0, s, out); return;
+  }
+  out[0] = out[1] = out[2] = NAN;
+}
+
+/* src/GSfM_nonlinear_rotation_estimator.cpp:251-288: the per-edge weight matrix U.
+ * Eigen's 3x3 inverse() is the cofactor/determinant closed form; llt() reads the lower
+ * triangle; U = L^T.  edge_weight multiplies U when the caller provides it (types 5/6
+ * pass #matches/100; the reference passes nothing else).                               */
+void Whiten(int type, const double* c6, double w, double* U) {
+  for (int k = 0; k < 9; ++k) U[k] = 0.0;
+  const bool use_cov = (type == GSFM_RA_ANGLE_AXIS_COVARIANCE || type == GSFM_RA_ANGLE_AXIS_COV_INLIERS);
+  if (use_cov) {
+    const double a = c6[0] * 1e8, d = c6[1] * 1e8, f = c6[2] * 1e8, b = c6[3] * 1e8, c = c6[4] * 1e8, e = c6[5] * 1e8;
+    /* cov = [a b c; b d e; c e f]; inverse by cofactors */
+    const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+    const double c11 = a * f - c * c, c12 = b * c - a * e, c22 = a * d - b * b;
+    const double det = a * c00 + b * c01 + c * c02;
+    const double id = 1.0 / det;
+    const double P00 = c00 * id, P10 = c01 * id, P20 = c02 * id, P11 = c11 * id, P21 = c12 * id, P22 = c22 * id;
+    const double l00 = std::sqrt(P00), l10 = P10 / l00, l20 = P20 / l00;
+    const double l11 = std::sqrt(P11 - l10 * l10), l21 = (P21 - l20 * l10) / l11;
+    const double l22 = std::sqrt(P22 - l20 * l20 - l21 * l21);
+    U[0] = l00 * w; U[1] = l10 * w; U[2] = l20 * w;
+    U[4] = l11 * w; U[5] = l21 * w;
+    U[8] = l22 * w;
+    return;
+  }
+  double s = w;
+  if (type == GSFM_RA_ANGLE_AXIS_COVTRACE) s = w * std::sqrt(1.0 / ((c6[0] + c6[1] + c6[2]) * 1e8));
+  if (type == GSFM_RA_ANGLE_AXIS_COVNORM) {
+    double n2 = 0;
+    for (int k = 0; k < 3; ++k) n2 += (c6[k] * 1e8) * (c6[k] * 1e8);
+    for (int k = 3; k < 6; ++k) n2 += 2 * (c6[k] * 1e8) * (c6[k] * 1e8);
+    s = w * std::sqrt(1.0 / std::sqrt(n2));
+  }
+  U[0] = U[4] = U[8] = s;
+}
+
+bool TypeNeedsCov(int type) {
+  return type == GSFM_RA_ANGLE_AXIS_COVARIANCE || type == GSFM_RA_ANGLE_AXIS_COV_INLIERS ||
+         type == GSFM_RA_ANGLE_AXIS_COVTRACE || type == GSFM_RA_ANGLE_AXIS_COVNORM;
+}
+bool TypeSupported(int type) { return type >= GSFM_RA_ANGLE_AXIS_COVARIANCE && type <= GSFM_RA_ANGLE_AXIS_COVNORM; }
+
+void EdgeU(const gsfm_ra_problem* p, uint64_t k, double* U) {
+  Whiten(p->error_type, p->cov6 ? p->cov6 + 6 * k : nullptr, p->edge_weight ? p->edge_weight[k] : 1.0, U);
+}
+
+struct LossEval {
+  const gsfm_ra_loss* loss;
+  ra_oracle_loss_cb cb;
+  void* ctx;
+  void operator()(double s, double* rho) const {
+    if (cb) { cb(s, rho, ctx); return; }
+    ra_oracle_loss(loss, s, rho);
+  }
+};
+
+/* One robustified residual block: ceres ResidualBlock::Evaluate + Corrector
+ * (SURVEY Appendix B.2).  Jacobian is corrected first, from the uncorrected residual. */
+struct EdgeEval { double r[3], Ji[9], Jj[9], rho[3]; };
+
+void EvalEdgeRaw(const gsfm_ra_problem* p, uint64_t k, const double* omega, EdgeEval* out, bool jac) {
+  double U[9];
+  EdgeU(p, k, U);
+  const double* wi = omega + 3 * (size_t)p->edge_i[k];
+  const double* wj = omega + 3 * (size_t)p->edge_j[k];
+  if (jac) {
+    ra_oracle_edge(wi, wj, p->omega_ij + 3 * k, U, out->r, out->Ji, out->Jj);
+  } else {
+    EdgeResidual<double>(wi, wj, p->omega_ij + 3 * k, U, out->r);
+  }
+}
+
+void Robustify(EdgeEval* e, bool jac) {
+  const double s = e->r[0] * e->r[0] + e->r[1] * e->r[1] + e->r[2] * e->r[2];
+  const double sqrt_rho1 = std::sqrt(e->rho[1]);
+  double residual_scaling, alpha_sq_norm;
+  if (s == 0.0 || e->rho[2] <= 0.0) {
+    residual_scaling = sqrt_rho1;
+    alpha_sq_norm = 0.0;
+  } else {
+    const double D = 1.0 + 2.0 * s * e->rho[2] / e->rho[1];
+    const double alpha = 1.0 - ((D > 0.0) ? std::sqrt(D) : 0.0);
+    residual_scaling = sqrt_rho1 / (1 - alpha);
+    alpha_sq_norm = alpha / s;
+  }
+  if (jac) {
+    for (double* J : {e->Ji, e->Jj}) {
+      if (alpha_sq_norm == 0.0) {
+        for (int k = 0; k < 9; ++k) J[k] *= sqrt_rho1;
+      } else {
+        for (int c = 0; c < 3; ++c) {
+          const double rtj = e->r[0] * J[c] + e->r[1] * J[3 + c] + e->r[2] * J[6 + c];
+          for (int r = 0; r < 3; ++r) J[3 * r + c] = sqrt_rho1 * (J[3 * r + c] - alpha_sq_norm * e->r[r] * rtj);
+        }
+      }
+    }
+  }
+  for (int k = 0; k < 3; ++k) e->r[k] *= residual_scaling;
+}
+
+int Threads(int n) {
+#ifdef _OPENMP
+  if (n <= 0) n = omp_get_max_threads();
+  return std::max(1, n);
+#else
+  (void)n;
+  return 1;
+#endif
+}
+
+/* Full-storage off-diagonal block-CSR structure of J^T J: row a lists every neighbour b
+ * (sorted); slot_ij[k] / slot_ji[k] locate the two blocks of edge k.                    */
+struct Structure {
+  std::vector<uint32_t> rowptr, col;
+  std::vector<uint64_t> slot_ij, slot_ji;
+};
+void BuildStructure(const gsfm_ra_problem* p, Structure* S) {
+  const uint32_t N = p->num_views;
+  const uint64_t E = p->num_edges;
+  S->rowptr.assign(N + 1, 0);
+  for (uint64_t k = 0; k < E; ++k) { S->rowptr[p->edge_i[k] + 1]++; S->rowptr[p->edge_j[k] + 1]++; }
+  for (uint32_t a = 0; a < N; ++a) S->rowptr[a + 1] += S->rowptr[a];
+  std::vector<std::pair<uint32_t, uint64_t>> ent(2 * E); /* (col, edge*2+side) */
+  std::vector<uint32_t> fill(S->rowptr.begin(), S->rowptr.end() - 1);
+  for (uint64_t k = 0; k < E; ++k) {
+    ent[fill[p->edge_i[k]]++] = {p->edge_j[k], 2 * k};
+    ent[fill[p->edge_j[k]]++] = {p->edge_i[k], 2 * k + 1};
+  }
+  S->col.resize(2 * E);
+  S->slot_ij.resize(E);
+  S->slot_ji.resize(E);
+  for (uint32_t a = 0; a < N; ++a) {
+    std::sort(ent.begin() + S->rowptr[a], ent.begin() + S->rowptr[a + 1]);
+    for (uint32_t s = S->rowptr[a]; s < S->rowptr[a + 1]; ++s) {
+      S->col[s] = ent[s].first;
+      const uint64_t k = ent[s].second >> 1;
+      if (ent[s].second & 1) S->slot_ji[k] = s; else S->slot_ij[k] = s;
+    }
+  }
+}
+
+/* Everything one evaluation produces.  scale == nullptr: unscaled.                       */
+struct Linearization {
+  double cost = 0;
+  std::vector<double> g;     /* [3N]   J~^T r~                                          */
+  std::vector<double> hdiag; /* [9N]   diagonal blocks, row-major                        */
+  std::vector<double> hoff;  /* [9*2E] off-diagonal blocks in Structure order            */
+};
+
+int Linearize(const gsfm_ra_problem* p, const LossEval& loss, const double* omega, const Structure& S,
+              Linearization* L, bool jac, int num_threads) {
+  const uint32_t N = p->num_views;
+  const uint64_t E = p->num_edges;
+  if (jac) {
+    L->g.assign(3 * (size_t)N, 0.0);
+    L->hdiag.assign(9 * (size_t)N, 0.0);
+    L->hoff.assign(9 * 2 * (size_t)E, 0.0);
+  }
+  std::vector<EdgeEval> ev;
+  std::vector<double> half_rho(E);
+  if (jac) ev.resize(E);
+  const int nt = Threads(num_threads);
+  /* Pass 1 (threaded, as Ceres' ProgramEvaluator): residual + Jacobian per block. The loss
+   * callback (Python in the reference, under the GIL) is called serially in pass 2.     */
+  std::vector<EdgeEval> tmp_noj;
+  if (!jac) tmp_noj.resize(E);
+  EdgeEval* arr = jac ? ev.data() : tmp_noj.data();
+#pragma omp parallel for num_threads(nt) schedule(static)
+  for (int64_t k = 0; k < (int64_t)E; ++k) EvalEdgeRaw(p, k, omega, &arr[k], jac);
+  if (loss.cb) {
+    for (uint64_t k = 0; k < E; ++k) {
+      const double* r = arr[k].r;
+      loss(r[0] * r[0] + r[1] * r[1] + r[2] * r[2], arr[k].rho);
+    }
+  } else {
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int64_t k = 0; k < (int64_t)E; ++k) {
+      const double* r = arr[k].r;
+      loss(r[0] * r[0] + r[1] * r[1] + r[2] * r[2], arr[k].rho);
+    }
+  }
+#pragma omp parallel for num_threads(nt) schedule(static)
+  for (int64_t k = 0; k < (int64_t)E; ++k) {
+    half_rho[k] = 0.5 * arr[k].rho[0];
+    if (jac) Robustify(&arr[k], true);
+  }
+  /* cost: summed in edge order (Ceres sums per-thread scratch; order is not specified) */
+  double cost = 0;
+  for (uint64_t k = 0; k < E; ++k) cost += half_rho[k];
+  L->cost = cost;
+  if (!jac) return 0;
+  /* serial accumulation in edge order: deterministic */
+  for (uint64_t k = 0; k < E; ++k) {
+    const EdgeEval& e = ev[k];
+    const size_t i = p->edge_i[k], j = p->edge_j[k];
+    double* gi = &L->g[3 * i];
+    double* gj = &L->g[3 * j];
+    double* Hii = &L->hdiag[9 * i];
+    double* Hjj = &L->hdiag[9 * j];
+    double* Hij = &L->hoff[9 * S.slot_ij[k]];
+    double* Hji = &L->hoff[9 * S.slot_ji[k]];
+    for (int a = 0; a < 3; ++a) {
+      gi[a] += e.Ji[a] * e.r[0] + e.Ji[3 + a] * e.r[1] + e.Ji[6 + a] * e.r[2];
+      gj[a] += e.Jj[a] * e.r[0] + e.Jj[3 + a] * e.r[1] + e.Jj[6 + a] * e.r[2];
+      for (int b = 0; b < 3; ++b) {
+        Hii[3 * a + b] += e.Ji[a] * e.Ji[b] + e.Ji[3 + a] * e.Ji[3 + b] + e.Ji[6 + a] * e.Ji[6 + b];
+        Hjj[3 * a + b] += e.Jj[a] * e.Jj[b] + e.Jj[3 + a] * e.Jj[3 + b] + e.Jj[6 + a] * e.Jj[6 + b];
+        const double hij = e.Ji[a] * e.Jj[b] + e.Ji[3 + a] * e.Jj[3 + b] + e.Ji[6 + a] * e.Jj[6 + b];
+        Hij[3 * a + b] = hij;
+        Hji[3 * b + a] = hij;
+      }
+    }
+  }
+  return 0;
+}
+
+/* y = (H + diag(d)) x on the block structure. */
+void Apply(const Structure& S, const Linearization& L, const double* d, const double* x, double* y, uint32_t N, int nt) {
+#pragma omp parallel for num_threads(nt) schedule(dynamic, 64)
+  for (int64_t a = 0; a < (int64_t)N; ++a) {
+    const double* D = &L.hdiag[9 * a];
+    const double* xa = x + 3 * a;
+    double acc[3];
+    for (int r = 0; r < 3; ++r) acc[r] = D[3 * r] * xa[0] + D[3 * r + 1] * xa[1] + D[3 * r + 2] * xa[2] + (d ? d[3 * a + r] * xa[r] : 0.0);
+    for (uint32_t s = S.rowptr[a]; s < S.rowptr[a + 1]; ++s) {
+      const double* B = &L.hoff[9 * (size_t)s];
+      const double* xb = x + 3 * (size_t)S.col[s];
+      for (int r = 0; r < 3; ++r) acc[r] += B[3 * r] * xb[0] + B[3 * r + 1] * xb[1] + B[3 * r + 2] * xb[2];
+    }
+    y[3 * a] = acc[0]; y[3 * a + 1] = acc[1]; y[3 * a + 2] = acc[2];
+  }
+}
+
+bool Inv3Sym(const double* A, double* inv) {
+  const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+  const double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
+  if (!(std::fabs(det) > 0)) return false;
+  const double id = 1.0 / det;
+  inv[0] = c00 * id; inv[1] = (A[2] * A[7] - A[1] * A[8]) * id; inv[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+  inv[3] = c01 * id; inv[4] = (A[0] * A[8] - A[2] * A[6]) * id; inv[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+  inv[6] = c02 * id; inv[7] = (A[1] * A[6] - A[0] * A[7]) * id; inv[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+  return true;
+}
+
+/* Block-Jacobi preconditioned CG on (H + diag(d)) x = b. Returns iterations. */
+int Pcg(const Structure& S, const Linearization& L, const double* d, const double* b, uint32_t N, double rtol, int max_it,
+        double* x, double* rel_res, int nt) {
+  const size_t n = 3 * (size_t)N;
+  std::vector<double> Minv(9 * (size_t)N), r(b, b + n), z(n), pvec(n), Ap(n);
+  for (size_t a = 0; a < N; ++a) {
+    double A[9];
+    for (int k = 0; k < 9; ++k) A[k] = L.hdiag[9 * a + k];
+    if (d) { A[0] += d[3 * a]; A[4] += d[3 * a + 1]; A[8] += d[3 * a + 2]; }
+    if (!Inv3Sym(A, &Minv[9 * a])) { for (int k = 0; k < 9; ++k) Minv[9 * a + k] = (k % 4 == 0) ? 1.0 : 0.0; }
+  }
+  auto precond = [&](const double* in, double* out) {
+    for (size_t a = 0; a < N; ++a)
+      for (int q = 0; q < 3; ++q) out[3 * a + q] = Minv[9 * a + 3 * q] * in[3 * a] + Minv[9 * a + 3 * q + 1] * in[3 * a + 1] + Minv[9 * a + 3 * q + 2] * in[3 * a + 2];
+  };
+  auto dot = [&](const double* u, const double* v) { double s = 0; for (size_t k = 0; k < n; ++k) s += u[k] * v[k]; return s; };
+  std::fill(x, x + n, 0.0);
+  const double bnorm = std::sqrt(dot(b, b));
+  if (bnorm == 0) { *rel_res = 0; return 0; }
+  precond(r.data(), z.data());
+  pvec = z;
+  double rz = dot(r.data(), z.data());
+  int it = 0;
+  double rn = bnorm;
+  for (; it < max_it; ++it) {
+    if (rn <= rtol * bnorm) break;
+    Apply(S, L, d, pvec.data(), Ap.data(), N, nt);
+    const double pAp = dot(pvec.data(), Ap.data());
+    if (!(pAp > 0)) break;
+    const double alpha = rz / pAp;
+    for (size_t k = 0; k < n; ++k) { x[k] += alpha * pvec[k]; r[k] -= alpha * Ap[k]; }
+    rn = std::sqrt(dot(r.data(), r.data()));
+    precond(r.data(), z.data());
+    const double rz_new = dot(r.data(), z.data());
+    const double beta = rz_new / rz;
+    rz = rz_new;
+    for (size_t k = 0; k < n; ++k) pvec[k] = z[k] + beta * pvec[k];
+  }
+  *rel_res = rn / bnorm;
+  return it;
+}
+
+/* Dense LL^T solve of (H + diag(d)) x = b; stands in for SPARSE_NORMAL_CHOLESKY
+ * (src/GSfM_nonlinear_rotation_estimator.cpp:300): both are exact factorisations.      */
+bool DenseSolve(const Structure& S, const Linearization& L, const double* d, const double* b, uint32_t N, double* x, int nt) {
+  const size_t n = 3 * (size_t)N;
+  std::vector<double> A(n * n, 0.0);
+  for (size_t a = 0; a < N; ++a) {
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) A[(3 * a + r) * n + 3 * a + c] = L.hdiag[9 * a + 3 * r + c];
+    for (int r = 0; r < 3; ++r) A[(3 * a + r) * n + 3 * a + r] += d ? d[3 * a + r] : 0.0;
+    for (uint32_t s = S.rowptr[a]; s < S.rowptr[a + 1]; ++s) {
+      const size_t bcol = S.col[s];
+      if (bcol > a) continue; /* lower triangle only */
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) A[(3 * a + r) * n + 3 * bcol + c] = L.hoff[9 * (size_t)s + 3 * r + c];
+    }
+  }
+  /* row-oriented Cholesky, contiguous dot products */
+  for (size_t j = 0; j < n; ++j) {
+    double* Lj = &A[j * n];
+    double djj = Lj[j];
+    for (size_t k = 0; k < j; ++k) djj -= Lj[k] * Lj[k];
+    if (!(djj > 0)) return false;
+    const double ljj = std::sqrt(djj);
+    Lj[j] = ljj;
+    const double inv = 1.0 / ljj;
+#pragma omp parallel for num_threads(nt) schedule(static) if (n - j > 256)
+    for (int64_t i = (int64_t)j + 1; i < (int64_t)n; ++i) {
+      double* Li = &A[i * n];
+      double v = Li[j];
+      for (size_t k = 0; k < j; ++k) v -= Li[k] * Lj[k];
+      Li[j] = v * inv;
+    }
+  }
+  std::vector<double> y(n);
+  for (size_t i = 0; i < n; ++i) {
+    double v = b[i];
+    for (size_t k = 0; k < i; ++k) v -= A[i * n + k] * y[k];
+    y[i] = v / A[i * n + i];
+  }
+  for (size_t ii = n; ii-- > 0;) {
+    double v = y[ii];
+    for (size_t k = ii + 1; k < n; ++k) v -= A[k * n + ii] * x[k];
+    x[ii] = v / A[ii * n + ii];
+  }
+  return true;
+}
+
+double NowMs() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int CheckProblem(const gsfm_ra_problem* p) {
+  if (!p || !p->edge_i || !p->edge_j || !p->omega_ij) return GSFM_RA_ERR_INVALID;
+  if (!TypeSupported(p->error_type)) return GSFM_RA_ERR_UNSUPPORTED;
+  if (TypeNeedsCov(p->error_type) && !p->cov6) return GSFM_RA_ERR_INVALID;
+  for (uint64_t k = 0; k < p->num_edges; ++k)
+    if (p->edge_i[k] >= p->num_views || p->edge_j[k] >= p->num_views || p->edge_i[k] == p->edge_j[k]) return GSFM_RA_ERR_INVALID;
+  return 0;
+}
+
+}  // namespace
+
+/* ------------------------------------------------------------------------------------ */
+extern "C" {
+
+void ra_oracle_loss(const gsfm_ra_loss* loss, double s, double* rho3) {
+  BaseLoss(loss, s, rho3);
+  /* ScaledLoss, scripts/loss_functions.py:267-281 */
+  if (loss->scale != 1.0 && loss->scale != 0.0) { rho3[0] *= loss->scale; rho3[1] *= loss->scale; rho3[2] *= loss->scale; }
+}
+
+double ra_oracle_gamma_table(int nu, int index) { return GammaTable(nu, index); }
+
+void ra_oracle_angle_axis_to_matrix(const double* w, double* R) {
+  Mat3<double> M;
+  AngleAxisToMatrix(w, &M);
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[3 * r + c] = M.m[r][c];
+}
+void ra_oracle_matrix_to_angle_axis(const double* R, double* w) {
+  Mat3<double> M;
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) M.m[r][c] = R[3 * r + c];
+  MatrixToAngleAxis(M, w);
+}
+
+void ra_oracle_whiten(int error_type, const double* cov6, double edge_weight, double* U) { Whiten(error_type, cov6, edge_weight, U); }
+
+void ra_oracle_edge(const double* wi, const double* wj, const double* wij, const double* U, double* r, double* Ji, double* Jj) {
+  Jet a[3], b[3], res[3];
+  for (int k = 0; k < 3; ++k) { a[k] = Jet(wi[k]); a[k].v[k] = 1.0; b[k] = Jet(wj[k]); b[k].v[3 + k] = 1.0; }
+  EdgeResidual<Jet>(a, b, wij, U, res);
+  for (int q = 0; q < 3; ++q) {
+    if (r) r[q] = res[q].a;
+    for (int c = 0; c < 3; ++c) {
+      if (Ji) Ji[3 * q + c] = res[q].v[c];
+      if (Jj) Jj[3 * q + c] = res[q].v[3 + c];
+    }
+  }
+}
+
+int ra_oracle_eval_edges(const gsfm_ra_problem* p, const gsfm_ra_loss* loss, const double* omega, double* r, double* Ji,
+                         double* Jj, double* rho, int num_threads) {
+  if (int rc = CheckProblem(p)) return rc;
+  const int nt = Threads(num_threads);
+#pragma omp parallel for num_threads(nt) schedule(static)
+  for (int64_t k = 0; k < (int64_t)p->num_edges; ++k) {
+    EdgeEval e;
+    EvalEdgeRaw(p, k, omega, &e, true);
+    if (r) for (int q = 0; q < 3; ++q) r[3 * k + q] = e.r[q];
+    if (Ji) for (int q = 0; q < 9; ++q) Ji[9 * k + q] = e.Ji[q];
+    if (Jj) for (int q = 0; q < 9; ++q) Jj[9 * k + q] = e.Jj[q];
+    if (rho && loss) ra_oracle_loss(loss, e.r[0] * e.r[0] + e.r[1] * e.r[1] + e.r[2] * e.r[2], rho + 3 * k);
+  }
+  return 0;
+}
+
+int ra_oracle_assemble(const gsfm_ra_problem* p, const gsfm_ra_loss* loss, const double* omega, double* cost, double* gradient,
+                       double* hdiag, uint32_t* rowptr, uint32_t* col, double* val, int num_threads) {
+  if (int rc = CheckProblem(p)) return rc;
+  Structure S;
+  BuildStructure(p, &S);
+  Linearization L;
+  LossEval le{loss, nullptr, nullptr};
+  Linearize(p, le, omega, S, &L, true, num_threads);
+  if (cost) *cost = L.cost;
+  if (gradient) std::memcpy(gradient, L.g.data(), L.g.size() * sizeof(double));
+  if (hdiag) std::memcpy(hdiag, L.hdiag.data(), L.hdiag.size() * sizeof(double));
+  if (rowptr) std::memcpy(rowptr, S.rowptr.data(), S.rowptr.size() * sizeof(uint32_t));
+  if (col) std::memcpy(col, S.col.data(), S.col.size() * sizeof(uint32_t));
+  if (val) std::memcpy(val, L.hoff.data(), L.hoff.size() * sizeof(double));
+  return 0;
+}
+
+int ra_oracle_cost(const gsfm_ra_problem* p, const gsfm_ra_loss* loss, const double* omega, double* cost, int num_threads) {
+  if (int rc = CheckProblem(p)) return rc;
+  Structure S; /* unused for cost-only */
+  Linearization L;
+  LossEval le{loss, nullptr, nullptr};
+  Linearize(p, le, omega, S, &L, false, num_threads);
+  *cost = L.cost;
+  return 0;
+}
+
+/* Ceres 1.14 TrustRegionMinimizer + LevenbergMarquardtStrategy, with
+ * the options of src/GSfM_nonlinear_rotation_estimator.cpp:299-303.  Order of the checks in
+ * one iteration, as in trust_region_minimizer.cc of 1.14:
+ *   compute step (invalid if model_cost_change <= 0) -> candidate cost -> parameter
+ *   tolerance -> function tolerance (both BEFORE the step is accepted: on those two exits
+ *   the parameters stay at the last accepted point) -> accept / reject -> (loop head)
+ *   max iterations, gradient tolerance (after successful steps), min radius.          */
+int ra_oracle_solve(const gsfm_ra_problem* p, const gsfm_ra_options* o, double* omega, gsfm_ra_summary* sum,
+                    ra_oracle_loss_cb loss_cb, void* cb_ctx) {
+  if (int rc = CheckProblem(p)) return rc;
+  if (!o || !omega) return GSFM_RA_ERR_INVALID;
+  const double t0 = NowMs();
+  const uint32_t N = p->num_views;
+  const size_t n = 3 * (size_t)N;
+  const int nt = Threads(o->num_threads);
+  Structure S;
+  BuildStructure(p, &S);
+  LossEval le{&o->loss, loss_cb, cb_ctx};
+  Linearization L, Ltrial;
+  std::vector<double> x(omega, omega + n), cand(n), scale(n, 1.0), damp(n), delta(n), negg(n), Hd(n), diag(n);
+  gsfm_ra_summary local;
+  std::memset(&local, 0, sizeof(local));
+  if (sum) { local.trace = sum->trace; local.trace_capacity = sum->trace_capacity; }
+  auto push = [&](const gsfm_ra_iteration& it) {
+    if (local.trace && local.trace_size < local.trace_capacity) local.trace[local.trace_size++] = it;
+  };
+  double t_asm = 0, t_lin = 0, t_cost = 0;
+
+  double t = NowMs();
+  Linearize(p, le, x.data(), S, &L, true, nt);
+  t_asm += NowMs() - t;
+  double x_cost = L.cost;
+  local.initial_cost = x_cost;
+  if (!std::isfinite(x_cost)) { if (sum) *sum = local; return GSFM_RA_ERR_NUMERIC; }
+  auto diag_of = [&](const Linearization& Lz, std::vector<double>* out) {
+    for (size_t a = 0; a < N; ++a) for (int q = 0; q < 3; ++q) (*out)[3 * a + q] = Lz.hdiag[9 * a + 4 * q];
+  };
+  /* Jacobi scaling estimated once, at the initial point */
+  if (o->jacobi_scaling) {
+    diag_of(L, &diag);
+    for (size_t c = 0; c < n; ++c) scale[c] = 1.0 / (1.0 + std::sqrt(diag[c]));
+  }
+  auto gmax = [&](const Linearization& Lz) { double m = 0; for (double v : Lz.g) m = std::max(m, std::fabs(v)); return m; };
+  auto norm = [&](const std::vector<double>& v) { double s = 0; for (double u : v) s += u * u; return std::sqrt(s); };
+  double x_norm = norm(x);
+  double radius = o->initial_trust_region_radius;
+  double decrease_factor = 2.0;
+  bool reuse_diagonal = false;
+  int invalid_steps = 0;
+  gsfm_ra_iteration it0;
+  std::memset(&it0, 0, sizeof(it0));
+  it0.cost = x_cost; it0.gradient_max_norm = gmax(L); it0.trust_region_radius = radius;
+  push(it0);
+  int iteration = 0;
+  int term = GSFM_RA_TERM_NONE;
+  bool last_successful = false;
+  double last_gmax = it0.gradient_max_norm;
+  /* gradient tolerance can already hold at the start */
+  if (last_gmax <= o->gradient_tolerance) term = GSFM_RA_TERM_GRADIENT_TOLERANCE;
+  while (term == GSFM_RA_TERM_NONE) {
+    /* loop-head checks (FinalizeIterationAndCheckIfMinimizerCanContinue) */
+    if (iteration >= o->max_num_iterations) { term = GSFM_RA_TERM_MAX_ITERATIONS; break; }
+    if (last_successful && last_gmax <= o->gradient_tolerance) { term = GSFM_RA_TERM_GRADIENT_TOLERANCE; break; }
+    if (radius <= o->min_trust_region_radius) { term = GSFM_RA_TERM_MIN_RADIUS; break; }
+    ++iteration;
+    gsfm_ra_iteration it;
+    std::memset(&it, 0, sizeof(it));
+    it.iteration = iteration;
+    /* LM diagonal in scaled coordinates: clamp(colnorm^2(J s), min, max) / radius.
+     * Expressed on the unscaled system: damping_c = that / scale_c^2.                  */
+    if (!reuse_diagonal) {
+      diag_of(L, &diag);
+      for (size_t c = 0; c < n; ++c) diag[c] = std::min(std::max(diag[c] * scale[c] * scale[c], o->min_lm_diagonal), o->max_lm_diagonal);
+    }
+    for (size_t c = 0; c < n; ++c) damp[c] = diag[c] / radius / (scale[c] * scale[c]);
+    for (size_t c = 0; c < n; ++c) negg[c] = -L.g[c];
+    t = NowMs();
+    bool solved = true;
+    if (o->linear_solver == GSFM_RA_SOLVER_DENSE_CHOLESKY) {
+      solved = DenseSolve(S, L, damp.data(), negg.data(), N, delta.data(), nt);
+      it.linear_iterations = 1;
+    } else {
+      it.linear_iterations = Pcg(S, L, damp.data(), negg.data(), N, o->pcg_rtol, o->pcg_max_iterations, delta.data(), &it.linear_residual, nt);
+      local.total_linear_iterations += it.linear_iterations;
+    }
+    t_lin += NowMs() - t;
+    reuse_diagonal = true;
+    bool valid = solved;
+    for (size_t c = 0; c < n && valid; ++c) valid = std::isfinite(delta[c]);
+    double model_change = 0;
+    if (valid) {
+      /* model_cost_change = -(J d)^T (r + J d / 2) = -d^T g - d^T H d / 2 */
+      Apply(S, L, nullptr, delta.data(), Hd.data(), N, nt);
+      double dg = 0, dHd = 0;
+      for (size_t c = 0; c < n; ++c) { dg += delta[c] * L.g[c]; dHd += delta[c] * Hd[c]; }
+      model_change = -dg - 0.5 * dHd;
+      if (!(model_change > 0.0)) valid = false;
+    }
+    it.model_cost_change = model_change;
+    it.step_is_valid = valid;
+    if (!valid) {
+      if (++invalid_steps >= 5) { term = GSFM_RA_TERM_INVALID_STEPS; it.cost = x_cost; it.trust_region_radius = radius; push(it); break; }
+      radius *= 0.5; /* StepIsInvalid */
+      reuse_diagonal = true;
+      it.cost = x_cost; it.trust_region_radius = radius; it.gradient_max_norm = last_gmax;
+      last_successful = false;
+      local.num_unsuccessful_steps++;
+      push(it);
+      continue;
+    }
+    invalid_steps = 0;
+    for (size_t c = 0; c < n; ++c) cand[c] = x[c] + delta[c];
+    t = NowMs();
+    Linearize(p, le, cand.data(), S, &Ltrial, false, nt);
+    t_cost += NowMs() - t;
+    double cand_cost = Ltrial.cost;
+    if (!std::isfinite(cand_cost)) cand_cost = DBL_MAX;
+    it.candidate_cost = cand_cost;
+    it.step_norm = norm(delta);
+    it.cost_change = x_cost - cand_cost;
+    it.relative_decrease = it.cost_change / model_change;
+    it.gradient_max_norm = last_gmax;
+    if (it.step_norm <= o->parameter_tolerance * (x_norm + o->parameter_tolerance)) {
+      term = GSFM_RA_TERM_PARAMETER_TOLERANCE; it.cost = x_cost; it.trust_region_radius = radius; push(it); break;
+    }
+    if (std::fabs(it.cost_change) <= o->function_tolerance * x_cost) {
+      term = GSFM_RA_TERM_FUNCTION_TOLERANCE; it.cost = x_cost; it.trust_region_radius = radius; push(it); break;
+    }
+    if (it.relative_decrease > o->min_relative_decrease) {
+      x = cand;
+      x_norm = norm(x);
+      t = NowMs();
+      Linearize(p, le, x.data(), S, &L, true, nt);
+      t_asm += NowMs() - t;
+      x_cost = L.cost;
+      last_gmax = gmax(L);
+      it.gradient_max_norm = last_gmax;
+      it.step_is_successful = 1;
+      const double q = it.relative_decrease;
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * q - 1.0, 3));
+      radius = std::min(o->max_trust_region_radius, radius);
+      decrease_factor = 2.0;
+      reuse_diagonal = false;
+      last_successful = true;
+      local.num_successful_steps++;
+      it.cost = x_cost;
+    } else {
+      radius = radius / decrease_factor;
+      decrease_factor *= 2.0;
+      reuse_diagonal = true;
+      last_successful = false;
+      local.num_unsuccessful_steps++;
+      it.cost = cand_cost; /* Ceres reports the candidate cost on a rejected step */
+    }
+    it.trust_region_radius = radius;
+    push(it);
+    if (o->verbose)
+      std::fprintf(stderr, "[oracle] it %3d cost %.12e dcost %+.3e |g| %.3e |step| %.3e q %.3e radius %.3e lin_it %d %s\n", iteration, x_cost,
+                   it.cost_change, it.gradient_max_norm, it.step_norm, it.relative_decrease, radius, it.linear_iterations,
+                   it.step_is_successful ? "ok" : "rejected");
+  }
+  std::memcpy(omega, x.data(), n * sizeof(double));
+  local.termination = term;
+  local.num_iterations = iteration;
+  local.final_cost = x_cost;
+  local.ms_assemble = t_asm; local.ms_linear = t_lin; local.ms_cost = t_cost;
+  local.ms_total = NowMs() - t0;
+  if (sum) *sum = local;
+  return 0;
+}
+
+/* T/sfm/filter_view_pairs_from_orientation.cc:55-118: an edge is kept iff the angle of
+ * R_ij^T * (R_j R_i^T) is <= max_degrees.                                               */
+int ra_oracle_filter_view_pairs(const gsfm_ra_problem* p, const double* omega, double max_degrees, uint8_t* keep, double* angle_rad) {
+  if (!p || !p->edge_i || !p->edge_j || !p->omega_ij) return GSFM_RA_ERR_INVALID;
+  const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  const double thr = max_degrees * M_PI / 180.0;
+  for (uint64_t k = 0; k < p->num_edges; ++k) {
+    double e[3];
+    EdgeResidual<double>(omega + 3 * (size_t)p->edge_i[k], omega + 3 * (size_t)p->edge_j[k], p->omega_ij + 3 * k, I, e);
+    const double a = std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+    if (angle_rad) angle_rad[k] = a;
+    if (keep) keep[k] = (a * a <= thr * thr) ? 1 : 0;
+  }
+  return 0;
+}
+
+} /* extern "C" */
