@@ -187,6 +187,9 @@ def declare(lib, oracle=False):
     lib.gsfm_ra_solver_ipc_export.argtypes = [vp, _u8p]
     lib.gsfm_ra_solver_ipc_import.argtypes = [vp, _u8p]
     lib.gsfm_ra_solver_row_range.argtypes = [vp, _u32p, _u32p]
+    lib.gsfm_ra_solver_cuda_stream.argtypes = [vp]
+    lib.gsfm_ra_solver_cuda_stream.restype = C.c_void_p
+    lib.gsfm_ra_solver_time_kernels.argtypes = [vp, C.c_int32, _dp]
     lib.gsfm_ra_eval_edges.argtypes = [pp, lp, _dp, _dp, _dp, _dp, _dp, C.c_int32]
     lib.gsfm_ra_whiten.argtypes = [pp, _dp, C.c_int32]
     lib.gsfm_ra_assemble.argtypes = [pp, lp, _dp, _dp, _dp, _dp, _u32p, _u32p, _dp, C.c_int32]
@@ -204,7 +207,7 @@ EXPORTED_SYMBOLS = [
     "gsfm_ra_solve", "gsfm_ra_solver_create", "gsfm_ra_solver_create_sharded", "gsfm_ra_solver_destroy",
     "gsfm_ra_solver_set_rotations", "gsfm_ra_solver_get_rotations", "gsfm_ra_solver_reset",
     "gsfm_ra_solver_iterate", "gsfm_ra_solver_ipc_export", "gsfm_ra_solver_ipc_import",
-    "gsfm_ra_solver_row_range", "gsfm_ra_eval_edges", "gsfm_ra_whiten", "gsfm_ra_assemble", "gsfm_ra_cost",
+    "gsfm_ra_solver_row_range", "gsfm_ra_solver_cuda_stream", "gsfm_ra_solver_time_kernels", "gsfm_ra_eval_edges", "gsfm_ra_whiten", "gsfm_ra_assemble", "gsfm_ra_cost",
     "gsfm_ra_spmv", "gsfm_ra_pcg", "gsfm_ra_eval_loss", "gsfm_ra_filter_view_pairs",
 ]
 

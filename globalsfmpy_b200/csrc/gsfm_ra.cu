@@ -1,0 +1,1444 @@
+// gsfm_ra.cu -- B200 (sm_100a) robust rotation averaging behind the C ABI of include/gsfm_ra.h.
+//
+// Replaces the Ceres solve inside GSfMNonlinearRotationEstimator
+// (reference src/GSfM_nonlinear_rotation_estimator.cpp:24-80, 201-309): per-edge residuals,
+// SO(3) Jacobians, covariance whitening and robust reweighting (K1), the block-3x3 normal
+// equations, and a block-Jacobi PCG whose SpMV is K2 -- all resident in HBM, fp64 throughout.
+//
+// Data layout.  The view graph is stored as HALF-EDGES: every edge (i,j)
+// appears once in row i and once in row j, sorted by (row, col); a row's half-edges are
+// contiguous, so per-view sums (diagonal block, gradient) are segmented reductions over a
+// contiguous range and need no atomics.  Rows are cut into TASKS of <= kTaskLen half-edges; one
+// warp owns one task, lanes stride the task with fully coalesced planar (SoA) loads.  The
+// normal-equation matrix lives in the LEFT TANGENT frame (see so3_device.cuh): H = D^T Ht D with
+// D = blockdiag(Jl(omega_i)), so the per-edge kernel never touches the per-view Jl factors; the
+// Euclidean (angle-axis) Levenberg-Marquardt of Ceres is reproduced exactly by transforming the
+// LM diagonal per view.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/gsfm_ra.h"
+#include "so3_device.cuh"
+
+using namespace gsfm;
+
+namespace {
+
+constexpr int kTaskLen = 128;      // half-edges per warp task
+constexpr int kBlock = 256;        // threads per block of every kernel
+constexpr int kWarpsPerBlock = kBlock / 32;
+constexpr uint32_t kSideBit = 0x80000000u;  // he_col bit 31: the ROW view is the j (second) view of the edge
+constexpr int kPartStride = 10;    // per-task partial: diag(6) grad(3) cost(1)
+
+thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t err__ = (expr);                                                               \
+    if (err__ != cudaSuccess) {                                                               \
+      set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+      return GSFM_RA_ERR_CUDA;                                                                \
+    }                                                                                         \
+  } while (0)
+
+#define RA_TRY(expr)            \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Scalars living on the device for the whole solve (one cache line group).
+struct DevScalars {
+  // evaluation
+  double cost;          // sum 1/2 rho at the last evaluated point
+  double gmax;          // max |g| (Euclidean gradient) at the last evaluated point
+  double xnorm2;        // |omega|^2 of the last evaluated point
+  // PCG
+  double rz, pAp, alpha, beta, rr, bb;
+  int pcg_iter, pcg_done, pcg_breakdown, pad0;
+  // step
+  double dg, dHd, step2;  // delta.g, delta.H.delta, |delta|^2 (Euclidean step)
+  int bad;                // non-finite detected
+  int pad1;
+};
+
+// Deterministic grid-wide sum of NV values: block tree -> per-block slot -> the LAST block to
+// arrive adds the slots in index order.  Returns true in the last block (all threads), with the
+// totals in `tot` (valid in thread 0 only).
+template <int NV>
+__device__ bool grid_sum(double (&v)[NV], double* slots, unsigned* counter, double (&tot)[NV]) {
+  __shared__ double sm[NV][kWarpsPerBlock];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double s = warp_sum(v[k]);
+    if (lane == 0) sm[k][warp] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double s = 0.0;
+      for (int w = 0; w < kWarpsPerBlock; ++w) s += sm[k][w];
+      slots[(size_t)blockIdx.x * NV + k] = s;
+    }
+    __threadfence();
+    const unsigned ticket = atomicAdd(counter, 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  if (threadIdx.x == 0) {
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) tot[k] = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) tot[k] += ((volatile double*)slots)[(size_t)b * NV + k];
+    *counter = 0u;
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// K0 setup: per half-edge, gather the edge's measurement and weight, store planar.
+//   qij[4][H] unit quaternion of omega_ij, U[6][H] whitening (rotation_estimator.cpp:251-288)
+// ------------------------------------------------------------------------------------------
+__global__ void k_setup_halfedges(uint64_t H, const uint32_t* __restrict__ he_edge, const double* __restrict__ omega_ij,
+                                  const double* __restrict__ cov6, const double* __restrict__ weight, int error_type,
+                                  double* __restrict__ qij, double* __restrict__ U) {
+  const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  const uint64_t k = he_edge[h];
+  const Q4 q = aa_to_quat(omega_ij[3 * k], omega_ij[3 * k + 1], omega_ij[3 * k + 2]);
+  qij[h] = q.w; qij[H + h] = q.x; qij[2 * H + h] = q.y; qij[3 * H + h] = q.z;
+  double c6[6] = {0, 0, 0, 0, 0, 0};
+  if (cov6) for (int t = 0; t < 6; ++t) c6[t] = cov6[6 * k + t];
+  double u[6];
+  whiten(error_type, c6, weight ? weight[k] : 1.0, u);
+#pragma unroll
+  for (int t = 0; t < 6; ++t) U[(uint64_t)t * H + h] = u[t];
+}
+
+// Per view: quaternion + left Jacobian of the current angle-axis estimate; also |omega|^2.
+__global__ void k_node_prep(uint32_t N, const double* __restrict__ omega, double* __restrict__ node_q, double* __restrict__ node_JL,
+                            double* slots, unsigned* counter, DevScalars* sc) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[1] = {0.0};
+  if (i < N) {
+    const double wx = omega[3 * i], wy = omega[3 * i + 1], wz = omega[3 * i + 2];
+    const Q4 q = aa_to_quat(wx, wy, wz);
+    reinterpret_cast<double4*>(node_q)[i] = make_double4(q.w, q.x, q.y, q.z);
+    double J[9];
+    so3_left_jacobian(wx, wy, wz, J);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) node_JL[9 * (size_t)i + t] = J[t];
+    v[0] = wx * wx + wy * wy + wz * wz;
+  }
+  double tot[1];
+  if (grid_sum<1>(v, slots, counter, tot) && threadIdx.x == 0) sc->xnorm2 = tot[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: fused residual + SO(3) Jacobian + whitening + robust loss + normal-equation assembly.
+// One warp per task (a run of <= kTaskLen half-edges of ONE row view).  Each lane evaluates one
+// half-edge per iteration: loads are planar and coalesced (qij 4x8 B, U 6x8 B, col 4 B), the row
+// view's quaternion is a warp broadcast, the column view's quaternion is one aligned 32 B gather
+// served by L2.  Writes the off-diagonal tangent block of the half-edge (planar, coalesced) and,
+// per task, the warp-reduced diagonal block / gradient / cost partial.
+// kWriteBlocks=false is K1c: cost only (trial point).
+// ------------------------------------------------------------------------------------------
+template <bool kWriteBlocks>
+__global__ void __launch_bounds__(kBlock)
+k_edges(uint32_t num_tasks, uint64_t H, const uint32_t* __restrict__ task_row, const uint32_t* __restrict__ task_begin,
+        const uint32_t* __restrict__ task_len, const uint32_t* __restrict__ he_col, const double* __restrict__ qij,
+        const double* __restrict__ U, const double* __restrict__ node_q, DevLoss loss, double* __restrict__ val,
+        double* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t t = warp_global; t < num_tasks; t += num_warps) {
+    const uint32_t row = task_row[t];
+    const uint64_t begin = task_begin[t];
+    const uint32_t len = task_len[t];
+    const double4 qa4 = reinterpret_cast<const double4*>(node_q)[row];
+    const Q4 qa{qa4.x, qa4.y, qa4.z, qa4.w};
+    double acc[kPartStride];
+#pragma unroll
+    for (int k = 0; k < kPartStride; ++k) acc[k] = 0.0;
+    for (uint32_t off = lane; off < len; off += 32) {
+      const uint64_t h = begin + off;
+      const uint32_t cf = he_col[h];
+      const uint32_t col = cf & ~kSideBit;
+      const bool row_is_j = (cf & kSideBit) != 0;
+      const double4 qb4 = reinterpret_cast<const double4*>(node_q)[col];
+      const Q4 qb{qb4.x, qb4.y, qb4.z, qb4.w};
+      const Q4 qm{qij[h], qij[H + h], qij[2 * H + h], qij[3 * H + h]};
+      double u[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) u[k] = U[(uint64_t)k * H + h];
+      EdgeTerms et;
+      if (row_is_j) edge_terms<kWriteBlocks>(qb, qa, qm, u, loss, et);
+      else edge_terms<kWriteBlocks>(qa, qb, qm, u, loss, et);
+      if (!row_is_j) acc[9] += 0.5 * et.rho[0];  // each edge's cost is counted once, in its i row
+      if (kWriteBlocks) {
+        const double* W = et.W;
+        const double* Q = et.Q;
+        double B[9];
+        if (row_is_j) {
+          // row j: diag += W, grad += v, block(j,i) = -W Q
+          acc[0] += W[0]; acc[1] += W[1]; acc[2] += W[2]; acc[3] += W[3]; acc[4] += W[4]; acc[5] += W[5];
+          acc[6] += et.v[0]; acc[7] += et.v[1]; acc[8] += et.v[2];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            B[c] = -(W[0] * Q[c] + W[1] * Q[3 + c] + W[2] * Q[6 + c]);
+            B[3 + c] = -(W[1] * Q[c] + W[3] * Q[3 + c] + W[4] * Q[6 + c]);
+            B[6 + c] = -(W[2] * Q[c] + W[4] * Q[3 + c] + W[5] * Q[6 + c]);
+          }
+        } else {
+          // row i: diag += Q^T W Q, grad += -Q^T v, block(i,j) = -Q^T W
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {  // B[r][c] = -sum_k Q[k][r] W[k][c]
+            B[3 * r + 0] = -(Q[r] * W[0] + Q[3 + r] * W[1] + Q[6 + r] * W[2]);
+            B[3 * r + 1] = -(Q[r] * W[1] + Q[3 + r] * W[3] + Q[6 + r] * W[4]);
+            B[3 * r + 2] = -(Q[r] * W[2] + Q[3 + r] * W[4] + Q[6 + r] * W[5]);
+          }
+          // Q^T W Q = -B Q
+          acc[0] -= B[0] * Q[0] + B[1] * Q[3] + B[2] * Q[6];
+          acc[1] -= B[0] * Q[1] + B[1] * Q[4] + B[2] * Q[7];
+          acc[2] -= B[0] * Q[2] + B[1] * Q[5] + B[2] * Q[8];
+          acc[3] -= B[3] * Q[1] + B[4] * Q[4] + B[5] * Q[7];
+          acc[4] -= B[3] * Q[2] + B[4] * Q[5] + B[5] * Q[8];
+          acc[5] -= B[6] * Q[2] + B[7] * Q[5] + B[8] * Q[8];
+          acc[6] -= Q[0] * et.v[0] + Q[3] * et.v[1] + Q[6] * et.v[2];
+          acc[7] -= Q[1] * et.v[0] + Q[4] * et.v[1] + Q[7] * et.v[2];
+          acc[8] -= Q[2] * et.v[0] + Q[5] * et.v[1] + Q[8] * et.v[2];
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) val[(uint64_t)k * H + h] = B[k];
+      }
+    }
+    if (kWriteBlocks) {
+#pragma unroll
+      for (int k = 0; k < kPartStride; ++k) acc[k] = warp_sum(acc[k]);
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kPartStride; ++k) part[(size_t)t * kPartStride + k] = acc[k];
+      }
+    } else {
+      const double c = warp_sum(acc[9]);
+      if (lane == 0) part[(size_t)t * kPartStride + 9] = c;
+    }
+  }
+}
+
+// Per view: add the task partials in task order -> tangent diagonal block Hd (packed sym 6),
+// tangent gradient gt; Euclidean gradient g = Jl^T gt (for the gradient tolerance), the Euclidean
+// diagonal diag(Jl^T Hd Jl) (for Jacobi scaling and the LM diagonal), total cost.
+__global__ void k_node_finalize(uint32_t N, const uint32_t* __restrict__ node_task_ptr, const double* __restrict__ part,
+                                const double* __restrict__ node_JL, double* __restrict__ Hd, double* __restrict__ gt,
+                                double* __restrict__ ediag, int cost_only, double* slots, unsigned* counter, DevScalars* sc) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[2] = {0.0, 0.0};
+  double gm = 0.0;
+  if (i < N) {
+    double a[kPartStride];
+#pragma unroll
+    for (int k = 0; k < kPartStride; ++k) a[k] = 0.0;
+    for (uint32_t t = node_task_ptr[i]; t < node_task_ptr[i + 1]; ++t) {
+      if (cost_only) a[9] += part[(size_t)t * kPartStride + 9];
+      else {
+#pragma unroll
+        for (int k = 0; k < kPartStride; ++k) a[k] += part[(size_t)t * kPartStride + k];
+      }
+    }
+    v[0] = a[9];
+    if (!cost_only) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) Hd[6 * (size_t)i + k] = a[k];
+      gt[3 * (size_t)i] = a[6]; gt[3 * (size_t)i + 1] = a[7]; gt[3 * (size_t)i + 2] = a[8];
+      double J[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) J[k] = node_JL[9 * (size_t)i + k];
+      double He[6];
+      congruence(J, a, He);
+      ediag[3 * (size_t)i] = He[0]; ediag[3 * (size_t)i + 1] = He[3]; ediag[3 * (size_t)i + 2] = He[5];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gm = fmax(gm, fabs(J[c] * a[6] + J[3 + c] * a[7] + J[6 + c] * a[8]));
+      if (!(isfinite(a[0]) && isfinite(a[3]) && isfinite(a[5]) && isfinite(a[6]) && isfinite(a[7]) && isfinite(a[8]))) v[1] = 1.0;
+    }
+  }
+  // max |g|: block max -> atomicMax on the bit pattern (non-negative doubles order like uint64)
+  if (!cost_only) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+    if ((threadIdx.x & 31) == 0 && gm > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(&sc->gmax), (unsigned long long)__double_as_longlong(gm));
+  }
+  double tot[2];
+  if (grid_sum<2>(v, slots, counter, tot) && threadIdx.x == 0) {
+    sc->cost = tot[0];
+    if (tot[1] != 0.0 || !isfinite(tot[0])) sc->bad = 1;
+  }
+}
+
+// Jacobi scaling, estimated once at the initial point (Ceres: scale_c = 1/(1 + |J_col c|)).
+__global__ void k_jacobi_scale(uint32_t n3, const double* __restrict__ ediag, double* __restrict__ scale, int enabled) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n3) scale[c] = enabled ? 1.0 / (1.0 + sqrt(ediag[c])) : 1.0;
+}
+
+// Per view, before a linear solve at trust-region radius mu:
+//   LM diagonal in scaled coordinates  d_c = clamp(ediag_c s_c^2, lo, hi) / mu           (LevenbergMarquardtStrategy)
+//   as damping of the unscaled Euclidean system  lam_c = d_c / s_c^2
+//   moved to the tangent frame  Lam = Jl^-T diag(lam) Jl^-1 ;  Dblk = Hd + Lam ; Minv = Dblk^-1.
+// Also initialises PCG: x = 0, r = b = -gt, z = Minv r, p = z, and reduces rz, bb.
+__global__ void k_prepare_solve(uint32_t N, double mu, double lo, double hi, const double* __restrict__ ediag,
+                                const double* __restrict__ scale, const double* __restrict__ node_JL, const double* __restrict__ Hd,
+                                const double* __restrict__ gt, const double* __restrict__ user_damp, const double* __restrict__ user_b,
+                                double* __restrict__ Dblk, double* __restrict__ Minv, double* __restrict__ x, double* __restrict__ r,
+                                double* __restrict__ z, double* __restrict__ p, double* slots, unsigned* counter, DevScalars* sc) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[2] = {0.0, 0.0};
+  if (i < N) {
+    double lam[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (user_damp) lam[c] = user_damp[3 * (size_t)i + c];
+      else {
+        const double s2 = scale[3 * (size_t)i + c] * scale[3 * (size_t)i + c];
+        lam[c] = fmin(fmax(ediag[3 * (size_t)i + c] * s2, lo), hi) / mu / s2;
+      }
+    }
+    double J[9], Ji[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) J[k] = node_JL[9 * (size_t)i + k];
+    inv3(J, Ji);
+    double lamS[6] = {lam[0], 0.0, 0.0, lam[1], 0.0, lam[2]};
+    double Lam[6];
+    congruence(Ji, lamS, Lam);
+    double D[6], M[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { D[k] = Hd[6 * (size_t)i + k] + Lam[k]; Dblk[6 * (size_t)i + k] = D[k]; }
+    sym_inv(D, M);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Minv[6 * (size_t)i + k] = M[k];
+    double b[3], zz[3];
+    if (user_b) {  // b given in Euclidean coordinates: bt = Jl^-T b
+#pragma unroll
+      for (int c = 0; c < 3; ++c) b[c] = Ji[c] * user_b[3 * (size_t)i] + Ji[3 + c] * user_b[3 * (size_t)i + 1] + Ji[6 + c] * user_b[3 * (size_t)i + 2];
+    } else {
+      b[0] = -gt[3 * (size_t)i]; b[1] = -gt[3 * (size_t)i + 1]; b[2] = -gt[3 * (size_t)i + 2];
+    }
+    sym_mul_vec(M, b, zz);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      x[3 * (size_t)i + c] = 0.0; r[3 * (size_t)i + c] = b[c]; z[3 * (size_t)i + c] = zz[c]; p[3 * (size_t)i + c] = zz[c];
+      v[0] += b[c] * zz[c];
+      v[1] += b[c] * b[c];
+    }
+  }
+  double tot[2];
+  if (grid_sum<2>(v, slots, counter, tot) && threadIdx.x == 0) {
+    sc->rz = tot[0]; sc->bb = tot[1]; sc->rr = tot[1];
+    sc->pcg_iter = 0; sc->pcg_breakdown = 0;
+    sc->pcg_done = (tot[1] == 0.0 || !isfinite(tot[1])) ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: block-3x3 CSR SpMV, off-diagonal part.  One warp per task; each lane streams one 72 B block
+// per iteration from the planar value array (9 coalesced 8 B loads), gathers x[col] (24 B, L2),
+// accumulates 3 doubles; one warp reduction per task.  ypart[t][3].
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+k_spmv(uint32_t num_tasks, uint64_t H, const uint32_t* __restrict__ task_begin, const uint32_t* __restrict__ task_len,
+       const uint32_t* __restrict__ he_col, const double* __restrict__ val, const double* __restrict__ x,
+       double* __restrict__ ypart, const DevScalars* sc, int check_done) {
+  if (check_done && sc->pcg_done) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t t = warp_global; t < num_tasks; t += num_warps) {
+    const uint64_t begin = task_begin[t];
+    const uint32_t len = task_len[t];
+    double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+    for (uint32_t off = lane; off < len; off += 32) {
+      const uint64_t h = begin + off;
+      const uint32_t col = he_col[h] & ~kSideBit;
+      const double x0 = x[3 * (size_t)col], x1 = x[3 * (size_t)col + 1], x2 = x[3 * (size_t)col + 2];
+      y0 += val[h] * x0 + val[H + h] * x1 + val[2 * H + h] * x2;
+      y1 += val[3 * H + h] * x0 + val[4 * H + h] * x1 + val[5 * H + h] * x2;
+      y2 += val[6 * H + h] * x0 + val[7 * H + h] * x1 + val[8 * H + h] * x2;
+    }
+    y0 = warp_sum(y0); y1 = warp_sum(y1); y2 = warp_sum(y2);
+    if (lane == 0) { ypart[3 * (size_t)t] = y0; ypart[3 * (size_t)t + 1] = y1; ypart[3 * (size_t)t + 2] = y2; }
+  }
+}
+
+// y_i = Dblk_i x_i + sum of the row's task partials (+ shard-local only: the diagonal part is
+// added after the cross-GPU reduction).  mode 0: write y, reduce p.y -> alpha (PCG step 1).
+// mode 1: y only.
+__global__ void k_spmv_finish(uint32_t N, const uint32_t* __restrict__ node_task_ptr, const double* __restrict__ ypart,
+                              const double* __restrict__ Dblk, const double* __restrict__ x, double* __restrict__ y,
+                              int mode, double* slots, unsigned* counter, DevScalars* sc) {
+  if (mode == 0 && sc->pcg_done) return;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[1] = {0.0};
+  if (i < N) {
+    double xi[3] = {x[3 * (size_t)i], x[3 * (size_t)i + 1], x[3 * (size_t)i + 2]};
+    double yi[3] = {0.0, 0.0, 0.0};
+    if (Dblk) sym_mul_vec(Dblk + 6 * (size_t)i, xi, yi);
+    for (uint32_t t = node_task_ptr[i]; t < node_task_ptr[i + 1]; ++t) {
+      yi[0] += ypart[3 * (size_t)t]; yi[1] += ypart[3 * (size_t)t + 1]; yi[2] += ypart[3 * (size_t)t + 2];
+    }
+    y[3 * (size_t)i] = yi[0]; y[3 * (size_t)i + 1] = yi[1]; y[3 * (size_t)i + 2] = yi[2];
+    v[0] = xi[0] * yi[0] + xi[1] * yi[1] + xi[2] * yi[2];
+  }
+  if (mode != 0) return;
+  double tot[1];
+  if (grid_sum<1>(v, slots, counter, tot) && threadIdx.x == 0) {
+    sc->pAp = tot[0];
+    if (!(tot[0] > 0.0) || !isfinite(tot[0])) { sc->pcg_done = 1; sc->pcg_breakdown = 1; sc->alpha = 0.0; }
+    else sc->alpha = sc->rz / tot[0];
+  }
+}
+
+// PCG step 2: x += alpha p ; r -= alpha y ; z = Minv r ; reduce r.z, r.r -> beta, convergence.
+__global__ void k_pcg_update(uint32_t N, const double* __restrict__ Minv, const double* __restrict__ p, const double* __restrict__ y,
+                             double* __restrict__ x, double* __restrict__ r, double* __restrict__ z, double rtol2, int max_iter,
+                             double* slots, unsigned* counter, DevScalars* sc) {
+  if (sc->pcg_done) return;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[2] = {0.0, 0.0};
+  if (i < N) {
+    const double alpha = sc->alpha;
+    double ri[3], zi[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      x[3 * (size_t)i + c] += alpha * p[3 * (size_t)i + c];
+      ri[c] = r[3 * (size_t)i + c] - alpha * y[3 * (size_t)i + c];
+      r[3 * (size_t)i + c] = ri[c];
+    }
+    sym_mul_vec(Minv + 6 * (size_t)i, ri, zi);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { z[3 * (size_t)i + c] = zi[c]; v[0] += ri[c] * zi[c]; v[1] += ri[c] * ri[c]; }
+  }
+  double tot[2];
+  if (grid_sum<2>(v, slots, counter, tot) && threadIdx.x == 0) {
+    sc->beta = tot[0] / sc->rz;
+    sc->rz = tot[0];
+    sc->rr = tot[1];
+    sc->pcg_iter += 1;
+    if (tot[1] <= rtol2 * sc->bb || sc->pcg_iter >= max_iter || !isfinite(tot[1])) sc->pcg_done = 1;
+  }
+}
+
+// PCG step 3: p = z + beta p.
+__global__ void k_pcg_direction(uint32_t n3, const double* __restrict__ z, double* __restrict__ p, const DevScalars* sc) {
+  if (sc->pcg_done) return;
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n3) p[c] = z[c] + sc->beta * p[c];
+}
+
+// After the solve (xt = tangent step, Hx = Ht xt without damping): Euclidean step
+// delta = Jl^-1 xt, candidate = omega + delta (Ceres updates the angle-axis vector additively);
+// reduce delta.g (= xt.gt), delta.H.delta (= xt.Hx), |delta|^2.
+__global__ void k_apply_step(uint32_t N, const double* __restrict__ node_JL, const double* __restrict__ xt, const double* __restrict__ Hx,
+                             const double* __restrict__ gt, const double* __restrict__ omega, double* __restrict__ cand,
+                             double* __restrict__ delta_out, double* slots, unsigned* counter, DevScalars* sc) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  if (i < N) {
+    double J[9], Ji[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) J[k] = node_JL[9 * (size_t)i + k];
+    inv3(J, Ji);
+    const double t0 = xt[3 * (size_t)i], t1 = xt[3 * (size_t)i + 1], t2 = xt[3 * (size_t)i + 2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double d = Ji[3 * c] * t0 + Ji[3 * c + 1] * t1 + Ji[3 * c + 2] * t2;
+      if (cand) cand[3 * (size_t)i + c] = omega[3 * (size_t)i + c] + d;
+      if (delta_out) delta_out[3 * (size_t)i + c] = d;
+      v[2] += d * d;
+      if (!isfinite(d)) v[3] = 1.0;
+    }
+    if (gt) v[0] = t0 * gt[3 * (size_t)i] + t1 * gt[3 * (size_t)i + 1] + t2 * gt[3 * (size_t)i + 2];
+    if (Hx) v[1] = t0 * Hx[3 * (size_t)i] + t1 * Hx[3 * (size_t)i + 1] + t2 * Hx[3 * (size_t)i + 2];
+  }
+  double tot[4];
+  if (grid_sum<4>(v, slots, counter, tot) && threadIdx.x == 0) {
+    sc->dg = tot[0]; sc->dHd = tot[1]; sc->step2 = tot[2];
+    if (tot[3] != 0.0) sc->bad = 1;
+  }
+}
+
+// ---- API-only kernels (parity tests / diagnostics; not on the solve path) ------------------
+// Raw per-edge outputs in EDGE order and Euclidean (angle-axis) coordinates, i.e. exactly what
+// AutoDiffCostFunction::Evaluate + LossFunction::Evaluate return in the reference.
+__global__ void k_eval_edges(uint64_t E, const uint32_t* __restrict__ ei, const uint32_t* __restrict__ ej, const double* __restrict__ omega_ij,
+                             const double* __restrict__ cov6, const double* __restrict__ weight, int error_type, const double* __restrict__ node_q,
+                             const double* __restrict__ node_JL, DevLoss loss, double* r, double* Ji, double* Jj, double* rho) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= E) return;
+  const uint32_t i = ei[k], j = ej[k];
+  const double4 a = reinterpret_cast<const double4*>(node_q)[i], b = reinterpret_cast<const double4*>(node_q)[j];
+  const Q4 qi{a.x, a.y, a.z, a.w}, qj{b.x, b.y, b.z, b.w};
+  const Q4 qm = aa_to_quat(omega_ij[3 * k], omega_ij[3 * k + 1], omega_ij[3 * k + 2]);
+  double c6[6] = {0, 0, 0, 0, 0, 0}, u[6];
+  if (cov6) for (int t = 0; t < 6; ++t) c6[t] = cov6[6 * k + t];
+  whiten(error_type, c6, weight ? weight[k] : 1.0, u);
+  EdgeTerms et;
+  edge_terms<true>(qi, qj, qm, u, loss, et);
+  if (r) for (int t = 0; t < 3; ++t) r[3 * k + t] = et.r[t];
+  if (rho) for (int t = 0; t < 3; ++t) rho[3 * k + t] = et.rho[t];
+  if (Jj) {  // d r / d omega_j = A Jl(omega_j)
+    const double* JL = node_JL + 9 * (size_t)j;
+    for (int rr = 0; rr < 3; ++rr)
+      for (int c = 0; c < 3; ++c) Jj[9 * k + 3 * rr + c] = et.A[3 * rr] * JL[c] + et.A[3 * rr + 1] * JL[3 + c] + et.A[3 * rr + 2] * JL[6 + c];
+  }
+  if (Ji) {  // d r / d omega_i = -A Q Jl(omega_i)
+    const double* JL = node_JL + 9 * (size_t)i;
+    double AQ[9];
+    for (int rr = 0; rr < 3; ++rr)
+      for (int c = 0; c < 3; ++c) AQ[3 * rr + c] = et.A[3 * rr] * et.Q[c] + et.A[3 * rr + 1] * et.Q[3 + c] + et.A[3 * rr + 2] * et.Q[6 + c];
+    for (int rr = 0; rr < 3; ++rr)
+      for (int c = 0; c < 3; ++c) Ji[9 * k + 3 * rr + c] = -(AQ[3 * rr] * JL[c] + AQ[3 * rr + 1] * JL[3 + c] + AQ[3 * rr + 2] * JL[6 + c]);
+  }
+}
+
+__global__ void k_whiten_edges(uint64_t E, const double* __restrict__ cov6, const double* __restrict__ weight, int error_type, double* U9) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= E) return;
+  double c6[6] = {0, 0, 0, 0, 0, 0}, u[6];
+  if (cov6) for (int t = 0; t < 6; ++t) c6[t] = cov6[6 * k + t];
+  whiten(error_type, c6, weight ? weight[k] : 1.0, u);
+  double* o = U9 + 9 * k;
+  o[0] = u[0]; o[1] = u[1]; o[2] = u[2]; o[3] = 0.0; o[4] = u[3]; o[5] = u[4]; o[6] = 0.0; o[7] = 0.0; o[8] = u[5];
+}
+
+__global__ void k_eval_loss(uint64_t n, const double* __restrict__ s, DevLoss loss, double* out) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  double rho[3];
+  eval_loss(loss, s[k], rho);
+  out[3 * k] = rho[0]; out[3 * k + 1] = rho[1]; out[3 * k + 2] = rho[2];
+}
+
+// Tangent -> Euclidean export of the assembled system (API gsfm_ra_assemble).
+__global__ void k_export_blocks(uint64_t H, const uint32_t* __restrict__ he_row, const uint32_t* __restrict__ he_col, const double* __restrict__ val,
+                                const double* __restrict__ node_JL, double* out_val, uint32_t* out_col) {
+  const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  const uint32_t row = he_row[h], col = he_col[h] & ~kSideBit;
+  double B[9], T[9];
+  for (int k = 0; k < 9; ++k) B[k] = val[(uint64_t)k * H + h];
+  const double* Jr = node_JL + 9 * (size_t)row;
+  const double* Jc = node_JL + 9 * (size_t)col;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) T[3 * r + c] = B[3 * r] * Jc[c] + B[3 * r + 1] * Jc[3 + c] + B[3 * r + 2] * Jc[6 + c];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) out_val[9 * h + 3 * r + c] = Jr[r] * T[c] + Jr[3 + r] * T[3 + c] + Jr[6 + r] * T[6 + c];
+  if (out_col) out_col[h] = col;
+}
+__global__ void k_export_nodes(uint32_t N, const double* __restrict__ Hd, const double* __restrict__ gt, const double* __restrict__ node_JL,
+                               double* hdiag9, double* grad) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double* J = node_JL + 9 * (size_t)i;
+  double He[6];
+  congruence(J, Hd + 6 * (size_t)i, He);
+  if (hdiag9) {
+    double* o = hdiag9 + 9 * (size_t)i;
+    o[0] = He[0]; o[1] = He[1]; o[2] = He[2]; o[3] = He[1]; o[4] = He[3]; o[5] = He[4]; o[6] = He[2]; o[7] = He[4]; o[8] = He[5];
+  }
+  if (grad) for (int c = 0; c < 3; ++c) grad[3 * (size_t)i + c] = J[c] * gt[3 * (size_t)i] + J[3 + c] * gt[3 * (size_t)i + 1] + J[6 + c] * gt[3 * (size_t)i + 2];
+}
+// v_out = Jl v (mode 0), Jl^T v (mode 1) [+ damp .* x2]
+__global__ void k_node_apply(uint32_t N, const double* __restrict__ node_JL, const double* __restrict__ v, int mode, const double* __restrict__ damp,
+                             const double* __restrict__ x2, double* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double* J = node_JL + 9 * (size_t)i;
+  const double a = v[3 * (size_t)i], b = v[3 * (size_t)i + 1], c = v[3 * (size_t)i + 2];
+  for (int q = 0; q < 3; ++q) {
+    double o = mode == 0 ? J[3 * q] * a + J[3 * q + 1] * b + J[3 * q + 2] * c : J[q] * a + J[3 + q] * b + J[6 + q] * c;
+    if (damp) o += damp[3 * (size_t)i + q] * x2[3 * (size_t)i + q];
+    out[3 * (size_t)i + q] = o;
+  }
+}
+
+// The step after the path: FilterViewPairsFromOrientation (T/sfm/filter_view_pairs_from_orientation.cc:55-118).
+__global__ void k_filter_pairs(uint64_t E, const uint32_t* __restrict__ ei, const uint32_t* __restrict__ ej, const double* __restrict__ omega_ij,
+                               const double* __restrict__ node_q, double sq_threshold, uint8_t* keep, double* angle) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= E) return;
+  const double4 a = reinterpret_cast<const double4*>(node_q)[ei[k]], b = reinterpret_cast<const double4*>(node_q)[ej[k]];
+  const Q4 qi{a.x, a.y, a.z, a.w}, qj{b.x, b.y, b.z, b.w};
+  const Q4 qm = aa_to_quat(omega_ij[3 * k], omega_ij[3 * k + 1], omega_ij[3 * k + 2]);
+  const Q4 qE = qmul(qmul(qj, qconj(qi)), qconj(qm));
+  double e[3], t2, c;
+  quat_log(qE, e, &t2, &c);
+  if (angle) angle[k] = sqrt(t2);
+  if (keep) keep[k] = (t2 <= sq_threshold) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+int make_dev_loss(const gsfm_ra_loss* in, DevLoss* L) {
+  std::memset(L, 0, sizeof(*L));
+  if (!in) { L->kind = kLossTrivial; L->scale = 1.0; return 0; }
+  if (in->kind < 0 || in->kind > GSFM_RA_LOSS_MAGSAC9) { set_error("unknown loss kind %d", in->kind); return GSFM_RA_ERR_INVALID; }
+  L->kind = in->kind; L->flags = in->flags; L->p0 = in->p[0]; L->p1 = in->p[1];
+  L->scale = (in->scale == 0.0) ? 1.0 : in->scale;
+  const bool needs_p0 = in->kind != GSFM_RA_LOSS_TRIVIAL;
+  if (needs_p0 && !(in->p[0] > 0.0)) { set_error("loss parameter p[0] must be > 0"); return GSFM_RA_ERR_INVALID; }
+  if ((in->kind == GSFM_RA_LOSS_TOLERANT || in->kind == GSFM_RA_LOSS_GEMANMCCLURE) && !(in->p[1] > 0.0)) {
+    set_error("loss parameter p[1] must be > 0"); return GSFM_RA_ERR_INVALID;
+  }
+  if (in->kind >= GSFM_RA_LOSS_MAGSAC3) {
+    // include/gamma_values.cpp:6-11, 384-389, 780-785
+    double C, quant, gk; int nu, n;
+    if (in->kind == GSFM_RA_LOSS_MAGSAC3) { nu = 3; C = 4.029720004054876e-01; quant = 3.368214175218727; gk = 3.439485560754856e-03; n = 36843; }
+    else if (in->kind == GSFM_RA_LOSS_MAGSAC4) { nu = 4; C = 2.525252525252525e-01; quant = 3.643721193503644e+00; gk = 3.611260617758625e-03; n = 38683; }
+    else { nu = 9; C = 3.837828575290349e-03; quant = 4.654674460524809e+00; gk = 3.344206155099048e-02; n = 48553; }
+    const double sigma = in->p[0];
+    L->nu = nu; L->table_size = n;
+    L->sq_sigma = sigma * sigma;
+    L->sq_sigma_max_2 = 2.0 * L->sq_sigma;
+    L->cubed_sigma = L->sq_sigma * sigma;
+    L->clamp_s = quant * quant * L->sq_sigma;
+    const double dof = (nu - 1.0) / 2.0;
+    L->Ctd = C * std::pow(2.0, dof);
+    L->one_over_sigma = L->Ctd / sigma;
+    L->gamma_k = gk;
+    L->weight_zero = L->one_over_sigma * (std::tgamma(dof) - gk);
+    L->expo = nu / 2.0 - 1.5;
+  }
+  return 0;
+}
+
+bool type_needs_cov(int t) { return t == 3 || t == 6 || t == 7 || t == 8; }
+
+int check_problem(const gsfm_ra_problem* p) {
+  if (!p) { set_error("problem is NULL"); return GSFM_RA_ERR_INVALID; }
+  if (p->num_views == 0 || p->num_edges == 0) { set_error("empty problem (views=%u edges=%llu)", p->num_views, (unsigned long long)p->num_edges); return GSFM_RA_ERR_INVALID; }
+  if (!p->edge_i || !p->edge_j || !p->omega_ij) { set_error("edge arrays are NULL"); return GSFM_RA_ERR_INVALID; }
+  if (p->num_views >= kSideBit) { set_error("too many views"); return GSFM_RA_ERR_INVALID; }
+  if (p->num_edges >= (1ull << 31)) { set_error("too many edges for 32-bit half-edge offsets"); return GSFM_RA_ERR_UNSUPPORTED; }
+  if (p->error_type < GSFM_RA_QUATERNION_NORM || p->error_type > GSFM_RA_ANGLE_AXIS_COVNORM) { set_error("unknown error_type %d", p->error_type); return GSFM_RA_ERR_INVALID; }
+  if (p->error_type < GSFM_RA_ANGLE_AXIS_COVARIANCE) { set_error("quaternion / matrix residual types are not implemented (angle-axis types 3..8 only)"); return GSFM_RA_ERR_UNSUPPORTED; }
+  if (type_needs_cov(p->error_type) && !p->cov6) { set_error("error_type %d needs cov6", p->error_type); return GSFM_RA_ERR_INVALID; }
+  return 0;
+}
+
+int select_device(int device, int* out) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device visible: libgsfm_ra has no CPU fallback");
+    return GSFM_RA_ERR_NO_DEVICE;
+  }
+  if (device < 0) { CUDA_TRY(cudaGetDevice(&device)); }
+  if (device >= n) { set_error("device %d out of range (%d visible)", device, n); return GSFM_RA_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(device));
+  *out = device;
+  return 0;
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return 0;
+    CUDA_TRY(cudaMalloc(&p, count * sizeof(T)));
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// the resident solver
+// ------------------------------------------------------------------------------------------
+struct gsfm_ra_solver {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  uint32_t N = 0;
+  uint64_t E = 0;       // edges of this shard
+  uint64_t H = 0;       // half-edges of this shard (2E)
+  uint32_t T = 0;       // tasks
+  int rank = 0, world = 1;
+  int error_type = 4;
+  gsfm_ra_options opt;
+  DevLoss loss;
+  int64_t launches = 0;
+
+  // structure
+  DevBuf<uint32_t> he_col, he_row, task_row, task_begin, task_len, node_task_ptr;
+  // per half-edge constants, planar
+  DevBuf<double> qij, U;
+  // edge-order copies for the API kernels
+  DevBuf<uint32_t> d_ei, d_ej;
+  DevBuf<double> d_omega_ij, d_cov6, d_weight;
+  // linearisation, double buffered: [cur] is the accepted point, [cur^1] the candidate
+  DevBuf<double> omega[2], node_q[2], node_JL[2], val[2], Hd[2], gt[2], ediag[2];
+  DevBuf<double> part;
+  int cur = 0;
+  // PCG
+  DevBuf<double> scale, Dblk, Minv, x, r, z, p, y, ypart, delta;
+  DevBuf<double> slots;
+  DevBuf<unsigned> counter;
+  DevBuf<DevScalars> sc;
+  DevScalars* h_sc = nullptr;  // pinned
+
+  // trust-region state (host)
+  bool linearized = false;
+  bool scale_ready = false;
+  double radius = 1e4, decrease_factor = 2.0, x_cost = 0.0, x_norm = 0.0, gmax = 0.0;
+  int iteration = 0, invalid_steps = 0;
+  bool last_successful = false;
+  int termination = GSFM_RA_TERM_NONE;
+  double initial_cost = 0.0;
+  // timing accumulators (ms, CUDA events)
+  double ms_setup = 0, ms_assemble = 0, ms_linear = 0, ms_cost = 0;
+
+  ~gsfm_ra_solver() {
+    if (h_sc) cudaFreeHost(h_sc);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  unsigned task_grid() const {
+    const unsigned want = (T + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const unsigned cap = (unsigned)sm_count * 8u;  // 8 blocks of 256 threads = 2048 threads per SM
+    return std::max(1u, std::min(want, cap));
+  }
+
+  int fetch_scalars() {
+    CUDA_TRY(cudaMemcpyAsync(h_sc, sc.p, sizeof(DevScalars), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return 0;
+  }
+
+  // ---- evaluation at omega[b]: node prep, K1 (or K1c), node finalize -------------------------
+  int evaluate(int b, bool jacobian) {
+    CUDA_TRY(cudaMemsetAsync(&sc.p->gmax, 0, sizeof(double), stream));
+    k_node_prep<<<grid_for(N), kBlock, 0, stream>>>(N, omega[b].p, node_q[b].p, node_JL[b].p, slots.p, counter.p, sc.p);
+    if (jacobian)
+      k_edges<true><<<task_grid(), kBlock, 0, stream>>>(T, H, task_row.p, task_begin.p, task_len.p, he_col.p, qij.p, U.p, node_q[b].p, loss, val[b].p, part.p);
+    else
+      k_edges<false><<<task_grid(), kBlock, 0, stream>>>(T, H, task_row.p, task_begin.p, task_len.p, he_col.p, qij.p, U.p, node_q[b].p, loss, nullptr, part.p);
+    k_node_finalize<<<grid_for(N), kBlock, 0, stream>>>(N, node_task_ptr.p, part.p, node_JL[b].p, Hd[b].p, gt[b].p, ediag[b].p, jacobian ? 0 : 1,
+                                                         slots.p, counter.p, sc.p);
+    launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+
+  // y = (Ht [+ Dblk]) x on linearisation b.  with_diag: Dblk (incl. damping) else the undamped Hd.
+  int spmv(int b, const double* xin, double* yout, const double* diag_blocks) {
+    k_spmv<<<task_grid(), kBlock, 0, stream>>>(T, H, task_begin.p, task_len.p, he_col.p, val[b].p, xin, ypart.p, sc.p, 0);
+    k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, node_task_ptr.p, ypart.p, diag_blocks, xin, yout, 1, slots.p, counter.p, sc.p);
+    launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+
+  // Block-Jacobi PCG on (Ht + Lam) xt = bt for linearisation b.  Everything stays on the device;
+  // the host enqueues `poll` iterations at a time and reads the convergence flag.
+  int pcg(int b, double mu, const double* user_damp, const double* user_b, double rtol, int max_iter, int* iters, double* rel_res) {
+    k_prepare_solve<<<grid_for(N), kBlock, 0, stream>>>(N, mu, opt.min_lm_diagonal, opt.max_lm_diagonal, ediag[b].p, scale.p, node_JL[b].p,
+                                                         Hd[b].p, gt[b].p, user_damp, user_b, Dblk.p, Minv.p, x.p, r.p, z.p, p.p, slots.p,
+                                                         counter.p, sc.p);
+    launches += 1;
+    const int poll = 8;
+    const double rtol2 = rtol * rtol;
+    int enq = 0;
+    while (true) {
+      for (int k = 0; k < poll && enq < max_iter; ++k, ++enq) {
+        k_spmv<<<task_grid(), kBlock, 0, stream>>>(T, H, task_begin.p, task_len.p, he_col.p, val[b].p, p.p, ypart.p, sc.p, 1);
+        k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, node_task_ptr.p, ypart.p, Dblk.p, p.p, y.p, 0, slots.p, counter.p, sc.p);
+        k_pcg_update<<<grid_for(N), kBlock, 0, stream>>>(N, Minv.p, p.p, y.p, x.p, r.p, z.p, rtol2, max_iter, slots.p, counter.p, sc.p);
+        k_pcg_direction<<<grid_for(3ull * N), kBlock, 0, stream>>>(3 * N, z.p, p.p, sc.p);
+        launches += 4;
+      }
+      CUDA_TRY(cudaGetLastError());
+      RA_TRY(fetch_scalars());
+      if (h_sc->pcg_done || enq >= max_iter) break;
+    }
+    if (iters) *iters = h_sc->pcg_iter;
+    if (rel_res) *rel_res = (h_sc->bb > 0.0) ? std::sqrt(h_sc->rr / h_sc->bb) : 0.0;
+    return 0;
+  }
+
+  double elapsed_since(cudaEvent_t a) {
+    cudaEventRecord(ev[1], stream);
+    cudaEventSynchronize(ev[1]);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, ev[1]);
+    return ms;
+  }
+};
+
+namespace {
+
+// Build the half-edge structure on the host and upload everything.
+int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, int rank, int world, gsfm_ra_solver** out) {
+  RA_TRY(check_problem(prob));
+  if (!options || !out) { set_error("options/out is NULL"); return GSFM_RA_ERR_INVALID; }
+  if (world < 1 || rank < 0 || rank >= world) { set_error("bad rank/world"); return GSFM_RA_ERR_INVALID; }
+  const uint32_t N = prob->num_views;
+  for (uint64_t k = 0; k < prob->num_edges; ++k) {
+    if (prob->edge_i[k] >= N || prob->edge_j[k] >= N || prob->edge_i[k] == prob->edge_j[k]) {
+      set_error("edge %llu (%u,%u) is out of range or a self loop", (unsigned long long)k, prob->edge_i[k], prob->edge_j[k]);
+      return GSFM_RA_ERR_INVALID;
+    }
+  }
+  int device = 0;
+  RA_TRY(select_device(options->device, &device));
+  std::unique_ptr<gsfm_ra_solver> s(new gsfm_ra_solver());
+  s->device = device;
+  s->opt = *options;
+  s->rank = rank; s->world = world;
+  s->error_type = prob->error_type;
+  RA_TRY(make_dev_loss(&options->loss, &s->loss));
+  cudaDeviceProp dp;
+  CUDA_TRY(cudaGetDeviceProperties(&dp, device));
+  s->sm_count = dp.multiProcessorCount;
+  CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&s->ev[0]));
+  CUDA_TRY(cudaEventCreate(&s->ev[1]));
+  CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
+
+  // shard: a contiguous range of the caller's edge list
+  const uint64_t e0 = prob->num_edges * (uint64_t)rank / world, e1 = prob->num_edges * (uint64_t)(rank + 1) / world;
+  const uint64_t E = e1 - e0, H = 2 * E;
+  s->N = N; s->E = E; s->H = H;
+  const uint32_t* ei = prob->edge_i + e0;
+  const uint32_t* ej = prob->edge_j + e0;
+
+  // counting sort of half-edges by row, then by column inside each row
+  std::vector<uint32_t> rowptr(N + 1, 0);
+  for (uint64_t k = 0; k < E; ++k) { rowptr[ei[k] + 1]++; rowptr[ej[k] + 1]++; }
+  for (uint32_t a = 0; a < N; ++a) rowptr[a + 1] += rowptr[a];
+  std::vector<uint64_t> ent(H);  // (col | side) << 32 | edge
+  {
+    std::vector<uint32_t> fill(rowptr.begin(), rowptr.end() - 1);
+    for (uint64_t k = 0; k < E; ++k) {
+      ent[fill[ei[k]]++] = ((uint64_t)ej[k] << 32) | (uint32_t)k;
+      ent[fill[ej[k]]++] = ((uint64_t)ei[k] << 32) | (uint32_t)k | (1ull << 63);
+    }
+  }
+  std::vector<uint32_t> he_col(H), he_row(H), he_edge(H);
+  std::vector<uint32_t> task_row, task_begin, task_len, node_task_ptr(N + 1, 0);
+  for (uint32_t a = 0; a < N; ++a) {
+    auto b = ent.begin() + rowptr[a], e = ent.begin() + rowptr[a + 1];
+    std::sort(b, e, [](uint64_t x, uint64_t y) { return (x & ~(1ull << 63)) < (y & ~(1ull << 63)); });
+    for (uint32_t h = rowptr[a]; h < rowptr[a + 1]; ++h) {
+      const uint64_t v = ent[h];
+      const uint32_t col = (uint32_t)((v >> 32) & 0x7fffffffu);
+      he_col[h] = col | ((v >> 63) ? kSideBit : 0u);
+      he_row[h] = a;
+      he_edge[h] = (uint32_t)(v & 0xffffffffu);
+      if (h > rowptr[a] && (he_col[h - 1] & ~kSideBit) == col) {
+        set_error("duplicate edge between views %u and %u", a, col);
+        return GSFM_RA_ERR_INVALID;
+      }
+    }
+    node_task_ptr[a] = (uint32_t)task_row.size();
+    for (uint32_t h = rowptr[a]; h < rowptr[a + 1]; h += kTaskLen) {
+      task_row.push_back(a);
+      task_begin.push_back(h);
+      task_len.push_back(std::min<uint32_t>(kTaskLen, rowptr[a + 1] - h));
+    }
+  }
+  node_task_ptr[N] = (uint32_t)task_row.size();
+  s->T = (uint32_t)task_row.size();
+
+  auto up32 = [&](DevBuf<uint32_t>& d, const uint32_t* src, size_t n) -> int {
+    RA_TRY(d.alloc(n));
+    CUDA_TRY(cudaMemcpyAsync(d.p, src, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+    return 0;
+  };
+  auto up64 = [&](DevBuf<double>& d, const double* src, size_t n) -> int {
+    RA_TRY(d.alloc(n));
+    CUDA_TRY(cudaMemcpyAsync(d.p, src, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    return 0;
+  };
+  RA_TRY(up32(s->he_col, he_col.data(), H));
+  RA_TRY(up32(s->he_row, he_row.data(), H));
+  RA_TRY(up32(s->task_row, task_row.data(), s->T));
+  RA_TRY(up32(s->task_begin, task_begin.data(), s->T));
+  RA_TRY(up32(s->task_len, task_len.data(), s->T));
+  RA_TRY(up32(s->node_task_ptr, node_task_ptr.data(), N + 1));
+  RA_TRY(up32(s->d_ei, ei, E));
+  RA_TRY(up32(s->d_ej, ej, E));
+  RA_TRY(up64(s->d_omega_ij, prob->omega_ij + 3 * e0, 3 * E));
+  if (prob->cov6) RA_TRY(up64(s->d_cov6, prob->cov6 + 6 * e0, 6 * E));
+  if (prob->edge_weight) RA_TRY(up64(s->d_weight, prob->edge_weight + e0, E));
+  DevBuf<uint32_t> d_he_edge;
+  RA_TRY(up32(d_he_edge, he_edge.data(), H));
+  RA_TRY(s->qij.alloc(4 * H));
+  RA_TRY(s->U.alloc(6 * H));
+  k_setup_halfedges<<<grid_for(H), kBlock, 0, s->stream>>>(H, d_he_edge.p, s->d_omega_ij.p, s->d_cov6.p, s->d_weight.p, prob->error_type, s->qij.p, s->U.p);
+  s->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  for (int b = 0; b < 2; ++b) {
+    RA_TRY(s->omega[b].alloc(3ull * N));
+    RA_TRY(s->node_q[b].alloc(4ull * N));
+    RA_TRY(s->node_JL[b].alloc(9ull * N));
+    RA_TRY(s->val[b].alloc(9 * H));
+    RA_TRY(s->Hd[b].alloc(6ull * N));
+    RA_TRY(s->gt[b].alloc(3ull * N));
+    RA_TRY(s->ediag[b].alloc(3ull * N));
+    CUDA_TRY(cudaMemsetAsync(s->omega[b].p, 0, 3ull * N * sizeof(double), s->stream));
+  }
+  RA_TRY(s->part.alloc((size_t)s->T * kPartStride));
+  RA_TRY(s->ypart.alloc((size_t)s->T * 3));
+  for (DevBuf<double>* d : {&s->scale, &s->x, &s->r, &s->z, &s->p, &s->y, &s->delta}) RA_TRY(d->alloc(3ull * N));
+  RA_TRY(s->Dblk.alloc(6ull * N));
+  RA_TRY(s->Minv.alloc(6ull * N));
+  RA_TRY(s->slots.alloc((size_t)std::max<unsigned>(grid_for(3ull * N), 64) * 4 + 64));
+  RA_TRY(s->counter.alloc(4));
+  RA_TRY(s->sc.alloc(1));
+  CUDA_TRY(cudaMemsetAsync(s->counter.p, 0, 4 * sizeof(unsigned), s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->sc.p, 0, sizeof(DevScalars), s->stream));
+  CUDA_TRY(cudaMallocHost(&s->h_sc, sizeof(DevScalars)));
+  k_jacobi_scale<<<grid_for(3ull * N), kBlock, 0, s->stream>>>(3 * N, s->ediag[0].p, s->scale.p, 0);
+  s->launches += 1;
+  CUDA_TRY(cudaStreamSynchronize(s->stream));  // host vectors go out of scope
+  s->ms_setup = s->elapsed_since(s->ev[0]);
+  s->radius = options->initial_trust_region_radius;
+  *out = s.release();
+  return 0;
+}
+
+void reset_trust_region(gsfm_ra_solver* s) {
+  s->linearized = false;
+  s->scale_ready = false;
+  s->radius = s->opt.initial_trust_region_radius;
+  s->decrease_factor = 2.0;
+  s->iteration = 0;
+  s->invalid_steps = 0;
+  s->last_successful = false;
+  s->termination = GSFM_RA_TERM_NONE;
+}
+
+void push_trace(gsfm_ra_summary* sum, const gsfm_ra_iteration& it) {
+  if (sum && sum->trace && sum->trace_size < sum->trace_capacity) sum->trace[sum->trace_size++] = it;
+}
+
+// Ceres-1.14 trust-region loop, same order of checks as oracle/ra_oracle.cc.
+// A candidate point is linearised speculatively (full K1 into the other buffer): an accepted step
+// then needs no second evaluation, a rejected one simply keeps the current buffer.
+int iterate(gsfm_ra_solver* s, int max_new_iterations, gsfm_ra_summary* sum) {
+  const gsfm_ra_options& o = s->opt;
+  const double t_start = now_ms();
+  const int64_t launches0 = s->launches;
+  const double asm0 = s->ms_assemble, lin0 = s->ms_linear, cost0 = s->ms_cost;
+  const uint32_t N = s->N;
+  int succ = 0, unsucc = 0;
+  int64_t lin_total = 0;
+  if (sum) sum->trace_size = 0;
+  CUDA_TRY(cudaSetDevice(s->device));
+  if (!s->linearized) {
+    CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
+    CUDA_TRY(cudaMemsetAsync(&s->sc.p->bad, 0, sizeof(int), s->stream));
+    RA_TRY(s->evaluate(s->cur, true));
+    RA_TRY(s->fetch_scalars());
+    s->ms_assemble += s->elapsed_since(s->ev[0]);
+    if (s->h_sc->bad) { set_error("non-finite cost or Jacobian at the initial point"); s->termination = GSFM_RA_TERM_FAILURE; return GSFM_RA_ERR_NUMERIC; }
+    s->x_cost = s->h_sc->cost; s->gmax = s->h_sc->gmax; s->x_norm = std::sqrt(s->h_sc->xnorm2);
+    s->initial_cost = s->x_cost;
+    s->linearized = true;
+    if (!s->scale_ready) {
+      k_jacobi_scale<<<grid_for(3ull * N), kBlock, 0, s->stream>>>(3 * N, s->ediag[s->cur].p, s->scale.p, o.jacobi_scaling);
+      s->launches += 1;
+      s->scale_ready = true;
+    }
+    gsfm_ra_iteration it0;
+    std::memset(&it0, 0, sizeof(it0));
+    it0.cost = s->x_cost; it0.gradient_max_norm = s->gmax; it0.trust_region_radius = s->radius;
+    push_trace(sum, it0);
+    if (s->gmax <= o.gradient_tolerance) s->termination = GSFM_RA_TERM_GRADIENT_TOLERANCE;
+  }
+  int done_here = 0;
+  while (s->termination == GSFM_RA_TERM_NONE && done_here < max_new_iterations) {
+    if (s->iteration >= o.max_num_iterations) { s->termination = GSFM_RA_TERM_MAX_ITERATIONS; break; }
+    if (s->last_successful && s->gmax <= o.gradient_tolerance) { s->termination = GSFM_RA_TERM_GRADIENT_TOLERANCE; break; }
+    if (s->radius <= o.min_trust_region_radius) { s->termination = GSFM_RA_TERM_MIN_RADIUS; break; }
+    ++s->iteration;
+    ++done_here;
+    gsfm_ra_iteration it;
+    std::memset(&it, 0, sizeof(it));
+    it.iteration = s->iteration;
+    const int b = s->cur, c = s->cur ^ 1;
+    // ---- linear solve ------------------------------------------------------------------
+    CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
+    CUDA_TRY(cudaMemsetAsync(&s->sc.p->bad, 0, sizeof(int), s->stream));
+    int lin_it = 0;
+    double lin_res = 0;
+    RA_TRY(s->pcg(b, s->radius, nullptr, nullptr, o.pcg_rtol, o.pcg_max_iterations, &lin_it, &lin_res));
+    const bool breakdown = s->h_sc->pcg_breakdown != 0;
+    it.linear_iterations = lin_it; it.linear_residual = lin_res;
+    lin_total += lin_it;
+    // model decrease and the candidate point
+    RA_TRY(s->spmv(b, s->x.p, s->y.p, s->Hd[b].p));
+    k_apply_step<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[b].p, s->x.p, s->y.p, s->gt[b].p, s->omega[b].p, s->omega[c].p, s->delta.p,
+                                                        s->slots.p, s->counter.p, s->sc.p);
+    s->launches += 1;
+    RA_TRY(s->fetch_scalars());
+    s->ms_linear += s->elapsed_since(s->ev[0]);
+    const double model_change = -s->h_sc->dg - 0.5 * s->h_sc->dHd;
+    it.model_cost_change = model_change;
+    bool valid = !breakdown && !s->h_sc->bad && std::isfinite(model_change) && model_change > 0.0;
+    it.step_is_valid = valid;
+    if (!valid) {
+      it.cost = s->x_cost; it.gradient_max_norm = s->gmax;
+      if (++s->invalid_steps >= 5) { s->termination = GSFM_RA_TERM_INVALID_STEPS; it.trust_region_radius = s->radius; push_trace(sum, it); break; }
+      s->radius *= 0.5;
+      it.trust_region_radius = s->radius;
+      s->last_successful = false;
+      ++unsucc;
+      push_trace(sum, it);
+      continue;
+    }
+    s->invalid_steps = 0;
+    // ---- candidate evaluation (speculative full linearisation) ---------------------------
+    CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
+    RA_TRY(s->evaluate(c, true));
+    RA_TRY(s->fetch_scalars());
+    s->ms_assemble += s->elapsed_since(s->ev[0]);
+    double cand_cost = s->h_sc->cost;
+    const bool cand_bad = s->h_sc->bad != 0 || !std::isfinite(cand_cost);
+    if (cand_bad) cand_cost = DBL_MAX;
+    it.candidate_cost = cand_cost;
+    it.step_norm = std::sqrt(s->h_sc->step2);
+    it.cost_change = s->x_cost - cand_cost;
+    it.relative_decrease = it.cost_change / model_change;
+    it.gradient_max_norm = s->gmax;
+    if (it.step_norm <= o.parameter_tolerance * (s->x_norm + o.parameter_tolerance)) {
+      s->termination = GSFM_RA_TERM_PARAMETER_TOLERANCE; it.cost = s->x_cost; it.trust_region_radius = s->radius; push_trace(sum, it); break;
+    }
+    if (std::fabs(it.cost_change) <= o.function_tolerance * s->x_cost) {
+      s->termination = GSFM_RA_TERM_FUNCTION_TOLERANCE; it.cost = s->x_cost; it.trust_region_radius = s->radius; push_trace(sum, it); break;
+    }
+    if (it.relative_decrease > o.min_relative_decrease && !cand_bad) {
+      s->cur = c;
+      s->x_cost = cand_cost;
+      s->gmax = s->h_sc->gmax;
+      s->x_norm = std::sqrt(s->h_sc->xnorm2);
+      it.gradient_max_norm = s->gmax;
+      it.step_is_successful = 1;
+      const double q = it.relative_decrease;
+      s->radius = s->radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * q - 1.0, 3));
+      s->radius = std::min(o.max_trust_region_radius, s->radius);
+      s->decrease_factor = 2.0;
+      s->last_successful = true;
+      ++succ;
+      it.cost = s->x_cost;
+    } else {
+      s->radius = s->radius / s->decrease_factor;
+      s->decrease_factor *= 2.0;
+      s->last_successful = false;
+      ++unsucc;
+      it.cost = cand_cost;
+    }
+    it.trust_region_radius = s->radius;
+    push_trace(sum, it);
+    if (o.verbose)
+      std::fprintf(stderr, "[gsfm_ra] it %3d cost %.12e dcost %+.3e |g| %.3e |step| %.3e q %.3e radius %.3e pcg %d (%.1e) %s\n", s->iteration, s->x_cost,
+                   it.cost_change, it.gradient_max_norm, it.step_norm, it.relative_decrease, s->radius, lin_it, lin_res, it.step_is_successful ? "ok" : "rejected");
+  }
+  if (sum) {
+    sum->termination = s->termination;
+    sum->num_iterations = s->iteration;
+    sum->num_successful_steps = succ;
+    sum->num_unsuccessful_steps = unsucc;
+    sum->total_linear_iterations = lin_total;
+    sum->initial_cost = s->initial_cost;
+    sum->final_cost = s->x_cost;
+    sum->ms_setup = s->ms_setup;
+    sum->ms_assemble = s->ms_assemble - asm0;
+    sum->ms_linear = s->ms_linear - lin0;
+    sum->ms_cost = s->ms_cost - cost0;
+    sum->ms_total = now_ms() - t_start;
+    sum->kernel_launches = s->launches - launches0;
+  }
+  return 0;
+}
+
+// RAII temp solver for the one-shot API calls
+struct TempSolver {
+  gsfm_ra_solver* s = nullptr;
+  ~TempSolver() { delete s; }
+};
+
+int make_temp(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, const double* omega, int device, TempSolver* t) {
+  gsfm_ra_options o;
+  gsfm_ra_default_options(&o);
+  if (loss) o.loss = *loss;
+  o.device = device;
+  RA_TRY(build_solver(problem, &o, 0, 1, &t->s));
+  if (omega) RA_TRY(gsfm_ra_solver_set_rotations(t->s, omega));
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int gsfm_ra_abi_version(void) { return GSFM_RA_ABI_VERSION; }
+const char* gsfm_ra_last_error(void) { return g_last_error.c_str(); }
+int gsfm_ra_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void gsfm_ra_default_options(gsfm_ra_options* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->loss.kind = GSFM_RA_LOSS_TRIVIAL;
+  o->loss.scale = 1.0;
+  o->max_num_iterations = 200;
+  o->jacobi_scaling = 1;
+  o->function_tolerance = 1e-6;
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->linear_solver = GSFM_RA_SOLVER_PCG;
+  o->pcg_max_iterations = 500;
+  o->pcg_rtol = 1e-10;
+  o->num_threads = 0;
+  o->device = -1;
+  o->verbose = 0;
+}
+
+int gsfm_ra_solver_create(const gsfm_ra_problem* problem, const gsfm_ra_options* options, gsfm_ra_solver** out) {
+  return build_solver(problem, options, 0, 1, out);
+}
+int gsfm_ra_solver_create_sharded(const gsfm_ra_problem* problem, const gsfm_ra_options* options, int32_t rank, int32_t world_size,
+                                  gsfm_ra_solver** out) {
+  if (world_size != 1) { set_error("sharded solver: multi-GPU exchange is not wired up in this build"); return GSFM_RA_ERR_UNSUPPORTED; }
+  return build_solver(problem, options, rank, world_size, out);
+}
+void gsfm_ra_solver_destroy(gsfm_ra_solver* solver) {
+  if (!solver) return;
+  cudaSetDevice(solver->device);
+  delete solver;
+}
+int gsfm_ra_solver_set_rotations(gsfm_ra_solver* s, const double* omega) {
+  if (!s || !omega) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaMemcpyAsync(s->omega[s->cur].p, omega, 3ull * s->N * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  reset_trust_region(s);
+  return 0;
+}
+int gsfm_ra_solver_get_rotations(gsfm_ra_solver* s, double* omega) {
+  if (!s || !omega) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaMemcpyAsync(omega, s->omega[s->cur].p, 3ull * s->N * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+int gsfm_ra_solver_reset(gsfm_ra_solver* s) {
+  if (!s) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
+  reset_trust_region(s);
+  return 0;
+}
+int gsfm_ra_solver_iterate(gsfm_ra_solver* s, int32_t num_iterations, gsfm_ra_summary* summary) {
+  if (!s) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
+  if (s->opt.linear_solver != GSFM_RA_SOLVER_PCG) { set_error("linear solver %d is not implemented (PCG only)", s->opt.linear_solver); return GSFM_RA_ERR_UNSUPPORTED; }
+  return iterate(s, num_iterations, summary);
+}
+int gsfm_ra_solver_ipc_export(gsfm_ra_solver*, uint8_t*) { set_error("peer-memory exchange is not implemented in this build"); return GSFM_RA_ERR_UNSUPPORTED; }
+int gsfm_ra_solver_ipc_import(gsfm_ra_solver*, const uint8_t*) { set_error("peer-memory exchange is not implemented in this build"); return GSFM_RA_ERR_UNSUPPORTED; }
+int gsfm_ra_solver_row_range(const gsfm_ra_solver* s, uint32_t* row_begin, uint32_t* row_end) {
+  if (!s) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
+  if (row_begin) *row_begin = 0;
+  if (row_end) *row_end = s->N;
+  return 0;
+}
+
+void* gsfm_ra_solver_cuda_stream(gsfm_ra_solver* s) { return s ? (void*)s->stream : nullptr; }
+
+int gsfm_ra_solver_time_kernels(gsfm_ra_solver* s, int32_t repeats, double* out_ms) {
+  if (!s || !out_ms || repeats < 1) { set_error("bad argument"); return GSFM_RA_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(s->device));
+  if (!s->linearized) { set_error("time_kernels needs a linearised solver (call iterate first)"); return GSFM_RA_ERR_INVALID; }
+  const int b = s->cur, c = s->cur ^ 1;  // scratch output goes to the candidate buffer
+  auto timed = [&](auto&& launch, double* ms) -> int {
+    launch();  // warm
+    CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
+    for (int k = 0; k < repeats; ++k) launch();
+    CUDA_TRY(cudaGetLastError());
+    *ms = s->elapsed_since(s->ev[0]) / repeats;
+    return 0;
+  };
+  RA_TRY(timed([&] { k_edges<true><<<s->task_grid(), kBlock, 0, s->stream>>>(s->T, s->H, s->task_row.p, s->task_begin.p, s->task_len.p, s->he_col.p, s->qij.p, s->U.p, s->node_q[b].p, s->loss, s->val[c].p, s->part.p); }, &out_ms[0]));
+  RA_TRY(timed([&] { k_edges<false><<<s->task_grid(), kBlock, 0, s->stream>>>(s->T, s->H, s->task_row.p, s->task_begin.p, s->task_len.p, s->he_col.p, s->qij.p, s->U.p, s->node_q[b].p, s->loss, nullptr, s->part.p); }, &out_ms[1]));
+  CUDA_TRY(cudaMemsetAsync(s->z.p, 0, 3ull * s->N * sizeof(double), s->stream));
+  RA_TRY(timed([&] { k_spmv<<<s->task_grid(), kBlock, 0, s->stream>>>(s->T, s->H, s->task_begin.p, s->task_len.p, s->he_col.p, s->val[b].p, s->z.p, s->ypart.p, s->sc.p, 0); }, &out_ms[2]));
+  // one PCG iteration: state is re-initialised first so pcg_done is clear, rtol 0 keeps it running
+  k_prepare_solve<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->radius, s->opt.min_lm_diagonal, s->opt.max_lm_diagonal, s->ediag[b].p, s->scale.p, s->node_JL[b].p,
+                                                          s->Hd[b].p, s->gt[b].p, nullptr, nullptr, s->Dblk.p, s->Minv.p, s->x.p, s->r.p, s->z.p, s->p.p, s->slots.p, s->counter.p, s->sc.p);
+  RA_TRY(timed([&] {
+    k_spmv<<<s->task_grid(), kBlock, 0, s->stream>>>(s->T, s->H, s->task_begin.p, s->task_len.p, s->he_col.p, s->val[b].p, s->p.p, s->ypart.p, s->sc.p, 1);
+    k_spmv_finish<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->node_task_ptr.p, s->ypart.p, s->Dblk.p, s->p.p, s->y.p, 0, s->slots.p, s->counter.p, s->sc.p);
+    k_pcg_update<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->Minv.p, s->p.p, s->y.p, s->x.p, s->r.p, s->z.p, 0.0, 1 << 30, s->slots.p, s->counter.p, s->sc.p);
+    k_pcg_direction<<<grid_for(3ull * s->N), kBlock, 0, s->stream>>>(3 * s->N, s->z.p, s->p.p, s->sc.p);
+  }, &out_ms[3]));
+  // restore the linearisation-dependent partials (K1 scratch wrote `part`): re-run the finalize inputs
+  RA_TRY(s->evaluate(b, true));
+  RA_TRY(s->fetch_scalars());
+  return 0;
+}
+
+int gsfm_ra_solve(const gsfm_ra_problem* problem, const gsfm_ra_options* options, double* omega_inout, gsfm_ra_summary* summary) {
+  if (!omega_inout) { set_error("omega_inout is NULL"); return GSFM_RA_ERR_INVALID; }
+  const double t0 = now_ms();
+  TempSolver t;
+  RA_TRY(build_solver(problem, options, 0, 1, &t.s));
+  RA_TRY(gsfm_ra_solver_set_rotations(t.s, omega_inout));
+  const int rc = gsfm_ra_solver_iterate(t.s, options->max_num_iterations + 1, summary);
+  if (rc != 0 && rc != GSFM_RA_ERR_NUMERIC) return rc;
+  RA_TRY(gsfm_ra_solver_get_rotations(t.s, omega_inout));
+  if (summary) summary->ms_total = now_ms() - t0;
+  return rc;
+}
+
+int gsfm_ra_eval_edges(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, const double* omega, double* r, double* jac_i, double* jac_j,
+                       double* rho, int32_t device) {
+  if (!omega) { set_error("omega is NULL"); return GSFM_RA_ERR_INVALID; }
+  TempSolver t;
+  RA_TRY(make_temp(problem, loss, omega, device, &t));
+  gsfm_ra_solver* s = t.s;
+  const uint64_t E = s->E;
+  DevBuf<double> dr, dji, djj, drho;
+  if (r) RA_TRY(dr.alloc(3 * E));
+  if (jac_i) RA_TRY(dji.alloc(9 * E));
+  if (jac_j) RA_TRY(djj.alloc(9 * E));
+  if (rho) RA_TRY(drho.alloc(3 * E));
+  k_node_prep<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->omega[0].p, s->node_q[0].p, s->node_JL[0].p, s->slots.p, s->counter.p, s->sc.p);
+  k_eval_edges<<<grid_for(E), kBlock, 0, s->stream>>>(E, s->d_ei.p, s->d_ej.p, s->d_omega_ij.p, s->d_cov6.p, s->d_weight.p, s->error_type,
+                                                      s->node_q[0].p, s->node_JL[0].p, s->loss, dr.p, dji.p, djj.p, drho.p);
+  CUDA_TRY(cudaGetLastError());
+  if (r) CUDA_TRY(cudaMemcpyAsync(r, dr.p, 3 * E * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (jac_i) CUDA_TRY(cudaMemcpyAsync(jac_i, dji.p, 9 * E * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (jac_j) CUDA_TRY(cudaMemcpyAsync(jac_j, djj.p, 9 * E * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (rho) CUDA_TRY(cudaMemcpyAsync(rho, drho.p, 3 * E * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int gsfm_ra_whiten(const gsfm_ra_problem* problem, double* U, int32_t device) {
+  RA_TRY(check_problem(problem));
+  if (!U) { set_error("U is NULL"); return GSFM_RA_ERR_INVALID; }
+  int dev;
+  RA_TRY(select_device(device, &dev));
+  const uint64_t E = problem->num_edges;
+  DevBuf<double> dc, dw, du;
+  if (problem->cov6) { RA_TRY(dc.alloc(6 * E)); CUDA_TRY(cudaMemcpy(dc.p, problem->cov6, 6 * E * sizeof(double), cudaMemcpyHostToDevice)); }
+  if (problem->edge_weight) { RA_TRY(dw.alloc(E)); CUDA_TRY(cudaMemcpy(dw.p, problem->edge_weight, E * sizeof(double), cudaMemcpyHostToDevice)); }
+  RA_TRY(du.alloc(9 * E));
+  k_whiten_edges<<<grid_for(E), kBlock>>>(E, dc.p, dw.p, problem->error_type, du.p);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(U, du.p, 9 * E * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int gsfm_ra_assemble(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, const double* omega, double* cost, double* gradient, double* hdiag,
+                     uint32_t* rowptr, uint32_t* col, double* val, int32_t device) {
+  if (!omega) { set_error("omega is NULL"); return GSFM_RA_ERR_INVALID; }
+  TempSolver t;
+  RA_TRY(make_temp(problem, loss, omega, device, &t));
+  gsfm_ra_solver* s = t.s;
+  RA_TRY(s->evaluate(0, true));
+  RA_TRY(s->fetch_scalars());
+  if (cost) *cost = s->h_sc->cost;
+  const uint32_t N = s->N;
+  const uint64_t H = s->H;
+  DevBuf<double> dval, dh, dg;
+  DevBuf<uint32_t> dcol;
+  if (val || col) {
+    RA_TRY(dval.alloc(9 * H));
+    RA_TRY(dcol.alloc(H));
+    k_export_blocks<<<grid_for(H), kBlock, 0, s->stream>>>(H, s->he_row.p, s->he_col.p, s->val[0].p, s->node_JL[0].p, dval.p, dcol.p);
+    CUDA_TRY(cudaGetLastError());
+    if (val) CUDA_TRY(cudaMemcpyAsync(val, dval.p, 9 * H * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (col) CUDA_TRY(cudaMemcpyAsync(col, dcol.p, H * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  }
+  if (hdiag || gradient) {
+    RA_TRY(dh.alloc(9ull * N));
+    RA_TRY(dg.alloc(3ull * N));
+    k_export_nodes<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->Hd[0].p, s->gt[0].p, s->node_JL[0].p, dh.p, dg.p);
+    CUDA_TRY(cudaGetLastError());
+    if (hdiag) CUDA_TRY(cudaMemcpyAsync(hdiag, dh.p, 9ull * N * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (gradient) CUDA_TRY(cudaMemcpyAsync(gradient, dg.p, 3ull * N * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if (rowptr) {
+    std::vector<uint32_t> he_row(H);
+    CUDA_TRY(cudaMemcpy(he_row.data(), s->he_row.p, H * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    std::fill(rowptr, rowptr + N + 1, 0u);
+    for (uint64_t h = 0; h < H; ++h) rowptr[he_row[h] + 1]++;
+    for (uint32_t a = 0; a < N; ++a) rowptr[a + 1] += rowptr[a];
+  }
+  return 0;
+}
+
+int gsfm_ra_cost(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, const double* omega, double* cost, int32_t device) {
+  if (!omega || !cost) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
+  TempSolver t;
+  RA_TRY(make_temp(problem, loss, omega, device, &t));
+  RA_TRY(t.s->evaluate(0, false));
+  RA_TRY(t.s->fetch_scalars());
+  *cost = t.s->h_sc->cost;
+  return 0;
+}
+
+int gsfm_ra_spmv(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, const double* omega, const double* damping, const double* x, double* y,
+                 int32_t device) {
+  if (!omega || !x || !y) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
+  TempSolver t;
+  RA_TRY(make_temp(problem, loss, omega, device, &t));
+  gsfm_ra_solver* s = t.s;
+  const uint32_t N = s->N;
+  RA_TRY(s->evaluate(0, true));
+  DevBuf<double> dx, dd;
+  RA_TRY(dx.alloc(3ull * N));
+  CUDA_TRY(cudaMemcpyAsync(dx.p, x, 3ull * N * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  if (damping) { RA_TRY(dd.alloc(3ull * N)); CUDA_TRY(cudaMemcpyAsync(dd.p, damping, 3ull * N * sizeof(double), cudaMemcpyHostToDevice, s->stream)); }
+  // y = Jl^T Ht (Jl x) + damping .* x
+  k_node_apply<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[0].p, dx.p, 0, nullptr, nullptr, s->p.p);
+  RA_TRY(s->spmv(0, s->p.p, s->y.p, s->Hd[0].p));
+  k_node_apply<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[0].p, s->y.p, 1, dd.p, dx.p, s->z.p);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(y, s->z.p, 3ull * N * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int gsfm_ra_pcg(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, const double* omega, const double* damping, const double* b, double rtol,
+                int32_t max_iterations, double* x, int32_t* iterations, double* rel_residual, int32_t device) {
+  if (!omega || !b || !x) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
+  TempSolver t;
+  RA_TRY(make_temp(problem, loss, omega, device, &t));
+  gsfm_ra_solver* s = t.s;
+  const uint32_t N = s->N;
+  RA_TRY(s->evaluate(0, true));
+  DevBuf<double> db, dd;
+  RA_TRY(db.alloc(3ull * N));
+  RA_TRY(dd.alloc(3ull * N));
+  CUDA_TRY(cudaMemcpyAsync(db.p, b, 3ull * N * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  if (damping) CUDA_TRY(cudaMemcpyAsync(dd.p, damping, 3ull * N * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  else CUDA_TRY(cudaMemsetAsync(dd.p, 0, 3ull * N * sizeof(double), s->stream));
+  int it = 0;
+  double res = 0;
+  RA_TRY(s->pcg(0, 1.0, dd.p, db.p, rtol, max_iterations, &it, &res));
+  // x = Jl^-1 xt
+  k_apply_step<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[0].p, s->x.p, nullptr, nullptr, nullptr, nullptr, s->delta.p, s->slots.p, s->counter.p, s->sc.p);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(x, s->delta.p, 3ull * N * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if (iterations) *iterations = it;
+  if (rel_residual) *rel_residual = res;
+  return 0;
+}
+
+int gsfm_ra_eval_loss(const gsfm_ra_loss* loss, const double* s_in, uint64_t n, double* out, int32_t device) {
+  if (!loss || !s_in || !out) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
+  int dev;
+  RA_TRY(select_device(device, &dev));
+  DevLoss L;
+  RA_TRY(make_dev_loss(loss, &L));
+  if (n == 0) return 0;
+  DevBuf<double> ds, dout;
+  RA_TRY(ds.alloc(n));
+  RA_TRY(dout.alloc(3 * n));
+  CUDA_TRY(cudaMemcpy(ds.p, s_in, n * sizeof(double), cudaMemcpyHostToDevice));
+  k_eval_loss<<<grid_for(n), kBlock>>>(n, ds.p, L, dout.p);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(out, dout.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int gsfm_ra_filter_view_pairs(const gsfm_ra_problem* problem, const double* omega, double max_degrees, uint8_t* keep, double* angle_rad,
+                              int32_t device) {
+  if (!omega || !problem) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
+  if (!(max_degrees >= 0.0)) { set_error("max_relative_rotation_difference_degrees must be >= 0"); return GSFM_RA_ERR_INVALID; }
+  gsfm_ra_problem p2 = *problem;
+  p2.error_type = GSFM_RA_ANGLE_AXIS;
+  TempSolver t;
+  RA_TRY(make_temp(&p2, nullptr, omega, device, &t));
+  gsfm_ra_solver* s = t.s;
+  const uint64_t E = s->E;
+  DevBuf<uint8_t> dk;
+  DevBuf<double> da;
+  RA_TRY(dk.alloc(E));
+  RA_TRY(da.alloc(E));
+  const double thr = max_degrees * M_PI / 180.0;
+  k_node_prep<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->omega[0].p, s->node_q[0].p, s->node_JL[0].p, s->slots.p, s->counter.p, s->sc.p);
+  k_filter_pairs<<<grid_for(E), kBlock, 0, s->stream>>>(E, s->d_ei.p, s->d_ej.p, s->d_omega_ij.p, s->node_q[0].p, thr * thr, dk.p, da.p);
+  CUDA_TRY(cudaGetLastError());
+  if (keep) CUDA_TRY(cudaMemcpyAsync(keep, dk.p, E, cudaMemcpyDeviceToHost, s->stream));
+  if (angle_rad) CUDA_TRY(cudaMemcpyAsync(angle_rad, da.p, E * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+}  // extern "C"

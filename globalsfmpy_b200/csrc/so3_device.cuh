@@ -1,0 +1,382 @@
+// so3_device.cuh -- device-side SO(3) algebra and robust losses for the rotation-averaging kernels.
+//
+// What it replaces (reference, CPU): one ceres::AutoDiffCostFunction evaluation of
+//   PairwiseRotationErrorAngleAxis   include/pairwise_rotation_error_quat.hpp:215-247
+//   theia::PairwiseRotationError     T/sfm/global_pose_estimation/pairwise_rotation_error.h:66-95
+// plus one Python LossFunction.Evaluate (scripts/loss_functions.py) per edge per evaluation.
+//
+// Design (not a translation): rotations travel as unit quaternions (w,x,y,z), the residual
+// e = Log(R_j R_i^T R_ij^T) comes straight from a quaternion product, and the Jacobians are the
+// closed-form SO(3) ones in the LEFT TANGENT frame:
+//     de/d(delta_j) = Jl^-1(e)            de/d(delta_i) = -Jl^-1(e) * (R_j R_i^T)
+// (R <- Exp(delta) R).  The reference differentiates w.r.t. the angle-axis vector omega itself;
+// d(delta) = Jl(omega) d(omega), a per-VIEW 3x3 factor that the solver applies once per view
+// (node kernels) instead of once per edge.  All fp64.
+#pragma once
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+
+namespace gsfm {
+
+struct Q4 { double w, x, y, z; };
+
+__host__ __device__ inline Q4 qmul(const Q4& a, const Q4& b) {
+  Q4 r;
+  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+  r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  r.y = a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x;
+  r.z = a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w;
+  return r;
+}
+__host__ __device__ inline Q4 qconj(const Q4& a) { return Q4{a.w, -a.x, -a.y, -a.z}; }
+
+// Angle-axis -> unit quaternion (ceres AngleAxisToQuaternion: half-angle form, first-order below).
+__host__ __device__ inline Q4 aa_to_quat(double wx, double wy, double wz) {
+  const double t2 = wx * wx + wy * wy + wz * wz;
+  if (t2 > 0.0) {
+    const double t = sqrt(t2);
+    double sh, ch;
+    sincos(0.5 * t, &sh, &ch);
+    const double k = sh / t;
+    return Q4{ch, wx * k, wy * k, wz * k};
+  }
+  return Q4{1.0, 0.5 * wx, 0.5 * wy, 0.5 * wz};
+}
+
+// Unit quaternion -> rotation matrix, row-major.
+__host__ __device__ inline void quat_to_mat(const Q4& q, double* R) {
+  const double xx = q.x * q.x, yy = q.y * q.y, zz = q.z * q.z;
+  const double xy = q.x * q.y, xz = q.x * q.z, yz = q.y * q.z;
+  const double wx = q.w * q.x, wy = q.w * q.y, wz = q.w * q.z;
+  R[0] = 1.0 - 2.0 * (yy + zz); R[1] = 2.0 * (xy - wz);       R[2] = 2.0 * (xz + wy);
+  R[3] = 2.0 * (xy + wz);       R[4] = 1.0 - 2.0 * (xx + zz); R[5] = 2.0 * (yz - wx);
+  R[6] = 2.0 * (xz - wy);       R[7] = 2.0 * (yz + wx);       R[8] = 1.0 - 2.0 * (xx + yy);
+}
+
+// Log of a unit quaternion as a rotation vector with angle in [0, pi] (ceres QuaternionToAngleAxis),
+// also returning c(theta) of Jl^-1(e) = I - [e]x/2 + c [e]x^2,
+//   c = 1/theta^2 - cot(theta/2)/(2 theta),  cot(theta/2) = w/|v| (no trigonometry needed).
+__host__ __device__ inline void quat_log(Q4 q, double* e, double* theta2_out, double* c_out) {
+  if (q.w < 0.0) { q.w = -q.w; q.x = -q.x; q.y = -q.y; q.z = -q.z; }
+  const double s2 = q.x * q.x + q.y * q.y + q.z * q.z;
+  double k = 2.0, theta2 = 0.0, c = 1.0 / 12.0;
+  if (s2 > 0.0) {
+    const double s = sqrt(s2);
+    const double theta = 2.0 * atan2(s, q.w);
+    k = theta / s;
+    theta2 = theta * theta;
+    if (theta2 < 1e-2) {
+      c = 1.0 / 12.0 + theta2 * (1.0 / 720.0 + theta2 * (1.0 / 30240.0 + theta2 * (1.0 / 1209600.0 + theta2 * (1.0 / 47900160.0))));
+    } else {
+      c = 1.0 / theta2 - q.w / (2.0 * theta * s);
+    }
+  }
+  e[0] = q.x * k; e[1] = q.y * k; e[2] = q.z * k;
+  *theta2_out = theta2;
+  *c_out = c;
+}
+
+// Left Jacobian of SO(3) at omega, row-major: Jl = I + a [w]x + b [w]x^2,
+// a = (1-cos t)/t^2 = 2 sin^2(t/2)/t^2, b = (t - sin t)/t^3.
+__host__ __device__ inline void so3_left_jacobian(double wx, double wy, double wz, double* J) {
+  const double t2 = wx * wx + wy * wy + wz * wz;
+  double a, b;
+  if (t2 < 0.04) {
+    a = 0.5 + t2 * (-1.0 / 24.0 + t2 * (1.0 / 720.0 + t2 * (-1.0 / 40320.0 + t2 * (1.0 / 3628800.0 + t2 * (-1.0 / 479001600.0)))));
+    b = 1.0 / 6.0 + t2 * (-1.0 / 120.0 + t2 * (1.0 / 5040.0 + t2 * (-1.0 / 362880.0 + t2 * (1.0 / 39916800.0 + t2 * (-1.0 / 6227020800.0)))));
+  } else {
+    const double t = sqrt(t2);
+    double sh, ch;
+    sincos(0.5 * t, &sh, &ch);
+    a = 2.0 * sh * sh / t2;
+    b = (t - 2.0 * sh * ch) / (t2 * t);
+  }
+  // [w]x^2 = w w^T - t2 I
+  J[0] = 1.0 + b * (wx * wx - t2); J[1] = -a * wz + b * wx * wy;    J[2] = a * wy + b * wx * wz;
+  J[3] = a * wz + b * wx * wy;     J[4] = 1.0 + b * (wy * wy - t2); J[5] = -a * wx + b * wy * wz;
+  J[6] = -a * wy + b * wx * wz;    J[7] = a * wx + b * wy * wz;     J[8] = 1.0 + b * (wz * wz - t2);
+}
+
+__host__ __device__ inline bool inv3(const double* A, double* inv) {
+  const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+  const double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
+  const double id = 1.0 / det;
+  inv[0] = c00 * id; inv[1] = (A[2] * A[7] - A[1] * A[8]) * id; inv[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+  inv[3] = c01 * id; inv[4] = (A[0] * A[8] - A[2] * A[6]) * id; inv[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+  inv[6] = c02 * id; inv[7] = (A[1] * A[6] - A[0] * A[7]) * id; inv[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+  return det != 0.0 && isfinite(id);
+}
+
+// symmetric 3x3 packed as (00,01,02,11,12,22)
+__host__ __device__ inline void sym_inv(const double* S, double* inv) {
+  const double c00 = S[3] * S[5] - S[4] * S[4], c01 = S[2] * S[4] - S[1] * S[5], c02 = S[1] * S[4] - S[2] * S[3];
+  const double det = S[0] * c00 + S[1] * c01 + S[2] * c02;
+  const double id = 1.0 / det;
+  inv[0] = c00 * id; inv[1] = c01 * id; inv[2] = c02 * id;
+  inv[3] = (S[0] * S[5] - S[2] * S[2]) * id; inv[4] = (S[1] * S[2] - S[0] * S[4]) * id;
+  inv[5] = (S[0] * S[3] - S[1] * S[1]) * id;
+}
+__host__ __device__ inline void sym_mul_vec(const double* S, const double* x, double* y) {
+  y[0] = S[0] * x[0] + S[1] * x[1] + S[2] * x[2];
+  y[1] = S[1] * x[0] + S[3] * x[1] + S[4] * x[2];
+  y[2] = S[2] * x[0] + S[4] * x[1] + S[5] * x[2];
+}
+// B^T S B for general B (row-major) and packed symmetric S; packed symmetric result.
+__host__ __device__ inline void congruence(const double* B, const double* S, double* out) {
+  double T[9];  // T = S B
+  for (int c = 0; c < 3; ++c) {
+    T[c] = S[0] * B[c] + S[1] * B[3 + c] + S[2] * B[6 + c];
+    T[3 + c] = S[1] * B[c] + S[3] * B[3 + c] + S[4] * B[6 + c];
+    T[6 + c] = S[2] * B[c] + S[4] * B[3 + c] + S[5] * B[6 + c];
+  }
+  out[0] = B[0] * T[0] + B[3] * T[3] + B[6] * T[6];
+  out[1] = B[0] * T[1] + B[3] * T[4] + B[6] * T[7];
+  out[2] = B[0] * T[2] + B[3] * T[5] + B[6] * T[8];
+  out[3] = B[1] * T[1] + B[4] * T[4] + B[7] * T[7];
+  out[4] = B[1] * T[2] + B[4] * T[5] + B[7] * T[8];
+  out[5] = B[2] * T[2] + B[5] * T[5] + B[8] * T[8];
+}
+
+// ------------------------------------------------------------------------------------------
+// Robust losses, scripts/loss_functions.py (line numbers per kind in include/gsfm_ra.h).
+// ------------------------------------------------------------------------------------------
+struct DevLoss {
+  int kind;
+  unsigned flags;
+  double p0, p1, scale;
+  // MAGSAC (scripts/loss_functions.py:285-459), constants of include/gamma_values.cpp
+  int nu;
+  int table_size;
+  double clamp_s;             // sigma_quantile^2 * sigma^2
+  double sq_sigma;            // sigma^2
+  double sq_sigma_max_2;      // 2 sigma^2
+  double cubed_sigma;         // sigma^3
+  double Ctd;                 // C * 2^((nu-1)/2)
+  double one_over_sigma;      // Ctd / sigma
+  double gamma_k;             // upper_incomplete_gamma_of_k
+  double weight_zero;         // one_over_sigma * (tgamma((nu-1)/2) - gamma_k)
+  double expo;                // nu/2 - 1.5
+};
+
+enum { kLossTrivial = 0, kLossHuber, kLossSoftLOne, kLossCauchy, kLossArctan, kLossTolerant, kLossTukey,
+       kLossLOneHalf, kLossLTwo, kLossGemanMcClure, kLossMagsac3, kLossMagsac4, kLossMagsac9 };
+
+// stored_gamma_values{nu}[index] = Gamma((nu-1)/2, index/1000), closed forms
+__host__ __device__ inline double gamma_table(int nu, double x) {
+  if (nu == 3) return exp(-x);
+  if (nu == 4) return 0.88622692545275801365 * erfc(sqrt(x)) + sqrt(x) * exp(-x);
+  return exp(-x) * (((x + 3.0) * x + 6.0) * x + 6.0);
+}
+
+__host__ __device__ inline double pow_expo(double b, int nu) {
+  // (s/2sigma^2)^(nu/2-1.5): nu=3 -> b^0 = 1 (also at b = 0), nu=4 -> sqrt(b), nu=9 -> b^3
+  if (nu == 3) return 1.0;
+  if (nu == 4) return sqrt(b);
+  return b * b * b;
+}
+
+__host__ __device__ inline void magsac_loss(const DevLoss& L, double s_in, double* rho) {
+  double sr = s_in;
+  bool zero_derivative = false;
+  if (sr > L.clamp_s) { sr = L.clamp_s; zero_derivative = true; }
+  double xr = rint(1000.0 * sr / L.sq_sigma_max_2);  // Python round(): half to even
+  if ((double)L.table_size < xr) xr = (double)L.table_size;
+  double s = xr * L.sq_sigma_max_2 / 1000.0;
+  const double weight = L.one_over_sigma * (gamma_table(L.nu, xr / 1000.0) - L.gamma_k);
+  const double ex = exp(-s / L.sq_sigma_max_2);
+  const double wd = -L.Ctd * pow_expo(s / L.sq_sigma_max_2, L.nu) * ex / (2.0 * L.cubed_sigma);
+  if (s < 1e-7) s = 1e-7;
+  const double wdd = 2.0 * L.Ctd * pow_expo(s / L.sq_sigma_max_2, L.nu) * (1.0 / L.sq_sigma - ((double)L.nu - 3.0) / s) *
+                     exp(-s / L.sq_sigma_max_2) / (8.0 * L.cubed_sigma);
+  if (L.flags & 1u) {
+    rho[0] = 1.0 / weight;
+    rho[1] = -1.0 / (weight * weight) * wd;
+    rho[2] = 2.0 / (weight * weight * weight) * wd * wd - wdd / (weight * weight);
+    if (zero_derivative) { rho[1] = 0.00001; rho[2] = 0.0; }
+  } else {
+    rho[0] = L.weight_zero - weight;
+    rho[1] = -wd;
+    rho[2] = -wdd;
+    if (rho[1] == 0.0) rho[1] = 0.00001;
+    if (zero_derivative) { rho[1] = 0.00001; rho[2] = 0.0; }
+  }
+}
+
+__host__ __device__ inline void eval_loss(const DevLoss& L, double s, double* out) {
+  switch (L.kind) {
+    case kLossTrivial: out[0] = s; out[1] = 1.0; out[2] = 0.0; break;
+    case kLossHuber: {
+      const double a = L.p0, b = a * a;
+      if (s > b) { const double r = sqrt(s); out[0] = 2.0 * a * r - b; out[1] = fmax(a / r, DBL_MIN); out[2] = -out[1] / (2.0 * s); }
+      else { out[0] = s; out[1] = 1.0; out[2] = 0.0; }
+      break;
+    }
+    case kLossSoftLOne: {
+      const double b = L.p0 * L.p0, c = 1.0 / b;
+      const double sum = 1.0 + s * c, tmp = sqrt(sum);
+      out[0] = 2.0 * b * (tmp - 1.0); out[1] = fmax(1.0 / tmp, DBL_MIN); out[2] = -(c * out[1]) / (2.0 * sum);
+      break;
+    }
+    case kLossCauchy: {
+      const double b = L.p0 * L.p0, c = 1.0 / b;
+      const double sum = 1.0 + s * c, inv = 1.0 / sum;
+      out[0] = b * log(sum); out[1] = fmax(inv, DBL_MIN); out[2] = -c * (inv * inv);
+      break;
+    }
+    case kLossArctan: {
+      const double a = L.p0, b = 1.0 / (a * a);
+      const double sum = 1.0 + s * s * b, inv = 1.0 / sum;
+      out[0] = a * atan2(s, a); out[1] = fmax(inv, DBL_MIN); out[2] = -2.0 * s * b * (inv * inv);
+      break;
+    }
+    case kLossTolerant: {
+      const double a = L.p0, b = L.p1, c = b * log(1.0 + exp(-a / b));
+      const double x = (s - a) / b;
+      if (x > 36.7) { out[0] = s - a - c; out[1] = 1.0; out[2] = 0.0; }
+      else { const double e_x = exp(x); out[0] = b * log(1.0 + e_x) - c; out[1] = fmax(e_x / (1.0 + e_x), DBL_MIN); out[2] = 0.5 / (b * (1.0 + cosh(x))); }
+      break;
+    }
+    case kLossTukey: {
+      const double a2 = L.p0 * L.p0;
+      if (s <= a2) { const double v = 1.0 - s / a2, v2 = v * v; out[0] = a2 / 6.0 * (1.0 - v2 * v); out[1] = 0.5 * v2; out[2] = -1.0 / a2 * v; }
+      else { out[0] = a2 / 6.0; out[1] = 0.0; out[2] = 0.0; }
+      break;
+    }
+    case kLossLOneHalf: {
+      const double a = L.p0, sa = sqrt(a);
+      out[0] = 2.0 * a * sa * pow(s, 0.25);
+      if (s < 0.01) s = 0.01;
+      out[1] = 0.5 * pow(a, -1.5) * pow(s, -0.75);
+      out[2] = -0.375 * a * sa * pow(s, -1.75);
+      break;
+    }
+    case kLossLTwo: {
+      const double a2 = L.p0 * L.p0;
+      out[0] = s * s / (a2 * 2.0); out[1] = s / a2; out[2] = 1.0 / a2;
+      break;
+    }
+    case kLossGemanMcClure: {
+      const double a2 = L.p0 * L.p0, sg = L.p1;
+      const double d = s / a2 + sg;
+      out[0] = a2 * sg * s / (2.0 * (s + a2 * sg));
+      out[1] = (sg * sg) / (2.0 * d * d);
+      out[2] = -(sg * sg) / (a2 * d * d * d);
+      break;
+    }
+    case kLossMagsac3: case kLossMagsac4: case kLossMagsac9: magsac_loss(L, s, out); break;
+    default: out[0] = out[1] = out[2] = NAN;
+  }
+  if (L.scale != 1.0 && L.scale != 0.0) { out[0] *= L.scale; out[1] *= L.scale; out[2] *= L.scale; }
+}
+
+// ------------------------------------------------------------------------------------------
+// One relative-rotation constraint.  Inputs: endpoint quaternions, the measured q_ij, the upper
+// triangular weight U (packed u00 u01 u02 u11 u12 u22).  Outputs, all in the left tangent frame
+// of view j (A = U Jl^-1(e) is d r / d delta_j; d r / d delta_i = -A Q, Q = R_j R_i^T):
+//   r = U e, rho[3] = loss(|r|^2),
+//   W = rho' (A^T A - kappa u u^T), u = A^T r   -- robustified J~_j^T J~_j incl. the Triggs term
+//   v = rho' u                                  -- J~_j^T r~
+// (Ceres Corrector, SURVEY Appendix B.2: J~ = sqrt(rho')(I - alpha/s r r^T) J, r~ = sqrt(rho')/(1-alpha) r
+//  =>  J~^T J~ = rho' J^T (I - kappa r r^T) J with kappa = (2 alpha - alpha^2)/s, and J~^T r~ = rho' J^T r.)
+// ------------------------------------------------------------------------------------------
+struct EdgeTerms {
+  double r[3];
+  double A[9];
+  double Q[9];
+  double W[6];
+  double v[3];
+  double rho[3];
+};
+
+template <bool kNeedJacobian>
+__host__ __device__ inline void edge_terms(const Q4& qi, const Q4& qj, const Q4& qij, const double* U, const DevLoss& L, EdgeTerms& o) {
+  const Q4 qL = qmul(qj, qconj(qi));   // loop rotation R_j R_i^T
+  const Q4 qE = qmul(qL, qconj(qij));  // error rotation R_j R_i^T R_ij^T
+  double e[3], theta2, c;
+  quat_log(qE, e, &theta2, &c);
+  o.r[0] = U[0] * e[0] + U[1] * e[1] + U[2] * e[2];
+  o.r[1] = U[3] * e[1] + U[4] * e[2];
+  o.r[2] = U[5] * e[2];
+  const double s = o.r[0] * o.r[0] + o.r[1] * o.r[1] + o.r[2] * o.r[2];
+  eval_loss(L, s, o.rho);
+  if (!kNeedJacobian) return;
+  // Jl^-1(e) = I - [e]x/2 + c (e e^T - theta2 I)
+  double Ji[9];
+  const double d = 1.0 - c * theta2;
+  Ji[0] = d + c * e[0] * e[0];           Ji[1] = 0.5 * e[2] + c * e[0] * e[1];  Ji[2] = -0.5 * e[1] + c * e[0] * e[2];
+  Ji[3] = -0.5 * e[2] + c * e[0] * e[1]; Ji[4] = d + c * e[1] * e[1];           Ji[5] = 0.5 * e[0] + c * e[1] * e[2];
+  Ji[6] = 0.5 * e[1] + c * e[0] * e[2];  Ji[7] = -0.5 * e[0] + c * e[1] * e[2]; Ji[8] = d + c * e[2] * e[2];
+#pragma unroll
+  for (int cc = 0; cc < 3; ++cc) {
+    o.A[cc] = U[0] * Ji[cc] + U[1] * Ji[3 + cc] + U[2] * Ji[6 + cc];
+    o.A[3 + cc] = U[3] * Ji[3 + cc] + U[4] * Ji[6 + cc];
+    o.A[6 + cc] = U[5] * Ji[6 + cc];
+  }
+  quat_to_mat(qL, o.Q);
+  double u[3];
+#pragma unroll
+  for (int cc = 0; cc < 3; ++cc) u[cc] = o.A[cc] * o.r[0] + o.A[3 + cc] * o.r[1] + o.A[6 + cc] * o.r[2];
+  double kappa = 0.0;
+  const double rho1 = o.rho[1];
+  if (s != 0.0 && o.rho[2] > 0.0) {
+    const double D = 1.0 + 2.0 * s * o.rho[2] / rho1;
+    const double alpha = 1.0 - ((D > 0.0) ? sqrt(D) : 0.0);
+    kappa = (2.0 * alpha - alpha * alpha) / s;
+  }
+  const double* A = o.A;
+  o.W[0] = rho1 * (A[0] * A[0] + A[3] * A[3] + A[6] * A[6] - kappa * u[0] * u[0]);
+  o.W[1] = rho1 * (A[0] * A[1] + A[3] * A[4] + A[6] * A[7] - kappa * u[0] * u[1]);
+  o.W[2] = rho1 * (A[0] * A[2] + A[3] * A[5] + A[6] * A[8] - kappa * u[0] * u[2]);
+  o.W[3] = rho1 * (A[1] * A[1] + A[4] * A[4] + A[7] * A[7] - kappa * u[1] * u[1]);
+  o.W[4] = rho1 * (A[1] * A[2] + A[4] * A[5] + A[7] * A[8] - kappa * u[1] * u[2]);
+  o.W[5] = rho1 * (A[2] * A[2] + A[5] * A[5] + A[8] * A[8] - kappa * u[2] * u[2]);
+  o.v[0] = rho1 * u[0]; o.v[1] = rho1 * u[1]; o.v[2] = rho1 * u[2];
+}
+
+// Whitening, src/GSfM_nonlinear_rotation_estimator.cpp:251-288:
+// U = chol((1e8 Sigma)^-1)^T for the covariance types, scalar otherwise; times edge_weight.
+// The cofactor inverse of a covariance with condition number up to 1e12 loses
+// cond * eps digits, so the RESULT depends on the exact operation sequence.  The sequence below is
+// evaluated with individually rounded multiplies/adds (no FMA contraction): bit-identical to the
+// CPU restatement (oracle/ra_oracle.cc Whiten) by construction; sqrt and division are IEEE on both.
+#ifdef __CUDA_ARCH__
+#define GSFM_MUL(a, b) __dmul_rn((a), (b))
+#define GSFM_ADD(a, b) __dadd_rn((a), (b))
+#define GSFM_SUB(a, b) __dsub_rn((a), (b))
+#else
+#define GSFM_MUL(a, b) ((a) * (b))
+#define GSFM_ADD(a, b) ((a) + (b))
+#define GSFM_SUB(a, b) ((a) - (b))
+#endif
+__host__ __device__ inline void whiten(int type, const double* c6, double w, double* U) {
+  U[0] = U[1] = U[2] = U[3] = U[4] = U[5] = 0.0;
+  if (type == 3 || type == 6) {
+    const double a = GSFM_MUL(c6[0], 1e8), d = GSFM_MUL(c6[1], 1e8), f = GSFM_MUL(c6[2], 1e8);
+    const double b = GSFM_MUL(c6[3], 1e8), c = GSFM_MUL(c6[4], 1e8), e = GSFM_MUL(c6[5], 1e8);
+    const double c00 = GSFM_SUB(GSFM_MUL(d, f), GSFM_MUL(e, e)), c01 = GSFM_SUB(GSFM_MUL(c, e), GSFM_MUL(b, f));
+    const double c02 = GSFM_SUB(GSFM_MUL(b, e), GSFM_MUL(c, d)), c11 = GSFM_SUB(GSFM_MUL(a, f), GSFM_MUL(c, c));
+    const double c12 = GSFM_SUB(GSFM_MUL(b, c), GSFM_MUL(a, e)), c22 = GSFM_SUB(GSFM_MUL(a, d), GSFM_MUL(b, b));
+    const double det = GSFM_ADD(GSFM_ADD(GSFM_MUL(a, c00), GSFM_MUL(b, c01)), GSFM_MUL(c, c02));
+    const double id = 1.0 / det;
+    const double P00 = GSFM_MUL(c00, id), P10 = GSFM_MUL(c01, id), P20 = GSFM_MUL(c02, id);
+    const double P11 = GSFM_MUL(c11, id), P21 = GSFM_MUL(c12, id), P22 = GSFM_MUL(c22, id);
+    const double l00 = sqrt(P00), l10 = P10 / l00, l20 = P20 / l00;
+    const double l11 = sqrt(GSFM_SUB(P11, GSFM_MUL(l10, l10))), l21 = GSFM_SUB(P21, GSFM_MUL(l20, l10)) / l11;
+    const double l22 = sqrt(GSFM_SUB(GSFM_SUB(P22, GSFM_MUL(l20, l20)), GSFM_MUL(l21, l21)));
+    U[0] = GSFM_MUL(l00, w); U[1] = GSFM_MUL(l10, w); U[2] = GSFM_MUL(l20, w);
+    U[3] = GSFM_MUL(l11, w); U[4] = GSFM_MUL(l21, w); U[5] = GSFM_MUL(l22, w);
+    return;
+  }
+  double s = w;
+  if (type == 7) s = GSFM_MUL(w, sqrt(1.0 / GSFM_MUL(GSFM_ADD(GSFM_ADD(c6[0], c6[1]), c6[2]), 1e8)));
+  if (type == 8) {
+    double n2 = 0.0;
+    for (int k = 0; k < 3; ++k) { const double t = GSFM_MUL(c6[k], 1e8); n2 = GSFM_ADD(n2, GSFM_MUL(t, t)); }
+    for (int k = 3; k < 6; ++k) { const double t = GSFM_MUL(c6[k], 1e8); n2 = GSFM_ADD(n2, GSFM_MUL(GSFM_MUL(2.0, t), t)); }
+    s = GSFM_MUL(w, sqrt(1.0 / sqrt(n2)));
+  }
+  U[0] = U[3] = U[5] = s;
+}
+
+}  // namespace gsfm

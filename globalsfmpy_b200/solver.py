@@ -1,0 +1,161 @@
+"""Python host API over the C ABI (include/gsfm_ra.h).  Everything here calls libgsfm_ra.so;
+nothing computes on the CPU, and nothing here imports the oracle."""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+
+
+def make_problem(graph, error_type, edge_weight=None):
+    """graph: viewgraph.PoseGraph (dense-renumbered views)."""
+    cov = graph.cov6 if error_type in (capi.ANGLE_AXIS_COVARIANCE, capi.ANGLE_AXIS_COV_INLIERS,
+                                       capi.ANGLE_AXIS_COVTRACE, capi.ANGLE_AXIS_COVNORM) else None
+    w = edge_weight if edge_weight is not None else graph.edge_weight
+    return capi.ProblemArrays(graph.num_views, graph.edge_i, graph.edge_j, graph.omega_ij, cov6=cov,
+                              edge_weight=w, error_type=error_type)
+
+
+def _omega(prob, omega):
+    return capi.as_f64(omega, (prob.num_views, 3))
+
+
+def eval_loss(loss, s, device=-1):
+    s = capi.as_f64(np.atleast_1d(s))
+    out = np.zeros((len(s), 3))
+    capi.check(capi.lib().gsfm_ra_eval_loss(C.byref(loss), capi.ptr(s), len(s), capi.ptr(out), device))
+    return out
+
+
+def whiten(prob, device=-1):
+    U = np.zeros((prob.num_edges, 3, 3))
+    capi.check(capi.lib().gsfm_ra_whiten(C.byref(prob.c), capi.ptr(U), device))
+    return U
+
+
+def eval_edges(prob, loss, omega, device=-1):
+    E = prob.num_edges
+    omega = _omega(prob, omega)
+    r, Ji, Jj, rho = np.zeros((E, 3)), np.zeros((E, 3, 3)), np.zeros((E, 3, 3)), np.zeros((E, 3))
+    capi.check(capi.lib().gsfm_ra_eval_edges(C.byref(prob.c), C.byref(loss), capi.ptr(omega), capi.ptr(r), capi.ptr(Ji),
+                                             capi.ptr(Jj), capi.ptr(rho), device))
+    return r, Ji, Jj, rho
+
+
+def assemble(prob, loss, omega, device=-1):
+    N, E = prob.num_views, prob.num_edges
+    omega = _omega(prob, omega)
+    cost = C.c_double()
+    g, hd = np.zeros((N, 3)), np.zeros((N, 3, 3))
+    rowptr, col, val = np.zeros(N + 1, np.uint32), np.zeros(2 * E, np.uint32), np.zeros((2 * E, 3, 3))
+    capi.check(capi.lib().gsfm_ra_assemble(C.byref(prob.c), C.byref(loss), capi.ptr(omega), C.byref(cost), capi.ptr(g),
+                                           capi.ptr(hd), capi.ptr(rowptr, C.c_uint32), capi.ptr(col, C.c_uint32),
+                                           capi.ptr(val), device))
+    return cost.value, g, hd, rowptr, col, val
+
+
+def cost(prob, loss, omega, device=-1):
+    omega = _omega(prob, omega)
+    c = C.c_double()
+    capi.check(capi.lib().gsfm_ra_cost(C.byref(prob.c), C.byref(loss), capi.ptr(omega), C.byref(c), device))
+    return c.value
+
+
+def spmv(prob, loss, omega, x, damping=None, device=-1):
+    omega = _omega(prob, omega)
+    x = capi.as_f64(x, (prob.num_views, 3))
+    d = None if damping is None else capi.as_f64(damping, (prob.num_views, 3))
+    y = np.zeros_like(x)
+    capi.check(capi.lib().gsfm_ra_spmv(C.byref(prob.c), C.byref(loss), capi.ptr(omega), capi.ptr(d), capi.ptr(x),
+                                       capi.ptr(y), device))
+    return y
+
+
+def pcg(prob, loss, omega, b, damping=None, rtol=1e-10, max_iterations=500, device=-1):
+    omega = _omega(prob, omega)
+    b = capi.as_f64(b, (prob.num_views, 3))
+    d = None if damping is None else capi.as_f64(damping, (prob.num_views, 3))
+    x = np.zeros_like(b)
+    it, res = C.c_int32(), C.c_double()
+    capi.check(capi.lib().gsfm_ra_pcg(C.byref(prob.c), C.byref(loss), capi.ptr(omega), capi.ptr(d), capi.ptr(b), rtol,
+                                      max_iterations, capi.ptr(x), C.byref(it), C.byref(res), device))
+    return x, it.value, res.value
+
+
+def filter_view_pairs(prob, omega, max_degrees, device=-1):
+    omega = _omega(prob, omega)
+    keep = np.zeros(prob.num_edges, np.uint8)
+    ang = np.zeros(prob.num_edges)
+    capi.check(capi.lib().gsfm_ra_filter_view_pairs(C.byref(prob.c), capi.ptr(omega), float(max_degrees),
+                                                    capi.ptr(keep, C.c_uint8), capi.ptr(ang), device))
+    return keep.astype(bool), ang
+
+
+def _summary(trace_capacity):
+    s = capi.Summary()
+    trace = (capi.Iteration * max(1, trace_capacity))()
+    if trace_capacity:
+        s.trace = trace
+        s.trace_capacity = trace_capacity
+    return s, trace
+
+
+def solve(prob, options, omega0, trace_capacity=0):
+    """One-shot gsfm_ra_solve: host buffers in, host buffers out. Returns (omega, summary, trace)."""
+    omega = capi.as_f64(np.array(omega0, dtype=np.float64, copy=True), (prob.num_views, 3))
+    s, trace = _summary(trace_capacity)
+    capi.check(capi.lib().gsfm_ra_solve(C.byref(prob.c), C.byref(options), capi.ptr(omega), C.byref(s)))
+    return omega, s, [trace[k] for k in range(s.trace_size)]
+
+
+class Solver:
+    """Resident solver handle (problem stays in HBM across iterations)."""
+
+    def __init__(self, prob, options, rank=0, world_size=1):
+        self.prob = prob
+        self.options = options
+        self._h = C.c_void_p()
+        if world_size == 1:
+            capi.check(capi.lib().gsfm_ra_solver_create(C.byref(prob.c), C.byref(options), C.byref(self._h)))
+        else:
+            capi.check(capi.lib().gsfm_ra_solver_create_sharded(C.byref(prob.c), C.byref(options), rank, world_size,
+                                                                C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            capi.lib().gsfm_ra_solver_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_rotations(self, omega):
+        omega = _omega(self.prob, omega)
+        capi.check(capi.lib().gsfm_ra_solver_set_rotations(self._h, capi.ptr(omega)))
+
+    def get_rotations(self):
+        omega = np.zeros((self.prob.num_views, 3))
+        capi.check(capi.lib().gsfm_ra_solver_get_rotations(self._h, capi.ptr(omega)))
+        return omega
+
+    def reset(self):
+        capi.check(capi.lib().gsfm_ra_solver_reset(self._h))
+
+    @property
+    def cuda_stream(self):
+        """Raw cudaStream_t of the solver (wrap with torch.cuda.ExternalStream to record events on it)."""
+        return capi.lib().gsfm_ra_solver_cuda_stream(self._h)
+
+    def time_kernels(self, repeats=20):
+        """Average ms per launch: dict(k1, k1c, spmv, pcg_iteration)."""
+        out = np.zeros(4)
+        capi.check(capi.lib().gsfm_ra_solver_time_kernels(self._h, int(repeats), capi.ptr(out)))
+        return dict(k1=out[0], k1c=out[1], spmv=out[2], pcg_iteration=out[3])
+
+    def iterate(self, num_iterations, trace_capacity=0):
+        s, trace = _summary(trace_capacity)
+        capi.check(capi.lib().gsfm_ra_solver_iterate(self._h, int(num_iterations), C.byref(s)))
+        return s, [trace[k] for k in range(s.trace_size)]

@@ -174,6 +174,34 @@ def max_spanning_tree_orientations(num_views, ei, ej, omega_ij, weights, root=No
     return omega
 
 
+def spanning_tree_orientations_bfs(num_views, ei, ej, Rrel, root=0):
+    """Breadth-first spanning-tree initialisation (level-synchronous, vectorised): the role
+    OrientationsFromMaximumSpanningTree plays in the pipeline, for graphs too large for a Python
+    Kruskal.  R_child = R_rel R_parent along (parent=i, child=j) edges, R_rel^T R_parent otherwise."""
+    ei, ej = np.asarray(ei, dtype=np.int64), np.asarray(ej, dtype=np.int64)
+    R = np.zeros((num_views, 3, 3))
+    R[root] = np.eye(3)
+    done = np.zeros(num_views, dtype=bool)
+    done[root] = True
+    while not done.all():
+        fwd = done[ei] & ~done[ej]
+        bwd = done[ej] & ~done[ei]
+        if not (fwd.any() or bwd.any()):
+            break
+        child = np.concatenate([ej[fwd], ei[bwd]])
+        k = np.concatenate([np.nonzero(fwd)[0], np.nonzero(bwd)[0]])
+        is_fwd = np.concatenate([np.ones(int(fwd.sum()), bool), np.zeros(int(bwd.sum()), bool)])
+        _, first = np.unique(child, return_index=True)  # first discovering edge wins
+        child, k, is_fwd = child[first], k[first], is_fwd[first]
+        parent = np.where(is_fwd, ei[k], ej[k])
+        Rk = np.where(is_fwd[:, None, None], Rrel[k], np.transpose(Rrel[k], (0, 2, 1)))
+        R[child] = Rk @ R[parent]
+        done[child] = True
+    omega = so3_log(R)
+    omega[~done] = np.nan
+    return omega
+
+
 # --------------------------------------------------------------------------- 1DSfM / covariance formats
 def egs_to_rotation_2(edge_R_rowmajor):
     """T/io/read_1dsfm.cc:309-325: rotation = S * R^T * S, S = diag(1,-1,-1); angle-axis."""
@@ -325,6 +353,8 @@ def synthetic_pose_graph(num_views, num_edges, seed=56, noise_deg=1.0, outlier_f
         for k in ck.tolist():  # edge (a, a+1): R_{a+1} = R_rel R_a
             R = Rrel[k] @ R
             omega0[ij[k, 1]] = so3_log(R)
+    elif init == "bfs":
+        omega0 = spanning_tree_orientations_bfs(N, ij[:, 0], ij[:, 1], Rrel)
     elif init == "gt_perturbed":
         omega0 = so3_log(so3_exp(np.deg2rad(5.0) * rng.normal(size=(N, 3))) @ Rgt)
     else:

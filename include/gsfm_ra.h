@@ -220,6 +220,15 @@ int gsfm_ra_solver_ipc_import(gsfm_ra_solver* solver, const uint8_t* handles /*[
 /* Row range owned by this rank (load-balanced on half-edge count). */
 int gsfm_ra_solver_row_range(const gsfm_ra_solver* solver, uint32_t* row_begin, uint32_t* row_end);
 
+/* The CUDA stream (a cudaStream_t) every kernel of this solver is launched on, so a host
+ * framework can bracket calls with its own events.                               */
+void* gsfm_ra_solver_cuda_stream(gsfm_ra_solver* solver);
+/* Measurement aid: average device time in ms (CUDA events on the solver stream) of `repeats`
+ * back-to-back launches of the production kernels on the solver's current linearisation.
+ * out_ms[0] K1 fused edge kernel, [1] K1c cost-only edge kernel, [2] K2 block SpMV,
+ * [3] one whole PCG iteration (K2 + the three vector kernels).  Does not change solver state. */
+int gsfm_ra_solver_time_kernels(gsfm_ra_solver* solver, int32_t repeats, double* out_ms /*[4]*/);
+
 /* ---- kernel-level entry points (parity tests, profiling) ---------------------*/
 /* K1 per edge, at omega [N][3]: raw residual r [E][3], raw Jacobians
  * d r/d omega_i, d r/d omega_j [E][9] row-major, and rho[E][3] = loss at |r|^2.

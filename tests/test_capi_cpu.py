@@ -1,0 +1,66 @@
+"""CPU tests of the drop-in boundary: the library loads, exports every symbol of include/gsfm_ra.h,
+agrees with the header's defaults, and FAILS LOUDLY (no CPU fallback) when no CUDA device exists."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from globalsfmpy_b200 import _capi as capi, solver, viewgraph as vg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "gsfm_ra.h")).read()
+    declared = set(re.findall(r"\b(gsfm_ra_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(capi.EXPORTED_SYMBOLS), declared ^ set(capi.EXPORTED_SYMBOLS)
+    lib = capi.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.gsfm_ra_abi_version() == capi.ABI_VERSION
+
+
+def test_default_options_match_ceres_defaults():
+    o = capi.Options()
+    capi.lib().gsfm_ra_default_options(C.byref(o))
+    p = capi.default_options_py()
+    for f, _ in capi.Options._fields_:
+        if f in ("loss", "reserved"):
+            continue
+        assert getattr(o, f) == getattr(p, f), f
+    assert (o.max_num_iterations, o.function_tolerance, o.gradient_tolerance, o.parameter_tolerance) == (200, 1e-6, 1e-10, 1e-8)
+    assert o.initial_trust_region_radius == 1e4 and o.min_relative_decrease == 1e-3 and o.jacobi_scaling == 1
+
+
+def test_struct_sizes_match_header():
+    assert C.sizeof(capi.Loss) == 48 and C.sizeof(capi.Problem) == 64
+    assert C.sizeof(capi.Iteration) == 88
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert capi.lib().gsfm_ra_device_count() == 0
+    g = vg.synthetic_pose_graph(6, 10, seed=1)
+    prob = solver.make_problem(g, capi.ANGLE_AXIS)
+    with pytest.raises(capi.GsfmError) as e:
+        solver.solve(prob, capi.default_options_py(), g.omega_init)
+    assert e.value.code == capi.ERR_NO_DEVICE
+    with pytest.raises(capi.GsfmError) as e:
+        solver.eval_loss(capi.Loss.make(capi.LOSS_CAUCHY, 0.1), np.array([0.1]))
+    assert e.value.code == capi.ERR_NO_DEVICE
+
+
+def test_invalid_arguments_are_rejected_before_the_device():
+    g = vg.synthetic_pose_graph(6, 10, seed=1)
+    prob = capi.ProblemArrays(6, g.edge_i, g.edge_j, g.omega_ij, error_type=capi.ANGLE_AXIS_COVARIANCE)  # no cov6
+    with pytest.raises(capi.GsfmError) as e:
+        solver.solve(prob, capi.default_options_py(), g.omega_init)
+    assert e.value.code == capi.ERR_INVALID
+    prob = capi.ProblemArrays(6, g.edge_i, g.edge_j, g.omega_ij, error_type=capi.QUATERNION_COSINE)
+    with pytest.raises(capi.GsfmError) as e:
+        solver.solve(prob, capi.default_options_py(), g.omega_init)
+    assert e.value.code == capi.ERR_UNSUPPORTED
