@@ -14,6 +14,7 @@
 // D = blockdiag(Jl(omega_i)), so the per-edge kernel never touches the per-view Jl factors; the
 // Euclidean (angle-axis) Levenberg-Marquardt of Ceres is reproduced exactly by transforming the
 // LM diagonal per view.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
@@ -22,6 +23,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -31,14 +33,25 @@
 #include "so3_device.cuh"
 
 using namespace gsfm;
+namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int kTaskLen = 128;      // half-edges per warp task
 constexpr int kBlock = 256;        // threads per block of every kernel
 constexpr int kWarpsPerBlock = kBlock / 32;
 constexpr uint32_t kSideBit = 0x80000000u;  // he_col bit 31: the ROW view is the j (second) view of the edge
 constexpr int kPartStride = 10;    // per-task partial: diag(6) grad(3) cost(1)
+// The block matrix is stored as CHUNK RECORDS of 32 consecutive half-edges:
+//   { double blk[9][32]; uint32_t col[32]; }  = 2432 B, 128 B aligned,
+// so 32 lanes still read/write 256 contiguous bytes per block component (coalesced), and K2 can
+// pull a whole record into shared memory with ONE bulk async copy (TMA, cp.async.bulk).
+constexpr int kRecDoubles = 304;                 // 2432 B / 8
+constexpr int kRecBytes = kRecDoubles * 8;
+constexpr int kRecColOffset = 288;               // doubles: col[] starts at byte 2304
+constexpr int kStages = 4;                       // TMA ring depth per warp
+constexpr int kSpmvSmemBytes = kWarpsPerBlock * kStages * kRecBytes + kWarpsPerBlock * kStages * 8;
+
+__device__ __host__ __forceinline__ size_t blk_index(uint64_t h, int k) { return (size_t)(h >> 5) * kRecDoubles + (size_t)k * 32 + (h & 31); }
 
 thread_local std::string g_last_error;
 
@@ -149,6 +162,15 @@ __global__ void k_setup_halfedges(uint64_t H, const uint32_t* __restrict__ he_ed
   for (int t = 0; t < 6; ++t) U[(uint64_t)t * H + h] = u[t];
 }
 
+// Column indices live inside the chunk records of both block buffers (written once).
+__global__ void k_embed_cols(uint64_t H, const uint32_t* __restrict__ he_col, double* rec0, double* rec1) {
+  const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  const size_t w = (size_t)(h >> 5) * kRecDoubles + kRecColOffset;
+  reinterpret_cast<uint32_t*>(rec0 + w)[h & 31] = he_col[h];
+  reinterpret_cast<uint32_t*>(rec1 + w)[h & 31] = he_col[h];
+}
+
 // Per view: quaternion + left Jacobian of the current angle-axis estimate; also |omega|^2.
 __global__ void k_node_prep(uint32_t N, const double* __restrict__ omega, double* __restrict__ node_q, double* __restrict__ node_JL,
                             double* slots, unsigned* counter, DevScalars* sc) {
@@ -178,16 +200,16 @@ __global__ void k_node_prep(uint32_t N, const double* __restrict__ omega, double
 // kWriteBlocks=false is K1c: cost only (trial point).
 // ------------------------------------------------------------------------------------------
 template <bool kWriteBlocks>
-__global__ void __launch_bounds__(kBlock)
-k_edges(uint32_t num_tasks, uint64_t H, const uint32_t* __restrict__ task_row, const uint32_t* __restrict__ task_begin,
-        const uint32_t* __restrict__ task_len, const uint32_t* __restrict__ he_col, const double* __restrict__ qij,
-        const double* __restrict__ U, const double* __restrict__ node_q, DevLoss loss, double* __restrict__ val,
-        double* __restrict__ part) {
+__global__ void __launch_bounds__(kBlock, 2)
+k_edges(uint32_t num_warps, uint64_t H, const uint32_t* __restrict__ warp_seg_ptr, const uint32_t* __restrict__ task_row,
+        const uint32_t* __restrict__ task_begin, const uint32_t* __restrict__ task_len, const uint32_t* __restrict__ he_col,
+        const double* __restrict__ qij, const double* __restrict__ U, const double* __restrict__ node_q, DevLoss loss,
+        double* __restrict__ val, double* __restrict__ part) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t t = warp_global; t < num_tasks; t += num_warps) {
-    const uint32_t row = task_row[t];
+  if (warp_global >= num_warps) return;
+  for (uint32_t t = warp_seg_ptr[warp_global]; t < warp_seg_ptr[warp_global + 1]; ++t) {
+    const uint32_t row = task_row[t] & ~kSideBit;
     const uint64_t begin = task_begin[t];
     const uint32_t len = task_len[t];
     const double4 qa4 = reinterpret_cast<const double4*>(node_q)[row];
@@ -244,7 +266,7 @@ k_edges(uint32_t num_tasks, uint64_t H, const uint32_t* __restrict__ task_row, c
           acc[8] -= Q[2] * et.v[0] + Q[5] * et.v[1] + Q[8] * et.v[2];
         }
 #pragma unroll
-        for (int k = 0; k < 9; ++k) val[(uint64_t)k * H + h] = B[k];
+        for (int k = 0; k < 9; ++k) val[blk_index(h, k)] = B[k];
       }
     }
     if (kWriteBlocks) {
@@ -325,7 +347,8 @@ __global__ void k_prepare_solve(uint32_t N, double mu, double lo, double hi, con
                                 const double* __restrict__ scale, const double* __restrict__ node_JL, const double* __restrict__ Hd,
                                 const double* __restrict__ gt, const double* __restrict__ user_damp, const double* __restrict__ user_b,
                                 double* __restrict__ Dblk, double* __restrict__ Minv, double* __restrict__ x, double* __restrict__ r,
-                                double* __restrict__ z, double* __restrict__ p, double* slots, unsigned* counter, DevScalars* sc) {
+                                double* __restrict__ z, double* __restrict__ p, double* __restrict__ p1, double* slots, unsigned* counter,
+                                DevScalars* sc) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   double v[2] = {0.0, 0.0};
   if (i < N) {
@@ -362,6 +385,7 @@ __global__ void k_prepare_solve(uint32_t N, double mu, double lo, double hi, con
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       x[3 * (size_t)i + c] = 0.0; r[3 * (size_t)i + c] = b[c]; z[3 * (size_t)i + c] = zz[c]; p[3 * (size_t)i + c] = zz[c];
+      p1[3 * (size_t)i + c] = 0.0;
       v[0] += b[c] * zz[c];
       v[1] += b[c] * b[c];
     }
@@ -375,33 +399,142 @@ __global__ void k_prepare_solve(uint32_t N, double mu, double lo, double hi, con
 }
 
 // ------------------------------------------------------------------------------------------
-// K2: block-3x3 CSR SpMV, off-diagonal part.  One warp per task; each lane streams one 72 B block
-// per iteration from the planar value array (9 coalesced 8 B loads), gathers x[col] (24 B, L2),
-// accumulates 3 doubles; one warp reduction per task.  ypart[t][3].
+// K2: block-3x3 CSR SpMV, off-diagonal part, TMA-staged.
+// Every warp owns one contiguous range of chunk records.  Lane 0 keeps kStages bulk async copies
+// (cp.async.bulk, one 2432 B record each, completion on a warp-private mbarrier) in flight; the
+// warp consumes a record from shared memory (conflict-free: lane l reads word l of each of the 9
+// component rows), gathers x[col] (24 B, L2) and accumulates.  Bytes in flight are set by the ring
+// depth, not by registers or occupancy.  Row boundaries inside a range are handled by visiting
+// the range segment by segment (segment = range ^ row); a record shared by two segments is read
+// twice from shared memory, never twice from HBM.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock)
-k_spmv(uint32_t num_tasks, uint64_t H, const uint32_t* __restrict__ task_begin, const uint32_t* __restrict__ task_len,
-       const uint32_t* __restrict__ he_col, const double* __restrict__ val, const double* __restrict__ x,
-       double* __restrict__ ypart, const DevScalars* sc, int check_done) {
-  if (check_done && sc->pcg_done) return;
-  const int lane = threadIdx.x & 31;
-  const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t t = warp_global; t < num_tasks; t += num_warps) {
-    const uint64_t begin = task_begin[t];
-    const uint32_t len = task_len[t];
-    double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-    for (uint32_t off = lane; off < len; off += 32) {
-      const uint64_t h = begin + off;
-      const uint32_t col = he_col[h] & ~kSideBit;
-      const double x0 = x[3 * (size_t)col], x1 = x[3 * (size_t)col + 1], x2 = x[3 * (size_t)col + 2];
-      y0 += val[h] * x0 + val[H + h] * x1 + val[2 * H + h] * x2;
-      y1 += val[3 * H + h] * x0 + val[4 * H + h] * x1 + val[5 * H + h] * x2;
-      y2 += val[6 * H + h] * x0 + val[7 * H + h] * x1 + val[8 * H + h] * x2;
-    }
-    y0 = warp_sum(y0); y1 = warp_sum(y1); y2 = warp_sum(y2);
-    if (lane == 0) { ypart[3 * (size_t)t] = y0; ypart[3 * (size_t)t + 1] = y1; ypart[3 * (size_t)t + 2] = y2; }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_bulk(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct WarpPipe {
+  double* ring;    // this warp's kStages records in shared memory
+  uint64_t* bars;  // this warp's kStages mbarriers
+  uint32_t pos;    // records consumed since init: ring slot = pos % kStages, phase = (pos / kStages) & 1
+};
+
+__device__ __forceinline__ void pipe_init(WarpPipe& wp, unsigned char* smem) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  wp.ring = reinterpret_cast<double*>(smem + (size_t)warp * kStages * kRecBytes);
+  wp.bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWarpsPerBlock * kStages * kRecBytes) + warp * kStages;
+  wp.pos = 0;
+  if (lane == 0) {
+    for (int st = 0; st < kStages; ++st) mbar_init(&wp.bars[st], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncwarp();
+}
+
+// Stream this warp's record range (nrec records from half-edge lo) and call finish(t, y0, y1, y2)
+// (all lanes, totals valid in every lane) for each segment t in [t0, t1).  x_j = a_j + beta b_j (b may be
+// null).  Record-major loop: the x gather of record c+1 (its columns are already in shared memory) is issued
+// before record c is consumed, so the L2 gather latency overlaps the arithmetic and the next wait; each
+// lane's 3-vector contribution is formed once per record and added to the running segment, segments that
+// end inside the record are reduced and handed to finish().
+template <typename Finish>
+__device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restrict__ recs, uint64_t lo, uint64_t hi, uint32_t t0, uint32_t t1,
+                                            const uint32_t* __restrict__ seg_begin, const uint32_t* __restrict__ seg_len, const double* a,
+                                            const double* b, double beta, Finish&& finish) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t nrec = (uint32_t)((hi - lo + 31) >> 5);
+  const uint32_t base = wp.pos;
+  const double* src = recs + (size_t)(lo >> 5) * kRecDoubles;
+  auto issue = [&](uint32_t c) {
+    if (lane == 0) {
+      const uint32_t st = (base + c) % kStages;
+      mbar_expect_tx(&wp.bars[st], kRecBytes);
+      tma_load_bulk(wp.ring + (size_t)st * kRecDoubles, src + (size_t)c * kRecDoubles, kRecBytes, &wp.bars[st]);
+    }
+  };
+  auto wait_rec = [&](uint32_t c) -> const double* {
+    const uint32_t p = base + c, st = p % kStages;
+    mbar_wait(&wp.bars[st], (p / kStages) & 1u);
+    return wp.ring + (size_t)st * kRecDoubles;
+  };
+  auto gather = [&](const double* rec, uint64_t h, double& x0, double& x1, double& x2) {
+    uint32_t col = reinterpret_cast<const uint32_t*>(rec + kRecColOffset)[lane] & ~kSideBit;
+    if (h >= hi) col = 0;  // padding lanes of the last record
+    if (beta == -12345.0) { x0 = col; x1 = 1.0; x2 = 2.0; return; }  // DEBUG: stream-only ceiling
+    x0 = a[3 * (size_t)col]; x1 = a[3 * (size_t)col + 1]; x2 = a[3 * (size_t)col + 2];
+    if (b) { x0 += beta * b[3 * (size_t)col]; x1 += beta * b[3 * (size_t)col + 1]; x2 += beta * b[3 * (size_t)col + 2]; }
+  };
+  for (uint32_t c = 0; c < nrec && c < (uint32_t)kStages; ++c) issue(c);
+  if (nrec == 0 || t0 == t1) { wp.pos = base + nrec; return; }
+  uint32_t t = t0;
+  uint64_t sb = seg_begin[t], se = sb + seg_len[t];
+  double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+  const double* rec = wait_rec(0);
+  double x0, x1, x2;
+  gather(rec, lo + lane, x0, x1, x2);
+  for (uint32_t c = 0; c < nrec; ++c) {
+    const uint64_t cb = lo + ((uint64_t)c << 5), ce = cb + 32, h = cb + lane;
+    // prefetch the next record's gather
+    const double* rec_n = nullptr;
+    double n0 = 0.0, n1 = 0.0, n2 = 0.0;
+    if (c + 1 < nrec) { rec_n = wait_rec(c + 1); gather(rec_n, ce + lane, n0, n1, n2); }
+    const double v0 = rec[lane] * x0 + rec[32 + lane] * x1 + rec[64 + lane] * x2;
+    const double v1 = rec[96 + lane] * x0 + rec[128 + lane] * x1 + rec[160 + lane] * x2;
+    const double v2 = rec[192 + lane] * x0 + rec[224 + lane] * x1 + rec[256 + lane] * x2;
+    // this record's slot can be refilled as soon as every lane has read it
+    __syncwarp();
+    if (c + kStages < nrec) issue(c + kStages);
+    while (true) {
+      if (h >= sb && h < se) { y0 += v0; y1 += v1; y2 += v2; }
+      if (se > ce) break;  // the segment continues in the next record
+      y0 = warp_sum(y0); y1 = warp_sum(y1); y2 = warp_sum(y2);
+      finish(t, y0, y1, y2);
+      y0 = y1 = y2 = 0.0;
+      if (++t == t1) break;
+      sb = se; se = sb + seg_len[t];
+      if (sb >= ce) break;
+    }
+    rec = rec_n; x0 = n0; x1 = n1; x2 = n2;
+    if (t == t1) break;
+  }
+  wp.pos = base + nrec;
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_spmv(uint32_t num_warps, uint64_t H, uint32_t warp_span, const uint32_t* __restrict__ warp_seg_ptr, const uint32_t* __restrict__ task_begin,
+       const uint32_t* __restrict__ task_len, const double* __restrict__ recs, const double* __restrict__ x, double* __restrict__ ypart,
+       const DevScalars* sc, int check_done) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  if (check_done == 1 && sc->pcg_done) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (gw >= num_warps) return;
+  WarpPipe wp;
+  pipe_init(wp, smem_raw);
+  const uint64_t lo = (uint64_t)gw * warp_span, hi = min(H, lo + warp_span);
+  spmv_stream(wp, recs, lo, hi, warp_seg_ptr[gw], warp_seg_ptr[gw + 1], task_begin, task_len, x, nullptr, check_done == 2 ? -12345.0 : 0.0,
+              [&](uint32_t t, double y0, double y1, double y2) {
+                if (lane == 0) { ypart[3 * (size_t)t] = y0; ypart[3 * (size_t)t + 1] = y1; ypart[3 * (size_t)t + 2] = y2; }
+              });
 }
 
 // y_i = Dblk_i x_i + sum of the row's task partials (+ shard-local only: the diagonal part is
@@ -469,6 +602,224 @@ __global__ void k_pcg_direction(uint32_t n3, const double* __restrict__ z, doubl
   if (c < n3) p[c] = z[c] + sc->beta * p[c];
 }
 
+// ------------------------------------------------------------------------------------------
+// The whole block-Jacobi PCG solve as ONE persistent cooperative kernel (one launch per linear
+// solve, convergence decided on the device, two grid barriers per CG step).
+//
+// Work distribution: the half-edge array is cut into num_warps equal contiguous ranges (one per
+// resident warp, grid = SMs x occupancy), each range into segments (range ^ row).  Per CG step:
+//   phase A  every warp streams its range: ypart[seg] = sum B x[col], with the search direction
+//            formed on the fly, x_j = z_j + beta p_old_j (so no separate "p = z + beta p" pass and
+//            no barrier for it).  The warp that completes the LAST segment of a row (per-row
+//            arrival counter) finishes the row in fixed segment order: y_i = D_i p_i + sum parts,
+//            stores p_new_i, y_i and accumulates p_i.y_i.                      -> barrier 1
+//   phase C  alpha from the block slots (every block adds them in the same order: bitwise equal
+//            everywhere), x += alpha p, r -= alpha y, z = Minv r, slots of r.z and r.r -> barrier 2
+// Epilogue: y = Ht x with the UNDAMPED diagonal, for the model cost change.
+// Vectors written inside the kernel are never accessed through __restrict__/read-only paths.
+// ------------------------------------------------------------------------------------------
+struct PcgParams {
+  uint32_t N, num_warps, n_iso, warp_span;
+  int max_iter;
+  uint64_t H;
+  double rtol2;
+  const uint32_t *warp_seg_ptr, *seg_row, *seg_begin, *seg_len, *node_seg_ptr, *iso;
+  const double *val, *Dblk, *Minv, *Hd;
+  double *x, *r, *z, *p0, *p1, *y, *ypart;
+  unsigned* row_cnt;
+  double *slotsA, *slotsB, *slotsC;
+  DevScalars* sc;
+  unsigned long long* prof;  // optional [8] phase timers in ns, accumulated by block 0 (measurement aid)
+};
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ double block_sum_to_thread0(double v, double* sm) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < kWarpsPerBlock; ++w) s += sm[w];
+  __syncthreads();
+  return s;
+}
+
+// Sum slot k of every block, same order in every block; result broadcast to all threads.
+__device__ __forceinline__ double all_blocks_sum(const double* slots, int stride, int k, double* sm_b) {
+  if (threadIdx.x < 32) {
+    double s = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += 32) s += __ldcg(slots + (size_t)b * stride + k);
+    s = warp_sum(s);
+    if (threadIdx.x == 0) *sm_b = s;
+  }
+  __syncthreads();
+  const double out = *sm_b;
+  __syncthreads();
+  return out;
+}
+
+__device__ __forceinline__ void all_blocks_sum2(const double* slots, double* o0, double* o1, double* sm_b2) {
+  if (threadIdx.x < 32) {
+    double s0 = 0.0, s1 = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += 32) { s0 += __ldcg(slots + 2 * (size_t)b); s1 += __ldcg(slots + 2 * (size_t)b + 1); }
+    s0 = warp_sum(s0); s1 = warp_sum(s1);
+    if (threadIdx.x == 0) { sm_b2[0] = s0; sm_b2[1] = s1; }
+  }
+  __syncthreads();
+  *o0 = sm_b2[0]; *o1 = sm_b2[1];
+  __syncthreads();
+}
+
+// One SpMV pass over this warp's range.  x_j = a_j + beta b_j (b may be null).  Returns (per lane)
+// the accumulated sum over the rows this lane finished of x_i . y_i.
+__device__ __forceinline__ double spmv_pass(const PcgParams& P, WarpPipe& wp, const double* a, const double* b, double beta, const double* diag,
+                                            double* xnew_out, double* y_out) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  double dot = 0.0;
+  if (gwarp < P.num_warps) {
+    const uint64_t lo = (uint64_t)gwarp * P.warp_span, hi = min(P.H, lo + P.warp_span);
+    // Rows are finished by a STATIC owner -- the warp holding the row's first segment -- so every
+    // sum has a fixed order and a fixed place (bit-reproducible).  A continuation segment (always the
+    // first segment of a warp's range) is published at once by lane 0: parts + fence + counter.
+    // Owned segments are parked one per lane and completed as a batch, so the wait / load latencies
+    // of up to 32 rows overlap instead of serialising while the record stream drains.  The owner
+    // spins on the row counter; the warps it waits for publish first thing in their pass and the
+    // cooperative launch keeps every block resident, so the wait cannot deadlock.
+    const uint32_t t0 = P.warp_seg_ptr[gwarp], t1 = P.warp_seg_ptr[gwarp + 1];
+    double my0 = 0.0, my1 = 0.0, my2 = 0.0;
+    uint32_t my_t = 0, nbatch = 0;
+    auto flush = [&]() {
+      if ((uint32_t)lane < nbatch) {
+        const uint32_t row = P.seg_row[my_t] & ~kSideBit;
+        const uint32_t s0 = P.node_seg_ptr[row], s1 = P.node_seg_ptr[row + 1];
+        if (s1 - s0 > 1) {
+          volatile unsigned* cnt = P.row_cnt + row;
+          while (*cnt != s1 - s0 - 1) { }
+          __threadfence();
+          *cnt = 0u;
+          for (uint32_t q = s0 + 1; q < s1; ++q) {
+            my0 += __ldcg(P.ypart + 3 * (size_t)q); my1 += __ldcg(P.ypart + 3 * (size_t)q + 1); my2 += __ldcg(P.ypart + 3 * (size_t)q + 2);
+          }
+        }
+        double xi[3] = {a[3 * (size_t)row], a[3 * (size_t)row + 1], a[3 * (size_t)row + 2]};
+        if (b) { xi[0] += beta * b[3 * (size_t)row]; xi[1] += beta * b[3 * (size_t)row + 1]; xi[2] += beta * b[3 * (size_t)row + 2]; }
+        double d[3];
+        sym_mul_vec(diag + 6 * (size_t)row, xi, d);
+        my0 += d[0]; my1 += d[1]; my2 += d[2];
+        y_out[3 * (size_t)row] = my0; y_out[3 * (size_t)row + 1] = my1; y_out[3 * (size_t)row + 2] = my2;
+        if (xnew_out) { xnew_out[3 * (size_t)row] = xi[0]; xnew_out[3 * (size_t)row + 1] = xi[1]; xnew_out[3 * (size_t)row + 2] = xi[2]; }
+        dot += xi[0] * my0 + xi[1] * my1 + xi[2] * my2;
+      }
+      nbatch = 0;
+      __syncwarp();
+    };
+    spmv_stream(wp, P.val, lo, hi, t0, t1, P.seg_begin, P.seg_len, a, b, beta, [&](uint32_t t, double y0, double y1, double y2) {
+      const uint32_t rowf = P.seg_row[t];
+      if (rowf & kSideBit) {  // continuation of a row owned by an earlier warp
+        if (lane == 0) {
+          __stcg(P.ypart + 3 * (size_t)t, y0); __stcg(P.ypart + 3 * (size_t)t + 1, y1); __stcg(P.ypart + 3 * (size_t)t + 2, y2);
+          __threadfence();
+          atomicAdd(P.row_cnt + (rowf & ~kSideBit), 1u);
+        }
+        return;
+      }
+      if ((uint32_t)lane == nbatch) { my0 = y0; my1 = y1; my2 = y2; my_t = t; }
+      if (++nbatch == 32) flush();
+    });
+    if (nbatch) flush();
+  }
+  // views without any half-edge: y_i = D_i x_i
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n_iso; k += gridDim.x * blockDim.x) {
+    const uint32_t row = P.iso[k];
+    double xi[3] = {a[3 * (size_t)row], a[3 * (size_t)row + 1], a[3 * (size_t)row + 2]};
+    if (b) { xi[0] += beta * b[3 * (size_t)row]; xi[1] += beta * b[3 * (size_t)row + 1]; xi[2] += beta * b[3 * (size_t)row + 2]; }
+    double d[3];
+    sym_mul_vec(diag + 6 * (size_t)row, xi, d);
+    y_out[3 * (size_t)row] = d[0]; y_out[3 * (size_t)row + 1] = d[1]; y_out[3 * (size_t)row + 2] = d[2];
+    if (xnew_out) { xnew_out[3 * (size_t)row] = xi[0]; xnew_out[3 * (size_t)row + 1] = xi[1]; xnew_out[3 * (size_t)row + 2] = xi[2]; }
+    dot += xi[0] * d[0] + xi[1] * d[1] + xi[2] * d[2];
+  }
+  return dot;
+}
+
+__global__ void __launch_bounds__(kBlock) k_pcg_persistent(PcgParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cg::grid_group grid = cg::this_grid();
+  WarpPipe wp;
+  pipe_init(wp, smem_raw);
+  __shared__ double sm_red[kWarpsPerBlock];
+  __shared__ double sm_b;
+  __shared__ double sm_b2[2];
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  double rz = P.sc->rz;
+  const double bb = P.sc->bb;
+  double rr = bb, beta = 0.0;
+  int iter = 0, breakdown = 0;
+  bool done = P.sc->pcg_done != 0;
+  double* pold = P.p1;  // zero-filled by k_prepare_solve: the first direction is p = z
+  double* pnew = P.p0;
+  while (!done) {
+    // ---- phase A: y = (Ht + Lam) p, p = z + beta p_old formed on the fly, p.y ----------------
+    const bool prof = P.prof != nullptr && gtid == 0;
+    unsigned long long tA = 0, tB = 0, tC = 0, tD = 0, tE = 0, tF = 0, tG = 0;
+    if (prof) tA = gtimer();
+    const double dot = spmv_pass(P, wp, P.z, pold, beta, P.Dblk, pnew, P.y);
+    if (prof) tB = gtimer();
+    const double bs = block_sum_to_thread0(dot, sm_red);
+    if (threadIdx.x == 0) __stcg(P.slotsA + blockIdx.x, bs);
+    grid.sync();
+    if (prof) tC = gtimer();
+    const double pAp = all_blocks_sum(P.slotsA, 1, 0, &sm_b);
+    if (prof) tD = gtimer();
+    if (!(pAp > 0.0) || !isfinite(pAp)) { breakdown = 1; break; }
+    const double alpha = rz / pAp;
+    // ---- phase C: x += alpha p ; r -= alpha y ; z = Minv r ; r.z, r.r -------------------------
+    double v0 = 0.0, v1 = 0.0;
+    for (uint32_t i = gtid; i < P.N; i += gthreads) {
+      double ri[3], zi[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        P.x[3 * (size_t)i + c] += alpha * pnew[3 * (size_t)i + c];
+        ri[c] = P.r[3 * (size_t)i + c] - alpha * P.y[3 * (size_t)i + c];
+        P.r[3 * (size_t)i + c] = ri[c];
+      }
+      sym_mul_vec(P.Minv + 6 * (size_t)i, ri, zi);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { P.z[3 * (size_t)i + c] = zi[c]; v0 += ri[c] * zi[c]; v1 += ri[c] * ri[c]; }
+    }
+    if (prof) tE = gtimer();
+    const double b0 = block_sum_to_thread0(v0, sm_red);
+    const double b1 = block_sum_to_thread0(v1, sm_red);
+    if (threadIdx.x == 0) { __stcg(P.slotsB + 2 * (size_t)blockIdx.x, b0); __stcg(P.slotsB + 2 * (size_t)blockIdx.x + 1, b1); }
+    grid.sync();
+    if (prof) tF = gtimer();
+    double rz_new;
+    all_blocks_sum2(P.slotsB, &rz_new, &rr, sm_b2);
+    if (prof) {
+      tG = gtimer();
+      P.prof[0] += tB - tA; P.prof[1] += tC - tB; P.prof[2] += tD - tC; P.prof[3] += tE - tD; P.prof[4] += tF - tE; P.prof[5] += tG - tF;
+      P.prof[6] += 1;
+    }
+    ++iter;
+    beta = rz_new / rz;
+    rz = rz_new;
+    double* t = pold; pold = pnew; pnew = t;
+    if (rr <= P.rtol2 * bb || iter >= P.max_iter || !isfinite(rr)) done = true;
+  }
+  // ---- epilogue: y = Ht x (undamped diagonal) for the model cost change --------------------------
+  spmv_pass(P, wp, P.x, nullptr, 0.0, P.Hd, nullptr, P.y);
+  if (gtid == 0) {
+    P.sc->rz = rz; P.sc->rr = rr; P.sc->beta = beta;
+    P.sc->pcg_iter = iter; P.sc->pcg_done = 1; P.sc->pcg_breakdown = breakdown;
+  }
+}
+
 // After the solve (xt = tangent step, Hx = Ht xt without damping): Euclidean step
 // delta = Jl^-1 xt, candidate = omega + delta (Ceres updates the angle-axis vector additively);
 // reduce delta.g (= xt.gt), delta.H.delta (= xt.Hx), |delta|^2.
@@ -497,7 +848,7 @@ __global__ void k_apply_step(uint32_t N, const double* __restrict__ node_JL, con
   double tot[4];
   if (grid_sum<4>(v, slots, counter, tot) && threadIdx.x == 0) {
     sc->dg = tot[0]; sc->dHd = tot[1]; sc->step2 = tot[2];
-    if (tot[3] != 0.0) sc->bad = 1;
+    (void)tot[3];  // a non-finite step makes step2 non-finite: the host treats it as an invalid step
   }
 }
 
@@ -560,7 +911,7 @@ __global__ void k_export_blocks(uint64_t H, const uint32_t* __restrict__ he_row,
   if (h >= H) return;
   const uint32_t row = he_row[h], col = he_col[h] & ~kSideBit;
   double B[9], T[9];
-  for (int k = 0; k < 9; ++k) B[k] = val[(uint64_t)k * H + h];
+  for (int k = 0; k < 9; ++k) B[k] = val[blk_index(h, k)];
   const double* Jr = node_JL + 9 * (size_t)row;
   const double* Jc = node_JL + 9 * (size_t)col;
   for (int r = 0; r < 3; ++r)
@@ -702,23 +1053,34 @@ inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kBlock - 1) / kBlo
 // ------------------------------------------------------------------------------------------
 // the resident solver
 // ------------------------------------------------------------------------------------------
+// A balanced work partition of the half-edge array for one kernel class: num_warps equal
+// contiguous ranges (a multiple of 32 half-edges each), every range cut at row boundaries into
+// segments.  num_warps = SMs x resident blocks x warps per block of THAT kernel, so the kernel runs
+// as exactly one full wave.
+struct Partition {
+  uint32_t num_warps = 0, num_segs = 0, grid = 0, span = 0;  // span = half-edges per warp (multiple of 32)
+  DevBuf<uint32_t> warp_seg_ptr, seg_row, seg_begin, seg_len, node_seg_ptr;
+};
+
 struct gsfm_ra_solver {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   uint32_t N = 0;
   uint64_t E = 0;       // edges of this shard
   uint64_t H = 0;       // half-edges of this shard (2E)
-  uint32_t T = 0;       // tasks
   int rank = 0, world = 1;
   int error_type = 4;
   gsfm_ra_options opt;
   DevLoss loss;
   int64_t launches = 0;
+  bool cooperative = true;  // persistent PCG kernel available
 
   // structure
-  DevBuf<uint32_t> he_col, he_row, task_row, task_begin, task_len, node_task_ptr;
+  DevBuf<uint32_t> he_col, he_row, iso;
+  uint32_t n_iso = 0;
+  Partition pk1, pk2;  // K1 (edge kernel) and K2 (SpMV / PCG) partitions
   // per half-edge constants, planar
   DevBuf<double> qij, U;
   // edge-order copies for the API kernels
@@ -729,11 +1091,12 @@ struct gsfm_ra_solver {
   DevBuf<double> part;
   int cur = 0;
   // PCG
-  DevBuf<double> scale, Dblk, Minv, x, r, z, p, y, ypart, delta;
-  DevBuf<double> slots;
-  DevBuf<unsigned> counter;
+  DevBuf<double> scale, Dblk, Minv, x, r, z, p, p1, y, ypart, delta;
+  DevBuf<double> slots, slotsA, slotsB, slotsC;
+  DevBuf<unsigned> counter, row_cnt;
   DevBuf<DevScalars> sc;
   DevScalars* h_sc = nullptr;  // pinned
+  unsigned long long* prof_buf = nullptr;  // device, set only by gsfm_ra_solver_time_kernels
 
   // trust-region state (host)
   bool linearized = false;
@@ -752,56 +1115,79 @@ struct gsfm_ra_solver {
     if (stream) cudaStreamDestroy(stream);
   }
 
-  unsigned task_grid() const {
-    const unsigned want = (T + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const unsigned cap = (unsigned)sm_count * 8u;  // 8 blocks of 256 threads = 2048 threads per SM
-    return std::max(1u, std::min(want, cap));
-  }
-
   int fetch_scalars() {
     CUDA_TRY(cudaMemcpyAsync(h_sc, sc.p, sizeof(DevScalars), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     return 0;
   }
 
+  void launch_edges(int b, bool jacobian, double* val_out) {
+    if (jacobian)
+      k_edges<true><<<pk1.grid, kBlock, 0, stream>>>(pk1.num_warps, H, pk1.warp_seg_ptr.p, pk1.seg_row.p, pk1.seg_begin.p, pk1.seg_len.p, he_col.p,
+                                                     qij.p, U.p, node_q[b].p, loss, val_out, part.p);
+    else
+      k_edges<false><<<pk1.grid, kBlock, 0, stream>>>(pk1.num_warps, H, pk1.warp_seg_ptr.p, pk1.seg_row.p, pk1.seg_begin.p, pk1.seg_len.p, he_col.p,
+                                                      qij.p, U.p, node_q[b].p, loss, nullptr, part.p);
+  }
+  void launch_spmv(int b, const double* xin, int check_done) {
+    k_spmv<<<pk2.grid, kBlock, kSpmvSmemBytes, stream>>>(pk2.num_warps, H, pk2.span, pk2.warp_seg_ptr.p, pk2.seg_begin.p, pk2.seg_len.p, val[b].p,
+                                                         xin, ypart.p, sc.p, check_done);
+  }
+
   // ---- evaluation at omega[b]: node prep, K1 (or K1c), node finalize -------------------------
   int evaluate(int b, bool jacobian) {
     CUDA_TRY(cudaMemsetAsync(&sc.p->gmax, 0, sizeof(double), stream));
     k_node_prep<<<grid_for(N), kBlock, 0, stream>>>(N, omega[b].p, node_q[b].p, node_JL[b].p, slots.p, counter.p, sc.p);
-    if (jacobian)
-      k_edges<true><<<task_grid(), kBlock, 0, stream>>>(T, H, task_row.p, task_begin.p, task_len.p, he_col.p, qij.p, U.p, node_q[b].p, loss, val[b].p, part.p);
-    else
-      k_edges<false><<<task_grid(), kBlock, 0, stream>>>(T, H, task_row.p, task_begin.p, task_len.p, he_col.p, qij.p, U.p, node_q[b].p, loss, nullptr, part.p);
-    k_node_finalize<<<grid_for(N), kBlock, 0, stream>>>(N, node_task_ptr.p, part.p, node_JL[b].p, Hd[b].p, gt[b].p, ediag[b].p, jacobian ? 0 : 1,
+    launch_edges(b, jacobian, val[b].p);
+    k_node_finalize<<<grid_for(N), kBlock, 0, stream>>>(N, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd[b].p, gt[b].p, ediag[b].p, jacobian ? 0 : 1,
                                                          slots.p, counter.p, sc.p);
     launches += 3;
     CUDA_TRY(cudaGetLastError());
     return 0;
   }
 
-  // y = (Ht [+ Dblk]) x on linearisation b.  with_diag: Dblk (incl. damping) else the undamped Hd.
+  // y = (Ht offdiag + diag_blocks) x on linearisation b (separate-kernel path).
   int spmv(int b, const double* xin, double* yout, const double* diag_blocks) {
-    k_spmv<<<task_grid(), kBlock, 0, stream>>>(T, H, task_begin.p, task_len.p, he_col.p, val[b].p, xin, ypart.p, sc.p, 0);
-    k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, node_task_ptr.p, ypart.p, diag_blocks, xin, yout, 1, slots.p, counter.p, sc.p);
+    launch_spmv(b, xin, 0);
+    k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, pk2.node_seg_ptr.p, ypart.p, diag_blocks, xin, yout, 1, slots.p, counter.p, sc.p);
     launches += 2;
     CUDA_TRY(cudaGetLastError());
     return 0;
   }
 
-  // Block-Jacobi PCG on (Ht + Lam) xt = bt for linearisation b.  Everything stays on the device;
-  // the host enqueues `poll` iterations at a time and reads the convergence flag.
-  int pcg(int b, double mu, const double* user_damp, const double* user_b, double rtol, int max_iter, int* iters, double* rel_res) {
+  PcgParams pcg_params(int b, double rtol, int max_iter) {
+    PcgParams P;
+    P.N = N; P.num_warps = pk2.num_warps; P.n_iso = n_iso; P.max_iter = max_iter; P.H = H; P.rtol2 = rtol * rtol;
+    P.warp_seg_ptr = pk2.warp_seg_ptr.p; P.seg_row = pk2.seg_row.p; P.seg_begin = pk2.seg_begin.p; P.seg_len = pk2.seg_len.p;
+    P.node_seg_ptr = pk2.node_seg_ptr.p; P.iso = iso.p; P.warp_span = pk2.span;
+    P.val = val[b].p; P.Dblk = Dblk.p; P.Minv = Minv.p; P.Hd = Hd[b].p;
+    P.x = x.p; P.r = r.p; P.z = z.p; P.p0 = p.p; P.p1 = p1.p; P.y = y.p; P.ypart = ypart.p;
+    P.row_cnt = row_cnt.p; P.slotsA = slotsA.p; P.slotsB = slotsB.p; P.slotsC = slotsC.p; P.sc = sc.p; P.prof = prof_buf;
+    return P;
+  }
+
+  // Block-Jacobi PCG on (Ht + Lam) xt = bt for linearisation b; on return (stream order) x = xt and
+  // y = Ht xt (undamped).  One cooperative launch; no host synchronisation.
+  int pcg_enqueue(int b, double mu, const double* user_damp, const double* user_b, double rtol, int max_iter) {
     k_prepare_solve<<<grid_for(N), kBlock, 0, stream>>>(N, mu, opt.min_lm_diagonal, opt.max_lm_diagonal, ediag[b].p, scale.p, node_JL[b].p,
-                                                         Hd[b].p, gt[b].p, user_damp, user_b, Dblk.p, Minv.p, x.p, r.p, z.p, p.p, slots.p,
+                                                         Hd[b].p, gt[b].p, user_damp, user_b, Dblk.p, Minv.p, x.p, r.p, z.p, p.p, p1.p, slots.p,
                                                          counter.p, sc.p);
     launches += 1;
+    if (cooperative) {
+      PcgParams P = pcg_params(b, rtol, max_iter);
+      void* args[] = {&P};
+      CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_pcg_persistent, dim3(pk2.grid), dim3(kBlock), args, kSpmvSmemBytes, stream));
+      launches += 1;
+      return 0;
+    }
+    // fallback (device without cooperative launch): separate kernels, polled
     const int poll = 8;
     const double rtol2 = rtol * rtol;
     int enq = 0;
     while (true) {
       for (int k = 0; k < poll && enq < max_iter; ++k, ++enq) {
-        k_spmv<<<task_grid(), kBlock, 0, stream>>>(T, H, task_begin.p, task_len.p, he_col.p, val[b].p, p.p, ypart.p, sc.p, 1);
-        k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, node_task_ptr.p, ypart.p, Dblk.p, p.p, y.p, 0, slots.p, counter.p, sc.p);
+        launch_spmv(b, p.p, 1);
+        k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, pk2.node_seg_ptr.p, ypart.p, Dblk.p, p.p, y.p, 0, slots.p, counter.p, sc.p);
         k_pcg_update<<<grid_for(N), kBlock, 0, stream>>>(N, Minv.p, p.p, y.p, x.p, r.p, z.p, rtol2, max_iter, slots.p, counter.p, sc.p);
         k_pcg_direction<<<grid_for(3ull * N), kBlock, 0, stream>>>(3 * N, z.p, p.p, sc.p);
         launches += 4;
@@ -810,17 +1196,19 @@ struct gsfm_ra_solver {
       RA_TRY(fetch_scalars());
       if (h_sc->pcg_done || enq >= max_iter) break;
     }
-    if (iters) *iters = h_sc->pcg_iter;
-    if (rel_res) *rel_res = (h_sc->bb > 0.0) ? std::sqrt(h_sc->rr / h_sc->bb) : 0.0;
+    RA_TRY(spmv(b, x.p, y.p, Hd[b].p));
     return 0;
   }
 
+  double elapsed(cudaEvent_t a, cudaEvent_t b2) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b2);
+    return ms;
+  }
   double elapsed_since(cudaEvent_t a) {
     cudaEventRecord(ev[1], stream);
     cudaEventSynchronize(ev[1]);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, a, ev[1]);
-    return ms;
+    return elapsed(a, ev[1]);
   }
 };
 
@@ -850,8 +1238,7 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   CUDA_TRY(cudaGetDeviceProperties(&dp, device));
   s->sm_count = dp.multiProcessorCount;
   CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaEventCreate(&s->ev[0]));
-  CUDA_TRY(cudaEventCreate(&s->ev[1]));
+  for (auto& e : s->ev) CUDA_TRY(cudaEventCreate(&e));
   CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
 
   // shard: a contiguous range of the caller's edge list
@@ -873,9 +1260,9 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
       ent[fill[ej[k]]++] = ((uint64_t)ei[k] << 32) | (uint32_t)k | (1ull << 63);
     }
   }
-  std::vector<uint32_t> he_col(H), he_row(H), he_edge(H);
-  std::vector<uint32_t> task_row, task_begin, task_len, node_task_ptr(N + 1, 0);
+  std::vector<uint32_t> he_col(H), he_row(H), he_edge(H), iso;
   for (uint32_t a = 0; a < N; ++a) {
+    if (rowptr[a] == rowptr[a + 1]) iso.push_back(a);
     auto b = ent.begin() + rowptr[a], e = ent.begin() + rowptr[a + 1];
     std::sort(b, e, [](uint64_t x, uint64_t y) { return (x & ~(1ull << 63)) < (y & ~(1ull << 63)); });
     for (uint32_t h = rowptr[a]; h < rowptr[a + 1]; ++h) {
@@ -889,18 +1276,12 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
         return GSFM_RA_ERR_INVALID;
       }
     }
-    node_task_ptr[a] = (uint32_t)task_row.size();
-    for (uint32_t h = rowptr[a]; h < rowptr[a + 1]; h += kTaskLen) {
-      task_row.push_back(a);
-      task_begin.push_back(h);
-      task_len.push_back(std::min<uint32_t>(kTaskLen, rowptr[a + 1] - h));
-    }
   }
-  node_task_ptr[N] = (uint32_t)task_row.size();
-  s->T = (uint32_t)task_row.size();
+  s->n_iso = (uint32_t)iso.size();
 
   auto up32 = [&](DevBuf<uint32_t>& d, const uint32_t* src, size_t n) -> int {
     RA_TRY(d.alloc(n));
+    if (n == 0) return 0;
     CUDA_TRY(cudaMemcpyAsync(d.p, src, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
     return 0;
   };
@@ -911,10 +1292,57 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   };
   RA_TRY(up32(s->he_col, he_col.data(), H));
   RA_TRY(up32(s->he_row, he_row.data(), H));
-  RA_TRY(up32(s->task_row, task_row.data(), s->T));
-  RA_TRY(up32(s->task_begin, task_begin.data(), s->T));
-  RA_TRY(up32(s->task_len, task_len.data(), s->T));
-  RA_TRY(up32(s->node_task_ptr, node_task_ptr.data(), N + 1));
+  RA_TRY(up32(s->iso, iso.data(), iso.size()));
+  // balanced partitions, one per kernel class, sized to exactly one resident wave of that kernel
+  {
+    int occ_k1 = 0, occ_k2 = 0, coop = 0;
+    CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpmvSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpmvSmemBytes));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_k1, k_edges<true>, kBlock, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_k2, k_pcg_persistent, kBlock, kSpmvSmemBytes));
+    CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    s->cooperative = coop != 0 && occ_k2 > 0;
+    occ_k1 = std::max(1, occ_k1); occ_k2 = std::max(1, occ_k2);
+    auto make = [&](Partition& P, int blocks_per_sm) -> int {
+      const uint64_t max_warps = (uint64_t)s->sm_count * blocks_per_sm * kWarpsPerBlock;
+      // at least 64 half-edges per warp, ranges a multiple of 32 half-edges
+      uint64_t per = (H + max_warps - 1) / max_warps;
+      per = std::max<uint64_t>(64, (per + 31) / 32 * 32);
+      const uint32_t nw = (uint32_t)std::max<uint64_t>(1, (H + per - 1) / per);
+      std::vector<uint32_t> wptr(nw + 1, 0), srow, sbegin, slen, nptr(N + 1, 0);
+      uint32_t a = 0;
+      for (uint32_t w = 0; w < nw; ++w) {
+        const uint64_t lo = (uint64_t)w * per, hi = std::min<uint64_t>(H, lo + per);
+        wptr[w] = (uint32_t)srow.size();
+        uint64_t h = lo;
+        while (h < hi) {
+          while (rowptr[a + 1] <= h) ++a;
+          const uint64_t end = std::min<uint64_t>(hi, rowptr[a + 1]);
+          // bit 31: continuation (the row's first segment lives in an earlier warp's range)
+          srow.push_back(a | ((h > rowptr[a]) ? kSideBit : 0u)); sbegin.push_back((uint32_t)h); slen.push_back((uint32_t)(end - h));
+          h = end;
+        }
+      }
+      wptr[nw] = (uint32_t)srow.size();
+      // rows -> their (consecutive) segments
+      std::vector<uint32_t> cnt(N, 0);
+      for (uint32_t r : srow) cnt[r & ~kSideBit]++;
+      for (uint32_t r = 0; r < N; ++r) nptr[r + 1] = nptr[r] + cnt[r];
+      P.num_warps = nw; P.num_segs = (uint32_t)srow.size(); P.span = (uint32_t)per;
+      P.grid = (nw + kWarpsPerBlock - 1) / kWarpsPerBlock;
+      RA_TRY(up32(P.warp_seg_ptr, wptr.data(), wptr.size()));
+      RA_TRY(up32(P.seg_row, srow.data(), srow.size()));
+      RA_TRY(up32(P.seg_begin, sbegin.data(), sbegin.size()));
+      RA_TRY(up32(P.seg_len, slen.data(), slen.size()));
+      RA_TRY(up32(P.node_seg_ptr, nptr.data(), nptr.size()));
+      CUDA_TRY(cudaStreamSynchronize(s->stream));  // the host vectors die with this scope
+      return 0;
+    };
+    RA_TRY(make(s->pk1, occ_k1));
+    RA_TRY(make(s->pk2, occ_k2));
+    // the cooperative grid must be fully resident; node loops are grid-strided so any size works
+    s->pk2.grid = std::min<uint32_t>(s->pk2.grid, (uint32_t)s->sm_count * occ_k2);
+  }
   RA_TRY(up32(s->d_ei, ei, E));
   RA_TRY(up32(s->d_ej, ej, E));
   RA_TRY(up64(s->d_omega_ij, prob->omega_ij + 3 * e0, 3 * E));
@@ -931,15 +1359,24 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
     RA_TRY(s->omega[b].alloc(3ull * N));
     RA_TRY(s->node_q[b].alloc(4ull * N));
     RA_TRY(s->node_JL[b].alloc(9ull * N));
-    RA_TRY(s->val[b].alloc(9 * H));
+    RA_TRY(s->val[b].alloc((size_t)((H + 31) / 32) * kRecDoubles));
+    CUDA_TRY(cudaMemsetAsync(s->val[b].p, 0, (size_t)((H + 31) / 32) * kRecBytes, s->stream));
     RA_TRY(s->Hd[b].alloc(6ull * N));
     RA_TRY(s->gt[b].alloc(3ull * N));
     RA_TRY(s->ediag[b].alloc(3ull * N));
     CUDA_TRY(cudaMemsetAsync(s->omega[b].p, 0, 3ull * N * sizeof(double), s->stream));
   }
-  RA_TRY(s->part.alloc((size_t)s->T * kPartStride));
-  RA_TRY(s->ypart.alloc((size_t)s->T * 3));
-  for (DevBuf<double>* d : {&s->scale, &s->x, &s->r, &s->z, &s->p, &s->y, &s->delta}) RA_TRY(d->alloc(3ull * N));
+  k_embed_cols<<<grid_for(H), kBlock, 0, s->stream>>>(H, s->he_col.p, s->val[0].p, s->val[1].p);
+  s->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  RA_TRY(s->part.alloc((size_t)s->pk1.num_segs * kPartStride));
+  RA_TRY(s->ypart.alloc((size_t)s->pk2.num_segs * 3));
+  for (DevBuf<double>* d : {&s->scale, &s->x, &s->r, &s->z, &s->p, &s->p1, &s->y, &s->delta}) RA_TRY(d->alloc(3ull * N));
+  RA_TRY(s->slotsA.alloc(s->pk2.grid + 8));
+  RA_TRY(s->slotsB.alloc(2 * (size_t)s->pk2.grid + 8));
+  RA_TRY(s->slotsC.alloc(2 * (size_t)s->pk2.grid + 8));
+  RA_TRY(s->row_cnt.alloc(N));
+  CUDA_TRY(cudaMemsetAsync(s->row_cnt.p, 0, (size_t)N * sizeof(unsigned), s->stream));
   RA_TRY(s->Dblk.alloc(6ull * N));
   RA_TRY(s->Minv.alloc(6ull * N));
   RA_TRY(s->slots.alloc((size_t)std::max<unsigned>(grid_for(3ull * N), 64) * 4 + 64));
@@ -1017,25 +1454,31 @@ int iterate(gsfm_ra_solver* s, int max_new_iterations, gsfm_ra_summary* sum) {
     std::memset(&it, 0, sizeof(it));
     it.iteration = s->iteration;
     const int b = s->cur, c = s->cur ^ 1;
-    // ---- linear solve ------------------------------------------------------------------
+    // ---- one trust-region iteration = one stream-ordered batch, ONE host synchronisation -------
+    //   k_prepare_solve -> k_pcg_persistent (whole PCG + Ht x) -> k_apply_step (step, candidate)
+    //   -> speculative linearisation of the candidate (k_node_prep, K1, k_node_finalize)
     CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
     CUDA_TRY(cudaMemsetAsync(&s->sc.p->bad, 0, sizeof(int), s->stream));
-    int lin_it = 0;
-    double lin_res = 0;
-    RA_TRY(s->pcg(b, s->radius, nullptr, nullptr, o.pcg_rtol, o.pcg_max_iterations, &lin_it, &lin_res));
-    const bool breakdown = s->h_sc->pcg_breakdown != 0;
-    it.linear_iterations = lin_it; it.linear_residual = lin_res;
-    lin_total += lin_it;
-    // model decrease and the candidate point
-    RA_TRY(s->spmv(b, s->x.p, s->y.p, s->Hd[b].p));
+    RA_TRY(s->pcg_enqueue(b, s->radius, nullptr, nullptr, o.pcg_rtol, o.pcg_max_iterations));
     k_apply_step<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[b].p, s->x.p, s->y.p, s->gt[b].p, s->omega[b].p, s->omega[c].p, s->delta.p,
                                                         s->slots.p, s->counter.p, s->sc.p);
     s->launches += 1;
+    CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
+    RA_TRY(s->evaluate(c, true));
+    CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
     RA_TRY(s->fetch_scalars());
-    s->ms_linear += s->elapsed_since(s->ev[0]);
+    s->ms_linear += s->elapsed(s->ev[0], s->ev[2]);
+    s->ms_assemble += s->elapsed(s->ev[2], s->ev[3]);
+    const bool breakdown = s->h_sc->pcg_breakdown != 0;
+    const int lin_it = s->h_sc->pcg_iter;
+    const double lin_res = (s->h_sc->bb > 0.0) ? std::sqrt(s->h_sc->rr / s->h_sc->bb) : 0.0;
+    it.linear_iterations = lin_it; it.linear_residual = lin_res;
+    lin_total += lin_it;
     const double model_change = -s->h_sc->dg - 0.5 * s->h_sc->dHd;
     it.model_cost_change = model_change;
-    bool valid = !breakdown && !s->h_sc->bad && std::isfinite(model_change) && model_change > 0.0;
+    // `bad` also covers a non-finite candidate evaluation; a non-finite STEP shows up in step2
+    const bool step_finite = std::isfinite(s->h_sc->step2) && std::isfinite(model_change);
+    bool valid = !breakdown && step_finite && model_change > 0.0;
     it.step_is_valid = valid;
     if (!valid) {
       it.cost = s->x_cost; it.gradient_max_norm = s->gmax;
@@ -1048,11 +1491,6 @@ int iterate(gsfm_ra_solver* s, int max_new_iterations, gsfm_ra_summary* sum) {
       continue;
     }
     s->invalid_steps = 0;
-    // ---- candidate evaluation (speculative full linearisation) ---------------------------
-    CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
-    RA_TRY(s->evaluate(c, true));
-    RA_TRY(s->fetch_scalars());
-    s->ms_assemble += s->elapsed_since(s->ev[0]);
     double cand_cost = s->h_sc->cost;
     const bool cand_bad = s->h_sc->bad != 0 || !std::isfinite(cand_cost);
     if (cand_bad) cand_cost = DBL_MAX;
@@ -1229,19 +1667,36 @@ int gsfm_ra_solver_time_kernels(gsfm_ra_solver* s, int32_t repeats, double* out_
     *ms = s->elapsed_since(s->ev[0]) / repeats;
     return 0;
   };
-  RA_TRY(timed([&] { k_edges<true><<<s->task_grid(), kBlock, 0, s->stream>>>(s->T, s->H, s->task_row.p, s->task_begin.p, s->task_len.p, s->he_col.p, s->qij.p, s->U.p, s->node_q[b].p, s->loss, s->val[c].p, s->part.p); }, &out_ms[0]));
-  RA_TRY(timed([&] { k_edges<false><<<s->task_grid(), kBlock, 0, s->stream>>>(s->T, s->H, s->task_row.p, s->task_begin.p, s->task_len.p, s->he_col.p, s->qij.p, s->U.p, s->node_q[b].p, s->loss, nullptr, s->part.p); }, &out_ms[1]));
+  RA_TRY(timed([&] { s->launch_edges(b, true, s->val[c].p); }, &out_ms[0]));
+  RA_TRY(timed([&] { s->launch_edges(b, false, nullptr); }, &out_ms[1]));
   CUDA_TRY(cudaMemsetAsync(s->z.p, 0, 3ull * s->N * sizeof(double), s->stream));
-  RA_TRY(timed([&] { k_spmv<<<s->task_grid(), kBlock, 0, s->stream>>>(s->T, s->H, s->task_begin.p, s->task_len.p, s->he_col.p, s->val[b].p, s->z.p, s->ypart.p, s->sc.p, 0); }, &out_ms[2]));
-  // one PCG iteration: state is re-initialised first so pcg_done is clear, rtol 0 keeps it running
-  k_prepare_solve<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->radius, s->opt.min_lm_diagonal, s->opt.max_lm_diagonal, s->ediag[b].p, s->scale.p, s->node_JL[b].p,
-                                                          s->Hd[b].p, s->gt[b].p, nullptr, nullptr, s->Dblk.p, s->Minv.p, s->x.p, s->r.p, s->z.p, s->p.p, s->slots.p, s->counter.p, s->sc.p);
-  RA_TRY(timed([&] {
-    k_spmv<<<s->task_grid(), kBlock, 0, s->stream>>>(s->T, s->H, s->task_begin.p, s->task_len.p, s->he_col.p, s->val[b].p, s->p.p, s->ypart.p, s->sc.p, 1);
-    k_spmv_finish<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->node_task_ptr.p, s->ypart.p, s->Dblk.p, s->p.p, s->y.p, 0, s->slots.p, s->counter.p, s->sc.p);
-    k_pcg_update<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->Minv.p, s->p.p, s->y.p, s->x.p, s->r.p, s->z.p, 0.0, 1 << 30, s->slots.p, s->counter.p, s->sc.p);
-    k_pcg_direction<<<grid_for(3ull * s->N), kBlock, 0, s->stream>>>(3 * s->N, s->z.p, s->p.p, s->sc.p);
-  }, &out_ms[3]));
+  RA_TRY(timed([&] { s->launch_spmv(b, s->z.p, std::getenv("GSFM_RA_DEBUG_NOGATHER") ? 2 : 0); }, &out_ms[2]));
+  // one PCG iteration inside the persistent kernel: (time of R iterations) / R with rtol = 0
+  {
+    const int R = std::max(8, (int)repeats);
+    RA_TRY(s->pcg_enqueue(b, s->radius, nullptr, nullptr, 0.0, R));  // warm
+    CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
+    RA_TRY(s->pcg_enqueue(b, s->radius, nullptr, nullptr, 0.0, R));
+    RA_TRY(s->fetch_scalars());
+    const int done_it = std::max(1, s->h_sc->pcg_iter);
+    out_ms[3] = s->elapsed_since(s->ev[0]) / done_it;
+    if (std::getenv("GSFM_RA_PROFILE_PHASES")) {
+      DevBuf<unsigned long long> pb;
+      RA_TRY(pb.alloc(8));
+      CUDA_TRY(cudaMemsetAsync(pb.p, 0, 64, s->stream));
+      s->prof_buf = pb.p;
+      const int rc = s->pcg_enqueue(b, s->radius, nullptr, nullptr, 0.0, R);
+      s->prof_buf = nullptr;
+      RA_TRY(rc);
+      unsigned long long hp[8];
+      CUDA_TRY(cudaMemcpyAsync(hp, pb.p, 64, cudaMemcpyDeviceToHost, s->stream));
+      CUDA_TRY(cudaStreamSynchronize(s->stream));
+      const double n = std::max<double>(1.0, (double)hp[6]);
+      std::fprintf(stderr, "[gsfm_ra] PCG phases of block 0, us per iteration: spmv_pass %.2f | reduce+grid.sync %.2f | slots sum %.2f | vector update %.2f | "
+                   "reduce+grid.sync %.2f | slots sum %.2f  (%d iterations)\n", hp[0] / n / 1e3, hp[1] / n / 1e3, hp[2] / n / 1e3, hp[3] / n / 1e3,
+                   hp[4] / n / 1e3, hp[5] / n / 1e3, (int)hp[6]);
+    }
+  }
   // restore the linearisation-dependent partials (K1 scratch wrote `part`): re-run the finalize inputs
   RA_TRY(s->evaluate(b, true));
   RA_TRY(s->fetch_scalars());
@@ -1387,9 +1842,10 @@ int gsfm_ra_pcg(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, const 
   CUDA_TRY(cudaMemcpyAsync(db.p, b, 3ull * N * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   if (damping) CUDA_TRY(cudaMemcpyAsync(dd.p, damping, 3ull * N * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   else CUDA_TRY(cudaMemsetAsync(dd.p, 0, 3ull * N * sizeof(double), s->stream));
-  int it = 0;
-  double res = 0;
-  RA_TRY(s->pcg(0, 1.0, dd.p, db.p, rtol, max_iterations, &it, &res));
+  RA_TRY(s->pcg_enqueue(0, 1.0, dd.p, db.p, rtol, max_iterations));
+  RA_TRY(s->fetch_scalars());
+  const int it = s->h_sc->pcg_iter;
+  const double res = (s->h_sc->bb > 0.0) ? std::sqrt(s->h_sc->rr / s->h_sc->bb) : 0.0;
   // x = Jl^-1 xt
   k_apply_step<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[0].p, s->x.p, nullptr, nullptr, nullptr, nullptr, s->delta.p, s->slots.p, s->counter.p, s->sc.p);
   CUDA_TRY(cudaGetLastError());
