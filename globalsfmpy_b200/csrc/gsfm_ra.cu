@@ -288,7 +288,10 @@ k_edges(uint32_t num_warps, uint64_t H, const uint32_t* __restrict__ warp_seg_pt
 // diagonal diag(Jl^T Hd Jl) (for Jacobi scaling and the LM diagonal), total cost.
 __global__ void k_node_finalize(uint32_t N, const uint32_t* __restrict__ node_task_ptr, const double* __restrict__ part,
                                 const double* __restrict__ node_JL, double* __restrict__ Hd, double* __restrict__ gt,
-                                double* __restrict__ ediag, int cost_only, double* slots, unsigned* counter, DevScalars* sc) {
+                                double* __restrict__ ediag, int cost_only, int stage, double* tail, double* slots, unsigned* counter,
+                                DevScalars* sc) {
+  // stage 0: single GPU, everything.  Edge-sharded: stage 1 = local sums (Hd, gt, tail = {cost, bad}) which
+  // the host all-reduces, stage 2 = the per-view post-processing on the reduced sums.
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   double v[2] = {0.0, 0.0};
   double gm = 0.0;
@@ -296,18 +299,26 @@ __global__ void k_node_finalize(uint32_t N, const uint32_t* __restrict__ node_ta
     double a[kPartStride];
 #pragma unroll
     for (int k = 0; k < kPartStride; ++k) a[k] = 0.0;
-    for (uint32_t t = node_task_ptr[i]; t < node_task_ptr[i + 1]; ++t) {
-      if (cost_only) a[9] += part[(size_t)t * kPartStride + 9];
-      else {
+    if (stage != 2) {
+      for (uint32_t t = node_task_ptr[i]; t < node_task_ptr[i + 1]; ++t) {
+        if (cost_only) a[9] += part[(size_t)t * kPartStride + 9];
+        else {
 #pragma unroll
-        for (int k = 0; k < kPartStride; ++k) a[k] += part[(size_t)t * kPartStride + k];
+          for (int k = 0; k < kPartStride; ++k) a[k] += part[(size_t)t * kPartStride + k];
+        }
       }
-    }
-    v[0] = a[9];
-    if (!cost_only) {
+      v[0] = a[9];
+      if (!cost_only) {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) Hd[6 * (size_t)i + k] = a[k];
-      gt[3 * (size_t)i] = a[6]; gt[3 * (size_t)i + 1] = a[7]; gt[3 * (size_t)i + 2] = a[8];
+        for (int k = 0; k < 6; ++k) Hd[6 * (size_t)i + k] = a[k];
+        gt[3 * (size_t)i] = a[6]; gt[3 * (size_t)i + 1] = a[7]; gt[3 * (size_t)i + 2] = a[8];
+      }
+    } else if (!cost_only) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) a[k] = Hd[6 * (size_t)i + k];
+      a[6] = gt[3 * (size_t)i]; a[7] = gt[3 * (size_t)i + 1]; a[8] = gt[3 * (size_t)i + 2];
+    }
+    if (!cost_only && stage != 1) {
       double J[9];
 #pragma unroll
       for (int k = 0; k < 9; ++k) J[k] = node_JL[9 * (size_t)i + k];
@@ -320,13 +331,15 @@ __global__ void k_node_finalize(uint32_t N, const uint32_t* __restrict__ node_ta
     }
   }
   // max |g|: block max -> atomicMax on the bit pattern (non-negative doubles order like uint64)
-  if (!cost_only) {
+  if (!cost_only && stage != 1) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, o));
     if ((threadIdx.x & 31) == 0 && gm > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(&sc->gmax), (unsigned long long)__double_as_longlong(gm));
   }
   double tot[2];
   if (grid_sum<2>(v, slots, counter, tot) && threadIdx.x == 0) {
+    if (stage == 1) { tail[0] = tot[0]; tail[1] = tot[1]; return; }
+    if (stage == 2) { tot[0] = tail[0]; tot[1] += tail[1]; }
     sc->cost = tot[0];
     if (tot[1] != 0.0 || !isfinite(tot[0])) sc->bad = 1;
   }
@@ -541,8 +554,9 @@ k_spmv(uint32_t num_warps, uint64_t H, uint32_t warp_span, const uint32_t* __res
 // added after the cross-GPU reduction).  mode 0: write y, reduce p.y -> alpha (PCG step 1).
 // mode 1: y only.
 __global__ void k_spmv_finish(uint32_t N, const uint32_t* __restrict__ node_task_ptr, const double* __restrict__ ypart,
-                              const double* __restrict__ Dblk, const double* __restrict__ x, double* __restrict__ y,
+                              const double* __restrict__ Dblk, const double* __restrict__ x, double* y, const double* ysum,
                               int mode, double* slots, unsigned* counter, DevScalars* sc) {
+  // ysum != null: the off-diagonal part was already summed (and all-reduced across GPUs) into ysum
   if (mode == 0 && sc->pcg_done) return;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   double v[1] = {0.0};
@@ -550,9 +564,11 @@ __global__ void k_spmv_finish(uint32_t N, const uint32_t* __restrict__ node_task
     double xi[3] = {x[3 * (size_t)i], x[3 * (size_t)i + 1], x[3 * (size_t)i + 2]};
     double yi[3] = {0.0, 0.0, 0.0};
     if (Dblk) sym_mul_vec(Dblk + 6 * (size_t)i, xi, yi);
-    for (uint32_t t = node_task_ptr[i]; t < node_task_ptr[i + 1]; ++t) {
-      yi[0] += ypart[3 * (size_t)t]; yi[1] += ypart[3 * (size_t)t + 1]; yi[2] += ypart[3 * (size_t)t + 2];
-    }
+    if (ysum) { yi[0] += ysum[3 * (size_t)i]; yi[1] += ysum[3 * (size_t)i + 1]; yi[2] += ysum[3 * (size_t)i + 2]; }
+    else
+      for (uint32_t t = node_task_ptr[i]; t < node_task_ptr[i + 1]; ++t) {
+        yi[0] += ypart[3 * (size_t)t]; yi[1] += ypart[3 * (size_t)t + 1]; yi[2] += ypart[3 * (size_t)t + 2];
+      }
     y[3 * (size_t)i] = yi[0]; y[3 * (size_t)i + 1] = yi[1]; y[3 * (size_t)i + 2] = yi[2];
     v[0] = xi[0] * yi[0] + xi[1] * yi[1] + xi[2] * yi[2];
   }
@@ -1053,6 +1069,63 @@ inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kBlock - 1) / kBlo
 // ------------------------------------------------------------------------------------------
 // the resident solver
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen) so the single-GPU library has no link dependency on it.  When the
+// host process already loaded a libnccl.so.2 (e.g. PyTorch's bundled one) the same copy is reused.
+// ------------------------------------------------------------------------------------------
+namespace ncclx {
+constexpr int kUniqueIdBytes = 128;
+struct UniqueId { char internal[kUniqueIdBytes]; };
+typedef void* Comm;
+typedef int (*GetUniqueId_t)(UniqueId*);
+typedef int (*CommInitRank_t)(Comm*, int, UniqueId, int);
+typedef int (*AllReduce_t)(const void*, void*, size_t, int /*dtype*/, int /*op*/, Comm, cudaStream_t);
+typedef int (*CommDestroy_t)(Comm);
+typedef const char* (*GetErrorString_t)(int);
+constexpr int kFloat64 = 8;  // ncclDouble
+constexpr int kSum = 0;      // ncclSum
+struct Api {
+  void* handle = nullptr;
+  GetUniqueId_t GetUniqueId = nullptr;
+  CommInitRank_t CommInitRank = nullptr;
+  AllReduce_t AllReduce = nullptr;
+  CommDestroy_t CommDestroy = nullptr;
+  GetErrorString_t GetErrorString = nullptr;
+};
+Api* api() {
+  static Api a;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* env = std::getenv("GSFM_RA_NCCL_LIB");
+    const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      if (!n) continue;
+      a.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (a.handle) break;
+    }
+    if (a.handle) {
+      a.GetUniqueId = (GetUniqueId_t)dlsym(a.handle, "ncclGetUniqueId");
+      a.CommInitRank = (CommInitRank_t)dlsym(a.handle, "ncclCommInitRank");
+      a.AllReduce = (AllReduce_t)dlsym(a.handle, "ncclAllReduce");
+      a.CommDestroy = (CommDestroy_t)dlsym(a.handle, "ncclCommDestroy");
+      a.GetErrorString = (GetErrorString_t)dlsym(a.handle, "ncclGetErrorString");
+      if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.CommDestroy) a.handle = nullptr;
+    }
+  }
+  return a.handle ? &a : nullptr;
+}
+}  // namespace ncclx
+
+#define NCCL_TRY(expr)                                                                                     \
+  do {                                                                                                     \
+    int r__ = (expr);                                                                                      \
+    if (r__ != 0) {                                                                                        \
+      set_error("%s failed: %s", #expr, ncclx::api()->GetErrorString ? ncclx::api()->GetErrorString(r__) : "?"); \
+      return GSFM_RA_ERR_CUDA;                                                                             \
+    }                                                                                                      \
+  } while (0)
+
 // A balanced work partition of the half-edge array for one kernel class: num_warps equal
 // contiguous ranges (a multiple of 32 half-edges each), every range cut at row boundaries into
 // segments.  num_warps = SMs x resident blocks x warps per block of THAT kernel, so the kernel runs
@@ -1069,6 +1142,7 @@ struct gsfm_ra_solver {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   uint32_t N = 0;
   uint64_t E = 0;       // edges of this shard
+  uint64_t edge_begin = 0;
   uint64_t H = 0;       // half-edges of this shard (2E)
   int rank = 0, world = 1;
   int error_type = 4;
@@ -1076,6 +1150,7 @@ struct gsfm_ra_solver {
   DevLoss loss;
   int64_t launches = 0;
   bool cooperative = true;  // persistent PCG kernel available
+  ncclx::Comm comm = nullptr;  // edge-sharded exchange (world > 1)
 
   // structure
   DevBuf<uint32_t> he_col, he_row, iso;
@@ -1087,7 +1162,12 @@ struct gsfm_ra_solver {
   DevBuf<uint32_t> d_ei, d_ej;
   DevBuf<double> d_omega_ij, d_cov6, d_weight;
   // linearisation, double buffered: [cur] is the accepted point, [cur^1] the candidate
-  DevBuf<double> omega[2], node_q[2], node_JL[2], val[2], Hd[2], gt[2], ediag[2];
+  DevBuf<double> omega[2], node_q[2], node_JL[2], val[2], ediag[2];
+  // lin[b] = [Hd 6N | gt 3N | cost, bad]: everything one evaluation sums over edges, contiguous so the
+  // edge-sharded solver reduces it across GPUs with ONE all-reduce
+  DevBuf<double> lin[2];
+  double* Hd_p[2] = {nullptr, nullptr};
+  double* gt_p[2] = {nullptr, nullptr};
   DevBuf<double> part;
   int cur = 0;
   // PCG
@@ -1110,9 +1190,17 @@ struct gsfm_ra_solver {
   double ms_setup = 0, ms_assemble = 0, ms_linear = 0, ms_cost = 0;
 
   ~gsfm_ra_solver() {
+    if (comm && ncclx::api()) ncclx::api()->CommDestroy(comm);
     if (h_sc) cudaFreeHost(h_sc);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
+  }
+
+  bool sharded() const { return world > 1; }
+  int allreduce(double* buf, size_t count) {
+    if (!comm) { set_error("sharded solver used before gsfm_ra_solver_comm_init"); return GSFM_RA_ERR_INVALID; }
+    NCCL_TRY(ncclx::api()->AllReduce(buf, buf, count, ncclx::kFloat64, ncclx::kSum, comm, stream));
+    return 0;
   }
 
   int fetch_scalars() {
@@ -1139,8 +1227,21 @@ struct gsfm_ra_solver {
     CUDA_TRY(cudaMemsetAsync(&sc.p->gmax, 0, sizeof(double), stream));
     k_node_prep<<<grid_for(N), kBlock, 0, stream>>>(N, omega[b].p, node_q[b].p, node_JL[b].p, slots.p, counter.p, sc.p);
     launch_edges(b, jacobian, val[b].p);
-    k_node_finalize<<<grid_for(N), kBlock, 0, stream>>>(N, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd[b].p, gt[b].p, ediag[b].p, jacobian ? 0 : 1,
-                                                         slots.p, counter.p, sc.p);
+    double* tail = lin[b].p + 9ull * N;
+    const int co = jacobian ? 0 : 1;
+    if (!sharded()) {
+      k_node_finalize<<<grid_for(N), kBlock, 0, stream>>>(N, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd_p[b], gt_p[b], ediag[b].p, co, 0, tail,
+                                                           slots.p, counter.p, sc.p);
+    } else {
+      // edge-sharded: local sums -> ONE all-reduce of [Hd | gt | cost, bad] -> per-view post-processing
+      k_node_finalize<<<grid_for(N), kBlock, 0, stream>>>(N, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd_p[b], gt_p[b], ediag[b].p, co, 1, tail,
+                                                           slots.p, counter.p, sc.p);
+      if (jacobian) RA_TRY(allreduce(lin[b].p, 9ull * N + 2));
+      else RA_TRY(allreduce(tail, 2));
+      k_node_finalize<<<grid_for(N), kBlock, 0, stream>>>(N, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd_p[b], gt_p[b], ediag[b].p, co, 2, tail,
+                                                           slots.p, counter.p, sc.p);
+      launches += 2;
+    }
     launches += 3;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -1149,7 +1250,14 @@ struct gsfm_ra_solver {
   // y = (Ht offdiag + diag_blocks) x on linearisation b (separate-kernel path).
   int spmv(int b, const double* xin, double* yout, const double* diag_blocks) {
     launch_spmv(b, xin, 0);
-    k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, pk2.node_seg_ptr.p, ypart.p, diag_blocks, xin, yout, 1, slots.p, counter.p, sc.p);
+    if (!sharded()) {
+      k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, pk2.node_seg_ptr.p, ypart.p, diag_blocks, xin, yout, nullptr, 1, slots.p, counter.p, sc.p);
+    } else {
+      k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, pk2.node_seg_ptr.p, ypart.p, nullptr, xin, yout, nullptr, 1, slots.p, counter.p, sc.p);
+      RA_TRY(allreduce(yout, 3ull * N));
+      k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, pk2.node_seg_ptr.p, ypart.p, diag_blocks, xin, yout, yout, 1, slots.p, counter.p, sc.p);
+      launches += 2;
+    }
     launches += 2;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -1160,7 +1268,7 @@ struct gsfm_ra_solver {
     P.N = N; P.num_warps = pk2.num_warps; P.n_iso = n_iso; P.max_iter = max_iter; P.H = H; P.rtol2 = rtol * rtol;
     P.warp_seg_ptr = pk2.warp_seg_ptr.p; P.seg_row = pk2.seg_row.p; P.seg_begin = pk2.seg_begin.p; P.seg_len = pk2.seg_len.p;
     P.node_seg_ptr = pk2.node_seg_ptr.p; P.iso = iso.p; P.warp_span = pk2.span;
-    P.val = val[b].p; P.Dblk = Dblk.p; P.Minv = Minv.p; P.Hd = Hd[b].p;
+    P.val = val[b].p; P.Dblk = Dblk.p; P.Minv = Minv.p; P.Hd = Hd_p[b];
     P.x = x.p; P.r = r.p; P.z = z.p; P.p0 = p.p; P.p1 = p1.p; P.y = y.p; P.ypart = ypart.p;
     P.row_cnt = row_cnt.p; P.slotsA = slotsA.p; P.slotsB = slotsB.p; P.slotsC = slotsC.p; P.sc = sc.p; P.prof = prof_buf;
     return P;
@@ -1170,10 +1278,10 @@ struct gsfm_ra_solver {
   // y = Ht xt (undamped).  One cooperative launch; no host synchronisation.
   int pcg_enqueue(int b, double mu, const double* user_damp, const double* user_b, double rtol, int max_iter) {
     k_prepare_solve<<<grid_for(N), kBlock, 0, stream>>>(N, mu, opt.min_lm_diagonal, opt.max_lm_diagonal, ediag[b].p, scale.p, node_JL[b].p,
-                                                         Hd[b].p, gt[b].p, user_damp, user_b, Dblk.p, Minv.p, x.p, r.p, z.p, p.p, p1.p, slots.p,
+                                                         Hd_p[b], gt_p[b], user_damp, user_b, Dblk.p, Minv.p, x.p, r.p, z.p, p.p, p1.p, slots.p,
                                                          counter.p, sc.p);
     launches += 1;
-    if (cooperative) {
+    if (cooperative && !sharded()) {
       PcgParams P = pcg_params(b, rtol, max_iter);
       void* args[] = {&P};
       CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_pcg_persistent, dim3(pk2.grid), dim3(kBlock), args, kSpmvSmemBytes, stream));
@@ -1187,7 +1295,15 @@ struct gsfm_ra_solver {
     while (true) {
       for (int k = 0; k < poll && enq < max_iter; ++k, ++enq) {
         launch_spmv(b, p.p, 1);
-        k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, pk2.node_seg_ptr.p, ypart.p, Dblk.p, p.p, y.p, 0, slots.p, counter.p, sc.p);
+        if (!sharded()) {
+          k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, pk2.node_seg_ptr.p, ypart.p, Dblk.p, p.p, y.p, nullptr, 0, slots.p, counter.p, sc.p);
+        } else {
+          // the ONE collective of a CG step: all-reduce of the 3N partial matvec
+          k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, pk2.node_seg_ptr.p, ypart.p, nullptr, p.p, y.p, nullptr, 1, slots.p, counter.p, sc.p);
+          RA_TRY(allreduce(y.p, 3ull * N));
+          k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, pk2.node_seg_ptr.p, ypart.p, Dblk.p, p.p, y.p, y.p, 0, slots.p, counter.p, sc.p);
+          launches += 2;
+        }
         k_pcg_update<<<grid_for(N), kBlock, 0, stream>>>(N, Minv.p, p.p, y.p, x.p, r.p, z.p, rtol2, max_iter, slots.p, counter.p, sc.p);
         k_pcg_direction<<<grid_for(3ull * N), kBlock, 0, stream>>>(3 * N, z.p, p.p, sc.p);
         launches += 4;
@@ -1196,7 +1312,7 @@ struct gsfm_ra_solver {
       RA_TRY(fetch_scalars());
       if (h_sc->pcg_done || enq >= max_iter) break;
     }
-    RA_TRY(spmv(b, x.p, y.p, Hd[b].p));
+    RA_TRY(spmv(b, x.p, y.p, Hd_p[b]));
     return 0;
   }
 
@@ -1244,7 +1360,7 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   // shard: a contiguous range of the caller's edge list
   const uint64_t e0 = prob->num_edges * (uint64_t)rank / world, e1 = prob->num_edges * (uint64_t)(rank + 1) / world;
   const uint64_t E = e1 - e0, H = 2 * E;
-  s->N = N; s->E = E; s->H = H;
+  s->N = N; s->E = E; s->H = H; s->edge_begin = e0;
   const uint32_t* ei = prob->edge_i + e0;
   const uint32_t* ej = prob->edge_j + e0;
 
@@ -1361,8 +1477,9 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
     RA_TRY(s->node_JL[b].alloc(9ull * N));
     RA_TRY(s->val[b].alloc((size_t)((H + 31) / 32) * kRecDoubles));
     CUDA_TRY(cudaMemsetAsync(s->val[b].p, 0, (size_t)((H + 31) / 32) * kRecBytes, s->stream));
-    RA_TRY(s->Hd[b].alloc(6ull * N));
-    RA_TRY(s->gt[b].alloc(3ull * N));
+    RA_TRY(s->lin[b].alloc(9ull * N + 2));
+    s->Hd_p[b] = s->lin[b].p;
+    s->gt_p[b] = s->lin[b].p + 6ull * N;
     RA_TRY(s->ediag[b].alloc(3ull * N));
     CUDA_TRY(cudaMemsetAsync(s->omega[b].p, 0, 3ull * N * sizeof(double), s->stream));
   }
@@ -1460,7 +1577,7 @@ int iterate(gsfm_ra_solver* s, int max_new_iterations, gsfm_ra_summary* sum) {
     CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
     CUDA_TRY(cudaMemsetAsync(&s->sc.p->bad, 0, sizeof(int), s->stream));
     RA_TRY(s->pcg_enqueue(b, s->radius, nullptr, nullptr, o.pcg_rtol, o.pcg_max_iterations));
-    k_apply_step<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[b].p, s->x.p, s->y.p, s->gt[b].p, s->omega[b].p, s->omega[c].p, s->delta.p,
+    k_apply_step<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[b].p, s->x.p, s->y.p, s->gt_p[b], s->omega[b].p, s->omega[c].p, s->delta.p,
                                                         s->slots.p, s->counter.p, s->sc.p);
     s->launches += 1;
     CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
@@ -1610,7 +1727,6 @@ int gsfm_ra_solver_create(const gsfm_ra_problem* problem, const gsfm_ra_options*
 }
 int gsfm_ra_solver_create_sharded(const gsfm_ra_problem* problem, const gsfm_ra_options* options, int32_t rank, int32_t world_size,
                                   gsfm_ra_solver** out) {
-  if (world_size != 1) { set_error("sharded solver: multi-GPU exchange is not wired up in this build"); return GSFM_RA_ERR_UNSUPPORTED; }
   return build_solver(problem, options, rank, world_size, out);
 }
 void gsfm_ra_solver_destroy(gsfm_ra_solver* solver) {
@@ -1643,12 +1759,28 @@ int gsfm_ra_solver_iterate(gsfm_ra_solver* s, int32_t num_iterations, gsfm_ra_su
   if (s->opt.linear_solver != GSFM_RA_SOLVER_PCG) { set_error("linear solver %d is not implemented (PCG only)", s->opt.linear_solver); return GSFM_RA_ERR_UNSUPPORTED; }
   return iterate(s, num_iterations, summary);
 }
-int gsfm_ra_solver_ipc_export(gsfm_ra_solver*, uint8_t*) { set_error("peer-memory exchange is not implemented in this build"); return GSFM_RA_ERR_UNSUPPORTED; }
-int gsfm_ra_solver_ipc_import(gsfm_ra_solver*, const uint8_t*) { set_error("peer-memory exchange is not implemented in this build"); return GSFM_RA_ERR_UNSUPPORTED; }
-int gsfm_ra_solver_row_range(const gsfm_ra_solver* s, uint32_t* row_begin, uint32_t* row_end) {
+int gsfm_ra_comm_unique_id(uint8_t* id) {
+  if (!id) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
+  if (!ncclx::api()) { set_error("libnccl.so.2 could not be loaded (set GSFM_RA_NCCL_LIB)"); return GSFM_RA_ERR_UNSUPPORTED; }
+  ncclx::UniqueId u;
+  NCCL_TRY(ncclx::api()->GetUniqueId(&u));
+  std::memcpy(id, u.internal, ncclx::kUniqueIdBytes);
+  return 0;
+}
+int gsfm_ra_solver_comm_init(gsfm_ra_solver* s, const uint8_t* id) {
+  if (!s || !id) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
+  if (s->world == 1) return 0;
+  if (!ncclx::api()) { set_error("libnccl.so.2 could not be loaded (set GSFM_RA_NCCL_LIB)"); return GSFM_RA_ERR_UNSUPPORTED; }
+  CUDA_TRY(cudaSetDevice(s->device));
+  ncclx::UniqueId u;
+  std::memcpy(u.internal, id, ncclx::kUniqueIdBytes);
+  NCCL_TRY(ncclx::api()->CommInitRank(&s->comm, s->world, u, s->rank));
+  return 0;
+}
+int gsfm_ra_solver_edge_range(const gsfm_ra_solver* s, uint64_t* e0, uint64_t* e1) {
   if (!s) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
-  if (row_begin) *row_begin = 0;
-  if (row_end) *row_end = s->N;
+  if (e0) *e0 = s->edge_begin;
+  if (e1) *e1 = s->edge_begin + s->E;
   return 0;
 }
 
@@ -1780,7 +1912,7 @@ int gsfm_ra_assemble(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, c
   if (hdiag || gradient) {
     RA_TRY(dh.alloc(9ull * N));
     RA_TRY(dg.alloc(3ull * N));
-    k_export_nodes<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->Hd[0].p, s->gt[0].p, s->node_JL[0].p, dh.p, dg.p);
+    k_export_nodes<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->Hd_p[0], s->gt_p[0], s->node_JL[0].p, dh.p, dg.p);
     CUDA_TRY(cudaGetLastError());
     if (hdiag) CUDA_TRY(cudaMemcpyAsync(hdiag, dh.p, 9ull * N * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     if (gradient) CUDA_TRY(cudaMemcpyAsync(gradient, dg.p, 3ull * N * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -1820,7 +1952,7 @@ int gsfm_ra_spmv(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, const
   if (damping) { RA_TRY(dd.alloc(3ull * N)); CUDA_TRY(cudaMemcpyAsync(dd.p, damping, 3ull * N * sizeof(double), cudaMemcpyHostToDevice, s->stream)); }
   // y = Jl^T Ht (Jl x) + damping .* x
   k_node_apply<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[0].p, dx.p, 0, nullptr, nullptr, s->p.p);
-  RA_TRY(s->spmv(0, s->p.p, s->y.p, s->Hd[0].p));
+  RA_TRY(s->spmv(0, s->p.p, s->y.p, s->Hd_p[0]));
   k_node_apply<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[0].p, s->y.p, 1, dd.p, dx.p, s->z.p);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(y, s->z.p, 3ull * N * sizeof(double), cudaMemcpyDeviceToHost, s->stream));

@@ -121,6 +121,25 @@ class Solver:
             capi.check(capi.lib().gsfm_ra_solver_create_sharded(C.byref(prob.c), C.byref(options), rank, world_size,
                                                                 C.byref(self._h)))
 
+    def connect(self, dist):
+        """Join the ranks of a sharded solver: rank 0 makes the NCCL id, torch.distributed (`dist`, already
+        initialised by the host framework) broadcasts it, every rank joins.  Collective."""
+        import torch
+        ident = np.zeros(capi.COMM_ID_BYTES, np.uint8)
+        if dist.get_rank() == 0:
+            capi.check(capi.lib().gsfm_ra_comm_unique_id(capi.ptr(ident, C.c_uint8)))
+        t = torch.from_numpy(ident)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, src=0)
+        ident = np.ascontiguousarray(t.cpu().numpy())
+        capi.check(capi.lib().gsfm_ra_solver_comm_init(self._h, capi.ptr(ident, C.c_uint8)))
+
+    def edge_range(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        capi.check(capi.lib().gsfm_ra_solver_edge_range(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def close(self):
         if self._h:
             capi.lib().gsfm_ra_solver_destroy(self._h)

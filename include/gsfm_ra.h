@@ -199,9 +199,11 @@ int gsfm_ra_solve(const gsfm_ra_problem* problem, const gsfm_ra_options* options
 /* ---- resident solver ---------------------------------------------------------*/
 int gsfm_ra_solver_create(const gsfm_ra_problem* problem, const gsfm_ra_options* options,
                           gsfm_ra_solver** out);
-/* Row-sharded variant: this process owns the rows [row_begin,row_end) of the
- * normal equations (all half-edges whose row view lies in the range).  peers are
- * exchanged with gsfm_ra_solver_ipc_* below; world_size==1 is the plain solver. */
+/* Edge-sharded variant (one process per GPU): every rank passes the SAME full problem and
+ * keeps the contiguous slice [E*rank/world, E*(rank+1)/world) of its edge list resident.  All ranks hold
+ * all N rotations and every PCG vector; they exchange one all-reduce of the 9N+2 per-view sums per outer
+ * iteration and one all-reduce of the 3N partial matvec per CG step.  world_size==1 is the plain solver.
+ * A sharded solver must be connected with gsfm_ra_solver_comm_init before it iterates.             */
 int gsfm_ra_solver_create_sharded(const gsfm_ra_problem* problem, const gsfm_ra_options* options,
                                   int32_t rank, int32_t world_size, gsfm_ra_solver** out);
 void gsfm_ra_solver_destroy(gsfm_ra_solver* solver);
@@ -212,13 +214,14 @@ int gsfm_ra_solver_reset(gsfm_ra_solver* solver);
 /* Run at most num_iterations further trust-region iterations from the current
  * state (stops earlier on convergence unless tolerances are <= 0).            */
 int gsfm_ra_solver_iterate(gsfm_ra_solver* solver, int32_t num_iterations, gsfm_ra_summary* summary);
-/* Peer-memory exchange for the sharded solver: each rank exports an opaque
- * 64-byte handle; all ranks then import every rank's handle (world_size*64 B). */
-#define GSFM_RA_IPC_HANDLE_BYTES 128
-int gsfm_ra_solver_ipc_export(gsfm_ra_solver* solver, uint8_t* handle /*[GSFM_RA_IPC_HANDLE_BYTES]*/);
-int gsfm_ra_solver_ipc_import(gsfm_ra_solver* solver, const uint8_t* handles /*[world][GSFM_RA_IPC_HANDLE_BYTES]*/);
-/* Row range owned by this rank (load-balanced on half-edge count). */
-int gsfm_ra_solver_row_range(const gsfm_ra_solver* solver, uint32_t* row_begin, uint32_t* row_end);
+/* Exchange set-up for the sharded solver (NCCL over NVLink; libnccl.so.2 is bound at run time, so
+ * the single-GPU path has no dependency on it).  Rank 0 creates a 128-byte id, the host framework
+ * broadcasts it (e.g. torch.distributed), every rank then joins -- collective, all ranks must call. */
+#define GSFM_RA_COMM_ID_BYTES 128
+int gsfm_ra_comm_unique_id(uint8_t* id /*[GSFM_RA_COMM_ID_BYTES]*/);
+int gsfm_ra_solver_comm_init(gsfm_ra_solver* solver, const uint8_t* id /*[GSFM_RA_COMM_ID_BYTES]*/);
+/* Edge range of the caller's list owned by this rank. */
+int gsfm_ra_solver_edge_range(const gsfm_ra_solver* solver, uint64_t* edge_begin, uint64_t* edge_end);
 
 /* The CUDA stream (a cudaStream_t) every kernel of this solver is launched on, so a host
  * framework can bracket calls with its own events.                               */
