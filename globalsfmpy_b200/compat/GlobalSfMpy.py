@@ -1,0 +1,524 @@
+"""`GlobalSfMpy`-compatible module: the rotation-averaging slice of the reference's pybind11 surface
+(bind_src/GlobalSfMpy.cpp), backed by the B200 solver through the C ABI.
+
+    sys.path.append('<repo>/globalsfmpy_b200/compat')     # where the reference scripts append '../build'
+    import GlobalSfMpy as sfm
+
+Everything `scripts/sfm_pipeline.py` touches through step 3 (global rotations) is here with the reference's names
+and argument meaning: options + `load_1DSFM_config`, `Reconstruction`, `ViewGraph`,
+`MapEdgesCovariance`, `Read1DSFM`, `ReadCovariance`, `ReconstructionBuilder.CheckView/get_view_graph/get_reconstruction`,
+`GlobalReconstructionEstimator.FilterInitialViewGraphAndCalibrateCameras / EstimateGlobalRotationsUncertainty /
+EstimateGlobalRotations / OrientationsFromMaximumSpanningTree / FilterRotations / orientations`, `SetOrientations`,
+`LossFunction`, `RotationEstimator`, `NonlinearRotationEstimator`, `RotationErrorType`, the MAGSAC gamma constants.
+Steps 4-9 of the pipeline (translations, positions, triangulation, bundle adjustment, file writers) are the rest of
+TheiaSfM and are out of scope: they raise NotImplementedError naming the reference function.
+"""
+import enum
+import math
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+
+from globalsfmpy_b200 import _capi as _capi  # noqa: E402
+from globalsfmpy_b200 import solver as _solver  # noqa: E402
+from globalsfmpy_b200 import viewgraph as _vg  # noqa: E402
+from globalsfmpy_b200.loss_functions import LossFunction  # noqa: E402,F401
+from globalsfmpy_b200.losses import UnsupportedLoss, loss_to_struct  # noqa: E402,F401
+
+
+# ------------------------------------------------------------------------------- enums, containers
+class RotationErrorType(enum.IntEnum):          # include/pairwise_rotation_error_quat.hpp:50-61, bind:431-439
+    QUATERNION_NORM = 0
+    ROTATION_MAT_FNORM = 1
+    QUATERNION_COSINE = 2
+    ANGLE_AXIS_COVARIANCE = 3
+    ANGLE_AXIS = 4
+    ANGLE_AXIS_INLIERS = 5
+    ANGLE_AXIS_COV_INLIERS = 6
+    ANGLE_AXIS_COVTRACE = 7
+    ANGLE_AXIS_COVNORM = 8
+
+
+class PositionErrorType(enum.IntEnum):
+    BASELINE = 0
+
+
+class MapViewIdVector3d(dict):
+    """std::unordered_map<ViewId, Eigen::Vector3d> (bind:153)."""
+
+
+class MapEdges(dict):
+    """std::unordered_map<ViewIdPair, TwoViewInfo> (bind:154)."""
+
+
+class MapEdgesCovariance(dict):
+    """std::unordered_map<ViewIdPair, pair<Matrix3d, Vector3d>> (bind:160, include/uncertainty.hpp:13)."""
+
+
+class TwoViewInfo:                               # T/sfm/twoview_info.h:54-98
+    def __init__(self):
+        self.focal_length_1 = 0.0
+        self.focal_length_2 = 0.0
+        self.position_2 = np.zeros(3)
+        self.rotation_2 = np.zeros(3)
+        self.num_verified_matches = 0
+        self.num_homography_inliers = 0
+        self.visibility_score = 1
+
+
+class ViewGraph:                                 # T/sfm/view_graph/view_graph.{h,cc}
+    def __init__(self):
+        self._adj = {}
+        self._edges = MapEdges()
+
+    def NumViews(self):
+        return len(self._adj)
+
+    def NumEdges(self):
+        return len(self._edges)
+
+    def HasView(self, view_id):
+        return view_id in self._adj
+
+    def HasEdge(self, a, b):
+        return ((a, b) if a < b else (b, a)) in self._edges
+
+    def ViewIds(self):
+        return set(self._adj)
+
+    def GetAllEdges(self):
+        return self._edges
+
+    def GetEdge(self, a, b):
+        return self._edges.get((a, b) if a < b else (b, a))
+
+    def GetNeighborIdsForView(self, view_id):
+        return self._adj.get(view_id)
+
+    def AddEdge(self, a, b, info):               # key normalised to (min,max); the info is stored as given (view_graph.cc:133-151)
+        if a == b:
+            return
+        self._adj.setdefault(a, set()).add(b)
+        self._adj.setdefault(b, set()).add(a)
+        self._edges[(a, b) if a < b else (b, a)] = info
+
+    def RemoveEdge(self, a, b):
+        key = (a, b) if a < b else (b, a)
+        if key not in self._edges:
+            return False
+        del self._edges[key]
+        self._adj[a].discard(b)
+        self._adj[b].discard(a)
+        return True
+
+    def RemoveView(self, view_id):
+        if view_id not in self._adj:
+            return False
+        for n in list(self._adj[view_id]):
+            self.RemoveEdge(view_id, n)
+        del self._adj[view_id]
+        return True
+
+
+class _View:
+    def __init__(self, name):
+        self.name = name
+        self.estimated = False
+        self.orientation = np.zeros(3)
+        self.focal_length_prior = None
+
+    def Name(self):
+        return self.name
+
+    def IsEstimated(self):
+        return self.estimated
+
+    def GetOrientationAsAngleAxis(self):
+        return self.orientation
+
+
+class Reconstruction:
+    """The slice of theia::Reconstruction the rotation stage touches: views by id, their names, estimated flags."""
+
+    def __init__(self):
+        self._views = {}
+        self._next_id = 0
+        self._view_tracks = {}   # view id -> set of track ids (common-track counts, read_1dsfm.cc:354-360)
+        self._num_tracks = 0
+
+    def AddView(self, name):
+        vid = self._next_id
+        self._next_id += 1
+        self._views[vid] = _View(name)
+        return vid
+
+    def RemoveView(self, view_id):
+        return self._views.pop(view_id, None) is not None
+
+    def NumViews(self):
+        return len(self._views)
+
+    def NumTracks(self):
+        return self._num_tracks
+
+    def ViewIds(self):
+        return list(self._views)
+
+    def View(self, view_id):
+        return self._views.get(view_id)
+
+    def MutableView(self, view_id):
+        return self._views.get(view_id)
+
+
+class ReconstructionEstimatorOptions:            # T/sfm/reconstruction_estimator_options.h (fields the path reads)
+    def __init__(self):
+        self.num_threads = 1
+        self.min_num_two_view_inliers = 30
+        self.rotation_filtering_max_difference_degrees = 5.0
+        self.global_rotation_estimator_type = "ROBUST_L1L2"
+        self.global_position_estimator_type = "NONLINEAR"
+        self.reconstruction_estimator_type = "GLOBAL"
+        self.num_retriangulation_iterations = 1
+        self.refine_camera_positions_and_points_after_position_estimation = True
+        self.extra = {}
+
+
+class ReconstructionBuilderOptions:
+    def __init__(self):
+        self.num_threads = 1
+        self.min_track_length = 2
+        self.max_track_length = 50
+        self.reconstruct_largest_connected_component = False
+        self.only_calibrated_views = False
+        self.reconstruction_estimator_options = ReconstructionEstimatorOptions()
+
+    def print(self):
+        print({k: v for k, v in vars(self).items() if k != "reconstruction_estimator_options"},
+              vars(self.reconstruction_estimator_options))
+
+
+def load_1DSFM_config(flagfile, options):
+    """bind_src/GlobalSfMpy.cpp:185-271: yaml -> options (the keys the rotation stage reads are typed; the
+    rest is kept verbatim in reconstruction_estimator_options.extra)."""
+    import yaml
+    cfg = yaml.safe_load(open(flagfile))
+    options.num_threads = int(cfg["num_threads"])
+    options.min_track_length = int(cfg["min_track_length"])
+    options.max_track_length = int(cfg["max_track_length"])
+    options.reconstruct_largest_connected_component = bool(cfg["reconstruct_largest_connected_component"])
+    options.only_calibrated_views = bool(cfg["only_calibrated_views"])
+    r = options.reconstruction_estimator_options
+    r.min_num_two_view_inliers = int(cfg["min_num_inliers_for_valid_match"])
+    r.num_threads = int(cfg["num_threads"])
+    r.reconstruction_estimator_type = str(cfg["reconstruction_estimator"])
+    r.global_rotation_estimator_type = str(cfg["global_rotation_estimator"])
+    r.global_position_estimator_type = str(cfg["global_position_estimator"])
+    r.rotation_filtering_max_difference_degrees = float(cfg["post_rotation_filtering_degrees"])
+    r.num_retriangulation_iterations = int(cfg["num_retriangulation_iterations"])
+    r.refine_camera_positions_and_points_after_position_estimation = bool(
+        cfg["refine_camera_positions_and_points_after_position_estimation"])
+    r.extra = dict(cfg)
+
+
+# ------------------------------------------------------------------------------- dataset readers
+def ReadCovariance(dataset_directory, rot_covariances):
+    """src/uncertainty.cpp:200-229 -> {(id1,id2): (3x3 covariance, refined rotation)}."""
+    ids, cov6, rot = _vg.parse_covariance_text(os.path.join(dataset_directory, "covariance_rot.txt"))
+    for (a, b), c, r in zip(ids.tolist(), cov6, rot):
+        S = np.array([[c[0], c[3], c[4]], [c[3], c[1], c[5]], [c[4], c[5], c[2]]])
+        rot_covariances[(int(a), int(b))] = (S, np.array(r))
+    return True
+
+
+def Read1DSFM(dataset_directory, reconstruction, view_graph, rot_covariances=None):
+    """T/io/read_1dsfm.cc:375-412 (cc -> list -> tracks -> EGs) + read_covariance (bind:611-617)."""
+    d = dataset_directory
+    cc = set(int(t) for t in open(os.path.join(d, "cc.txt")).read().split())
+    for line in open(os.path.join(d, "list.txt")):
+        tok = line.split()
+        if not tok:
+            continue
+        vid = reconstruction.AddView(os.path.splitext(os.path.basename(tok[0]))[0])
+        if vid not in cc:
+            reconstruction.RemoveView(vid)        # ids stay in sync with the line index (read_1dsfm.cc:139-146)
+            continue
+        if len(tok) >= 3 and float(tok[2]) != 0:
+            reconstruction.View(vid).focal_length_prior = float(tok[2])
+    tok = open(os.path.join(d, "tracks.txt")).read().split()
+    pos, n_tracks = 1, int(tok[0])
+    for t in range(n_tracks):
+        n = int(tok[pos]); pos += 1
+        views = [int(v) for v in tok[pos:pos + 2 * n:2]]
+        pos += 2 * n
+        if len(set(views)) != len(views):
+            continue                               # Reconstruction::AddTrack rejects a track seeing one view twice
+        for v in views:
+            reconstruction._view_tracks.setdefault(v, set()).add(t)
+        reconstruction._num_tracks += 1
+    eg = np.loadtxt(os.path.join(d, "EGs.txt"), dtype=np.float64, ndmin=2)
+    rot2 = _vg.egs_to_rotation_2(eg[:, 2:11])
+    S = np.array([1.0, -1.0, -1.0])
+    empty = set()
+    for k in range(len(eg)):
+        a, b = int(eg[k, 0]), int(eg[k, 1])
+        if reconstruction.View(a) is None or reconstruction.View(b) is None:
+            continue
+        info = TwoViewInfo()
+        info.rotation_2 = rot2[k].copy()
+        info.position_2 = S * eg[k, 11:14]
+        common = len(reconstruction._view_tracks.get(a, empty) & reconstruction._view_tracks.get(b, empty))
+        info.num_verified_matches = common
+        info.visibility_score = common
+        view_graph.AddEdge(a, b, info)
+    if rot_covariances is not None:
+        ReadCovariance(d, rot_covariances)
+    return True
+
+
+def CalcCovariance(dataset_path):
+    raise NotImplementedError("CalcCovariance (src/uncertainty.cpp:82-198) needs Ceres' covariance estimation over the matched "
+                              "features: an offline pre-step outside the rotation-averaging path; use the shipped covariance_rot.txt")
+
+
+# ------------------------------------------------------------------------------- solver front-ends
+def _flatten(view_pairs, orientations, covariances, error_type):
+    """What rotation_estimator.cpp:228-293 does with the hash maps: skip edges whose endpoints have no initial
+    orientation or (covariance types) no covariance; dense-renumber the views."""
+    ids = np.array(sorted(orientations), dtype=np.int64)
+    dense = {int(v): k for k, v in enumerate(ids.tolist())}
+    needs_cov = error_type in (3, 6, 7, 8)
+    ei, ej, wij, cov6 = [], [], [], []
+    for (a, b), info in view_pairs.items():
+        if a not in dense or b not in dense:
+            continue
+        if needs_cov:
+            c = covariances.get((a, b)) if covariances is not None else None
+            if c is None:
+                continue
+            S = c[0]
+            cov6.append([S[0][0], S[1][1], S[2][2], S[0][1], S[0][2], S[1][2]])
+        ei.append(dense[a]); ej.append(dense[b]); wij.append(np.asarray(info.rotation_2, dtype=np.float64))
+    omega = np.array([np.asarray(orientations[int(v)], dtype=np.float64) for v in ids.tolist()]).reshape(len(ids), 3)
+    return ids, np.array(ei, np.uint32), np.array(ej, np.uint32), np.array(wij).reshape(len(ei), 3), \
+        (np.array(cov6).reshape(len(ei), 6) if needs_cov else None), omega
+
+
+def _solve(view_pairs, orientations, loss, error_type, covariances=None, num_threads=1, options=None):
+    error_type = int(error_type)
+    if len(orientations) == 0 or len(view_pairs) == 0:
+        return False                                  # rotation_estimator.cpp:209-220
+    if error_type < 3:
+        raise NotImplementedError("RotationErrorType QUATERNION_NORM / ROTATION_MAT_FNORM / QUATERNION_COSINE "
+                                  "(EstimateRotationsWithCustomizedLoss, rotation_estimator.cpp:82-198) are not implemented "
+                                  "on the device; the angle-axis types 3..8 are")
+    ids, ei, ej, wij, cov6, omega = _flatten(view_pairs, orientations, covariances, error_type)
+    if len(ei) == 0:
+        return True
+    prob = _capi.ProblemArrays(len(ids), ei, ej, wij, cov6=cov6, error_type=error_type)
+    o = options or _capi.default_options_py()
+    o.loss = loss_to_struct(loss)
+    o.num_threads = int(num_threads)
+    omega, summary, _ = _solver.solve(prob, o, omega)
+    for k, v in enumerate(ids.tolist()):
+        orientations[int(v)] = omega[k].copy()
+    _solve.last_summary = summary
+    return True                                       # the reference returns true whatever Ceres reports (:308)
+
+
+class RotationEstimator:
+    """theia::RotationEstimator (T/sfm/global_pose_estimation/rotation_estimator.h:50-66); subclassable."""
+
+    def EstimateRotations(self, view_pairs, rotations):
+        raise NotImplementedError("pure virtual")
+
+
+class NonlinearRotationEstimator(RotationEstimator):
+    """GSfMNonlinearRotationEstimator (include/GSfM_nonlinear_rotation_estimator.hpp:22-59)."""
+
+    def __init__(self, robust_loss_width=0.1):
+        self.robust_loss_width_ = robust_loss_width
+
+    def EstimateRotations(self, view_pairs, rotations):
+        """rotation_estimator.cpp:24-80: SoftLOneLoss(robust_loss_width), PairwiseRotationError weight 1."""
+        return _solve(view_pairs, rotations, _capi.Loss.make(_capi.LOSS_SOFTLONE, self.robust_loss_width_),
+                      RotationErrorType.ANGLE_AXIS)
+
+    def EstimateRotationsWithCustomizedLoss(self, view_pairs, rotations, loss_function, thread_num=1,
+                                            rotation_error_type=RotationErrorType.QUATERNION_COSINE):
+        return _solve(view_pairs, rotations, loss_function, rotation_error_type, num_threads=thread_num)
+
+    def EstimateRotationsWithCustomizedLossAndCovariance(self, view_pairs, rotations, loss_function, thread_num, covariances,
+                                                         rotation_error_type, reconstruction=None):
+        return _solve(view_pairs, rotations, loss_function, rotation_error_type, covariances, thread_num)
+
+
+class ReconstructionBuilder:
+    def __init__(self, options, reconstruction, view_graph=None):
+        if view_graph is None:
+            raise NotImplementedError("ReconstructionBuilder(options, database): the RocksDB feature/match database path is out of scope")
+        self.options_, self.reconstruction_, self.view_graph_ = options, reconstruction, view_graph
+
+    def CheckView(self):
+        assert self.view_graph_.NumViews() >= 2, "At least 2 images must be provided in order to create a reconstruction."
+
+    def get_view_graph(self):
+        return self.view_graph_
+
+    def get_reconstruction(self):
+        return self.reconstruction_
+
+
+class GlobalReconstructionEstimator:
+    """The steppable estimator (src/GSfM_global_reconstruction_estimator.cpp), steps 1-3 and the rotation filter."""
+
+    def __init__(self, options):
+        self.options = options
+        self.orientations = MapViewIdVector3d()
+        self.positions = {}
+        self.view_graph_ = None
+        self.reconstruction_ = None
+        self.solver_options = None       # optional _capi.Options override (PCG tolerances, device, ...)
+
+    def get_view_graph(self):
+        return self.view_graph_
+
+    def get_reconstruction(self):
+        return self.reconstruction_
+
+    def FilterInitialViewGraphAndCalibrateCameras(self, view_graph, reconstruction):
+        """Estimate_BeforeStep3 -> FilterInitialViewGraph (:369-390): drop edges with too few verified matches,
+        keep the largest connected component; camera calibration from priors is a no-op for rotations."""
+        self.view_graph_, self.reconstruction_ = view_graph, reconstruction
+        self.orientations.clear()
+        edges = view_graph.GetAllEdges()
+        keys = list(edges)
+        if not keys:
+            return False
+        ij = np.array(keys, dtype=np.int64)
+        nvm = np.array([edges[k].num_verified_matches for k in keys])
+        keep, ids = _vg.filter_initial_view_graph(np.array(sorted(view_graph.ViewIds())), ij, nvm,
+                                                  self.options.min_num_two_view_inliers)
+        for k, kp in zip(keys, keep.tolist()):
+            if not kp:
+                view_graph.RemoveEdge(*k)
+        alive = set(int(v) for v in ids.tolist())
+        for v in list(view_graph.ViewIds()):
+            if v not in alive:
+                view_graph.RemoveView(v)
+        return view_graph.NumEdges() >= 1
+
+    def OrientationsFromMaximumSpanningTree(self):
+        edges = self.view_graph_.GetAllEdges()
+        keys = sorted(edges)
+        ids = np.array(sorted(self.view_graph_.ViewIds()), dtype=np.int64)
+        ij = np.searchsorted(ids, np.array(keys, dtype=np.int64))
+        w = np.array([edges[k].num_verified_matches for k in keys])
+        rot = np.array([edges[k].rotation_2 for k in keys])
+        om = _vg.max_spanning_tree_orientations(len(ids), ij[:, 0], ij[:, 1], rot, w)
+        for k, v in enumerate(ids.tolist()):
+            if not np.isnan(om[k, 0]):
+                self.orientations[int(v)] = om[k].copy()
+        return True
+
+    def EstimateGlobalRotationsUncertainty(self, loss_func, covariances, rotation_error_type):
+        """:463-485: MST initialisation, then EstimateRotationsWithCustomizedLossAndCovariance."""
+        self.OrientationsFromMaximumSpanningTree()
+        return _solve(self.view_graph_.GetAllEdges(), self.orientations, loss_func, rotation_error_type, covariances,
+                      self.options.num_threads, self.solver_options)
+
+    def EstimateGlobalRotations(self, loss_func=None, rotation_error_type=RotationErrorType.QUATERNION_COSINE):
+        """:440-461 (EstimateGlobalRotationsNonLinear)."""
+        self.OrientationsFromMaximumSpanningTree()
+        return _solve(self.view_graph_.GetAllEdges(), self.orientations, loss_func, rotation_error_type, None,
+                      self.options.num_threads, self.solver_options)
+
+    def EstimateGlobalRotationsWithSigmaConsensus(self, loss_func, iters_num, sigma_max):
+        raise NotImplementedError("EstimateRotationsWithSigmaConsensus (rotation_estimator.cpp:314-457) is not implemented yet")
+
+    def FilterRotations(self):
+        """FilterViewPairsFromOrientation with options.rotation_filtering_max_difference_degrees, on the device."""
+        edges = self.view_graph_.GetAllEdges()
+        keys = [k for k in edges if k[0] in self.orientations and k[1] in self.orientations]
+        missing = [k for k in edges if k not in set(keys)]
+        ids, ei, ej, wij, _, omega = _flatten({k: edges[k] for k in keys}, self.orientations, None, 4)
+        prob = _capi.ProblemArrays(len(ids), ei, ej, wij)
+        keep, _ = _solver.filter_view_pairs(prob, omega, self.options.rotation_filtering_max_difference_degrees)
+        for k, kp in zip(keys, keep.tolist()):
+            if not kp:
+                self.view_graph_.RemoveEdge(*k)
+        for k in missing:
+            self.view_graph_.RemoveEdge(*k)
+        return True
+
+    def _todo(name):  # noqa: N805
+        def f(self, *a, **k):
+            raise NotImplementedError(f"{name}: pipeline steps after rotation averaging are TheiaSfM's (out of scope here)")
+        return f
+
+    OptimizePairwiseTranslations = _todo("OptimizePairwiseTranslations")
+    FilterRelativeTranslation = _todo("FilterRelativeTranslation")
+    EstimatePosition = _todo("EstimatePosition")
+    EstimateStructure = _todo("EstimateStructure")
+    BundleAdjustCameraPositionsAndPoints = _todo("BundleAdjustCameraPositionsAndPoints")
+    BundleAdjustmentAndRemoveOutlierPoints = _todo("BundleAdjustmentAndRemoveOutlierPoints")
+
+
+def SetOrientations(orientations, reconstruction):
+    """bind_src/GlobalSfMpy.cpp:80-98."""
+    for vid in reconstruction.ViewIds():
+        reconstruction.MutableView(vid).estimated = False
+    for vid, w in orientations.items():
+        v = reconstruction.MutableView(vid)
+        if v is None:
+            continue
+        v.orientation = np.asarray(w, dtype=np.float64).copy()
+        v.estimated = True
+
+
+def test_loss_with_input_x(loss_func, x):       # bind:179-183
+    out = [0.0, 0.0, 0.0]
+    loss_func.Evaluate(x, out)
+    print(f"[{out[0]:g}, {out[1]:g}, {out[2]:g}]")
+
+
+def InitGlog(log_level=0, logtostderr=True, log_dir="./log"):
+    return None
+
+
+def StopGlog():
+    return None
+
+
+tgamma = math.gamma                              # bind:31,667
+
+# MAGSAC constants (include/gamma_values.cpp:6-11,384-389,780-785) and tables (closed forms)
+nu3, C3, sigma_quantile3, upper_incomplete_gamma_of_k3 = 3.0, 4.029720004054876e-01, 3.368214175218727, 3.439485560754856e-03
+nu4, C4, sigma_quantile4, upper_incomplete_gamma_of_k4 = 4.0, 2.525252525252525e-01, 3.643721193503644e+00, 3.611260617758625e-03
+nu9, C9, sigma_quantile9, upper_incomplete_gamma_of_k9 = 9.0, 3.837828575290349e-03, 4.654674460524809e+00, 3.344206155099048e-02
+stored_gamma_number3, stored_gamma_number4, stored_gamma_number9 = 36843, 38683, 48553
+precision_of_stored_gamma3 = precision_of_stored_gamma4 = precision_of_stored_gamma9 = 1000.0
+
+
+def _table(nu, n):
+    x = np.arange(n) / 1000.0
+    if nu == 3:
+        return np.exp(-x).tolist()
+    if nu == 4:
+        return (0.5 * math.sqrt(math.pi) * np.array([math.erfc(math.sqrt(v)) for v in x]) + np.sqrt(x) * np.exp(-x)).tolist()
+    return (np.exp(-x) * (((x + 3.0) * x + 6.0) * x + 6.0)).tolist()
+
+
+def __getattr__(name):                           # the three 36k..48k-entry lists are built on first use
+    if name in ("stored_gamma_values3", "stored_gamma_values4", "stored_gamma_values9"):
+        nu = int(name[-1])
+        val = _table(nu, {3: stored_gamma_number3, 4: stored_gamma_number4, 9: stored_gamma_number9}[nu])
+        globals()[name] = val
+        return val
+    raise AttributeError(name)

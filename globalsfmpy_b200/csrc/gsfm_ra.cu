@@ -15,6 +15,8 @@
 // Euclidean (angle-axis) Levenberg-Marquardt of Ceres is reproduced exactly by transforming the
 // LM diagonal per view.
 #include <cooperative_groups.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
@@ -160,6 +162,84 @@ __global__ void k_setup_halfedges(uint64_t H, const uint32_t* __restrict__ he_ed
   whiten(error_type, c6, weight ? weight[k] : 1.0, u);
 #pragma unroll
   for (int t = 0; t < 6; ++t) U[(uint64_t)t * H + h] = u[t];
+}
+
+// ------------------------------------------------------------------------------------------
+// Structure build on the device (one-time per problem): half-edge keys -> radix sort -> rows,
+// row pointers, duplicate / range checks, balanced warp partitions and their segments.
+// ------------------------------------------------------------------------------------------
+__global__ void k_build_keys(uint64_t E, uint32_t N, const uint32_t* __restrict__ ei, const uint32_t* __restrict__ ej, uint64_t* __restrict__ keys,
+                             uint32_t* __restrict__ vals, int* err) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= E) return;
+  uint32_t i = ei[k], j = ej[k];
+  if (i >= N || j >= N || i == j) { atomicMax(err, 1); i = 0; j = (N > 1) ? 1 : 0; }
+  keys[2 * k] = (uint64_t)i * N + j;     vals[2 * k] = (uint32_t)k;
+  keys[2 * k + 1] = (uint64_t)j * N + i; vals[2 * k + 1] = (uint32_t)k | kSideBit;
+}
+__global__ void k_unpack_keys(uint64_t H, uint32_t N, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t* __restrict__ he_row,
+                              uint32_t* __restrict__ he_col, uint32_t* __restrict__ he_edge, int* err) {
+  const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  const uint64_t key = keys[h];
+  const uint32_t v = vals[h];
+  he_row[h] = (uint32_t)(key / N);
+  he_col[h] = (uint32_t)(key % N) | (v & kSideBit);
+  he_edge[h] = v & ~kSideBit;
+  if (h > 0 && keys[h - 1] == key) atomicMax(err, 2);  // the same view pair twice
+}
+__global__ void k_rowptr(uint32_t N, uint64_t H, const uint64_t* __restrict__ keys, uint32_t* __restrict__ rowptr) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > N) return;
+  const uint64_t target = (uint64_t)r * N;
+  uint64_t lo = 0, hi = H;
+  while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (keys[mid] < target) lo = mid + 1; else hi = mid; }
+  rowptr[r] = (uint32_t)lo;
+}
+__global__ void k_row_flags(uint32_t N, const uint32_t* __restrict__ rowptr, uint32_t* __restrict__ nonempty, uint32_t* __restrict__ isoflag) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > N) return;
+  const uint32_t ne = (r < N && rowptr[r + 1] > rowptr[r]) ? 1u : 0u;
+  nonempty[r] = ne;
+  isoflag[r] = (r < N) ? 1u - ne : 0u;
+}
+__global__ void k_iso_fill(uint32_t N, const uint32_t* __restrict__ isoflag, const uint32_t* __restrict__ iso_rank, uint32_t* __restrict__ iso) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < N && isoflag[r]) iso[iso_rank[r]] = r;
+}
+__global__ void k_part_count(uint32_t nw, uint32_t per, uint64_t H, const uint32_t* __restrict__ he_row, const uint32_t* __restrict__ nz_rank,
+                             uint32_t* __restrict__ nseg) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w > nw) return;
+  if (w == nw) { nseg[w] = 0; return; }
+  const uint64_t lo = (uint64_t)w * per, hi = min(H, lo + per);
+  nseg[w] = nz_rank[he_row[hi - 1]] - nz_rank[he_row[lo]] + 1;
+}
+__global__ void k_part_fill(uint32_t nw, uint32_t per, uint64_t H, const uint32_t* __restrict__ he_row, const uint32_t* __restrict__ rowptr,
+                            const uint32_t* __restrict__ warp_seg_ptr, uint32_t* __restrict__ seg_row, uint32_t* __restrict__ seg_begin,
+                            uint32_t* __restrict__ seg_len) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  const uint64_t lo = (uint64_t)w * per, hi = min(H, lo + per);
+  uint32_t t = warp_seg_ptr[w];
+  uint64_t h = lo;
+  uint32_t r = he_row[lo];
+  while (h < hi) {
+    while (rowptr[r + 1] <= h) ++r;
+    const uint64_t end = min(hi, (uint64_t)rowptr[r + 1]);
+    seg_row[t] = r | ((h > rowptr[r]) ? kSideBit : 0u);  // bit 31: continuation of a row begun in an earlier range
+    seg_begin[t] = (uint32_t)h;
+    seg_len[t] = (uint32_t)(end - h);
+    ++t;
+    h = end;
+  }
+}
+__global__ void k_node_seg_count(uint32_t N, uint32_t per, const uint32_t* __restrict__ rowptr, uint32_t* __restrict__ cnt) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > N) return;
+  uint32_t c = 0;
+  if (r < N && rowptr[r + 1] > rowptr[r]) c = (rowptr[r + 1] - 1) / per - rowptr[r] / per + 1;
+  cnt[r] = c;
 }
 
 // Column indices live inside the chunk records of both block buffers (written once).
@@ -1044,23 +1124,61 @@ int select_device(int device, int* out) {
   return 0;
 }
 
+// Device buffers come from the device's stream-ordered memory pool (cudaMallocAsync) on the stream that
+// is "current" for this thread while a solver is being built; the pool's release threshold is raised so a
+// second gsfm_ra_solve() call reuses the memory of the first instead of paying cudaMalloc/cudaFree again.
+thread_local cudaStream_t g_alloc_stream = nullptr;
+thread_local bool g_alloc_async = false;
+
+struct AllocScope {
+  cudaStream_t prev_s;
+  bool prev_a;
+  explicit AllocScope(cudaStream_t st) : prev_s(g_alloc_stream), prev_a(g_alloc_async) { g_alloc_stream = st; g_alloc_async = true; }
+  ~AllocScope() { g_alloc_stream = prev_s; g_alloc_async = prev_a; }
+};
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  bool async = false;
+  cudaStream_t st = nullptr;
   int alloc(size_t count) {
     release();
     n = count;
     if (count == 0) return 0;
-    CUDA_TRY(cudaMalloc(&p, count * sizeof(T)));
+    if (g_alloc_async) {
+      async = true; st = g_alloc_stream;
+      CUDA_TRY(cudaMallocAsync(&p, count * sizeof(T), st));
+    } else {
+      async = false;
+      CUDA_TRY(cudaMalloc(&p, count * sizeof(T)));
+    }
     return 0;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() {
+    if (p) { if (async) cudaFreeAsync(p, st); else cudaFree(p); }
+    p = nullptr; n = 0;
+  }
   ~DevBuf() { release(); }
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
 };
+
+// Owns the solver's stream; declared FIRST in the solver so it is destroyed LAST, after every DevBuf has
+// queued its cudaFreeAsync on it.
+struct StreamHolder {
+  cudaStream_t s = nullptr;
+  ~StreamHolder() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } }
+};
+
+// Per-device facts that are expensive to query: cached for the life of the process.
+struct DeviceInfo {
+  bool ready = false;
+  int sm_count = 0, coop = 0, occ_k1 = 1, occ_k2 = 1;
+};
+DeviceInfo g_device_info[64];
 
 inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
@@ -1136,6 +1254,7 @@ struct Partition {
 };
 
 struct gsfm_ra_solver {
+  StreamHolder stream_holder;  // first member: destroyed last
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
@@ -1193,7 +1312,7 @@ struct gsfm_ra_solver {
     if (comm && ncclx::api()) ncclx::api()->CommDestroy(comm);
     if (h_sc) cudaFreeHost(h_sc);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
-    if (stream) cudaStreamDestroy(stream);
+    // the stream itself is destroyed by stream_holder after the buffers have been returned to the pool
   }
 
   bool sharded() const { return world > 1; }
@@ -1330,162 +1449,168 @@ struct gsfm_ra_solver {
 
 namespace {
 
-// Build the half-edge structure on the host and upload everything.
+int device_info(int device, DeviceInfo** out) {
+  DeviceInfo& d = g_device_info[device & 63];
+  if (!d.ready) {
+    CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&d.coop, cudaDevAttrCooperativeLaunch, device));
+    CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpmvSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpmvSmemBytes));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k1, k_edges<true>, kBlock, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2, k_pcg_persistent, kBlock, kSpmvSmemBytes));
+    // keep freed blocks in the pool: the next solver reuses them
+    cudaMemPool_t pool;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    d.ready = true;
+  }
+  *out = &d;
+  return 0;
+}
+
+template <typename T>
+int exclusive_scan(const T* in, T* out, size_t n, cudaStream_t st) {
+  size_t bytes = 0;
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, st));
+  DevBuf<unsigned char> tmp;
+  RA_TRY(tmp.alloc(bytes + 16));
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, (int)n, st));
+  return 0;
+}
+
+// Upload the (shard of the) problem and build every device structure; one host sync at the end.
 int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, int rank, int world, gsfm_ra_solver** out) {
   RA_TRY(check_problem(prob));
   if (!options || !out) { set_error("options/out is NULL"); return GSFM_RA_ERR_INVALID; }
   if (world < 1 || rank < 0 || rank >= world) { set_error("bad rank/world"); return GSFM_RA_ERR_INVALID; }
   const uint32_t N = prob->num_views;
-  for (uint64_t k = 0; k < prob->num_edges; ++k) {
-    if (prob->edge_i[k] >= N || prob->edge_j[k] >= N || prob->edge_i[k] == prob->edge_j[k]) {
-      set_error("edge %llu (%u,%u) is out of range or a self loop", (unsigned long long)k, prob->edge_i[k], prob->edge_j[k]);
-      return GSFM_RA_ERR_INVALID;
-    }
-  }
+  const double tb0 = now_ms();
+  double tb_prev = tb0;
+  auto lap = [&](const char* what) {
+    if (options->verbose >= 2) { const double t = now_ms(); std::fprintf(stderr, "[gsfm_ra] setup %-28s %8.2f ms\n", what, t - tb_prev); tb_prev = t; }
+  };
   int device = 0;
   RA_TRY(select_device(options->device, &device));
+  DeviceInfo* di = nullptr;
+  RA_TRY(device_info(device, &di));
   std::unique_ptr<gsfm_ra_solver> s(new gsfm_ra_solver());
   s->device = device;
   s->opt = *options;
   s->rank = rank; s->world = world;
   s->error_type = prob->error_type;
   RA_TRY(make_dev_loss(&options->loss, &s->loss));
-  cudaDeviceProp dp;
-  CUDA_TRY(cudaGetDeviceProperties(&dp, device));
-  s->sm_count = dp.multiProcessorCount;
-  CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-  for (auto& e : s->ev) CUDA_TRY(cudaEventCreate(&e));
+  s->sm_count = di->sm_count;
+  CUDA_TRY(cudaStreamCreateWithFlags(&s->stream_holder.s, cudaStreamNonBlocking));
+  s->stream = s->stream_holder.s;
+  AllocScope alloc_scope(s->stream);
+  for (auto& e : s->ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDefault));
   CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
+  lap("context/stream");
 
   // shard: a contiguous range of the caller's edge list
   const uint64_t e0 = prob->num_edges * (uint64_t)rank / world, e1 = prob->num_edges * (uint64_t)(rank + 1) / world;
   const uint64_t E = e1 - e0, H = 2 * E;
+  if (E == 0) { set_error("rank %d of %d owns no edges", rank, world); return GSFM_RA_ERR_INVALID; }
   s->N = N; s->E = E; s->H = H; s->edge_begin = e0;
-  const uint32_t* ei = prob->edge_i + e0;
-  const uint32_t* ej = prob->edge_j + e0;
-
-  // counting sort of half-edges by row, then by column inside each row
-  std::vector<uint32_t> rowptr(N + 1, 0);
-  for (uint64_t k = 0; k < E; ++k) { rowptr[ei[k] + 1]++; rowptr[ej[k] + 1]++; }
-  for (uint32_t a = 0; a < N; ++a) rowptr[a + 1] += rowptr[a];
-  std::vector<uint64_t> ent(H);  // (col | side) << 32 | edge
-  {
-    std::vector<uint32_t> fill(rowptr.begin(), rowptr.end() - 1);
-    for (uint64_t k = 0; k < E; ++k) {
-      ent[fill[ei[k]]++] = ((uint64_t)ej[k] << 32) | (uint32_t)k;
-      ent[fill[ej[k]]++] = ((uint64_t)ei[k] << 32) | (uint32_t)k | (1ull << 63);
-    }
-  }
-  std::vector<uint32_t> he_col(H), he_row(H), he_edge(H), iso;
-  for (uint32_t a = 0; a < N; ++a) {
-    if (rowptr[a] == rowptr[a + 1]) iso.push_back(a);
-    auto b = ent.begin() + rowptr[a], e = ent.begin() + rowptr[a + 1];
-    std::sort(b, e, [](uint64_t x, uint64_t y) { return (x & ~(1ull << 63)) < (y & ~(1ull << 63)); });
-    for (uint32_t h = rowptr[a]; h < rowptr[a + 1]; ++h) {
-      const uint64_t v = ent[h];
-      const uint32_t col = (uint32_t)((v >> 32) & 0x7fffffffu);
-      he_col[h] = col | ((v >> 63) ? kSideBit : 0u);
-      he_row[h] = a;
-      he_edge[h] = (uint32_t)(v & 0xffffffffu);
-      if (h > rowptr[a] && (he_col[h - 1] & ~kSideBit) == col) {
-        set_error("duplicate edge between views %u and %u", a, col);
-        return GSFM_RA_ERR_INVALID;
-      }
-    }
-  }
-  s->n_iso = (uint32_t)iso.size();
+  cudaStream_t st = s->stream;
 
   auto up32 = [&](DevBuf<uint32_t>& d, const uint32_t* src, size_t n) -> int {
     RA_TRY(d.alloc(n));
     if (n == 0) return 0;
-    CUDA_TRY(cudaMemcpyAsync(d.p, src, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.p, src, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     return 0;
   };
   auto up64 = [&](DevBuf<double>& d, const double* src, size_t n) -> int {
     RA_TRY(d.alloc(n));
-    CUDA_TRY(cudaMemcpyAsync(d.p, src, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.p, src, n * sizeof(double), cudaMemcpyHostToDevice, st));
     return 0;
   };
-  RA_TRY(up32(s->he_col, he_col.data(), H));
-  RA_TRY(up32(s->he_row, he_row.data(), H));
-  RA_TRY(up32(s->iso, iso.data(), iso.size()));
-  // balanced partitions, one per kernel class, sized to exactly one resident wave of that kernel
-  {
-    int occ_k1 = 0, occ_k2 = 0, coop = 0;
-    CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpmvSmemBytes));
-    CUDA_TRY(cudaFuncSetAttribute(k_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpmvSmemBytes));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_k1, k_edges<true>, kBlock, 0));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_k2, k_pcg_persistent, kBlock, kSpmvSmemBytes));
-    CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
-    s->cooperative = coop != 0 && occ_k2 > 0;
-    occ_k1 = std::max(1, occ_k1); occ_k2 = std::max(1, occ_k2);
-    auto make = [&](Partition& P, int blocks_per_sm) -> int {
-      const uint64_t max_warps = (uint64_t)s->sm_count * blocks_per_sm * kWarpsPerBlock;
-      // at least 64 half-edges per warp, ranges a multiple of 32 half-edges
-      uint64_t per = (H + max_warps - 1) / max_warps;
-      per = std::max<uint64_t>(64, (per + 31) / 32 * 32);
-      const uint32_t nw = (uint32_t)std::max<uint64_t>(1, (H + per - 1) / per);
-      std::vector<uint32_t> wptr(nw + 1, 0), srow, sbegin, slen, nptr(N + 1, 0);
-      uint32_t a = 0;
-      for (uint32_t w = 0; w < nw; ++w) {
-        const uint64_t lo = (uint64_t)w * per, hi = std::min<uint64_t>(H, lo + per);
-        wptr[w] = (uint32_t)srow.size();
-        uint64_t h = lo;
-        while (h < hi) {
-          while (rowptr[a + 1] <= h) ++a;
-          const uint64_t end = std::min<uint64_t>(hi, rowptr[a + 1]);
-          // bit 31: continuation (the row's first segment lives in an earlier warp's range)
-          srow.push_back(a | ((h > rowptr[a]) ? kSideBit : 0u)); sbegin.push_back((uint32_t)h); slen.push_back((uint32_t)(end - h));
-          h = end;
-        }
-      }
-      wptr[nw] = (uint32_t)srow.size();
-      // rows -> their (consecutive) segments
-      std::vector<uint32_t> cnt(N, 0);
-      for (uint32_t r : srow) cnt[r & ~kSideBit]++;
-      for (uint32_t r = 0; r < N; ++r) nptr[r + 1] = nptr[r] + cnt[r];
-      P.num_warps = nw; P.num_segs = (uint32_t)srow.size(); P.span = (uint32_t)per;
-      P.grid = (nw + kWarpsPerBlock - 1) / kWarpsPerBlock;
-      RA_TRY(up32(P.warp_seg_ptr, wptr.data(), wptr.size()));
-      RA_TRY(up32(P.seg_row, srow.data(), srow.size()));
-      RA_TRY(up32(P.seg_begin, sbegin.data(), sbegin.size()));
-      RA_TRY(up32(P.seg_len, slen.data(), slen.size()));
-      RA_TRY(up32(P.node_seg_ptr, nptr.data(), nptr.size()));
-      CUDA_TRY(cudaStreamSynchronize(s->stream));  // the host vectors die with this scope
-      return 0;
-    };
-    RA_TRY(make(s->pk1, occ_k1));
-    RA_TRY(make(s->pk2, occ_k2));
-    // the cooperative grid must be fully resident; node loops are grid-strided so any size works
-    s->pk2.grid = std::min<uint32_t>(s->pk2.grid, (uint32_t)s->sm_count * occ_k2);
-  }
-  RA_TRY(up32(s->d_ei, ei, E));
-  RA_TRY(up32(s->d_ej, ej, E));
+  RA_TRY(up32(s->d_ei, prob->edge_i + e0, E));
+  RA_TRY(up32(s->d_ej, prob->edge_j + e0, E));
   RA_TRY(up64(s->d_omega_ij, prob->omega_ij + 3 * e0, 3 * E));
   if (prob->cov6) RA_TRY(up64(s->d_cov6, prob->cov6 + 6 * e0, 6 * E));
   if (prob->edge_weight) RA_TRY(up64(s->d_weight, prob->edge_weight + e0, E));
-  DevBuf<uint32_t> d_he_edge;
-  RA_TRY(up32(d_he_edge, he_edge.data(), H));
+  lap("enqueue uploads");
+
+  // ---- half-edges sorted by (row, col): keys -> radix sort -> unpack ----------------------------
+  DevBuf<int> d_err;
+  DevBuf<uint64_t> keys_a, keys_b;
+  DevBuf<uint32_t> vals_a, vals_b, he_edge, rowptr, flags_ne, flags_iso, nz_rank, iso_rank;
+  RA_TRY(d_err.alloc(4));
+  CUDA_TRY(cudaMemsetAsync(d_err.p, 0, 4 * sizeof(int), st));
+  RA_TRY(keys_a.alloc(H)); RA_TRY(keys_b.alloc(H)); RA_TRY(vals_a.alloc(H)); RA_TRY(vals_b.alloc(H));
+  k_build_keys<<<grid_for(E), kBlock, 0, st>>>(E, N, s->d_ei.p, s->d_ej.p, keys_a.p, vals_a.p, d_err.p);
+  {
+    int bits = 1;
+    while (bits < 64 && ((uint64_t)N * N - 1) >> bits) ++bits;
+    size_t bytes = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_a.p, keys_b.p, vals_a.p, vals_b.p, (int)H, 0, bits, st));
+    DevBuf<unsigned char> tmp;
+    RA_TRY(tmp.alloc(bytes + 16));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, keys_a.p, keys_b.p, vals_a.p, vals_b.p, (int)H, 0, bits, st));
+  }
+  RA_TRY(s->he_col.alloc(H)); RA_TRY(s->he_row.alloc(H)); RA_TRY(he_edge.alloc(H));
+  k_unpack_keys<<<grid_for(H), kBlock, 0, st>>>(H, N, keys_b.p, vals_b.p, s->he_row.p, s->he_col.p, he_edge.p, d_err.p);
+  RA_TRY(rowptr.alloc(N + 2)); RA_TRY(flags_ne.alloc(N + 2)); RA_TRY(flags_iso.alloc(N + 2)); RA_TRY(nz_rank.alloc(N + 2)); RA_TRY(iso_rank.alloc(N + 2));
+  k_rowptr<<<grid_for(N + 1), kBlock, 0, st>>>(N, H, keys_b.p, rowptr.p);
+  k_row_flags<<<grid_for(N + 1), kBlock, 0, st>>>(N, rowptr.p, flags_ne.p, flags_iso.p);
+  RA_TRY(exclusive_scan(flags_ne.p, nz_rank.p, N + 1, st));
+  RA_TRY(exclusive_scan(flags_iso.p, iso_rank.p, N + 1, st));
+  RA_TRY(s->iso.alloc(N));
+  k_iso_fill<<<grid_for(N), kBlock, 0, st>>>(N, flags_iso.p, iso_rank.p, s->iso.p);
+  CUDA_TRY(cudaMemcpyAsync(d_err.p + 1, iso_rank.p + N, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));  // n_iso
+  s->launches += 6;
+
+  // ---- balanced partitions, one per kernel class, sized to exactly one resident wave of that kernel ----
+  s->cooperative = di->coop != 0 && di->occ_k2 > 0;
+  auto make = [&](Partition& P, int blocks_per_sm) -> int {
+    const uint64_t max_warps = (uint64_t)s->sm_count * std::max(1, blocks_per_sm) * kWarpsPerBlock;
+    uint64_t per = (H + max_warps - 1) / max_warps;
+    per = std::max<uint64_t>(64, (per + 31) / 32 * 32);  // at least 64 half-edges per warp, whole records
+    const uint32_t nw = (uint32_t)std::max<uint64_t>(1, (H + per - 1) / per);
+    P.num_warps = nw; P.span = (uint32_t)per;
+    P.num_segs = nw + N;  // upper bound: every range start + every row start opens one segment
+    P.grid = (nw + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    DevBuf<uint32_t> nseg, cnt;
+    RA_TRY(nseg.alloc(nw + 2)); RA_TRY(cnt.alloc(N + 2));
+    RA_TRY(P.warp_seg_ptr.alloc(nw + 2)); RA_TRY(P.seg_row.alloc(P.num_segs)); RA_TRY(P.seg_begin.alloc(P.num_segs));
+    RA_TRY(P.seg_len.alloc(P.num_segs)); RA_TRY(P.node_seg_ptr.alloc(N + 2));
+    k_part_count<<<grid_for(nw + 1), kBlock, 0, st>>>(nw, (uint32_t)per, H, s->he_row.p, nz_rank.p, nseg.p);
+    RA_TRY(exclusive_scan(nseg.p, P.warp_seg_ptr.p, nw + 1, st));
+    k_part_fill<<<grid_for(nw), kBlock, 0, st>>>(nw, (uint32_t)per, H, s->he_row.p, rowptr.p, P.warp_seg_ptr.p, P.seg_row.p, P.seg_begin.p, P.seg_len.p);
+    k_node_seg_count<<<grid_for(N + 1), kBlock, 0, st>>>(N, (uint32_t)per, rowptr.p, cnt.p);
+    RA_TRY(exclusive_scan(cnt.p, P.node_seg_ptr.p, N + 1, st));
+    s->launches += 5;
+    return 0;
+  };
+  RA_TRY(make(s->pk1, di->occ_k1));
+  RA_TRY(make(s->pk2, di->occ_k2));
+  // the cooperative grid must be fully resident; node loops are grid-strided so any size works
+  s->pk2.grid = std::min<uint32_t>(s->pk2.grid, (uint32_t)s->sm_count * std::max(1, di->occ_k2));
+  lap("enqueue structure build");
+
+  // ---- per half-edge constants (K0) and the solver's working set ---------------------------------
   RA_TRY(s->qij.alloc(4 * H));
   RA_TRY(s->U.alloc(6 * H));
-  k_setup_halfedges<<<grid_for(H), kBlock, 0, s->stream>>>(H, d_he_edge.p, s->d_omega_ij.p, s->d_cov6.p, s->d_weight.p, prob->error_type, s->qij.p, s->U.p);
+  k_setup_halfedges<<<grid_for(H), kBlock, 0, st>>>(H, he_edge.p, s->d_omega_ij.p, s->d_cov6.p, s->d_weight.p, prob->error_type, s->qij.p, s->U.p);
   s->launches += 1;
-  CUDA_TRY(cudaGetLastError());
+  const size_t nrec = (size_t)((H + 31) / 32);
   for (int b = 0; b < 2; ++b) {
     RA_TRY(s->omega[b].alloc(3ull * N));
     RA_TRY(s->node_q[b].alloc(4ull * N));
     RA_TRY(s->node_JL[b].alloc(9ull * N));
-    RA_TRY(s->val[b].alloc((size_t)((H + 31) / 32) * kRecDoubles));
-    CUDA_TRY(cudaMemsetAsync(s->val[b].p, 0, (size_t)((H + 31) / 32) * kRecBytes, s->stream));
+    RA_TRY(s->val[b].alloc(nrec * kRecDoubles));
+    // only the last (partial) record has lanes K1 never writes
+    CUDA_TRY(cudaMemsetAsync(s->val[b].p + (nrec - 1) * kRecDoubles, 0, kRecBytes, st));
     RA_TRY(s->lin[b].alloc(9ull * N + 2));
     s->Hd_p[b] = s->lin[b].p;
     s->gt_p[b] = s->lin[b].p + 6ull * N;
     RA_TRY(s->ediag[b].alloc(3ull * N));
-    CUDA_TRY(cudaMemsetAsync(s->omega[b].p, 0, 3ull * N * sizeof(double), s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->omega[b].p, 0, 3ull * N * sizeof(double), st));
   }
-  k_embed_cols<<<grid_for(H), kBlock, 0, s->stream>>>(H, s->he_col.p, s->val[0].p, s->val[1].p);
+  k_embed_cols<<<grid_for(H), kBlock, 0, st>>>(H, s->he_col.p, s->val[0].p, s->val[1].p);
   s->launches += 1;
-  CUDA_TRY(cudaGetLastError());
   RA_TRY(s->part.alloc((size_t)s->pk1.num_segs * kPartStride));
   RA_TRY(s->ypart.alloc((size_t)s->pk2.num_segs * 3));
   for (DevBuf<double>* d : {&s->scale, &s->x, &s->r, &s->z, &s->p, &s->p1, &s->y, &s->delta}) RA_TRY(d->alloc(3ull * N));
@@ -1493,18 +1618,28 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   RA_TRY(s->slotsB.alloc(2 * (size_t)s->pk2.grid + 8));
   RA_TRY(s->slotsC.alloc(2 * (size_t)s->pk2.grid + 8));
   RA_TRY(s->row_cnt.alloc(N));
-  CUDA_TRY(cudaMemsetAsync(s->row_cnt.p, 0, (size_t)N * sizeof(unsigned), s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->row_cnt.p, 0, (size_t)N * sizeof(unsigned), st));
   RA_TRY(s->Dblk.alloc(6ull * N));
   RA_TRY(s->Minv.alloc(6ull * N));
   RA_TRY(s->slots.alloc((size_t)std::max<unsigned>(grid_for(3ull * N), 64) * 4 + 64));
   RA_TRY(s->counter.alloc(4));
   RA_TRY(s->sc.alloc(1));
-  CUDA_TRY(cudaMemsetAsync(s->counter.p, 0, 4 * sizeof(unsigned), s->stream));
-  CUDA_TRY(cudaMemsetAsync(s->sc.p, 0, sizeof(DevScalars), s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->counter.p, 0, 4 * sizeof(unsigned), st));
+  CUDA_TRY(cudaMemsetAsync(s->sc.p, 0, sizeof(DevScalars), st));
   CUDA_TRY(cudaMallocHost(&s->h_sc, sizeof(DevScalars)));
-  k_jacobi_scale<<<grid_for(3ull * N), kBlock, 0, s->stream>>>(3 * N, s->ediag[0].p, s->scale.p, 0);
+  k_jacobi_scale<<<grid_for(3ull * N), kBlock, 0, st>>>(3 * N, s->ediag[0].p, s->scale.p, 0);
   s->launches += 1;
-  CUDA_TRY(cudaStreamSynchronize(s->stream));  // host vectors go out of scope
+  CUDA_TRY(cudaGetLastError());
+  lap("enqueue K0 + allocations");
+  // the only synchronisation of the build: input checks and the isolated-view count
+  int h_err[4] = {0, 0, 0, 0};
+  CUDA_TRY(cudaMemcpyAsync(h_err, d_err.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  lap("wait for the device");
+  if (h_err[0] == 1) { set_error("an edge is out of range or a self loop"); return GSFM_RA_ERR_INVALID; }
+  if (h_err[0] == 2) { set_error("duplicate edge: the same view pair appears twice"); return GSFM_RA_ERR_INVALID; }
+  s->n_iso = (uint32_t)h_err[1];
+  if (options->verbose >= 2) std::fprintf(stderr, "[gsfm_ra] setup total %.2f ms\n", now_ms() - tb0);
   s->ms_setup = s->elapsed_since(s->ev[0]);
   s->radius = options->initial_trust_region_radius;
   *out = s.release();

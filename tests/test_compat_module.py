@@ -1,0 +1,189 @@
+"""The `GlobalSfMpy`-compatible module (globalsfmpy_b200/compat): same names and call sequence as the reference's
+pybind11 module for the rotation-averaging stage of scripts/sfm_pipeline.py."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+COMPAT = os.path.join(ROOT, "globalsfmpy_b200", "compat")
+REF = "/root/reference"
+MADRID = os.path.join(REF, "datasets", "Madrid_Metropolis")
+
+
+@pytest.fixture(scope="module")
+def sfm():
+    if COMPAT not in sys.path:
+        sys.path.insert(0, COMPAT)
+    import GlobalSfMpy
+    return GlobalSfMpy
+
+
+def _graph_from_fixture(sfm, golden_dir):
+    from globalsfmpy_b200 import viewgraph as vg
+    z = np.load(os.path.join(golden_dir, "madrid_metropolis.npz"))
+    recon, graph, covs = sfm.Reconstruction(), sfm.ViewGraph(), sfm.MapEdgesCovariance()
+    cc = set(z["cc"].tolist())
+    for k in range(int(z["num_images"])):
+        vid = recon.AddView(f"img{k}")
+        if vid not in cc:
+            recon.RemoveView(vid)
+    rot2 = vg.egs_to_rotation_2(z["edge_R"])
+    for (a, b), w, n in zip(z["edge_ij"].tolist(), rot2, z["num_verified_matches"].tolist()):
+        info = sfm.TwoViewInfo()
+        info.rotation_2 = w
+        info.num_verified_matches = n
+        graph.AddEdge(a, b, info)
+    for (a, b), c in zip(z["cov_ij"].tolist(), z["cov6"]):
+        covs[(a, b)] = (np.array([[c[0], c[3], c[4]], [c[3], c[1], c[5]], [c[4], c[5], c[2]]]), np.zeros(3))
+    return recon, graph, covs
+
+
+def test_surface_names(sfm):
+    for name in ["LossFunction", "RotationEstimator", "NonlinearRotationEstimator", "ReconstructionEstimatorOptions",
+                 "ReconstructionBuilderOptions", "Reconstruction", "ViewGraph", "TwoViewInfo", "ReconstructionBuilder",
+                 "GlobalReconstructionEstimator", "RotationErrorType", "PositionErrorType", "MapEdges", "MapEdgesCovariance",
+                 "MapViewIdVector3d", "load_1DSFM_config", "Read1DSFM", "ReadCovariance", "CalcCovariance", "SetOrientations",
+                 "InitGlog", "StopGlog", "tgamma", "test_loss_with_input_x", "nu3", "C3", "sigma_quantile3",
+                 "upper_incomplete_gamma_of_k3", "stored_gamma_number3", "precision_of_stored_gamma3", "stored_gamma_values3",
+                 "nu4", "C4", "stored_gamma_values4", "nu9", "C9", "stored_gamma_values9"]:
+        assert hasattr(sfm, name), name
+    E = sfm.RotationErrorType
+    assert (E.QUATERNION_NORM, E.ROTATION_MAT_FNORM, E.QUATERNION_COSINE, E.ANGLE_AXIS_COVARIANCE, E.ANGLE_AXIS,
+            E.ANGLE_AXIS_COVTRACE, E.ANGLE_AXIS_COVNORM) == (0, 1, 2, 3, 4, 7, 8)
+    assert len(sfm.stored_gamma_values3) == 36843 and len(sfm.stored_gamma_values9) == 48553
+
+
+def test_gamma_tables_match_reference(sfm, golden_dir):
+    z = np.load(os.path.join(golden_dir, "loss_golden.npz"))
+    for nu in (3, 4, 9):
+        tab = np.array(getattr(sfm, f"stored_gamma_values{nu}"))
+        assert np.abs(tab[z[f"gamma{nu}_idx"]] - z[f"gamma{nu}_val"]).max() < 2e-14
+        c = z[f"const{nu}"]
+        assert (getattr(sfm, f"nu{nu}"), getattr(sfm, f"C{nu}"), getattr(sfm, f"sigma_quantile{nu}"),
+                getattr(sfm, f"upper_incomplete_gamma_of_k{nu}"), getattr(sfm, f"stored_gamma_number{nu}"),
+                getattr(sfm, f"precision_of_stored_gamma{nu}")) == tuple(c.tolist())
+
+
+def test_filter_and_mst_through_module(sfm, golden_dir, madrid):
+    recon, graph, covs = _graph_from_fixture(sfm, golden_dir)
+    assert graph.NumViews() == 394 and graph.NumEdges() == 23784 and len(covs) == 23783
+    opts = sfm.ReconstructionBuilderOptions()
+    builder = sfm.ReconstructionBuilder(opts, recon, graph)
+    builder.CheckView()
+    est = sfm.GlobalReconstructionEstimator(opts.reconstruction_estimator_options)
+    assert est.FilterInitialViewGraphAndCalibrateCameras(builder.get_view_graph(), builder.get_reconstruction())
+    assert graph.NumViews() == 379 and graph.NumEdges() == 18811
+    est.OrientationsFromMaximumSpanningTree()
+    om = np.array([est.orientations[int(v)] for v in madrid.view_ids])
+    assert np.array_equal(om, madrid.omega_init)
+
+
+@pytest.mark.skipif(not os.path.isdir(MADRID), reason="reference dataset not mounted (GPU box)")
+def test_read1dsfm_on_the_reference_dataset(sfm, golden_dir):
+    z = np.load(os.path.join(golden_dir, "madrid_metropolis.npz"))
+    recon, graph, covs = sfm.Reconstruction(), sfm.ViewGraph(), sfm.MapEdgesCovariance()
+    assert sfm.Read1DSFM(MADRID, recon, graph, covs)
+    assert recon.NumViews() == 394 and graph.NumEdges() == 23784 and len(covs) == 23783
+    from globalsfmpy_b200 import viewgraph as vg
+    rot2 = vg.egs_to_rotation_2(z["edge_R"])
+    edges = graph.GetAllEdges()
+    for k in range(0, len(rot2), 37):
+        info = edges[tuple(z["edge_ij"][k].tolist())]
+        assert np.array_equal(info.rotation_2, rot2[k]) and info.num_verified_matches == z["num_verified_matches"][k]
+    k = 1234
+    c = z["cov6"][k]
+    S = covs[tuple(z["cov_ij"][k].tolist())][0]
+    assert S[0, 0] == c[0] and S[1, 2] == c[5] and S[0, 1] == c[3]
+    opts = sfm.ReconstructionBuilderOptions()
+    sfm.load_1DSFM_config(os.path.join(REF, "flags_1dsfm.yaml"), opts)
+    assert opts.reconstruction_estimator_options.min_num_two_view_inliers == 30 and opts.num_threads == 16
+    assert opts.reconstruction_estimator_options.rotation_filtering_max_difference_degrees == 15.0
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference not mounted (GPU box)")
+def test_reference_loss_classes_are_recognised(sfm):
+    """The UNMODIFIED scripts/loss_functions.py, importing OUR module as GlobalSfMpy, maps onto the device losses."""
+    from globalsfmpy_b200 import _capi as capi
+    from globalsfmpy_b200.losses import loss_to_struct, UnsupportedLoss
+    sys.modules["GlobalSfMpy"] = sfm
+    sys.path.insert(0, os.path.join(REF, "scripts"))
+    try:
+        lf = importlib.import_module("loss_functions")
+    finally:
+        sys.path.pop(0)
+    cases = [(lf.TrivialLoss(), capi.LOSS_TRIVIAL, []), (lf.HuberLoss(0.1), capi.LOSS_HUBER, [0.1]),
+             (lf.SoftLOneLoss(0.1), capi.LOSS_SOFTLONE, [0.1]), (lf.CauchyLoss(0.05), capi.LOSS_CAUCHY, [0.05]),
+             (lf.ArctanLoss(0.3), capi.LOSS_ARCTAN, [0.3]), (lf.TolerantLoss(0.5, 0.1), capi.LOSS_TOLERANT, [0.5, 0.1]),
+             (lf.TukeyLoss(0.4), capi.LOSS_TUKEY, [0.4]), (lf.LOneHalfLoss(0.7), capi.LOSS_LONEHALF, [0.7]),
+             (lf.LTwoLoss(0.6, 1.0), capi.LOSS_LTWO, [0.6]), (lf.GemanMcClureLoss(0.3, 2.0), capi.LOSS_GEMANMCCLURE, [0.3, 2.0]),
+             (lf.MAGSACWeightBasedLoss(0.02), capi.LOSS_MAGSAC3, [0.02]), (lf.MAGSACWeightBasedLoss4(0.02), capi.LOSS_MAGSAC4, [0.02]),
+             (lf.MAGSACWeightBasedLoss9(0.3), capi.LOSS_MAGSAC9, [0.3])]
+    for obj, kind, params in cases:
+        L = loss_to_struct(obj, verify=False)
+        assert L.kind == kind, type(obj).__name__
+        assert np.allclose([L.p[k] for k in range(len(params))], params, rtol=1e-15)
+    assert loss_to_struct(lf.MAGSACWeightBasedLoss4(0.02), verify=False).flags == 1      # nu=4 defaults to the inverse weight
+    L = loss_to_struct(lf.ScaledLoss(lf.ScaledLoss(lf.CauchyLoss(0.05), 2.0), 1.25), verify=False)
+    assert L.kind == capi.LOSS_CAUCHY and L.scale == 2.5
+    with pytest.raises(UnsupportedLoss):
+        loss_to_struct(lf.ComposedLoss(lf.CauchyLoss(0.1), lf.HuberLoss(0.1)), verify=False)
+    # the reference classes evaluated against OUR module's constants/tables reproduce the golden vectors
+    z = np.load(os.path.join(ROOT, "tests", "golden", "loss_golden.npz"))
+    out = [0.0, 0.0, 0.0]
+    for k in range(0, len(z["s"]), 5):
+        lf.MAGSACWeightBasedLoss(0.02).Evaluate(float(z["s"][k]), out)
+        assert np.allclose(out, z["magsac3_0.02"][k], rtol=1e-12, atol=1e-11)
+
+
+@pytest.mark.gpu
+def test_pipeline_call_sequence_on_madrid(sfm, golden_dir, madrid):
+    """scripts/sfm_pipeline.py:31-70 with onlyRotationAvg=True, same calls in the same order, through the module;
+    must equal the direct C-ABI solve on the same inputs bit for bit."""
+    from globalsfmpy_b200 import _capi as capi, solver, loss_functions as lf
+    recon, graph, covs = _graph_from_fixture(sfm, golden_dir)
+    options = sfm.ReconstructionBuilderOptions()
+    builder = sfm.ReconstructionBuilder(options, recon, graph)
+    builder.CheckView()
+    view_graph, reconstruction = builder.get_view_graph(), builder.get_reconstruction()
+    est = sfm.GlobalReconstructionEstimator(options.reconstruction_estimator_options)
+    est.FilterInitialViewGraphAndCalibrateCameras(view_graph, reconstruction)
+    loss = lf.MAGSACWeightBasedLoss(0.02)
+    assert est.EstimateGlobalRotationsUncertainty(loss, covs, sfm.RotationErrorType.ANGLE_AXIS_COVARIANCE)
+    sfm.SetOrientations(est.orientations, reconstruction)
+    got = np.array([reconstruction.View(int(v)).GetOrientationAsAngleAxis() for v in madrid.view_ids])
+    assert all(reconstruction.View(int(v)).IsEstimated() for v in madrid.view_ids)
+    prob = solver.make_problem(madrid, capi.ANGLE_AXIS_COVARIANCE)
+    o = capi.default_options_py()
+    o.loss = capi.Loss.make(capi.LOSS_MAGSAC3, 0.02)
+    # the module hands the edges over in hash-map order; the solver sorts half-edges itself, so the result is the same
+    ref, s, _ = solver.solve(prob, o, madrid.omega_init)
+    assert np.array_equal(got, ref)
+    # step 4 of the pipeline: the rotation filter (15 degrees in flags_1dsfm.yaml) on the device
+    est.options.rotation_filtering_max_difference_degrees = 15.0
+    n0 = view_graph.NumEdges()
+    est.FilterRotations()
+    keep, _ = solver.filter_view_pairs(prob, ref, 15.0)
+    assert view_graph.NumEdges() == int(keep.sum()) < n0
+
+
+@pytest.mark.gpu
+def test_loss_objects_evaluate_on_device(sfm, golden_dir):
+    from globalsfmpy_b200 import loss_functions as lf
+    from globalsfmpy_b200.losses import loss_to_struct, UnsupportedLoss
+    z = np.load(os.path.join(golden_dir, "loss_golden.npz"))
+    out = [0.0, 0.0, 0.0]
+    for k in (3, 40, 200, 500):
+        lf.CauchyLoss(0.05).Evaluate(float(z["s"][k]), out)
+        assert np.allclose(out, z["cauchy_0.05"][k], rtol=1e-12, atol=1e-12)
+
+    class CauchyLoss(sfm.LossFunction):          # same NAME as a shipped loss, different behaviour: must be rejected
+        def __init__(self):
+            self.b, self.c = 0.01, 100.0
+
+        def Evaluate(self, s, out):
+            out[0], out[1], out[2] = s, 1.0, 0.0
+    with pytest.raises(UnsupportedLoss):
+        loss_to_struct(CauchyLoss())
