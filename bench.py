@@ -53,13 +53,30 @@ def build_workload(name, per_gpu_scale=1):
 
 def bench_options(loss):
     """Solver options of the bench: Ceres defaults of the reference (200 its, ftol 1e-6, ...) and an inexact-Newton
-    PCG tolerance of 1e-6 (the converged rotations are independent of it; tests pin parity at 1e-12)."""
+    PCG tolerance of 1e-3 on the residual (Ceres' own inexact step solvers default to eta = 1e-1).  The minimiser
+    reached does not depend on it: `accuracy` in the JSON line reports the distance of the solution obtained with
+    exactly these options from a tightly converged solve (bar: 1e-4 rad); the parity tests use 1e-12."""
     from globalsfmpy_b200 import _capi as capi
     o = capi.default_options_py()
     o.loss = loss
-    o.pcg_rtol = 1e-6
+    o.pcg_rtol = 1e-3
     o.pcg_max_iterations = 200
     return o
+
+
+def accuracy_report(S, vg, capi, prob, g, opt):
+    """Full solves with the bench options and with tight tolerances: iterations, cost, mean angular error."""
+    import copy
+    om, s, _ = S.solve(prob, opt, g.omega_init)
+    t = copy.copy(opt)
+    t.pcg_rtol, t.pcg_max_iterations, t.function_tolerance, t.max_num_iterations = 1e-12, 2000, 1e-14, 400
+    om_t, s_t, _ = S.solve(prob, t, g.omega_init)
+    rep = {"lm_iterations": s.num_iterations, "pcg_iterations_total": int(s.total_linear_iterations), "final_cost": s.final_cost,
+           "termination": capi.TERMINATION[s.termination], "tight_lm_iterations": s_t.num_iterations, "tight_final_cost": s_t.final_cost,
+           "mean_angular_error_vs_tight_rad": vg.mean_angular_error(om_t, om)[0]}
+    if g.omega_gt is not None:
+        rep["mean_angular_error_vs_ground_truth_deg"] = float(np.degrees(vg.mean_angular_error(g.omega_gt, om)[0]))
+    return rep
 
 
 class ClockSampler:
@@ -73,7 +90,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(self.dev)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -149,13 +166,64 @@ def run_reference(args, name):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": name, "views": g.num_views, "edges": g.num_edges, "loss": WORKLOADS[name]["loss"],
-                       "error_type": WORKLOADS[name]["etype"], "linear_solver": "block-Jacobi PCG rtol 1e-6 (the reference's "
+                       "error_type": WORKLOADS[name]["etype"], "linear_solver": "block-Jacobi PCG rtol 1e-3 (the reference's "
                        "SPARSE_NORMAL_CHOLESKY would be a dense 30k x 30k factorisation here; PCG is the faster CPU choice)"},
             "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "port",
                              "sample": f"{iters} LM iterations of the full workload (warm-up not excluded: no device to warm)"},
             "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def madrid_report():
+    """BASELINE configs[0] / north_star: 1DSfM Madrid_Metropolis with the shipped pipeline's settings
+    (ANGLE_AXIS_COVARIANCE + MAGSACWeightBasedLoss(0.02), Ceres defaults), whole-solve wall clock on one GPU through the
+    one-shot C-ABI call vs the CPU oracle (exact dense Cholesky standing in for SPARSE_NORMAL_CHOLESKY): (a) native C++
+    loss, all cores; (b) the reference's actual mode of operation -- the loss is a Python object called back once per
+    edge per evaluation (bind_src/GlobalSfMpy.cpp:36-59)."""
+    from globalsfmpy_b200 import _capi as capi, solver as S, viewgraph as vg, loss_functions as lf
+    from globalsfmpy_b200.losses import loss_to_struct
+    from oracle import ra_oracle as orc
+    path = os.path.join(ROOT, "tests", "golden", "madrid_metropolis.npz")
+    if not os.path.exists(path):
+        return None
+    g = vg.load_madrid_fixture(path)
+    prob = S.make_problem(g, capi.ANGLE_AXIS_COVARIANCE)
+    o = capi.default_options_py()
+    o.loss = capi.Loss.make(capi.LOSS_MAGSAC3, 0.02)
+    o.linear_solver = capi.SOLVER_DENSE_CHOLESKY   # exact factorisation on the device, as the reference's sparse Cholesky
+    S.solve(prob, o, g.omega_init)  # warm
+    t0 = time.perf_counter()
+    om, s, _ = S.solve(prob, o, g.omega_init)
+    t_gpu = time.perf_counter() - t0
+    o.linear_solver = capi.SOLVER_DENSE_CHOLESKY
+    o.num_threads = os.cpu_count()
+    t0 = time.perf_counter()
+    om_c, s_c, _ = orc.solve(prob, o, g.omega_init)
+    t_cpu = time.perf_counter() - t0
+    # (b) Python loss callback: this repo's mirror class cannot be used (it is device backed), so the callback evaluates
+    # the oracle's C loss through ctypes -- one Python call per edge per evaluation, like the reference, but with a
+    # CHEAPER body than the reference's ~25 bytecode-level float operations
+    L = o.loss
+    buf = np.zeros(3)
+    lib = orc.lib()
+    pbuf = capi.ptr(buf)
+    ncalls = [0]
+
+    def cb(sq):
+        ncalls[0] += 1
+        lib.ra_oracle_loss(C.byref(L), sq, pbuf)
+        return buf
+    t0 = time.perf_counter()
+    om_p, s_p, _ = orc.solve(prob, o, g.omega_init, loss_callback=cb)
+    t_py = time.perf_counter() - t0
+    return {"views": g.num_views, "edges": g.num_edges, "gpu_solve_ms": 1e3 * t_gpu, "gpu_lm_iterations": s.num_iterations,
+            "gpu_final_cost": s.final_cost, "cpu_native_solve_ms": 1e3 * t_cpu, "cpu_lm_iterations": s_c.num_iterations,
+            "cpu_final_cost": s_c.final_cost, "cpu_python_loss_solve_ms": 1e3 * t_py, "python_loss_calls": ncalls[0],
+            "speedup_vs_cpu_native": t_cpu / t_gpu, "speedup_vs_cpu_python_loss": t_py / t_gpu, "cores": os.cpu_count(),
+            "mean_angular_error_gpu_vs_cpu_rad": vg.mean_angular_error(om_c, om)[0],
+            "note": "MAGSAC's quantised loss makes the trajectory chaotic (SURVEY Appendix E): the two solutions agree to the "
+                    "oracle's own reproducibility (~1e-3 rad), not to 1e-4; smooth-loss parity is pinned at 1e-6 in tests/"}
 
 
 def cpu_baseline_sample(prob, g, loss, seconds_budget=20.0):
@@ -177,14 +245,14 @@ def cpu_baseline_sample(prob, g, loss, seconds_budget=20.0):
     wall = time.perf_counter() - t0
     iters = max(1, s.num_iterations)
     return {"value": g.num_edges * iters / wall, "unit": "edges/s", "cores": cores, "kind": "port",
-            "sample": f"{iters} LM iterations of the full workload, native C++ loss, OpenMP over edges, PCG rtol 1e-6 "
+            "sample": f"{iters} LM iterations of the full workload, native C++ loss, OpenMP over edges, PCG rtol 1e-3 "
                       f"({1e3 * wall / iters:.0f} ms/iteration)"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="syn_10k_1M", choices=sorted(WORKLOADS))
@@ -313,8 +381,12 @@ def main():
                        "calls": calls, "iterations_per_call": it_total / max(1, calls), "ms_per_call": 1e3 * t_total / max(1, calls),
                        "note": "one gsfm_ra_solve() per call: host structure build + upload + every LM iteration + download; "
                                "bytes are per LM iteration (call bytes / iterations)"}
+    if rank == 0 and world == 1 and not args.no_e2e:
+        from globalsfmpy_b200 import viewgraph as vg
+        line["accuracy"] = accuracy_report(S, vg, capi, prob, g, opt)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(prob, g, loss)
+        line["madrid"] = madrid_report()
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -916,6 +916,181 @@ __global__ void __launch_bounds__(kBlock) k_pcg_persistent(PcgParams P) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Small problems: exact dense LL^T of (Ht + Lam) on the device (GSFM_RA_SOLVER_DENSE_CHOLESKY), the
+// role SPARSE_NORMAL_CHOLESKY plays in the reference (rotation_estimator.cpp:300).  For a view graph
+// like Madrid_Metropolis (379 views, 26 % dense, covariance weights spanning 12 decades) PCG needs
+// hundreds of steps per solve; the 1137 x 1137 factorisation does not care.
+// One cooperative kernel, right-looking blocked factorisation with 32 x 32 tiles:
+//   per panel: every CTA factors the diagonal tile in shared memory (redundantly: no barrier for it),
+//   the tiles below are solved against it, barrier, the trailing tiles are updated, barrier;
+//   then forward/backward substitution by CTA 0.
+// A is column-major, lower triangle, n padded to a multiple of 32 with a unit diagonal.
+// ------------------------------------------------------------------------------------------
+constexpr int kNB = 32;
+
+// The right-hand side rides along as an EXTRA ROW of the matrix (row index n, inside the padding): factoring
+// [A b; b^T beta] = [L 0; y^T *][L^T y; 0 *] leaves y = L^-1 b in that row, so the forward substitution costs nothing.
+__global__ void k_dense_assemble(uint64_t H, uint32_t N, uint32_t np, const uint32_t* __restrict__ he_row, const uint32_t* __restrict__ he_col,
+                                 const double* __restrict__ recs, const double* __restrict__ Dblk, const double* __restrict__ rhs,
+                                 double* __restrict__ A) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n = 3 * N;
+  if (t < H) {
+    const uint32_t row = he_row[t], col = he_col[t] & ~kSideBit;
+    if (row > col) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) A[(size_t)(3 * col + c) * np + 3 * row + r] = recs[blk_index(t, 3 * r + c)];
+    }
+  }
+  if (t < N) {
+    const double* D = Dblk + 6 * (size_t)t;
+    const size_t o = 3 * (size_t)t;
+    A[o * np + o] = D[0]; A[o * np + o + 1] = D[1]; A[o * np + o + 2] = D[2];
+    A[(o + 1) * np + o + 1] = D[3]; A[(o + 1) * np + o + 2] = D[4];
+    A[(o + 2) * np + o + 2] = D[5];
+  }
+  if (t < n) A[(size_t)t * np + n] = rhs[t];
+  if (t == n) A[(size_t)t * np + t] = 1e200;
+  if (t > n && t < np) A[(size_t)t * np + t] = 1.0;
+}
+
+// 32 x 32 lower-triangular tile in shared memory: factor it (LL^T) and invert the factor, one warp, everything
+// in registers with compile-time indices.  Lt <- L, Wt <- L^-1.
+__device__ __forceinline__ void tile_potrf_inv(double (*Lt)[kNB + 1], double (*Wt)[kNB + 1], int* fail) {
+  const int lane = threadIdx.x & 31;
+  double row[kNB];
+#pragma unroll
+  for (int c = 0; c < kNB; ++c) row[c] = Lt[lane][c];
+#pragma unroll
+  for (int j = 0; j < kNB; ++j) {
+    const double d = __shfl_sync(0xffffffffu, row[j], j);
+    if (!(d > 0.0) && lane == 0) *fail = 1;
+    const double inv = rsqrt(d > 0.0 ? d : 1.0);
+    if (lane == j) row[j] = d * inv;
+    else if (lane > j) row[j] *= inv;
+    const double lj = row[j];
+#pragma unroll
+    for (int c = 0; c < kNB; ++c) {
+      if (c > j) {
+        const double lc = __shfl_sync(0xffffffffu, lj, c);
+        if (lane >= c) row[c] -= lj * lc;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kNB; ++c) Lt[lane][c] = (c <= lane) ? row[c] : 0.0;
+  __syncwarp();
+  // column `lane` of X = L^-1: forward substitution, L read from shared memory (broadcast)
+  double x[kNB];
+#pragma unroll
+  for (int i = 0; i < kNB; ++i) {
+    double acc = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int m = 0; m < kNB; ++m)
+      if (m < i) acc -= Lt[i][m] * x[m];
+    x[i] = (i >= lane) ? acc / Lt[i][i] : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < kNB; ++i) Wt[i][lane] = x[i];
+}
+
+__global__ void __launch_bounds__(kBlock) k_dense_cholesky_solve(uint32_t n, uint32_t np, double* __restrict__ A, double* __restrict__ x,
+                                                                  double* __restrict__ winv, double* __restrict__ work, DevScalars* sc) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double L11[kNB][kNB + 1];
+  __shared__ double W11[kNB][kNB + 1];
+  __shared__ double T1[kNB][kNB + 1];
+  __shared__ double T2[kNB][kNB + 1];
+  __shared__ int s_fail;
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;  // 32 x 8
+  const uint32_t nblk = np / kNB;
+  if (tid == 0) s_fail = 0;
+  __syncthreads();
+  for (uint32_t kb = 0; kb < nblk; ++kb) {
+    // (1) diagonal tile -> shared; factor + invert (every CTA, redundantly: no barrier needed for it)
+    for (int c = ty; c < kNB; c += 8) L11[tx][c] = A[(size_t)(kb * kNB + c) * np + kb * kNB + tx];
+    __syncthreads();
+    if (tid < 32) tile_potrf_inv(L11, W11, &s_fail);
+    __syncthreads();
+    // (2) panel: L[ib][kb] = A[ib][kb] W^T   (W = L11^-1, lower triangular)
+    for (uint32_t ib = kb + 1 + blockIdx.x; ib < nblk; ib += gridDim.x) {
+      for (int c = ty; c < kNB; c += 8) T1[tx][c] = A[(size_t)(kb * kNB + c) * np + ib * kNB + tx];
+      __syncthreads();
+      for (int c = ty; c < kNB; c += 8) {
+        double acc = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < kNB; ++k) acc += T1[tx][k] * W11[c][k];
+        A[(size_t)(kb * kNB + c) * np + ib * kNB + tx] = acc;
+      }
+      __syncthreads();
+    }
+    grid.sync();
+    if (blockIdx.x == 0) {  // factored tile + its inverse back to global (after the barrier: others were still loading it)
+      for (int c = ty; c < kNB; c += 8) {
+        if (tx >= c) A[(size_t)(kb * kNB + c) * np + kb * kNB + tx] = L11[tx][c];
+        winv[(size_t)kb * kNB * kNB + c * kNB + tx] = W11[tx][c];  // winv[kb][col c][row tx]
+      }
+    }
+    // (3) trailing update: A[i][j] -= L[i][kb] L[j][kb]^T for kb < j <= i
+    const uint32_t m = nblk - kb - 1;
+    const uint32_t ntiles = m * (m + 1) / 2;
+    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      uint32_t i = (uint32_t)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+      while ((uint64_t)(i + 1) * (i + 2) / 2 <= t) ++i;
+      while ((uint64_t)i * (i + 1) / 2 > t) --i;
+      const uint32_t j = t - i * (i + 1) / 2;
+      const uint32_t ib = kb + 1 + i, jb = kb + 1 + j;
+      for (int c = ty; c < kNB; c += 8) {
+        T1[tx][c] = A[(size_t)(kb * kNB + c) * np + ib * kNB + tx];
+        T2[tx][c] = A[(size_t)(kb * kNB + c) * np + jb * kNB + tx];
+      }
+      __syncthreads();
+      for (int c = ty; c < kNB; c += 8) {
+        double acc = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < kNB; ++k) acc += T1[tx][k] * T2[c][k];
+        A[(size_t)(jb * kNB + c) * np + ib * kNB + tx] -= acc;
+      }
+      __syncthreads();
+    }
+    grid.sync();
+  }
+  // (4) back substitution L^T x = y by CTA 0, y = row n of the factor; inverted diagonal tiles make each step a
+  //     column dot-product sweep + a 32 x 32 mat-vec, no serial recurrence
+  if (blockIdx.x == 0) {
+    for (uint32_t i = tid; i < np; i += kBlock) work[i] = (i < n) ? A[(size_t)i * np + n] : 0.0;
+    __syncthreads();
+    for (int kbi = (int)nblk - 1; kbi >= 0; --kbi) {
+      const uint32_t kb = (uint32_t)kbi;
+      for (int c = ty; c < kNB; c += 8) W11[tx][c] = winv[(size_t)kb * kNB * kNB + c * kNB + tx];
+      {
+        double acc = 0.0;  // column kb*32+tx: sum over rows below the tile (rows >= n carry no unknowns)
+        for (uint32_t r = (kb + 1) * kNB + ty; r < n; r += 8) acc += A[(size_t)(kb * kNB + tx) * np + r] * work[r];
+        T2[ty][tx] = acc;
+      }
+      __syncthreads();
+      if (tid < 32) {
+        double s = 0.0;
+        for (int q = 0; q < 8; ++q) s += T2[q][tid];
+        T1[0][tid] = (kb * kNB + tid < n) ? work[kb * kNB + tid] - s : 0.0;
+      }
+      __syncthreads();
+      if (tid < 32) {  // x_tile = W^T rhs
+        double xv = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < kNB; ++k) xv += W11[k][tid] * T1[0][k];
+        work[kb * kNB + tid] = (kb * kNB + tid < n) ? xv : 0.0;
+      }
+      __syncthreads();
+    }
+    for (uint32_t i = tid; i < n; i += kBlock) x[i] = work[i];
+    if (tid == 0) { sc->pcg_iter = 1; sc->pcg_done = 1; sc->pcg_breakdown = s_fail; sc->rr = 0.0; }
+  }
+}
+
 // After the solve (xt = tangent step, Hx = Ht xt without damping): Euclidean step
 // delta = Jl^-1 xt, candidate = omega + delta (Ceres updates the angle-axis vector additively);
 // reduce delta.g (= xt.gt), delta.H.delta (= xt.Hx), |delta|^2.
@@ -1290,7 +1465,7 @@ struct gsfm_ra_solver {
   DevBuf<double> part;
   int cur = 0;
   // PCG
-  DevBuf<double> scale, Dblk, Minv, x, r, z, p, p1, y, ypart, delta;
+  DevBuf<double> scale, Dblk, Minv, x, r, z, p, p1, y, ypart, delta, dense_A, dense_work, dense_winv;
   DevBuf<double> slots, slotsA, slotsB, slotsC;
   DevBuf<unsigned> counter, row_cnt;
   DevBuf<DevScalars> sc;
@@ -1400,6 +1575,28 @@ struct gsfm_ra_solver {
                                                          Hd_p[b], gt_p[b], user_damp, user_b, Dblk.p, Minv.p, x.p, r.p, z.p, p.p, p1.p, slots.p,
                                                          counter.p, sc.p);
     launches += 1;
+    if (opt.linear_solver == GSFM_RA_SOLVER_DENSE_CHOLESKY) {
+      const uint32_t n = 3 * N, np = (n + 1 + kNB - 1) / kNB * kNB;  // room for the right-hand-side row
+      if (dense_A.n < (size_t)np * np) {
+        AllocScope scope(stream);
+        RA_TRY(dense_A.alloc((size_t)np * np));
+        RA_TRY(dense_work.alloc(np));
+        RA_TRY(dense_winv.alloc((size_t)np * kNB));
+      }
+      CUDA_TRY(cudaMemsetAsync(dense_A.p, 0, (size_t)np * np * sizeof(double), stream));
+      k_dense_assemble<<<grid_for(std::max<uint64_t>(H, np)), kBlock, 0, stream>>>(H, N, np, he_row.p, he_col.p, val[b].p, Dblk.p, r.p, dense_A.p);
+      uint32_t n_arg = n, np_arg = np;
+      double* A_arg = dense_A.p; double* x_arg = x.p; double* wi_arg = dense_winv.p; double* w_arg = dense_work.p; DevScalars* sc_arg = sc.p;
+      void* args[] = {&n_arg, &np_arg, &A_arg, &x_arg, &wi_arg, &w_arg, &sc_arg};
+      // all SMs: the trailing update of panel kb has (nblk-kb)(nblk-kb-1)/2 tiles to spread
+      int occ = 1;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dense_cholesky_solve, kBlock, 0));
+      const unsigned grid = (unsigned)(sm_count * std::max(1, std::min(occ, 2)));
+      CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_dense_cholesky_solve, dim3(grid), dim3(kBlock), args, 0, stream));
+      launches += 2;
+      RA_TRY(spmv(b, x.p, y.p, Hd_p[b]));
+      return 0;
+    }
     if (cooperative && !sharded()) {
       PcgParams P = pcg_params(b, rtol, max_iter);
       void* args[] = {&P};
@@ -1891,7 +2088,13 @@ int gsfm_ra_solver_reset(gsfm_ra_solver* s) {
 }
 int gsfm_ra_solver_iterate(gsfm_ra_solver* s, int32_t num_iterations, gsfm_ra_summary* summary) {
   if (!s) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
-  if (s->opt.linear_solver != GSFM_RA_SOLVER_PCG) { set_error("linear solver %d is not implemented (PCG only)", s->opt.linear_solver); return GSFM_RA_ERR_UNSUPPORTED; }
+  if (s->opt.linear_solver == GSFM_RA_SOLVER_DENSE_CHOLESKY) {
+    if (s->N > 2730) { set_error("dense Cholesky is limited to 2730 views (8190 unknowns); use PCG"); return GSFM_RA_ERR_UNSUPPORTED; }
+    if (s->sharded() || !s->cooperative) { set_error("dense Cholesky needs a single cooperative-launch device"); return GSFM_RA_ERR_UNSUPPORTED; }
+  } else if (s->opt.linear_solver != GSFM_RA_SOLVER_PCG) {
+    set_error("unknown linear solver %d", s->opt.linear_solver);
+    return GSFM_RA_ERR_INVALID;
+  }
   return iterate(s, num_iterations, summary);
 }
 int gsfm_ra_comm_unique_id(uint8_t* id) {

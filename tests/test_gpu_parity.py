@@ -271,6 +271,39 @@ def test_madrid_magsac_reference_path(madrid):
     assert mean < 5e-3, mean
 
 
+def test_dense_cholesky_path_tracks_the_oracle_on_madrid(madrid):
+    """GSFM_RA_SOLVER_DENSE_CHOLESKY: exact factorisation on the device, like the reference's SPARSE_NORMAL_CHOLESKY.
+    With exact solves on both sides the GPU loop follows the oracle's trajectory on the shipped dataset with the shipped
+    settings far longer than PCG can (MAGSAC's staircase loss amplifies 1e-10 step differences)."""
+    prob = solver.make_problem(madrid, capi.ANGLE_AXIS_COVARIANCE)
+    o = capi.default_options_py()
+    o.loss = MAGSAC
+    o.linear_solver = capi.SOLVER_DENSE_CHOLESKY
+    og, sg, tg = solver.solve(prob, o, madrid.omega_init, trace_capacity=256)
+    oo, so, to = orc.solve(prob, o, madrid.omega_init, trace_capacity=256)
+    for a, b in list(zip(tg, to))[:25]:
+        assert a.step_is_successful == b.step_is_successful
+        assert abs(a.cost - b.cost) <= 1e-7 * abs(b.cost), (a.iteration, a.cost, b.cost)
+    assert abs(sg.final_cost - so.final_cost) <= 2e-4 * so.final_cost
+    mean, _ = vg.mean_angular_error(oo, og)
+    assert mean < 5e-3, mean
+    # smooth loss, tight tolerances: the north_star bar with margin
+    og, sg, _ = solver.solve(prob, _tight(CAUCHY, linear_solver=capi.SOLVER_DENSE_CHOLESKY), madrid.omega_init)
+    oo, so, _ = orc.solve(prob, _tight(CAUCHY, linear_solver=capi.SOLVER_DENSE_CHOLESKY), madrid.omega_init)
+    mean, mx = vg.mean_angular_error(oo, og)
+    assert mean <= 1e-6, (mean, mx, sg.final_cost, so.final_cost)
+
+
+def test_dense_cholesky_small_and_padded():
+    for n_views, n_edges in ((5, 8), (33, 200), (150, 2500)):
+        g = vg.synthetic_pose_graph(n_views, n_edges, seed=n_views, noise_deg=1.0, outlier_fraction=0.1)
+        prob = solver.make_problem(g, capi.ANGLE_AXIS)
+        a, sa, _ = solver.solve(prob, _tight(CAUCHY, linear_solver=capi.SOLVER_DENSE_CHOLESKY), g.omega_init)
+        b, sb, _ = orc.solve(prob, _tight(CAUCHY, linear_solver=capi.SOLVER_DENSE_CHOLESKY), g.omega_init)
+        mean, _ = vg.mean_angular_error(b, a)
+        assert mean < 1e-7 and sa.num_iterations == sb.num_iterations, (n_views, mean, sa.num_iterations, sb.num_iterations)
+
+
 def test_madrid_cauchy_tight(madrid):
     prob = solver.make_problem(madrid, capi.ANGLE_AXIS_COVARIANCE)
     og, sg, _ = solver.solve(prob, _tight(CAUCHY, pcg_max_iterations=5000), madrid.omega_init)
