@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libgsfm_ra.so")
 
 ABI_VERSION = 1
 COMM_ID_BYTES = 128
+IPC_HANDLE_BYTES = 128
 
 # gsfm_ra_status
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NUMERIC = 0, -1, -2, -3, -4, -5
@@ -186,6 +187,8 @@ def declare(lib, oracle=False):
     lib.gsfm_ra_solver_iterate.argtypes = [vp, C.c_int32, sp]
     lib.gsfm_ra_comm_unique_id.argtypes = [_u8p]
     lib.gsfm_ra_solver_comm_init.argtypes = [vp, _u8p]
+    lib.gsfm_ra_solver_ipc_export.argtypes = [vp, _u8p]
+    lib.gsfm_ra_solver_ipc_import.argtypes = [vp, _u8p]
     lib.gsfm_ra_solver_edge_range.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.gsfm_ra_solver_cuda_stream.argtypes = [vp]
     lib.gsfm_ra_solver_cuda_stream.restype = C.c_void_p
@@ -207,7 +210,7 @@ EXPORTED_SYMBOLS = [
     "gsfm_ra_solve", "gsfm_ra_solver_create", "gsfm_ra_solver_create_sharded", "gsfm_ra_solver_destroy",
     "gsfm_ra_solver_set_rotations", "gsfm_ra_solver_get_rotations", "gsfm_ra_solver_reset",
     "gsfm_ra_solver_iterate", "gsfm_ra_comm_unique_id", "gsfm_ra_solver_comm_init",
-    "gsfm_ra_solver_edge_range", "gsfm_ra_solver_cuda_stream", "gsfm_ra_solver_time_kernels", "gsfm_ra_eval_edges", "gsfm_ra_whiten", "gsfm_ra_assemble", "gsfm_ra_cost",
+    "gsfm_ra_solver_ipc_export", "gsfm_ra_solver_ipc_import", "gsfm_ra_solver_edge_range", "gsfm_ra_solver_cuda_stream", "gsfm_ra_solver_time_kernels", "gsfm_ra_eval_edges", "gsfm_ra_whiten", "gsfm_ra_assemble", "gsfm_ra_cost",
     "gsfm_ra_spmv", "gsfm_ra_pcg", "gsfm_ra_eval_loss", "gsfm_ra_filter_view_pairs",
 ]
 

@@ -101,8 +101,8 @@ struct DevScalars {
   int pcg_iter, pcg_done, pcg_breakdown, pad0;
   // step
   double dg, dHd, step2;  // delta.g, delta.H.delta, |delta|^2 (Euclidean step)
-  int bad;                // non-finite detected
-  int pad1;
+  int bad;                // non-finite detected (1) / a peer GPU did not show up (2)
+  int xseq;               // cross-GPU exchange sequence number (multi-GPU persistent PCG)
 };
 
 // Deterministic grid-wide sum of NV values: block tree -> per-block slot -> the LAST block to
@@ -714,6 +714,8 @@ __global__ void k_pcg_direction(uint32_t n3, const double* __restrict__ z, doubl
 // Epilogue: y = Ht x with the UNDAMPED diagonal, for the model cost change.
 // Vectors written inside the kernel are never accessed through __restrict__/read-only paths.
 // ------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+
 struct PcgParams {
   uint32_t N, num_warps, n_iso, warp_span;
   int max_iter;
@@ -726,6 +728,12 @@ struct PcgParams {
   double *slotsA, *slotsB, *slotsC;
   DevScalars* sc;
   unsigned long long* prof;  // optional [8] phase timers in ns, accumulated by block 0 (measurement aid)
+  // edge-sharded multi-GPU (world > 1): every rank's exchange block, mapped into this process over NVLink
+  // (CUDA IPC).  Layout of one block: double y[2][3N] (partial matvec, double buffered by step parity) followed
+  // by the rank's sequence flag.  peer_y[rank] / peer_flag[rank] are this rank's own block.
+  int world, rank;
+  double* peer_y[kMaxPeers];
+  unsigned* peer_flag[kMaxPeers];
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -774,7 +782,9 @@ __device__ __forceinline__ void all_blocks_sum2(const double* slots, double* o0,
 // One SpMV pass over this warp's range.  x_j = a_j + beta b_j (b may be null).  Returns (per lane)
 // the accumulated sum over the rows this lane finished of x_i . y_i.
 __device__ __forceinline__ double spmv_pass(const PcgParams& P, WarpPipe& wp, const double* a, const double* b, double beta, const double* diag,
-                                            double* xnew_out, double* y_out) {
+                                            double* xnew_out, double* y_out, double* ylocal_out = nullptr) {
+  // ylocal_out != null (multi-GPU): only the shard-local off-diagonal row sums are produced, into the exchange
+  // buffer; diagonal, direction and dot product follow after the cross-GPU reduction (exchange_finish).
   const int lane = threadIdx.x & 31;
   const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   double dot = 0.0;
@@ -803,14 +813,18 @@ __device__ __forceinline__ double spmv_pass(const PcgParams& P, WarpPipe& wp, co
             my0 += __ldcg(P.ypart + 3 * (size_t)q); my1 += __ldcg(P.ypart + 3 * (size_t)q + 1); my2 += __ldcg(P.ypart + 3 * (size_t)q + 2);
           }
         }
-        double xi[3] = {a[3 * (size_t)row], a[3 * (size_t)row + 1], a[3 * (size_t)row + 2]};
-        if (b) { xi[0] += beta * b[3 * (size_t)row]; xi[1] += beta * b[3 * (size_t)row + 1]; xi[2] += beta * b[3 * (size_t)row + 2]; }
-        double d[3];
-        sym_mul_vec(diag + 6 * (size_t)row, xi, d);
-        my0 += d[0]; my1 += d[1]; my2 += d[2];
-        y_out[3 * (size_t)row] = my0; y_out[3 * (size_t)row + 1] = my1; y_out[3 * (size_t)row + 2] = my2;
-        if (xnew_out) { xnew_out[3 * (size_t)row] = xi[0]; xnew_out[3 * (size_t)row + 1] = xi[1]; xnew_out[3 * (size_t)row + 2] = xi[2]; }
-        dot += xi[0] * my0 + xi[1] * my1 + xi[2] * my2;
+        if (ylocal_out) {
+          ylocal_out[3 * (size_t)row] = my0; ylocal_out[3 * (size_t)row + 1] = my1; ylocal_out[3 * (size_t)row + 2] = my2;
+        } else {
+          double xi[3] = {a[3 * (size_t)row], a[3 * (size_t)row + 1], a[3 * (size_t)row + 2]};
+          if (b) { xi[0] += beta * b[3 * (size_t)row]; xi[1] += beta * b[3 * (size_t)row + 1]; xi[2] += beta * b[3 * (size_t)row + 2]; }
+          double d[3];
+          sym_mul_vec(diag + 6 * (size_t)row, xi, d);
+          my0 += d[0]; my1 += d[1]; my2 += d[2];
+          y_out[3 * (size_t)row] = my0; y_out[3 * (size_t)row + 1] = my1; y_out[3 * (size_t)row + 2] = my2;
+          if (xnew_out) { xnew_out[3 * (size_t)row] = xi[0]; xnew_out[3 * (size_t)row + 1] = xi[1]; xnew_out[3 * (size_t)row + 2] = xi[2]; }
+          dot += xi[0] * my0 + xi[1] * my1 + xi[2] * my2;
+        }
       }
       nbatch = 0;
       __syncwarp();
@@ -830,8 +844,8 @@ __device__ __forceinline__ double spmv_pass(const PcgParams& P, WarpPipe& wp, co
     });
     if (nbatch) flush();
   }
-  // views without any half-edge: y_i = D_i x_i
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n_iso; k += gridDim.x * blockDim.x) {
+  // views without any half-edge: y_i = D_i x_i  (multi-GPU: their exchange slots stay zero, nothing to do)
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; !ylocal_out && k < P.n_iso; k += gridDim.x * blockDim.x) {
     const uint32_t row = P.iso[k];
     double xi[3] = {a[3 * (size_t)row], a[3 * (size_t)row + 1], a[3 * (size_t)row + 2]};
     if (b) { xi[0] += beta * b[3 * (size_t)row]; xi[1] += beta * b[3 * (size_t)row + 1]; xi[2] += beta * b[3 * (size_t)row + 2]; }
@@ -840,6 +854,51 @@ __device__ __forceinline__ double spmv_pass(const PcgParams& P, WarpPipe& wp, co
     y_out[3 * (size_t)row] = d[0]; y_out[3 * (size_t)row + 1] = d[1]; y_out[3 * (size_t)row + 2] = d[2];
     if (xnew_out) { xnew_out[3 * (size_t)row] = xi[0]; xnew_out[3 * (size_t)row + 1] = xi[1]; xnew_out[3 * (size_t)row + 2] = xi[2]; }
     dot += xi[0] * d[0] + xi[1] * d[1] + xi[2] * d[2];
+  }
+  return dot;
+}
+
+// Fused cross-GPU reduction of the partial matvec, inside the persistent kernel (no NCCL call, no kernel
+// boundary): publish "my partial sums for step `seq` are complete" with a system-scope release, wait for every
+// peer's flag, then every rank adds the partial vectors of ALL ranks in rank order straight out of peer memory
+// over NVLink (bitwise identical result everywhere) and finishes the row: y_i = D_i x_i + sum, direction, dot.
+// Buffer reuse is safe with two buffers: a rank can only reach step seq+2 after every peer published seq+1,
+// i.e. after every peer finished reading step seq.
+__device__ __forceinline__ double exchange_finish(const PcgParams& P, cg::grid_group& grid, unsigned seq, const double* a, const double* b,
+                                                  double beta, const double* diag, double* xnew_out, double* y_out) {
+  grid.sync();  // all local row sums of this step are in my exchange buffer
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    __threadfence_system();
+    *((volatile unsigned*)P.peer_flag[P.rank]) = seq;
+  }
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    for (int r = 0; r < P.world; ++r) {
+      if (r == P.rank) continue;
+      volatile unsigned* f = (volatile unsigned*)P.peer_flag[r];
+      while ((int)(*f - seq) < 0) {
+        if (clock64() - t0 > 8000000000ll) { P.sc->bad = 2; break; }  // ~4 s: a peer died; do not hang the GPU
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const size_t off = (size_t)(seq & 1u) * 3 * P.N;
+  double dot = 0.0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.N; i += gridDim.x * blockDim.x) {
+    double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+    for (int r = 0; r < P.world; ++r) {
+      const double* src = P.peer_y[r] + off + 3 * (size_t)i;
+      y0 += __ldcv(src); y1 += __ldcv(src + 1); y2 += __ldcv(src + 2);
+    }
+    double xi[3] = {a[3 * (size_t)i], a[3 * (size_t)i + 1], a[3 * (size_t)i + 2]};
+    if (b) { xi[0] += beta * b[3 * (size_t)i]; xi[1] += beta * b[3 * (size_t)i + 1]; xi[2] += beta * b[3 * (size_t)i + 2]; }
+    double d[3];
+    sym_mul_vec(diag + 6 * (size_t)i, xi, d);
+    y0 += d[0]; y1 += d[1]; y2 += d[2];
+    y_out[3 * (size_t)i] = y0; y_out[3 * (size_t)i + 1] = y1; y_out[3 * (size_t)i + 2] = y2;
+    if (xnew_out) { xnew_out[3 * (size_t)i] = xi[0]; xnew_out[3 * (size_t)i + 1] = xi[1]; xnew_out[3 * (size_t)i + 2] = xi[2]; }
+    dot += xi[0] * y0 + xi[1] * y1 + xi[2] * y2;
   }
   return dot;
 }
@@ -860,12 +919,21 @@ __global__ void __launch_bounds__(kBlock) k_pcg_persistent(PcgParams P) {
   bool done = P.sc->pcg_done != 0;
   double* pold = P.p1;  // zero-filled by k_prepare_solve: the first direction is p = z
   double* pnew = P.p0;
+  const bool multi = P.world > 1;
+  unsigned seq = multi ? (unsigned)P.sc->xseq : 0u;  // exchange sequence number, continues across launches
+  double* my_y = multi ? P.peer_y[P.rank] : nullptr;
   while (!done) {
     // ---- phase A: y = (Ht + Lam) p, p = z + beta p_old formed on the fly, p.y ----------------
     const bool prof = P.prof != nullptr && gtid == 0;
     unsigned long long tA = 0, tB = 0, tC = 0, tD = 0, tE = 0, tF = 0, tG = 0;
     if (prof) tA = gtimer();
-    const double dot = spmv_pass(P, wp, P.z, pold, beta, P.Dblk, pnew, P.y);
+    double dot;
+    if (!multi) dot = spmv_pass(P, wp, P.z, pold, beta, P.Dblk, pnew, P.y);
+    else {
+      ++seq;
+      spmv_pass(P, wp, P.z, pold, beta, P.Dblk, pnew, P.y, my_y + (size_t)(seq & 1u) * 3 * P.N);
+      dot = exchange_finish(P, grid, seq, P.z, pold, beta, P.Dblk, pnew, P.y);
+    }
     if (prof) tB = gtimer();
     const double bs = block_sum_to_thread0(dot, sm_red);
     if (threadIdx.x == 0) __stcg(P.slotsA + blockIdx.x, bs);
@@ -909,8 +977,14 @@ __global__ void __launch_bounds__(kBlock) k_pcg_persistent(PcgParams P) {
     if (rr <= P.rtol2 * bb || iter >= P.max_iter || !isfinite(rr)) done = true;
   }
   // ---- epilogue: y = Ht x (undamped diagonal) for the model cost change --------------------------
-  spmv_pass(P, wp, P.x, nullptr, 0.0, P.Hd, nullptr, P.y);
+  if (!multi) spmv_pass(P, wp, P.x, nullptr, 0.0, P.Hd, nullptr, P.y);
+  else {
+    ++seq;
+    spmv_pass(P, wp, P.x, nullptr, 0.0, P.Hd, nullptr, P.y, my_y + (size_t)(seq & 1u) * 3 * P.N);
+    exchange_finish(P, grid, seq, P.x, nullptr, 0.0, P.Hd, nullptr, P.y);
+  }
   if (gtid == 0) {
+    P.sc->xseq = (int)seq;
     P.sc->rz = rz; P.sc->rr = rr; P.sc->beta = beta;
     P.sc->pcg_iter = iter; P.sc->pcg_done = 1; P.sc->pcg_breakdown = breakdown;
   }
@@ -1445,6 +1519,10 @@ struct gsfm_ra_solver {
   int64_t launches = 0;
   bool cooperative = true;  // persistent PCG kernel available
   ncclx::Comm comm = nullptr;  // edge-sharded exchange (world > 1)
+  // fused exchange: one cudaMalloc'ed block per rank {double y[2][3N]; unsigned flag;}, every peer's block mapped here
+  double* xchg = nullptr;
+  void* peer_base[kMaxPeers] = {};
+  bool peers_connected = false;
 
   // structure
   DevBuf<uint32_t> he_col, he_row, iso;
@@ -1485,6 +1563,8 @@ struct gsfm_ra_solver {
 
   ~gsfm_ra_solver() {
     if (comm && ncclx::api()) ncclx::api()->CommDestroy(comm);
+    for (int r = 0; r < kMaxPeers; ++r) if (peer_base[r] && r != rank) cudaIpcCloseMemHandle(peer_base[r]);
+    if (xchg) cudaFree(xchg);
     if (h_sc) cudaFreeHost(h_sc);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     // the stream itself is destroyed by stream_holder after the buffers have been returned to the pool
@@ -1565,6 +1645,11 @@ struct gsfm_ra_solver {
     P.val = val[b].p; P.Dblk = Dblk.p; P.Minv = Minv.p; P.Hd = Hd_p[b];
     P.x = x.p; P.r = r.p; P.z = z.p; P.p0 = p.p; P.p1 = p1.p; P.y = y.p; P.ypart = ypart.p;
     P.row_cnt = row_cnt.p; P.slotsA = slotsA.p; P.slotsB = slotsB.p; P.slotsC = slotsC.p; P.sc = sc.p; P.prof = prof_buf;
+    P.world = peers_connected ? world : 1; P.rank = rank;
+    for (int r = 0; r < kMaxPeers; ++r) {
+      P.peer_y[r] = (double*)peer_base[r];
+      P.peer_flag[r] = peer_base[r] ? (unsigned*)((double*)peer_base[r] + 6ull * N) : nullptr;
+    }
     return P;
   }
 
@@ -1597,7 +1682,7 @@ struct gsfm_ra_solver {
       RA_TRY(spmv(b, x.p, y.p, Hd_p[b]));
       return 0;
     }
-    if (cooperative && !sharded()) {
+    if (cooperative && (!sharded() || peers_connected)) {
       PcgParams P = pcg_params(b, rtol, max_iter);
       void* args[] = {&P};
       CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_pcg_persistent, dim3(pk2.grid), dim3(kBlock), args, kSpmvSmemBytes, stream));
@@ -1918,6 +2003,7 @@ int iterate(gsfm_ra_solver* s, int max_new_iterations, gsfm_ra_summary* sum) {
     RA_TRY(s->fetch_scalars());
     s->ms_linear += s->elapsed(s->ev[0], s->ev[2]);
     s->ms_assemble += s->elapsed(s->ev[2], s->ev[3]);
+    if (s->h_sc->bad == 2) { set_error("multi-GPU exchange timed out: a peer rank did not reach the same CG step"); s->termination = GSFM_RA_TERM_FAILURE; return GSFM_RA_ERR_CUDA; }
     const bool breakdown = s->h_sc->pcg_breakdown != 0;
     const int lin_it = s->h_sc->pcg_iter;
     const double lin_res = (s->h_sc->bb > 0.0) ? std::sqrt(s->h_sc->rr / s->h_sc->bb) : 0.0;
@@ -2113,6 +2199,35 @@ int gsfm_ra_solver_comm_init(gsfm_ra_solver* s, const uint8_t* id) {
   ncclx::UniqueId u;
   std::memcpy(u.internal, id, ncclx::kUniqueIdBytes);
   NCCL_TRY(ncclx::api()->CommInitRank(&s->comm, s->world, u, s->rank));
+  return 0;
+}
+int gsfm_ra_solver_ipc_export(gsfm_ra_solver* s, uint8_t* handle) {
+  if (!s || !handle) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(s->device));
+  if (!s->xchg) {
+    const size_t bytes = (6ull * s->N + 16) * sizeof(double);
+    CUDA_TRY(cudaMalloc(&s->xchg, bytes));  // plain cudaMalloc: IPC handles cannot be taken from the async pool
+    CUDA_TRY(cudaMemset(s->xchg, 0, bytes));
+  }
+  std::memset(handle, 0, GSFM_RA_IPC_HANDLE_BYTES);
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, s->xchg));
+  static_assert(sizeof(h) <= GSFM_RA_IPC_HANDLE_BYTES, "handle size");
+  std::memcpy(handle, &h, sizeof(h));
+  return 0;
+}
+int gsfm_ra_solver_ipc_import(gsfm_ra_solver* s, const uint8_t* handles) {
+  if (!s || !handles) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
+  if (s->world > kMaxPeers) { set_error("at most %d ranks", kMaxPeers); return GSFM_RA_ERR_UNSUPPORTED; }
+  if (!s->xchg) { set_error("call gsfm_ra_solver_ipc_export first"); return GSFM_RA_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(s->device));
+  for (int r = 0; r < s->world; ++r) {
+    if (r == s->rank) { s->peer_base[r] = s->xchg; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + (size_t)r * GSFM_RA_IPC_HANDLE_BYTES, sizeof(h));
+    CUDA_TRY(cudaIpcOpenMemHandle(&s->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  s->peers_connected = true;
   return 0;
 }
 int gsfm_ra_solver_edge_range(const gsfm_ra_solver* s, uint64_t* e0, uint64_t* e1) {

@@ -121,7 +121,7 @@ class Solver:
             capi.check(capi.lib().gsfm_ra_solver_create_sharded(C.byref(prob.c), C.byref(options), rank, world_size,
                                                                 C.byref(self._h)))
 
-    def connect(self, dist):
+    def connect(self, dist, fused=None):
         """Join the ranks of a sharded solver: rank 0 makes the NCCL id, torch.distributed (`dist`, already
         initialised by the host framework) broadcasts it, every rank joins.  Collective."""
         import torch
@@ -134,6 +134,22 @@ class Solver:
         dist.broadcast(t, src=0)
         ident = np.ascontiguousarray(t.cpu().numpy())
         capi.check(capi.lib().gsfm_ra_solver_comm_init(self._h, capi.ptr(ident, C.c_uint8)))
+        if fused is None:
+            import os
+            fused = os.environ.get("GSFM_RA_EXCHANGE", "fused") != "nccl"
+        if fused:
+            # fused exchange: all-gather the CUDA IPC handles of the per-rank exchange blocks
+            world = dist.get_world_size()
+            mine = np.zeros(capi.IPC_HANDLE_BYTES, np.uint8)
+            capi.check(capi.lib().gsfm_ra_solver_ipc_export(self._h, capi.ptr(mine, C.c_uint8)))
+            tm = torch.from_numpy(mine)
+            if dist.get_backend() == "nccl":
+                tm = tm.cuda()
+            parts = [torch.empty_like(tm) for _ in range(world)]
+            dist.all_gather(parts, tm)
+            allh = np.ascontiguousarray(torch.stack(parts).cpu().numpy())
+            capi.check(capi.lib().gsfm_ra_solver_ipc_import(self._h, capi.ptr(allh, C.c_uint8)))
+            dist.barrier()
 
     def edge_range(self):
         a, b = C.c_uint64(), C.c_uint64()

@@ -220,6 +220,13 @@ int gsfm_ra_solver_iterate(gsfm_ra_solver* solver, int32_t num_iterations, gsfm_
 #define GSFM_RA_COMM_ID_BYTES 128
 int gsfm_ra_comm_unique_id(uint8_t* id /*[GSFM_RA_COMM_ID_BYTES]*/);
 int gsfm_ra_solver_comm_init(gsfm_ra_solver* solver, const uint8_t* id /*[GSFM_RA_COMM_ID_BYTES]*/);
+/* Fused exchange (optional, after comm_init): the per-CG-step reduction then runs INSIDE the persistent PCG
+ * kernel over peer memory (CUDA IPC + NVLink loads, system-scope flags) instead of as an NCCL call between
+ * kernels.  Each rank exports one opaque handle; the host framework all-gathers them; every rank imports all.
+ * Without it the sharded solver uses ncclAllReduce per CG step.                                           */
+#define GSFM_RA_IPC_HANDLE_BYTES 128
+int gsfm_ra_solver_ipc_export(gsfm_ra_solver* solver, uint8_t* handle /*[GSFM_RA_IPC_HANDLE_BYTES]*/);
+int gsfm_ra_solver_ipc_import(gsfm_ra_solver* solver, const uint8_t* handles /*[world][GSFM_RA_IPC_HANDLE_BYTES]*/);
 /* Edge range of the caller's list owned by this rank. */
 int gsfm_ra_solver_edge_range(const gsfm_ra_solver* solver, uint64_t* edge_begin, uint64_t* edge_end);
 

@@ -19,12 +19,15 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     out = {}
-    for name, kw, etype, loss in [
+    cases = [
         ("aa_cauchy", dict(num_views=400, num_edges=12000, seed=3, noise_deg=1.0, outlier_fraction=0.1), capi.ANGLE_AXIS,
          capi.Loss.make(capi.LOSS_CAUCHY, 0.05)),
         ("cov_softl1", dict(num_views=150, num_edges=3000, seed=5, outlier_fraction=0.05, covariance=True), capi.ANGLE_AXIS_COVARIANCE,
          capi.Loss.make(capi.LOSS_SOFTLONE, 1.0)),
-    ]:
+    ]
+    # both exchange modes: fused (peer memory inside the persistent PCG kernel) and ncclAllReduce between kernels
+    for (name, kw, etype, loss), fused in [(c, f) for c in cases for f in (True, False)]:
+        name = f"{name}_{'fused' if fused else 'nccl'}"
         g = vg.synthetic_pose_graph(**kw)
         prob = S.make_problem(g, etype)
         o = capi.default_options_py()
@@ -33,7 +36,7 @@ def main():
         o.pcg_max_iterations = 2000
         o.device = local
         sh = S.Solver(prob, o, rank=rank, world_size=world)
-        sh.connect(dist)
+        sh.connect(dist, fused=fused)
         e0, e1 = sh.edge_range()
         assert (e0, e1) == (g.num_edges * rank // world, g.num_edges * (rank + 1) // world)
         sh.set_rotations(g.omega_init)
