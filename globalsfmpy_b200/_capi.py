@@ -84,7 +84,8 @@ class Summary(C.Structure):
                 ("initial_cost", C.c_double), ("final_cost", C.c_double), ("ms_setup", C.c_double),
                 ("ms_assemble", C.c_double), ("ms_linear", C.c_double), ("ms_cost", C.c_double),
                 ("ms_total", C.c_double), ("kernel_launches", C.c_int64), ("trace", C.POINTER(Iteration)),
-                ("trace_capacity", C.c_int32), ("trace_size", C.c_int32)]
+                ("trace_capacity", C.c_int32), ("trace_size", C.c_int32), ("outer_iterations", C.c_int32), ("reserved", C.c_int32),
+                ("last_weight_change", C.c_double)]
 
 
 def default_options_py():
@@ -167,6 +168,7 @@ def declare(lib, oracle=False):
         lib.ra_oracle_assemble.argtypes = [pp, lp, _dp, _dp, _dp, _dp, _u32p, _u32p, _dp, C.c_int]
         lib.ra_oracle_cost.argtypes = [pp, lp, _dp, _dp, C.c_int]
         lib.ra_oracle_solve.argtypes = [pp, op, _dp, sp, cb, C.c_void_p]
+        lib.ra_oracle_solve_sigma_consensus.argtypes = [pp, op, C.c_int32, C.c_double, _dp, sp, _dp]
         lib.ra_oracle_filter_view_pairs.argtypes = [pp, _dp, C.c_double, _u8p, _dp]
         lib.loss_cb_type = cb
         return lib
@@ -177,6 +179,7 @@ def declare(lib, oracle=False):
     lib.gsfm_ra_default_options.argtypes = [op]
     lib.gsfm_ra_default_options.restype = None
     lib.gsfm_ra_solve.argtypes = [pp, op, _dp, sp]
+    lib.gsfm_ra_solve_sigma_consensus.argtypes = [pp, op, C.c_int32, C.c_double, _dp, sp]
     lib.gsfm_ra_solver_create.argtypes = [pp, op, C.POINTER(vp)]
     lib.gsfm_ra_solver_create_sharded.argtypes = [pp, op, C.c_int32, C.c_int32, C.POINTER(vp)]
     lib.gsfm_ra_solver_destroy.argtypes = [vp]
@@ -207,7 +210,7 @@ def declare(lib, oracle=False):
 # every symbol include/gsfm_ra.h declares (checked by the CPU test-suite)
 EXPORTED_SYMBOLS = [
     "gsfm_ra_abi_version", "gsfm_ra_last_error", "gsfm_ra_device_count", "gsfm_ra_default_options",
-    "gsfm_ra_solve", "gsfm_ra_solver_create", "gsfm_ra_solver_create_sharded", "gsfm_ra_solver_destroy",
+    "gsfm_ra_solve", "gsfm_ra_solve_sigma_consensus", "gsfm_ra_solver_create", "gsfm_ra_solver_create_sharded", "gsfm_ra_solver_destroy",
     "gsfm_ra_solver_set_rotations", "gsfm_ra_solver_get_rotations", "gsfm_ra_solver_reset",
     "gsfm_ra_solver_iterate", "gsfm_ra_comm_unique_id", "gsfm_ra_solver_comm_init",
     "gsfm_ra_solver_ipc_export", "gsfm_ra_solver_ipc_import", "gsfm_ra_solver_edge_range", "gsfm_ra_solver_cuda_stream", "gsfm_ra_solver_time_kernels", "gsfm_ra_eval_edges", "gsfm_ra_whiten", "gsfm_ra_assemble", "gsfm_ra_cost",

@@ -440,7 +440,20 @@ class GlobalReconstructionEstimator:
                       self.options.num_threads, self.solver_options)
 
     def EstimateGlobalRotationsWithSigmaConsensus(self, loss_func, iters_num, sigma_max):
-        raise NotImplementedError("EstimateRotationsWithSigmaConsensus (rotation_estimator.cpp:314-457) is not implemented yet")
+        """EstimateGlobalRotationsSigmaConsensus -> EstimateRotationsWithSigmaConsensus (rotation_estimator.cpp:314-457)."""
+        self.OrientationsFromMaximumSpanningTree()
+        edges = self.view_graph_.GetAllEdges()
+        if len(self.orientations) == 0 or len(edges) == 0:
+            return False
+        ids, ei, ej, wij, _, omega = _flatten(edges, self.orientations, None, 4)
+        prob = _capi.ProblemArrays(len(ids), ei, ej, wij, error_type=4)
+        o = self.solver_options or _capi.default_options_py()
+        o.loss = loss_to_struct(loss_func)
+        omega, summary = _solver.solve_sigma_consensus(prob, o, omega, int(iters_num), float(sigma_max))
+        for k, v in enumerate(ids.tolist()):
+            self.orientations[int(v)] = omega[k].copy()
+        _solve.last_summary = summary
+        return True
 
     def FilterRotations(self):
         """FilterViewPairsFromOrientation with options.rotation_filtering_max_difference_degrees, on the device."""

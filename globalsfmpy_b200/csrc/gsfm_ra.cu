@@ -1292,6 +1292,37 @@ __global__ void k_node_apply(uint32_t N, const double* __restrict__ node_JL, con
   }
 }
 
+// Sigma-consensus weights (rotation_estimator.cpp:378-418): w = (C3*2/sigma)(Gamma_tab[round(1000 r^2/(2 sigma^2))] - Gamma_k)
+// from the angular residual at the current rotations; C++ round() = half away from zero; the table is exp(-x/1000).
+// Also reduces sum |w - w_prev| (deterministic grid sum) into sc->dg.
+__global__ void k_sigma_weights(uint64_t E, const uint32_t* __restrict__ ei, const uint32_t* __restrict__ ej, const double* __restrict__ omega_ij,
+                                const double* __restrict__ node_q, double one_over_sigma, double sq_sigma_max_2, double gamma_k,
+                                double weight_zero, double table_size, double* __restrict__ w, double* slots, unsigned* counter,
+                                DevScalars* sc) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double v[1] = {0.0};
+  if (k < E) {
+    const double4 a = reinterpret_cast<const double4*>(node_q)[ei[k]], b = reinterpret_cast<const double4*>(node_q)[ej[k]];
+    const Q4 qi{a.x, a.y, a.z, a.w}, qj{b.x, b.y, b.z, b.w};
+    const Q4 qm = aa_to_quat(omega_ij[3 * k], omega_ij[3 * k + 1], omega_ij[3 * k + 2]);
+    const Q4 qE = qmul(qmul(qj, qconj(qi)), qconj(qm));
+    double e[3], t2, c;
+    quat_log(qE, e, &t2, &c);
+    const double residual = sqrt(t2);
+    double wk;
+    if (residual < DBL_EPSILON) wk = weight_zero;
+    else {
+      double x = round(1000.0 * (residual * residual) / sq_sigma_max_2);
+      if (table_size < x) x = table_size;
+      wk = one_over_sigma * (exp(-x / 1000.0) - gamma_k);
+    }
+    v[0] = fabs(wk - w[k]);
+    w[k] = wk;
+  }
+  double tot[1];
+  if (grid_sum<1>(v, slots, counter, tot) && threadIdx.x == 0) sc->dg = tot[0];
+}
+
 // The step after the path: FilterViewPairsFromOrientation (T/sfm/filter_view_pairs_from_orientation.cc:55-118).
 __global__ void k_filter_pairs(uint64_t E, const uint32_t* __restrict__ ei, const uint32_t* __restrict__ ej, const double* __restrict__ omega_ij,
                                const double* __restrict__ node_q, double sq_threshold, uint8_t* keep, double* angle) {
@@ -1525,7 +1556,7 @@ struct gsfm_ra_solver {
   bool peers_connected = false;
 
   // structure
-  DevBuf<uint32_t> he_col, he_row, iso;
+  DevBuf<uint32_t> he_col, he_row, he_edge, iso;
   uint32_t n_iso = 0;
   Partition pk1, pk2;  // K1 (edge kernel) and K2 (SpMV / PCG) partitions
   // per half-edge constants, planar
@@ -1818,7 +1849,7 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   // ---- half-edges sorted by (row, col): keys -> radix sort -> unpack ----------------------------
   DevBuf<int> d_err;
   DevBuf<uint64_t> keys_a, keys_b;
-  DevBuf<uint32_t> vals_a, vals_b, he_edge, rowptr, flags_ne, flags_iso, nz_rank, iso_rank;
+  DevBuf<uint32_t> vals_a, vals_b, rowptr, flags_ne, flags_iso, nz_rank, iso_rank;
   RA_TRY(d_err.alloc(4));
   CUDA_TRY(cudaMemsetAsync(d_err.p, 0, 4 * sizeof(int), st));
   RA_TRY(keys_a.alloc(H)); RA_TRY(keys_b.alloc(H)); RA_TRY(vals_a.alloc(H)); RA_TRY(vals_b.alloc(H));
@@ -1832,8 +1863,8 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
     RA_TRY(tmp.alloc(bytes + 16));
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, keys_a.p, keys_b.p, vals_a.p, vals_b.p, (int)H, 0, bits, st));
   }
-  RA_TRY(s->he_col.alloc(H)); RA_TRY(s->he_row.alloc(H)); RA_TRY(he_edge.alloc(H));
-  k_unpack_keys<<<grid_for(H), kBlock, 0, st>>>(H, N, keys_b.p, vals_b.p, s->he_row.p, s->he_col.p, he_edge.p, d_err.p);
+  RA_TRY(s->he_col.alloc(H)); RA_TRY(s->he_row.alloc(H)); RA_TRY(s->he_edge.alloc(H));
+  k_unpack_keys<<<grid_for(H), kBlock, 0, st>>>(H, N, keys_b.p, vals_b.p, s->he_row.p, s->he_col.p, s->he_edge.p, d_err.p);
   RA_TRY(rowptr.alloc(N + 2)); RA_TRY(flags_ne.alloc(N + 2)); RA_TRY(flags_iso.alloc(N + 2)); RA_TRY(nz_rank.alloc(N + 2)); RA_TRY(iso_rank.alloc(N + 2));
   k_rowptr<<<grid_for(N + 1), kBlock, 0, st>>>(N, H, keys_b.p, rowptr.p);
   k_row_flags<<<grid_for(N + 1), kBlock, 0, st>>>(N, rowptr.p, flags_ne.p, flags_iso.p);
@@ -1875,7 +1906,7 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   // ---- per half-edge constants (K0) and the solver's working set ---------------------------------
   RA_TRY(s->qij.alloc(4 * H));
   RA_TRY(s->U.alloc(6 * H));
-  k_setup_halfedges<<<grid_for(H), kBlock, 0, st>>>(H, he_edge.p, s->d_omega_ij.p, s->d_cov6.p, s->d_weight.p, prob->error_type, s->qij.p, s->U.p);
+  k_setup_halfedges<<<grid_for(H), kBlock, 0, st>>>(H, s->he_edge.p, s->d_omega_ij.p, s->d_cov6.p, s->d_weight.p, prob->error_type, s->qij.p, s->U.p);
   s->launches += 1;
   const size_t nrec = (size_t)((H + 31) / 32);
   for (int b = 0; b < 2; ++b) {
@@ -1903,7 +1934,7 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   CUDA_TRY(cudaMemsetAsync(s->row_cnt.p, 0, (size_t)N * sizeof(unsigned), st));
   RA_TRY(s->Dblk.alloc(6ull * N));
   RA_TRY(s->Minv.alloc(6ull * N));
-  RA_TRY(s->slots.alloc((size_t)std::max<unsigned>(grid_for(3ull * N), 64) * 4 + 64));
+  RA_TRY(s->slots.alloc((size_t)std::max<unsigned>(std::max(grid_for(3ull * N), grid_for(E)), 64) * 4 + 64));
   RA_TRY(s->counter.alloc(4));
   RA_TRY(s->sc.alloc(1));
   CUDA_TRY(cudaMemsetAsync(s->counter.p, 0, 4 * sizeof(unsigned), st));
@@ -2298,6 +2329,62 @@ int gsfm_ra_solve(const gsfm_ra_problem* problem, const gsfm_ra_options* options
   if (rc != 0 && rc != GSFM_RA_ERR_NUMERIC) return rc;
   RA_TRY(gsfm_ra_solver_get_rotations(t.s, omega_inout));
   if (summary) summary->ms_total = now_ms() - t0;
+  return rc;
+}
+
+int gsfm_ra_solve_sigma_consensus(const gsfm_ra_problem* problem, const gsfm_ra_options* options, int32_t iters_num, double sigma_max,
+                                  double* omega_inout, gsfm_ra_summary* summary) {
+  if (!omega_inout || !options || !problem) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
+  if (problem->error_type != GSFM_RA_ANGLE_AXIS) { set_error("sigma consensus runs on GSFM_RA_ANGLE_AXIS (PairwiseRotationError with a scalar weight)"); return GSFM_RA_ERR_INVALID; }
+  if (!(sigma_max > 0.0) || iters_num < 1) { set_error("sigma_max must be > 0 and iters_num >= 1"); return GSFM_RA_ERR_INVALID; }
+  const double t0 = now_ms();
+  gsfm_ra_problem q = *problem;
+  q.edge_weight = nullptr;
+  TempSolver t;
+  RA_TRY(build_solver(&q, options, 0, 1, &t.s));
+  gsfm_ra_solver* s = t.s;
+  RA_TRY(gsfm_ra_solver_set_rotations(s, omega_inout));
+  const uint64_t E = s->E, H = s->H;
+  {
+    AllocScope scope(s->stream);
+    RA_TRY(s->d_weight.alloc(E));
+  }
+  CUDA_TRY(cudaMemsetAsync(s->d_weight.p, 0, E * sizeof(double), s->stream));  // last_weights start at 0
+  // include/gamma_values.cpp:6-11 (nu = 3)
+  const double C3 = 4.029720004054876e-01, gamma_k = 3.439485560754856e-03, table_size = 36843.0;
+  const double sq2 = sigma_max * sigma_max * 2.0, one_over_sigma = C3 * 2.0 / sigma_max, weight_zero = one_over_sigma * (1.0 - gamma_k);
+  gsfm_ra_summary total;
+  std::memset(&total, 0, sizeof(total));
+  if (summary) { total.trace = summary->trace; total.trace_capacity = summary->trace_capacity; }
+  int rc = 0;
+  for (int it = 0; it < iters_num; ++it) {
+    const int b = s->cur;
+    k_node_prep<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->omega[b].p, s->node_q[b].p, s->node_JL[b].p, s->slots.p, s->counter.p, s->sc.p);
+    k_sigma_weights<<<grid_for(E), kBlock, 0, s->stream>>>(E, s->d_ei.p, s->d_ej.p, s->d_omega_ij.p, s->node_q[b].p, one_over_sigma, sq2, gamma_k,
+                                                           weight_zero, table_size, s->d_weight.p, s->slots.p, s->counter.p, s->sc.p);
+    k_setup_halfedges<<<grid_for(H), kBlock, 0, s->stream>>>(H, s->he_edge.p, s->d_omega_ij.p, s->d_cov6.p, s->d_weight.p, s->error_type, s->qij.p, s->U.p);
+    s->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    RA_TRY(s->fetch_scalars());
+    const double diff = s->h_sc->dg / (double)E;
+    reset_trust_region(s);
+    gsfm_ra_summary s1;
+    std::memset(&s1, 0, sizeof(s1));
+    rc = gsfm_ra_solver_iterate(s, options->max_num_iterations + 1, &s1);
+    if (rc != 0 && rc != GSFM_RA_ERR_NUMERIC) return rc;
+    if (it == 0) total.initial_cost = s1.initial_cost;
+    total.final_cost = s1.final_cost; total.termination = s1.termination;
+    total.num_iterations += s1.num_iterations; total.num_successful_steps += s1.num_successful_steps;
+    total.num_unsuccessful_steps += s1.num_unsuccessful_steps; total.total_linear_iterations += s1.total_linear_iterations;
+    total.ms_assemble += s1.ms_assemble; total.ms_linear += s1.ms_linear; total.kernel_launches += s1.kernel_launches + 3;
+    total.outer_iterations = it + 1;
+    total.last_weight_change = diff;
+    if (rc != 0 || diff <= 1e-7) break;
+  }
+  RA_TRY(gsfm_ra_solver_get_rotations(s, omega_inout));
+  total.ms_setup = s->ms_setup;
+  total.ms_total = now_ms() - t0;
+  if (summary) *summary = total;
   return rc;
 }
 

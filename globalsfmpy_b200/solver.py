@@ -108,6 +108,15 @@ def solve(prob, options, omega0, trace_capacity=0):
     return omega, s, [trace[k] for k in range(s.trace_size)]
 
 
+def solve_sigma_consensus(prob, options, omega0, iters_num, sigma_max):
+    """gsfm_ra_solve_sigma_consensus (EstimateRotationsWithSigmaConsensus). Returns (omega, summary)."""
+    omega = capi.as_f64(np.array(omega0, dtype=np.float64, copy=True), (prob.num_views, 3))
+    s, _ = _summary(0)
+    capi.check(capi.lib().gsfm_ra_solve_sigma_consensus(C.byref(prob.c), C.byref(options), int(iters_num), float(sigma_max),
+                                                        capi.ptr(omega), C.byref(s)))
+    return omega, s
+
+
 class Solver:
     """Resident solver handle (problem stays in HBM across iterations)."""
 

@@ -177,6 +177,10 @@ typedef struct {
   gsfm_ra_iteration* trace;
   int32_t trace_capacity;
   int32_t trace_size;
+  /* sigma-consensus only: outer re-weighting iterations executed and the last mean |w - w_prev| */
+  int32_t outer_iterations;
+  int32_t reserved;
+  double last_weight_change;
 } gsfm_ra_summary;
 
 typedef struct gsfm_ra_solver gsfm_ra_solver; /* opaque, device-resident problem */
@@ -195,6 +199,15 @@ void gsfm_ra_default_options(gsfm_ra_options* options);
  *      caller's unordered_map<ViewId,Vector3d> in place).                      */
 int gsfm_ra_solve(const gsfm_ra_problem* problem, const gsfm_ra_options* options,
                   double* omega_inout, gsfm_ra_summary* summary);
+
+/* ---- sigma-consensus outer loop: replaces EstimateRotationsWithSigmaConsensus
+ *      (rotation_estimator.cpp:314-457).  Up to iters_num times: per edge w = (C3*2/sigma_max) *
+ *      (Gamma_table[round(1000 r^2 / (2 sigma_max^2))] - Gamma_k) from the angular residual r at the current
+ *      rotations (weight_zero below DBL_EPSILON), a full trust-region solve of PairwiseRotationError(omega_ij, w)
+ *      under options->loss, stop once mean |w - w_prev| <= 1e-7 (checked after the solve, as the reference does).
+ *      problem->error_type must be GSFM_RA_ANGLE_AXIS; problem->edge_weight is ignored.                        */
+int gsfm_ra_solve_sigma_consensus(const gsfm_ra_problem* problem, const gsfm_ra_options* options, int32_t iters_num,
+                                  double sigma_max, double* omega_inout, gsfm_ra_summary* summary);
 
 /* ---- resident solver ---------------------------------------------------------*/
 int gsfm_ra_solver_create(const gsfm_ra_problem* problem, const gsfm_ra_options* options,

@@ -891,6 +891,61 @@ int ra_oracle_solve(const gsfm_ra_problem* p, const gsfm_ra_options* o, double* 
   return 0;
 }
 
+/* src/GSfM_nonlinear_rotation_estimator.cpp:314-457.  Per outer iteration: weights from the MAGSAC nu=3 table at the
+ * current angular residuals (C++ round(): half away from zero; the reference's clamp `if (N < x) x = N` then reads
+ * table[N], one past the end -- the closed form continues the table there), a FULL Ceres solve with
+ * PairwiseRotationError(omega_ij, weight) under the caller's loss, stop when mean |w - w_prev| <= 1e-7 (tested
+ * after the solve).                                                                                             */
+int ra_oracle_solve_sigma_consensus(const gsfm_ra_problem* p, const gsfm_ra_options* o, int32_t iters_num, double sigma_max,
+                                    double* omega, gsfm_ra_summary* sum, double* weights_out) {
+  if (!p || !o || !omega) return GSFM_RA_ERR_INVALID;
+  if (p->error_type != GSFM_RA_ANGLE_AXIS) return GSFM_RA_ERR_INVALID;
+  const uint64_t E = p->num_edges;
+  const double squared_sigma_max_2 = sigma_max * sigma_max * 2.0;
+  const double dof_minus_one_per_two = (kMagsac3.nu - 1.0) / 2.0;
+  const double C_times_two_ad_dof = kMagsac3.C * std::pow(2.0, dof_minus_one_per_two);
+  const double one_over_sigma = C_times_two_ad_dof / sigma_max;
+  const double weight_zero = one_over_sigma * (std::tgamma(dof_minus_one_per_two) - kMagsac3.gamma_k);
+  std::vector<double> last(E, 0.0), w(E, 0.0);
+  gsfm_ra_problem q = *p;
+  const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  gsfm_ra_summary total;
+  std::memset(&total, 0, sizeof(total));
+  for (int it = 0; it < iters_num; ++it) {
+    for (uint64_t k = 0; k < E; ++k) {
+      double e[3];
+      EdgeResidual<double>(omega + 3 * (size_t)p->edge_i[k], omega + 3 * (size_t)p->edge_j[k], p->omega_ij + 3 * k, I, e);
+      const double residual = std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+      if (residual < DBL_EPSILON) w[k] = weight_zero;
+      else {
+        double x = std::round(kGammaPrecision * (residual * residual) / squared_sigma_max_2);
+        if ((double)kMagsac3.table_size < x) x = kMagsac3.table_size;
+        w[k] = one_over_sigma * (std::exp(-x / kGammaPrecision) - kMagsac3.gamma_k);
+      }
+    }
+    double diff = 0;
+    for (uint64_t k = 0; k < E; ++k) diff += std::fabs(w[k] - last[k]);
+    diff /= (double)E;
+    std::swap(w, last);  /* `last` now holds the weights of this iteration */
+    q.edge_weight = last.data();
+    gsfm_ra_summary s1;
+    std::memset(&s1, 0, sizeof(s1));
+    const int rc = ra_oracle_solve(&q, o, omega, &s1, nullptr, nullptr);
+    if (rc != 0) return rc;
+    if (it == 0) total.initial_cost = s1.initial_cost;
+    total.final_cost = s1.final_cost; total.termination = s1.termination;
+    total.num_iterations += s1.num_iterations; total.num_successful_steps += s1.num_successful_steps;
+    total.num_unsuccessful_steps += s1.num_unsuccessful_steps; total.total_linear_iterations += s1.total_linear_iterations;
+    total.ms_total += s1.ms_total;
+    total.outer_iterations = it + 1;
+    total.last_weight_change = diff;
+    if (diff <= 1e-7) break;
+  }
+  if (weights_out) std::memcpy(weights_out, last.data(), E * sizeof(double));
+  if (sum) { total.trace = sum->trace; total.trace_capacity = sum->trace_capacity; *sum = total; }
+  return 0;
+}
+
 /* T/sfm/filter_view_pairs_from_orientation.cc:55-118: an edge is kept iff the angle of
  * R_ij^T * (R_j R_i^T) is <= max_degrees.                                               */
 int ra_oracle_filter_view_pairs(const gsfm_ra_problem* p, const double* omega, double max_degrees, uint8_t* keep, double* angle_rad) {

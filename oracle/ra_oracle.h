@@ -63,6 +63,10 @@ int ra_oracle_cost(const gsfm_ra_problem* p, const gsfm_ra_loss* loss, const dou
 int ra_oracle_solve(const gsfm_ra_problem* p, const gsfm_ra_options* options, double* omega_inout,
                     gsfm_ra_summary* summary, ra_oracle_loss_cb loss_cb, void* cb_ctx);
 
+/* EstimateRotationsWithSigmaConsensus (rotation_estimator.cpp:314-457); weights_out [E] = the last weights, may be NULL. */
+int ra_oracle_solve_sigma_consensus(const gsfm_ra_problem* p, const gsfm_ra_options* options, int32_t iters_num, double sigma_max,
+                                    double* omega_inout, gsfm_ra_summary* summary, double* weights_out);
+
 /* FilterViewPairsFromOrientation restatement. */
 int ra_oracle_filter_view_pairs(const gsfm_ra_problem* p, const double* omega, double max_degrees,
                                 uint8_t* keep, double* angle_rad);

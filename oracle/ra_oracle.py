@@ -127,6 +127,16 @@ def solve(prob, options, omega0, trace_capacity=0, loss_callback=None):
     return omega, s, [trace[k] for k in range(s.trace_size)]
 
 
+def solve_sigma_consensus(prob, options, omega0, iters_num, sigma_max):
+    omega = capi.as_f64(np.array(omega0, dtype=np.float64, copy=True), (prob.num_views, 3))
+    s = capi.Summary()
+    w = np.zeros(prob.num_edges)
+    rc = lib().ra_oracle_solve_sigma_consensus(C.byref(prob.c), C.byref(options), int(iters_num), float(sigma_max), _p(omega),
+                                               C.byref(s), _p(w))
+    assert rc == 0, rc
+    return omega, s, w
+
+
 def filter_view_pairs(prob, omega, max_degrees):
     omega = capi.as_f64(omega, (prob.num_views, 3))
     keep = np.zeros(prob.num_edges, np.uint8)

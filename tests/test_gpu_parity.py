@@ -313,6 +313,27 @@ def test_madrid_cauchy_tight(madrid):
     assert sg.final_cost <= so.final_cost * (1 + 1e-9)
 
 
+def test_sigma_consensus_matches_oracle():
+    """EstimateRotationsWithSigmaConsensus (rotation_estimator.cpp:314-457): outer re-weighting loop."""
+    g = vg.synthetic_pose_graph(120, 1500, seed=77, noise_deg=1.0, outlier_fraction=0.15)
+    prob = solver.make_problem(g, capi.ANGLE_AXIS)
+    o = capi.default_options_py()
+    o.loss = capi.Loss.make(capi.LOSS_HUBER, 0.1)
+    o.pcg_rtol = 1e-13
+    o.pcg_max_iterations = 2000
+    og, sg = solver.solve_sigma_consensus(prob, o, g.omega_init, 6, 0.05)
+    o.linear_solver = capi.SOLVER_DENSE_CHOLESKY
+    oo, so, w = orc.solve_sigma_consensus(prob, o, g.omega_init, 6, 0.05)
+    assert sg.outer_iterations == so.outer_iterations == 6
+    assert (w < 0).any() and w.max() > 15.0   # beyond k*sigma the table weight goes slightly negative; inliers ~ 2 C3 / sigma = 16.1
+    assert abs(sg.last_weight_change - so.last_weight_change) <= 1e-6 * max(so.last_weight_change, 1e-12) + 1e-12
+    assert abs(sg.final_cost - so.final_cost) <= 1e-6 * so.final_cost
+    mean, _ = vg.mean_angular_error(oo, og)
+    assert mean < 1e-6, mean
+    _, mx = vg.mean_angular_error(g.omega_gt, og)
+    assert np.degrees(mx) < 3.0
+
+
 def test_resident_solver_stepwise_equals_one_shot():
     g = vg.synthetic_pose_graph(100, 1200, seed=13, noise_deg=1.0, outlier_fraction=0.1)
     prob = solver.make_problem(g, capi.ANGLE_AXIS)
