@@ -253,7 +253,7 @@ __global__ void k_embed_cols(uint64_t H, const uint32_t* __restrict__ he_col, do
 
 // Per view: quaternion + left Jacobian of the current angle-axis estimate; also |omega|^2.
 __global__ void k_node_prep(uint32_t N, const double* __restrict__ omega, double* __restrict__ node_q, double* __restrict__ node_JL,
-                            double* slots, unsigned* counter, DevScalars* sc) {
+                            double* slots, unsigned* counter, DevScalars* sc, int manifold) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   double v[1] = {0.0};
   if (i < N) {
@@ -261,10 +261,15 @@ __global__ void k_node_prep(uint32_t N, const double* __restrict__ omega, double
     const Q4 q = aa_to_quat(wx, wy, wz);
     reinterpret_cast<double4*>(node_q)[i] = make_double4(q.w, q.x, q.y, q.z);
     double J[9];
-    so3_left_jacobian(wx, wy, wz, J);
+    if (manifold) {  // local coordinates of EigenQuaternionParameterization: phi = 2 delta  ->  J = 2 I; |x|^2 = 1 per unit quaternion
+      J[0] = J[4] = J[8] = 2.0; J[1] = J[2] = J[3] = J[5] = J[6] = J[7] = 0.0;
+      v[0] = 1.0;
+    } else {
+      so3_left_jacobian(wx, wy, wz, J);
+      v[0] = wx * wx + wy * wy + wz * wz;
+    }
 #pragma unroll
     for (int t = 0; t < 9; ++t) node_JL[9 * (size_t)i + t] = J[t];
-    v[0] = wx * wx + wy * wy + wz * wz;
   }
   double tot[1];
   if (grid_sum<1>(v, slots, counter, tot) && threadIdx.x == 0) sc->xnorm2 = tot[0];
@@ -279,7 +284,7 @@ __global__ void k_node_prep(uint32_t N, const double* __restrict__ omega, double
 // per task, the warp-reduced diagonal block / gradient / cost partial.
 // kWriteBlocks=false is K1c: cost only (trial point).
 // ------------------------------------------------------------------------------------------
-template <bool kWriteBlocks>
+template <bool kWriteBlocks, int kResidual>
 __global__ void __launch_bounds__(kBlock, 2)
 k_edges(uint32_t num_warps, uint64_t H, const uint32_t* __restrict__ warp_seg_ptr, const uint32_t* __restrict__ task_row,
         const uint32_t* __restrict__ task_begin, const uint32_t* __restrict__ task_len, const uint32_t* __restrict__ he_col,
@@ -309,8 +314,8 @@ k_edges(uint32_t num_warps, uint64_t H, const uint32_t* __restrict__ warp_seg_pt
 #pragma unroll
       for (int k = 0; k < 6; ++k) u[k] = U[(uint64_t)k * H + h];
       EdgeTerms et;
-      if (row_is_j) edge_terms<kWriteBlocks>(qb, qa, qm, u, loss, et);
-      else edge_terms<kWriteBlocks>(qa, qb, qm, u, loss, et);
+      if (row_is_j) edge_terms<kWriteBlocks, kResidual>(qb, qa, qm, u, loss, et);
+      else edge_terms<kWriteBlocks, kResidual>(qa, qb, qm, u, loss, et);
       if (!row_is_j) acc[9] += 0.5 * et.rho[0];  // each edge's cost is counted once, in its i row
       if (kWriteBlocks) {
         const double* W = et.W;
@@ -1170,7 +1175,7 @@ __global__ void __launch_bounds__(kBlock) k_dense_cholesky_solve(uint32_t n, uin
 // reduce delta.g (= xt.gt), delta.H.delta (= xt.Hx), |delta|^2.
 __global__ void k_apply_step(uint32_t N, const double* __restrict__ node_JL, const double* __restrict__ xt, const double* __restrict__ Hx,
                              const double* __restrict__ gt, const double* __restrict__ omega, double* __restrict__ cand,
-                             double* __restrict__ delta_out, double* slots, unsigned* counter, DevScalars* sc) {
+                             double* __restrict__ delta_out, double* slots, unsigned* counter, DevScalars* sc, int manifold) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   double v[4] = {0.0, 0.0, 0.0, 0.0};
   if (i < N) {
@@ -1179,6 +1184,20 @@ __global__ void k_apply_step(uint32_t N, const double* __restrict__ node_JL, con
     for (int k = 0; k < 9; ++k) J[k] = node_JL[9 * (size_t)i + k];
     inv3(J, Ji);
     const double t0 = xt[3 * (size_t)i], t1 = xt[3 * (size_t)i + 1], t2 = xt[3 * (size_t)i + 2];
+    if (manifold) {
+      // x (+) delta = [sin|d| d/|d|, cos|d|] (x) x with d = xt / 2, i.e. R <- Exp(xt) R; the state stays an angle-axis vector
+      // (principal branch of the product quaternion).  |step| in the ambient quaternion space = 2 sin(|d| / 2) per view.
+      const Q4 qd = aa_to_quat(t0, t1, t2);
+      const Q4 qo = aa_to_quat(omega[3 * (size_t)i], omega[3 * (size_t)i + 1], omega[3 * (size_t)i + 2]);
+      double e[3], th2, cc;
+      quat_log(qmul(qd, qo), e, &th2, &cc);
+      const double dn = 0.5 * sqrt(t0 * t0 + t1 * t1 + t2 * t2);
+      const double sh = sin(0.5 * dn);
+      if (cand) { cand[3 * (size_t)i] = e[0]; cand[3 * (size_t)i + 1] = e[1]; cand[3 * (size_t)i + 2] = e[2]; }
+      if (delta_out) { delta_out[3 * (size_t)i] = 0.5 * t0; delta_out[3 * (size_t)i + 1] = 0.5 * t1; delta_out[3 * (size_t)i + 2] = 0.5 * t2; }
+      v[2] = 4.0 * sh * sh;
+      if (!isfinite(dn)) v[3] = 1.0;
+    } else
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const double d = Ji[3 * c] * t0 + Ji[3 * c + 1] * t1 + Ji[3 * c + 2] * t2;
@@ -1213,7 +1232,8 @@ __global__ void k_eval_edges(uint64_t E, const uint32_t* __restrict__ ei, const 
   if (cov6) for (int t = 0; t < 6; ++t) c6[t] = cov6[6 * k + t];
   whiten(error_type, c6, weight ? weight[k] : 1.0, u);
   EdgeTerms et;
-  edge_terms<true>(qi, qj, qm, u, loss, et);
+  if (error_type == 2) edge_terms<true, 1>(qi, qj, qm, u, loss, et);
+  else edge_terms<true, 0>(qi, qj, qm, u, loss, et);
   if (r) for (int t = 0; t < 3; ++t) r[3 * k + t] = et.r[t];
   if (rho) for (int t = 0; t < 3; ++t) rho[3 * k + t] = et.rho[t];
   if (Jj) {  // d r / d omega_j = A Jl(omega_j)
@@ -1385,7 +1405,7 @@ int check_problem(const gsfm_ra_problem* p) {
   if (p->num_views >= kSideBit) { set_error("too many views"); return GSFM_RA_ERR_INVALID; }
   if (p->num_edges >= (1ull << 31)) { set_error("too many edges for 32-bit half-edge offsets"); return GSFM_RA_ERR_UNSUPPORTED; }
   if (p->error_type < GSFM_RA_QUATERNION_NORM || p->error_type > GSFM_RA_ANGLE_AXIS_COVNORM) { set_error("unknown error_type %d", p->error_type); return GSFM_RA_ERR_INVALID; }
-  if (p->error_type < GSFM_RA_ANGLE_AXIS_COVARIANCE) { set_error("quaternion / matrix residual types are not implemented (angle-axis types 3..8 only)"); return GSFM_RA_ERR_UNSUPPORTED; }
+  if (p->error_type < GSFM_RA_QUATERNION_COSINE) { set_error("QUATERNION_NORM / ROTATION_MAT_FNORM are not implemented (QUATERNION_COSINE and the angle-axis types 3..8 are)"); return GSFM_RA_ERR_UNSUPPORTED; }
   if (type_needs_cov(p->error_type) && !p->cov6) { set_error("error_type %d needs cov6", p->error_type); return GSFM_RA_ERR_INVALID; }
   return 0;
 }
@@ -1602,6 +1622,8 @@ struct gsfm_ra_solver {
   }
 
   bool sharded() const { return world > 1; }
+  // QUATERNION_COSINE: parameters live on the manifold (left-multiplicative update, local coordinates delta = phi/2)
+  bool manifold() const { return error_type == GSFM_RA_QUATERNION_COSINE; }
   int allreduce(double* buf, size_t count) {
     if (!comm) { set_error("sharded solver used before gsfm_ra_solver_comm_init"); return GSFM_RA_ERR_INVALID; }
     NCCL_TRY(ncclx::api()->AllReduce(buf, buf, count, ncclx::kFloat64, ncclx::kSum, comm, stream));
@@ -1615,12 +1637,12 @@ struct gsfm_ra_solver {
   }
 
   void launch_edges(int b, bool jacobian, double* val_out) {
-    if (jacobian)
-      k_edges<true><<<pk1.grid, kBlock, 0, stream>>>(pk1.num_warps, H, pk1.warp_seg_ptr.p, pk1.seg_row.p, pk1.seg_begin.p, pk1.seg_len.p, he_col.p,
-                                                     qij.p, U.p, node_q[b].p, loss, val_out, part.p);
-    else
-      k_edges<false><<<pk1.grid, kBlock, 0, stream>>>(pk1.num_warps, H, pk1.warp_seg_ptr.p, pk1.seg_row.p, pk1.seg_begin.p, pk1.seg_len.p, he_col.p,
-                                                      qij.p, U.p, node_q[b].p, loss, nullptr, part.p);
+#define GSFM_LAUNCH_EDGES(JAC, RES, VAL)                                                                                                  \
+  k_edges<JAC, RES><<<pk1.grid, kBlock, 0, stream>>>(pk1.num_warps, H, pk1.warp_seg_ptr.p, pk1.seg_row.p, pk1.seg_begin.p, pk1.seg_len.p, he_col.p, \
+                                                     qij.p, U.p, node_q[b].p, loss, VAL, part.p)
+    if (manifold()) { if (jacobian) GSFM_LAUNCH_EDGES(true, 1, val_out); else GSFM_LAUNCH_EDGES(false, 1, nullptr); }
+    else { if (jacobian) GSFM_LAUNCH_EDGES(true, 0, val_out); else GSFM_LAUNCH_EDGES(false, 0, nullptr); }
+#undef GSFM_LAUNCH_EDGES
   }
   void launch_spmv(int b, const double* xin, int check_done) {
     k_spmv<<<pk2.grid, kBlock, kSpmvSmemBytes, stream>>>(pk2.num_warps, H, pk2.span, pk2.warp_seg_ptr.p, pk2.seg_begin.p, pk2.seg_len.p, val[b].p,
@@ -1630,7 +1652,7 @@ struct gsfm_ra_solver {
   // ---- evaluation at omega[b]: node prep, K1 (or K1c), node finalize -------------------------
   int evaluate(int b, bool jacobian) {
     CUDA_TRY(cudaMemsetAsync(&sc.p->gmax, 0, sizeof(double), stream));
-    k_node_prep<<<grid_for(N), kBlock, 0, stream>>>(N, omega[b].p, node_q[b].p, node_JL[b].p, slots.p, counter.p, sc.p);
+    k_node_prep<<<grid_for(N), kBlock, 0, stream>>>(N, omega[b].p, node_q[b].p, node_JL[b].p, slots.p, counter.p, sc.p, manifold() ? 1 : 0);
     launch_edges(b, jacobian, val[b].p);
     double* tail = lin[b].p + 9ull * N;
     const int co = jacobian ? 0 : 1;
@@ -1769,7 +1791,7 @@ int device_info(int device, DeviceInfo** out) {
     CUDA_TRY(cudaDeviceGetAttribute(&d.coop, cudaDevAttrCooperativeLaunch, device));
     CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpmvSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpmvSmemBytes));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k1, k_edges<true>, kBlock, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k1, k_edges<true, 0>, kBlock, 0));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2, k_pcg_persistent, kBlock, kSpmvSmemBytes));
     // keep freed blocks in the pool: the next solver reuses them
     cudaMemPool_t pool;
@@ -2026,7 +2048,7 @@ int iterate(gsfm_ra_solver* s, int max_new_iterations, gsfm_ra_summary* sum) {
     CUDA_TRY(cudaMemsetAsync(&s->sc.p->bad, 0, sizeof(int), s->stream));
     RA_TRY(s->pcg_enqueue(b, s->radius, nullptr, nullptr, o.pcg_rtol, o.pcg_max_iterations));
     k_apply_step<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[b].p, s->x.p, s->y.p, s->gt_p[b], s->omega[b].p, s->omega[c].p, s->delta.p,
-                                                        s->slots.p, s->counter.p, s->sc.p);
+                                                        s->slots.p, s->counter.p, s->sc.p, s->manifold() ? 1 : 0);
     s->launches += 1;
     CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
     RA_TRY(s->evaluate(c, true));
@@ -2359,7 +2381,7 @@ int gsfm_ra_solve_sigma_consensus(const gsfm_ra_problem* problem, const gsfm_ra_
   int rc = 0;
   for (int it = 0; it < iters_num; ++it) {
     const int b = s->cur;
-    k_node_prep<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->omega[b].p, s->node_q[b].p, s->node_JL[b].p, s->slots.p, s->counter.p, s->sc.p);
+    k_node_prep<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->omega[b].p, s->node_q[b].p, s->node_JL[b].p, s->slots.p, s->counter.p, s->sc.p, 0);
     k_sigma_weights<<<grid_for(E), kBlock, 0, s->stream>>>(E, s->d_ei.p, s->d_ej.p, s->d_omega_ij.p, s->node_q[b].p, one_over_sigma, sq2, gamma_k,
                                                            weight_zero, table_size, s->d_weight.p, s->slots.p, s->counter.p, s->sc.p);
     k_setup_halfedges<<<grid_for(H), kBlock, 0, s->stream>>>(H, s->he_edge.p, s->d_omega_ij.p, s->d_cov6.p, s->d_weight.p, s->error_type, s->qij.p, s->U.p);
@@ -2400,7 +2422,7 @@ int gsfm_ra_eval_edges(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss,
   if (jac_i) RA_TRY(dji.alloc(9 * E));
   if (jac_j) RA_TRY(djj.alloc(9 * E));
   if (rho) RA_TRY(drho.alloc(3 * E));
-  k_node_prep<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->omega[0].p, s->node_q[0].p, s->node_JL[0].p, s->slots.p, s->counter.p, s->sc.p);
+  k_node_prep<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->omega[0].p, s->node_q[0].p, s->node_JL[0].p, s->slots.p, s->counter.p, s->sc.p, s->manifold() ? 1 : 0);
   k_eval_edges<<<grid_for(E), kBlock, 0, s->stream>>>(E, s->d_ei.p, s->d_ej.p, s->d_omega_ij.p, s->d_cov6.p, s->d_weight.p, s->error_type,
                                                       s->node_q[0].p, s->node_JL[0].p, s->loss, dr.p, dji.p, djj.p, drho.p);
   CUDA_TRY(cudaGetLastError());
@@ -2519,7 +2541,7 @@ int gsfm_ra_pcg(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, const 
   const int it = s->h_sc->pcg_iter;
   const double res = (s->h_sc->bb > 0.0) ? std::sqrt(s->h_sc->rr / s->h_sc->bb) : 0.0;
   // x = Jl^-1 xt
-  k_apply_step<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[0].p, s->x.p, nullptr, nullptr, nullptr, nullptr, s->delta.p, s->slots.p, s->counter.p, s->sc.p);
+  k_apply_step<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[0].p, s->x.p, nullptr, nullptr, nullptr, nullptr, s->delta.p, s->slots.p, s->counter.p, s->sc.p, 0);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(x, s->delta.p, 3ull * N * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -2560,7 +2582,7 @@ int gsfm_ra_filter_view_pairs(const gsfm_ra_problem* problem, const double* omeg
   RA_TRY(dk.alloc(E));
   RA_TRY(da.alloc(E));
   const double thr = max_degrees * M_PI / 180.0;
-  k_node_prep<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->omega[0].p, s->node_q[0].p, s->node_JL[0].p, s->slots.p, s->counter.p, s->sc.p);
+  k_node_prep<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->omega[0].p, s->node_q[0].p, s->node_JL[0].p, s->slots.p, s->counter.p, s->sc.p, s->manifold() ? 1 : 0);
   k_filter_pairs<<<grid_for(E), kBlock, 0, s->stream>>>(E, s->d_ei.p, s->d_ej.p, s->d_omega_ij.p, s->node_q[0].p, thr * thr, dk.p, da.p);
   CUDA_TRY(cudaGetLastError());
   if (keep) CUDA_TRY(cudaMemcpyAsync(keep, dk.p, E, cudaMemcpyDeviceToHost, s->stream));

@@ -289,10 +289,45 @@ struct EdgeTerms {
   double rho[3];
 };
 
-template <bool kNeedJacobian>
+// kResidual = 0: r = U Log(E)                    (angle-axis types 3..8)
+// kResidual = 1: r = -2 w vec(q_E) = 2 w vec(q_ij (q_j q_i^-1)^-1)   (QUATERNION_COSINE,
+//                include/pairwise_rotation_error_quat.hpp:82-106; w = U[0]); with the left perturbation
+//                q_E <- [phi/2, 1] q_E:  d r / d phi_j = A = w ([v_E]x - w_E I), and d r / d phi_i = -A Q as for any
+//                residual that is a function of E.  No logarithm, smooth through theta = pi.
+template <bool kNeedJacobian, int kResidual = 0>
 __host__ __device__ inline void edge_terms(const Q4& qi, const Q4& qj, const Q4& qij, const double* U, const DevLoss& L, EdgeTerms& o) {
   const Q4 qL = qmul(qj, qconj(qi));   // loop rotation R_j R_i^T
   const Q4 qE = qmul(qL, qconj(qij));  // error rotation R_j R_i^T R_ij^T
+  if (kResidual == 1) {
+    const double w = U[0];
+    o.r[0] = -2.0 * w * qE.x; o.r[1] = -2.0 * w * qE.y; o.r[2] = -2.0 * w * qE.z;
+    const double s = o.r[0] * o.r[0] + o.r[1] * o.r[1] + o.r[2] * o.r[2];
+    eval_loss(L, s, o.rho);
+    if (!kNeedJacobian) return;
+    o.A[0] = -w * qE.w; o.A[1] = -w * qE.z; o.A[2] = w * qE.y;
+    o.A[3] = w * qE.z;  o.A[4] = -w * qE.w; o.A[5] = -w * qE.x;
+    o.A[6] = -w * qE.y; o.A[7] = w * qE.x;  o.A[8] = -w * qE.w;
+    quat_to_mat(qL, o.Q);
+    double u[3];
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) u[cc] = o.A[cc] * o.r[0] + o.A[3 + cc] * o.r[1] + o.A[6 + cc] * o.r[2];
+    double kappa = 0.0;
+    const double rho1 = o.rho[1];
+    if (s != 0.0 && o.rho[2] > 0.0) {
+      const double D = 1.0 + 2.0 * s * o.rho[2] / rho1;
+      const double alpha = 1.0 - ((D > 0.0) ? sqrt(D) : 0.0);
+      kappa = (2.0 * alpha - alpha * alpha) / s;
+    }
+    const double* A = o.A;
+    o.W[0] = rho1 * (A[0] * A[0] + A[3] * A[3] + A[6] * A[6] - kappa * u[0] * u[0]);
+    o.W[1] = rho1 * (A[0] * A[1] + A[3] * A[4] + A[6] * A[7] - kappa * u[0] * u[1]);
+    o.W[2] = rho1 * (A[0] * A[2] + A[3] * A[5] + A[6] * A[8] - kappa * u[0] * u[2]);
+    o.W[3] = rho1 * (A[1] * A[1] + A[4] * A[4] + A[7] * A[7] - kappa * u[1] * u[1]);
+    o.W[4] = rho1 * (A[1] * A[2] + A[4] * A[5] + A[7] * A[8] - kappa * u[1] * u[2]);
+    o.W[5] = rho1 * (A[2] * A[2] + A[5] * A[5] + A[8] * A[8] - kappa * u[2] * u[2]);
+    o.v[0] = rho1 * u[0]; o.v[1] = rho1 * u[1]; o.v[2] = rho1 * u[2];
+    return;
+  }
   double e[3], theta2, c;
   quat_log(qE, e, &theta2, &c);
   o.r[0] = U[0] * e[0] + U[1] * e[1] + U[2] * e[2];

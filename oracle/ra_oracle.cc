@@ -34,7 +34,7 @@ namespace {
 /* ------------------------------------------------------------------------------------ */
 /* forward-mode dual numbers, the role ceres::Jet<double,6> plays in the reference       */
 /* ------------------------------------------------------------------------------------ */
-constexpr int kN = 6;
+constexpr int kN = 8; /* 3+3 angle-axis blocks use the first six; the quaternion functor needs 4+4 */
 struct Jet {
   double a;
   double v[kN];
@@ -153,6 +153,85 @@ void EdgeResidual(const T* w1, const T* w2, const double* w12, const double* U, 
   T e[3];
   MatrixToAngleAxis(err, e);
   for (int r = 0; r < 3; ++r) res[r] = T(U[3 * r + 0]) * e[0] + T(U[3 * r + 1]) * e[1] + T(U[3 * r + 2]) * e[2];
+}
+
+/* include/pairwise_rotation_error_quat.hpp:82-106 (PairwiseRotationErrorQuat): parameter blocks are Eigen
+ * quaternions in coefficient order (x,y,z,w); delta_q = q_rel * conj(q_b * conj(q_a)); residual = 2 w delta_q.vec(). */
+template <typename T>
+void QMul(const T* a, const T* b, T* o) { /* Hamilton product, (x,y,z,w) storage */
+  o[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+  o[1] = a[3] * b[1] - a[0] * b[2] + a[1] * b[3] + a[2] * b[0];
+  o[2] = a[3] * b[2] + a[0] * b[1] - a[1] * b[0] + a[2] * b[3];
+  o[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+}
+template <typename T>
+void QuatCosineResidual(const T* qa, const T* qb, const double* qrel, double weight, T* res) {
+  const T qa_inv[4] = {-qa[0], -qa[1], -qa[2], qa[3]};
+  T est[4];
+  QMul(qb, qa_inv, est);
+  const T est_conj[4] = {-est[0], -est[1], -est[2], est[3]};
+  const T rel[4] = {T(qrel[0]), T(qrel[1]), T(qrel[2]), T(qrel[3])};
+  T dq[4];
+  QMul(rel, est_conj, dq);
+  for (int k = 0; k < 3; ++k) res[k] = T(weight) * T(2.0) * dq[k];
+}
+/* ceres AngleAxisToQuaternion, output in Eigen coefficient order (x,y,z,w) as rotation_estimator.cpp:127-136 builds it */
+void AngleAxisToQuatXYZW(const double* w, double* q) {
+  const double t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  if (t2 > 0.0) {
+    const double t = std::sqrt(t2), half = t * 0.5, k = std::sin(half) / t;
+    q[3] = std::cos(half); q[0] = w[0] * k; q[1] = w[1] * k; q[2] = w[2] * k;
+  } else {
+    q[3] = 1.0; q[0] = w[0] * 0.5; q[1] = w[1] * 0.5; q[2] = w[2] * 0.5;
+  }
+}
+/* ceres QuaternionToAngleAxis on (w,x,y,z) = (q[3],q[0],q[1],q[2]) (rotation_estimator.cpp:185-194) */
+void QuatXYZWToAngleAxis(const double* q, double* w) {
+  const double sin2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+  if (sin2 > 0.0) {
+    const double s = std::sqrt(sin2), c = q[3];
+    const double two_theta = 2.0 * ((c < 0.0) ? std::atan2(-s, -c) : std::atan2(s, c));
+    const double k = two_theta / s;
+    w[0] = q[0] * k; w[1] = q[1] * k; w[2] = q[2] * k;
+  } else {
+    w[0] = q[0] * 2.0; w[1] = q[1] * 2.0; w[2] = q[2] * 2.0;
+  }
+}
+/* ceres EigenQuaternionParameterization: Plus and its 4x3 Jacobian at delta = 0 */
+void QuatPlus(const double* x, const double* d, double* out) {
+  const double n = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  if (n > 0.0) {
+    const double k = std::sin(n) / n;
+    const double qd[4] = {k * d[0], k * d[1], k * d[2], std::cos(n)};
+    QMul(qd, x, out);
+  } else {
+    for (int k = 0; k < 4; ++k) out[k] = x[k];
+  }
+}
+void QuatPlusJacobian(const double* x, double* J /*4x3 row-major*/) {
+  J[0] = x[3];  J[1] = x[2];   J[2] = -x[1];
+  J[3] = -x[2]; J[4] = x[3];   J[5] = x[0];
+  J[6] = x[1];  J[7] = -x[0];  J[8] = x[3];
+  J[9] = -x[0]; J[10] = -x[1]; J[11] = -x[2];
+}
+/* one quaternion edge through jets; Jacobians returned in the 3-dim LOCAL (tangent) coordinates Ceres optimises in:
+ * J_local = J_ambient(3x4) * PlusJacobian(4x3). */
+void QuatEdge(const double* qa, const double* qb, const double* qrel, double weight, double* r, double* Ji, double* Jj) {
+  Jet a[4], b[4], res[3];
+  for (int k = 0; k < 4; ++k) { a[k] = Jet(qa[k]); a[k].v[k] = 1.0; b[k] = Jet(qb[k]); b[k].v[4 + k] = 1.0; }
+  QuatCosineResidual<Jet>(a, b, qrel, weight, res);
+  double Pa[12], Pb[12];
+  QuatPlusJacobian(qa, Pa);
+  QuatPlusJacobian(qb, Pb);
+  for (int q = 0; q < 3; ++q) {
+    if (r) r[q] = res[q].a;
+    for (int c = 0; c < 3; ++c) {
+      double si = 0, sj = 0;
+      for (int m = 0; m < 4; ++m) { si += res[q].v[m] * Pa[3 * m + c]; sj += res[q].v[4 + m] * Pb[3 * m + c]; }
+      if (Ji) Ji[3 * q + c] = si;
+      if (Jj) Jj[3 * q + c] = sj;
+    }
+  }
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -332,7 +411,8 @@ bool TypeNeedsCov(int type) {
   return type == GSFM_RA_ANGLE_AXIS_COVARIANCE || type == GSFM_RA_ANGLE_AXIS_COV_INLIERS ||
          type == GSFM_RA_ANGLE_AXIS_COVTRACE || type == GSFM_RA_ANGLE_AXIS_COVNORM;
 }
-bool TypeSupported(int type) { return type >= GSFM_RA_ANGLE_AXIS_COVARIANCE && type <= GSFM_RA_ANGLE_AXIS_COVNORM; }
+bool TypeSupported(int type) { return type == GSFM_RA_QUATERNION_COSINE || (type >= GSFM_RA_ANGLE_AXIS_COVARIANCE && type <= GSFM_RA_ANGLE_AXIS_COVNORM); }
+bool IsQuat(const gsfm_ra_problem* p) { return p->error_type == GSFM_RA_QUATERNION_COSINE; }
 
 void EdgeU(const gsfm_ra_problem* p, uint64_t k, double* U) {
   Whiten(p->error_type, p->cov6 ? p->cov6 + 6 * k : nullptr, p->edge_weight ? p->edge_weight[k] : 1.0, U);
@@ -352,7 +432,16 @@ struct LossEval {
  * (SURVEY Appendix B.2).  Jacobian is corrected first, from the uncorrected residual. */
 struct EdgeEval { double r[3], Ji[9], Jj[9], rho[3]; };
 
+/* `omega` is the state: [N][3] angle-axis, or [N][4] quaternions (x,y,z,w) for QUATERNION_COSINE */
 void EvalEdgeRaw(const gsfm_ra_problem* p, uint64_t k, const double* omega, EdgeEval* out, bool jac) {
+  if (IsQuat(p)) {
+    double qrel[4];
+    AngleAxisToQuatXYZW(p->omega_ij + 3 * k, qrel);
+    const double w = p->edge_weight ? p->edge_weight[k] : 1.0;  /* cost_weight = 1.0, rotation_estimator.cpp:125 */
+    QuatEdge(omega + 4 * (size_t)p->edge_i[k], omega + 4 * (size_t)p->edge_j[k], qrel, w, out->r, jac ? out->Ji : nullptr,
+             jac ? out->Jj : nullptr);
+    return;
+  }
   double U[9];
   EdgeU(p, k, U);
   const double* wi = omega + 3 * (size_t)p->edge_i[k];
@@ -677,9 +766,19 @@ void ra_oracle_edge(const double* wi, const double* wj, const double* wij, const
   }
 }
 
+static std::vector<double> StateFromOmega(const gsfm_ra_problem* p, const double* omega) {
+  std::vector<double> st;
+  if (!IsQuat(p)) return st;
+  st.resize(4 * (size_t)p->num_views);
+  for (size_t a = 0; a < p->num_views; ++a) AngleAxisToQuatXYZW(omega + 3 * a, &st[4 * a]);
+  return st;
+}
+
 int ra_oracle_eval_edges(const gsfm_ra_problem* p, const gsfm_ra_loss* loss, const double* omega, double* r, double* Ji,
                          double* Jj, double* rho, int num_threads) {
   if (int rc = CheckProblem(p)) return rc;
+  const std::vector<double> qstate = StateFromOmega(p, omega);
+  if (IsQuat(p)) omega = qstate.data();
   const int nt = Threads(num_threads);
 #pragma omp parallel for num_threads(nt) schedule(static)
   for (int64_t k = 0; k < (int64_t)p->num_edges; ++k) {
@@ -700,6 +799,8 @@ int ra_oracle_assemble(const gsfm_ra_problem* p, const gsfm_ra_loss* loss, const
   BuildStructure(p, &S);
   Linearization L;
   LossEval le{loss, nullptr, nullptr};
+  const std::vector<double> qstate = StateFromOmega(p, omega);
+  if (IsQuat(p)) omega = qstate.data();
   Linearize(p, le, omega, S, &L, true, num_threads);
   if (cost) *cost = L.cost;
   if (gradient) std::memcpy(gradient, L.g.data(), L.g.size() * sizeof(double));
@@ -715,6 +816,8 @@ int ra_oracle_cost(const gsfm_ra_problem* p, const gsfm_ra_loss* loss, const dou
   Structure S; /* unused for cost-only */
   Linearization L;
   LossEval le{loss, nullptr, nullptr};
+  const std::vector<double> qstate = StateFromOmega(p, omega);
+  if (IsQuat(p)) omega = qstate.data();
   Linearize(p, le, omega, S, &L, false, num_threads);
   *cost = L.cost;
   return 0;
@@ -739,7 +842,15 @@ int ra_oracle_solve(const gsfm_ra_problem* p, const gsfm_ra_options* o, double* 
   BuildStructure(p, &S);
   LossEval le{&o->loss, loss_cb, cb_ctx};
   Linearization L, Ltrial;
-  std::vector<double> x(omega, omega + n), cand(n), scale(n, 1.0), damp(n), delta(n), negg(n), Hd(n), diag(n);
+  const bool quat = IsQuat(p);
+  /* QUATERNION_COSINE (rotation_estimator.cpp:82-198): the parameters are unit quaternions (x,y,z,w) with
+   * EigenQuaternionParameterization; the trust region works in the 3-dim local coordinates, Plus() maps back. */
+  std::vector<double> x = quat ? StateFromOmega(p, omega) : std::vector<double>(omega, omega + n);
+  std::vector<double> cand(x.size()), scale(n, 1.0), damp(n), delta(n), negg(n), Hd(n), diag(n), tmp4(x.size());
+  auto plus = [&](const std::vector<double>& from, const double* d, std::vector<double>* to) {
+    if (!quat) { for (size_t c = 0; c < n; ++c) (*to)[c] = from[c] + d[c]; return; }
+    for (size_t a = 0; a < N; ++a) QuatPlus(&from[4 * a], d + 3 * a, &(*to)[4 * a]);
+  };
   gsfm_ra_summary local;
   std::memset(&local, 0, sizeof(local));
   if (sum) { local.trace = sum->trace; local.trace_capacity = sum->trace_capacity; }
@@ -762,7 +873,16 @@ int ra_oracle_solve(const gsfm_ra_problem* p, const gsfm_ra_options* o, double* 
     diag_of(L, &diag);
     for (size_t c = 0; c < n; ++c) scale[c] = 1.0 / (1.0 + std::sqrt(diag[c]));
   }
-  auto gmax = [&](const Linearization& Lz) { double m = 0; for (double v : Lz.g) m = std::max(m, std::fabs(v)); return m; };
+  /* gradient_max_norm = |x - Plus(x, -g)|_inf (ambient coordinates) */
+  auto gmax = [&](const Linearization& Lz) {
+    double m = 0;
+    if (!quat) { for (double v : Lz.g) m = std::max(m, std::fabs(v)); return m; }
+    std::vector<double> ng(n);
+    for (size_t c = 0; c < n; ++c) ng[c] = -Lz.g[c];
+    plus(x, ng.data(), &tmp4);
+    for (size_t c = 0; c < x.size(); ++c) m = std::max(m, std::fabs(x[c] - tmp4[c]));
+    return m;
+  };
   auto norm = [&](const std::vector<double>& v) { double s = 0; for (double u : v) s += u * u; return std::sqrt(s); };
   double x_norm = norm(x);
   double radius = o->initial_trust_region_radius;
@@ -831,14 +951,15 @@ int ra_oracle_solve(const gsfm_ra_problem* p, const gsfm_ra_options* o, double* 
       continue;
     }
     invalid_steps = 0;
-    for (size_t c = 0; c < n; ++c) cand[c] = x[c] + delta[c];
+    plus(x, delta.data(), &cand);
     t = NowMs();
     Linearize(p, le, cand.data(), S, &Ltrial, false, nt);
     t_cost += NowMs() - t;
     double cand_cost = Ltrial.cost;
     if (!std::isfinite(cand_cost)) cand_cost = DBL_MAX;
     it.candidate_cost = cand_cost;
-    it.step_norm = norm(delta);
+    if (!quat) it.step_norm = norm(delta);
+    else { double s2 = 0; for (size_t c = 0; c < x.size(); ++c) s2 += (x[c] - cand[c]) * (x[c] - cand[c]); it.step_norm = std::sqrt(s2); }
     it.cost_change = x_cost - cand_cost;
     it.relative_decrease = it.cost_change / model_change;
     it.gradient_max_norm = last_gmax;
@@ -881,7 +1002,13 @@ int ra_oracle_solve(const gsfm_ra_problem* p, const gsfm_ra_options* o, double* 
                    it.cost_change, it.gradient_max_norm, it.step_norm, it.relative_decrease, radius, it.linear_iterations,
                    it.step_is_successful ? "ok" : "rejected");
   }
-  std::memcpy(omega, x.data(), n * sizeof(double));
+  if (!quat) std::memcpy(omega, x.data(), n * sizeof(double));
+  else {
+    /* only the views that own a parameter block (touched by an edge) are converted back (:185-194) */
+    std::vector<char> touched(N, 0);
+    for (uint64_t k = 0; k < p->num_edges; ++k) { touched[p->edge_i[k]] = 1; touched[p->edge_j[k]] = 1; }
+    for (size_t a = 0; a < N; ++a) if (touched[a]) QuatXYZWToAngleAxis(&x[4 * a], omega + 3 * a);
+  }
   local.termination = term;
   local.num_iterations = iteration;
   local.final_cost = x_cost;

@@ -60,7 +60,7 @@ def test_invalid_arguments_are_rejected_before_the_device():
     with pytest.raises(capi.GsfmError) as e:
         solver.solve(prob, capi.default_options_py(), g.omega_init)
     assert e.value.code == capi.ERR_INVALID
-    prob = capi.ProblemArrays(6, g.edge_i, g.edge_j, g.omega_ij, error_type=capi.QUATERNION_COSINE)
+    prob = capi.ProblemArrays(6, g.edge_i, g.edge_j, g.omega_ij, error_type=capi.QUATERNION_NORM)
     with pytest.raises(capi.GsfmError) as e:
         solver.solve(prob, capi.default_options_py(), g.omega_init)
     assert e.value.code == capi.ERR_UNSUPPORTED

@@ -313,6 +313,49 @@ def test_madrid_cauchy_tight(madrid):
     assert sg.final_cost <= so.final_cost * (1 + 1e-9)
 
 
+def test_quaternion_cosine_type():
+    """RotationErrorType.QUATERNION_COSINE, the default of EstimateGlobalRotations (rotation_estimator.cpp:82-198):
+    residual 2 w vec(q_ij (q_j q_i^-1)^-1) on quaternion parameter blocks with EigenQuaternionParameterization.  The oracle
+    differentiates the functor with 8-wide jets and projects with the parameterisation's Jacobian; the kernel uses the
+    closed form in the left tangent frame."""
+    g = vg.synthetic_pose_graph(200, 3000, seed=12, noise_deg=2.0, outlier_fraction=0.2)
+    prob = capi.ProblemArrays(200, g.edge_i, g.edge_j, g.omega_ij, error_type=capi.QUATERNION_COSINE)
+    rng = np.random.default_rng(5)
+    omega = g.omega_init + 0.05 * rng.normal(size=g.omega_init.shape)
+    L = capi.Loss.make(capi.LOSS_HUBER, 0.05)
+    r, Ji, Jj, rho = solver.eval_edges(prob, L, omega)
+    r0, Ji0, Jj0, rho0 = orc.eval_edges(prob, L, omega)
+    # the sign of a quaternion is a representation choice: the residual is defined up to one global sign per edge
+    sgn = np.sign(np.einsum("ek,ek->e", r, r0))
+    sgn[sgn == 0] = 1
+    assert rel_err_rows(r * sgn[:, None], r0) < 1e-10
+    assert rel_err_rows(Ji * sgn[:, None, None], Ji0) < 1e-10 and rel_err_rows(Jj * sgn[:, None, None], Jj0) < 1e-10
+    assert np.allclose(rho, rho0, rtol=1e-10, atol=1e-12)
+    c, gr, hd, rp, col, val = solver.assemble(prob, L, omega)
+    c0, gr0, hd0, rp0, col0, val0 = orc.assemble(prob, L, omega)
+    assert abs(c - c0) <= 1e-12 * abs(c0)
+    assert_close(gr, gr0, 1e-10, "gradient (local coordinates)")
+    assert_close(hd, hd0, 1e-10, "diagonal blocks")
+    assert_close(val, val0, 1e-10, "off-diagonal blocks")
+    # default Ceres tolerances: same trajectory; tight: same minimiser
+    o = capi.default_options_py()
+    o.loss = L
+    o.pcg_rtol = 1e-13
+    o.pcg_max_iterations = 2000
+    og, sg, tg = solver.solve(prob, o, g.omega_init, trace_capacity=256)
+    o.linear_solver = capi.SOLVER_DENSE_CHOLESKY
+    oo, so, to = orc.solve(prob, o, g.omega_init, trace_capacity=256)
+    assert sg.termination == so.termination and sg.num_iterations == so.num_iterations
+    for a, b in zip(tg, to):
+        assert a.step_is_successful == b.step_is_successful and abs(a.cost - b.cost) <= 1e-8 * abs(b.cost)
+        assert abs(a.step_norm - b.step_norm) <= 1e-6 * max(b.step_norm, 1e-12)
+    assert vg.mean_angular_error(oo, og)[0] < 1e-7
+    og, sg, _ = solver.solve(prob, _tight(L), g.omega_init)
+    oo, so, _ = orc.solve(prob, _tight(L, linear_solver=capi.SOLVER_DENSE_CHOLESKY), g.omega_init)
+    assert vg.mean_angular_error(oo, og)[0] < 1e-7
+    assert np.degrees(vg.mean_angular_error(g.omega_gt, og)[1]) < 3.0
+
+
 def test_sigma_consensus_matches_oracle():
     """EstimateRotationsWithSigmaConsensus (rotation_estimator.cpp:314-457): outer re-weighting loop."""
     g = vg.synthetic_pose_graph(120, 1500, seed=77, noise_deg=1.0, outlier_fraction=0.15)
