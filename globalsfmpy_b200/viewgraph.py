@@ -290,8 +290,36 @@ def madrid_like_covariances(rng, E):
     lam = 10.0 ** np.clip(np.sort(rng.normal(mu, sd, size=(E, 3)), axis=1), -3, 9)
     Q = so3_exp(random_rotation_vectors(rng, E))
     S = np.einsum("eij,ej,ekj->eik", Q, lam * 1e-8, Q)
+    # The reference whitens with a cofactor inverse + LLT and no PD check (rotation_estimator.cpp:252-255); at condition
+    # numbers near 1e12 roughly one sample in a few million cancels to a negative pivot (NaN for the reference too).
+    # Such samples are redrawn with the spread capped at 1e6 so a synthetic graph never carries an input the reference
+    # itself could not digest.
+    bad = ~whitening_is_finite(S)
+    if bad.any():
+        lam_b = lam[bad]
+        lam_b = np.maximum(lam_b, lam_b[:, 2:3] * 1e-6)
+        S[bad] = np.einsum("eij,ej,ekj->eik", Q[bad], lam_b * 1e-8, Q[bad])
     cov6 = np.stack([S[:, 0, 0], S[:, 1, 1], S[:, 2, 2], S[:, 0, 1], S[:, 0, 2], S[:, 1, 2]], axis=1)
     return cov6, S
+
+
+def whitening_is_finite(S):
+    """The whitening formula of rotation_estimator.cpp:252-255 (cofactor inverse of 1e8 Sigma, then Cholesky), vectorised,
+    only to tell whether it stays finite for each covariance [E,3,3]."""
+    with np.errstate(all="ignore"):
+        a, d, f = S[:, 0, 0] * 1e8, S[:, 1, 1] * 1e8, S[:, 2, 2] * 1e8
+        b, c, e = S[:, 0, 1] * 1e8, S[:, 0, 2] * 1e8, S[:, 1, 2] * 1e8
+        c00, c01, c02 = d * f - e * e, c * e - b * f, b * e - c * d
+        c11, c12, c22 = a * f - c * c, b * c - a * e, a * d - b * b
+        idet = 1.0 / (a * c00 + b * c01 + c * c02)
+        P00, P10, P20, P11, P21, P22 = c00 * idet, c01 * idet, c02 * idet, c11 * idet, c12 * idet, c22 * idet
+        l00 = np.sqrt(P00); l10 = P10 / l00; l20 = P20 / l00
+        l11 = np.sqrt(P11 - l10 * l10); l21 = (P21 - l20 * l10) / l11
+        l22 = np.sqrt(P22 - l20 * l20 - l21 * l21)
+        ok = np.isfinite(l00) & np.isfinite(l11) & np.isfinite(l22) & np.isfinite(l10) & np.isfinite(l20) & np.isfinite(l21)
+        # keep a safety margin: pivots that survive only by a few ulps are treated as failures too
+        ok &= (P11 - l10 * l10 > 1e-9 * np.abs(P11)) & (P22 - l20 * l20 - l21 * l21 > 1e-9 * np.abs(P22))
+    return ok
 
 
 def synthetic_pose_graph(num_views, num_edges, seed=56, noise_deg=1.0, outlier_fraction=0.1,
