@@ -44,16 +44,22 @@ constexpr int kWarpsPerBlock = kBlock / 32;
 constexpr uint32_t kSideBit = 0x80000000u;  // he_col bit 31: the ROW view is the j (second) view of the edge
 constexpr int kPartStride = 10;    // per-task partial: diag(6) grad(3) cost(1)
 // The block matrix is stored as CHUNK RECORDS of 32 consecutive half-edges:
-//   { double blk[9][32]; uint32_t col[32]; }  = 2432 B, 128 B aligned,
+//   { double blk[kBlk][32]; uint32_t col[32]; }   128 B aligned,
 // so 32 lanes still read/write 256 contiguous bytes per block component (coalesced), and K2 can
 // pull a whole record into shared memory with ONE bulk async copy (TMA, cp.async.bulk).
-constexpr int kRecDoubles = 304;                 // 2432 B / 8
-constexpr int kRecBytes = kRecDoubles * 8;
-constexpr int kRecColOffset = 288;               // doubles: col[] starts at byte 2304
+//   kBlk = 6: symmetric off-diagonal block -S packed (00,01,02,11,12,22) -- every residual that is a function of the
+//             error rotation (types 2..8) is a Laplacian stencil in the body frame;  1664 B per record (52 B / half-edge)
+//   kBlk = 9: general row-major block (QUATERNION_NORM, ROTATION_MAT_FNORM);         2432 B per record (76 B / half-edge)
+template <int kBlk>
+struct Rec {
+  static constexpr int kDoubles = kBlk * 32 + 16;
+  static constexpr int kBytes = kDoubles * 8;
+  static constexpr int kColOffset = kBlk * 32;  // doubles: col[] starts here
+};
 constexpr int kStages = 4;                       // TMA ring depth per warp
-constexpr int kSpmvSmemBytes = kWarpsPerBlock * kStages * kRecBytes + kWarpsPerBlock * kStages * 8;
+constexpr int spmv_smem_bytes(int blk) { return kWarpsPerBlock * kStages * (blk * 32 + 16) * 8 + kWarpsPerBlock * kStages * 8; }
 
-__device__ __host__ __forceinline__ size_t blk_index(uint64_t h, int k) { return (size_t)(h >> 5) * kRecDoubles + (size_t)k * 32 + (h & 31); }
+__device__ __host__ __forceinline__ size_t blk_index(uint64_t h, int k, int rec_doubles) { return (size_t)(h >> 5) * rec_doubles + (size_t)k * 32 + (h & 31); }
 
 thread_local std::string g_last_error;
 
@@ -243,15 +249,19 @@ __global__ void k_node_seg_count(uint32_t N, uint32_t per, const uint32_t* __res
 }
 
 // Column indices live inside the chunk records of both block buffers (written once).
-__global__ void k_embed_cols(uint64_t H, const uint32_t* __restrict__ he_col, double* rec0, double* rec1) {
+__global__ void k_embed_cols(uint64_t H, int blk, const uint32_t* __restrict__ he_col, double* rec0, double* rec1) {
   const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= H) return;
-  const size_t w = (size_t)(h >> 5) * kRecDoubles + kRecColOffset;
+  const size_t w = (size_t)(h >> 5) * (blk * 32 + 16) + blk * 32;
   reinterpret_cast<uint32_t*>(rec0 + w)[h & 31] = he_col[h];
   reinterpret_cast<uint32_t*>(rec1 + w)[h & 31] = he_col[h];
 }
 
-// Per view: quaternion + left Jacobian of the current angle-axis estimate; also |omega|^2.
+// Per view: quaternion + the factor D of d(beta) = D d(parameters) at the current estimate; also |x|^2.
+//   angle-axis parameters:  D = Jr(omega) = Jl(-omega)   (R(omega + d omega) = R(omega) Exp(Jr d omega))
+//   quaternion parameters with EigenQuaternionParameterization (x (+) delta = [sin|d| d/|d|, cos|d|] (x) x, i.e. a LEFT
+//   perturbation phi = 2 delta):  beta = R^T phi  ->  D = 2 R^T;  |x|^2 = 1 per unit quaternion
+// The array keeps its historical name node_JL.
 __global__ void k_node_prep(uint32_t N, const double* __restrict__ omega, double* __restrict__ node_q, double* __restrict__ node_JL,
                             double* slots, unsigned* counter, DevScalars* sc, int manifold) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -261,11 +271,16 @@ __global__ void k_node_prep(uint32_t N, const double* __restrict__ omega, double
     const Q4 q = aa_to_quat(wx, wy, wz);
     reinterpret_cast<double4*>(node_q)[i] = make_double4(q.w, q.x, q.y, q.z);
     double J[9];
-    if (manifold) {  // local coordinates of EigenQuaternionParameterization: phi = 2 delta  ->  J = 2 I; |x|^2 = 1 per unit quaternion
-      J[0] = J[4] = J[8] = 2.0; J[1] = J[2] = J[3] = J[5] = J[6] = J[7] = 0.0;
+    if (manifold) {
+      double R[9];
+      quat_to_mat(q, R);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) J[3 * r + c] = 2.0 * R[3 * c + r];
       v[0] = 1.0;
     } else {
-      so3_left_jacobian(wx, wy, wz, J);
+      so3_left_jacobian(-wx, -wy, -wz, J);
       v[0] = wx * wx + wy * wy + wz * wz;
     }
 #pragma unroll
@@ -277,14 +292,14 @@ __global__ void k_node_prep(uint32_t N, const double* __restrict__ omega, double
 
 // ------------------------------------------------------------------------------------------
 // K1: fused residual + SO(3) Jacobian + whitening + robust loss + normal-equation assembly.
-// One warp per task (a run of <= kTaskLen half-edges of ONE row view).  Each lane evaluates one
-// half-edge per iteration: loads are planar and coalesced (qij 4x8 B, U 6x8 B, col 4 B), the row
-// view's quaternion is a warp broadcast, the column view's quaternion is one aligned 32 B gather
-// served by L2.  Writes the off-diagonal tangent block of the half-edge (planar, coalesced) and,
-// per task, the warp-reduced diagonal block / gradient / cost partial.
+// One warp per balanced range of half-edges, visited segment by segment (segment = range ^ row).  Each lane
+// evaluates one half-edge per iteration: loads are planar and coalesced (qij 4x8 B, U 6x8 B or 8 B, col 4 B),
+// the row view's quaternion is a warp broadcast, the column view's quaternion is one aligned 32 B gather
+// served by L2.  Writes the off-diagonal block -S of the half-edge (6 doubles, planar, coalesced) and, per
+// segment, the warp-reduced diagonal block / gradient / cost partial.
 // kWriteBlocks=false is K1c: cost only (trial point).
 // ------------------------------------------------------------------------------------------
-template <bool kWriteBlocks, int kResidual>
+template <bool kWriteBlocks, int kResidual, bool kScalarU>
 __global__ void __launch_bounds__(kBlock, 2)
 k_edges(uint32_t num_warps, uint64_t H, const uint32_t* __restrict__ warp_seg_ptr, const uint32_t* __restrict__ task_row,
         const uint32_t* __restrict__ task_begin, const uint32_t* __restrict__ task_len, const uint32_t* __restrict__ he_col,
@@ -311,47 +326,21 @@ k_edges(uint32_t num_warps, uint64_t H, const uint32_t* __restrict__ warp_seg_pt
       const Q4 qb{qb4.x, qb4.y, qb4.z, qb4.w};
       const Q4 qm{qij[h], qij[H + h], qij[2 * H + h], qij[3 * H + h]};
       double u[6];
+      u[0] = U[h];
+      if (!kScalarU && kResidual == 0) {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) u[k] = U[(uint64_t)k * H + h];
+        for (int k = 1; k < 6; ++k) u[k] = U[(uint64_t)k * H + h];
+      }
       EdgeTerms et;
-      if (row_is_j) edge_terms<kWriteBlocks, kResidual>(qb, qa, qm, u, loss, et);
-      else edge_terms<kWriteBlocks, kResidual>(qa, qb, qm, u, loss, et);
+      if (row_is_j) edge_terms<kWriteBlocks, kResidual, kScalarU>(qb, qa, qm, u, loss, et);
+      else edge_terms<kWriteBlocks, kResidual, kScalarU>(qa, qb, qm, u, loss, et);
       if (!row_is_j) acc[9] += 0.5 * et.rho[0];  // each edge's cost is counted once, in its i row
       if (kWriteBlocks) {
-        const double* W = et.W;
-        const double* Q = et.Q;
-        double B[9];
-        if (row_is_j) {
-          // row j: diag += W, grad += v, block(j,i) = -W Q
-          acc[0] += W[0]; acc[1] += W[1]; acc[2] += W[2]; acc[3] += W[3]; acc[4] += W[4]; acc[5] += W[5];
-          acc[6] += et.v[0]; acc[7] += et.v[1]; acc[8] += et.v[2];
+        // both rows of the edge: diag += S, block(row, col) = -S; gradient: +v in row j, -v in row i
+        const double sgn = row_is_j ? 1.0 : -1.0;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            B[c] = -(W[0] * Q[c] + W[1] * Q[3 + c] + W[2] * Q[6 + c]);
-            B[3 + c] = -(W[1] * Q[c] + W[3] * Q[3 + c] + W[4] * Q[6 + c]);
-            B[6 + c] = -(W[2] * Q[c] + W[4] * Q[3 + c] + W[5] * Q[6 + c]);
-          }
-        } else {
-          // row i: diag += Q^T W Q, grad += -Q^T v, block(i,j) = -Q^T W
-#pragma unroll
-          for (int r = 0; r < 3; ++r) {  // B[r][c] = -sum_k Q[k][r] W[k][c]
-            B[3 * r + 0] = -(Q[r] * W[0] + Q[3 + r] * W[1] + Q[6 + r] * W[2]);
-            B[3 * r + 1] = -(Q[r] * W[1] + Q[3 + r] * W[3] + Q[6 + r] * W[4]);
-            B[3 * r + 2] = -(Q[r] * W[2] + Q[3 + r] * W[4] + Q[6 + r] * W[5]);
-          }
-          // Q^T W Q = -B Q
-          acc[0] -= B[0] * Q[0] + B[1] * Q[3] + B[2] * Q[6];
-          acc[1] -= B[0] * Q[1] + B[1] * Q[4] + B[2] * Q[7];
-          acc[2] -= B[0] * Q[2] + B[1] * Q[5] + B[2] * Q[8];
-          acc[3] -= B[3] * Q[1] + B[4] * Q[4] + B[5] * Q[7];
-          acc[4] -= B[3] * Q[2] + B[4] * Q[5] + B[5] * Q[8];
-          acc[5] -= B[6] * Q[2] + B[7] * Q[5] + B[8] * Q[8];
-          acc[6] -= Q[0] * et.v[0] + Q[3] * et.v[1] + Q[6] * et.v[2];
-          acc[7] -= Q[1] * et.v[0] + Q[4] * et.v[1] + Q[7] * et.v[2];
-          acc[8] -= Q[2] * et.v[0] + Q[5] * et.v[1] + Q[8] * et.v[2];
-        }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) val[blk_index(h, k)] = B[k];
+        for (int k = 0; k < 6; ++k) { acc[k] += et.S[k]; val[blk_index(h, k, Rec<6>::kDoubles)] = -et.S[k]; }
+        acc[6] += sgn * et.v[0]; acc[7] += sgn * et.v[1]; acc[8] += sgn * et.v[2];
       }
     }
     if (kWriteBlocks) {
@@ -440,13 +429,14 @@ __global__ void k_jacobi_scale(uint32_t n3, const double* __restrict__ ediag, do
 //   LM diagonal in scaled coordinates  d_c = clamp(ediag_c s_c^2, lo, hi) / mu           (LevenbergMarquardtStrategy)
 //   as damping of the unscaled Euclidean system  lam_c = d_c / s_c^2
 //   moved to the tangent frame  Lam = Jl^-T diag(lam) Jl^-1 ;  Dblk = Hd + Lam ; Minv = Dblk^-1.
-// Also initialises PCG: x = 0, r = b = -gt, z = Minv r, p = z, and reduces rz, bb.
+// Also initialises PCG: x = 0, r = b = -gt, z = Minv r, p = z, q = 0, and reduces rz, bb.  z and p are the vectors
+// the SpMV gathers: stored with stride 4 (double4), everything else with stride 3.
 __global__ void k_prepare_solve(uint32_t N, double mu, double lo, double hi, const double* __restrict__ ediag,
                                 const double* __restrict__ scale, const double* __restrict__ node_JL, const double* __restrict__ Hd,
                                 const double* __restrict__ gt, const double* __restrict__ user_damp, const double* __restrict__ user_b,
                                 double* __restrict__ Dblk, double* __restrict__ Minv, double* __restrict__ x, double* __restrict__ r,
-                                double* __restrict__ z, double* __restrict__ p, double* __restrict__ p1, double* slots, unsigned* counter,
-                                DevScalars* sc) {
+                                double* __restrict__ z, double* __restrict__ p, double* __restrict__ q, double* __restrict__ bvec,
+                                double* slots, unsigned* counter, DevScalars* sc) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   double v[2] = {0.0, 0.0};
   if (i < N) {
@@ -482,11 +472,13 @@ __global__ void k_prepare_solve(uint32_t N, double mu, double lo, double hi, con
     sym_mul_vec(M, b, zz);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      x[3 * (size_t)i + c] = 0.0; r[3 * (size_t)i + c] = b[c]; z[3 * (size_t)i + c] = zz[c]; p[3 * (size_t)i + c] = zz[c];
-      p1[3 * (size_t)i + c] = 0.0;
+      x[3 * (size_t)i + c] = 0.0; r[3 * (size_t)i + c] = b[c]; bvec[3 * (size_t)i + c] = b[c]; q[3 * (size_t)i + c] = 0.0;
       v[0] += b[c] * zz[c];
       v[1] += b[c] * b[c];
     }
+    // the gathered vectors are padded to one aligned 32 B sector per view
+    reinterpret_cast<double4*>(z)[i] = make_double4(zz[0], zz[1], zz[2], 0.0);
+    reinterpret_cast<double4*>(p)[i] = make_double4(zz[0], zz[1], zz[2], 0.0);
   }
   double tot[2];
   if (grid_sum<2>(v, slots, counter, tot) && threadIdx.x == 0) {
@@ -536,10 +528,11 @@ struct WarpPipe {
   uint32_t pos;    // records consumed since init: ring slot = pos % kStages, phase = (pos / kStages) & 1
 };
 
+template <int kBlk>
 __device__ __forceinline__ void pipe_init(WarpPipe& wp, unsigned char* smem) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  wp.ring = reinterpret_cast<double*>(smem + (size_t)warp * kStages * kRecBytes);
-  wp.bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWarpsPerBlock * kStages * kRecBytes) + warp * kStages;
+  wp.ring = reinterpret_cast<double*>(smem + (size_t)warp * kStages * Rec<kBlk>::kBytes);
+  wp.bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWarpsPerBlock * kStages * Rec<kBlk>::kBytes) + warp * kStages;
   wp.pos = 0;
   if (lane == 0) {
     for (int st = 0; st < kStages; ++st) mbar_init(&wp.bars[st], 1);
@@ -549,37 +542,38 @@ __device__ __forceinline__ void pipe_init(WarpPipe& wp, unsigned char* smem) {
 }
 
 // Stream this warp's record range (nrec records from half-edge lo) and call finish(t, y0, y1, y2)
-// (all lanes, totals valid in every lane) for each segment t in [t0, t1).  x_j = a_j + beta b_j (b may be
-// null).  Record-major loop: the x gather of record c+1 (its columns are already in shared memory) is issued
-// before record c is consumed, so the L2 gather latency overlaps the arithmetic and the next wait; each
-// lane's 3-vector contribution is formed once per record and added to the running segment, segments that
-// end inside the record are reduced and handed to finish().
-template <typename Finish>
+// (all lanes, totals valid in every lane) for each segment t in [t0, t1).  x4 is the gathered vector, one
+// aligned double4 (32 B sector) per view.  Record-major loop: the x gather of record c+1 (its columns are
+// already in shared memory) is issued before record c is consumed, so the L2 gather latency overlaps the
+// arithmetic and the next wait; each lane's 3-vector contribution is formed once per record and added to
+// the running segment, segments that end inside the record are reduced and handed to finish().
+template <int kBlk, typename Finish>
 __device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restrict__ recs, uint64_t lo, uint64_t hi, uint32_t t0, uint32_t t1,
-                                            const uint32_t* __restrict__ seg_begin, const uint32_t* __restrict__ seg_len, const double* a,
-                                            const double* b, double beta, Finish&& finish) {
+                                            const uint32_t* __restrict__ seg_begin, const uint32_t* __restrict__ seg_len, const double* x4,
+                                            bool nogather, Finish&& finish) {
+  constexpr int kRD = Rec<kBlk>::kDoubles;
   const int lane = threadIdx.x & 31;
   const uint32_t nrec = (uint32_t)((hi - lo + 31) >> 5);
   const uint32_t base = wp.pos;
-  const double* src = recs + (size_t)(lo >> 5) * kRecDoubles;
+  const double* src = recs + (size_t)(lo >> 5) * kRD;
   auto issue = [&](uint32_t c) {
     if (lane == 0) {
       const uint32_t st = (base + c) % kStages;
-      mbar_expect_tx(&wp.bars[st], kRecBytes);
-      tma_load_bulk(wp.ring + (size_t)st * kRecDoubles, src + (size_t)c * kRecDoubles, kRecBytes, &wp.bars[st]);
+      mbar_expect_tx(&wp.bars[st], Rec<kBlk>::kBytes);
+      tma_load_bulk(wp.ring + (size_t)st * kRD, src + (size_t)c * kRD, Rec<kBlk>::kBytes, &wp.bars[st]);
     }
   };
   auto wait_rec = [&](uint32_t c) -> const double* {
     const uint32_t p = base + c, st = p % kStages;
     mbar_wait(&wp.bars[st], (p / kStages) & 1u);
-    return wp.ring + (size_t)st * kRecDoubles;
+    return wp.ring + (size_t)st * kRD;
   };
   auto gather = [&](const double* rec, uint64_t h, double& x0, double& x1, double& x2) {
-    uint32_t col = reinterpret_cast<const uint32_t*>(rec + kRecColOffset)[lane] & ~kSideBit;
+    uint32_t col = reinterpret_cast<const uint32_t*>(rec + Rec<kBlk>::kColOffset)[lane] & ~kSideBit;
     if (h >= hi) col = 0;  // padding lanes of the last record
-    if (beta == -12345.0) { x0 = col; x1 = 1.0; x2 = 2.0; return; }  // DEBUG: stream-only ceiling
-    x0 = a[3 * (size_t)col]; x1 = a[3 * (size_t)col + 1]; x2 = a[3 * (size_t)col + 2];
-    if (b) { x0 += beta * b[3 * (size_t)col]; x1 += beta * b[3 * (size_t)col + 1]; x2 += beta * b[3 * (size_t)col + 2]; }
+    if (nogather) { x0 = col; x1 = 1.0; x2 = 2.0; return; }  // measurement aid: stream-only ceiling
+    const double4 xv = reinterpret_cast<const double4*>(x4)[col];
+    x0 = xv.x; x1 = xv.y; x2 = xv.z;
   };
   for (uint32_t c = 0; c < nrec && c < (uint32_t)kStages; ++c) issue(c);
   if (nrec == 0 || t0 == t1) { wp.pos = base + nrec; return; }
@@ -595,9 +589,17 @@ __device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restri
     const double* rec_n = nullptr;
     double n0 = 0.0, n1 = 0.0, n2 = 0.0;
     if (c + 1 < nrec) { rec_n = wait_rec(c + 1); gather(rec_n, ce + lane, n0, n1, n2); }
-    const double v0 = rec[lane] * x0 + rec[32 + lane] * x1 + rec[64 + lane] * x2;
-    const double v1 = rec[96 + lane] * x0 + rec[128 + lane] * x1 + rec[160 + lane] * x2;
-    const double v2 = rec[192 + lane] * x0 + rec[224 + lane] * x1 + rec[256 + lane] * x2;
+    double v0, v1, v2;
+    if (kBlk == 6) {
+      const double b0 = rec[lane], b1 = rec[32 + lane], b2 = rec[64 + lane], b3 = rec[96 + lane], b4 = rec[128 + lane], b5 = rec[160 + lane];
+      v0 = b0 * x0 + b1 * x1 + b2 * x2;
+      v1 = b1 * x0 + b3 * x1 + b4 * x2;
+      v2 = b2 * x0 + b4 * x1 + b5 * x2;
+    } else {
+      v0 = rec[lane] * x0 + rec[32 + lane] * x1 + rec[64 + lane] * x2;
+      v1 = rec[96 + lane] * x0 + rec[128 + lane] * x1 + rec[160 + lane] * x2;
+      v2 = rec[192 + lane] * x0 + rec[224 + lane] * x1 + rec[256 + lane] * x2;
+    }
     // this record's slot can be refilled as soon as every lane has read it
     __syncwarp();
     if (c + kStages < nrec) issue(c + kStages);
@@ -617,9 +619,10 @@ __device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restri
   wp.pos = base + nrec;
 }
 
+template <int kBlk>
 __global__ void __launch_bounds__(kBlock)
 k_spmv(uint32_t num_warps, uint64_t H, uint32_t warp_span, const uint32_t* __restrict__ warp_seg_ptr, const uint32_t* __restrict__ task_begin,
-       const uint32_t* __restrict__ task_len, const double* __restrict__ recs, const double* __restrict__ x, double* __restrict__ ypart,
+       const uint32_t* __restrict__ task_len, const double* __restrict__ recs, const double* __restrict__ x4, double* __restrict__ ypart,
        const DevScalars* sc, int check_done) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   if (check_done == 1 && sc->pcg_done) return;
@@ -627,12 +630,12 @@ k_spmv(uint32_t num_warps, uint64_t H, uint32_t warp_span, const uint32_t* __res
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (gw >= num_warps) return;
   WarpPipe wp;
-  pipe_init(wp, smem_raw);
+  pipe_init<kBlk>(wp, smem_raw);
   const uint64_t lo = (uint64_t)gw * warp_span, hi = min(H, lo + warp_span);
-  spmv_stream(wp, recs, lo, hi, warp_seg_ptr[gw], warp_seg_ptr[gw + 1], task_begin, task_len, x, nullptr, check_done == 2 ? -12345.0 : 0.0,
-              [&](uint32_t t, double y0, double y1, double y2) {
-                if (lane == 0) { ypart[3 * (size_t)t] = y0; ypart[3 * (size_t)t + 1] = y1; ypart[3 * (size_t)t + 2] = y2; }
-              });
+  spmv_stream<kBlk>(wp, recs, lo, hi, warp_seg_ptr[gw], warp_seg_ptr[gw + 1], task_begin, task_len, x4, check_done == 2,
+                    [&](uint32_t t, double y0, double y1, double y2) {
+                      if (lane == 0) { ypart[3 * (size_t)t] = y0; ypart[3 * (size_t)t + 1] = y1; ypart[3 * (size_t)t + 2] = y2; }
+                    });
 }
 
 // y_i = Dblk_i x_i + sum of the row's task partials (+ shard-local only: the diagonal part is
@@ -646,7 +649,7 @@ __global__ void k_spmv_finish(uint32_t N, const uint32_t* __restrict__ node_task
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   double v[1] = {0.0};
   if (i < N) {
-    double xi[3] = {x[3 * (size_t)i], x[3 * (size_t)i + 1], x[3 * (size_t)i + 2]};
+    double xi[3] = {x[4 * (size_t)i], x[4 * (size_t)i + 1], x[4 * (size_t)i + 2]};  // x is a gathered vector: stride 4
     double yi[3] = {0.0, 0.0, 0.0};
     if (Dblk) sym_mul_vec(Dblk + 6 * (size_t)i, xi, yi);
     if (ysum) { yi[0] += ysum[3 * (size_t)i]; yi[1] += ysum[3 * (size_t)i + 1]; yi[2] += ysum[3 * (size_t)i + 2]; }
@@ -678,13 +681,13 @@ __global__ void k_pcg_update(uint32_t N, const double* __restrict__ Minv, const 
     double ri[3], zi[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      x[3 * (size_t)i + c] += alpha * p[3 * (size_t)i + c];
+      x[3 * (size_t)i + c] += alpha * p[4 * (size_t)i + c];
       ri[c] = r[3 * (size_t)i + c] - alpha * y[3 * (size_t)i + c];
       r[3 * (size_t)i + c] = ri[c];
     }
     sym_mul_vec(Minv + 6 * (size_t)i, ri, zi);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { z[3 * (size_t)i + c] = zi[c]; v[0] += ri[c] * zi[c]; v[1] += ri[c] * ri[c]; }
+    for (int c = 0; c < 3; ++c) { z[4 * (size_t)i + c] = zi[c]; v[0] += ri[c] * zi[c]; v[1] += ri[c] * ri[c]; }
   }
   double tot[2];
   if (grid_sum<2>(v, slots, counter, tot) && threadIdx.x == 0) {
@@ -696,7 +699,7 @@ __global__ void k_pcg_update(uint32_t N, const double* __restrict__ Minv, const 
   }
 }
 
-// PCG step 3: p = z + beta p.
+// PCG step 3: p = z + beta p (both stride 4; the pad element stays 0).
 __global__ void k_pcg_direction(uint32_t n3, const double* __restrict__ z, double* __restrict__ p, const DevScalars* sc) {
   if (sc->pcg_done) return;
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -707,16 +710,18 @@ __global__ void k_pcg_direction(uint32_t n3, const double* __restrict__ z, doubl
 // The whole block-Jacobi PCG solve as ONE persistent cooperative kernel (one launch per linear
 // solve, convergence decided on the device, two grid barriers per CG step).
 //
-// Work distribution: the half-edge array is cut into num_warps equal contiguous ranges (one per
-// resident warp, grid = SMs x occupancy), each range into segments (range ^ row).  Per CG step:
-//   phase A  every warp streams its range: ypart[seg] = sum B x[col], with the search direction
-//            formed on the fly, x_j = z_j + beta p_old_j (so no separate "p = z + beta p" pass and
-//            no barrier for it).  The warp that completes the LAST segment of a row (per-row
-//            arrival counter) finishes the row in fixed segment order: y_i = D_i p_i + sum parts,
-//            stores p_new_i, y_i and accumulates p_i.y_i.                      -> barrier 1
-//   phase C  alpha from the block slots (every block adds them in the same order: bitwise equal
-//            everywhere), x += alpha p, r -= alpha y, z = Minv r, slots of r.z and r.r -> barrier 2
-// Epilogue: y = Ht x with the UNDAMPED diagonal, for the model cost change.
+// CG in the Chronopoulos-Gear arrangement: the matrix is applied to the preconditioned residual z (ONE gathered
+// vector, one aligned 32 B sector per half-edge), the search direction and its image follow by recurrence
+// (p = z + beta p, q = s + beta q, q = A p), and both inner products of a step come out of the same pass:
+//   phase A  every warp streams its range of records: spart[seg] = sum blk z[col].  The warp that owns a row
+//            (static owner = the warp holding the row's first segment) finishes it in fixed segment order:
+//            s_i = D_i z_i + sum parts, stores s_i and accumulates gamma += r_i.z_i, delta += z_i.s_i.   -> barrier 1
+//   phase C  gamma, delta from the block slots (every block adds them in the same order: bitwise equal
+//            everywhere);  beta = gamma/gamma_old,  alpha = gamma / (delta - beta gamma / alpha_old);
+//            p = z + beta p, q = s + beta q, x += alpha p, r -= alpha q, z = Minv r, slots of r.r          -> barrier 2
+// No epilogue pass: the model decrease needs x.H x = x.(b - r) - x.Lam x, all per-view quantities (k_apply_step).
+// Work distribution: the half-edge array is cut into num_warps equal contiguous ranges (one per resident warp,
+// grid = SMs x occupancy), each range into segments (range ^ row).
 // Vectors written inside the kernel are never accessed through __restrict__/read-only paths.
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 16;
@@ -727,10 +732,10 @@ struct PcgParams {
   uint64_t H;
   double rtol2;
   const uint32_t *warp_seg_ptr, *seg_row, *seg_begin, *seg_len, *node_seg_ptr, *iso;
-  const double *val, *Dblk, *Minv, *Hd;
-  double *x, *r, *z, *p0, *p1, *y, *ypart;
+  const double *val, *Dblk, *Minv;
+  double *x, *r, *z, *p, *q, *s, *ypart;
   unsigned* row_cnt;
-  double *slotsA, *slotsB, *slotsC;
+  double *slotsA, *slotsB;
   DevScalars* sc;
   unsigned long long* prof;  // optional [8] phase timers in ns, accumulated by block 0 (measurement aid)
   // edge-sharded multi-GPU (world > 1): every rank's exchange block, mapped into this process over NVLink
@@ -784,15 +789,26 @@ __device__ __forceinline__ void all_blocks_sum2(const double* slots, double* o0,
   __syncthreads();
 }
 
-// One SpMV pass over this warp's range.  x_j = a_j + beta b_j (b may be null).  Returns (per lane)
-// the accumulated sum over the rows this lane finished of x_i . y_i.
-__device__ __forceinline__ double spmv_pass(const PcgParams& P, WarpPipe& wp, const double* a, const double* b, double beta, const double* diag,
-                                            double* xnew_out, double* y_out, double* ylocal_out = nullptr) {
+// Row i once its off-diagonal sum (y0,y1,y2) is complete: s_i = D_i z_i + y, store, inner products.
+__device__ __forceinline__ void finish_row(const PcgParams& P, uint32_t row, double y0, double y1, double y2, double& gamma, double& delta) {
+  const double4 zv = reinterpret_cast<const double4*>(P.z)[row];
+  const double zi[3] = {zv.x, zv.y, zv.z};
+  double d[3];
+  sym_mul_vec(P.Dblk + 6 * (size_t)row, zi, d);
+  y0 += d[0]; y1 += d[1]; y2 += d[2];
+  P.s[3 * (size_t)row] = y0; P.s[3 * (size_t)row + 1] = y1; P.s[3 * (size_t)row + 2] = y2;
+  gamma += P.r[3 * (size_t)row] * zi[0] + P.r[3 * (size_t)row + 1] * zi[1] + P.r[3 * (size_t)row + 2] * zi[2];
+  delta += zi[0] * y0 + zi[1] * y1 + zi[2] * y2;
+}
+
+// One SpMV pass over this warp's range, s = (Ht + Lam) z.  Accumulates (per lane) gamma = r.z and delta = z.s over
+// the rows this lane finished.
+template <int kBlk>
+__device__ __forceinline__ void spmv_pass(const PcgParams& P, WarpPipe& wp, double& gamma, double& delta, double* ylocal_out = nullptr) {
   // ylocal_out != null (multi-GPU): only the shard-local off-diagonal row sums are produced, into the exchange
-  // buffer; diagonal, direction and dot product follow after the cross-GPU reduction (exchange_finish).
+  // buffer; diagonal and inner products follow after the cross-GPU reduction (exchange_finish).
   const int lane = threadIdx.x & 31;
   const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  double dot = 0.0;
   if (gwarp < P.num_warps) {
     const uint64_t lo = (uint64_t)gwarp * P.warp_span, hi = min(P.H, lo + P.warp_span);
     // Rows are finished by a STATIC owner -- the warp holding the row's first segment -- so every
@@ -814,27 +830,20 @@ __device__ __forceinline__ double spmv_pass(const PcgParams& P, WarpPipe& wp, co
           while (*cnt != s1 - s0 - 1) { }
           __threadfence();
           *cnt = 0u;
-          for (uint32_t q = s0 + 1; q < s1; ++q) {
-            my0 += __ldcg(P.ypart + 3 * (size_t)q); my1 += __ldcg(P.ypart + 3 * (size_t)q + 1); my2 += __ldcg(P.ypart + 3 * (size_t)q + 2);
+          for (uint32_t k = s0 + 1; k < s1; ++k) {
+            my0 += __ldcg(P.ypart + 3 * (size_t)k); my1 += __ldcg(P.ypart + 3 * (size_t)k + 1); my2 += __ldcg(P.ypart + 3 * (size_t)k + 2);
           }
         }
         if (ylocal_out) {
           ylocal_out[3 * (size_t)row] = my0; ylocal_out[3 * (size_t)row + 1] = my1; ylocal_out[3 * (size_t)row + 2] = my2;
         } else {
-          double xi[3] = {a[3 * (size_t)row], a[3 * (size_t)row + 1], a[3 * (size_t)row + 2]};
-          if (b) { xi[0] += beta * b[3 * (size_t)row]; xi[1] += beta * b[3 * (size_t)row + 1]; xi[2] += beta * b[3 * (size_t)row + 2]; }
-          double d[3];
-          sym_mul_vec(diag + 6 * (size_t)row, xi, d);
-          my0 += d[0]; my1 += d[1]; my2 += d[2];
-          y_out[3 * (size_t)row] = my0; y_out[3 * (size_t)row + 1] = my1; y_out[3 * (size_t)row + 2] = my2;
-          if (xnew_out) { xnew_out[3 * (size_t)row] = xi[0]; xnew_out[3 * (size_t)row + 1] = xi[1]; xnew_out[3 * (size_t)row + 2] = xi[2]; }
-          dot += xi[0] * my0 + xi[1] * my1 + xi[2] * my2;
+          finish_row(P, row, my0, my1, my2, gamma, delta);
         }
       }
       nbatch = 0;
       __syncwarp();
     };
-    spmv_stream(wp, P.val, lo, hi, t0, t1, P.seg_begin, P.seg_len, a, b, beta, [&](uint32_t t, double y0, double y1, double y2) {
+    spmv_stream<kBlk>(wp, P.val, lo, hi, t0, t1, P.seg_begin, P.seg_len, P.z, false, [&](uint32_t t, double y0, double y1, double y2) {
       const uint32_t rowf = P.seg_row[t];
       if (rowf & kSideBit) {  // continuation of a row owned by an earlier warp
         if (lane == 0) {
@@ -849,28 +858,18 @@ __device__ __forceinline__ double spmv_pass(const PcgParams& P, WarpPipe& wp, co
     });
     if (nbatch) flush();
   }
-  // views without any half-edge: y_i = D_i x_i  (multi-GPU: their exchange slots stay zero, nothing to do)
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; !ylocal_out && k < P.n_iso; k += gridDim.x * blockDim.x) {
-    const uint32_t row = P.iso[k];
-    double xi[3] = {a[3 * (size_t)row], a[3 * (size_t)row + 1], a[3 * (size_t)row + 2]};
-    if (b) { xi[0] += beta * b[3 * (size_t)row]; xi[1] += beta * b[3 * (size_t)row + 1]; xi[2] += beta * b[3 * (size_t)row + 2]; }
-    double d[3];
-    sym_mul_vec(diag + 6 * (size_t)row, xi, d);
-    y_out[3 * (size_t)row] = d[0]; y_out[3 * (size_t)row + 1] = d[1]; y_out[3 * (size_t)row + 2] = d[2];
-    if (xnew_out) { xnew_out[3 * (size_t)row] = xi[0]; xnew_out[3 * (size_t)row + 1] = xi[1]; xnew_out[3 * (size_t)row + 2] = xi[2]; }
-    dot += xi[0] * d[0] + xi[1] * d[1] + xi[2] * d[2];
-  }
-  return dot;
+  // views without any half-edge: s_i = D_i z_i  (multi-GPU: their exchange slots stay zero, nothing to do)
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; !ylocal_out && k < P.n_iso; k += gridDim.x * blockDim.x)
+    finish_row(P, P.iso[k], 0.0, 0.0, 0.0, gamma, delta);
 }
 
 // Fused cross-GPU reduction of the partial matvec, inside the persistent kernel (no NCCL call, no kernel
 // boundary): publish "my partial sums for step `seq` are complete" with a system-scope release, wait for every
 // peer's flag, then every rank adds the partial vectors of ALL ranks in rank order straight out of peer memory
-// over NVLink (bitwise identical result everywhere) and finishes the row: y_i = D_i x_i + sum, direction, dot.
+// over NVLink (bitwise identical result everywhere) and finishes the row: s_i = D_i z_i + sum, inner products.
 // Buffer reuse is safe with two buffers: a rank can only reach step seq+2 after every peer published seq+1,
 // i.e. after every peer finished reading step seq.
-__device__ __forceinline__ double exchange_finish(const PcgParams& P, cg::grid_group& grid, unsigned seq, const double* a, const double* b,
-                                                  double beta, const double* diag, double* xnew_out, double* y_out) {
+__device__ __forceinline__ void exchange_finish(const PcgParams& P, cg::grid_group& grid, unsigned seq, double& gamma, double& delta) {
   grid.sync();  // all local row sums of this step are in my exchange buffer
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     __threadfence_system();
@@ -889,108 +888,99 @@ __device__ __forceinline__ double exchange_finish(const PcgParams& P, cg::grid_g
   }
   __syncthreads();
   const size_t off = (size_t)(seq & 1u) * 3 * P.N;
-  double dot = 0.0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.N; i += gridDim.x * blockDim.x) {
     double y0 = 0.0, y1 = 0.0, y2 = 0.0;
     for (int r = 0; r < P.world; ++r) {
       const double* src = P.peer_y[r] + off + 3 * (size_t)i;
       y0 += __ldcv(src); y1 += __ldcv(src + 1); y2 += __ldcv(src + 2);
     }
-    double xi[3] = {a[3 * (size_t)i], a[3 * (size_t)i + 1], a[3 * (size_t)i + 2]};
-    if (b) { xi[0] += beta * b[3 * (size_t)i]; xi[1] += beta * b[3 * (size_t)i + 1]; xi[2] += beta * b[3 * (size_t)i + 2]; }
-    double d[3];
-    sym_mul_vec(diag + 6 * (size_t)i, xi, d);
-    y0 += d[0]; y1 += d[1]; y2 += d[2];
-    y_out[3 * (size_t)i] = y0; y_out[3 * (size_t)i + 1] = y1; y_out[3 * (size_t)i + 2] = y2;
-    if (xnew_out) { xnew_out[3 * (size_t)i] = xi[0]; xnew_out[3 * (size_t)i + 1] = xi[1]; xnew_out[3 * (size_t)i + 2] = xi[2]; }
-    dot += xi[0] * y0 + xi[1] * y1 + xi[2] * y2;
+    finish_row(P, i, y0, y1, y2, gamma, delta);
   }
-  return dot;
 }
 
+template <int kBlk>
 __global__ void __launch_bounds__(kBlock) k_pcg_persistent(PcgParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cg::grid_group grid = cg::this_grid();
   WarpPipe wp;
-  pipe_init(wp, smem_raw);
+  pipe_init<kBlk>(wp, smem_raw);
   __shared__ double sm_red[kWarpsPerBlock];
   __shared__ double sm_b;
   __shared__ double sm_b2[2];
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-  double rz = P.sc->rz;
   const double bb = P.sc->bb;
-  double rr = bb, beta = 0.0;
+  double rr = bb, beta = 0.0, alpha = 0.0, gamma_old = 0.0;
   int iter = 0, breakdown = 0;
   bool done = P.sc->pcg_done != 0;
-  double* pold = P.p1;  // zero-filled by k_prepare_solve: the first direction is p = z
-  double* pnew = P.p0;
   const bool multi = P.world > 1;
   unsigned seq = multi ? (unsigned)P.sc->xseq : 0u;  // exchange sequence number, continues across launches
   double* my_y = multi ? P.peer_y[P.rank] : nullptr;
   while (!done) {
-    // ---- phase A: y = (Ht + Lam) p, p = z + beta p_old formed on the fly, p.y ----------------
+    // ---- phase A: s = (Ht + Lam) z, gamma = r.z, delta = z.s ---------------------------------
     const bool prof = P.prof != nullptr && gtid == 0;
     unsigned long long tA = 0, tB = 0, tC = 0, tD = 0, tE = 0, tF = 0, tG = 0;
     if (prof) tA = gtimer();
-    double dot;
-    if (!multi) dot = spmv_pass(P, wp, P.z, pold, beta, P.Dblk, pnew, P.y);
+    double g_part = 0.0, d_part = 0.0;
+    if (!multi) spmv_pass<kBlk>(P, wp, g_part, d_part);
     else {
       ++seq;
-      spmv_pass(P, wp, P.z, pold, beta, P.Dblk, pnew, P.y, my_y + (size_t)(seq & 1u) * 3 * P.N);
-      dot = exchange_finish(P, grid, seq, P.z, pold, beta, P.Dblk, pnew, P.y);
+      spmv_pass<kBlk>(P, wp, g_part, d_part, my_y + (size_t)(seq & 1u) * 3 * P.N);
+      exchange_finish(P, grid, seq, g_part, d_part);
     }
     if (prof) tB = gtimer();
-    const double bs = block_sum_to_thread0(dot, sm_red);
-    if (threadIdx.x == 0) __stcg(P.slotsA + blockIdx.x, bs);
+    const double bs0 = block_sum_to_thread0(g_part, sm_red);
+    const double bs1 = block_sum_to_thread0(d_part, sm_red);
+    if (threadIdx.x == 0) { __stcg(P.slotsA + 2 * (size_t)blockIdx.x, bs0); __stcg(P.slotsA + 2 * (size_t)blockIdx.x + 1, bs1); }
     grid.sync();
     if (prof) tC = gtimer();
-    const double pAp = all_blocks_sum(P.slotsA, 1, 0, &sm_b);
+    double gamma, delta;
+    all_blocks_sum2(P.slotsA, &gamma, &delta, sm_b2);
     if (prof) tD = gtimer();
+    // p = z + beta p  =>  p.Ap = delta - beta^2 (p_old.A p_old) = delta - beta gamma / alpha_old
+    beta = (iter == 0) ? 0.0 : gamma / gamma_old;
+    const double pAp = (iter == 0) ? delta : delta - beta * gamma / alpha;
     if (!(pAp > 0.0) || !isfinite(pAp)) { breakdown = 1; break; }
-    const double alpha = rz / pAp;
-    // ---- phase C: x += alpha p ; r -= alpha y ; z = Minv r ; r.z, r.r -------------------------
-    double v0 = 0.0, v1 = 0.0;
+    alpha = gamma / pAp;
+    gamma_old = gamma;
+    // ---- phase C: p, q, x, r, z ; r.r ----------------------------------------------------------
+    double v1 = 0.0;
     for (uint32_t i = gtid; i < P.N; i += gthreads) {
-      double ri[3], zi[3];
+      const double4 zv = reinterpret_cast<const double4*>(P.z)[i];
+      const double4 pv = reinterpret_cast<const double4*>(P.p)[i];
+      const double zi[3] = {zv.x, zv.y, zv.z};
+      const double po[3] = {pv.x, pv.y, pv.z};
+      double ri[3], zn[3], pn[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        P.x[3 * (size_t)i + c] += alpha * pnew[3 * (size_t)i + c];
-        ri[c] = P.r[3 * (size_t)i + c] - alpha * P.y[3 * (size_t)i + c];
+        pn[c] = zi[c] + beta * po[c];
+        const double qn = P.s[3 * (size_t)i + c] + beta * P.q[3 * (size_t)i + c];
+        P.q[3 * (size_t)i + c] = qn;
+        P.x[3 * (size_t)i + c] += alpha * pn[c];
+        ri[c] = P.r[3 * (size_t)i + c] - alpha * qn;
         P.r[3 * (size_t)i + c] = ri[c];
+        v1 += ri[c] * ri[c];
       }
-      sym_mul_vec(P.Minv + 6 * (size_t)i, ri, zi);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { P.z[3 * (size_t)i + c] = zi[c]; v0 += ri[c] * zi[c]; v1 += ri[c] * ri[c]; }
+      sym_mul_vec(P.Minv + 6 * (size_t)i, ri, zn);
+      reinterpret_cast<double4*>(P.p)[i] = make_double4(pn[0], pn[1], pn[2], 0.0);
+      reinterpret_cast<double4*>(P.z)[i] = make_double4(zn[0], zn[1], zn[2], 0.0);
     }
     if (prof) tE = gtimer();
-    const double b0 = block_sum_to_thread0(v0, sm_red);
     const double b1 = block_sum_to_thread0(v1, sm_red);
-    if (threadIdx.x == 0) { __stcg(P.slotsB + 2 * (size_t)blockIdx.x, b0); __stcg(P.slotsB + 2 * (size_t)blockIdx.x + 1, b1); }
+    if (threadIdx.x == 0) __stcg(P.slotsB + blockIdx.x, b1);
     grid.sync();
     if (prof) tF = gtimer();
-    double rz_new;
-    all_blocks_sum2(P.slotsB, &rz_new, &rr, sm_b2);
+    rr = all_blocks_sum(P.slotsB, 1, 0, &sm_b);
     if (prof) {
       tG = gtimer();
       P.prof[0] += tB - tA; P.prof[1] += tC - tB; P.prof[2] += tD - tC; P.prof[3] += tE - tD; P.prof[4] += tF - tE; P.prof[5] += tG - tF;
       P.prof[6] += 1;
     }
     ++iter;
-    beta = rz_new / rz;
-    rz = rz_new;
-    double* t = pold; pold = pnew; pnew = t;
     if (rr <= P.rtol2 * bb || iter >= P.max_iter || !isfinite(rr)) done = true;
-  }
-  // ---- epilogue: y = Ht x (undamped diagonal) for the model cost change --------------------------
-  if (!multi) spmv_pass(P, wp, P.x, nullptr, 0.0, P.Hd, nullptr, P.y);
-  else {
-    ++seq;
-    spmv_pass(P, wp, P.x, nullptr, 0.0, P.Hd, nullptr, P.y, my_y + (size_t)(seq & 1u) * 3 * P.N);
-    exchange_finish(P, grid, seq, P.x, nullptr, 0.0, P.Hd, nullptr, P.y);
   }
   if (gtid == 0) {
     P.sc->xseq = (int)seq;
-    P.sc->rz = rz; P.sc->rr = rr; P.sc->beta = beta;
+    P.sc->rz = gamma_old; P.sc->rr = rr; P.sc->beta = beta; P.sc->alpha = alpha;
     P.sc->pcg_iter = iter; P.sc->pcg_done = 1; P.sc->pcg_breakdown = breakdown;
   }
 }
@@ -1010,7 +1000,15 @@ constexpr int kNB = 32;
 
 // The right-hand side rides along as an EXTRA ROW of the matrix (row index n, inside the padding): factoring
 // [A b; b^T beta] = [L 0; y^T *][L^T y; 0 *] leaves y = L^-1 b in that row, so the forward substitution costs nothing.
-__global__ void k_dense_assemble(uint64_t H, uint32_t N, uint32_t np, const uint32_t* __restrict__ he_row, const uint32_t* __restrict__ he_col,
+// Entry (r, c) of the stored off-diagonal block of half-edge h (blk = 6: packed symmetric; 9: row-major).
+__device__ __forceinline__ double blk_entry(const double* recs, uint64_t h, int blk, int r, int c) {
+  int k;
+  if (blk == 6) { const int a = r < c ? r : c, b2 = r < c ? c : r; k = a * 3 - a * (a - 1) / 2 + (b2 - a); }
+  else k = 3 * r + c;
+  return recs[blk_index(h, k, blk * 32 + 16)];
+}
+
+__global__ void k_dense_assemble(uint64_t H, uint32_t N, uint32_t np, int blk, const uint32_t* __restrict__ he_row, const uint32_t* __restrict__ he_col,
                                  const double* __restrict__ recs, const double* __restrict__ Dblk, const double* __restrict__ rhs,
                                  double* __restrict__ A) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1021,7 +1019,7 @@ __global__ void k_dense_assemble(uint64_t H, uint32_t N, uint32_t np, const uint
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) A[(size_t)(3 * col + c) * np + 3 * row + r] = recs[blk_index(t, 3 * r + c)];
+        for (int c = 0; c < 3; ++c) A[(size_t)(3 * col + c) * np + 3 * row + r] = blk_entry(recs, t, blk, r, c);
     }
   }
   if (t < N) {
@@ -1170,10 +1168,12 @@ __global__ void __launch_bounds__(kBlock) k_dense_cholesky_solve(uint32_t n, uin
   }
 }
 
-// After the solve (xt = tangent step, Hx = Ht xt without damping): Euclidean step
-// delta = Jl^-1 xt, candidate = omega + delta (Ceres updates the angle-axis vector additively);
-// reduce delta.g (= xt.gt), delta.H.delta (= xt.Hx), |delta|^2.
-__global__ void k_apply_step(uint32_t N, const double* __restrict__ node_JL, const double* __restrict__ xt, const double* __restrict__ Hx,
+// After the solve (xt = tangent step): parameter step delta = D^-1 xt, candidate = omega + delta (Ceres updates the
+// angle-axis vector additively) or, on the manifold, R <- R Exp(xt); reduces delta.g (= xt.gt),
+// delta.H.delta = xt.Ht.xt and |delta|^2.  The quadratic form needs no matrix pass: (Ht + Lam) xt = b - r with the
+// solver's residual r, so xt.Ht.xt = xt.(b - r) - xt.Lam.xt, Lam_i = Dblk_i - Hd_i -- all per-view quantities.
+__global__ void k_apply_step(uint32_t N, const double* __restrict__ node_JL, const double* __restrict__ xt, const double* __restrict__ bvec,
+                             const double* __restrict__ res, const double* __restrict__ Dblk, const double* __restrict__ Hd,
                              const double* __restrict__ gt, const double* __restrict__ omega, double* __restrict__ cand,
                              double* __restrict__ delta_out, double* slots, unsigned* counter, DevScalars* sc, int manifold) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1184,30 +1184,41 @@ __global__ void k_apply_step(uint32_t N, const double* __restrict__ node_JL, con
     for (int k = 0; k < 9; ++k) J[k] = node_JL[9 * (size_t)i + k];
     inv3(J, Ji);
     const double t0 = xt[3 * (size_t)i], t1 = xt[3 * (size_t)i + 1], t2 = xt[3 * (size_t)i + 2];
+    double d[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) d[c] = Ji[3 * c] * t0 + Ji[3 * c + 1] * t1 + Ji[3 * c + 2] * t2;
+    if (delta_out) { delta_out[3 * (size_t)i] = d[0]; delta_out[3 * (size_t)i + 1] = d[1]; delta_out[3 * (size_t)i + 2] = d[2]; }
     if (manifold) {
-      // x (+) delta = [sin|d| d/|d|, cos|d|] (x) x with d = xt / 2, i.e. R <- Exp(xt) R; the state stays an angle-axis vector
-      // (principal branch of the product quaternion).  |step| in the ambient quaternion space = 2 sin(|d| / 2) per view.
+      // x (+) delta = [sin|d| d/|d|, cos|d|] (x) x, a left rotation by 2 delta = R xt, i.e. R <- R Exp(xt); the state stays
+      // an angle-axis vector (principal branch of the product quaternion).  |step| in the ambient quaternion space =
+      // 2 sin(|delta| / 2) per view, |delta| = |xt| / 2.
       const Q4 qd = aa_to_quat(t0, t1, t2);
       const Q4 qo = aa_to_quat(omega[3 * (size_t)i], omega[3 * (size_t)i + 1], omega[3 * (size_t)i + 2]);
       double e[3], th2, cc;
-      quat_log(qmul(qd, qo), e, &th2, &cc);
+      quat_log(qmul(qo, qd), e, &th2, &cc);
       const double dn = 0.5 * sqrt(t0 * t0 + t1 * t1 + t2 * t2);
       const double sh = sin(0.5 * dn);
       if (cand) { cand[3 * (size_t)i] = e[0]; cand[3 * (size_t)i + 1] = e[1]; cand[3 * (size_t)i + 2] = e[2]; }
-      if (delta_out) { delta_out[3 * (size_t)i] = 0.5 * t0; delta_out[3 * (size_t)i + 1] = 0.5 * t1; delta_out[3 * (size_t)i + 2] = 0.5 * t2; }
       v[2] = 4.0 * sh * sh;
       if (!isfinite(dn)) v[3] = 1.0;
-    } else
+    } else {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const double d = Ji[3 * c] * t0 + Ji[3 * c + 1] * t1 + Ji[3 * c + 2] * t2;
-      if (cand) cand[3 * (size_t)i + c] = omega[3 * (size_t)i + c] + d;
-      if (delta_out) delta_out[3 * (size_t)i + c] = d;
-      v[2] += d * d;
-      if (!isfinite(d)) v[3] = 1.0;
+      for (int c = 0; c < 3; ++c) {
+        if (cand) cand[3 * (size_t)i + c] = omega[3 * (size_t)i + c] + d[c];
+        v[2] += d[c] * d[c];
+        if (!isfinite(d[c])) v[3] = 1.0;
+      }
     }
     if (gt) v[0] = t0 * gt[3 * (size_t)i] + t1 * gt[3 * (size_t)i + 1] + t2 * gt[3 * (size_t)i + 2];
-    if (Hx) v[1] = t0 * Hx[3 * (size_t)i] + t1 * Hx[3 * (size_t)i + 1] + t2 * Hx[3 * (size_t)i + 2];
+    if (bvec) {
+      const double t[3] = {t0, t1, t2};
+      double lam[6], lx[3];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) lam[k] = Dblk[6 * (size_t)i + k] - Hd[6 * (size_t)i + k];
+      sym_mul_vec(lam, t, lx);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[1] += t[c] * (bvec[3 * (size_t)i + c] - (res ? res[3 * (size_t)i + c] : 0.0) - lx[c]);
+    }
   }
   double tot[4];
   if (grid_sum<4>(v, slots, counter, tot) && threadIdx.x == 0) {
@@ -1236,18 +1247,14 @@ __global__ void k_eval_edges(uint64_t E, const uint32_t* __restrict__ ei, const 
   else edge_terms<true, 0>(qi, qj, qm, u, loss, et);
   if (r) for (int t = 0; t < 3; ++t) r[3 * k + t] = et.r[t];
   if (rho) for (int t = 0; t < 3; ++t) rho[3 * k + t] = et.rho[t];
-  if (Jj) {  // d r / d omega_j = A Jl(omega_j)
-    const double* JL = node_JL + 9 * (size_t)j;
+  // d r / d(parameters of view j) = B D_j,  d r / d(parameters of view i) = -B D_i
+  for (int side = 0; side < 2; ++side) {
+    double* out = side ? Jj : Ji;
+    if (!out) continue;
+    const double* D = node_JL + 9 * (size_t)(side ? j : i);
+    const double sgn = side ? 1.0 : -1.0;
     for (int rr = 0; rr < 3; ++rr)
-      for (int c = 0; c < 3; ++c) Jj[9 * k + 3 * rr + c] = et.A[3 * rr] * JL[c] + et.A[3 * rr + 1] * JL[3 + c] + et.A[3 * rr + 2] * JL[6 + c];
-  }
-  if (Ji) {  // d r / d omega_i = -A Q Jl(omega_i)
-    const double* JL = node_JL + 9 * (size_t)i;
-    double AQ[9];
-    for (int rr = 0; rr < 3; ++rr)
-      for (int c = 0; c < 3; ++c) AQ[3 * rr + c] = et.A[3 * rr] * et.Q[c] + et.A[3 * rr + 1] * et.Q[3 + c] + et.A[3 * rr + 2] * et.Q[6 + c];
-    for (int rr = 0; rr < 3; ++rr)
-      for (int c = 0; c < 3; ++c) Ji[9 * k + 3 * rr + c] = -(AQ[3 * rr] * JL[c] + AQ[3 * rr + 1] * JL[3 + c] + AQ[3 * rr + 2] * JL[6 + c]);
+      for (int c = 0; c < 3; ++c) out[9 * k + 3 * rr + c] = sgn * (et.B[3 * rr] * D[c] + et.B[3 * rr + 1] * D[3 + c] + et.B[3 * rr + 2] * D[6 + c]);
   }
 }
 
@@ -1270,13 +1277,14 @@ __global__ void k_eval_loss(uint64_t n, const double* __restrict__ s, DevLoss lo
 }
 
 // Tangent -> Euclidean export of the assembled system (API gsfm_ra_assemble).
-__global__ void k_export_blocks(uint64_t H, const uint32_t* __restrict__ he_row, const uint32_t* __restrict__ he_col, const double* __restrict__ val,
+__global__ void k_export_blocks(uint64_t H, int blk, const uint32_t* __restrict__ he_row, const uint32_t* __restrict__ he_col, const double* __restrict__ val,
                                 const double* __restrict__ node_JL, double* out_val, uint32_t* out_col) {
   const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= H) return;
   const uint32_t row = he_row[h], col = he_col[h] & ~kSideBit;
   double B[9], T[9];
-  for (int k = 0; k < 9; ++k) B[k] = val[blk_index(h, k)];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) B[3 * r + c] = blk_entry(val, h, blk, r, c);
   const double* Jr = node_JL + 9 * (size_t)row;
   const double* Jc = node_JL + 9 * (size_t)col;
   for (int r = 0; r < 3; ++r)
@@ -1300,7 +1308,7 @@ __global__ void k_export_nodes(uint32_t N, const double* __restrict__ Hd, const 
 }
 // v_out = Jl v (mode 0), Jl^T v (mode 1) [+ damp .* x2]
 __global__ void k_node_apply(uint32_t N, const double* __restrict__ node_JL, const double* __restrict__ v, int mode, const double* __restrict__ damp,
-                             const double* __restrict__ x2, double* out) {
+                             const double* __restrict__ x2, double* out, int out_stride) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const double* J = node_JL + 9 * (size_t)i;
@@ -1308,8 +1316,9 @@ __global__ void k_node_apply(uint32_t N, const double* __restrict__ node_JL, con
   for (int q = 0; q < 3; ++q) {
     double o = mode == 0 ? J[3 * q] * a + J[3 * q + 1] * b + J[3 * q + 2] * c : J[q] * a + J[3 + q] * b + J[6 + q] * c;
     if (damp) o += damp[3 * (size_t)i + q] * x2[3 * (size_t)i + q];
-    out[3 * (size_t)i + q] = o;
+    out[(size_t)out_stride * i + q] = o;
   }
+  if (out_stride == 4) out[4 * (size_t)i + 3] = 0.0;
 }
 
 // Sigma-consensus weights (rotation_estimator.cpp:378-418): w = (C3*2/sigma)(Gamma_tab[round(1000 r^2/(2 sigma^2))] - Gamma_k)
@@ -1476,7 +1485,7 @@ struct StreamHolder {
 // Per-device facts that are expensive to query: cached for the life of the process.
 struct DeviceInfo {
   bool ready = false;
-  int sm_count = 0, coop = 0, occ_k1 = 1, occ_k2 = 1;
+  int sm_count = 0, coop = 0, occ_k1 = 1, occ_k2[2] = {1, 1};  // occ_k2[0]: 6-double records, [1]: 9-double records
 };
 DeviceInfo g_device_info[64];
 
@@ -1565,6 +1574,8 @@ struct gsfm_ra_solver {
   uint64_t H = 0;       // half-edges of this shard (2E)
   int rank = 0, world = 1;
   int error_type = 4;
+  int blk = 6;          // doubles per stored off-diagonal block (6: symmetric Laplacian stencil, 9: general)
+  bool scalar_u = false;  // the whitening factor is a scalar multiple of the identity (types 2, 4, 5, 7, 8)
   gsfm_ra_options opt;
   DevLoss loss;
   int64_t launches = 0;
@@ -1594,8 +1605,8 @@ struct gsfm_ra_solver {
   DevBuf<double> part;
   int cur = 0;
   // PCG
-  DevBuf<double> scale, Dblk, Minv, x, r, z, p, p1, y, ypart, delta, dense_A, dense_work, dense_winv;
-  DevBuf<double> slots, slotsA, slotsB, slotsC;
+  DevBuf<double> scale, Dblk, Minv, x, r, z, p, q, sv, bvec, y, ypart, delta, dense_A, dense_work, dense_winv;  // z, p: stride 4
+  DevBuf<double> slots, slotsA, slotsB;
   DevBuf<unsigned> counter, row_cnt;
   DevBuf<DevScalars> sc;
   DevScalars* h_sc = nullptr;  // pinned
@@ -1636,17 +1647,24 @@ struct gsfm_ra_solver {
     return 0;
   }
 
+  int rec_doubles() const { return blk * 32 + 16; }
+  int smem_bytes() const { return spmv_smem_bytes(blk); }
   void launch_edges(int b, bool jacobian, double* val_out) {
-#define GSFM_LAUNCH_EDGES(JAC, RES, VAL)                                                                                                  \
-  k_edges<JAC, RES><<<pk1.grid, kBlock, 0, stream>>>(pk1.num_warps, H, pk1.warp_seg_ptr.p, pk1.seg_row.p, pk1.seg_begin.p, pk1.seg_len.p, he_col.p, \
-                                                     qij.p, U.p, node_q[b].p, loss, VAL, part.p)
-    if (manifold()) { if (jacobian) GSFM_LAUNCH_EDGES(true, 1, val_out); else GSFM_LAUNCH_EDGES(false, 1, nullptr); }
-    else { if (jacobian) GSFM_LAUNCH_EDGES(true, 0, val_out); else GSFM_LAUNCH_EDGES(false, 0, nullptr); }
+#define GSFM_LAUNCH_EDGES(JAC, RES, SCAL, VAL)                                                                                                  \
+  k_edges<JAC, RES, SCAL><<<pk1.grid, kBlock, 0, stream>>>(pk1.num_warps, H, pk1.warp_seg_ptr.p, pk1.seg_row.p, pk1.seg_begin.p, pk1.seg_len.p, \
+                                                           he_col.p, qij.p, U.p, node_q[b].p, loss, VAL, part.p)
+    if (manifold()) { if (jacobian) GSFM_LAUNCH_EDGES(true, 1, true, val_out); else GSFM_LAUNCH_EDGES(false, 1, true, nullptr); }
+    else if (scalar_u) { if (jacobian) GSFM_LAUNCH_EDGES(true, 0, true, val_out); else GSFM_LAUNCH_EDGES(false, 0, true, nullptr); }
+    else { if (jacobian) GSFM_LAUNCH_EDGES(true, 0, false, val_out); else GSFM_LAUNCH_EDGES(false, 0, false, nullptr); }
 #undef GSFM_LAUNCH_EDGES
   }
-  void launch_spmv(int b, const double* xin, int check_done) {
-    k_spmv<<<pk2.grid, kBlock, kSpmvSmemBytes, stream>>>(pk2.num_warps, H, pk2.span, pk2.warp_seg_ptr.p, pk2.seg_begin.p, pk2.seg_len.p, val[b].p,
-                                                         xin, ypart.p, sc.p, check_done);
+  void launch_spmv(int b, const double* x4, int check_done) {
+    if (blk == 6)
+      k_spmv<6><<<pk2.grid, kBlock, smem_bytes(), stream>>>(pk2.num_warps, H, pk2.span, pk2.warp_seg_ptr.p, pk2.seg_begin.p, pk2.seg_len.p, val[b].p,
+                                                            x4, ypart.p, sc.p, check_done);
+    else
+      k_spmv<9><<<pk2.grid, kBlock, smem_bytes(), stream>>>(pk2.num_warps, H, pk2.span, pk2.warp_seg_ptr.p, pk2.seg_begin.p, pk2.seg_len.p, val[b].p,
+                                                            x4, ypart.p, sc.p, check_done);
   }
 
   // ---- evaluation at omega[b]: node prep, K1 (or K1c), node finalize -------------------------
@@ -1674,7 +1692,7 @@ struct gsfm_ra_solver {
     return 0;
   }
 
-  // y = (Ht offdiag + diag_blocks) x on linearisation b (separate-kernel path).
+  // y = (Ht offdiag + diag_blocks) x on linearisation b (separate-kernel path); xin has stride 4, yout stride 3.
   int spmv(int b, const double* xin, double* yout, const double* diag_blocks) {
     launch_spmv(b, xin, 0);
     if (!sharded()) {
@@ -1695,9 +1713,9 @@ struct gsfm_ra_solver {
     P.N = N; P.num_warps = pk2.num_warps; P.n_iso = n_iso; P.max_iter = max_iter; P.H = H; P.rtol2 = rtol * rtol;
     P.warp_seg_ptr = pk2.warp_seg_ptr.p; P.seg_row = pk2.seg_row.p; P.seg_begin = pk2.seg_begin.p; P.seg_len = pk2.seg_len.p;
     P.node_seg_ptr = pk2.node_seg_ptr.p; P.iso = iso.p; P.warp_span = pk2.span;
-    P.val = val[b].p; P.Dblk = Dblk.p; P.Minv = Minv.p; P.Hd = Hd_p[b];
-    P.x = x.p; P.r = r.p; P.z = z.p; P.p0 = p.p; P.p1 = p1.p; P.y = y.p; P.ypart = ypart.p;
-    P.row_cnt = row_cnt.p; P.slotsA = slotsA.p; P.slotsB = slotsB.p; P.slotsC = slotsC.p; P.sc = sc.p; P.prof = prof_buf;
+    P.val = val[b].p; P.Dblk = Dblk.p; P.Minv = Minv.p;
+    P.x = x.p; P.r = r.p; P.z = z.p; P.p = p.p; P.q = q.p; P.s = sv.p; P.ypart = ypart.p;
+    P.row_cnt = row_cnt.p; P.slotsA = slotsA.p; P.slotsB = slotsB.p; P.sc = sc.p; P.prof = prof_buf;
     P.world = peers_connected ? world : 1; P.rank = rank;
     for (int r = 0; r < kMaxPeers; ++r) {
       P.peer_y[r] = (double*)peer_base[r];
@@ -1706,12 +1724,12 @@ struct gsfm_ra_solver {
     return P;
   }
 
-  // Block-Jacobi PCG on (Ht + Lam) xt = bt for linearisation b; on return (stream order) x = xt and
-  // y = Ht xt (undamped).  One cooperative launch; no host synchronisation.
+  // Block-Jacobi PCG on (Ht + Lam) xt = bt for linearisation b; on return (stream order) x = xt, r = the
+  // residual bt - (Ht + Lam) xt and bvec = bt.  One cooperative launch; no host synchronisation.
   int pcg_enqueue(int b, double mu, const double* user_damp, const double* user_b, double rtol, int max_iter) {
     k_prepare_solve<<<grid_for(N), kBlock, 0, stream>>>(N, mu, opt.min_lm_diagonal, opt.max_lm_diagonal, ediag[b].p, scale.p, node_JL[b].p,
-                                                         Hd_p[b], gt_p[b], user_damp, user_b, Dblk.p, Minv.p, x.p, r.p, z.p, p.p, p1.p, slots.p,
-                                                         counter.p, sc.p);
+                                                         Hd_p[b], gt_p[b], user_damp, user_b, Dblk.p, Minv.p, x.p, r.p, z.p, p.p, q.p, bvec.p,
+                                                         slots.p, counter.p, sc.p);
     launches += 1;
     if (opt.linear_solver == GSFM_RA_SOLVER_DENSE_CHOLESKY) {
       const uint32_t n = 3 * N, np = (n + 1 + kNB - 1) / kNB * kNB;  // room for the right-hand-side row
@@ -1722,7 +1740,7 @@ struct gsfm_ra_solver {
         RA_TRY(dense_winv.alloc((size_t)np * kNB));
       }
       CUDA_TRY(cudaMemsetAsync(dense_A.p, 0, (size_t)np * np * sizeof(double), stream));
-      k_dense_assemble<<<grid_for(std::max<uint64_t>(H, np)), kBlock, 0, stream>>>(H, N, np, he_row.p, he_col.p, val[b].p, Dblk.p, r.p, dense_A.p);
+      k_dense_assemble<<<grid_for(std::max<uint64_t>(H, np)), kBlock, 0, stream>>>(H, N, np, blk, he_row.p, he_col.p, val[b].p, Dblk.p, r.p, dense_A.p);
       uint32_t n_arg = n, np_arg = np;
       double* A_arg = dense_A.p; double* x_arg = x.p; double* wi_arg = dense_winv.p; double* w_arg = dense_work.p; DevScalars* sc_arg = sc.p;
       void* args[] = {&n_arg, &np_arg, &A_arg, &x_arg, &wi_arg, &w_arg, &sc_arg};
@@ -1731,18 +1749,19 @@ struct gsfm_ra_solver {
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dense_cholesky_solve, kBlock, 0));
       const unsigned grid = (unsigned)(sm_count * std::max(1, std::min(occ, 2)));
       CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_dense_cholesky_solve, dim3(grid), dim3(kBlock), args, 0, stream));
+      CUDA_TRY(cudaMemsetAsync(r.p, 0, 3ull * N * sizeof(double), stream));  // exact solve: residual 0
       launches += 2;
-      RA_TRY(spmv(b, x.p, y.p, Hd_p[b]));
       return 0;
     }
     if (cooperative && (!sharded() || peers_connected)) {
       PcgParams P = pcg_params(b, rtol, max_iter);
       void* args[] = {&P};
-      CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_pcg_persistent, dim3(pk2.grid), dim3(kBlock), args, kSpmvSmemBytes, stream));
+      const void* fn = (blk == 6) ? (const void*)k_pcg_persistent<6> : (const void*)k_pcg_persistent<9>;
+      CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(pk2.grid), dim3(kBlock), args, smem_bytes(), stream));
       launches += 1;
       return 0;
     }
-    // fallback (device without cooperative launch): separate kernels, polled
+    // fallback (device without cooperative launch, or NCCL exchange): textbook PCG from separate kernels, polled
     const int poll = 8;
     const double rtol2 = rtol * rtol;
     int enq = 0;
@@ -1759,14 +1778,13 @@ struct gsfm_ra_solver {
           launches += 2;
         }
         k_pcg_update<<<grid_for(N), kBlock, 0, stream>>>(N, Minv.p, p.p, y.p, x.p, r.p, z.p, rtol2, max_iter, slots.p, counter.p, sc.p);
-        k_pcg_direction<<<grid_for(3ull * N), kBlock, 0, stream>>>(3 * N, z.p, p.p, sc.p);
+        k_pcg_direction<<<grid_for(4ull * N), kBlock, 0, stream>>>(4 * N, z.p, p.p, sc.p);
         launches += 4;
       }
       CUDA_TRY(cudaGetLastError());
       RA_TRY(fetch_scalars());
       if (h_sc->pcg_done || enq >= max_iter) break;
     }
-    RA_TRY(spmv(b, x.p, y.p, Hd_p[b]));
     return 0;
   }
 
@@ -1789,10 +1807,13 @@ int device_info(int device, DeviceInfo** out) {
   if (!d.ready) {
     CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaDeviceGetAttribute(&d.coop, cudaDevAttrCooperativeLaunch, device));
-    CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpmvSmemBytes));
-    CUDA_TRY(cudaFuncSetAttribute(k_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpmvSmemBytes));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k1, k_edges<true, 0>, kBlock, 0));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2, k_pcg_persistent, kBlock, kSpmvSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(6)));
+    CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(9)));
+    CUDA_TRY(cudaFuncSetAttribute(k_spmv<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(6)));
+    CUDA_TRY(cudaFuncSetAttribute(k_spmv<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(9)));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k1, k_edges<true, 0, false>, kBlock, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2[0], k_pcg_persistent<6>, kBlock, spmv_smem_bytes(6)));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2[1], k_pcg_persistent<9>, kBlock, spmv_smem_bytes(9)));
     // keep freed blocks in the pool: the next solver reuses them
     cudaMemPool_t pool;
     CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -1834,6 +1855,8 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   s->opt = *options;
   s->rank = rank; s->world = world;
   s->error_type = prob->error_type;
+  s->blk = 6;
+  s->scalar_u = !(prob->error_type == GSFM_RA_ANGLE_AXIS_COVARIANCE || prob->error_type == GSFM_RA_ANGLE_AXIS_COV_INLIERS);
   RA_TRY(make_dev_loss(&options->loss, &s->loss));
   s->sm_count = di->sm_count;
   CUDA_TRY(cudaStreamCreateWithFlags(&s->stream_holder.s, cudaStreamNonBlocking));
@@ -1898,7 +1921,8 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   s->launches += 6;
 
   // ---- balanced partitions, one per kernel class, sized to exactly one resident wave of that kernel ----
-  s->cooperative = di->coop != 0 && di->occ_k2 > 0;
+  const int occ_k2 = di->occ_k2[s->blk == 6 ? 0 : 1];
+  s->cooperative = di->coop != 0 && occ_k2 > 0;
   auto make = [&](Partition& P, int blocks_per_sm) -> int {
     const uint64_t max_warps = (uint64_t)s->sm_count * std::max(1, blocks_per_sm) * kWarpsPerBlock;
     uint64_t per = (H + max_warps - 1) / max_warps;
@@ -1920,9 +1944,9 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
     return 0;
   };
   RA_TRY(make(s->pk1, di->occ_k1));
-  RA_TRY(make(s->pk2, di->occ_k2));
+  RA_TRY(make(s->pk2, occ_k2));
   // the cooperative grid must be fully resident; node loops are grid-strided so any size works
-  s->pk2.grid = std::min<uint32_t>(s->pk2.grid, (uint32_t)s->sm_count * std::max(1, di->occ_k2));
+  s->pk2.grid = std::min<uint32_t>(s->pk2.grid, (uint32_t)s->sm_count * std::max(1, occ_k2));
   lap("enqueue structure build");
 
   // ---- per half-edge constants (K0) and the solver's working set ---------------------------------
@@ -1935,23 +1959,24 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
     RA_TRY(s->omega[b].alloc(3ull * N));
     RA_TRY(s->node_q[b].alloc(4ull * N));
     RA_TRY(s->node_JL[b].alloc(9ull * N));
-    RA_TRY(s->val[b].alloc(nrec * kRecDoubles));
+    RA_TRY(s->val[b].alloc(nrec * s->rec_doubles()));
     // only the last (partial) record has lanes K1 never writes
-    CUDA_TRY(cudaMemsetAsync(s->val[b].p + (nrec - 1) * kRecDoubles, 0, kRecBytes, st));
+    CUDA_TRY(cudaMemsetAsync(s->val[b].p + (nrec - 1) * s->rec_doubles(), 0, (size_t)s->rec_doubles() * 8, st));
     RA_TRY(s->lin[b].alloc(9ull * N + 2));
     s->Hd_p[b] = s->lin[b].p;
     s->gt_p[b] = s->lin[b].p + 6ull * N;
     RA_TRY(s->ediag[b].alloc(3ull * N));
     CUDA_TRY(cudaMemsetAsync(s->omega[b].p, 0, 3ull * N * sizeof(double), st));
   }
-  k_embed_cols<<<grid_for(H), kBlock, 0, st>>>(H, s->he_col.p, s->val[0].p, s->val[1].p);
+  k_embed_cols<<<grid_for(H), kBlock, 0, st>>>(H, s->blk, s->he_col.p, s->val[0].p, s->val[1].p);
   s->launches += 1;
   RA_TRY(s->part.alloc((size_t)s->pk1.num_segs * kPartStride));
   RA_TRY(s->ypart.alloc((size_t)s->pk2.num_segs * 3));
-  for (DevBuf<double>* d : {&s->scale, &s->x, &s->r, &s->z, &s->p, &s->p1, &s->y, &s->delta}) RA_TRY(d->alloc(3ull * N));
-  RA_TRY(s->slotsA.alloc(s->pk2.grid + 8));
+  for (DevBuf<double>* d : {&s->scale, &s->x, &s->r, &s->q, &s->sv, &s->bvec, &s->y, &s->delta}) RA_TRY(d->alloc(3ull * N));
+  RA_TRY(s->z.alloc(4ull * N));
+  RA_TRY(s->p.alloc(4ull * N));
+  RA_TRY(s->slotsA.alloc(2 * (size_t)s->pk2.grid + 8));
   RA_TRY(s->slotsB.alloc(2 * (size_t)s->pk2.grid + 8));
-  RA_TRY(s->slotsC.alloc(2 * (size_t)s->pk2.grid + 8));
   RA_TRY(s->row_cnt.alloc(N));
   CUDA_TRY(cudaMemsetAsync(s->row_cnt.p, 0, (size_t)N * sizeof(unsigned), st));
   RA_TRY(s->Dblk.alloc(6ull * N));
@@ -2047,8 +2072,8 @@ int iterate(gsfm_ra_solver* s, int max_new_iterations, gsfm_ra_summary* sum) {
     CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
     CUDA_TRY(cudaMemsetAsync(&s->sc.p->bad, 0, sizeof(int), s->stream));
     RA_TRY(s->pcg_enqueue(b, s->radius, nullptr, nullptr, o.pcg_rtol, o.pcg_max_iterations));
-    k_apply_step<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[b].p, s->x.p, s->y.p, s->gt_p[b], s->omega[b].p, s->omega[c].p, s->delta.p,
-                                                        s->slots.p, s->counter.p, s->sc.p, s->manifold() ? 1 : 0);
+    k_apply_step<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[b].p, s->x.p, s->bvec.p, s->r.p, s->Dblk.p, s->Hd_p[b], s->gt_p[b], s->omega[b].p,
+                                                        s->omega[c].p, s->delta.p, s->slots.p, s->counter.p, s->sc.p, s->manifold() ? 1 : 0);
     s->launches += 1;
     CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
     RA_TRY(s->evaluate(c, true));
@@ -2307,7 +2332,7 @@ int gsfm_ra_solver_time_kernels(gsfm_ra_solver* s, int32_t repeats, double* out_
   };
   RA_TRY(timed([&] { s->launch_edges(b, true, s->val[c].p); }, &out_ms[0]));
   RA_TRY(timed([&] { s->launch_edges(b, false, nullptr); }, &out_ms[1]));
-  CUDA_TRY(cudaMemsetAsync(s->z.p, 0, 3ull * s->N * sizeof(double), s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->z.p, 0, 4ull * s->N * sizeof(double), s->stream));
   RA_TRY(timed([&] { s->launch_spmv(b, s->z.p, std::getenv("GSFM_RA_DEBUG_NOGATHER") ? 2 : 0); }, &out_ms[2]));
   // one PCG iteration inside the persistent kernel: (time of R iterations) / R with rtol = 0
   {
@@ -2466,7 +2491,7 @@ int gsfm_ra_assemble(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, c
   if (val || col) {
     RA_TRY(dval.alloc(9 * H));
     RA_TRY(dcol.alloc(H));
-    k_export_blocks<<<grid_for(H), kBlock, 0, s->stream>>>(H, s->he_row.p, s->he_col.p, s->val[0].p, s->node_JL[0].p, dval.p, dcol.p);
+    k_export_blocks<<<grid_for(H), kBlock, 0, s->stream>>>(H, s->blk, s->he_row.p, s->he_col.p, s->val[0].p, s->node_JL[0].p, dval.p, dcol.p);
     CUDA_TRY(cudaGetLastError());
     if (val) CUDA_TRY(cudaMemcpyAsync(val, dval.p, 9 * H * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     if (col) CUDA_TRY(cudaMemcpyAsync(col, dcol.p, H * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
@@ -2513,11 +2538,11 @@ int gsfm_ra_spmv(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, const
   CUDA_TRY(cudaMemcpyAsync(dx.p, x, 3ull * N * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   if (damping) { RA_TRY(dd.alloc(3ull * N)); CUDA_TRY(cudaMemcpyAsync(dd.p, damping, 3ull * N * sizeof(double), cudaMemcpyHostToDevice, s->stream)); }
   // y = Jl^T Ht (Jl x) + damping .* x
-  k_node_apply<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[0].p, dx.p, 0, nullptr, nullptr, s->p.p);
+  k_node_apply<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[0].p, dx.p, 0, nullptr, nullptr, s->p.p, 4);
   RA_TRY(s->spmv(0, s->p.p, s->y.p, s->Hd_p[0]));
-  k_node_apply<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[0].p, s->y.p, 1, dd.p, dx.p, s->z.p);
+  k_node_apply<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[0].p, s->y.p, 1, dd.p, dx.p, s->delta.p, 3);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(y, s->z.p, 3ull * N * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(y, s->delta.p, 3ull * N * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   return 0;
 }
@@ -2541,7 +2566,8 @@ int gsfm_ra_pcg(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, const 
   const int it = s->h_sc->pcg_iter;
   const double res = (s->h_sc->bb > 0.0) ? std::sqrt(s->h_sc->rr / s->h_sc->bb) : 0.0;
   // x = Jl^-1 xt
-  k_apply_step<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[0].p, s->x.p, nullptr, nullptr, nullptr, nullptr, s->delta.p, s->slots.p, s->counter.p, s->sc.p, 0);
+  k_apply_step<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[0].p, s->x.p, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, s->delta.p,
+                                                      s->slots.p, s->counter.p, s->sc.p, 0);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(x, s->delta.p, 3ull * N * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));

@@ -7,11 +7,11 @@
 //
 // Design (not a translation): rotations travel as unit quaternions (w,x,y,z), the residual
 // e = Log(R_j R_i^T R_ij^T) comes straight from a quaternion product, and the Jacobians are the
-// closed-form SO(3) ones in the LEFT TANGENT frame:
-//     de/d(delta_j) = Jl^-1(e)            de/d(delta_i) = -Jl^-1(e) * (R_j R_i^T)
-// (R <- Exp(delta) R).  The reference differentiates w.r.t. the angle-axis vector omega itself;
-// d(delta) = Jl(omega) d(omega), a per-VIEW 3x3 factor that the solver applies once per view
-// (node kernels) instead of once per edge.  All fp64.
+// closed-form SO(3) ones in the BODY (right) TANGENT frame, R <- R Exp(beta):
+//     de/d(beta_j) = Jl^-1(e) R_j =: B        de/d(beta_i) = -B
+// so every edge is a symmetric 3x3 Laplacian stencil (see edge_terms).  The reference differentiates
+// w.r.t. the angle-axis vector omega itself; d(beta) = Jr(omega) d(omega), a per-VIEW 3x3 factor that
+// the solver applies once per view (node kernels) instead of once per edge.  All fp64.
 #pragma once
 #include <cfloat>
 #include <cmath>
@@ -271,101 +271,102 @@ __host__ __device__ inline void eval_loss(const DevLoss& L, double s, double* ou
 }
 
 // ------------------------------------------------------------------------------------------
-// One relative-rotation constraint.  Inputs: endpoint quaternions, the measured q_ij, the upper
-// triangular weight U (packed u00 u01 u02 u11 u12 u22).  Outputs, all in the left tangent frame
-// of view j (A = U Jl^-1(e) is d r / d delta_j; d r / d delta_i = -A Q, Q = R_j R_i^T):
-//   r = U e, rho[3] = loss(|r|^2),
-//   W = rho' (A^T A - kappa u u^T), u = A^T r   -- robustified J~_j^T J~_j incl. the Triggs term
-//   v = rho' u                                  -- J~_j^T r~
+// One relative-rotation constraint in the BODY (right) tangent frame, R <- R Exp(beta).
+// For any residual that is a function of the error rotation E = R_j R_i^T R_ij^T,
+//     d r / d beta_j = +B,   d r / d beta_i = -B,   B = A R_j,  A = d r / d(left perturbation of E),
+// so one edge contributes a matrix-weighted graph-Laplacian stencil to the normal equations:
+//     S = rho' (B^T B - kappa u u^T), u = B^T r :   H_ii += S, H_jj += S, H_ij = H_ji = -S   (S symmetric)
+//     v = rho' u :                                   g_j += v, g_i -= v
 // (Ceres Corrector, SURVEY Appendix B.2: J~ = sqrt(rho')(I - alpha/s r r^T) J, r~ = sqrt(rho')/(1-alpha) r
 //  =>  J~^T J~ = rho' J^T (I - kappa r r^T) J with kappa = (2 alpha - alpha^2)/s, and J~^T r~ = rho' J^T r.)
+// The reference differentiates w.r.t. the angle-axis vector omega; d(beta) = Jr(omega) d(omega) is a
+// per-VIEW factor applied by the node kernels.  Inputs: endpoint quaternions, the measured q_ij, the
+// upper triangular weight U (packed u00 u01 u02 u11 u12 u22; kScalarU: U = u00 I).
 // ------------------------------------------------------------------------------------------
 struct EdgeTerms {
   double r[3];
-  double A[9];
-  double Q[9];
-  double W[6];
+  double B[9];
+  double S[6];
   double v[3];
   double rho[3];
 };
 
-// kResidual = 0: r = U Log(E)                    (angle-axis types 3..8)
+// Ceres Corrector's kappa (zero for every loss with rho'' <= 0).
+__host__ __device__ inline double triggs_kappa(double s, const double* rho) {
+  if (s != 0.0 && rho[2] > 0.0) {
+    const double D = 1.0 + 2.0 * s * rho[2] / rho[1];
+    const double alpha = 1.0 - ((D > 0.0) ? sqrt(D) : 0.0);
+    return (2.0 * alpha - alpha * alpha) / s;
+  }
+  return 0.0;
+}
+
+// kResidual = 0: r = U Log(E)                    (angle-axis types 3..8);  A = U Jl^-1(e)
 // kResidual = 1: r = -2 w vec(q_E) = 2 w vec(q_ij (q_j q_i^-1)^-1)   (QUATERNION_COSINE,
-//                include/pairwise_rotation_error_quat.hpp:82-106; w = U[0]); with the left perturbation
-//                q_E <- [phi/2, 1] q_E:  d r / d phi_j = A = w ([v_E]x - w_E I), and d r / d phi_i = -A Q as for any
-//                residual that is a function of E.  No logarithm, smooth through theta = pi.
-template <bool kNeedJacobian, int kResidual = 0>
+//                include/pairwise_rotation_error_quat.hpp:82-106; w = U[0]);  A = w ([v_E]x - w_E I).
+//                No logarithm, smooth through theta = pi.
+template <bool kNeedJacobian, int kResidual = 0, bool kScalarU = false>
 __host__ __device__ inline void edge_terms(const Q4& qi, const Q4& qj, const Q4& qij, const double* U, const DevLoss& L, EdgeTerms& o) {
-  const Q4 qL = qmul(qj, qconj(qi));   // loop rotation R_j R_i^T
-  const Q4 qE = qmul(qL, qconj(qij));  // error rotation R_j R_i^T R_ij^T
+  const Q4 qE = qmul(qmul(qj, qconj(qi)), qconj(qij));  // error rotation R_j R_i^T R_ij^T
+  double M[9];                                           // d r / d(left perturbation of E) before the weight
   if (kResidual == 1) {
     const double w = U[0];
     o.r[0] = -2.0 * w * qE.x; o.r[1] = -2.0 * w * qE.y; o.r[2] = -2.0 * w * qE.z;
-    const double s = o.r[0] * o.r[0] + o.r[1] * o.r[1] + o.r[2] * o.r[2];
-    eval_loss(L, s, o.rho);
-    if (!kNeedJacobian) return;
-    o.A[0] = -w * qE.w; o.A[1] = -w * qE.z; o.A[2] = w * qE.y;
-    o.A[3] = w * qE.z;  o.A[4] = -w * qE.w; o.A[5] = -w * qE.x;
-    o.A[6] = -w * qE.y; o.A[7] = w * qE.x;  o.A[8] = -w * qE.w;
-    quat_to_mat(qL, o.Q);
-    double u[3];
-#pragma unroll
-    for (int cc = 0; cc < 3; ++cc) u[cc] = o.A[cc] * o.r[0] + o.A[3 + cc] * o.r[1] + o.A[6 + cc] * o.r[2];
-    double kappa = 0.0;
-    const double rho1 = o.rho[1];
-    if (s != 0.0 && o.rho[2] > 0.0) {
-      const double D = 1.0 + 2.0 * s * o.rho[2] / rho1;
-      const double alpha = 1.0 - ((D > 0.0) ? sqrt(D) : 0.0);
-      kappa = (2.0 * alpha - alpha * alpha) / s;
+  } else {
+    double e[3], theta2, c;
+    quat_log(qE, e, &theta2, &c);
+    if (kScalarU) {
+      o.r[0] = U[0] * e[0]; o.r[1] = U[0] * e[1]; o.r[2] = U[0] * e[2];
+    } else {
+      o.r[0] = U[0] * e[0] + U[1] * e[1] + U[2] * e[2];
+      o.r[1] = U[3] * e[1] + U[4] * e[2];
+      o.r[2] = U[5] * e[2];
     }
-    const double* A = o.A;
-    o.W[0] = rho1 * (A[0] * A[0] + A[3] * A[3] + A[6] * A[6] - kappa * u[0] * u[0]);
-    o.W[1] = rho1 * (A[0] * A[1] + A[3] * A[4] + A[6] * A[7] - kappa * u[0] * u[1]);
-    o.W[2] = rho1 * (A[0] * A[2] + A[3] * A[5] + A[6] * A[8] - kappa * u[0] * u[2]);
-    o.W[3] = rho1 * (A[1] * A[1] + A[4] * A[4] + A[7] * A[7] - kappa * u[1] * u[1]);
-    o.W[4] = rho1 * (A[1] * A[2] + A[4] * A[5] + A[7] * A[8] - kappa * u[1] * u[2]);
-    o.W[5] = rho1 * (A[2] * A[2] + A[5] * A[5] + A[8] * A[8] - kappa * u[2] * u[2]);
-    o.v[0] = rho1 * u[0]; o.v[1] = rho1 * u[1]; o.v[2] = rho1 * u[2];
-    return;
+    if (kNeedJacobian) {
+      // Jl^-1(e) = I - [e]x/2 + c (e e^T - theta2 I)
+      const double d = 1.0 - c * theta2;
+      M[0] = d + c * e[0] * e[0];           M[1] = 0.5 * e[2] + c * e[0] * e[1];  M[2] = -0.5 * e[1] + c * e[0] * e[2];
+      M[3] = -0.5 * e[2] + c * e[0] * e[1]; M[4] = d + c * e[1] * e[1];           M[5] = 0.5 * e[0] + c * e[1] * e[2];
+      M[6] = 0.5 * e[1] + c * e[0] * e[2];  M[7] = -0.5 * e[0] + c * e[1] * e[2]; M[8] = d + c * e[2] * e[2];
+    }
   }
-  double e[3], theta2, c;
-  quat_log(qE, e, &theta2, &c);
-  o.r[0] = U[0] * e[0] + U[1] * e[1] + U[2] * e[2];
-  o.r[1] = U[3] * e[1] + U[4] * e[2];
-  o.r[2] = U[5] * e[2];
   const double s = o.r[0] * o.r[0] + o.r[1] * o.r[1] + o.r[2] * o.r[2];
   eval_loss(L, s, o.rho);
   if (!kNeedJacobian) return;
-  // Jl^-1(e) = I - [e]x/2 + c (e e^T - theta2 I)
-  double Ji[9];
-  const double d = 1.0 - c * theta2;
-  Ji[0] = d + c * e[0] * e[0];           Ji[1] = 0.5 * e[2] + c * e[0] * e[1];  Ji[2] = -0.5 * e[1] + c * e[0] * e[2];
-  Ji[3] = -0.5 * e[2] + c * e[0] * e[1]; Ji[4] = d + c * e[1] * e[1];           Ji[5] = 0.5 * e[0] + c * e[1] * e[2];
-  Ji[6] = 0.5 * e[1] + c * e[0] * e[2];  Ji[7] = -0.5 * e[0] + c * e[1] * e[2]; Ji[8] = d + c * e[2] * e[2];
-#pragma unroll
-  for (int cc = 0; cc < 3; ++cc) {
-    o.A[cc] = U[0] * Ji[cc] + U[1] * Ji[3 + cc] + U[2] * Ji[6 + cc];
-    o.A[3 + cc] = U[3] * Ji[3 + cc] + U[4] * Ji[6 + cc];
-    o.A[6 + cc] = U[5] * Ji[6 + cc];
+  if (kResidual == 1) {
+    M[0] = -qE.w; M[1] = -qE.z; M[2] = qE.y;
+    M[3] = qE.z;  M[4] = -qE.w; M[5] = -qE.x;
+    M[6] = -qE.y; M[7] = qE.x;  M[8] = -qE.w;
   }
-  quat_to_mat(qL, o.Q);
+  double Rj[9], T[9];
+  quat_to_mat(qj, Rj);
+#pragma unroll
+  for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) T[3 * rr + cc] = M[3 * rr] * Rj[cc] + M[3 * rr + 1] * Rj[3 + cc] + M[3 * rr + 2] * Rj[6 + cc];
+  double* B = o.B;
+  if (kScalarU || kResidual == 1) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) B[k] = U[0] * T[k];
+  } else {
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      B[cc] = U[0] * T[cc] + U[1] * T[3 + cc] + U[2] * T[6 + cc];
+      B[3 + cc] = U[3] * T[3 + cc] + U[4] * T[6 + cc];
+      B[6 + cc] = U[5] * T[6 + cc];
+    }
+  }
   double u[3];
 #pragma unroll
-  for (int cc = 0; cc < 3; ++cc) u[cc] = o.A[cc] * o.r[0] + o.A[3 + cc] * o.r[1] + o.A[6 + cc] * o.r[2];
-  double kappa = 0.0;
+  for (int cc = 0; cc < 3; ++cc) u[cc] = B[cc] * o.r[0] + B[3 + cc] * o.r[1] + B[6 + cc] * o.r[2];
+  const double kappa = triggs_kappa(s, o.rho);
   const double rho1 = o.rho[1];
-  if (s != 0.0 && o.rho[2] > 0.0) {
-    const double D = 1.0 + 2.0 * s * o.rho[2] / rho1;
-    const double alpha = 1.0 - ((D > 0.0) ? sqrt(D) : 0.0);
-    kappa = (2.0 * alpha - alpha * alpha) / s;
-  }
-  const double* A = o.A;
-  o.W[0] = rho1 * (A[0] * A[0] + A[3] * A[3] + A[6] * A[6] - kappa * u[0] * u[0]);
-  o.W[1] = rho1 * (A[0] * A[1] + A[3] * A[4] + A[6] * A[7] - kappa * u[0] * u[1]);
-  o.W[2] = rho1 * (A[0] * A[2] + A[3] * A[5] + A[6] * A[8] - kappa * u[0] * u[2]);
-  o.W[3] = rho1 * (A[1] * A[1] + A[4] * A[4] + A[7] * A[7] - kappa * u[1] * u[1]);
-  o.W[4] = rho1 * (A[1] * A[2] + A[4] * A[5] + A[7] * A[8] - kappa * u[1] * u[2]);
-  o.W[5] = rho1 * (A[2] * A[2] + A[5] * A[5] + A[8] * A[8] - kappa * u[2] * u[2]);
+  o.S[0] = rho1 * (B[0] * B[0] + B[3] * B[3] + B[6] * B[6] - kappa * u[0] * u[0]);
+  o.S[1] = rho1 * (B[0] * B[1] + B[3] * B[4] + B[6] * B[7] - kappa * u[0] * u[1]);
+  o.S[2] = rho1 * (B[0] * B[2] + B[3] * B[5] + B[6] * B[8] - kappa * u[0] * u[2]);
+  o.S[3] = rho1 * (B[1] * B[1] + B[4] * B[4] + B[7] * B[7] - kappa * u[1] * u[1]);
+  o.S[4] = rho1 * (B[1] * B[2] + B[4] * B[5] + B[7] * B[8] - kappa * u[1] * u[2]);
+  o.S[5] = rho1 * (B[2] * B[2] + B[5] * B[5] + B[8] * B[8] - kappa * u[2] * u[2]);
   o.v[0] = rho1 * u[0]; o.v[1] = rho1 * u[1]; o.v[2] = rho1 * u[2];
 }
 
