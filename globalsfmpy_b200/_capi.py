@@ -88,6 +88,11 @@ class Summary(C.Structure):
                 ("last_weight_change", C.c_double)]
 
 
+def residual_dim(error_type):
+    """Residual dimension of a RotationErrorType (include/pairwise_rotation_error_quat.hpp: 4 for QuatFNorm, 9 for RotFNorm)."""
+    return {QUATERNION_NORM: 4, ROTATION_MAT_FNORM: 9}.get(int(error_type), 3)
+
+
 def default_options_py():
     """The Ceres 1.14 defaults the reference runs with (SURVEY Appendix B.3,
     src/GSfM_nonlinear_rotation_estimator.cpp:299-303); the same numbers
@@ -176,6 +181,8 @@ def declare(lib, oracle=False):
     lib.gsfm_ra_abi_version.restype = C.c_int
     lib.gsfm_ra_last_error.restype = C.c_char_p
     lib.gsfm_ra_device_count.restype = C.c_int
+    lib.gsfm_ra_residual_dim.argtypes = [C.c_int32]
+    lib.gsfm_ra_residual_dim.restype = C.c_int
     lib.gsfm_ra_default_options.argtypes = [op]
     lib.gsfm_ra_default_options.restype = None
     lib.gsfm_ra_solve.argtypes = [pp, op, _dp, sp]
@@ -214,7 +221,7 @@ EXPORTED_SYMBOLS = [
     "gsfm_ra_solver_set_rotations", "gsfm_ra_solver_get_rotations", "gsfm_ra_solver_reset",
     "gsfm_ra_solver_iterate", "gsfm_ra_comm_unique_id", "gsfm_ra_solver_comm_init",
     "gsfm_ra_solver_ipc_export", "gsfm_ra_solver_ipc_import", "gsfm_ra_solver_edge_range", "gsfm_ra_solver_cuda_stream", "gsfm_ra_solver_time_kernels", "gsfm_ra_eval_edges", "gsfm_ra_whiten", "gsfm_ra_assemble", "gsfm_ra_cost",
-    "gsfm_ra_spmv", "gsfm_ra_pcg", "gsfm_ra_eval_loss", "gsfm_ra_filter_view_pairs",
+    "gsfm_ra_spmv", "gsfm_ra_pcg", "gsfm_ra_eval_loss", "gsfm_ra_filter_view_pairs", "gsfm_ra_residual_dim",
 ]
 
 _lib = None

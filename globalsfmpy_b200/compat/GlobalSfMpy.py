@@ -314,10 +314,6 @@ def _solve(view_pairs, orientations, loss, error_type, covariances=None, num_thr
     error_type = int(error_type)
     if len(orientations) == 0 or len(view_pairs) == 0:
         return False                                  # rotation_estimator.cpp:209-220
-    if error_type < 2:
-        raise NotImplementedError("RotationErrorType QUATERNION_NORM / ROTATION_MAT_FNORM (EstimateRotationsWithCustomizedLoss, "
-                                  "rotation_estimator.cpp:82-198) are not implemented on the device; QUATERNION_COSINE and the "
-                                  "angle-axis types 3..8 are")
     ids, ei, ej, wij, cov6, omega = _flatten(view_pairs, orientations, covariances, error_type)
     if len(ei) == 0:
         return True

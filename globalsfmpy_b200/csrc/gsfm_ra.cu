@@ -299,7 +299,7 @@ __global__ void k_node_prep(uint32_t N, const double* __restrict__ omega, double
 // segment, the warp-reduced diagonal block / gradient / cost partial.
 // kWriteBlocks=false is K1c: cost only (trial point).
 // ------------------------------------------------------------------------------------------
-template <bool kWriteBlocks, int kResidual, bool kScalarU>
+template <bool kWriteBlocks, int kResidual, bool kScalarU, int kLoss>
 __global__ void __launch_bounds__(kBlock, 2)
 k_edges(uint32_t num_warps, uint64_t H, const uint32_t* __restrict__ warp_seg_ptr, const uint32_t* __restrict__ task_row,
         const uint32_t* __restrict__ task_begin, const uint32_t* __restrict__ task_len, const uint32_t* __restrict__ he_col,
@@ -332,8 +332,7 @@ k_edges(uint32_t num_warps, uint64_t H, const uint32_t* __restrict__ warp_seg_pt
         for (int k = 1; k < 6; ++k) u[k] = U[(uint64_t)k * H + h];
       }
       EdgeTerms et;
-      if (row_is_j) edge_terms<kWriteBlocks, kResidual, kScalarU>(qb, qa, qm, u, loss, et);
-      else edge_terms<kWriteBlocks, kResidual, kScalarU>(qa, qb, qm, u, loss, et);
+      edge_terms<kWriteBlocks, kResidual, kScalarU, kLoss>(row_is_j ? qb : qa, row_is_j ? qa : qb, qm, u, loss, et);
       if (!row_is_j) acc[9] += 0.5 * et.rho[0];  // each edge's cost is counted once, in its i row
       if (kWriteBlocks) {
         // both rows of the edge: diag += S, block(row, col) = -S; gradient: +v in row j, -v in row i
@@ -341,6 +340,59 @@ k_edges(uint32_t num_warps, uint64_t H, const uint32_t* __restrict__ warp_seg_pt
 #pragma unroll
         for (int k = 0; k < 6; ++k) { acc[k] += et.S[k]; val[blk_index(h, k, Rec<6>::kDoubles)] = -et.S[k]; }
         acc[6] += sgn * et.v[0]; acc[7] += sgn * et.v[1]; acc[8] += sgn * et.v[2];
+      }
+    }
+    if (kWriteBlocks) {
+#pragma unroll
+      for (int k = 0; k < kPartStride; ++k) acc[k] = warp_sum(acc[k]);
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kPartStride; ++k) part[(size_t)t * kPartStride + k] = acc[k];
+      }
+    } else {
+      const double c = warp_sum(acc[9]);
+      if (lane == 0) part[(size_t)t * kPartStride + 9] = c;
+    }
+  }
+}
+
+// K1 for the general two-block residuals (QUATERNION_NORM, ROTATION_MAT_FNORM): same work distribution, the stored
+// off-diagonal block is a full row-major 3x3 (9-double records), the diagonal contribution depends on the side.
+template <bool kWriteBlocks, int kType>
+__global__ void __launch_bounds__(kBlock, 1)
+k_edges_general(uint32_t num_warps, uint64_t H, const uint32_t* __restrict__ warp_seg_ptr, const uint32_t* __restrict__ task_row,
+                const uint32_t* __restrict__ task_begin, const uint32_t* __restrict__ task_len, const uint32_t* __restrict__ he_col,
+                const double* __restrict__ qij, const double* __restrict__ U, const double* __restrict__ node_q, DevLoss loss,
+                double* __restrict__ val, double* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp_global >= num_warps) return;
+  for (uint32_t t = warp_seg_ptr[warp_global]; t < warp_seg_ptr[warp_global + 1]; ++t) {
+    const uint32_t row = task_row[t] & ~kSideBit;
+    const uint64_t begin = task_begin[t];
+    const uint32_t len = task_len[t];
+    const double4 qa4 = reinterpret_cast<const double4*>(node_q)[row];
+    const Q4 qrow{qa4.x, qa4.y, qa4.z, qa4.w};
+    double acc[kPartStride];
+#pragma unroll
+    for (int k = 0; k < kPartStride; ++k) acc[k] = 0.0;
+    for (uint32_t off = lane; off < len; off += 32) {
+      const uint64_t h = begin + off;
+      const uint32_t cf = he_col[h];
+      const uint32_t col = cf & ~kSideBit;
+      const bool row_is_j = (cf & kSideBit) != 0;
+      const double4 qb4 = reinterpret_cast<const double4*>(node_q)[col];
+      const Q4 qcol{qb4.x, qb4.y, qb4.z, qb4.w};
+      const Q4 qm{qij[h], qij[H + h], qij[2 * H + h], qij[3 * H + h]};
+      GeneralTerms gt;
+      general_edge_terms<kWriteBlocks, kType>(row_is_j ? qcol : qrow, row_is_j ? qrow : qcol, qm, U[h], row_is_j, loss, gt);
+      if (!row_is_j) acc[9] += 0.5 * gt.rho[0];
+      if (kWriteBlocks) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc[k] += gt.D[k];
+        acc[6] += gt.g[0]; acc[7] += gt.g[1]; acc[8] += gt.g[2];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) val[blk_index(h, k, Rec<9>::kDoubles)] = gt.G[k];
       }
     }
     if (kWriteBlocks) {
@@ -1258,6 +1310,50 @@ __global__ void k_eval_edges(uint64_t E, const uint32_t* __restrict__ ei, const 
   }
 }
 
+// Same for the general two-block residuals: r [E][d], Ji/Jj [E][d][3], d = 4 (QUATERNION_NORM) or 9 (ROTATION_MAT_FNORM).
+// The row-view interface of general_edge_terms does not expose the raw Jacobians, so they are rebuilt here from the same
+// helpers (API-only path).
+template <int kType>
+__global__ void k_eval_edges_general(uint64_t E, const uint32_t* __restrict__ ei, const uint32_t* __restrict__ ej, const double* __restrict__ omega_ij,
+                                     const double* __restrict__ weight, const double* __restrict__ node_q, const double* __restrict__ node_JL,
+                                     DevLoss loss, double* r_out, double* Ji, double* Jj, double* rho) {
+  constexpr int kDim = (kType == 0) ? 4 : 9;
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= E) return;
+  const uint32_t i = ei[k], j = ej[k];
+  const double4 a = reinterpret_cast<const double4*>(node_q)[i], b = reinterpret_cast<const double4*>(node_q)[j];
+  const Q4 qa{a.x, a.y, a.z, a.w}, qb{b.x, b.y, b.z, b.w};
+  const Q4 qm = aa_to_quat(omega_ij[3 * k], omega_ij[3 * k + 1], omega_ij[3 * k + 2]);
+  const double w = weight ? weight[k] : 1.0;
+  double r[kDim], Ja[3 * kDim], Jb[3 * kDim];
+  if (kType == 0) {
+    const Q4 qe = qmul(qm, qa);
+    const double sb = (qb.y < 0.0) ? -1.0 : 1.0, se = (qe.y < 0.0) ? -1.0 : 1.0;
+    r[0] = w * (sb * qb.x - se * qe.x); r[1] = w * (sb * qb.y - se * qe.y);
+    r[2] = w * (sb * qb.z - se * qe.z); r[3] = w * (sb * qb.w - se * qe.w);
+    quat_right_jac(qb, 0.5 * w * sb, Jb); quat_right_jac(qe, -0.5 * w * se, Ja);
+  } else {
+    double Ra[9], Rb[9], Rr[9], Re[9];
+    quat_to_mat(qa, Ra); quat_to_mat(qb, Rb); quat_to_mat(qm, Rr);
+    for (int rr = 0; rr < 3; ++rr)
+      for (int c = 0; c < 3; ++c) Re[3 * rr + c] = Rr[3 * rr] * Ra[c] + Rr[3 * rr + 1] * Ra[3 + c] + Rr[3 * rr + 2] * Ra[6 + c];
+    for (int c = 0; c < 3; ++c)
+      for (int rr = 0; rr < 3; ++rr) r[3 * c + rr] = w * (Re[3 * rr + c] - Rb[3 * rr + c]);
+    rot_right_jac(Re, w, Ja); rot_right_jac(Rb, -w, Jb);
+  }
+  double s = 0.0;
+  for (int q = 0; q < kDim; ++q) { s += r[q] * r[q]; if (r_out) r_out[kDim * k + q] = r[q]; }
+  if (rho) eval_loss(loss, s, rho + 3 * k);
+  for (int side = 0; side < 2; ++side) {
+    double* out = side ? Jj : Ji;
+    if (!out) continue;
+    const double* D = node_JL + 9 * (size_t)(side ? j : i);
+    const double* J = side ? Jb : Ja;
+    for (int q = 0; q < kDim; ++q)
+      for (int c = 0; c < 3; ++c) out[3 * kDim * k + 3 * q + c] = J[3 * q] * D[c] + J[3 * q + 1] * D[3 + c] + J[3 * q + 2] * D[6 + c];
+  }
+}
+
 __global__ void k_whiten_edges(uint64_t E, const double* __restrict__ cov6, const double* __restrict__ weight, int error_type, double* U9) {
   const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= E) return;
@@ -1378,6 +1474,8 @@ int make_dev_loss(const gsfm_ra_loss* in, DevLoss* L) {
   if (in->kind < 0 || in->kind > GSFM_RA_LOSS_MAGSAC9) { set_error("unknown loss kind %d", in->kind); return GSFM_RA_ERR_INVALID; }
   L->kind = in->kind; L->flags = in->flags; L->p0 = in->p[0]; L->p1 = in->p[1];
   L->scale = (in->scale == 0.0) ? 1.0 : in->scale;
+  L->sq0 = in->p[0] * in->p[0];
+  L->inv_sq0 = 1.0 / L->sq0;
   const bool needs_p0 = in->kind != GSFM_RA_LOSS_TRIVIAL;
   if (needs_p0 && !(in->p[0] > 0.0)) { set_error("loss parameter p[0] must be > 0"); return GSFM_RA_ERR_INVALID; }
   if ((in->kind == GSFM_RA_LOSS_TOLERANT || in->kind == GSFM_RA_LOSS_GEMANMCCLURE) && !(in->p[1] > 0.0)) {
@@ -1414,7 +1512,6 @@ int check_problem(const gsfm_ra_problem* p) {
   if (p->num_views >= kSideBit) { set_error("too many views"); return GSFM_RA_ERR_INVALID; }
   if (p->num_edges >= (1ull << 31)) { set_error("too many edges for 32-bit half-edge offsets"); return GSFM_RA_ERR_UNSUPPORTED; }
   if (p->error_type < GSFM_RA_QUATERNION_NORM || p->error_type > GSFM_RA_ANGLE_AXIS_COVNORM) { set_error("unknown error_type %d", p->error_type); return GSFM_RA_ERR_INVALID; }
-  if (p->error_type < GSFM_RA_QUATERNION_COSINE) { set_error("QUATERNION_NORM / ROTATION_MAT_FNORM are not implemented (QUATERNION_COSINE and the angle-axis types 3..8 are)"); return GSFM_RA_ERR_UNSUPPORTED; }
   if (type_needs_cov(p->error_type) && !p->cov6) { set_error("error_type %d needs cov6", p->error_type); return GSFM_RA_ERR_INVALID; }
   return 0;
 }
@@ -1634,7 +1731,8 @@ struct gsfm_ra_solver {
 
   bool sharded() const { return world > 1; }
   // QUATERNION_COSINE: parameters live on the manifold (left-multiplicative update, local coordinates delta = phi/2)
-  bool manifold() const { return error_type == GSFM_RA_QUATERNION_COSINE; }
+  bool manifold() const { return error_type <= GSFM_RA_QUATERNION_COSINE; }
+  bool general() const { return error_type < GSFM_RA_QUATERNION_COSINE; }  // two-block residuals, 9-double records
   int allreduce(double* buf, size_t count) {
     if (!comm) { set_error("sharded solver used before gsfm_ra_solver_comm_init"); return GSFM_RA_ERR_INVALID; }
     NCCL_TRY(ncclx::api()->AllReduce(buf, buf, count, ncclx::kFloat64, ncclx::kSum, comm, stream));
@@ -1649,14 +1747,33 @@ struct gsfm_ra_solver {
 
   int rec_doubles() const { return blk * 32 + 16; }
   int smem_bytes() const { return spmv_smem_bytes(blk); }
+  // K1 is specialised on (Jacobian?, residual kind, scalar weight?, loss): the common losses get their own instantiation
+  // (no switch, fewer registers), everything else runs the generic one.
+  template <bool JAC, int RES, bool SCAL, int LOSS>
+  void launch_edges_t(int b, double* val_out) {
+    k_edges<JAC, RES, SCAL, LOSS><<<pk1.grid, kBlock, 0, stream>>>(pk1.num_warps, H, pk1.warp_seg_ptr.p, pk1.seg_row.p, pk1.seg_begin.p, pk1.seg_len.p,
+                                                                   he_col.p, qij.p, U.p, node_q[b].p, loss, val_out, part.p);
+  }
+  template <bool JAC, int RES, bool SCAL>
+  void launch_edges_l(int b, double* val_out) {
+    const bool plain = loss.scale == 1.0;
+    if (plain && loss.kind == kLossCauchy) launch_edges_t<JAC, RES, SCAL, kLossCauchy>(b, val_out);
+    else if (plain && loss.kind == kLossSoftLOne) launch_edges_t<JAC, RES, SCAL, kLossSoftLOne>(b, val_out);
+    else if (plain && loss.kind == kLossHuber) launch_edges_t<JAC, RES, SCAL, kLossHuber>(b, val_out);
+    else if (plain && loss.kind == kLossMagsac3) launch_edges_t<JAC, RES, SCAL, kLossMagsac3>(b, val_out);
+    else launch_edges_t<JAC, RES, SCAL, -1>(b, val_out);
+  }
+  template <bool JAC, int TYPE>
+  void launch_edges_g(int b, double* val_out) {
+    k_edges_general<JAC, TYPE><<<pk1.grid, kBlock, 0, stream>>>(pk1.num_warps, H, pk1.warp_seg_ptr.p, pk1.seg_row.p, pk1.seg_begin.p, pk1.seg_len.p,
+                                                                he_col.p, qij.p, U.p, node_q[b].p, loss, val_out, part.p);
+  }
   void launch_edges(int b, bool jacobian, double* val_out) {
-#define GSFM_LAUNCH_EDGES(JAC, RES, SCAL, VAL)                                                                                                  \
-  k_edges<JAC, RES, SCAL><<<pk1.grid, kBlock, 0, stream>>>(pk1.num_warps, H, pk1.warp_seg_ptr.p, pk1.seg_row.p, pk1.seg_begin.p, pk1.seg_len.p, \
-                                                           he_col.p, qij.p, U.p, node_q[b].p, loss, VAL, part.p)
-    if (manifold()) { if (jacobian) GSFM_LAUNCH_EDGES(true, 1, true, val_out); else GSFM_LAUNCH_EDGES(false, 1, true, nullptr); }
-    else if (scalar_u) { if (jacobian) GSFM_LAUNCH_EDGES(true, 0, true, val_out); else GSFM_LAUNCH_EDGES(false, 0, true, nullptr); }
-    else { if (jacobian) GSFM_LAUNCH_EDGES(true, 0, false, val_out); else GSFM_LAUNCH_EDGES(false, 0, false, nullptr); }
-#undef GSFM_LAUNCH_EDGES
+    if (error_type == GSFM_RA_QUATERNION_NORM) { if (jacobian) launch_edges_g<true, 0>(b, val_out); else launch_edges_g<false, 0>(b, nullptr); }
+    else if (error_type == GSFM_RA_ROTATION_MAT_FNORM) { if (jacobian) launch_edges_g<true, 1>(b, val_out); else launch_edges_g<false, 1>(b, nullptr); }
+    else if (manifold()) { if (jacobian) launch_edges_l<true, 1, true>(b, val_out); else launch_edges_l<false, 1, true>(b, nullptr); }
+    else if (scalar_u) { if (jacobian) launch_edges_l<true, 0, true>(b, val_out); else launch_edges_l<false, 0, true>(b, nullptr); }
+    else { if (jacobian) launch_edges_l<true, 0, false>(b, val_out); else launch_edges_l<false, 0, false>(b, nullptr); }
   }
   void launch_spmv(int b, const double* x4, int check_done) {
     if (blk == 6)
@@ -1811,7 +1928,7 @@ int device_info(int device, DeviceInfo** out) {
     CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(9)));
     CUDA_TRY(cudaFuncSetAttribute(k_spmv<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(6)));
     CUDA_TRY(cudaFuncSetAttribute(k_spmv<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(9)));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k1, k_edges<true, 0, false>, kBlock, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k1, k_edges<true, 0, false, -1>, kBlock, 0));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2[0], k_pcg_persistent<6>, kBlock, spmv_smem_bytes(6)));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2[1], k_pcg_persistent<9>, kBlock, spmv_smem_bytes(9)));
     // keep freed blocks in the pool: the next solver reuses them
@@ -1855,7 +1972,7 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   s->opt = *options;
   s->rank = rank; s->world = world;
   s->error_type = prob->error_type;
-  s->blk = 6;
+  s->blk = s->general() ? 9 : 6;
   s->scalar_u = !(prob->error_type == GSFM_RA_ANGLE_AXIS_COVARIANCE || prob->error_type == GSFM_RA_ANGLE_AXIS_COV_INLIERS);
   RA_TRY(make_dev_loss(&options->loss, &s->loss));
   s->sm_count = di->sm_count;
@@ -1943,7 +2060,7 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
     s->launches += 5;
     return 0;
   };
-  RA_TRY(make(s->pk1, di->occ_k1));
+  RA_TRY(make(s->pk1, s->general() ? 1 : di->occ_k1));
   RA_TRY(make(s->pk2, occ_k2));
   // the cooperative grid must be fully resident; node loops are grid-strided so any size works
   s->pk2.grid = std::min<uint32_t>(s->pk2.grid, (uint32_t)s->sm_count * std::max(1, occ_k2));
@@ -2188,6 +2305,9 @@ extern "C" {
 
 int gsfm_ra_abi_version(void) { return GSFM_RA_ABI_VERSION; }
 const char* gsfm_ra_last_error(void) { return g_last_error.c_str(); }
+int gsfm_ra_residual_dim(int32_t error_type) {
+  return error_type == GSFM_RA_QUATERNION_NORM ? 4 : (error_type == GSFM_RA_ROTATION_MAT_FNORM ? 9 : 3);
+}
 int gsfm_ra_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -2443,17 +2563,25 @@ int gsfm_ra_eval_edges(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss,
   gsfm_ra_solver* s = t.s;
   const uint64_t E = s->E;
   DevBuf<double> dr, dji, djj, drho;
-  if (r) RA_TRY(dr.alloc(3 * E));
-  if (jac_i) RA_TRY(dji.alloc(9 * E));
-  if (jac_j) RA_TRY(djj.alloc(9 * E));
+  const uint64_t d = (uint64_t)gsfm_ra_residual_dim(s->error_type);
+  if (r) RA_TRY(dr.alloc(d * E));
+  if (jac_i) RA_TRY(dji.alloc(3 * d * E));
+  if (jac_j) RA_TRY(djj.alloc(3 * d * E));
   if (rho) RA_TRY(drho.alloc(3 * E));
   k_node_prep<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->omega[0].p, s->node_q[0].p, s->node_JL[0].p, s->slots.p, s->counter.p, s->sc.p, s->manifold() ? 1 : 0);
-  k_eval_edges<<<grid_for(E), kBlock, 0, s->stream>>>(E, s->d_ei.p, s->d_ej.p, s->d_omega_ij.p, s->d_cov6.p, s->d_weight.p, s->error_type,
-                                                      s->node_q[0].p, s->node_JL[0].p, s->loss, dr.p, dji.p, djj.p, drho.p);
+  if (s->error_type == GSFM_RA_QUATERNION_NORM)
+    k_eval_edges_general<0><<<grid_for(E), kBlock, 0, s->stream>>>(E, s->d_ei.p, s->d_ej.p, s->d_omega_ij.p, s->d_weight.p, s->node_q[0].p, s->node_JL[0].p,
+                                                                   s->loss, dr.p, dji.p, djj.p, drho.p);
+  else if (s->error_type == GSFM_RA_ROTATION_MAT_FNORM)
+    k_eval_edges_general<1><<<grid_for(E), kBlock, 0, s->stream>>>(E, s->d_ei.p, s->d_ej.p, s->d_omega_ij.p, s->d_weight.p, s->node_q[0].p, s->node_JL[0].p,
+                                                                   s->loss, dr.p, dji.p, djj.p, drho.p);
+  else
+    k_eval_edges<<<grid_for(E), kBlock, 0, s->stream>>>(E, s->d_ei.p, s->d_ej.p, s->d_omega_ij.p, s->d_cov6.p, s->d_weight.p, s->error_type,
+                                                        s->node_q[0].p, s->node_JL[0].p, s->loss, dr.p, dji.p, djj.p, drho.p);
   CUDA_TRY(cudaGetLastError());
-  if (r) CUDA_TRY(cudaMemcpyAsync(r, dr.p, 3 * E * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-  if (jac_i) CUDA_TRY(cudaMemcpyAsync(jac_i, dji.p, 9 * E * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-  if (jac_j) CUDA_TRY(cudaMemcpyAsync(jac_j, djj.p, 9 * E * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (r) CUDA_TRY(cudaMemcpyAsync(r, dr.p, d * E * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (jac_i) CUDA_TRY(cudaMemcpyAsync(jac_i, dji.p, 3 * d * E * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (jac_j) CUDA_TRY(cudaMemcpyAsync(jac_j, djj.p, 3 * d * E * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   if (rho) CUDA_TRY(cudaMemcpyAsync(rho, drho.p, 3 * E * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   return 0;

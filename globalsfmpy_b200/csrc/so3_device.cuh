@@ -61,15 +61,18 @@ __host__ __device__ inline void quat_log(Q4 q, double* e, double* theta2_out, do
   if (q.w < 0.0) { q.w = -q.w; q.x = -q.x; q.y = -q.y; q.z = -q.z; }
   const double s2 = q.x * q.x + q.y * q.y + q.z * q.z;
   double k = 2.0, theta2 = 0.0, c = 1.0 / 12.0;
-  if (s2 > 0.0) {
+  if (s2 > 1e-280) {
     const double s = sqrt(s2);
     const double theta = 2.0 * atan2(s, q.w);
-    k = theta / s;
+    // one reciprocal serves theta/s, 1/theta^2 and w/(2 theta s): 1/theta = s inv, 1/s = theta inv
+    const double inv = 1.0 / (theta * s);
+    const double it = s * inv, is = theta * inv;
+    k = theta * is;
     theta2 = theta * theta;
     if (theta2 < 1e-2) {
       c = 1.0 / 12.0 + theta2 * (1.0 / 720.0 + theta2 * (1.0 / 30240.0 + theta2 * (1.0 / 1209600.0 + theta2 * (1.0 / 47900160.0))));
     } else {
-      c = 1.0 / theta2 - q.w / (2.0 * theta * s);
+      c = it * (it - 0.5 * q.w * is);
     }
   }
   e[0] = q.x * k; e[1] = q.y * k; e[2] = q.z * k;
@@ -145,6 +148,7 @@ struct DevLoss {
   int kind;
   unsigned flags;
   double p0, p1, scale;
+  double sq0, inv_sq0;        // p0^2 and 1 / p0^2, rounded exactly as the formulas below would compute them
   // MAGSAC (scripts/loss_functions.py:285-459), constants of include/gamma_values.cpp
   int nu;
   int table_size;
@@ -203,23 +207,25 @@ __host__ __device__ inline void magsac_loss(const DevLoss& L, double s_in, doubl
   }
 }
 
+// kKind >= 0 fixes the loss at compile time (the switch folds away); kKind < 0 dispatches on L.kind.
+template <int kKind = -1>
 __host__ __device__ inline void eval_loss(const DevLoss& L, double s, double* out) {
-  switch (L.kind) {
+  switch (kKind < 0 ? L.kind : kKind) {
     case kLossTrivial: out[0] = s; out[1] = 1.0; out[2] = 0.0; break;
     case kLossHuber: {
-      const double a = L.p0, b = a * a;
+      const double a = L.p0, b = L.sq0;
       if (s > b) { const double r = sqrt(s); out[0] = 2.0 * a * r - b; out[1] = fmax(a / r, DBL_MIN); out[2] = -out[1] / (2.0 * s); }
       else { out[0] = s; out[1] = 1.0; out[2] = 0.0; }
       break;
     }
     case kLossSoftLOne: {
-      const double b = L.p0 * L.p0, c = 1.0 / b;
+      const double b = L.sq0, c = L.inv_sq0;
       const double sum = 1.0 + s * c, tmp = sqrt(sum);
       out[0] = 2.0 * b * (tmp - 1.0); out[1] = fmax(1.0 / tmp, DBL_MIN); out[2] = -(c * out[1]) / (2.0 * sum);
       break;
     }
     case kLossCauchy: {
-      const double b = L.p0 * L.p0, c = 1.0 / b;
+      const double b = L.sq0, c = L.inv_sq0;
       const double sum = 1.0 + s * c, inv = 1.0 / sum;
       out[0] = b * log(sum); out[1] = fmax(inv, DBL_MIN); out[2] = -c * (inv * inv);
       break;
@@ -305,7 +311,7 @@ __host__ __device__ inline double triggs_kappa(double s, const double* rho) {
 // kResidual = 1: r = -2 w vec(q_E) = 2 w vec(q_ij (q_j q_i^-1)^-1)   (QUATERNION_COSINE,
 //                include/pairwise_rotation_error_quat.hpp:82-106; w = U[0]);  A = w ([v_E]x - w_E I).
 //                No logarithm, smooth through theta = pi.
-template <bool kNeedJacobian, int kResidual = 0, bool kScalarU = false>
+template <bool kNeedJacobian, int kResidual = 0, bool kScalarU = false, int kLoss = -1>
 __host__ __device__ inline void edge_terms(const Q4& qi, const Q4& qj, const Q4& qij, const double* U, const DevLoss& L, EdgeTerms& o) {
   const Q4 qE = qmul(qmul(qj, qconj(qi)), qconj(qij));  // error rotation R_j R_i^T R_ij^T
   double M[9];                                           // d r / d(left perturbation of E) before the weight
@@ -331,7 +337,7 @@ __host__ __device__ inline void edge_terms(const Q4& qi, const Q4& qj, const Q4&
     }
   }
   const double s = o.r[0] * o.r[0] + o.r[1] * o.r[1] + o.r[2] * o.r[2];
-  eval_loss(L, s, o.rho);
+  eval_loss<kLoss>(L, s, o.rho);
   if (!kNeedJacobian) return;
   if (kResidual == 1) {
     M[0] = -qE.w; M[1] = -qE.z; M[2] = qE.y;
@@ -368,6 +374,95 @@ __host__ __device__ inline void edge_terms(const Q4& qi, const Q4& qj, const Q4&
   o.S[4] = rho1 * (B[1] * B[2] + B[4] * B[5] + B[7] * B[8] - kappa * u[1] * u[2]);
   o.S[5] = rho1 * (B[2] * B[2] + B[5] * B[5] + B[8] * B[8] - kappa * u[2] * u[2]);
   o.v[0] = rho1 * u[0]; o.v[1] = rho1 * u[1]; o.v[2] = rho1 * u[2];
+}
+
+// ------------------------------------------------------------------------------------------
+// The two residuals that are NOT functions of the error rotation alone (general two-block edges):
+//   kType 0  QUATERNION_NORM      include/pairwise_rotation_error_quat.hpp:125-150, 4 residuals
+//            r = w (s_b q_b - s_e q_e), q_e = q_ij q_a, s = -1 where the quaternion's y coefficient is negative
+//   kType 1  ROTATION_MAT_FNORM   include/pairwise_rotation_error_quat.hpp:169-196, 9 residuals
+//            r = w vec(R_ij R_a - R_b)
+// Body-frame Jacobians (q <- q (x) [beta/2, 1], R <- R Exp(beta)); with M(q) = d(q (x) [beta, 0])/d beta (4x3, rows x,y,z,w):
+//   type 0:  J_b = (w s_b / 2) M(q_b),   J_a = -(w s_e / 2) M(q_e)
+//   type 1:  column k of J_b = -w vec(R_b [e_k]x),   of J_a = +w vec(R_e [e_k]x),  R_e = R_ij R_a
+// The caller names the view whose ROW is being assembled: outputs are that row's diagonal contribution
+// D = rho' (Jr^T Jr - kappa ur ur^T), off-diagonal block G = rho' (Jr^T Jc - kappa ur uc^T) (row-major, row view x column
+// view), gradient g = rho' ur, with ur = Jr^T r, uc = Jc^T r.
+// ------------------------------------------------------------------------------------------
+struct GeneralTerms {
+  double D[6];
+  double G[9];
+  double g[3];
+  double rho[3];
+};
+
+__host__ __device__ inline void quat_right_jac(const Q4& q, double k, double* M /*4x3*/) {
+  M[0] = k * q.w;  M[1] = -k * q.z; M[2] = k * q.y;
+  M[3] = k * q.z;  M[4] = k * q.w;  M[5] = -k * q.x;
+  M[6] = -k * q.y; M[7] = k * q.x;  M[8] = k * q.w;
+  M[9] = -k * q.x; M[10] = -k * q.y; M[11] = -k * q.z;
+}
+// columns of k * R [e_k]x stacked as a 9x3 Jacobian; residual index 3*c + r (Eigen's column-major linear index)
+__host__ __device__ inline void rot_right_jac(const double* R, double k, double* J /*9x3*/) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const double r0 = k * R[3 * r], r1 = k * R[3 * r + 1], r2 = k * R[3 * r + 2];
+    // d/d beta_x: (0, R[:,2], -R[:,1]);  d/d beta_y: (-R[:,2], 0, R[:,0]);  d/d beta_z: (R[:,1], -R[:,0], 0)
+    J[3 * (0 + r) + 0] = 0.0;  J[3 * (0 + r) + 1] = -r2;  J[3 * (0 + r) + 2] = r1;   // column c = 0 of the matrix
+    J[3 * (3 + r) + 0] = r2;   J[3 * (3 + r) + 1] = 0.0;  J[3 * (3 + r) + 2] = -r0;  // c = 1
+    J[3 * (6 + r) + 0] = -r1;  J[3 * (6 + r) + 1] = r0;   J[3 * (6 + r) + 2] = 0.0;  // c = 2
+  }
+}
+
+template <bool kNeedJacobian, int kType>
+__host__ __device__ inline void general_edge_terms(const Q4& qa, const Q4& qb, const Q4& qij, double w, bool row_is_b, const DevLoss& L,
+                                                   GeneralTerms& o) {
+  constexpr int kDim = (kType == 0) ? 4 : 9;
+  double r[kDim], Ja[3 * kDim], Jb[3 * kDim];
+  if (kType == 0) {
+    const Q4 qe = qmul(qij, qa);
+    const double sb = (qb.y < 0.0) ? -1.0 : 1.0, se = (qe.y < 0.0) ? -1.0 : 1.0;
+    r[0] = w * (sb * qb.x - se * qe.x); r[1] = w * (sb * qb.y - se * qe.y);
+    r[2] = w * (sb * qb.z - se * qe.z); r[3] = w * (sb * qb.w - se * qe.w);
+    if (kNeedJacobian) { quat_right_jac(qb, 0.5 * w * sb, Jb); quat_right_jac(qe, -0.5 * w * se, Ja); }
+  } else {
+    double Ra[9], Rb[9], Rr[9], Re[9];
+    quat_to_mat(qa, Ra); quat_to_mat(qb, Rb); quat_to_mat(qij, Rr);
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) Re[3 * rr + c] = Rr[3 * rr] * Ra[c] + Rr[3 * rr + 1] * Ra[3 + c] + Rr[3 * rr + 2] * Ra[6 + c];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr) r[3 * c + rr] = w * (Re[3 * rr + c] - Rb[3 * rr + c]);
+    if (kNeedJacobian) { rot_right_jac(Re, w, Ja); rot_right_jac(Rb, -w, Jb); }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < kDim; ++q) s += r[q] * r[q];
+  eval_loss(L, s, o.rho);
+  if (!kNeedJacobian) return;
+  const double* Jr = row_is_b ? Jb : Ja;
+  const double* Jc = row_is_b ? Ja : Jb;
+  double ur[3] = {0, 0, 0}, uc[3] = {0, 0, 0};
+#pragma unroll
+  for (int q = 0; q < kDim; ++q)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { ur[c] += Jr[3 * q + c] * r[q]; uc[c] += Jc[3 * q + c] * r[q]; }
+  const double kappa = triggs_kappa(s, o.rho), rho1 = o.rho[1];
+  int t = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      double jj = 0.0, jc = 0.0;
+#pragma unroll
+      for (int q = 0; q < kDim; ++q) { jj += Jr[3 * q + a] * Jr[3 * q + b]; jc += Jr[3 * q + a] * Jc[3 * q + b]; }
+      o.G[3 * a + b] = rho1 * (jc - kappa * ur[a] * uc[b]);
+      if (b >= a) o.D[t++] = rho1 * (jj - kappa * ur[a] * ur[b]);
+    }
+  o.g[0] = rho1 * ur[0]; o.g[1] = rho1 * ur[1]; o.g[2] = rho1 * ur[2];
 }
 
 // Whitening, src/GSfM_nonlinear_rotation_estimator.cpp:251-288:

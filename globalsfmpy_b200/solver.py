@@ -36,7 +36,8 @@ def whiten(prob, device=-1):
 def eval_edges(prob, loss, omega, device=-1):
     E = prob.num_edges
     omega = _omega(prob, omega)
-    r, Ji, Jj, rho = np.zeros((E, 3)), np.zeros((E, 3, 3)), np.zeros((E, 3, 3)), np.zeros((E, 3))
+    d = capi.residual_dim(prob.c.error_type)
+    r, Ji, Jj, rho = np.zeros((E, d)), np.zeros((E, d, 3)), np.zeros((E, d, 3)), np.zeros((E, 3))
     capi.check(capi.lib().gsfm_ra_eval_edges(C.byref(prob.c), C.byref(loss), capi.ptr(omega), capi.ptr(r), capi.ptr(Ji),
                                              capi.ptr(Jj), capi.ptr(rho), device))
     return r, Ji, Jj, rho

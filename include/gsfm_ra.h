@@ -253,8 +253,13 @@ void* gsfm_ra_solver_cuda_stream(gsfm_ra_solver* solver);
 int gsfm_ra_solver_time_kernels(gsfm_ra_solver* solver, int32_t repeats, double* out_ms /*[4]*/);
 
 /* ---- kernel-level entry points (parity tests, profiling) ---------------------*/
-/* K1 per edge, at omega [N][3]: raw residual r [E][3], raw Jacobians
- * d r/d omega_i, d r/d omega_j [E][9] row-major, and rho[E][3] = loss at |r|^2.
+/* Residual dimension of an error type: 4 for QUATERNION_NORM (include/pairwise_rotation_error_quat.hpp:125-150),
+ * 9 for ROTATION_MAT_FNORM (:169-196), 3 otherwise. */
+int gsfm_ra_residual_dim(int32_t error_type);
+
+/* K1 per edge, at omega [N][3]: raw residual r [E][d], raw Jacobians w.r.t. the parameters Ceres optimises
+ * (the angle-axis vector for types 3..8; the 3 local coordinates of EigenQuaternionParameterization for types 0..2)
+ * d r/d x_i, d r/d x_j [E][d][3] row-major, d = gsfm_ra_residual_dim(error_type), and rho[E][3] = loss at |r|^2.
  * Any output pointer may be NULL.  Replaces one AutoDiffCostFunction::Evaluate +
  * LossFunction::Evaluate per edge (src/pairwise_rotation_error.cpp:75-85,
  * bind_src/GlobalSfMpy.cpp:36-59).                                             */

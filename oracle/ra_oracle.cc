@@ -175,6 +175,46 @@ void QuatCosineResidual(const T* qa, const T* qb, const double* qrel, double wei
   QMul(rel, est_conj, dq);
   for (int k = 0; k < 3; ++k) res[k] = T(weight) * T(2.0) * dq[k];
 }
+/* include/pairwise_rotation_error_quat.hpp:125-150 (PairwiseRotationErrorQuatFNorm): q_b_estimated = q_rel * q_a; both q_b and
+ * the estimate are negated when their coeffs()[1] (the y component in Eigen's x,y,z,w order) is negative; 4 residuals. */
+template <typename T>
+void QuatFNormResidual(const T* qa, const T* qb, const double* qrel, double weight, T* res) {
+  const T rel[4] = {T(qrel[0]), T(qrel[1]), T(qrel[2]), T(qrel[3])};
+  T est[4];
+  QMul(rel, qa, est);
+  const bool flip_b = val(qb[1]) < 0.0, flip_e = val(est[1]) < 0.0;
+  for (int k = 0; k < 4; ++k) {
+    const T b = flip_b ? -qb[k] : qb[k];
+    const T e = flip_e ? -est[k] : est[k];
+    res[k] = T(weight) * (b - e);
+  }
+}
+/* Eigen::QuaternionBase::toRotationMatrix (no normalisation), coefficients (x,y,z,w) */
+template <typename T>
+void EigenQuatToMatrix(const T* q, Mat3<T>* R) {
+  const T tx = T(2.0) * q[0], ty = T(2.0) * q[1], tz = T(2.0) * q[2];
+  const T twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
+  const T txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
+  const T tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+  R->m[0][0] = T(1.0) - (tyy + tzz); R->m[0][1] = txy - twz;          R->m[0][2] = txz + twy;
+  R->m[1][0] = txy + twz;          R->m[1][1] = T(1.0) - (txx + tzz); R->m[1][2] = tyz - twx;
+  R->m[2][0] = txz - twy;          R->m[2][1] = tyz + twx;          R->m[2][2] = T(1.0) - (txx + tyy);
+}
+/* include/pairwise_rotation_error_quat.hpp:169-196 (PairwiseRotationErrorRotFNorm): residual(k) = w (R_rel R_a - R_b)(k) with
+ * Eigen's linear (column-major) index k = 0..8. */
+template <typename T>
+void RotFNormResidual(const T* qa, const T* qb, const double* qrel, double weight, T* res) {
+  Mat3<T> Ra, Rb;
+  Mat3<double> Rr;
+  EigenQuatToMatrix(qa, &Ra);
+  EigenQuatToMatrix(qb, &Rb);
+  EigenQuatToMatrix(qrel, &Rr);
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) {
+      T est = T(Rr.m[r][0]) * Ra.m[0][c] + T(Rr.m[r][1]) * Ra.m[1][c] + T(Rr.m[r][2]) * Ra.m[2][c];
+      res[3 * c + r] = T(weight) * (est - Rb.m[r][c]);
+    }
+}
 /* ceres AngleAxisToQuaternion, output in Eigen coefficient order (x,y,z,w) as rotation_estimator.cpp:127-136 builds it */
 void AngleAxisToQuatXYZW(const double* w, double* q) {
   const double t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
@@ -215,15 +255,19 @@ void QuatPlusJacobian(const double* x, double* J /*4x3 row-major*/) {
   J[9] = -x[0]; J[10] = -x[1]; J[11] = -x[2];
 }
 /* one quaternion edge through jets; Jacobians returned in the 3-dim LOCAL (tangent) coordinates Ceres optimises in:
- * J_local = J_ambient(3x4) * PlusJacobian(4x3). */
-void QuatEdge(const double* qa, const double* qb, const double* qrel, double weight, double* r, double* Ji, double* Jj) {
-  Jet a[4], b[4], res[3];
+ * J_local = J_ambient(dim x 4) * PlusJacobian(4x3).  type selects the functor (0: QuatFNorm, 1: RotFNorm, 2: Quat). */
+int ResidualDim(int type) { return type == GSFM_RA_QUATERNION_NORM ? 4 : (type == GSFM_RA_ROTATION_MAT_FNORM ? 9 : 3); }
+void QuatEdge(int type, const double* qa, const double* qb, const double* qrel, double weight, double* r, double* Ji, double* Jj) {
+  Jet a[4], b[4], res[9];
   for (int k = 0; k < 4; ++k) { a[k] = Jet(qa[k]); a[k].v[k] = 1.0; b[k] = Jet(qb[k]); b[k].v[4 + k] = 1.0; }
-  QuatCosineResidual<Jet>(a, b, qrel, weight, res);
+  if (type == GSFM_RA_QUATERNION_NORM) QuatFNormResidual<Jet>(a, b, qrel, weight, res);
+  else if (type == GSFM_RA_ROTATION_MAT_FNORM) RotFNormResidual<Jet>(a, b, qrel, weight, res);
+  else QuatCosineResidual<Jet>(a, b, qrel, weight, res);
+  const int dim = ResidualDim(type);
   double Pa[12], Pb[12];
   QuatPlusJacobian(qa, Pa);
   QuatPlusJacobian(qb, Pb);
-  for (int q = 0; q < 3; ++q) {
+  for (int q = 0; q < dim; ++q) {
     if (r) r[q] = res[q].a;
     for (int c = 0; c < 3; ++c) {
       double si = 0, sj = 0;
@@ -411,8 +455,8 @@ bool TypeNeedsCov(int type) {
   return type == GSFM_RA_ANGLE_AXIS_COVARIANCE || type == GSFM_RA_ANGLE_AXIS_COV_INLIERS ||
          type == GSFM_RA_ANGLE_AXIS_COVTRACE || type == GSFM_RA_ANGLE_AXIS_COVNORM;
 }
-bool TypeSupported(int type) { return type == GSFM_RA_QUATERNION_COSINE || (type >= GSFM_RA_ANGLE_AXIS_COVARIANCE && type <= GSFM_RA_ANGLE_AXIS_COVNORM); }
-bool IsQuat(const gsfm_ra_problem* p) { return p->error_type == GSFM_RA_QUATERNION_COSINE; }
+bool TypeSupported(int type) { return type >= GSFM_RA_QUATERNION_NORM && type <= GSFM_RA_ANGLE_AXIS_COVNORM; }
+bool IsQuat(const gsfm_ra_problem* p) { return p->error_type <= GSFM_RA_QUATERNION_COSINE; }
 
 void EdgeU(const gsfm_ra_problem* p, uint64_t k, double* U) {
   Whiten(p->error_type, p->cov6 ? p->cov6 + 6 * k : nullptr, p->edge_weight ? p->edge_weight[k] : 1.0, U);
@@ -430,15 +474,20 @@ struct LossEval {
 
 /* One robustified residual block: ceres ResidualBlock::Evaluate + Corrector
  * (SURVEY Appendix B.2).  Jacobian is corrected first, from the uncorrected residual. */
-struct EdgeEval { double r[3], Ji[9], Jj[9], rho[3]; };
+struct EdgeEval {
+  int dim;  /* residual dimension: 3, or 4 / 9 for QUATERNION_NORM / ROTATION_MAT_FNORM */
+  double r[9], Ji[27], Jj[27], rho[3];
+  double sq_norm() const { double s = 0; for (int q = 0; q < dim; ++q) s += r[q] * r[q]; return s; }
+};
 
 /* `omega` is the state: [N][3] angle-axis, or [N][4] quaternions (x,y,z,w) for QUATERNION_COSINE */
 void EvalEdgeRaw(const gsfm_ra_problem* p, uint64_t k, const double* omega, EdgeEval* out, bool jac) {
+  out->dim = ResidualDim(p->error_type);
   if (IsQuat(p)) {
     double qrel[4];
     AngleAxisToQuatXYZW(p->omega_ij + 3 * k, qrel);
     const double w = p->edge_weight ? p->edge_weight[k] : 1.0;  /* cost_weight = 1.0, rotation_estimator.cpp:125 */
-    QuatEdge(omega + 4 * (size_t)p->edge_i[k], omega + 4 * (size_t)p->edge_j[k], qrel, w, out->r, jac ? out->Ji : nullptr,
+    QuatEdge(p->error_type, omega + 4 * (size_t)p->edge_i[k], omega + 4 * (size_t)p->edge_j[k], qrel, w, out->r, jac ? out->Ji : nullptr,
              jac ? out->Jj : nullptr);
     return;
   }
@@ -454,7 +503,8 @@ void EvalEdgeRaw(const gsfm_ra_problem* p, uint64_t k, const double* omega, Edge
 }
 
 void Robustify(EdgeEval* e, bool jac) {
-  const double s = e->r[0] * e->r[0] + e->r[1] * e->r[1] + e->r[2] * e->r[2];
+  const int dim = e->dim;
+  const double s = e->sq_norm();
   const double sqrt_rho1 = std::sqrt(e->rho[1]);
   double residual_scaling, alpha_sq_norm;
   if (s == 0.0 || e->rho[2] <= 0.0) {
@@ -469,16 +519,17 @@ void Robustify(EdgeEval* e, bool jac) {
   if (jac) {
     for (double* J : {e->Ji, e->Jj}) {
       if (alpha_sq_norm == 0.0) {
-        for (int k = 0; k < 9; ++k) J[k] *= sqrt_rho1;
+        for (int k = 0; k < 3 * dim; ++k) J[k] *= sqrt_rho1;
       } else {
         for (int c = 0; c < 3; ++c) {
-          const double rtj = e->r[0] * J[c] + e->r[1] * J[3 + c] + e->r[2] * J[6 + c];
-          for (int r = 0; r < 3; ++r) J[3 * r + c] = sqrt_rho1 * (J[3 * r + c] - alpha_sq_norm * e->r[r] * rtj);
+          double rtj = 0;
+          for (int r = 0; r < dim; ++r) rtj += e->r[r] * J[3 * r + c];
+          for (int r = 0; r < dim; ++r) J[3 * r + c] = sqrt_rho1 * (J[3 * r + c] - alpha_sq_norm * e->r[r] * rtj);
         }
       }
     }
   }
-  for (int k = 0; k < 3; ++k) e->r[k] *= residual_scaling;
+  for (int k = 0; k < dim; ++k) e->r[k] *= residual_scaling;
 }
 
 int Threads(int n) {
@@ -552,14 +603,12 @@ int Linearize(const gsfm_ra_problem* p, const LossEval& loss, const double* omeg
   for (int64_t k = 0; k < (int64_t)E; ++k) EvalEdgeRaw(p, k, omega, &arr[k], jac);
   if (loss.cb) {
     for (uint64_t k = 0; k < E; ++k) {
-      const double* r = arr[k].r;
-      loss(r[0] * r[0] + r[1] * r[1] + r[2] * r[2], arr[k].rho);
+      loss(arr[k].sq_norm(), arr[k].rho);
     }
   } else {
 #pragma omp parallel for num_threads(nt) schedule(static)
     for (int64_t k = 0; k < (int64_t)E; ++k) {
-      const double* r = arr[k].r;
-      loss(r[0] * r[0] + r[1] * r[1] + r[2] * r[2], arr[k].rho);
+      loss(arr[k].sq_norm(), arr[k].rho);
     }
   }
 #pragma omp parallel for num_threads(nt) schedule(static)
@@ -583,12 +632,19 @@ int Linearize(const gsfm_ra_problem* p, const LossEval& loss, const double* omeg
     double* Hij = &L->hoff[9 * S.slot_ij[k]];
     double* Hji = &L->hoff[9 * S.slot_ji[k]];
     for (int a = 0; a < 3; ++a) {
-      gi[a] += e.Ji[a] * e.r[0] + e.Ji[3 + a] * e.r[1] + e.Ji[6 + a] * e.r[2];
-      gj[a] += e.Jj[a] * e.r[0] + e.Jj[3 + a] * e.r[1] + e.Jj[6 + a] * e.r[2];
+      double ga = 0, gb = 0;
+      for (int q = 0; q < e.dim; ++q) { ga += e.Ji[3 * q + a] * e.r[q]; gb += e.Jj[3 * q + a] * e.r[q]; }
+      gi[a] += ga;
+      gj[a] += gb;
       for (int b = 0; b < 3; ++b) {
-        Hii[3 * a + b] += e.Ji[a] * e.Ji[b] + e.Ji[3 + a] * e.Ji[3 + b] + e.Ji[6 + a] * e.Ji[6 + b];
-        Hjj[3 * a + b] += e.Jj[a] * e.Jj[b] + e.Jj[3 + a] * e.Jj[3 + b] + e.Jj[6 + a] * e.Jj[6 + b];
-        const double hij = e.Ji[a] * e.Jj[b] + e.Ji[3 + a] * e.Jj[3 + b] + e.Ji[6 + a] * e.Jj[6 + b];
+        double hii = 0, hjj = 0, hij = 0;
+        for (int q = 0; q < e.dim; ++q) {
+          hii += e.Ji[3 * q + a] * e.Ji[3 * q + b];
+          hjj += e.Jj[3 * q + a] * e.Jj[3 * q + b];
+          hij += e.Ji[3 * q + a] * e.Jj[3 * q + b];
+        }
+        Hii[3 * a + b] += hii;
+        Hjj[3 * a + b] += hjj;
         Hij[3 * a + b] = hij;
         Hji[3 * b + a] = hij;
       }
@@ -784,10 +840,11 @@ int ra_oracle_eval_edges(const gsfm_ra_problem* p, const gsfm_ra_loss* loss, con
   for (int64_t k = 0; k < (int64_t)p->num_edges; ++k) {
     EdgeEval e;
     EvalEdgeRaw(p, k, omega, &e, true);
-    if (r) for (int q = 0; q < 3; ++q) r[3 * k + q] = e.r[q];
-    if (Ji) for (int q = 0; q < 9; ++q) Ji[9 * k + q] = e.Ji[q];
-    if (Jj) for (int q = 0; q < 9; ++q) Jj[9 * k + q] = e.Jj[q];
-    if (rho && loss) ra_oracle_loss(loss, e.r[0] * e.r[0] + e.r[1] * e.r[1] + e.r[2] * e.r[2], rho + 3 * k);
+    const int d = e.dim;
+    if (r) for (int q = 0; q < d; ++q) r[d * k + q] = e.r[q];
+    if (Ji) for (int q = 0; q < 3 * d; ++q) Ji[3 * d * k + q] = e.Ji[q];
+    if (Jj) for (int q = 0; q < 3 * d; ++q) Jj[3 * d * k + q] = e.Jj[q];
+    if (rho && loss) ra_oracle_loss(loss, e.sq_norm(), rho + 3 * k);
   }
   return 0;
 }

@@ -45,7 +45,8 @@ void ra_oracle_whiten(int error_type, const double* cov6, double edge_weight, do
 void ra_oracle_edge(const double* wi, const double* wj, const double* wij, const double* U,
                     double* r, double* Ji, double* Jj);
 
-/* All edges: r [E][3], Ji/Jj [E][9], rho [E][3]; any output may be NULL. */
+/* All edges: r [E][d], Ji/Jj [E][d][3], rho [E][3], d = the residual dimension of the error type (3; 4 for QUATERNION_NORM,
+ * 9 for ROTATION_MAT_FNORM); any output may be NULL. */
 int ra_oracle_eval_edges(const gsfm_ra_problem* p, const gsfm_ra_loss* loss, const double* omega,
                          double* r, double* Ji, double* Jj, double* rho, int num_threads);
 

@@ -78,7 +78,8 @@ def edge(wi, wj, wij, U):
 def eval_edges(prob, loss_struct, omega, num_threads=0):
     E = prob.num_edges
     omega = capi.as_f64(omega, (prob.num_views, 3))
-    r, Ji, Jj, rho = np.zeros((E, 3)), np.zeros((E, 3, 3)), np.zeros((E, 3, 3)), np.zeros((E, 3))
+    d = capi.residual_dim(prob.c.error_type)
+    r, Ji, Jj, rho = np.zeros((E, d)), np.zeros((E, d, 3)), np.zeros((E, d, 3)), np.zeros((E, 3))
     rc = lib().ra_oracle_eval_edges(C.byref(prob.c), C.byref(loss_struct), _p(omega), _p(r), _p(Ji), _p(Jj), _p(rho),
                                     num_threads)
     assert rc == 0, rc

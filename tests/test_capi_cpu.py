@@ -60,7 +60,8 @@ def test_invalid_arguments_are_rejected_before_the_device():
     with pytest.raises(capi.GsfmError) as e:
         solver.solve(prob, capi.default_options_py(), g.omega_init)
     assert e.value.code == capi.ERR_INVALID
-    prob = capi.ProblemArrays(6, g.edge_i, g.edge_j, g.omega_ij, error_type=capi.QUATERNION_NORM)
+    prob = capi.ProblemArrays(6, g.edge_i, g.edge_j, g.omega_ij, error_type=9)  # not a RotationErrorType
     with pytest.raises(capi.GsfmError) as e:
         solver.solve(prob, capi.default_options_py(), g.omega_init)
-    assert e.value.code == capi.ERR_UNSUPPORTED
+    assert e.value.code == capi.ERR_INVALID
+    assert [capi.lib().gsfm_ra_residual_dim(t) for t in range(9)] == [4, 9, 3, 3, 3, 3, 3, 3, 3]

@@ -356,6 +356,47 @@ def test_quaternion_cosine_type():
     assert np.degrees(vg.mean_angular_error(g.omega_gt, og)[1]) < 3.0
 
 
+@pytest.mark.parametrize("etype", [capi.QUATERNION_NORM, capi.ROTATION_MAT_FNORM])
+def test_general_two_block_types(etype):
+    """RotationErrorType.QUATERNION_NORM (4 residuals, include/pairwise_rotation_error_quat.hpp:125-150) and ROTATION_MAT_FNORM
+    (9 residuals, :169-196) of EstimateRotationsWithCustomizedLoss (rotation_estimator.cpp:82-198).  These residuals are not
+    functions of the error rotation alone, so the two Jacobian blocks are unrelated: the kernel assembles a general block pair
+    (9-double records).  The oracle differentiates the functors with 8-wide jets and EigenQuaternionParameterization."""
+    g = vg.synthetic_pose_graph(150, 2000, seed=21, noise_deg=2.0, outlier_fraction=0.15)
+    prob = capi.ProblemArrays(150, g.edge_i, g.edge_j, g.omega_ij, error_type=etype)
+    rng = np.random.default_rng(8)
+    omega = g.omega_init + 0.05 * rng.normal(size=g.omega_init.shape)
+    for L in (capi.Loss.make(capi.LOSS_HUBER, 0.05), capi.Loss.make(capi.LOSS_MAGSAC9, 0.05)):  # MAGSAC9: rho'' > 0 -> Triggs term
+        r, Ji, Jj, rho = solver.eval_edges(prob, L, omega)
+        r0, Ji0, Jj0, rho0 = orc.eval_edges(prob, L, omega)
+        assert r.shape == (2000, capi.residual_dim(etype))
+        assert rel_err_rows(r, r0) < 1e-10
+        assert rel_err_rows(Ji, Ji0) < 1e-10 and rel_err_rows(Jj, Jj0) < 1e-10
+        assert np.allclose(rho, rho0, rtol=1e-9, atol=1e-12)
+        c, gr, hd, rp, col, val = solver.assemble(prob, L, omega)
+        c0, gr0, hd0, rp0, col0, val0 = orc.assemble(prob, L, omega)
+        assert abs(c - c0) <= 1e-12 * abs(c0)
+        assert_close(gr, gr0, 1e-9, "gradient (local coordinates)")
+        assert_close(hd, hd0, 1e-9, "diagonal blocks")
+        assert_close(val, val0, 1e-9, "off-diagonal blocks")
+    L = capi.Loss.make(capi.LOSS_HUBER, 0.05)
+    o = capi.default_options_py()
+    o.loss = L
+    o.pcg_rtol = 1e-13
+    o.pcg_max_iterations = 2000
+    og, sg, tg = solver.solve(prob, o, g.omega_init, trace_capacity=256)
+    o.linear_solver = capi.SOLVER_DENSE_CHOLESKY
+    oo, so, to = orc.solve(prob, o, g.omega_init, trace_capacity=256)
+    assert sg.termination == so.termination and sg.num_iterations == so.num_iterations
+    for a, b in zip(tg, to):
+        assert a.step_is_successful == b.step_is_successful and abs(a.cost - b.cost) <= 1e-8 * abs(b.cost)
+    assert vg.mean_angular_error(oo, og)[0] < 1e-6
+    # the dense Cholesky path reads the 9-double records too
+    og2, _, _ = solver.solve(prob, o, g.omega_init)
+    assert vg.mean_angular_error(og2, og)[0] < 1e-7
+    assert np.degrees(vg.mean_angular_error(g.omega_gt, og)[1]) < 3.0
+
+
 def test_sigma_consensus_matches_oracle():
     """EstimateRotationsWithSigmaConsensus (rotation_estimator.cpp:314-457): outer re-weighting loop."""
     g = vg.synthetic_pose_graph(120, 1500, seed=77, noise_deg=1.0, outlier_fraction=0.15)

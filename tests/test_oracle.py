@@ -194,3 +194,67 @@ def test_filter_view_pairs():
     assert np.abs(ang - ref).max() < 1e-12
     assert np.array_equal(keep, ref <= np.radians(15.0))
     assert keep[~g.is_outlier].all() and (~keep[g.is_outlier]).mean() > 0.9
+
+
+def _quat_xyzw(w):
+    """ceres AngleAxisToQuaternion, Eigen coefficient order (x, y, z, w)."""
+    t = np.linalg.norm(w)
+    if t == 0:
+        return np.array([0.0, 0.0, 0.0, 1.0])
+    return np.concatenate([np.sin(t / 2) * w / t, [np.cos(t / 2)]])
+
+
+def _qmul_xyzw(a, b):
+    av, aw, bv, bw = a[:3], a[3], b[:3], b[3]
+    return np.concatenate([aw * bv + bw * av + np.cross(av, bv), [aw * bw - av @ bv]])
+
+
+def _eigen_rot(q):
+    """Eigen::Quaternion::toRotationMatrix, coefficients (x, y, z, w)."""
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def _general_residual(etype, qa, qb, qrel):
+    """include/pairwise_rotation_error_quat.hpp:125-150 (QuatFNorm) and :169-196 (RotFNorm), restated with numpy."""
+    if etype == capi.QUATERNION_NORM:
+        est = _qmul_xyzw(qrel, qa)
+        b = -qb if qb[1] < 0 else qb
+        e = -est if est[1] < 0 else est
+        return b - e
+    return (_eigen_rot(qrel) @ _eigen_rot(qa) - _eigen_rot(qb)).reshape(-1, order="F")  # Eigen linear index = column-major
+
+
+@pytest.mark.parametrize("etype", [capi.QUATERNION_NORM, capi.ROTATION_MAT_FNORM])
+def test_general_residual_types(etype):
+    """The oracle's jet evaluation of the 4- and 9-dimensional functors against a numpy restatement of the reference formulas,
+    and its local-coordinate Jacobians against finite differences through EigenQuaternionParameterization::Plus
+    (x (+) d = [sin|d| d/|d|, cos|d|] (x) x)."""
+    g = vg.synthetic_pose_graph(12, 40, seed=3, noise_deg=5.0, outlier_fraction=0.2)
+    prob = capi.ProblemArrays(12, g.edge_i, g.edge_j, g.omega_ij, error_type=etype)
+    rng = np.random.default_rng(0)
+    omega = g.omega_init + 0.1 * rng.normal(size=g.omega_init.shape)
+    L = capi.Loss.make(capi.LOSS_TRIVIAL)
+    r, Ji, Jj, _ = orc.eval_edges(prob, L, omega)
+    d = capi.residual_dim(etype)
+    assert r.shape == (40, d) and Ji.shape == (40, d, 3)
+
+    def plus(q, dl):
+        n = np.linalg.norm(dl)
+        return _qmul_xyzw(np.concatenate([np.sin(n) * dl / n, [np.cos(n)]]), q) if n > 0 else q
+
+    h = 1e-6
+    for k in range(40):
+        qa, qb, qrel = _quat_xyzw(omega[g.edge_i[k]]), _quat_xyzw(omega[g.edge_j[k]]), _quat_xyzw(g.omega_ij[k])
+        assert np.allclose(r[k], _general_residual(etype, qa, qb, qrel), atol=1e-14)
+        for c in range(3):
+            e = np.zeros(3); e[c] = h
+            fa = (_general_residual(etype, plus(qa, e), qb, qrel) - _general_residual(etype, plus(qa, -e), qb, qrel)) / (2 * h)
+            fb = (_general_residual(etype, qa, plus(qb, e), qrel) - _general_residual(etype, qa, plus(qb, -e), qrel)) / (2 * h)
+            assert np.allclose(Ji[k][:, c], fa, atol=1e-8) and np.allclose(Jj[k][:, c], fb, atol=1e-8)
+    # the solve runs and reduces the cost
+    o = _opts(capi.Loss.make(capi.LOSS_HUBER, 0.1), linear_solver=capi.SOLVER_DENSE_CHOLESKY)
+    om, s, _ = orc.solve(prob, o, g.omega_init)
+    assert s.final_cost < s.initial_cost and np.isfinite(om).all()
