@@ -151,23 +151,33 @@ __device__ bool grid_sum(double (&v)[NV], double* slots, unsigned* counter, doub
 }
 
 // ------------------------------------------------------------------------------------------
-// K0 setup: per half-edge, gather the edge's measurement and weight, store planar.
-//   qij[4][H] unit quaternion of omega_ij, U[6][H] whitening (rotation_estimator.cpp:251-288)
+// K0 setup: per half-edge, gather the edge's measurement and weight into K1's INPUT RECORDS, one record per 32
+// consecutive half-edges:
+//   { double qij[4][32]; double U[kU][32]; uint32_t col[32]; uint32_t row[32]; }      128 B aligned
+//   qij = unit quaternion of omega_ij, U = whitening (rotation_estimator.cpp:251-288), kU = 6 (upper triangle) or 1
+//   (scalar weight); col carries the side bit.  1536 B (kU = 1) / 2816 B (kU = 6) per record: K1 pulls a record with
+//   ONE bulk async copy.
 // ------------------------------------------------------------------------------------------
-__global__ void k_setup_halfedges(uint64_t H, const uint32_t* __restrict__ he_edge, const double* __restrict__ omega_ij,
-                                  const double* __restrict__ cov6, const double* __restrict__ weight, int error_type,
-                                  double* __restrict__ qij, double* __restrict__ U) {
+__device__ __host__ __forceinline__ int in_rec_doubles(int ku) { return (4 + ku) * 32 + 32; }
+
+__global__ void k_setup_halfedges(uint64_t H, int ku, const uint32_t* __restrict__ he_edge, const uint32_t* __restrict__ he_row,
+                                  const uint32_t* __restrict__ he_col, const double* __restrict__ omega_ij, const double* __restrict__ cov6,
+                                  const double* __restrict__ weight, int error_type, double* __restrict__ inrec) {
   const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= H) return;
   const uint64_t k = he_edge[h];
   const Q4 q = aa_to_quat(omega_ij[3 * k], omega_ij[3 * k + 1], omega_ij[3 * k + 2]);
-  qij[h] = q.w; qij[H + h] = q.x; qij[2 * H + h] = q.y; qij[3 * H + h] = q.z;
+  double* rec = inrec + (size_t)(h >> 5) * in_rec_doubles(ku);
+  const int lane = (int)(h & 31);
+  rec[lane] = q.w; rec[32 + lane] = q.x; rec[64 + lane] = q.y; rec[96 + lane] = q.z;
   double c6[6] = {0, 0, 0, 0, 0, 0};
   if (cov6) for (int t = 0; t < 6; ++t) c6[t] = cov6[6 * k + t];
   double u[6];
   whiten(error_type, c6, weight ? weight[k] : 1.0, u);
-#pragma unroll
-  for (int t = 0; t < 6; ++t) U[(uint64_t)t * H + h] = u[t];
+  for (int t = 0; t < ku; ++t) rec[(4 + t) * 32 + lane] = u[t];
+  uint32_t* idx = reinterpret_cast<uint32_t*>(rec + (4 + ku) * 32);
+  idx[lane] = he_col[h];
+  idx[32 + lane] = he_row[h];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -291,68 +301,177 @@ __global__ void k_node_prep(uint32_t N, const double* __restrict__ omega, double
 }
 
 // ------------------------------------------------------------------------------------------
-// K1: fused residual + SO(3) Jacobian + whitening + robust loss + normal-equation assembly.
-// One warp per balanced range of half-edges, visited segment by segment (segment = range ^ row).  Each lane
-// evaluates one half-edge per iteration: loads are planar and coalesced (qij 4x8 B, U 6x8 B or 8 B, col 4 B),
-// the row view's quaternion is a warp broadcast, the column view's quaternion is one aligned 32 B gather
-// served by L2.  Writes the off-diagonal block -S of the half-edge (6 doubles, planar, coalesced) and, per
-// segment, the warp-reduced diagonal block / gradient / cost partial.
-// kWriteBlocks=false is K1c: cost only (trial point).
+// TMA record pipeline shared by K1 and K2: every warp keeps kStages bulk async copies (cp.async.bulk, one record
+// each, completion on a warp-private mbarrier) in flight.  Bytes in flight are set by the ring depth, not by
+// registers or occupancy.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_bulk(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct WarpPipe {
+  double* ring;    // this warp's kStages records in shared memory
+  uint64_t* bars;  // this warp's kStages mbarriers
+  uint32_t pos;    // records consumed since init: ring slot = pos % kStages, phase = (pos / kStages) & 1
+};
+
+template <int kRecBytes>
+__device__ __forceinline__ void pipe_init_bytes(WarpPipe& wp, unsigned char* smem) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  wp.ring = reinterpret_cast<double*>(smem + (size_t)warp * kStages * kRecBytes);
+  wp.bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWarpsPerBlock * kStages * kRecBytes) + warp * kStages;
+  wp.pos = 0;
+  if (lane == 0) {
+    for (int st = 0; st < kStages; ++st) mbar_init(&wp.bars[st], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+}
+template <int kBlk>
+__device__ __forceinline__ void pipe_init(WarpPipe& wp, unsigned char* smem) { pipe_init_bytes<Rec<kBlk>::kBytes>(wp, smem); }
+
+// ------------------------------------------------------------------------------------------
+// K1: fused residual + SO(3) Jacobian + whitening + robust loss + normal-equation assembly.
+// One warp per balanced range of half-edges.  The per-half-edge constants arrive as INPUT RECORDS through the TMA
+// ring (see k_setup_halfedges): lane l owns half-edge l of the record, reads its q_ij / U / col / row from shared
+// memory, gathers the two endpoint quaternions (one aligned 32 B sector each, L2; issued one record ahead so the
+// latency overlaps the arithmetic of the current record), evaluates the edge and writes the off-diagonal block -S
+// (6 doubles, planar in the OUTPUT record, coalesced).  Per segment (range ^ row) the warp reduces the diagonal block /
+// gradient / cost partial.  kWriteBlocks=false is K1c: cost only (trial point).
+// ------------------------------------------------------------------------------------------
+struct K1Args {
+  uint32_t num_warps, warp_span;
+  uint64_t H;
+  const uint32_t *warp_seg_ptr, *seg_begin, *seg_len;
+  const double *inrec, *node_q;
+  double *val, *part;
+  DevLoss loss;
+};
+
 template <bool kWriteBlocks, int kResidual, bool kScalarU, int kLoss>
-__global__ void __launch_bounds__(kBlock, 2)
-k_edges(uint32_t num_warps, uint64_t H, const uint32_t* __restrict__ warp_seg_ptr, const uint32_t* __restrict__ task_row,
-        const uint32_t* __restrict__ task_begin, const uint32_t* __restrict__ task_len, const uint32_t* __restrict__ he_col,
-        const double* __restrict__ qij, const double* __restrict__ U, const double* __restrict__ node_q, DevLoss loss,
-        double* __restrict__ val, double* __restrict__ part) {
+__global__ void __launch_bounds__(kBlock, 2) k_edges(const K1Args A) {
+  constexpr int kU = (kScalarU || kResidual == 1) ? 1 : 6;
+  constexpr int kRD = (4 + kU) * 32 + 32;  // doubles per input record
+  constexpr int kRB = kRD * 8;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
-  const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (warp_global >= num_warps) return;
-  for (uint32_t t = warp_seg_ptr[warp_global]; t < warp_seg_ptr[warp_global + 1]; ++t) {
-    const uint32_t row = task_row[t] & ~kSideBit;
-    const uint64_t begin = task_begin[t];
-    const uint32_t len = task_len[t];
-    const double4 qa4 = reinterpret_cast<const double4*>(node_q)[row];
-    const Q4 qa{qa4.x, qa4.y, qa4.z, qa4.w};
-    double acc[kPartStride];
-#pragma unroll
-    for (int k = 0; k < kPartStride; ++k) acc[k] = 0.0;
-    for (uint32_t off = lane; off < len; off += 32) {
-      const uint64_t h = begin + off;
-      const uint32_t cf = he_col[h];
-      const uint32_t col = cf & ~kSideBit;
-      const bool row_is_j = (cf & kSideBit) != 0;
-      const double4 qb4 = reinterpret_cast<const double4*>(node_q)[col];
-      const Q4 qb{qb4.x, qb4.y, qb4.z, qb4.w};
-      const Q4 qm{qij[h], qij[H + h], qij[2 * H + h], qij[3 * H + h]};
-      double u[6];
-      u[0] = U[h];
-      if (!kScalarU && kResidual == 0) {
-#pragma unroll
-        for (int k = 1; k < 6; ++k) u[k] = U[(uint64_t)k * H + h];
-      }
-      EdgeTerms et;
-      edge_terms<kWriteBlocks, kResidual, kScalarU, kLoss>(row_is_j ? qb : qa, row_is_j ? qa : qb, qm, u, loss, et);
-      if (!row_is_j) acc[9] += 0.5 * et.rho[0];  // each edge's cost is counted once, in its i row
-      if (kWriteBlocks) {
-        // both rows of the edge: diag += S, block(row, col) = -S; gradient: +v in row j, -v in row i
-        const double sgn = row_is_j ? 1.0 : -1.0;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) { acc[k] += et.S[k]; val[blk_index(h, k, Rec<6>::kDoubles)] = -et.S[k]; }
-        acc[6] += sgn * et.v[0]; acc[7] += sgn * et.v[1]; acc[8] += sgn * et.v[2];
-      }
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (gw >= A.num_warps) return;
+  WarpPipe wp;
+  pipe_init_bytes<kRB>(wp, smem_raw);
+  const uint64_t lo = (uint64_t)gw * A.warp_span, hi = min(A.H, lo + A.warp_span);
+  const uint32_t t0 = A.warp_seg_ptr[gw], t1 = A.warp_seg_ptr[gw + 1];
+  const uint32_t nrec = (uint32_t)((hi - lo + 31) >> 5);
+  const double* src = A.inrec + (size_t)(lo >> 5) * kRD;
+  auto issue = [&](uint32_t c) {
+    if (lane == 0) {
+      const uint32_t st = c % kStages;
+      mbar_expect_tx(&wp.bars[st], kRB);
+      tma_load_bulk(wp.ring + (size_t)st * kRD, src + (size_t)c * kRD, kRB, &wp.bars[st]);
     }
+  };
+  auto wait_rec = [&](uint32_t c) -> const double* {
+    const uint32_t st = c % kStages;
+    mbar_wait(&wp.bars[st], (c / kStages) & 1u);
+    return wp.ring + (size_t)st * kRD;
+  };
+  auto gather = [&](const double* rec, uint64_t h, uint32_t& cf, Q4& qrow, Q4& qcol) {
+    const uint32_t* idx = reinterpret_cast<const uint32_t*>(rec + (4 + kU) * 32);
+    cf = idx[lane];
+    uint32_t row = idx[32 + lane];
+    if (h >= hi) { cf = 0; row = 0; }  // padding lanes of the last record
+    const double4 a = reinterpret_cast<const double4*>(A.node_q)[row];
+    const double4 b = reinterpret_cast<const double4*>(A.node_q)[cf & ~kSideBit];
+    qrow = Q4{a.x, a.y, a.z, a.w};
+    qcol = Q4{b.x, b.y, b.z, b.w};
+  };
+  for (uint32_t c = 0; c < nrec && c < (uint32_t)kStages; ++c) issue(c);
+  if (nrec == 0 || t0 == t1) return;
+  uint32_t t = t0;
+  uint64_t sb = A.seg_begin[t], se = sb + A.seg_len[t];
+  constexpr int kAcc = kWriteBlocks ? kPartStride : 1;
+  double acc[kAcc];
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+  const double* rec = wait_rec(0);
+  uint32_t cf;
+  Q4 qrow, qcol;
+  gather(rec, lo + lane, cf, qrow, qcol);
+  for (uint32_t c = 0; c < nrec; ++c) {
+    const uint64_t cb = lo + ((uint64_t)c << 5), ce = cb + 32, h = cb + lane;
+    const double* rec_n = nullptr;
+    uint32_t cf_n = 0;
+    Q4 qrow_n{1, 0, 0, 0}, qcol_n{1, 0, 0, 0};
+    if (c + 1 < nrec) { rec_n = wait_rec(c + 1); gather(rec_n, ce + lane, cf_n, qrow_n, qcol_n); }
+    const bool row_is_j = (cf & kSideBit) != 0;
+    const Q4 qm{rec[lane], rec[32 + lane], rec[64 + lane], rec[96 + lane]};
+    double u[6];
+#pragma unroll
+    for (int k = 0; k < kU; ++k) u[k] = rec[(4 + k) * 32 + lane];
+    // this record's slot can be refilled as soon as every lane has read it
+    __syncwarp();
+    if (c + kStages < nrec) issue(c + kStages);
+    EdgeTerms et;
+    edge_terms<kWriteBlocks, kResidual, kScalarU, kLoss>(row_is_j ? qcol : qrow, row_is_j ? qrow : qcol, qm, u, A.loss, et);
+    double cur[kAcc];
     if (kWriteBlocks) {
+      // both rows of the edge: diag += S, block(row, col) = -S; gradient: +v in row j, -v in row i; cost once, in row i
+      const double sgn = row_is_j ? 1.0 : -1.0;
 #pragma unroll
-      for (int k = 0; k < kPartStride; ++k) acc[k] = warp_sum(acc[k]);
-      if (lane == 0) {
+      for (int k = 0; k < 6; ++k) cur[k] = et.S[k];
+      cur[6] = sgn * et.v[0]; cur[7] = sgn * et.v[1]; cur[8] = sgn * et.v[2];
+      cur[kAcc - 1] = row_is_j ? 0.0 : 0.5 * et.rho[0];
+      if (h < hi) {
 #pragma unroll
-        for (int k = 0; k < kPartStride; ++k) part[(size_t)t * kPartStride + k] = acc[k];
+        for (int k = 0; k < 6; ++k) A.val[blk_index(h, k, Rec<6>::kDoubles)] = -et.S[k];
       }
     } else {
-      const double c = warp_sum(acc[9]);
-      if (lane == 0) part[(size_t)t * kPartStride + 9] = c;
+      cur[0] = row_is_j ? 0.0 : 0.5 * et.rho[0];
     }
+    while (true) {
+      if (h >= sb && h < se) {
+#pragma unroll
+        for (int k = 0; k < kAcc; ++k) acc[k] += cur[k];
+      }
+      if (se > ce) break;  // the segment continues in the next record
+#pragma unroll
+      for (int k = 0; k < kAcc; ++k) acc[k] = warp_sum(acc[k]);
+      if (lane == 0) {
+        if (kWriteBlocks) {
+#pragma unroll
+          for (int k = 0; k < kPartStride; ++k) A.part[(size_t)t * kPartStride + k] = acc[k];
+        } else {
+          A.part[(size_t)t * kPartStride + 9] = acc[0];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+      if (++t == t1) break;
+      sb = se; se = sb + A.seg_len[t];
+      if (sb >= ce) break;
+    }
+    rec = rec_n; cf = cf_n; qrow = qrow_n; qcol = qcol_n;
+    if (t == t1) break;
   }
 }
 
@@ -362,7 +481,7 @@ template <bool kWriteBlocks, int kType>
 __global__ void __launch_bounds__(kBlock, 1)
 k_edges_general(uint32_t num_warps, uint64_t H, const uint32_t* __restrict__ warp_seg_ptr, const uint32_t* __restrict__ task_row,
                 const uint32_t* __restrict__ task_begin, const uint32_t* __restrict__ task_len, const uint32_t* __restrict__ he_col,
-                const double* __restrict__ qij, const double* __restrict__ U, const double* __restrict__ node_q, DevLoss loss,
+                const double* __restrict__ inrec, const double* __restrict__ node_q, DevLoss loss,
                 double* __restrict__ val, double* __restrict__ part) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -383,9 +502,10 @@ k_edges_general(uint32_t num_warps, uint64_t H, const uint32_t* __restrict__ war
       const bool row_is_j = (cf & kSideBit) != 0;
       const double4 qb4 = reinterpret_cast<const double4*>(node_q)[col];
       const Q4 qcol{qb4.x, qb4.y, qb4.z, qb4.w};
-      const Q4 qm{qij[h], qij[H + h], qij[2 * H + h], qij[3 * H + h]};
+      const double* rec = inrec + (size_t)(h >> 5) * in_rec_doubles(1) + (h & 31);  // scalar-weight input records
+      const Q4 qm{rec[0], rec[32], rec[64], rec[96]};
       GeneralTerms gt;
-      general_edge_terms<kWriteBlocks, kType>(row_is_j ? qcol : qrow, row_is_j ? qrow : qcol, qm, U[h], row_is_j, loss, gt);
+      general_edge_terms<kWriteBlocks, kType>(row_is_j ? qcol : qrow, row_is_j ? qrow : qcol, qm, rec[128], row_is_j, loss, gt);
       if (!row_is_j) acc[9] += 0.5 * gt.rho[0];
       if (kWriteBlocks) {
 #pragma unroll
@@ -550,49 +670,6 @@ __global__ void k_prepare_solve(uint32_t N, double mu, double lo, double hi, con
 // the range segment by segment (segment = range ^ row); a record shared by two segments is read
 // twice from shared memory, never twice from HBM.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_bulk(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-struct WarpPipe {
-  double* ring;    // this warp's kStages records in shared memory
-  uint64_t* bars;  // this warp's kStages mbarriers
-  uint32_t pos;    // records consumed since init: ring slot = pos % kStages, phase = (pos / kStages) & 1
-};
-
-template <int kBlk>
-__device__ __forceinline__ void pipe_init(WarpPipe& wp, unsigned char* smem) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  wp.ring = reinterpret_cast<double*>(smem + (size_t)warp * kStages * Rec<kBlk>::kBytes);
-  wp.bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWarpsPerBlock * kStages * Rec<kBlk>::kBytes) + warp * kStages;
-  wp.pos = 0;
-  if (lane == 0) {
-    for (int st = 0; st < kStages; ++st) mbar_init(&wp.bars[st], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-}
-
 // Stream this warp's record range (nrec records from half-edge lo) and call finish(t, y0, y1, y2)
 // (all lanes, totals valid in every lane) for each segment t in [t0, t1).  x4 is the gathered vector, one
 // aligned double4 (32 B sector) per view.  Record-major loop: the x gather of record c+1 (its columns are
@@ -1582,7 +1659,7 @@ struct StreamHolder {
 // Per-device facts that are expensive to query: cached for the life of the process.
 struct DeviceInfo {
   bool ready = false;
-  int sm_count = 0, coop = 0, occ_k1 = 1, occ_k2[2] = {1, 1};  // occ_k2[0]: 6-double records, [1]: 9-double records
+  int sm_count = 0, coop = 0, occ_k2[2] = {1, 1};  // occ_k2[0]: 6-double records, [1]: 9-double records
 };
 DeviceInfo g_device_info[64];
 
@@ -1688,7 +1765,8 @@ struct gsfm_ra_solver {
   uint32_t n_iso = 0;
   Partition pk1, pk2;  // K1 (edge kernel) and K2 (SpMV / PCG) partitions
   // per half-edge constants, planar
-  DevBuf<double> qij, U;
+  DevBuf<double> inrec;  // K1's input records (k_setup_halfedges)
+  int ku = 1;            // whitening entries per half-edge in the input records: 1 (scalar) or 6 (upper triangle)
   // edge-order copies for the API kernels
   DevBuf<uint32_t> d_ei, d_ej;
   DevBuf<double> d_omega_ij, d_cov6, d_weight;
@@ -1749,31 +1827,35 @@ struct gsfm_ra_solver {
   int smem_bytes() const { return spmv_smem_bytes(blk); }
   // K1 is specialised on (Jacobian?, residual kind, scalar weight?, loss): the common losses get their own instantiation
   // (no switch, fewer registers), everything else runs the generic one.
-  template <bool JAC, int RES, bool SCAL, int LOSS>
-  void launch_edges_t(int b, double* val_out) {
-    k_edges<JAC, RES, SCAL, LOSS><<<pk1.grid, kBlock, 0, stream>>>(pk1.num_warps, H, pk1.warp_seg_ptr.p, pk1.seg_row.p, pk1.seg_begin.p, pk1.seg_len.p,
-                                                                   he_col.p, qij.p, U.p, node_q[b].p, loss, val_out, part.p);
-  }
+  typedef void (*K1Fn)(const K1Args);
   template <bool JAC, int RES, bool SCAL>
-  void launch_edges_l(int b, double* val_out) {
+  K1Fn pick_k1_loss() const {
     const bool plain = loss.scale == 1.0;
-    if (plain && loss.kind == kLossCauchy) launch_edges_t<JAC, RES, SCAL, kLossCauchy>(b, val_out);
-    else if (plain && loss.kind == kLossSoftLOne) launch_edges_t<JAC, RES, SCAL, kLossSoftLOne>(b, val_out);
-    else if (plain && loss.kind == kLossHuber) launch_edges_t<JAC, RES, SCAL, kLossHuber>(b, val_out);
-    else if (plain && loss.kind == kLossMagsac3) launch_edges_t<JAC, RES, SCAL, kLossMagsac3>(b, val_out);
-    else launch_edges_t<JAC, RES, SCAL, -1>(b, val_out);
+    if (plain && loss.kind == kLossCauchy) return k_edges<JAC, RES, SCAL, kLossCauchy>;
+    if (plain && loss.kind == kLossSoftLOne) return k_edges<JAC, RES, SCAL, kLossSoftLOne>;
+    if (plain && loss.kind == kLossHuber) return k_edges<JAC, RES, SCAL, kLossHuber>;
+    if (plain && loss.kind == kLossMagsac3) return k_edges<JAC, RES, SCAL, kLossMagsac3>;
+    return k_edges<JAC, RES, SCAL, -1>;
   }
+  K1Fn pick_k1(bool jacobian) const {
+    if (manifold()) return jacobian ? pick_k1_loss<true, 1, true>() : pick_k1_loss<false, 1, true>();
+    if (scalar_u) return jacobian ? pick_k1_loss<true, 0, true>() : pick_k1_loss<false, 0, true>();
+    return jacobian ? pick_k1_loss<true, 0, false>() : pick_k1_loss<false, 0, false>();
+  }
+  int k1_smem_bytes() const { return kWarpsPerBlock * kStages * in_rec_doubles(ku) * 8 + kWarpsPerBlock * kStages * 8; }
   template <bool JAC, int TYPE>
   void launch_edges_g(int b, double* val_out) {
     k_edges_general<JAC, TYPE><<<pk1.grid, kBlock, 0, stream>>>(pk1.num_warps, H, pk1.warp_seg_ptr.p, pk1.seg_row.p, pk1.seg_begin.p, pk1.seg_len.p,
-                                                                he_col.p, qij.p, U.p, node_q[b].p, loss, val_out, part.p);
+                                                                he_col.p, inrec.p, node_q[b].p, loss, val_out, part.p);
   }
   void launch_edges(int b, bool jacobian, double* val_out) {
-    if (error_type == GSFM_RA_QUATERNION_NORM) { if (jacobian) launch_edges_g<true, 0>(b, val_out); else launch_edges_g<false, 0>(b, nullptr); }
-    else if (error_type == GSFM_RA_ROTATION_MAT_FNORM) { if (jacobian) launch_edges_g<true, 1>(b, val_out); else launch_edges_g<false, 1>(b, nullptr); }
-    else if (manifold()) { if (jacobian) launch_edges_l<true, 1, true>(b, val_out); else launch_edges_l<false, 1, true>(b, nullptr); }
-    else if (scalar_u) { if (jacobian) launch_edges_l<true, 0, true>(b, val_out); else launch_edges_l<false, 0, true>(b, nullptr); }
-    else { if (jacobian) launch_edges_l<true, 0, false>(b, val_out); else launch_edges_l<false, 0, false>(b, nullptr); }
+    if (error_type == GSFM_RA_QUATERNION_NORM) { if (jacobian) launch_edges_g<true, 0>(b, val_out); else launch_edges_g<false, 0>(b, nullptr); return; }
+    if (error_type == GSFM_RA_ROTATION_MAT_FNORM) { if (jacobian) launch_edges_g<true, 1>(b, val_out); else launch_edges_g<false, 1>(b, nullptr); return; }
+    K1Args A;
+    A.num_warps = pk1.num_warps; A.warp_span = pk1.span; A.H = H;
+    A.warp_seg_ptr = pk1.warp_seg_ptr.p; A.seg_begin = pk1.seg_begin.p; A.seg_len = pk1.seg_len.p;
+    A.inrec = inrec.p; A.node_q = node_q[b].p; A.val = val_out; A.part = part.p; A.loss = loss;
+    pick_k1(jacobian)<<<pk1.grid, kBlock, k1_smem_bytes(), stream>>>(A);
   }
   void launch_spmv(int b, const double* x4, int check_done) {
     if (blk == 6)
@@ -1928,7 +2010,6 @@ int device_info(int device, DeviceInfo** out) {
     CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(9)));
     CUDA_TRY(cudaFuncSetAttribute(k_spmv<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(6)));
     CUDA_TRY(cudaFuncSetAttribute(k_spmv<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(9)));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k1, k_edges<true, 0, false, -1>, kBlock, 0));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2[0], k_pcg_persistent<6>, kBlock, spmv_smem_bytes(6)));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2[1], k_pcg_persistent<9>, kBlock, spmv_smem_bytes(9)));
     // keep freed blocks in the pool: the next solver reuses them
@@ -1974,6 +2055,7 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   s->error_type = prob->error_type;
   s->blk = s->general() ? 9 : 6;
   s->scalar_u = !(prob->error_type == GSFM_RA_ANGLE_AXIS_COVARIANCE || prob->error_type == GSFM_RA_ANGLE_AXIS_COV_INLIERS);
+  s->ku = s->scalar_u ? 1 : 6;
   RA_TRY(make_dev_loss(&options->loss, &s->loss));
   s->sm_count = di->sm_count;
   CUDA_TRY(cudaStreamCreateWithFlags(&s->stream_holder.s, cudaStreamNonBlocking));
@@ -2060,16 +2142,27 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
     s->launches += 5;
     return 0;
   };
-  RA_TRY(make(s->pk1, s->general() ? 1 : di->occ_k1));
+  int occ_k1 = 1;
+  if (!s->general()) {
+    // the two K1 instantiations this solver will launch (with / without Jacobian): opt in to their shared memory, size the
+    // partition for the occupancy of the heavier one
+    for (int jac = 0; jac < 2; ++jac) CUDA_TRY(cudaFuncSetAttribute((const void*)s->pick_k1(jac != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, s->k1_smem_bytes()));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_k1, (const void*)s->pick_k1(true), kBlock, s->k1_smem_bytes()));
+  }
+  RA_TRY(make(s->pk1, occ_k1));
   RA_TRY(make(s->pk2, occ_k2));
   // the cooperative grid must be fully resident; node loops are grid-strided so any size works
   s->pk2.grid = std::min<uint32_t>(s->pk2.grid, (uint32_t)s->sm_count * std::max(1, occ_k2));
   lap("enqueue structure build");
 
   // ---- per half-edge constants (K0) and the solver's working set ---------------------------------
-  RA_TRY(s->qij.alloc(4 * H));
-  RA_TRY(s->U.alloc(6 * H));
-  k_setup_halfedges<<<grid_for(H), kBlock, 0, st>>>(H, s->he_edge.p, s->d_omega_ij.p, s->d_cov6.p, s->d_weight.p, prob->error_type, s->qij.p, s->U.p);
+  {
+    const size_t nrec_in = (size_t)((H + 31) / 32), rd = (size_t)in_rec_doubles(s->ku);
+    RA_TRY(s->inrec.alloc(nrec_in * rd));
+    CUDA_TRY(cudaMemsetAsync(s->inrec.p + (nrec_in - 1) * rd, 0, rd * 8, st));  // lanes past H in the last record
+  }
+  k_setup_halfedges<<<grid_for(H), kBlock, 0, st>>>(H, s->ku, s->he_edge.p, s->he_row.p, s->he_col.p, s->d_omega_ij.p, s->d_cov6.p, s->d_weight.p,
+                                                    prob->error_type, s->inrec.p);
   s->launches += 1;
   const size_t nrec = (size_t)((H + 31) / 32);
   for (int b = 0; b < 2; ++b) {
@@ -2529,7 +2622,8 @@ int gsfm_ra_solve_sigma_consensus(const gsfm_ra_problem* problem, const gsfm_ra_
     k_node_prep<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->omega[b].p, s->node_q[b].p, s->node_JL[b].p, s->slots.p, s->counter.p, s->sc.p, 0);
     k_sigma_weights<<<grid_for(E), kBlock, 0, s->stream>>>(E, s->d_ei.p, s->d_ej.p, s->d_omega_ij.p, s->node_q[b].p, one_over_sigma, sq2, gamma_k,
                                                            weight_zero, table_size, s->d_weight.p, s->slots.p, s->counter.p, s->sc.p);
-    k_setup_halfedges<<<grid_for(H), kBlock, 0, s->stream>>>(H, s->he_edge.p, s->d_omega_ij.p, s->d_cov6.p, s->d_weight.p, s->error_type, s->qij.p, s->U.p);
+    k_setup_halfedges<<<grid_for(H), kBlock, 0, s->stream>>>(H, s->ku, s->he_edge.p, s->he_row.p, s->he_col.p, s->d_omega_ij.p, s->d_cov6.p, s->d_weight.p,
+                                                             s->error_type, s->inrec.p);
     s->launches += 3;
     CUDA_TRY(cudaGetLastError());
     RA_TRY(s->fetch_scalars());
