@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libgsfm_ra.so")
+# GSFM_RA_LIB: another build of the SAME library (kernel-tuning experiments, profiles/kernel_times.py)
+LIB_PATH = os.environ.get("GSFM_RA_LIB") or os.path.join(HERE, "csrc", "libgsfm_ra.so")
 
 ABI_VERSION = 1
 COMM_ID_BYTES = 128
