@@ -21,6 +21,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -109,7 +110,30 @@ struct DevScalars {
   double dg, dHd, step2;  // delta.g, delta.H.delta, |delta|^2 (Euclidean step)
   int bad;                // non-finite detected (1) / a peer GPU did not show up (2)
   int xseq;               // cross-GPU exchange sequence number (multi-GPU persistent PCG)
+  // %globaltimer stamps of the trust-region batch: start of k_prepare_solve, end of k_apply_step, end of k_node_finalize
+  unsigned long long t_begin, t_linear_end, t_end;
 };
+// What changes from one trust-region batch to the next when the batch is replayed as a CUDA graph: read by the kernels
+// from device memory, refreshed by the graph's first node (a 16-byte H2D copy from pinned host memory).
+struct IterParams {
+  double mu;
+  unsigned seq, pad;
+};
+static_assert(sizeof(DevScalars) % 8 == 0, "DevScalars is copied to the host mailbox in 8-byte words");
+
+// Host mailbox (pinned, mapped into the device): the last kernel of a trust-region batch copies the device scalars here and
+// then publishes the batch's sequence number, so the host learns the outcome by polling its own memory -- no D2H copy
+// operation, no stream synchronisation on the critical path of an iteration.
+struct HostMailbox {
+  DevScalars sc;
+  volatile unsigned seq;
+};
+
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 // Deterministic grid-wide sum of NV values: block tree -> per-block slot -> the LAST block to
 // arrive adds the slots in index order.  Returns true in the last block (all threads), with the
@@ -432,7 +456,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_edges(const K1Args A) {
     __syncwarp();
     if (c + kStages < nrec) issue(c + kStages);
     EdgeTerms et;
-    edge_terms<kWriteBlocks, kResidual, kScalarU, kLoss>(row_is_j ? qcol : qrow, row_is_j ? qrow : qcol, qm, u, A.loss, et);
+    edge_terms<kWriteBlocks, kResidual, kScalarU, kLoss, true>(row_is_j ? qcol : qrow, row_is_j ? qrow : qcol, qm, u, A.loss, et);
     double cur[kAcc];
     if (kWriteBlocks) {
       // both rows of the edge: diag += S, block(row, col) = -S; gradient: +v in row j, -v in row i; cost once, in row i
@@ -535,7 +559,7 @@ k_edges_general(uint32_t num_warps, uint64_t H, const uint32_t* __restrict__ war
 __global__ void k_node_finalize(uint32_t N, const uint32_t* __restrict__ node_task_ptr, const double* __restrict__ part,
                                 const double* __restrict__ node_JL, double* __restrict__ Hd, double* __restrict__ gt,
                                 double* __restrict__ ediag, int cost_only, int stage, double* tail, double* slots, unsigned* counter,
-                                DevScalars* sc) {
+                                DevScalars* sc, HostMailbox* mailbox, unsigned mailbox_seq, const IterParams* ip) {
   // stage 0: single GPU, everything.  Edge-sharded: stage 1 = local sums (Hd, gt, tail = {cost, bad}) which
   // the host all-reduces, stage 2 = the per-view post-processing on the reduced sums.
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -588,6 +612,19 @@ __global__ void k_node_finalize(uint32_t N, const uint32_t* __restrict__ node_ta
     if (stage == 2) { tot[0] = tail[0]; tot[1] += tail[1]; }
     sc->cost = tot[0];
     if (tot[1] != 0.0 || !isfinite(tot[0])) sc->bad = 1;
+    if (mailbox) {
+      if (ip) mailbox_seq = ip->seq;
+      sc->t_end = gtimer_ns();
+      // every scalar of this batch is final: the kernels that wrote them precede this one in the stream, this block is
+      // the last one of this kernel (grid_sum) and has fenced.  Copy, fence to the system, publish.
+      __threadfence();
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(sc);
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(&mailbox->sc);
+#pragma unroll
+      for (int k = 0; k < (int)(sizeof(DevScalars) / 8); ++k) dst[k] = __ldcg(src + k);
+      __threadfence_system();
+      mailbox->seq = mailbox_seq;
+    }
   }
 }
 
@@ -608,8 +645,10 @@ __global__ void k_prepare_solve(uint32_t N, double mu, double lo, double hi, con
                                 const double* __restrict__ gt, const double* __restrict__ user_damp, const double* __restrict__ user_b,
                                 double* __restrict__ Dblk, double* __restrict__ Minv, double* __restrict__ x, double* __restrict__ r,
                                 double* __restrict__ z, double* __restrict__ p, double* __restrict__ q, double* __restrict__ bvec,
-                                double* slots, unsigned* counter, DevScalars* sc) {
+                                double* slots, unsigned* counter, DevScalars* sc, const IterParams* ip) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip) mu = ip->mu;
+  if (i == 0) sc->t_begin = gtimer_ns();
   double v[2] = {0.0, 0.0};
   if (i < N) {
     double lam[3];
@@ -1072,24 +1111,34 @@ __global__ void __launch_bounds__(kBlock) k_pcg_persistent(PcgParams P) {
     alpha = gamma / pAp;
     gamma_old = gamma;
     // ---- phase C: p, q, x, r, z ; r.r ----------------------------------------------------------
+    // views are dealt round-robin to the blocks (view i -> block i % grid) so every SM carries a few; all loads of a
+    // view are issued before its first store (the vectors may alias as far as the compiler knows: a store between two
+    // loads would serialise the L2 round trips)
     double v1 = 0.0;
-    for (uint32_t i = gtid; i < P.N; i += gthreads) {
+    for (uint32_t i = blockIdx.x + gridDim.x * threadIdx.x; i < P.N; i += gthreads) {
       const double4 zv = reinterpret_cast<const double4*>(P.z)[i];
       const double4 pv = reinterpret_cast<const double4*>(P.p)[i];
+      double sv[3], qv[3], xv[3], rv[3], Mi[6];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        sv[c] = P.s[3 * (size_t)i + c]; qv[c] = P.q[3 * (size_t)i + c]; xv[c] = P.x[3 * (size_t)i + c]; rv[c] = P.r[3 * (size_t)i + c];
+      }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) Mi[c] = P.Minv[6 * (size_t)i + c];
       const double zi[3] = {zv.x, zv.y, zv.z};
       const double po[3] = {pv.x, pv.y, pv.z};
-      double ri[3], zn[3], pn[3];
+      double ri[3], zn[3], pn[3], qn[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         pn[c] = zi[c] + beta * po[c];
-        const double qn = P.s[3 * (size_t)i + c] + beta * P.q[3 * (size_t)i + c];
-        P.q[3 * (size_t)i + c] = qn;
-        P.x[3 * (size_t)i + c] += alpha * pn[c];
-        ri[c] = P.r[3 * (size_t)i + c] - alpha * qn;
-        P.r[3 * (size_t)i + c] = ri[c];
+        qn[c] = sv[c] + beta * qv[c];
+        xv[c] += alpha * pn[c];
+        ri[c] = rv[c] - alpha * qn[c];
         v1 += ri[c] * ri[c];
       }
-      sym_mul_vec(P.Minv + 6 * (size_t)i, ri, zn);
+      sym_mul_vec(Mi, ri, zn);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { P.q[3 * (size_t)i + c] = qn[c]; P.x[3 * (size_t)i + c] = xv[c]; P.r[3 * (size_t)i + c] = ri[c]; }
       reinterpret_cast<double4*>(P.p)[i] = make_double4(pn[0], pn[1], pn[2], 0.0);
       reinterpret_cast<double4*>(P.z)[i] = make_double4(zn[0], zn[1], zn[2], 0.0);
     }
@@ -1352,6 +1401,7 @@ __global__ void k_apply_step(uint32_t N, const double* __restrict__ node_JL, con
   double tot[4];
   if (grid_sum<4>(v, slots, counter, tot) && threadIdx.x == 0) {
     sc->dg = tot[0]; sc->dHd = tot[1]; sc->step2 = tot[2];
+    sc->t_linear_end = gtimer_ns();
     (void)tot[3];  // a non-finite step makes step2 non-finite: the host treats it as an invalid step
   }
 }
@@ -1785,6 +1835,18 @@ struct gsfm_ra_solver {
   DevBuf<unsigned> counter, row_cnt;
   DevBuf<DevScalars> sc;
   DevScalars* h_sc = nullptr;  // pinned
+  HostMailbox* mailbox = nullptr;      // pinned + mapped; device alias below
+  HostMailbox* mailbox_dev = nullptr;
+  unsigned mailbox_seq = 0;
+  // One trust-region batch as a CUDA graph (one per linearisation buffer): replayed with a single launch, its kernels
+  // run back to back instead of waiting for the host to enqueue them one by one.  What varies between replays lives in
+  // it_params (refreshed by the graph's first node from h_it_params).
+  DevBuf<IterParams> it_params;
+  IterParams* h_it_params = nullptr;   // pinned
+  cudaGraphExec_t batch_graph[2] = {nullptr, nullptr};
+  int64_t batch_launches = 0;
+  bool graph_params = false;           // true while a batch is being captured: kernels read mu / seq from it_params
+  int graph_state = 0;                 // 0 untried, 1 in use, -1 unavailable (direct launches)
   unsigned long long* prof_buf = nullptr;  // device, set only by gsfm_ra_solver_time_kernels
 
   // trust-region state (host)
@@ -1803,6 +1865,9 @@ struct gsfm_ra_solver {
     for (int r = 0; r < kMaxPeers; ++r) if (peer_base[r] && r != rank) cudaIpcCloseMemHandle(peer_base[r]);
     if (xchg) cudaFree(xchg);
     if (h_sc) cudaFreeHost(h_sc);
+    if (mailbox) cudaFreeHost(mailbox);
+    if (h_it_params) cudaFreeHost(h_it_params);
+    for (auto& g : batch_graph) if (g) cudaGraphExecDestroy(g);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     // the stream itself is destroyed by stream_holder after the buffers have been returned to the pool
   }
@@ -1821,6 +1886,31 @@ struct gsfm_ra_solver {
     CUDA_TRY(cudaMemcpyAsync(h_sc, sc.p, sizeof(DevScalars), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     return 0;
+  }
+
+  // Wait for the mailbox of the batch published as `seq` (see HostMailbox) and take its scalars.  Polls host memory;
+  // cudaStreamQuery every few thousand polls catches a failed launch, and a finished stream without the flag is an error.
+  int fetch_mailbox(unsigned seq) {
+    unsigned spins = 0;
+    while (mailbox->seq != seq) {
+      if ((++spins & 0xfffu) == 0) {
+        const cudaError_t q = cudaStreamQuery(stream);
+        if (q == cudaSuccess) {
+          if (mailbox->seq == seq) break;
+          set_error("trust-region batch finished without publishing its scalars");
+          return GSFM_RA_ERR_CUDA;
+        }
+        if (q != cudaErrorNotReady) { set_error("CUDA failure while waiting for a trust-region batch: %s", cudaGetErrorString(q)); return GSFM_RA_ERR_CUDA; }
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    std::memcpy(h_sc, const_cast<DevScalars*>(&mailbox->sc), sizeof(DevScalars));
+    return 0;
+  }
+  // kernel times of the batch whose scalars were just fetched (%globaltimer stamps written by its kernels)
+  void account_batch() {
+    if (h_sc->t_linear_end >= h_sc->t_begin) ms_linear += 1e-6 * (double)(h_sc->t_linear_end - h_sc->t_begin);
+    if (h_sc->t_end >= h_sc->t_linear_end) ms_assemble += 1e-6 * (double)(h_sc->t_end - h_sc->t_linear_end);
   }
 
   int rec_doubles() const { return blk * 32 + 16; }
@@ -1867,7 +1957,10 @@ struct gsfm_ra_solver {
   }
 
   // ---- evaluation at omega[b]: node prep, K1 (or K1c), node finalize -------------------------
-  int evaluate(int b, bool jacobian) {
+  int evaluate(int b, bool jacobian, bool publish = false) {
+    HostMailbox* mb = publish ? mailbox_dev : nullptr;
+    const IterParams* ip_dev = graph_params ? it_params.p : nullptr;  // graph replay: the sequence number comes from device memory
+    const unsigned mseq = (publish && !graph_params) ? ++mailbox_seq : 0u;
     CUDA_TRY(cudaMemsetAsync(&sc.p->gmax, 0, sizeof(double), stream));
     k_node_prep<<<grid_for(N), kBlock, 0, stream>>>(N, omega[b].p, node_q[b].p, node_JL[b].p, slots.p, counter.p, sc.p, manifold() ? 1 : 0);
     launch_edges(b, jacobian, val[b].p);
@@ -1875,15 +1968,15 @@ struct gsfm_ra_solver {
     const int co = jacobian ? 0 : 1;
     if (!sharded()) {
       k_node_finalize<<<grid_for(N), kBlock, 0, stream>>>(N, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd_p[b], gt_p[b], ediag[b].p, co, 0, tail,
-                                                           slots.p, counter.p, sc.p);
+                                                           slots.p, counter.p, sc.p, mb, mseq, publish ? ip_dev : nullptr);
     } else {
       // edge-sharded: local sums -> ONE all-reduce of [Hd | gt | cost, bad] -> per-view post-processing
       k_node_finalize<<<grid_for(N), kBlock, 0, stream>>>(N, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd_p[b], gt_p[b], ediag[b].p, co, 1, tail,
-                                                           slots.p, counter.p, sc.p);
+                                                           slots.p, counter.p, sc.p, nullptr, 0u, nullptr);
       if (jacobian) RA_TRY(allreduce(lin[b].p, 9ull * N + 2));
       else RA_TRY(allreduce(tail, 2));
       k_node_finalize<<<grid_for(N), kBlock, 0, stream>>>(N, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd_p[b], gt_p[b], ediag[b].p, co, 2, tail,
-                                                           slots.p, counter.p, sc.p);
+                                                           slots.p, counter.p, sc.p, mb, mseq, publish ? ip_dev : nullptr);
       launches += 2;
     }
     launches += 3;
@@ -1928,7 +2021,7 @@ struct gsfm_ra_solver {
   int pcg_enqueue(int b, double mu, const double* user_damp, const double* user_b, double rtol, int max_iter) {
     k_prepare_solve<<<grid_for(N), kBlock, 0, stream>>>(N, mu, opt.min_lm_diagonal, opt.max_lm_diagonal, ediag[b].p, scale.p, node_JL[b].p,
                                                          Hd_p[b], gt_p[b], user_damp, user_b, Dblk.p, Minv.p, x.p, r.p, z.p, p.p, q.p, bvec.p,
-                                                         slots.p, counter.p, sc.p);
+                                                         slots.p, counter.p, sc.p, graph_params ? it_params.p : nullptr);
     launches += 1;
     if (opt.linear_solver == GSFM_RA_SOLVER_DENSE_CHOLESKY) {
       const uint32_t n = 3 * N, np = (n + 1 + kNB - 1) / kNB * kNB;  // room for the right-hand-side row
@@ -2197,6 +2290,11 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   CUDA_TRY(cudaMemsetAsync(s->counter.p, 0, 4 * sizeof(unsigned), st));
   CUDA_TRY(cudaMemsetAsync(s->sc.p, 0, sizeof(DevScalars), st));
   CUDA_TRY(cudaMallocHost(&s->h_sc, sizeof(DevScalars)));
+  CUDA_TRY(cudaHostAlloc(&s->mailbox, sizeof(HostMailbox), cudaHostAllocMapped));
+  std::memset(s->mailbox, 0, sizeof(HostMailbox));
+  CUDA_TRY(cudaHostGetDevicePointer(&s->mailbox_dev, s->mailbox, 0));
+  CUDA_TRY(cudaMallocHost(&s->h_it_params, sizeof(IterParams)));
+  RA_TRY(s->it_params.alloc(1));
   k_jacobi_scale<<<grid_for(3ull * N), kBlock, 0, st>>>(3 * N, s->ediag[0].p, s->scale.p, 0);
   s->launches += 1;
   CUDA_TRY(cudaGetLastError());
@@ -2229,6 +2327,61 @@ void reset_trust_region(gsfm_ra_solver* s) {
 
 void push_trace(gsfm_ra_summary* sum, const gsfm_ra_iteration& it) {
   if (sum && sum->trace && sum->trace_size < sum->trace_capacity) sum->trace[sum->trace_size++] = it;
+}
+
+// One trust-region batch at linearisation buffer b: damping + PCG initialisation, the whole PCG solve, the step and the
+// candidate point, and the speculative linearisation of the candidate (node prep, K1, node finalize + host mailbox).
+int enqueue_batch(gsfm_ra_solver* s, int b, double mu) {
+  const int c = b ^ 1;
+  const uint32_t N = s->N;
+  CUDA_TRY(cudaMemsetAsync(&s->sc.p->bad, 0, sizeof(int), s->stream));
+  RA_TRY(s->pcg_enqueue(b, mu, nullptr, nullptr, s->opt.pcg_rtol, s->opt.pcg_max_iterations));
+  k_apply_step<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[b].p, s->x.p, s->bvec.p, s->r.p, s->Dblk.p, s->Hd_p[b], s->gt_p[b], s->omega[b].p,
+                                                      s->omega[c].p, s->delta.p, s->slots.p, s->counter.p, s->sc.p, s->manifold() ? 1 : 0);
+  s->launches += 1;
+  RA_TRY(s->evaluate(c, true, true));
+  return 0;
+}
+
+// Run the batch: as a CUDA graph replay where possible (single GPU, persistent PCG kernel) -- one launch, the kernels run
+// back to back -- else as direct launches.  GSFM_RA_NO_GRAPH=1 forces direct launches.
+int run_batch(gsfm_ra_solver* s, int b) {
+  if (s->graph_state == 0) {
+    const bool eligible = s->opt.linear_solver == GSFM_RA_SOLVER_PCG && s->cooperative && !s->sharded() && !std::getenv("GSFM_RA_NO_GRAPH");
+    s->graph_state = eligible ? 1 : -1;
+  }
+  if (s->graph_state == 1 && !s->batch_graph[b]) {
+    // capture this buffer's batch once
+    const int64_t l0 = s->launches;
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      s->graph_params = true;
+      int rc = (cudaMemcpyAsync(s->it_params.p, s->h_it_params, sizeof(IterParams), cudaMemcpyHostToDevice, s->stream) == cudaSuccess) ? 0 : 1;
+      if (rc == 0) rc = enqueue_batch(s, b, 0.0);
+      s->graph_params = false;
+      const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+      ok = rc == 0 && e == cudaSuccess && graph != nullptr;
+      if (ok) ok = cudaGraphInstantiate(&s->batch_graph[b], graph, 0) == cudaSuccess;
+      if (graph) cudaGraphDestroy(graph);
+    }
+    s->batch_launches = s->launches - l0;
+    s->launches = l0;
+    if (!ok) {
+      (void)cudaGetLastError();
+      s->batch_graph[b] = nullptr;
+      s->graph_state = -1;
+      if (s->opt.verbose) std::fprintf(stderr, "[gsfm_ra] CUDA graph capture of the trust-region batch failed; using direct launches\n");
+    }
+  }
+  if (s->graph_state == 1) {
+    s->h_it_params->mu = s->radius;
+    s->h_it_params->seq = ++s->mailbox_seq;
+    CUDA_TRY(cudaGraphLaunch(s->batch_graph[b], s->stream));
+    s->launches += s->batch_launches;
+    return 0;
+  }
+  return enqueue_batch(s, b, s->radius);
 }
 
 // Ceres-1.14 trust-region loop, same order of checks as oracle/ra_oracle.cc.
@@ -2279,18 +2432,9 @@ int iterate(gsfm_ra_solver* s, int max_new_iterations, gsfm_ra_summary* sum) {
     // ---- one trust-region iteration = one stream-ordered batch, ONE host synchronisation -------
     //   k_prepare_solve -> k_pcg_persistent (whole PCG + Ht x) -> k_apply_step (step, candidate)
     //   -> speculative linearisation of the candidate (k_node_prep, K1, k_node_finalize)
-    CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
-    CUDA_TRY(cudaMemsetAsync(&s->sc.p->bad, 0, sizeof(int), s->stream));
-    RA_TRY(s->pcg_enqueue(b, s->radius, nullptr, nullptr, o.pcg_rtol, o.pcg_max_iterations));
-    k_apply_step<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[b].p, s->x.p, s->bvec.p, s->r.p, s->Dblk.p, s->Hd_p[b], s->gt_p[b], s->omega[b].p,
-                                                        s->omega[c].p, s->delta.p, s->slots.p, s->counter.p, s->sc.p, s->manifold() ? 1 : 0);
-    s->launches += 1;
-    CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
-    RA_TRY(s->evaluate(c, true));
-    CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
-    RA_TRY(s->fetch_scalars());
-    s->ms_linear += s->elapsed(s->ev[0], s->ev[2]);
-    s->ms_assemble += s->elapsed(s->ev[2], s->ev[3]);
+    RA_TRY(run_batch(s, b));
+    RA_TRY(s->fetch_mailbox(s->mailbox_seq));
+    s->account_batch();
     if (s->h_sc->bad == 2) { set_error("multi-GPU exchange timed out: a peer rank did not reach the same CG step"); s->termination = GSFM_RA_TERM_FAILURE; return GSFM_RA_ERR_CUDA; }
     const bool breakdown = s->h_sc->pcg_breakdown != 0;
     const int lin_it = s->h_sc->pcg_iter;

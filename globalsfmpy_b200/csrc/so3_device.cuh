@@ -311,9 +311,41 @@ __host__ __device__ inline double triggs_kappa(double s, const double* rho) {
 // kResidual = 1: r = -2 w vec(q_E) = 2 w vec(q_ij (q_j q_i^-1)^-1)   (QUATERNION_COSINE,
 //                include/pairwise_rotation_error_quat.hpp:82-106; w = U[0]);  A = w ([v_E]x - w_E I).
 //                No logarithm, smooth through theta = pi.
-template <bool kNeedJacobian, int kResidual = 0, bool kScalarU = false, int kLoss = -1>
+// kStencilOnly (K1): only S, v, rho are produced, B is not formed.  With a scalar weight w the stencil has a closed form:
+//   B = w M R_j, M = Jl^-1(e) = I - K/2 + c K^2, K = [e]x  =>  M^T M = I + g K^2 = (1 - g theta^2) I + g e e^T,
+//   g = 2c - 1/4 - c^2 theta^2, and M^T e = e, so with f = R_j^T e (the error in view j's body frame)
+//   B^T B = w^2 ((1 - g theta^2) I + g f f^T),   u = B^T r = w^2 f,
+//   S = rho' w^2 ((1 - g theta^2) I + (g - kappa w^2) f f^T),   v = rho' w^2 f
+// -- no rotation matrix, no 3x3 products.
+template <bool kNeedJacobian, int kResidual = 0, bool kScalarU = false, int kLoss = -1, bool kStencilOnly = false>
 __host__ __device__ inline void edge_terms(const Q4& qi, const Q4& qj, const Q4& qij, const double* U, const DevLoss& L, EdgeTerms& o) {
   const Q4 qE = qmul(qmul(qj, qconj(qi)), qconj(qij));  // error rotation R_j R_i^T R_ij^T
+  #ifndef GSFM_NO_STENCIL_FAST
+  if (kNeedJacobian && kStencilOnly && kScalarU && kResidual == 0) {
+#else
+  if (false) {
+#endif
+    double e[3], theta2, c;
+    quat_log(qE, e, &theta2, &c);
+    const double w = U[0], w2 = w * w;
+    o.r[0] = w * e[0]; o.r[1] = w * e[1]; o.r[2] = w * e[2];
+    const double s = o.r[0] * o.r[0] + o.r[1] * o.r[1] + o.r[2] * o.r[2];  // exactly as the general path (quantised losses)
+    eval_loss<kLoss>(L, s, o.rho);
+    // f = R_j^T e = e - w_j t + v_j x t,  t = 2 v_j x e
+    const double tx = 2.0 * (qj.y * e[2] - qj.z * e[1]), ty = 2.0 * (qj.z * e[0] - qj.x * e[2]), tz = 2.0 * (qj.x * e[1] - qj.y * e[0]);
+    const double f0 = e[0] - qj.w * tx + (qj.y * tz - qj.z * ty);
+    const double f1 = e[1] - qj.w * ty + (qj.z * tx - qj.x * tz);
+    const double f2 = e[2] - qj.w * tz + (qj.x * ty - qj.y * tx);
+    const double g = 2.0 * c - 0.25 - c * c * theta2;
+    const double kappa = triggs_kappa(s, o.rho);
+    const double rw = o.rho[1] * w2;
+    const double a = rw * (1.0 - g * theta2), b = rw * (g - kappa * w2);
+    const double bf0 = b * f0, bf1 = b * f1, bf2 = b * f2;
+    o.S[0] = a + bf0 * f0; o.S[1] = bf0 * f1; o.S[2] = bf0 * f2;
+    o.S[3] = a + bf1 * f1; o.S[4] = bf1 * f2; o.S[5] = a + bf2 * f2;
+    o.v[0] = rw * f0; o.v[1] = rw * f1; o.v[2] = rw * f2;
+    return;
+  }
   double M[9];                                           // d r / d(left perturbation of E) before the weight
   if (kResidual == 1) {
     const double w = U[0];
