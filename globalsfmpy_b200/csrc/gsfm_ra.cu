@@ -110,6 +110,7 @@ struct DevScalars {
   double dg, dHd, step2;  // delta.g, delta.H.delta, |delta|^2 (Euclidean step)
   int bad;                // non-finite detected (1) / a peer GPU did not show up (2)
   int xseq;               // cross-GPU exchange sequence number (multi-GPU persistent PCG)
+  int bar_seq, pad1;      // grid barrier sequence number of the persistent PCG kernel
   // %globaltimer stamps of the trust-region batch: start of k_prepare_solve, end of k_apply_step, end of k_node_finalize
   unsigned long long t_begin, t_linear_end, t_end;
 };
@@ -136,7 +137,7 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 }
 
 // Deterministic grid-wide sum of NV values: block tree -> per-block slot -> the LAST block to
-// arrive adds the slots in index order.  Returns true in the last block (all threads), with the
+// arrive adds the slots in a fixed order.  Returns true in the last block (all threads), with the
 // totals in `tot` (valid in thread 0 only).
 template <int NV>
 __device__ bool grid_sum(double (&v)[NV], double* slots, unsigned* counter, double (&tot)[NV]) {
@@ -162,14 +163,19 @@ __device__ bool grid_sum(double (&v)[NV], double* slots, unsigned* counter, doub
   }
   __syncthreads();
   if (!is_last) return false;
-  if (threadIdx.x == 0) {
+  // the last block: warp 0 adds the slots, lane l the blocks l, l+32, ... in order, then a butterfly -- a fixed order
+  // whatever block happens to be last, and all loads of a lane are independent (no serial chain of L2 round trips)
+  if (warp == 0) {
     __threadfence();
+    double acc[NV];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) tot[k] = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b)
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    for (unsigned b = lane; b < gridDim.x; b += 32)
 #pragma unroll
-      for (int k = 0; k < NV; ++k) tot[k] += ((volatile double*)slots)[(size_t)b * NV + k];
-    *counter = 0u;
+      for (int k = 0; k < NV; ++k) acc[k] += __ldcg(slots + (size_t)b * NV + k);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) tot[k] = warp_sum(acc[k]);
+    if (lane == 0) *counter = 0u;
   }
   return true;
 }
@@ -296,29 +302,38 @@ __global__ void k_embed_cols(uint64_t H, int blk, const uint32_t* __restrict__ h
 //   quaternion parameters with EigenQuaternionParameterization (x (+) delta = [sin|d| d/|d|, cos|d|] (x) x, i.e. a LEFT
 //   perturbation phi = 2 delta):  beta = R^T phi  ->  D = 2 R^T;  |x|^2 = 1 per unit quaternion
 // The array keeps its historical name node_JL.
+// per-view body of k_node_prep; returns the view's contribution to |x|^2
+__device__ __forceinline__ double node_prep_view(uint32_t i, const double* w3, double* __restrict__ node_q, double* __restrict__ node_JL, int manifold) {
+  const double wx = w3[0], wy = w3[1], wz = w3[2];
+  const Q4 q = aa_to_quat(wx, wy, wz);
+  reinterpret_cast<double4*>(node_q)[i] = make_double4(q.w, q.x, q.y, q.z);
+  double J[9];
+  double xn;
+  if (manifold) {
+    double R[9];
+    quat_to_mat(q, R);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) J[3 * r + c] = 2.0 * R[3 * c + r];
+    xn = 1.0;
+  } else {
+    so3_left_jacobian(-wx, -wy, -wz, J);
+    xn = wx * wx + wy * wy + wz * wz;
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) node_JL[9 * (size_t)i + t] = J[t];
+  return xn;
+}
+
 __global__ void k_node_prep(uint32_t N, const double* __restrict__ omega, double* __restrict__ node_q, double* __restrict__ node_JL,
                             double* slots, unsigned* counter, DevScalars* sc, int manifold) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   double v[1] = {0.0};
+  if (i == 0) sc->gmax = 0.0;  // max |g| of this evaluation is accumulated (atomicMax) by the k_node_finalize that follows
   if (i < N) {
-    const double wx = omega[3 * i], wy = omega[3 * i + 1], wz = omega[3 * i + 2];
-    const Q4 q = aa_to_quat(wx, wy, wz);
-    reinterpret_cast<double4*>(node_q)[i] = make_double4(q.w, q.x, q.y, q.z);
-    double J[9];
-    if (manifold) {
-      double R[9];
-      quat_to_mat(q, R);
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) J[3 * r + c] = 2.0 * R[3 * c + r];
-      v[0] = 1.0;
-    } else {
-      so3_left_jacobian(-wx, -wy, -wz, J);
-      v[0] = wx * wx + wy * wy + wz * wz;
-    }
-#pragma unroll
-    for (int t = 0; t < 9; ++t) node_JL[9 * (size_t)i + t] = J[t];
+    const double w3[3] = {omega[3 * (size_t)i], omega[3 * (size_t)i + 1], omega[3 * (size_t)i + 2]};
+    v[0] = node_prep_view(i, w3, node_q, node_JL, manifold);
   }
   double tot[1];
   if (grid_sum<1>(v, slots, counter, tot) && threadIdx.x == 0) sc->xnorm2 = tot[0];
@@ -640,57 +655,65 @@ __global__ void k_jacobi_scale(uint32_t n3, const double* __restrict__ ediag, do
 //   moved to the tangent frame  Lam = Jl^-T diag(lam) Jl^-1 ;  Dblk = Hd + Lam ; Minv = Dblk^-1.
 // Also initialises PCG: x = 0, r = b = -gt, z = Minv r, p = z, q = 0, and reduces rz, bb.  z and p are the vectors
 // the SpMV gathers: stored with stride 4 (double4), everything else with stride 3.
-__global__ void k_prepare_solve(uint32_t N, double mu, double lo, double hi, const double* __restrict__ ediag,
-                                const double* __restrict__ scale, const double* __restrict__ node_JL, const double* __restrict__ Hd,
-                                const double* __restrict__ gt, const double* __restrict__ user_damp, const double* __restrict__ user_b,
-                                double* __restrict__ Dblk, double* __restrict__ Minv, double* __restrict__ x, double* __restrict__ r,
-                                double* __restrict__ z, double* __restrict__ p, double* __restrict__ q, double* __restrict__ bvec,
-                                double* slots, unsigned* counter, DevScalars* sc, const IterParams* ip) {
+struct PrepareArgs {
+  double mu, lo, hi;
+  const double *ediag, *scale, *node_JL, *Hd, *gt, *user_damp, *user_b;
+  double *Dblk, *Minv, *x, *r, *z, *p, *q, *bvec;
+};
+// per-view body of k_prepare_solve; adds the view's (b.z, b.b) to v
+__device__ __forceinline__ void prepare_view(uint32_t i, const PrepareArgs& A, double (&v)[2]) {
+  // every load first (the arrays may alias as far as the compiler knows: a store between two loads serialises the
+  // L2 round trips)
+  double lam[3], J[9], Hd[6], b[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    if (A.user_damp) lam[c] = A.user_damp[3 * (size_t)i + c];
+    else {
+      const double s2 = A.scale[3 * (size_t)i + c] * A.scale[3 * (size_t)i + c];
+      lam[c] = fmin(fmax(A.ediag[3 * (size_t)i + c] * s2, A.lo), A.hi) / A.mu / s2;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) J[k] = A.node_JL[9 * (size_t)i + k];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) Hd[k] = A.Hd[6 * (size_t)i + k];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) b[c] = A.user_b ? A.user_b[3 * (size_t)i + c] : -A.gt[3 * (size_t)i + c];
+  double Ji[9];
+  inv3(J, Ji);
+  double lamS[6] = {lam[0], 0.0, 0.0, lam[1], 0.0, lam[2]};
+  double Lam[6];
+  congruence(Ji, lamS, Lam);
+  double D[6], M[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) D[k] = Hd[k] + Lam[k];
+  sym_inv(D, M);
+  if (A.user_b) {  // b given in Euclidean coordinates: bt = Jl^-T b
+    const double u0 = b[0], u1 = b[1], u2 = b[2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) b[c] = Ji[c] * u0 + Ji[3 + c] * u1 + Ji[6 + c] * u2;
+  }
+  double zz[3];
+  sym_mul_vec(M, b, zz);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { A.Dblk[6 * (size_t)i + k] = D[k]; A.Minv[6 * (size_t)i + k] = M[k]; }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    A.x[3 * (size_t)i + c] = 0.0; A.r[3 * (size_t)i + c] = b[c]; A.bvec[3 * (size_t)i + c] = b[c]; A.q[3 * (size_t)i + c] = 0.0;
+    v[0] += b[c] * zz[c];
+    v[1] += b[c] * b[c];
+  }
+  // the gathered vectors are padded to one aligned 32 B sector per view
+  reinterpret_cast<double4*>(A.z)[i] = make_double4(zz[0], zz[1], zz[2], 0.0);
+  reinterpret_cast<double4*>(A.p)[i] = make_double4(zz[0], zz[1], zz[2], 0.0);
+}
+
+__global__ void k_prepare_solve(uint32_t N, PrepareArgs A, double* slots, unsigned* counter, DevScalars* sc, const IterParams* ip) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ip) mu = ip->mu;
+  if (ip) A.mu = ip->mu;
   if (i == 0) sc->t_begin = gtimer_ns();
   double v[2] = {0.0, 0.0};
-  if (i < N) {
-    double lam[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      if (user_damp) lam[c] = user_damp[3 * (size_t)i + c];
-      else {
-        const double s2 = scale[3 * (size_t)i + c] * scale[3 * (size_t)i + c];
-        lam[c] = fmin(fmax(ediag[3 * (size_t)i + c] * s2, lo), hi) / mu / s2;
-      }
-    }
-    double J[9], Ji[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) J[k] = node_JL[9 * (size_t)i + k];
-    inv3(J, Ji);
-    double lamS[6] = {lam[0], 0.0, 0.0, lam[1], 0.0, lam[2]};
-    double Lam[6];
-    congruence(Ji, lamS, Lam);
-    double D[6], M[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) { D[k] = Hd[6 * (size_t)i + k] + Lam[k]; Dblk[6 * (size_t)i + k] = D[k]; }
-    sym_inv(D, M);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) Minv[6 * (size_t)i + k] = M[k];
-    double b[3], zz[3];
-    if (user_b) {  // b given in Euclidean coordinates: bt = Jl^-T b
-#pragma unroll
-      for (int c = 0; c < 3; ++c) b[c] = Ji[c] * user_b[3 * (size_t)i] + Ji[3 + c] * user_b[3 * (size_t)i + 1] + Ji[6 + c] * user_b[3 * (size_t)i + 2];
-    } else {
-      b[0] = -gt[3 * (size_t)i]; b[1] = -gt[3 * (size_t)i + 1]; b[2] = -gt[3 * (size_t)i + 2];
-    }
-    sym_mul_vec(M, b, zz);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      x[3 * (size_t)i + c] = 0.0; r[3 * (size_t)i + c] = b[c]; bvec[3 * (size_t)i + c] = b[c]; q[3 * (size_t)i + c] = 0.0;
-      v[0] += b[c] * zz[c];
-      v[1] += b[c] * b[c];
-    }
-    // the gathered vectors are padded to one aligned 32 B sector per view
-    reinterpret_cast<double4*>(z)[i] = make_double4(zz[0], zz[1], zz[2], 0.0);
-    reinterpret_cast<double4*>(p)[i] = make_double4(zz[0], zz[1], zz[2], 0.0);
-  }
+  if (i < N) prepare_view(i, A, v);
   double tot[2];
   if (grid_sum<2>(v, slots, counter, tot) && threadIdx.x == 0) {
     sc->rz = tot[0]; sc->bb = tot[1]; sc->rr = tot[1];
@@ -892,6 +915,81 @@ __global__ void k_pcg_direction(uint32_t n3, const double* __restrict__ z, doubl
 // grid = SMs x occupancy), each range into segments (range ^ row).
 // Vectors written inside the kernel are never accessed through __restrict__/read-only paths.
 // ------------------------------------------------------------------------------------------
+// After the solve (xt = tangent step): parameter step delta = D^-1 xt, candidate = omega + delta (Ceres updates the
+// angle-axis vector additively) or, on the manifold, R <- R Exp(xt); reduces delta.g (= xt.gt),
+// delta.H.delta = xt.Ht.xt and |delta|^2.  The quadratic form needs no matrix pass: (Ht + Lam) xt = b - r with the
+// solver's residual r, so xt.Ht.xt = xt.(b - r) - xt.Lam.xt, Lam_i = Dblk_i - Hd_i -- all per-view quantities.
+struct ApplyArgs {
+  const double *node_JL, *xt, *bvec, *res, *Dblk, *Hd, *gt, *omega;
+  double *cand, *delta_out;
+  int manifold;
+};
+// per-view body of k_apply_step: v += (delta.g, delta.H.delta, |delta|^2, non-finite flag); the candidate is also returned in w3
+__device__ __forceinline__ void apply_view(uint32_t i, const ApplyArgs& A, double (&v)[4], double* w3) {
+  // every load first (see prepare_view)
+  double J[9], om[3] = {0.0, 0.0, 0.0}, g3[3] = {0.0, 0.0, 0.0}, lam[6] = {0, 0, 0, 0, 0, 0}, br[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < 9; ++k) J[k] = A.node_JL[9 * (size_t)i + k];
+  const double t0 = A.xt[3 * (size_t)i], t1 = A.xt[3 * (size_t)i + 1], t2 = A.xt[3 * (size_t)i + 2];
+  if (A.omega) { om[0] = A.omega[3 * (size_t)i]; om[1] = A.omega[3 * (size_t)i + 1]; om[2] = A.omega[3 * (size_t)i + 2]; }
+  if (A.gt) { g3[0] = A.gt[3 * (size_t)i]; g3[1] = A.gt[3 * (size_t)i + 1]; g3[2] = A.gt[3 * (size_t)i + 2]; }
+  if (A.bvec) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) lam[k] = A.Dblk[6 * (size_t)i + k] - A.Hd[6 * (size_t)i + k];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) br[c] = A.bvec[3 * (size_t)i + c] - (A.res ? A.res[3 * (size_t)i + c] : 0.0);
+  }
+  double Ji[9];
+  inv3(J, Ji);
+  double d[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) d[c] = Ji[3 * c] * t0 + Ji[3 * c + 1] * t1 + Ji[3 * c + 2] * t2;
+  w3[0] = w3[1] = w3[2] = 0.0;
+  if (A.manifold) {
+    // x (+) delta = [sin|d| d/|d|, cos|d|] (x) x, a left rotation by 2 delta = R xt, i.e. R <- R Exp(xt); the state stays
+    // an angle-axis vector (principal branch of the product quaternion).  |step| in the ambient quaternion space =
+    // 2 sin(|delta| / 2) per view, |delta| = |xt| / 2.
+    const Q4 qd = aa_to_quat(t0, t1, t2);
+    const Q4 qo = aa_to_quat(om[0], om[1], om[2]);
+    double th2, cc;
+    quat_log(qmul(qo, qd), w3, &th2, &cc);
+    const double dn = 0.5 * sqrt(t0 * t0 + t1 * t1 + t2 * t2);
+    const double sh = sin(0.5 * dn);
+    v[2] += 4.0 * sh * sh;
+    if (!isfinite(dn)) v[3] = 1.0;
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      w3[c] = om[c] + d[c];
+      v[2] += d[c] * d[c];
+      if (!isfinite(d[c])) v[3] = 1.0;
+    }
+  }
+  if (A.gt) v[0] += t0 * g3[0] + t1 * g3[1] + t2 * g3[2];
+  if (A.bvec) {
+    const double t[3] = {t0, t1, t2};
+    double lx[3];
+    sym_mul_vec(lam, t, lx);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[1] += t[c] * (br[c] - lx[c]);
+  }
+  if (A.delta_out) { A.delta_out[3 * (size_t)i] = d[0]; A.delta_out[3 * (size_t)i + 1] = d[1]; A.delta_out[3 * (size_t)i + 2] = d[2]; }
+  if (A.cand) { A.cand[3 * (size_t)i] = w3[0]; A.cand[3 * (size_t)i + 1] = w3[1]; A.cand[3 * (size_t)i + 2] = w3[2]; }
+}
+
+__global__ void k_apply_step(uint32_t N, ApplyArgs A, double* slots, unsigned* counter, DevScalars* sc) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  double w3[3];
+  if (i < N) apply_view(i, A, v, w3);
+  double tot[4];
+  if (grid_sum<4>(v, slots, counter, tot) && threadIdx.x == 0) {
+    sc->dg = tot[0]; sc->dHd = tot[1]; sc->step2 = tot[2];
+    sc->t_linear_end = gtimer_ns();
+    (void)tot[3];  // a non-finite step makes step2 non-finite: the host treats it as an invalid step
+  }
+}
+
 constexpr int kMaxPeers = 16;
 
 struct PcgParams {
@@ -903,9 +1001,17 @@ struct PcgParams {
   const double *val, *Dblk, *Minv;
   double *x, *r, *z, *p, *q, *s, *ypart;
   unsigned* row_cnt;
-  double *slotsA, *slotsB;
+  unsigned long long* bar_slots;  // [2][grid][4]: grid barrier + reduction (grid_bar_sum2)
+  double* slots;                  // grid_sum scratch (epilogue)
+  unsigned* counter;
   DevScalars* sc;
   unsigned long long* prof;  // optional [8] phase timers in ns, accumulated by block 0 (measurement aid)
+  // fused trust-region step: prologue = k_prepare_solve's per-view work, epilogue = k_apply_step + k_node_prep of the candidate
+  int fused;
+  const IterParams* ip;
+  PrepareArgs prep;
+  ApplyArgs apply;
+  double *cand_q, *cand_JL;
   // edge-sharded multi-GPU (world > 1): every rank's exchange block, mapped into this process over NVLink
   // (CUDA IPC).  Layout of one block: double y[2][3N] (partial matvec, double buffered by step parity) followed
   // by the rank's sequence flag.  peer_y[rank] / peer_flag[rank] are this rank's own block.
@@ -920,41 +1026,33 @@ __device__ __forceinline__ unsigned long long gtimer() {
   return t;
 }
 
-__device__ __forceinline__ double block_sum_to_thread0(double v, double* sm) {
-  v = warp_sum(v);
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+// Grid barrier + deterministic reduction of two doubles (the persistent PCG kernel): block sums go to per-block slots,
+// cooperative groups' grid.sync, then every block adds the slots in the same order.  Two slot sets alternate by barrier
+// parity (a block can reach barrier n+2 only after every block arrived at n+1, i.e. finished reading n).
+// (Measured alternative, profiles/r01_h: publishing {data | sequence} words and polling all blocks' slots instead of
+// grid.sync is slower -- 296 pollers x 296 slots of dependent L2 round trips.)
+__device__ __forceinline__ void grid_bar_sum2(cg::grid_group& grid, unsigned long long* bar_slots, unsigned& seq, double v0, double v1,
+                                              double* sm_red /*[2*kWarpsPerBlock + 2]*/, double& out0, double& out1) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v0 = warp_sum(v0); v1 = warp_sum(v1);
+  if (lane == 0) { sm_red[2 * warp] = v0; sm_red[2 * warp + 1] = v1; }
   __syncthreads();
-  double s = 0.0;
-  if (threadIdx.x == 0)
-    for (int w = 0; w < kWarpsPerBlock; ++w) s += sm[w];
-  __syncthreads();
-  return s;
-}
-
-// Sum slot k of every block, same order in every block; result broadcast to all threads.
-__device__ __forceinline__ double all_blocks_sum(const double* slots, int stride, int k, double* sm_b) {
-  if (threadIdx.x < 32) {
-    double s = 0.0;
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += 32) s += __ldcg(slots + (size_t)b * stride + k);
-    s = warp_sum(s);
-    if (threadIdx.x == 0) *sm_b = s;
+  ++seq;
+  double* set = reinterpret_cast<double*>(bar_slots) + (size_t)(seq & 1u) * 2 * gridDim.x;
+  if (threadIdx.x == 0) {
+    double b0 = 0.0, b1 = 0.0;
+    for (int w = 0; w < kWarpsPerBlock; ++w) { b0 += sm_red[2 * w]; b1 += sm_red[2 * w + 1]; }
+    __stcg(set + 2 * (size_t)blockIdx.x, b0); __stcg(set + 2 * (size_t)blockIdx.x + 1, b1);
   }
-  __syncthreads();
-  const double out = *sm_b;
-  __syncthreads();
-  return out;
-}
-
-__device__ __forceinline__ void all_blocks_sum2(const double* slots, double* o0, double* o1, double* sm_b2) {
-  if (threadIdx.x < 32) {
+  grid.sync();
+  if (warp == 0) {
     double s0 = 0.0, s1 = 0.0;
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += 32) { s0 += __ldcg(slots + 2 * (size_t)b); s1 += __ldcg(slots + 2 * (size_t)b + 1); }
+    for (unsigned b = lane; b < gridDim.x; b += 32) { s0 += __ldcg(set + 2 * (size_t)b); s1 += __ldcg(set + 2 * (size_t)b + 1); }
     s0 = warp_sum(s0); s1 = warp_sum(s1);
-    if (threadIdx.x == 0) { sm_b2[0] = s0; sm_b2[1] = s1; }
+    if (lane == 0) { sm_red[2 * kWarpsPerBlock] = s0; sm_red[2 * kWarpsPerBlock + 1] = s1; }
   }
   __syncthreads();
-  *o0 = sm_b2[0]; *o1 = sm_b2[1];
-  __syncthreads();
+  out0 = sm_red[2 * kWarpsPerBlock]; out1 = sm_red[2 * kWarpsPerBlock + 1];
 }
 
 // Row i once its off-diagonal sum (y0,y1,y2) is complete: s_i = D_i z_i + y, store, inner products.
@@ -1072,21 +1170,35 @@ __global__ void __launch_bounds__(kBlock) k_pcg_persistent(PcgParams P) {
   cg::grid_group grid = cg::this_grid();
   WarpPipe wp;
   pipe_init<kBlk>(wp, smem_raw);
-  __shared__ double sm_red[kWarpsPerBlock];
-  __shared__ double sm_b;
-  __shared__ double sm_b2[2];
+  __shared__ double sm_red[2 * kWarpsPerBlock + 2];
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-  const double bb = P.sc->bb;
+  unsigned bseq = (unsigned)P.sc->bar_seq;  // barrier sequence number, continues across launches
+  double bb;
+  bool done;
+  if (P.fused) {
+    // ---- prologue (k_prepare_solve): LM damping in the tangent frame, block-Jacobi inverse, x = 0, r = b, z = p = M^-1 b
+    if (gtid == 0) { P.sc->t_begin = gtimer_ns(); P.sc->bad = 0; }
+    PrepareArgs A = P.prep;
+    if (P.ip) A.mu = P.ip->mu;
+    double v[2] = {0.0, 0.0};
+    for (uint32_t i = blockIdx.x + gridDim.x * threadIdx.x; i < P.N; i += gthreads) prepare_view(i, A, v);
+    double rz0;
+    grid_bar_sum2(grid, P.bar_slots, bseq, v[0], v[1], sm_red, rz0, bb);
+    done = (bb == 0.0 || !isfinite(bb));
+    if (gtid == 0) { P.sc->bb = bb; P.sc->rz = rz0; }
+  } else {
+    bb = P.sc->bb;
+    done = P.sc->pcg_done != 0;
+  }
   double rr = bb, beta = 0.0, alpha = 0.0, gamma_old = 0.0;
   int iter = 0, breakdown = 0;
-  bool done = P.sc->pcg_done != 0;
   const bool multi = P.world > 1;
   unsigned seq = multi ? (unsigned)P.sc->xseq : 0u;  // exchange sequence number, continues across launches
   double* my_y = multi ? P.peer_y[P.rank] : nullptr;
   while (!done) {
     // ---- phase A: s = (Ht + Lam) z, gamma = r.z, delta = z.s ---------------------------------
     const bool prof = P.prof != nullptr && gtid == 0;
-    unsigned long long tA = 0, tB = 0, tC = 0, tD = 0, tE = 0, tF = 0, tG = 0;
+    unsigned long long tA = 0, tB = 0, tC = 0, tE = 0, tF = 0;
     if (prof) tA = gtimer();
     double g_part = 0.0, d_part = 0.0;
     if (!multi) spmv_pass<kBlk>(P, wp, g_part, d_part);
@@ -1096,14 +1208,9 @@ __global__ void __launch_bounds__(kBlock) k_pcg_persistent(PcgParams P) {
       exchange_finish(P, grid, seq, g_part, d_part);
     }
     if (prof) tB = gtimer();
-    const double bs0 = block_sum_to_thread0(g_part, sm_red);
-    const double bs1 = block_sum_to_thread0(d_part, sm_red);
-    if (threadIdx.x == 0) { __stcg(P.slotsA + 2 * (size_t)blockIdx.x, bs0); __stcg(P.slotsA + 2 * (size_t)blockIdx.x + 1, bs1); }
-    grid.sync();
-    if (prof) tC = gtimer();
     double gamma, delta;
-    all_blocks_sum2(P.slotsA, &gamma, &delta, sm_b2);
-    if (prof) tD = gtimer();
+    grid_bar_sum2(grid, P.bar_slots, bseq, g_part, d_part, sm_red, gamma, delta);
+    if (prof) tC = gtimer();
     // p = z + beta p  =>  p.Ap = delta - beta^2 (p_old.A p_old) = delta - beta gamma / alpha_old
     beta = (iter == 0) ? 0.0 : gamma / gamma_old;
     const double pAp = (iter == 0) ? delta : delta - beta * gamma / alpha;
@@ -1143,14 +1250,11 @@ __global__ void __launch_bounds__(kBlock) k_pcg_persistent(PcgParams P) {
       reinterpret_cast<double4*>(P.z)[i] = make_double4(zn[0], zn[1], zn[2], 0.0);
     }
     if (prof) tE = gtimer();
-    const double b1 = block_sum_to_thread0(v1, sm_red);
-    if (threadIdx.x == 0) __stcg(P.slotsB + blockIdx.x, b1);
-    grid.sync();
-    if (prof) tF = gtimer();
-    rr = all_blocks_sum(P.slotsB, 1, 0, &sm_b);
+    double unused;
+    grid_bar_sum2(grid, P.bar_slots, bseq, v1, 0.0, sm_red, rr, unused);
     if (prof) {
-      tG = gtimer();
-      P.prof[0] += tB - tA; P.prof[1] += tC - tB; P.prof[2] += tD - tC; P.prof[3] += tE - tD; P.prof[4] += tF - tE; P.prof[5] += tG - tF;
+      tF = gtimer();
+      P.prof[0] += tB - tA; P.prof[1] += tC - tB; P.prof[3] += tE - tC; P.prof[4] += tF - tE;
       P.prof[6] += 1;
     }
     ++iter;
@@ -1158,8 +1262,25 @@ __global__ void __launch_bounds__(kBlock) k_pcg_persistent(PcgParams P) {
   }
   if (gtid == 0) {
     P.sc->xseq = (int)seq;
+    P.sc->bar_seq = (int)bseq;
     P.sc->rz = gamma_old; P.sc->rr = rr; P.sc->beta = beta; P.sc->alpha = alpha;
     P.sc->pcg_iter = iter; P.sc->pcg_done = 1; P.sc->pcg_breakdown = breakdown;
+  }
+  if (P.fused) {
+    // ---- epilogue (k_apply_step + k_node_prep of the candidate): x is complete and visible (the loop ends on a barrier;
+    // a breakdown leaves the previous, barrier-covered x) ------------------------------------------
+    double v[4] = {0.0, 0.0, 0.0, 0.0}, xn = 0.0;
+    for (uint32_t i = blockIdx.x + gridDim.x * threadIdx.x; i < P.N; i += gthreads) {
+      double w3[3];
+      apply_view(i, P.apply, v, w3);
+      xn += node_prep_view(i, w3, P.cand_q, P.cand_JL, P.apply.manifold);
+    }
+    double v5[5] = {v[0], v[1], v[2], v[3], xn}, tot[5];
+    if (grid_sum<5>(v5, P.slots, P.counter, tot) && threadIdx.x == 0) {
+      P.sc->dg = tot[0]; P.sc->dHd = tot[1]; P.sc->step2 = tot[2]; P.sc->xnorm2 = tot[4];
+      P.sc->gmax = 0.0;  // accumulated by the k_node_finalize of the candidate's evaluation
+      P.sc->t_linear_end = gtimer_ns();
+    }
   }
 }
 
@@ -1343,66 +1464,6 @@ __global__ void __launch_bounds__(kBlock) k_dense_cholesky_solve(uint32_t n, uin
     }
     for (uint32_t i = tid; i < n; i += kBlock) x[i] = work[i];
     if (tid == 0) { sc->pcg_iter = 1; sc->pcg_done = 1; sc->pcg_breakdown = s_fail; sc->rr = 0.0; }
-  }
-}
-
-// After the solve (xt = tangent step): parameter step delta = D^-1 xt, candidate = omega + delta (Ceres updates the
-// angle-axis vector additively) or, on the manifold, R <- R Exp(xt); reduces delta.g (= xt.gt),
-// delta.H.delta = xt.Ht.xt and |delta|^2.  The quadratic form needs no matrix pass: (Ht + Lam) xt = b - r with the
-// solver's residual r, so xt.Ht.xt = xt.(b - r) - xt.Lam.xt, Lam_i = Dblk_i - Hd_i -- all per-view quantities.
-__global__ void k_apply_step(uint32_t N, const double* __restrict__ node_JL, const double* __restrict__ xt, const double* __restrict__ bvec,
-                             const double* __restrict__ res, const double* __restrict__ Dblk, const double* __restrict__ Hd,
-                             const double* __restrict__ gt, const double* __restrict__ omega, double* __restrict__ cand,
-                             double* __restrict__ delta_out, double* slots, unsigned* counter, DevScalars* sc, int manifold) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  double v[4] = {0.0, 0.0, 0.0, 0.0};
-  if (i < N) {
-    double J[9], Ji[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) J[k] = node_JL[9 * (size_t)i + k];
-    inv3(J, Ji);
-    const double t0 = xt[3 * (size_t)i], t1 = xt[3 * (size_t)i + 1], t2 = xt[3 * (size_t)i + 2];
-    double d[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) d[c] = Ji[3 * c] * t0 + Ji[3 * c + 1] * t1 + Ji[3 * c + 2] * t2;
-    if (delta_out) { delta_out[3 * (size_t)i] = d[0]; delta_out[3 * (size_t)i + 1] = d[1]; delta_out[3 * (size_t)i + 2] = d[2]; }
-    if (manifold) {
-      // x (+) delta = [sin|d| d/|d|, cos|d|] (x) x, a left rotation by 2 delta = R xt, i.e. R <- R Exp(xt); the state stays
-      // an angle-axis vector (principal branch of the product quaternion).  |step| in the ambient quaternion space =
-      // 2 sin(|delta| / 2) per view, |delta| = |xt| / 2.
-      const Q4 qd = aa_to_quat(t0, t1, t2);
-      const Q4 qo = aa_to_quat(omega[3 * (size_t)i], omega[3 * (size_t)i + 1], omega[3 * (size_t)i + 2]);
-      double e[3], th2, cc;
-      quat_log(qmul(qo, qd), e, &th2, &cc);
-      const double dn = 0.5 * sqrt(t0 * t0 + t1 * t1 + t2 * t2);
-      const double sh = sin(0.5 * dn);
-      if (cand) { cand[3 * (size_t)i] = e[0]; cand[3 * (size_t)i + 1] = e[1]; cand[3 * (size_t)i + 2] = e[2]; }
-      v[2] = 4.0 * sh * sh;
-      if (!isfinite(dn)) v[3] = 1.0;
-    } else {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (cand) cand[3 * (size_t)i + c] = omega[3 * (size_t)i + c] + d[c];
-        v[2] += d[c] * d[c];
-        if (!isfinite(d[c])) v[3] = 1.0;
-      }
-    }
-    if (gt) v[0] = t0 * gt[3 * (size_t)i] + t1 * gt[3 * (size_t)i + 1] + t2 * gt[3 * (size_t)i + 2];
-    if (bvec) {
-      const double t[3] = {t0, t1, t2};
-      double lam[6], lx[3];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) lam[k] = Dblk[6 * (size_t)i + k] - Hd[6 * (size_t)i + k];
-      sym_mul_vec(lam, t, lx);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) v[1] += t[c] * (bvec[3 * (size_t)i + c] - (res ? res[3 * (size_t)i + c] : 0.0) - lx[c]);
-    }
-  }
-  double tot[4];
-  if (grid_sum<4>(v, slots, counter, tot) && threadIdx.x == 0) {
-    sc->dg = tot[0]; sc->dHd = tot[1]; sc->step2 = tot[2];
-    sc->t_linear_end = gtimer_ns();
-    (void)tot[3];  // a non-finite step makes step2 non-finite: the host treats it as an invalid step
   }
 }
 
@@ -1831,7 +1892,9 @@ struct gsfm_ra_solver {
   int cur = 0;
   // PCG
   DevBuf<double> scale, Dblk, Minv, x, r, z, p, q, sv, bvec, y, ypart, delta, dense_A, dense_work, dense_winv;  // z, p: stride 4
-  DevBuf<double> slots, slotsA, slotsB;
+  DevBuf<double> slots;
+  DevBuf<unsigned long long> bar_slots;  // grid barrier + reduction slots of the persistent PCG kernel (see grid_bar_sum2)
+  bool fused_step = false;               // set while a trust-region batch is enqueued: PCG kernel runs prologue + epilogue
   DevBuf<unsigned> counter, row_cnt;
   DevBuf<DevScalars> sc;
   DevScalars* h_sc = nullptr;  // pinned
@@ -1957,12 +2020,14 @@ struct gsfm_ra_solver {
   }
 
   // ---- evaluation at omega[b]: node prep, K1 (or K1c), node finalize -------------------------
-  int evaluate(int b, bool jacobian, bool publish = false) {
+  int evaluate(int b, bool jacobian, bool publish = false, bool prepped = false) {
     HostMailbox* mb = publish ? mailbox_dev : nullptr;
     const IterParams* ip_dev = graph_params ? it_params.p : nullptr;  // graph replay: the sequence number comes from device memory
     const unsigned mseq = (publish && !graph_params) ? ++mailbox_seq : 0u;
-    CUDA_TRY(cudaMemsetAsync(&sc.p->gmax, 0, sizeof(double), stream));
-    k_node_prep<<<grid_for(N), kBlock, 0, stream>>>(N, omega[b].p, node_q[b].p, node_JL[b].p, slots.p, counter.p, sc.p, manifold() ? 1 : 0);
+    if (!prepped) {
+      k_node_prep<<<grid_for(N), kBlock, 0, stream>>>(N, omega[b].p, node_q[b].p, node_JL[b].p, slots.p, counter.p, sc.p, manifold() ? 1 : 0);
+      launches += 1;
+    }
     launch_edges(b, jacobian, val[b].p);
     double* tail = lin[b].p + 9ull * N;
     const int co = jacobian ? 0 : 1;
@@ -1979,7 +2044,7 @@ struct gsfm_ra_solver {
                                                            slots.p, counter.p, sc.p, mb, mseq, publish ? ip_dev : nullptr);
       launches += 2;
     }
-    launches += 3;
+    launches += 2;
     CUDA_TRY(cudaGetLastError());
     return 0;
   }
@@ -2000,6 +2065,19 @@ struct gsfm_ra_solver {
     return 0;
   }
 
+  PrepareArgs prepare_args(int b, double mu, const double* user_damp, const double* user_b) {
+    PrepareArgs A;
+    A.mu = mu; A.lo = opt.min_lm_diagonal; A.hi = opt.max_lm_diagonal;
+    A.ediag = ediag[b].p; A.scale = scale.p; A.node_JL = node_JL[b].p; A.Hd = Hd_p[b]; A.gt = gt_p[b]; A.user_damp = user_damp; A.user_b = user_b;
+    A.Dblk = Dblk.p; A.Minv = Minv.p; A.x = x.p; A.r = r.p; A.z = z.p; A.p = p.p; A.q = q.p; A.bvec = bvec.p;
+    return A;
+  }
+  ApplyArgs apply_args(int b, int c) {
+    ApplyArgs A;
+    A.node_JL = node_JL[b].p; A.xt = x.p; A.bvec = bvec.p; A.res = r.p; A.Dblk = Dblk.p; A.Hd = Hd_p[b]; A.gt = gt_p[b]; A.omega = omega[b].p;
+    A.cand = omega[c].p; A.delta_out = delta.p; A.manifold = manifold() ? 1 : 0;
+    return A;
+  }
   PcgParams pcg_params(int b, double rtol, int max_iter) {
     PcgParams P;
     P.N = N; P.num_warps = pk2.num_warps; P.n_iso = n_iso; P.max_iter = max_iter; P.H = H; P.rtol2 = rtol * rtol;
@@ -2007,7 +2085,9 @@ struct gsfm_ra_solver {
     P.node_seg_ptr = pk2.node_seg_ptr.p; P.iso = iso.p; P.warp_span = pk2.span;
     P.val = val[b].p; P.Dblk = Dblk.p; P.Minv = Minv.p;
     P.x = x.p; P.r = r.p; P.z = z.p; P.p = p.p; P.q = q.p; P.s = sv.p; P.ypart = ypart.p;
-    P.row_cnt = row_cnt.p; P.slotsA = slotsA.p; P.slotsB = slotsB.p; P.sc = sc.p; P.prof = prof_buf;
+    P.row_cnt = row_cnt.p; P.bar_slots = bar_slots.p; P.slots = slots.p; P.counter = counter.p; P.sc = sc.p; P.prof = prof_buf;
+    P.fused = 0; P.ip = nullptr; P.cand_q = nullptr; P.cand_JL = nullptr;
+    std::memset(&P.prep, 0, sizeof(P.prep)); std::memset(&P.apply, 0, sizeof(P.apply));
     P.world = peers_connected ? world : 1; P.rank = rank;
     for (int r = 0; r < kMaxPeers; ++r) {
       P.peer_y[r] = (double*)peer_base[r];
@@ -2019,10 +2099,12 @@ struct gsfm_ra_solver {
   // Block-Jacobi PCG on (Ht + Lam) xt = bt for linearisation b; on return (stream order) x = xt, r = the
   // residual bt - (Ht + Lam) xt and bvec = bt.  One cooperative launch; no host synchronisation.
   int pcg_enqueue(int b, double mu, const double* user_damp, const double* user_b, double rtol, int max_iter) {
-    k_prepare_solve<<<grid_for(N), kBlock, 0, stream>>>(N, mu, opt.min_lm_diagonal, opt.max_lm_diagonal, ediag[b].p, scale.p, node_JL[b].p,
-                                                         Hd_p[b], gt_p[b], user_damp, user_b, Dblk.p, Minv.p, x.p, r.p, z.p, p.p, q.p, bvec.p,
-                                                         slots.p, counter.p, sc.p, graph_params ? it_params.p : nullptr);
-    launches += 1;
+    const bool fuse = fused_step && !user_damp && !user_b;  // a trust-region batch: prologue and epilogue live in the PCG kernel
+    if (!fuse) {
+      k_prepare_solve<<<grid_for(N), kBlock, 0, stream>>>(N, prepare_args(b, mu, user_damp, user_b), slots.p, counter.p, sc.p,
+                                                           graph_params ? it_params.p : nullptr);
+      launches += 1;
+    }
     if (opt.linear_solver == GSFM_RA_SOLVER_DENSE_CHOLESKY) {
       const uint32_t n = 3 * N, np = (n + 1 + kNB - 1) / kNB * kNB;  // room for the right-hand-side row
       if (dense_A.n < (size_t)np * np) {
@@ -2047,6 +2129,13 @@ struct gsfm_ra_solver {
     }
     if (cooperative && (!sharded() || peers_connected)) {
       PcgParams P = pcg_params(b, rtol, max_iter);
+      P.fused = fuse ? 1 : 0;
+      if (fuse) {
+        P.prep = prepare_args(b, mu, nullptr, nullptr);
+        P.apply = apply_args(b, b ^ 1);
+        P.cand_q = node_q[b ^ 1].p; P.cand_JL = node_JL[b ^ 1].p;
+        P.ip = graph_params ? it_params.p : nullptr;
+      }
       void* args[] = {&P};
       const void* fn = (blk == 6) ? (const void*)k_pcg_persistent<6> : (const void*)k_pcg_persistent<9>;
       CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(pk2.grid), dim3(kBlock), args, smem_bytes(), stream));
@@ -2278,8 +2367,8 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   for (DevBuf<double>* d : {&s->scale, &s->x, &s->r, &s->q, &s->sv, &s->bvec, &s->y, &s->delta}) RA_TRY(d->alloc(3ull * N));
   RA_TRY(s->z.alloc(4ull * N));
   RA_TRY(s->p.alloc(4ull * N));
-  RA_TRY(s->slotsA.alloc(2 * (size_t)s->pk2.grid + 8));
-  RA_TRY(s->slotsB.alloc(2 * (size_t)s->pk2.grid + 8));
+  RA_TRY(s->bar_slots.alloc(2 * 4 * (size_t)s->pk2.grid + 8));
+  CUDA_TRY(cudaMemsetAsync(s->bar_slots.p, 0, (2 * 4 * (size_t)s->pk2.grid + 8) * sizeof(unsigned long long), st));
   RA_TRY(s->row_cnt.alloc(N));
   CUDA_TRY(cudaMemsetAsync(s->row_cnt.p, 0, (size_t)N * sizeof(unsigned), st));
   RA_TRY(s->Dblk.alloc(6ull * N));
@@ -2334,12 +2423,19 @@ void push_trace(gsfm_ra_summary* sum, const gsfm_ra_iteration& it) {
 int enqueue_batch(gsfm_ra_solver* s, int b, double mu) {
   const int c = b ^ 1;
   const uint32_t N = s->N;
-  CUDA_TRY(cudaMemsetAsync(&s->sc.p->bad, 0, sizeof(int), s->stream));
-  RA_TRY(s->pcg_enqueue(b, mu, nullptr, nullptr, s->opt.pcg_rtol, s->opt.pcg_max_iterations));
-  k_apply_step<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[b].p, s->x.p, s->bvec.p, s->r.p, s->Dblk.p, s->Hd_p[b], s->gt_p[b], s->omega[b].p,
-                                                      s->omega[c].p, s->delta.p, s->slots.p, s->counter.p, s->sc.p, s->manifold() ? 1 : 0);
-  s->launches += 1;
-  RA_TRY(s->evaluate(c, true, true));
+  // single GPU / fused exchange with the persistent PCG kernel: damping + PCG initialisation run as the kernel's prologue,
+  // step + candidate + its per-view preparation as its epilogue -> the batch is PCG, K1, node finalize
+  const bool fuse = s->opt.linear_solver == GSFM_RA_SOLVER_PCG && s->cooperative && (!s->sharded() || s->peers_connected) && !std::getenv("GSFM_RA_NO_FUSE");
+  if (!fuse) CUDA_TRY(cudaMemsetAsync(&s->sc.p->bad, 0, sizeof(int), s->stream));
+  s->fused_step = fuse;
+  const int rc = s->pcg_enqueue(b, mu, nullptr, nullptr, s->opt.pcg_rtol, s->opt.pcg_max_iterations);
+  s->fused_step = false;
+  RA_TRY(rc);
+  if (!fuse) {
+    k_apply_step<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->apply_args(b, c), s->slots.p, s->counter.p, s->sc.p);
+    s->launches += 1;
+  }
+  RA_TRY(s->evaluate(c, true, true, fuse));
   return 0;
 }
 
@@ -2712,9 +2808,8 @@ int gsfm_ra_solver_time_kernels(gsfm_ra_solver* s, int32_t repeats, double* out_
       CUDA_TRY(cudaMemcpyAsync(hp, pb.p, 64, cudaMemcpyDeviceToHost, s->stream));
       CUDA_TRY(cudaStreamSynchronize(s->stream));
       const double n = std::max<double>(1.0, (double)hp[6]);
-      std::fprintf(stderr, "[gsfm_ra] PCG phases of block 0, us per iteration: spmv_pass %.2f | reduce+grid.sync %.2f | slots sum %.2f | vector update %.2f | "
-                   "reduce+grid.sync %.2f | slots sum %.2f  (%d iterations)\n", hp[0] / n / 1e3, hp[1] / n / 1e3, hp[2] / n / 1e3, hp[3] / n / 1e3,
-                   hp[4] / n / 1e3, hp[5] / n / 1e3, (int)hp[6]);
+      std::fprintf(stderr, "[gsfm_ra] PCG phases of block 0, us per iteration: spmv_pass %.2f | barrier+sum %.2f | vector update %.2f | barrier+sum %.2f  "
+                   "(%d iterations)\n", hp[0] / n / 1e3, hp[1] / n / 1e3, hp[3] / n / 1e3, hp[4] / n / 1e3, (int)hp[6]);
     }
   }
   // restore the linearisation-dependent partials (K1 scratch wrote `part`): re-run the finalize inputs
@@ -2932,8 +3027,12 @@ int gsfm_ra_pcg(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, const 
   const int it = s->h_sc->pcg_iter;
   const double res = (s->h_sc->bb > 0.0) ? std::sqrt(s->h_sc->rr / s->h_sc->bb) : 0.0;
   // x = Jl^-1 xt
-  k_apply_step<<<grid_for(N), kBlock, 0, s->stream>>>(N, s->node_JL[0].p, s->x.p, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, s->delta.p,
-                                                      s->slots.p, s->counter.p, s->sc.p, 0);
+  {
+    ApplyArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.node_JL = s->node_JL[0].p; A.xt = s->x.p; A.delta_out = s->delta.p;
+    k_apply_step<<<grid_for(N), kBlock, 0, s->stream>>>(N, A, s->slots.p, s->counter.p, s->sc.p);
+  }
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(x, s->delta.p, 3ull * N * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
