@@ -95,15 +95,30 @@ class ClockSampler:
         except OSError:
             self.p = None
 
+    def _lines(self):
+        try:
+            with open(self.f.name) as f:
+                return f.read().splitlines()
+        except OSError:
+            return []
+
+    def wait_first_sample(self, timeout=3.0):
+        t0 = time.perf_counter()
+        while self.p is not None and not self._lines() and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        """Samples delivered so far were taken before the timed region: skip them in stop()."""
+        self.skip = len(self._lines())
+
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.03)     # let the sample that covers the end of the timed region arrive
         self.p.terminate()
         self.p.wait()
-        self.f.flush()
-        self.f.seek(0)
         sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
+        for line in self._lines()[getattr(self, "skip", 0):]:
             c = [t.strip() for t in line.split(",")]
             if len(c) < 9:
                 continue
@@ -255,8 +270,8 @@ def cpu_baseline_sample(prob, g, loss, seconds_budget=20.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="syn_10k_1M", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -305,11 +320,16 @@ def main():
             solver.set_rotations(g.omega_init)
         return s
 
-    for _ in range(args.warmup):
-        step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()      # nvidia-smi needs a few hundred ms to deliver its first sample: start it ahead of the warm-up
+    for _ in range(args.warmup):
+        step()
+    if rank == 0:
+        sampler.wait_first_sample()
+        for _ in range(args.warmup):   # back under load after the wait
+            step()
+        sampler.mark()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

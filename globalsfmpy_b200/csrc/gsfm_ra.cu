@@ -408,7 +408,10 @@ struct K1Args {
 };
 
 template <bool kWriteBlocks, int kResidual, bool kScalarU, int kLoss>
-__global__ void __launch_bounds__(kBlock, 2) k_edges(const K1Args A) {
+#ifndef GSFM_K1_MINBLOCKS
+#define GSFM_K1_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(kBlock, GSFM_K1_MINBLOCKS) k_edges(const K1Args A) {
   constexpr int kU = (kScalarU || kResidual == 1) ? 1 : 6;
   constexpr int kRD = (4 + kU) * 32 + 32;  // doubles per input record
   constexpr int kRB = kRD * 8;
@@ -1359,15 +1362,24 @@ __device__ __forceinline__ void tile_potrf_inv(double (*Lt)[kNB + 1], double (*W
 #pragma unroll
   for (int c = 0; c < kNB; ++c) Lt[lane][c] = (c <= lane) ? row[c] : 0.0;
   __syncwarp();
-  // column `lane` of X = L^-1: forward substitution, L read from shared memory (broadcast)
+  // column `lane` of X = L^-1 by forward substitution in saxpy form: once x[m] is known every remaining row takes its
+  // update independently (no serial dot products), L is read from shared memory as broadcasts, and the 32 reciprocals of
+  // the diagonal are formed in parallel (lane m holds L[m][m]) instead of one division per step.
+  double dg = 1.0;  // L[lane][lane] (select chain: a dynamic index would push row[] to local memory)
+#pragma unroll
+  for (int c = 0; c < kNB; ++c)
+    if (c == lane) dg = row[c];
+  const double rdiag = 1.0 / dg;
   double x[kNB];
 #pragma unroll
-  for (int i = 0; i < kNB; ++i) {
-    double acc = (i == lane) ? 1.0 : 0.0;
+  for (int i = 0; i < kNB; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
-    for (int m = 0; m < kNB; ++m)
-      if (m < i) acc -= Lt[i][m] * x[m];
-    x[i] = (i >= lane) ? acc / Lt[i][i] : 0.0;
+  for (int m = 0; m < kNB; ++m) {
+    const double xm = x[m] * __shfl_sync(0xffffffffu, rdiag, m);
+    x[m] = xm;
+#pragma unroll
+    for (int i = 0; i < kNB; ++i)
+      if (i > m) x[i] -= Lt[i][m] * xm;
   }
 #pragma unroll
   for (int i = 0; i < kNB; ++i) Wt[i][lane] = x[i];
@@ -1395,11 +1407,16 @@ __global__ void __launch_bounds__(kBlock) k_dense_cholesky_solve(uint32_t n, uin
     for (uint32_t ib = kb + 1 + blockIdx.x; ib < nblk; ib += gridDim.x) {
       for (int c = ty; c < kNB; c += 8) T1[tx][c] = A[(size_t)(kb * kNB + c) * np + ib * kNB + tx];
       __syncthreads();
-      for (int c = ty; c < kNB; c += 8) {
-        double acc = 0.0;
+      {  // k outer: one T1 read (2 wavefronts) serves the thread's four outputs, the W11 reads are broadcasts
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 8
-        for (int k = 0; k < kNB; ++k) acc += T1[tx][k] * W11[c][k];
-        A[(size_t)(kb * kNB + c) * np + ib * kNB + tx] = acc;
+        for (int k = 0; k < kNB; ++k) {
+          const double a = T1[tx][k];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[q] += a * W11[ty + 8 * q][k];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) A[(size_t)(kb * kNB + ty + 8 * q) * np + ib * kNB + tx] = acc[q];
       }
       __syncthreads();
     }
@@ -1419,16 +1436,24 @@ __global__ void __launch_bounds__(kBlock) k_dense_cholesky_solve(uint32_t n, uin
       while ((uint64_t)i * (i + 1) / 2 > t) --i;
       const uint32_t j = t - i * (i + 1) / 2;
       const uint32_t ib = kb + 1 + i, jb = kb + 1 + j;
+      double cur[4];  // the tile being updated: loaded with the operands, not after the products
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cur[q] = A[(size_t)(jb * kNB + ty + 8 * q) * np + ib * kNB + tx];
       for (int c = ty; c < kNB; c += 8) {
         T1[tx][c] = A[(size_t)(kb * kNB + c) * np + ib * kNB + tx];
         T2[tx][c] = A[(size_t)(kb * kNB + c) * np + jb * kNB + tx];
       }
       __syncthreads();
-      for (int c = ty; c < kNB; c += 8) {
-        double acc = 0.0;
+      {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 8
-        for (int k = 0; k < kNB; ++k) acc += T1[tx][k] * T2[c][k];
-        A[(size_t)(jb * kNB + c) * np + ib * kNB + tx] -= acc;
+        for (int k = 0; k < kNB; ++k) {
+          const double a = T1[tx][k];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[q] += a * T2[ty + 8 * q][k];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) A[(size_t)(jb * kNB + ty + 8 * q) * np + ib * kNB + tx] = cur[q] - acc[q];
       }
       __syncthreads();
     }

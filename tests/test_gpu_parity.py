@@ -437,6 +437,44 @@ def test_resident_solver_stepwise_equals_one_shot():
     S.close()
 
 
+@pytest.mark.parametrize("cfg", ["angle_axis", "covariance", "quaternion"])
+def test_batch_execution_paths_agree(cfg):
+    """One trust-region iteration can run as a CUDA graph replay of (fused PCG kernel, K1, node finalize), as direct
+    launches of the same kernels, or as the un-fused sequence (k_prepare_solve, PCG, k_apply_step, k_node_prep, K1,
+    k_node_finalize).  Same arithmetic per view and per edge; only the grouping of a few grid-wide sums differs, so the
+    solves must take the same number of iterations and agree to rounding."""
+    if cfg == "covariance":
+        g = vg.synthetic_pose_graph(150, 2500, seed=23, noise_deg=1.0, outlier_fraction=0.05, covariance=True)
+        et, loss = capi.ANGLE_AXIS_COVARIANCE, capi.Loss.make(capi.LOSS_SOFTLONE, 0.5)
+    else:
+        g = vg.synthetic_pose_graph(150, 2500, seed=23, noise_deg=1.0, outlier_fraction=0.05)
+        et, loss = (capi.ANGLE_AXIS if cfg == "angle_axis" else capi.QUATERNION_COSINE), CAUCHY
+    prob = solver.make_problem(g, et)
+    o = capi.default_options_py()
+    o.loss = loss
+    o.pcg_rtol = 1e-10
+    res = {}
+    for name, env in (("graph", {}), ("direct", {"GSFM_RA_NO_GRAPH": "1"}), ("unfused", {"GSFM_RA_NO_GRAPH": "1", "GSFM_RA_NO_FUSE": "1"})):
+        for k in ("GSFM_RA_NO_GRAPH", "GSFM_RA_NO_FUSE"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        try:
+            res[name] = solver.solve(prob, o, g.omega_init)
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+    om0, s0, _ = res["graph"]
+    assert capi.TERMINATION[s0.termination] in ("FUNCTION_TOLERANCE", "PARAMETER_TOLERANCE", "GRADIENT_TOLERANCE")
+    # graph replay and direct launches run the very same kernels: bit identical
+    assert np.array_equal(om0, res["direct"][0]) and s0.num_iterations == res["direct"][1].num_iterations
+    om2, s2, _ = res["unfused"]
+    assert s2.num_iterations == s0.num_iterations and s2.termination == s0.termination
+    assert abs(s2.final_cost - s0.final_cost) <= 1e-11 * abs(s0.final_cost)
+    assert vg.mean_angular_error(om0, om2)[0] < 1e-9
+    # and the un-fused run launches more kernels per iteration
+    assert s2.kernel_launches > s0.kernel_launches
+
+
 def test_filter_view_pairs():
     g = vg.synthetic_pose_graph(500, 20000, seed=4, noise_deg=1.0, outlier_fraction=0.2)
     prob = solver.make_problem(g, capi.ANGLE_AXIS)
