@@ -5,9 +5,9 @@
 
 Workload (BASELINE.json north_star / configs[3]): synthetic pose graph, 10k cameras / 1M relative
 rotations, 1 degree noise, 10% outlier R_ij, unit covariance (ANGLE_AXIS), Cauchy(0.05) loss, spanning-tree
-initialisation.  A STEP is one trust-region iteration of the solver: K1 fused residual/Jacobian/loss/assembly
-kernel at the candidate point + one full PCG solve (K2 SpMV per CG step) + the model/step kernels, exactly what
-gsfm_ra_solver_iterate() runs.  When a solve converges the rotations are reset to the initial guess and the next
+initialisation.  A STEP is one trust-region iteration of the solver: one full PCG solve (persistent kernel: damping /
+PCG init, a K2 SpMV pass per CG step, step + candidate) + the K1 fused residual/Jacobian/loss/assembly kernel at the
+candidate point + the per-view finalisation, replayed as one CUDA graph -- exactly what gsfm_ra_solver_iterate() runs.  When a solve converges the rotations are reset to the initial guess and the next
 solve starts (the restart's H2D copy and first linearisation stay inside the timed region).
 
 `value`     whole-job edges * iterations / second, problem resident in HBM when the timed region starts.
@@ -141,6 +141,8 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per CG step of k_pcg_persistent from the committed ncu --set full
+# capture of this workload (profiles/r01_h_ncu_full_summary.txt: a launch of 50 CG steps); None for workloads never captured
 NCU_TRAFFIC_PER_PASS = {}
 
 
