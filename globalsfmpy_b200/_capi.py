@@ -212,6 +212,9 @@ def declare(lib, oracle=False):
     lib.gsfm_ra_pcg.argtypes = [pp, lp, _dp, _dp, _dp, C.c_double, C.c_int32, _dp, C.POINTER(C.c_int32), _dp, C.c_int32]
     lib.gsfm_ra_eval_loss.argtypes = [lp, _dp, C.c_uint64, _dp, C.c_int32]
     lib.gsfm_ra_filter_view_pairs.argtypes = [pp, _dp, C.c_double, _u8p, _dp, C.c_int32]
+    _i32p = C.POINTER(C.c_int32)
+    lib.gsfm_ra_filter_initial_view_graph.argtypes = [C.c_uint32, C.c_uint64, _u32p, _u32p, _i32p, C.c_int32, _u8p, _u8p, C.c_int32]
+    lib.gsfm_ra_init_orientations_mst.argtypes = [C.c_uint32, C.c_uint64, _u32p, _u32p, _dp, _i32p, C.c_int64, _dp, _u8p, _i32p, C.c_int32]
     return lib
 
 
@@ -223,6 +226,7 @@ EXPORTED_SYMBOLS = [
     "gsfm_ra_solver_iterate", "gsfm_ra_comm_unique_id", "gsfm_ra_solver_comm_init",
     "gsfm_ra_solver_ipc_export", "gsfm_ra_solver_ipc_import", "gsfm_ra_solver_edge_range", "gsfm_ra_solver_cuda_stream", "gsfm_ra_solver_time_kernels", "gsfm_ra_eval_edges", "gsfm_ra_whiten", "gsfm_ra_assemble", "gsfm_ra_cost",
     "gsfm_ra_spmv", "gsfm_ra_pcg", "gsfm_ra_eval_loss", "gsfm_ra_filter_view_pairs", "gsfm_ra_residual_dim",
+    "gsfm_ra_filter_initial_view_graph", "gsfm_ra_init_orientations_mst",
 ]
 
 _lib = None

@@ -371,6 +371,14 @@ class ReconstructionBuilder:
         return self.reconstruction_
 
 
+def _on_device():
+    """True when a CUDA device is present: the view-graph shaping then runs there as well (the solve always does)."""
+    try:
+        return _capi.lib().gsfm_ra_device_count() > 0
+    except Exception:
+        return False
+
+
 class GlobalReconstructionEstimator:
     """The steppable estimator (src/GSfM_global_reconstruction_estimator.cpp), steps 1-3 and the rotation filter."""
 
@@ -399,8 +407,13 @@ class GlobalReconstructionEstimator:
             return False
         ij = np.array(keys, dtype=np.int64)
         nvm = np.array([edges[k].num_verified_matches for k in keys])
-        keep, ids = _vg.filter_initial_view_graph(np.array(sorted(view_graph.ViewIds())), ij, nvm,
-                                                  self.options.min_num_two_view_inliers)
+        all_ids = np.unique(np.concatenate([np.array(sorted(view_graph.ViewIds()), dtype=np.int64), ij.ravel()]))
+        if _on_device():   # edge filter + largest connected component on the device (gsfm_ra_filter_initial_view_graph)
+            dense = np.searchsorted(all_ids, ij)
+            keep, vkeep = _solver.filter_initial_view_graph(len(all_ids), dense[:, 0], dense[:, 1], nvm, self.options.min_num_two_view_inliers)
+            ids = all_ids[vkeep]
+        else:              # no CUDA device (CPU test-suite): the host restatement
+            keep, ids = _vg.filter_initial_view_graph(all_ids, ij, nvm, self.options.min_num_two_view_inliers)
         for k, kp in zip(keys, keep.tolist()):
             if not kp:
                 view_graph.RemoveEdge(*k)
@@ -417,7 +430,10 @@ class GlobalReconstructionEstimator:
         ij = np.searchsorted(ids, np.array(keys, dtype=np.int64))
         w = np.array([edges[k].num_verified_matches for k in keys])
         rot = np.array([edges[k].rotation_2 for k in keys])
-        om = _vg.max_spanning_tree_orientations(len(ids), ij[:, 0], ij[:, 1], rot, w)
+        if _on_device():   # Boruvka + tree propagation on the device (gsfm_ra_init_orientations_mst)
+            om = _solver.init_orientations_mst(len(ids), ij[:, 0], ij[:, 1], rot, w)[0]
+        else:
+            om = _vg.max_spanning_tree_orientations(len(ids), ij[:, 0], ij[:, 1], rot, w)
         for k, v in enumerate(ids.tolist()):
             if not np.isnan(om[k, 0]):
                 self.orientations[int(v)] = om[k].copy()

@@ -3108,3 +3108,5 @@ int gsfm_ra_filter_view_pairs(const gsfm_ra_problem* problem, const double* omeg
 }
 
 }  // extern "C"
+
+#include "gsfm_graph.cuh"

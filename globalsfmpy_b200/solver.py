@@ -92,6 +92,37 @@ def filter_view_pairs(prob, omega, max_degrees, device=-1):
     return keep.astype(bool), ang
 
 
+def filter_initial_view_graph(num_views, edge_i, edge_j, num_verified_matches, min_num_two_view_inliers=30, device=-1):
+    """FilterInitialViewGraph + largest connected component on the device (dense view indices).
+    Reference: src/GSfM_global_reconstruction_estimator.cpp:369-390.  Returns (edge_keep, view_keep) boolean masks."""
+    ei = np.ascontiguousarray(edge_i, dtype=np.uint32)
+    ej = np.ascontiguousarray(edge_j, dtype=np.uint32)
+    m = np.ascontiguousarray(num_verified_matches, dtype=np.int32)
+    ek = np.zeros(len(ei), np.uint8)
+    vk = np.zeros(int(num_views), np.uint8)
+    capi.check(capi.lib().gsfm_ra_filter_initial_view_graph(int(num_views), len(ei), capi.ptr(ei, C.c_uint32), capi.ptr(ej, C.c_uint32),
+                                                            capi.ptr(m, C.c_int32), int(min_num_two_view_inliers),
+                                                            capi.ptr(ek, C.c_uint8), capi.ptr(vk, C.c_uint8), device))
+    return ek.astype(bool), vk.astype(bool)
+
+
+def init_orientations_mst(num_views, edge_i, edge_j, omega_ij, weights, root=None, device=-1):
+    """OrientationsFromMaximumSpanningTree on the device (Boruvka + level-synchronous propagation).
+    Reference: T/sfm/view_graph/orientations_from_maximum_spanning_tree.cc:109-178.
+    Returns (omega [N,3] with NaN for unreachable views, tree-edge mask, Boruvka rounds)."""
+    ei = np.ascontiguousarray(edge_i, dtype=np.uint32)
+    ej = np.ascontiguousarray(edge_j, dtype=np.uint32)
+    w = np.ascontiguousarray(weights, dtype=np.int32)
+    wij = np.ascontiguousarray(omega_ij, dtype=np.float64).reshape(-1, 3)
+    om = np.zeros((int(num_views), 3))
+    tree = np.zeros(len(ei), np.uint8)
+    rounds = C.c_int32(0)
+    capi.check(capi.lib().gsfm_ra_init_orientations_mst(int(num_views), len(ei), capi.ptr(ei, C.c_uint32), capi.ptr(ej, C.c_uint32),
+                                                        capi.ptr(wij), capi.ptr(w, C.c_int32), -1 if root is None else int(root),
+                                                        capi.ptr(om), capi.ptr(tree, C.c_uint8), C.byref(rounds), device))
+    return om, tree.astype(bool), rounds.value
+
+
 def _summary(trace_capacity):
     s = capi.Summary()
     trace = (capi.Iteration * max(1, trace_capacity))()

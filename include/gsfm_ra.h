@@ -298,6 +298,28 @@ int gsfm_ra_filter_view_pairs(const gsfm_ra_problem* problem, const double* omeg
                               double max_relative_rotation_difference_degrees,
                               uint8_t* keep, double* angle_rad /*may be NULL*/, int32_t device);
 
+/* ---- view-graph shaping on the device: the steps immediately before the solve ----------------- */
+
+/* FilterInitialViewGraph (reference src/GSfM_global_reconstruction_estimator.cpp:369-390): drop view pairs with
+ * num_verified_matches < min_num_two_view_inliers, then keep the largest connected component
+ * (RemoveDisconnectedViewPairs, thirdparty/TheiaSfM/src/theia/sfm/view_graph/remove_disconnected_view_pairs.cc:48-;
+ * ties between equally large components: the one holding the smallest view index).  Views are dense indices
+ * 0..num_views-1.  edge_keep[E] / view_keep[num_views] receive 0/1. */
+int gsfm_ra_filter_initial_view_graph(uint32_t num_views, uint64_t num_edges, const uint32_t* edge_i, const uint32_t* edge_j,
+                                      const int32_t* num_verified_matches, int32_t min_num_two_view_inliers, uint8_t* edge_keep,
+                                      uint8_t* view_keep, int32_t device);
+
+/* OrientationsFromMaximumSpanningTree
+ * (thirdparty/TheiaSfM/src/theia/sfm/view_graph/orientations_from_maximum_spanning_tree.cc:109-178): maximum spanning
+ * tree over edge_weight (the reference: num_verified_matches; Kruskal, theia/math/graph/minimum_spanning_tree.h:70-98;
+ * ties broken by (edge_i, edge_j) so that the tree is unique), then R_neighbor = (src < nbr ? R_rel : R_rel^T) R_src
+ * from the root (:60-83).  root < 0: the smallest view index that has an edge.  omega_out[3 * num_views]: angle-axis,
+ * NaN for views the root cannot reach.  edge_in_tree (E, optional) flags the tree edges, rounds_out (optional) the
+ * number of Boruvka rounds. */
+int gsfm_ra_init_orientations_mst(uint32_t num_views, uint64_t num_edges, const uint32_t* edge_i, const uint32_t* edge_j,
+                                  const double* omega_ij, const int32_t* edge_weight, int64_t root, double* omega_out,
+                                  uint8_t* edge_in_tree, int32_t* rounds_out, int32_t device);
+
 #ifdef __cplusplus
 }
 #endif
