@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <string>
+#include <type_traits>
 #include <unordered_map>
 #include <utility>
 #include <vector>
@@ -210,6 +211,71 @@ class GSfMNonlinearRotationEstimator : public RotationEstimator<ViewPairs, Orien
   gsfm_ra_summary summary_{};
   std::string error_;
 };
+
+// ---- the step before the solve -------------------------------------------------------------------------------------
+// theia::OrientationsFromMaximumSpanningTree(const ViewGraph&, unordered_map<ViewId, Vector3d>*)
+//   T/sfm/view_graph/orientations_from_maximum_spanning_tree.cc:109-178 -- here over the same view-pair map the
+//   estimators take (Info::num_verified_matches is the tree weight, Info::rotation_2 the relative rotation of the pair
+//   (smaller id, larger id)), on the device through gsfm_ra_init_orientations_mst.  Fills `orientations` with the views
+//   the root's component reaches (root: the smallest view id that has a pair); returns false on empty input or a failed
+//   device call (message in *error when given).
+template <class ViewPairs, class Orientations>
+bool OrientationsFromMaximumSpanningTree(const ViewPairs& view_pairs, Orientations* orientations, std::string* error = nullptr) {
+  using Id = typename Orientations::key_type;
+  if (!orientations || view_pairs.size() == 0) return false;
+  std::vector<Id> ids;
+  for (const auto& vp : view_pairs) { ids.push_back(vp.first.first); ids.push_back(vp.first.second); }
+  std::sort(ids.begin(), ids.end());
+  ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+  auto dense = [&](const Id& v) { return (uint32_t)(std::lower_bound(ids.begin(), ids.end(), v) - ids.begin()); };
+  std::vector<uint32_t> ei, ej;
+  std::vector<int32_t> w;
+  std::vector<double> wij;
+  for (const auto& vp : view_pairs) {
+    ei.push_back(dense(vp.first.first)); ej.push_back(dense(vp.first.second));
+    w.push_back((int32_t)vp.second.num_verified_matches);
+    for (int t = 0; t < 3; ++t) wij.push_back(vp.second.rotation_2[t]);
+  }
+  std::vector<double> omega(3 * ids.size());
+  const int rc = gsfm_ra_init_orientations_mst((uint32_t)ids.size(), ei.size(), ei.data(), ej.data(), wij.data(), w.data(), -1, omega.data(),
+                                               nullptr, nullptr, -1);
+  if (rc != 0) { if (error) *error = gsfm_ra_last_error(); return false; }
+  for (uint32_t k = 0; k < ids.size(); ++k) {
+    if (omega[3 * k] != omega[3 * k]) continue;  // NaN: not reachable from the root
+    auto& v = (*orientations)[ids[k]];
+    for (int t = 0; t < 3; ++t) v[t] = omega[3 * k + t];
+  }
+  return true;
+}
+
+// GSfMGlobalReconstructionEstimator::FilterInitialViewGraph  src/GSfM_global_reconstruction_estimator.cpp:369-390:
+// erases the view pairs with fewer than min_num_two_view_inliers verified matches and everything outside the largest
+// connected component (gsfm_ra_filter_initial_view_graph).  Returns false when no pair survives or the device call fails.
+template <class ViewPairs>
+bool FilterInitialViewGraph(ViewPairs* view_pairs, int min_num_two_view_inliers, std::string* error = nullptr) {
+  if (!view_pairs || view_pairs->size() == 0) return false;
+  using Id = typename std::decay<decltype(view_pairs->begin()->first.first)>::type;
+  std::vector<Id> ids;
+  for (const auto& vp : *view_pairs) { ids.push_back(vp.first.first); ids.push_back(vp.first.second); }
+  std::sort(ids.begin(), ids.end());
+  ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+  auto dense = [&](const Id& v) { return (uint32_t)(std::lower_bound(ids.begin(), ids.end(), v) - ids.begin()); };
+  std::vector<uint32_t> ei, ej;
+  std::vector<int32_t> m;
+  std::vector<typename ViewPairs::key_type> keys;
+  for (const auto& vp : *view_pairs) {
+    keys.push_back(vp.first);
+    ei.push_back(dense(vp.first.first)); ej.push_back(dense(vp.first.second));
+    m.push_back((int32_t)vp.second.num_verified_matches);
+  }
+  std::vector<uint8_t> ekeep(ei.size()), vkeep(ids.size());
+  const int rc = gsfm_ra_filter_initial_view_graph((uint32_t)ids.size(), ei.size(), ei.data(), ej.data(), m.data(), min_num_two_view_inliers,
+                                                   ekeep.data(), vkeep.data(), -1);
+  if (rc != 0) { if (error) *error = gsfm_ra_last_error(); return false; }
+  for (size_t k = 0; k < keys.size(); ++k)
+    if (!ekeep[k]) view_pairs->erase(keys[k]);
+  return view_pairs->size() >= 1;
+}
 
 }  // namespace gsfm_b200
 

@@ -169,6 +169,23 @@ int main(int argc, char** argv) {
     Check(est.EstimateRotationsWithSigmaConsensus(pairs, &o, gsfm_b200::TrivialLoss(), 1, 5, 0.05), "EstimateRotationsWithSigmaConsensus");
     Check(MeanError(o, gt, n) < 0.5 * M_PI / 180.0 && est.summary().outer_iterations >= 1, "  converges below 0.5 deg");
   }
+  {  // the steps before the solve, on the device: initial view-graph filter and spanning-tree initialisation
+    ViewPairs vp = pairs;
+    vp[{(ViewId)0, (ViewId)1}].num_verified_matches = 5;        // below the threshold: removed (the ring keeps 0 and 1 connected)
+    TwoViewInfo island; island.num_verified_matches = 100;       // a two-view island: not the largest component
+    vp[{(ViewId)1000, (ViewId)1001}] = island;
+    std::string err;
+    Check(gsfm_b200::FilterInitialViewGraph(&vp, 30, &err), "FilterInitialViewGraph");
+    Check(vp.count({0, 1}) == 0 && vp.count({1000, 1001}) == 0 && vp.size() == pairs.size() - 1, "  weak pair and island removed, the rest kept");
+    Orientations o;
+    Check(gsfm_b200::OrientationsFromMaximumSpanningTree(vp, &o, &err), "OrientationsFromMaximumSpanningTree");
+    Check(o.size() == (size_t)n, "  every view of the component gets an orientation");
+    // the relative rotations carry 1 degree of noise: a tree path of a few edges stays within a few degrees of the truth
+    const double e = MeanError(o, gt, n);
+    std::printf("      spanning-tree initialisation: mean error vs ground truth %.3f deg\n", e * 180 / M_PI);
+    Check(e < 10.0 * M_PI / 180.0, "  initialisation is consistent with the measurements");
+    Check(base->EstimateRotations(vp, &o) && MeanError(o, gt, n) < 0.5 * M_PI / 180.0, "  and the solve converges from it");
+  }
   std::printf("%s\n", g_failed ? "FAILED" : "ALL OK");
   return g_failed ? 1 : 0;
 }
