@@ -142,7 +142,7 @@ def test_reference_loss_classes_are_recognised(sfm):
 def test_pipeline_call_sequence_on_madrid(sfm, golden_dir, madrid):
     """scripts/sfm_pipeline.py:31-70 with onlyRotationAvg=True, same calls in the same order, through the module;
     must equal the direct C-ABI solve on the same inputs bit for bit."""
-    from globalsfmpy_b200 import _capi as capi, solver, loss_functions as lf
+    from globalsfmpy_b200 import _capi as capi, solver, loss_functions as lf, viewgraph as vg
     recon, graph, covs = _graph_from_fixture(sfm, golden_dir)
     options = sfm.ReconstructionBuilderOptions()
     builder = sfm.ReconstructionBuilder(options, recon, graph)
@@ -151,6 +151,11 @@ def test_pipeline_call_sequence_on_madrid(sfm, golden_dir, madrid):
     est = sfm.GlobalReconstructionEstimator(options.reconstruction_estimator_options)
     est.FilterInitialViewGraphAndCalibrateCameras(view_graph, reconstruction)
     loss = lf.MAGSACWeightBasedLoss(0.02)
+    # the spanning-tree initialisation runs on the device (gsfm_ra_init_orientations_mst): same tree as the fixture's host
+    # Kruskal, orientations equal to rounding (quaternion chain vs matrix chain)
+    est.OrientationsFromMaximumSpanningTree()
+    init_dev = np.array([est.orientations[int(v)] for v in madrid.view_ids])
+    assert np.abs(vg.so3_exp(init_dev) - vg.so3_exp(madrid.omega_init)).max() < 1e-12
     assert est.EstimateGlobalRotationsUncertainty(loss, covs, sfm.RotationErrorType.ANGLE_AXIS_COVARIANCE)
     sfm.SetOrientations(est.orientations, reconstruction)
     got = np.array([reconstruction.View(int(v)).GetOrientationAsAngleAxis() for v in madrid.view_ids])
@@ -159,7 +164,7 @@ def test_pipeline_call_sequence_on_madrid(sfm, golden_dir, madrid):
     o = capi.default_options_py()
     o.loss = capi.Loss.make(capi.LOSS_MAGSAC3, 0.02)
     # the module hands the edges over in hash-map order; the solver sorts half-edges itself, so the result is the same
-    ref, s, _ = solver.solve(prob, o, madrid.omega_init)
+    ref, s, _ = solver.solve(prob, o, init_dev)
     assert np.array_equal(got, ref)
     # step 4 of the pipeline: the rotation filter (15 degrees in flags_1dsfm.yaml) on the device
     est.options.rotation_filtering_max_difference_degrees = 15.0
