@@ -142,8 +142,9 @@ def measured_peak_gbs():
 
 
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per CG step of k_pcg_persistent from the committed ncu --set full
-# capture of this workload (profiles/r01_h_ncu_full_summary.txt: a launch of 50 CG steps); None for workloads never captured
-NCU_TRAFFIC_PER_PASS = {}
+# capture of this workload (profiles/r01_i_ncu_full_summary.txt: a launch of exactly 50 CG steps read 4.393 GB and wrote
+# 68.5 MB); None for workloads never captured
+NCU_TRAFFIC_PER_PASS = {("syn_10k_1M", 1): (4.393041e9 + 68.521984e6) / 50}
 
 
 def spmv_algorithmic_bytes(N, E):
