@@ -2329,14 +2329,20 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   // ---- balanced partitions, one per kernel class, sized to exactly one resident wave of that kernel ----
   const int occ_k2 = di->occ_k2[s->blk == 6 ? 0 : 1];
   s->cooperative = di->coop != 0 && occ_k2 > 0;
+  // Edge-sharded: the range length and the launch grid are sized from the LARGEST shard (ceil(E_total / world) edges), so
+  // every rank launches the same grid even when the shards differ by an edge -- the replicated grid-wide sums then add in
+  // the same order on every rank and the replicas stay bit-identical.  (A rank with fewer half-edges leaves its last
+  // warps idle.)
+  const uint64_t H_sizing = 2 * ((prob->num_edges + (uint64_t)world - 1) / (uint64_t)world);
   auto make = [&](Partition& P, int blocks_per_sm) -> int {
     const uint64_t max_warps = (uint64_t)s->sm_count * std::max(1, blocks_per_sm) * kWarpsPerBlock;
-    uint64_t per = (H + max_warps - 1) / max_warps;
+    uint64_t per = (H_sizing + max_warps - 1) / max_warps;
     per = std::max<uint64_t>(64, (per + 31) / 32 * 32);  // at least 64 half-edges per warp, whole records
     const uint32_t nw = (uint32_t)std::max<uint64_t>(1, (H + per - 1) / per);
+    const uint32_t nw_sizing = (uint32_t)std::max<uint64_t>(1, (H_sizing + per - 1) / per);
     P.num_warps = nw; P.span = (uint32_t)per;
     P.num_segs = nw + N;  // upper bound: every range start + every row start opens one segment
-    P.grid = (nw + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    P.grid = (nw_sizing + kWarpsPerBlock - 1) / kWarpsPerBlock;
     DevBuf<uint32_t> nseg, cnt;
     RA_TRY(nseg.alloc(nw + 2)); RA_TRY(cnt.alloc(N + 2));
     RA_TRY(P.warp_seg_ptr.alloc(nw + 2)); RA_TRY(P.seg_row.alloc(P.num_segs)); RA_TRY(P.seg_begin.alloc(P.num_segs));

@@ -24,6 +24,9 @@ def main():
          capi.Loss.make(capi.LOSS_CAUCHY, 0.05)),
         ("cov_softl1", dict(num_views=150, num_edges=3000, seed=5, outlier_fraction=0.05, covariance=True), capi.ANGLE_AXIS_COVARIANCE,
          capi.Loss.make(capi.LOSS_SOFTLONE, 1.0)),
+        # an edge count no world size divides: the shards differ by one edge, the replicas must still be bit-identical
+        ("aa_uneven", dict(num_views=300, num_edges=7001, seed=11, noise_deg=1.0, outlier_fraction=0.05), capi.ANGLE_AXIS,
+         capi.Loss.make(capi.LOSS_CAUCHY, 0.05)),
     ]
     # both exchange modes: fused (peer memory inside the persistent PCG kernel) and ncclAllReduce between kernels
     for (name, kw, etype, loss), fused in [(c, f) for c in cases for f in (True, False)]:
