@@ -367,6 +367,29 @@ __device__ __forceinline__ void tma_load_bulk(void* smem_dst, const void* gsrc, 
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void tma_load_bulk_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+
+// L2 residency of the matrix stream (K2): a PCG solve reads the same records once per CG step.  When the stream is somewhat
+// larger than the L2 (104 MB vs 126 MB of L2 shared with everything else at 1M edges) plain LRU keeps almost nothing of a
+// cyclic sweep; loading `keep8` of every 8 records with an evict_last policy and the rest with evict_first pins a fixed
+// fraction of the matrix from one pass to the next and only the remainder streams from HBM (measured at 1M edges,
+// profiles/r01_j_l2_keep.txt: K2 alone 25.9 -> 22.6 us, CG step 33.3 -> 31.9 us with 6 of 8).  keep8 = 0 (streams far larger
+// than the L2, or small enough for LRU to hold them): no hints.  The host picks it from the device's L2 size.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 
 struct WarpPipe {
   double* ring;    // this warp's kStages records in shared memory
@@ -744,17 +767,24 @@ __global__ void k_prepare_solve(uint32_t N, PrepareArgs A, double* slots, unsign
 template <int kBlk, typename Finish>
 __device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restrict__ recs, uint64_t lo, uint64_t hi, uint32_t t0, uint32_t t1,
                                             const uint32_t* __restrict__ seg_begin, const uint32_t* __restrict__ seg_len, const double* x4,
-                                            bool nogather, Finish&& finish) {
+                                            bool nogather, uint32_t keep8, Finish&& finish) {
   constexpr int kRD = Rec<kBlk>::kDoubles;
   const int lane = threadIdx.x & 31;
   const uint32_t nrec = (uint32_t)((hi - lo + 31) >> 5);
   const uint32_t base = wp.pos;
   const double* src = recs + (size_t)(lo >> 5) * kRD;
+  uint64_t pol_keep = 0, pol_stream = 0;
+  if (keep8) { pol_keep = l2_policy_evict_last(); pol_stream = l2_policy_evict_first(); }
+  const uint32_t rec0 = (uint32_t)(lo >> 5);
   auto issue = [&](uint32_t c) {
     if (lane == 0) {
       const uint32_t st = (base + c) % kStages;
       mbar_expect_tx(&wp.bars[st], Rec<kBlk>::kBytes);
-      tma_load_bulk(wp.ring + (size_t)st * kRD, src + (size_t)c * kRD, Rec<kBlk>::kBytes, &wp.bars[st]);
+      if (keep8)
+        tma_load_bulk_hint(wp.ring + (size_t)st * kRD, src + (size_t)c * kRD, Rec<kBlk>::kBytes, &wp.bars[st],
+                           ((rec0 + c) & 7u) < keep8 ? pol_keep : pol_stream);
+      else
+        tma_load_bulk(wp.ring + (size_t)st * kRD, src + (size_t)c * kRD, Rec<kBlk>::kBytes, &wp.bars[st]);
     }
   };
   auto wait_rec = [&](uint32_t c) -> const double* {
@@ -817,7 +847,7 @@ template <int kBlk>
 __global__ void __launch_bounds__(kBlock)
 k_spmv(uint32_t num_warps, uint64_t H, uint32_t warp_span, const uint32_t* __restrict__ warp_seg_ptr, const uint32_t* __restrict__ task_begin,
        const uint32_t* __restrict__ task_len, const double* __restrict__ recs, const double* __restrict__ x4, double* __restrict__ ypart,
-       const DevScalars* sc, int check_done) {
+       const DevScalars* sc, int check_done, uint32_t keep8) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   if (check_done == 1 && sc->pcg_done) return;
   const int lane = threadIdx.x & 31;
@@ -826,7 +856,7 @@ k_spmv(uint32_t num_warps, uint64_t H, uint32_t warp_span, const uint32_t* __res
   WarpPipe wp;
   pipe_init<kBlk>(wp, smem_raw);
   const uint64_t lo = (uint64_t)gw * warp_span, hi = min(H, lo + warp_span);
-  spmv_stream<kBlk>(wp, recs, lo, hi, warp_seg_ptr[gw], warp_seg_ptr[gw + 1], task_begin, task_len, x4, check_done == 2,
+  spmv_stream<kBlk>(wp, recs, lo, hi, warp_seg_ptr[gw], warp_seg_ptr[gw + 1], task_begin, task_len, x4, check_done == 2, keep8,
                     [&](uint32_t t, double y0, double y1, double y2) {
                       if (lane == 0) { ypart[3 * (size_t)t] = y0; ypart[3 * (size_t)t + 1] = y1; ypart[3 * (size_t)t + 2] = y2; }
                     });
@@ -997,6 +1027,7 @@ constexpr int kMaxPeers = 16;
 
 struct PcgParams {
   uint32_t N, num_warps, n_iso, warp_span;
+  uint32_t keep8;  // records of every 8 loaded with the evict_last L2 policy (0: no cache hints)
   int max_iter;
   uint64_t H;
   double rtol2;
@@ -1112,7 +1143,7 @@ __device__ __forceinline__ void spmv_pass(const PcgParams& P, WarpPipe& wp, doub
       nbatch = 0;
       __syncwarp();
     };
-    spmv_stream<kBlk>(wp, P.val, lo, hi, t0, t1, P.seg_begin, P.seg_len, P.z, false, [&](uint32_t t, double y0, double y1, double y2) {
+    spmv_stream<kBlk>(wp, P.val, lo, hi, t0, t1, P.seg_begin, P.seg_len, P.z, false, P.keep8, [&](uint32_t t, double y0, double y1, double y2) {
       const uint32_t rowf = P.seg_row[t];
       if (rowf & kSideBit) {  // continuation of a row owned by an earlier warp
         if (lane == 0) {
@@ -1796,6 +1827,7 @@ struct StreamHolder {
 struct DeviceInfo {
   bool ready = false;
   int sm_count = 0, coop = 0, occ_k2[2] = {1, 1};  // occ_k2[0]: 6-double records, [1]: 9-double records
+  int l2_bytes = 0;
 };
 DeviceInfo g_device_info[64];
 
@@ -1920,6 +1952,7 @@ struct gsfm_ra_solver {
   DevBuf<double> slots;
   DevBuf<unsigned long long> bar_slots;  // grid barrier + reduction slots of the persistent PCG kernel (see grid_bar_sum2)
   bool fused_step = false;               // set while a trust-region batch is enqueued: PCG kernel runs prologue + epilogue
+  uint32_t keep8 = 0;                    // L2 residency of the matrix stream, see l2_policy_evict_last
   DevBuf<unsigned> counter, row_cnt;
   DevBuf<DevScalars> sc;
   DevScalars* h_sc = nullptr;  // pinned
@@ -2038,10 +2071,10 @@ struct gsfm_ra_solver {
   void launch_spmv(int b, const double* x4, int check_done) {
     if (blk == 6)
       k_spmv<6><<<pk2.grid, kBlock, smem_bytes(), stream>>>(pk2.num_warps, H, pk2.span, pk2.warp_seg_ptr.p, pk2.seg_begin.p, pk2.seg_len.p, val[b].p,
-                                                            x4, ypart.p, sc.p, check_done);
+                                                            x4, ypart.p, sc.p, check_done, keep8);
     else
       k_spmv<9><<<pk2.grid, kBlock, smem_bytes(), stream>>>(pk2.num_warps, H, pk2.span, pk2.warp_seg_ptr.p, pk2.seg_begin.p, pk2.seg_len.p, val[b].p,
-                                                            x4, ypart.p, sc.p, check_done);
+                                                            x4, ypart.p, sc.p, check_done, keep8);
   }
 
   // ---- evaluation at omega[b]: node prep, K1 (or K1c), node finalize -------------------------
@@ -2106,6 +2139,7 @@ struct gsfm_ra_solver {
   PcgParams pcg_params(int b, double rtol, int max_iter) {
     PcgParams P;
     P.N = N; P.num_warps = pk2.num_warps; P.n_iso = n_iso; P.max_iter = max_iter; P.H = H; P.rtol2 = rtol * rtol;
+    P.keep8 = keep8;
     P.warp_seg_ptr = pk2.warp_seg_ptr.p; P.seg_row = pk2.seg_row.p; P.seg_begin = pk2.seg_begin.p; P.seg_len = pk2.seg_len.p;
     P.node_seg_ptr = pk2.node_seg_ptr.p; P.iso = iso.p; P.warp_span = pk2.span;
     P.val = val[b].p; P.Dblk = Dblk.p; P.Minv = Minv.p;
@@ -2213,6 +2247,7 @@ int device_info(int device, DeviceInfo** out) {
   if (!d.ready) {
     CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaDeviceGetAttribute(&d.coop, cudaDevAttrCooperativeLaunch, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&d.l2_bytes, cudaDevAttrL2CacheSize, device));
     CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(6)));
     CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(9)));
     CUDA_TRY(cudaFuncSetAttribute(k_spmv<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(6)));
@@ -2366,6 +2401,15 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   RA_TRY(make(s->pk2, occ_k2));
   // the cooperative grid must be fully resident; node loops are grid-strided so any size works
   s->pk2.grid = std::min<uint32_t>(s->pk2.grid, (uint32_t)s->sm_count * std::max(1, occ_k2));
+  {
+    // L2 residency of the matrix stream: pin what 62 % of the L2 can hold when the stream is larger than that but still
+    // comparable to the L2 (GSFM_RA_L2_KEEP=0..7 overrides, 0 disables)
+    const double stream = (double)((H + 31) / 32) * s->rec_doubles() * 8.0, budget = 0.62 * (double)di->l2_bytes;
+    uint32_t k = 0;
+    if (stream > budget) k = (uint32_t)std::min(7.0, std::floor(8.0 * budget / stream));
+    if (const char* e = std::getenv("GSFM_RA_L2_KEEP")) k = (uint32_t)std::min(7, std::max(0, std::atoi(e)));
+    s->keep8 = k;
+  }
   lap("enqueue structure build");
 
   // ---- per half-edge constants (K0) and the solver's working set ---------------------------------
