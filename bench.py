@@ -142,9 +142,10 @@ def measured_peak_gbs():
 
 
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per CG step of k_pcg_persistent from the committed ncu --set full
-# capture of this workload (profiles/r01_i_ncu_full_summary.txt: a launch of exactly 50 CG steps read 4.393 GB and wrote
-# 68.5 MB); None for workloads never captured
-NCU_TRAFFIC_PER_PASS = {("syn_10k_1M", 1): (4.393041e9 + 68.521984e6) / 50}
+# capture of this workload (profiles/r01_j_ncu_full_summary.txt: a launch of exactly 50 CG steps read 1.487 GB and wrote
+# 18.9 MB -- with the L2 residency hints three quarters of the 104 MB stream are served by the L2, lts hit rate 71 %; the
+# build before the hints moved 89.2 MB per step); None for workloads never captured
+NCU_TRAFFIC_PER_PASS = {("syn_10k_1M", 1): (1.487013e9 + 18.917120e6) / 50}
 
 
 def spmv_algorithmic_bytes(N, E):
@@ -388,7 +389,8 @@ def main():
                 "stored_bytes_per_pass": 52 * 2 * E_local,
                 "note": "algorithmic bytes are SURVEY 8(d)'s symmetric-half figure 76(N+E)+4(N+1)+48N; this build stores both triangles "
                         "(deterministic gather-only SpMV) as symmetric 6-double blocks, 52 B per half-edge = 104 B per edge, so 0.73 is "
-                        "the ceiling of this layout",
+                        "the ceiling of this layout on an HBM-bound pass; with the L2 residency hints most of the stream is served by the "
+                        "L2 (see traffic) and the pass is bounded by the x[col] gather + L2 delivery, the CG step by its two grid barriers",
                 "k2_alone": {"kernel": "k_spmv", "ms_per_launch": kt["spmv"], "achieved": b_spmv / (kt["spmv"] * 1e-3) / 1e9,
                              "frac": b_spmv / (kt["spmv"] * 1e-3) / 1e9 / peak,
                              "stored_bytes_GBps": 52 * 2 * E_local / (kt["spmv"] * 1e-3) / 1e9},
