@@ -431,10 +431,8 @@ struct K1Args {
 };
 
 template <bool kWriteBlocks, int kResidual, bool kScalarU, int kLoss>
-#ifndef GSFM_K1_MINBLOCKS
-#define GSFM_K1_MINBLOCKS 2
-#endif
-__global__ void __launch_bounds__(kBlock, GSFM_K1_MINBLOCKS) k_edges(const K1Args A) {
+// two blocks (16 warps) per SM: three (<= 80 registers) spill and measure 10 % slower (profiles/r01_g_microbench.txt item 5)
+__global__ void __launch_bounds__(kBlock, 2) k_edges(const K1Args A) {
   constexpr int kU = (kScalarU || kResidual == 1) ? 1 : 6;
   constexpr int kRD = (4 + kU) * 32 + 32;  // doubles per input record
   constexpr int kRB = kRD * 8;

@@ -320,11 +320,7 @@ __host__ __device__ inline double triggs_kappa(double s, const double* rho) {
 template <bool kNeedJacobian, int kResidual = 0, bool kScalarU = false, int kLoss = -1, bool kStencilOnly = false>
 __host__ __device__ inline void edge_terms(const Q4& qi, const Q4& qj, const Q4& qij, const double* U, const DevLoss& L, EdgeTerms& o) {
   const Q4 qE = qmul(qmul(qj, qconj(qi)), qconj(qij));  // error rotation R_j R_i^T R_ij^T
-  #ifndef GSFM_NO_STENCIL_FAST
   if (kNeedJacobian && kStencilOnly && kScalarU && kResidual == 0) {
-#else
-  if (false) {
-#endif
     double e[3], theta2, c;
     quat_log(qE, e, &theta2, &c);
     const double w = U[0], w2 = w * w;
