@@ -408,8 +408,9 @@ def main():
             "config": {"workload": name, "views": g.num_views, "edges": g.num_edges, "edges_per_gpu": E_local,
                        "loss": WORKLOADS[name]["loss"], "error_type": WORKLOADS[name]["etype"], "outlier_fraction": 0.1,
                        "pcg_rtol": opt.pcg_rtol, "parallelism": f"edge-sharded x{world}" if world > 1 else "single GPU",
-                       "l2": "no explicit flush: one step streams the half-edge arrays + block matrix (>= 450 MB at 1M edges), "
-                             "larger than the 126 MB L2"},
+                       "l2": "no explicit flush: one step touches K1's input records, the candidate's block matrix and one sweep of "
+                             "the current matrix per CG step (~0.8 GB at 1M edges), far more than the 126 MB L2; inside a step the CG "
+                             "sweeps deliberately re-use the part of the matrix the L2 hints keep resident (roofline.traffic)"},
             "clocks": clocks, "gpu_launches": int(launches), "wall_ms_per_step": 1e3 * t_wall / args.steps,
             "roofline": roofline}
 
