@@ -290,8 +290,7 @@ def main():
     name = args.workload
 
     import __graft_entry__ as ge
-    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
-        ge.build()
+    ge.build()   # every rank: serialised by a file lock, a no-op when the library is fresh
 
     if args.impl == "reference":
         run_reference(args, name)
