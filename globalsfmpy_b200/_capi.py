@@ -215,6 +215,13 @@ def declare(lib, oracle=False):
     _i32p = C.POINTER(C.c_int32)
     lib.gsfm_ra_filter_initial_view_graph.argtypes = [C.c_uint32, C.c_uint64, _u32p, _u32p, _i32p, C.c_int32, _u8p, _u8p, C.c_int32]
     lib.gsfm_ra_init_orientations_mst.argtypes = [C.c_uint32, C.c_uint64, _u32p, _u32p, _dp, _i32p, C.c_int64, _dp, _u8p, _i32p, C.c_int32]
+    PP = C.POINTER
+    lib.gsfm_ra_free.argtypes = [C.c_void_p]
+    lib.gsfm_ra_free.restype = None
+    lib.gsfm_ra_read_covariance_rot.argtypes = [C.c_char_p, PP(C.c_uint64), PP(_u32p), PP(_u32p), PP(_dp), PP(_dp)]
+    lib.gsfm_ra_write_covariance_rot.argtypes = [C.c_char_p, C.c_uint64, _u32p, _u32p, _dp, _dp]
+    lib.gsfm_ra_read_1dsfm.argtypes = [C.c_char_p, PP(C.c_uint32), PP(C.c_uint64), PP(_u32p), PP(_dp), PP(C.c_uint64), PP(_u32p), PP(_u32p),
+                                       PP(_dp), PP(_dp), PP(_i32p)]
     return lib
 
 
@@ -227,6 +234,7 @@ EXPORTED_SYMBOLS = [
     "gsfm_ra_solver_ipc_export", "gsfm_ra_solver_ipc_import", "gsfm_ra_solver_edge_range", "gsfm_ra_solver_cuda_stream", "gsfm_ra_solver_time_kernels", "gsfm_ra_eval_edges", "gsfm_ra_whiten", "gsfm_ra_assemble", "gsfm_ra_cost",
     "gsfm_ra_spmv", "gsfm_ra_pcg", "gsfm_ra_eval_loss", "gsfm_ra_filter_view_pairs", "gsfm_ra_residual_dim",
     "gsfm_ra_filter_initial_view_graph", "gsfm_ra_init_orientations_mst",
+    "gsfm_ra_free", "gsfm_ra_read_covariance_rot", "gsfm_ra_write_covariance_rot", "gsfm_ra_read_1dsfm",
 ]
 
 _lib = None

@@ -230,7 +230,8 @@ def load_1DSFM_config(flagfile, options):
 # ------------------------------------------------------------------------------- dataset readers
 def ReadCovariance(dataset_directory, rot_covariances):
     """src/uncertainty.cpp:200-229 -> {(id1,id2): (3x3 covariance, refined rotation)}."""
-    ids, cov6, rot = _vg.parse_covariance_text(os.path.join(dataset_directory, "covariance_rot.txt"))
+    # the native reader of libgsfm_ra.so (csrc/gsfm_io.cpp); viewgraph.parse_covariance_text is its Python twin
+    ids, cov6, rot = _solver.read_covariance_rot(os.path.join(dataset_directory, "covariance_rot.txt"))
     for (a, b), c, r in zip(ids.tolist(), cov6, rot):
         S = np.array([[c[0], c[3], c[4]], [c[3], c[1], c[5]], [c[4], c[5], c[2]]])
         rot_covariances[(int(a), int(b))] = (S, np.array(r))

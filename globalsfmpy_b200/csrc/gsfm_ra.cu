@@ -73,6 +73,13 @@ void set_error(const char* fmt, ...) {
   g_last_error = buf;
 }
 
+}  // namespace
+namespace gsfm_io {
+// bridge for the host-only translation unit gsfm_io.cpp: same thread-local last-error slot
+void set_io_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace gsfm_io
+namespace {
+
 #define CUDA_TRY(expr)                                                                        \
   do {                                                                                        \
     cudaError_t err__ = (expr);                                                               \

@@ -1,6 +1,7 @@
 """Python host API over the C ABI (include/gsfm_ra.h).  Everything here calls libgsfm_ra.so;
 nothing computes on the CPU, and nothing here imports the oracle."""
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -121,6 +122,58 @@ def init_orientations_mst(num_views, edge_i, edge_j, omega_ij, weights, root=Non
                                                         capi.ptr(wij), capi.ptr(w, C.c_int32), -1 if root is None else int(root),
                                                         capi.ptr(om), capi.ptr(tree, C.c_uint8), C.byref(rounds), device))
     return om, tree.astype(bool), rounds.value
+
+
+def _take(ptr_obj, n, dtype):
+    """Copy n elements out of a malloc'ed array returned by the library and release it."""
+    if n == 0 or not ptr_obj:
+        out = np.zeros(0, dtype=dtype)
+    else:
+        out = np.ctypeslib.as_array(ptr_obj, shape=(n,)).astype(dtype, copy=True)
+    if ptr_obj:
+        capi.lib().gsfm_ra_free(C.cast(ptr_obj, C.c_void_p))
+    return out
+
+
+def read_covariance_rot(path):
+    """covariance_rot.txt through the native reader (reference src/uncertainty.cpp:200-229).
+    Returns ids [C,2] int64, cov6 [C,6] (C00 C11 C22 C01 C02 C12), rot [C,3]."""
+    n = C.c_uint64(0)
+    a, b = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)()
+    c6, r3 = C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
+    capi.check(capi.lib().gsfm_ra_read_covariance_rot(os.fsencode(path), C.byref(n), C.byref(a), C.byref(b), C.byref(c6), C.byref(r3)))
+    k = n.value
+    ids = np.stack([_take(a, k, np.int64), _take(b, k, np.int64)], axis=1) if k else np.zeros((0, 2), np.int64)
+    return ids, _take(c6, 6 * k, np.float64).reshape(k, 6), _take(r3, 3 * k, np.float64).reshape(k, 3)
+
+
+def write_covariance_rot(path, ids, cov6, rot):
+    """store_covariance_rot's file layout (reference src/uncertainty.cpp:164-198) through the native writer."""
+    ids = np.asarray(ids)
+    a = np.ascontiguousarray(ids[:, 0], dtype=np.uint32)
+    b = np.ascontiguousarray(ids[:, 1], dtype=np.uint32)
+    c6 = capi.as_f64(cov6, (len(a), 6))
+    r3 = capi.as_f64(rot, (len(a), 3))
+    capi.check(capi.lib().gsfm_ra_write_covariance_rot(os.fsencode(path), len(a), capi.ptr(a, C.c_uint32), capi.ptr(b, C.c_uint32),
+                                                       capi.ptr(c6), capi.ptr(r3)))
+
+
+def read_1dsfm(dataset_directory, with_matches=True):
+    """A 1DSfM dataset directory through the native reader (T/io/read_1dsfm.cc:93-412).  Returns a dict:
+    num_listed_views, view_ids [V], focal_length_priors [V], pairs [P,2] (as listed in EGs.txt), rotation_2 [P,3],
+    position_2 [P,3], num_verified_matches [P] (None unless with_matches)."""
+    listed, nv, npairs = C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
+    ids, a, b = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)()
+    focal, rot, pos = C.POINTER(C.c_double)(), C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
+    m = C.POINTER(C.c_int32)()
+    capi.check(capi.lib().gsfm_ra_read_1dsfm(os.fsencode(dataset_directory), C.byref(listed), C.byref(nv), C.byref(ids), C.byref(focal),
+                                             C.byref(npairs), C.byref(a), C.byref(b), C.byref(rot), C.byref(pos),
+                                             C.byref(m) if with_matches else None))
+    V, P = nv.value, npairs.value
+    pairs = np.stack([_take(a, P, np.int64), _take(b, P, np.int64)], axis=1) if P else np.zeros((0, 2), np.int64)
+    return dict(num_listed_views=listed.value, view_ids=_take(ids, V, np.int64), focal_length_priors=_take(focal, V, np.float64), pairs=pairs,
+                rotation_2=_take(rot, 3 * P, np.float64).reshape(P, 3), position_2=_take(pos, 3 * P, np.float64).reshape(P, 3),
+                num_verified_matches=_take(m, P, np.int64) if with_matches else None)
 
 
 def _summary(trace_capacity):

@@ -320,6 +320,28 @@ int gsfm_ra_init_orientations_mst(uint32_t num_views, uint64_t num_edges, const 
                                   const double* omega_ij, const int32_t* edge_weight, int64_t root, double* omega_out,
                                   uint8_t* edge_in_tree, int32_t* rounds_out, int32_t device);
 
+/* ---- on-disk formats either side of the path; host-only code, no CUDA device needed ---------------- */
+
+/* Arrays returned by the readers below live in malloc'ed memory: release each with gsfm_ra_free. */
+void gsfm_ra_free(void* p);
+
+/* covariance_rot.txt  (reference src/uncertainty.cpp:200-229 read_covariance; :164-198 store_covariance_rot): two header
+ * lines, then per view pair `id1 id2` and 9 doubles written as the decimal of their uint64 bit pattern:
+ * C00 C11 C22 C01 C02 C12 (cov6, the layout gsfm_ra_problem.cov6 takes) and R0 R1 R2 (the pair's rotation). */
+int gsfm_ra_read_covariance_rot(const char* path, uint64_t* count, uint32_t** view_id1, uint32_t** view_id2, double** cov6,
+                                double** rot);
+int gsfm_ra_write_covariance_rot(const char* path, uint64_t count, const uint32_t* view_id1, const uint32_t* view_id2,
+                                 const double* cov6, const double* rot);
+
+/* A 1DSfM dataset directory (thirdparty/TheiaSfM/src/theia/io/read_1dsfm.cc:93-412: cc.txt, list.txt, tracks.txt, EGs.txt).
+ * Views: the ids of cc.txt that list.txt defines (line index = id) with their focal-length priors (0 = none).  Pairs: the
+ * EGs.txt entries between those views, rotation_2 = angle-axis of S R^T S and position_2 = S t with S = diag(1,-1,-1)
+ * (:309-333), num_verified_matches = number of tracks that see both views.  num_listed_views, focal_length_priors,
+ * position_2 and num_verified_matches may be NULL (tracks.txt is then not read). */
+int gsfm_ra_read_1dsfm(const char* dataset_directory, uint32_t* num_listed_views, uint64_t* num_views, uint32_t** view_ids,
+                       double** focal_length_priors, uint64_t* num_pairs, uint32_t** view_id1, uint32_t** view_id2,
+                       double** rotation_2, double** position_2, int32_t** num_verified_matches);
+
 #ifdef __cplusplus
 }
 #endif
