@@ -277,6 +277,48 @@ bool FilterInitialViewGraph(ViewPairs* view_pairs, int min_num_two_view_inliers,
   return view_pairs->size() >= 1;
 }
 
+// ---- covariance_rot.txt ---------------------------------------------------------------------------------------------
+// read_covariance / store_covariance_rot of the reference (src/uncertainty.cpp:200-229, :164-198) over the native reader
+// and writer of the library (host-only code: no CUDA device needed).  `Covariances` is the reference's CovarianceMap shape:
+// map pair<Id, Id> -> pair<M, V>, M with a mutable (row, col) accessor, V indexable.
+template <class Covariances>
+bool ReadCovariance(const std::string& dataset_directory, Covariances* covariances, std::string* error = nullptr) {
+  if (!covariances) return false;
+  uint64_t n = 0;
+  uint32_t *a = nullptr, *b = nullptr;
+  double *c6 = nullptr, *r3 = nullptr;
+  const std::string path = dataset_directory + "/covariance_rot.txt";
+  if (gsfm_ra_read_covariance_rot(path.c_str(), &n, &a, &b, &c6, &r3) != 0) { if (error) *error = gsfm_ra_last_error(); return false; }
+  for (uint64_t e = 0; e < n; ++e) {
+    auto& entry = (*covariances)[{a[e], b[e]}];
+    const double* c = c6 + 6 * e;  // C00 C11 C22 C01 C02 C12
+    auto& S = entry.first;
+    S(0, 0) = c[0]; S(1, 1) = c[1]; S(2, 2) = c[2];
+    S(0, 1) = S(1, 0) = c[3]; S(0, 2) = S(2, 0) = c[4]; S(1, 2) = S(2, 1) = c[5];
+    for (int t = 0; t < 3; ++t) entry.second[t] = r3[3 * e + t];
+  }
+  gsfm_ra_free(a); gsfm_ra_free(b); gsfm_ra_free(c6); gsfm_ra_free(r3);
+  return true;
+}
+
+template <class Covariances>
+bool StoreCovarianceRot(const std::string& dataset_directory, const Covariances& covariances, std::string* error = nullptr) {
+  std::vector<uint32_t> a, b;
+  std::vector<double> c6, r3;
+  for (const auto& kv : covariances) {
+    a.push_back((uint32_t)kv.first.first); b.push_back((uint32_t)kv.first.second);
+    const auto& S = kv.second.first;
+    for (double x : {S(0, 0), S(1, 1), S(2, 2), S(0, 1), S(0, 2), S(1, 2)}) c6.push_back(x);
+    for (int t = 0; t < 3; ++t) r3.push_back(kv.second.second[t]);
+  }
+  const std::string path = dataset_directory + "/covariance_rot.txt";
+  if (gsfm_ra_write_covariance_rot(path.c_str(), a.size(), a.data(), b.data(), c6.data(), r3.data()) != 0) {
+    if (error) *error = gsfm_ra_last_error();
+    return false;
+  }
+  return true;
+}
+
 }  // namespace gsfm_b200
 
 #endif  // GSFM_ROTATION_ESTIMATOR_HPP_

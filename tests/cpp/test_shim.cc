@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <random>
+#include <string>
+#include <unistd.h>
 #include <unordered_map>
 
 #include "../../include/gsfm_rotation_estimator.hpp"
@@ -25,6 +27,7 @@ struct Vector3d {                                 // stand-in for Eigen::Vector3
 struct Matrix3d {                                 // stand-in for Eigen::Matrix3d
   double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   double operator()(int r, int c) const { return m[3 * r + c]; }
+  double& operator()(int r, int c) { return m[3 * r + c]; }
 };
 struct TwoViewInfo { Vector3d rotation_2; int num_verified_matches = 0; };  // T/sfm/twoview_info.h:54-98
 typedef std::unordered_map<ViewIdPair, TwoViewInfo, PairHash> ViewPairs;
@@ -125,6 +128,25 @@ int main(int argc, char** argv) {
     Orientations none; ViewPairs nopairs; Orientations some = init;
     Check(!base->EstimateRotations(pairs, &none), "EstimateRotations returns false without initial orientations");
     Check(!base->EstimateRotations(nopairs, &some), "EstimateRotations returns false without view pairs");
+  }
+  {  // covariance_rot.txt through the library's native writer / reader (host-only: runs without a device too)
+    const char* tmp = std::getenv("TMPDIR");
+    const std::string dir = std::string(tmp ? tmp : "/tmp") + "/gsfm_shim_" + std::to_string((long)getpid());
+    Check(system(("mkdir -p " + dir).c_str()) == 0, "scratch directory");
+    std::string err;
+    Check(gsfm_b200::StoreCovarianceRot(dir, covs, &err), "StoreCovarianceRot");
+    CovarianceMap back;
+    Check(gsfm_b200::ReadCovariance(dir, &back, &err) && back.size() == covs.size(), "ReadCovariance");
+    bool same = true;
+    for (const auto& kv : covs) {
+      const auto it = back.find(kv.first);
+      if (it == back.end()) { same = false; break; }
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) same = same && std::memcmp(&kv.second.first.m[3 * r + c], &it->second.first.m[3 * (r < c ? r : c) + (r < c ? c : r)], 8) == 0;
+    }
+    Check(same, "  covariances survive the round trip bit for bit (upper triangle mirrored)");
+    Check(!gsfm_b200::ReadCovariance(dir + "/nowhere", &back, &err) && err.find("cannot open") != std::string::npos, "  a missing file fails loudly");
+    if (system(("rm -rf " + dir).c_str()) != 0) std::printf("      (could not remove %s)\n", dir.c_str());
   }
   if (expect_no_device) {
     Orientations o = init;
