@@ -32,8 +32,14 @@
     if (e__ != cudaSuccess) { std::printf("%s failed: %s\n", #x, cudaGetErrorString(e__)); std::exit(1); } \
   } while (0)
 
-constexpr int GS = 1250;        // views per group: 2 slices x GS x 24 B = 60 KB of shared memory
-constexpr int CE = 1664;        // edges per chunk (52 records)
+#ifndef TILED_GS
+#define TILED_GS 1250
+#endif
+#ifndef TILED_CE
+#define TILED_CE 1664
+#endif
+constexpr int GS = TILED_GS;    // views per group: 2 slices x GS x 24 B of shared memory (1250 -> 60 KB)
+constexpr int CE = TILED_CE;    // edges per chunk (a multiple of 32; 1664 = 52 records)
 constexpr int kRecBytes = 6 * 32 * 8 + 2 * 32 * 2;  // 1664
 constexpr int kThreads = 256, kWarps = 8, kStages = 2;
 
