@@ -157,27 +157,9 @@ class ProblemArrays:
         self.c = p
 
 
-def declare(lib, oracle=False):
-    """Attach argtypes/restypes shared by the product library and the oracle."""
+def declare(lib):
+    """Attach argtypes/restypes of every entry point of include/gsfm_ra.h."""
     pp, lp, op, sp = C.POINTER(Problem), C.POINTER(Loss), C.POINTER(Options), C.POINTER(Summary)
-    if oracle:
-        cb = C.CFUNCTYPE(None, C.c_double, _dp, C.c_void_p)
-        lib.ra_oracle_loss.argtypes = [lp, C.c_double, _dp]
-        lib.ra_oracle_loss.restype = None
-        lib.ra_oracle_gamma_table.argtypes = [C.c_int, C.c_int]
-        lib.ra_oracle_gamma_table.restype = C.c_double
-        lib.ra_oracle_angle_axis_to_matrix.argtypes = [_dp, _dp]
-        lib.ra_oracle_matrix_to_angle_axis.argtypes = [_dp, _dp]
-        lib.ra_oracle_whiten.argtypes = [C.c_int, _dp, C.c_double, _dp]
-        lib.ra_oracle_edge.argtypes = [_dp] * 7
-        lib.ra_oracle_eval_edges.argtypes = [pp, lp, _dp, _dp, _dp, _dp, _dp, C.c_int]
-        lib.ra_oracle_assemble.argtypes = [pp, lp, _dp, _dp, _dp, _dp, _u32p, _u32p, _dp, C.c_int]
-        lib.ra_oracle_cost.argtypes = [pp, lp, _dp, _dp, C.c_int]
-        lib.ra_oracle_solve.argtypes = [pp, op, _dp, sp, cb, C.c_void_p]
-        lib.ra_oracle_solve_sigma_consensus.argtypes = [pp, op, C.c_int32, C.c_double, _dp, sp, _dp]
-        lib.ra_oracle_filter_view_pairs.argtypes = [pp, _dp, C.c_double, _u8p, _dp]
-        lib.loss_cb_type = cb
-        return lib
     vp = C.c_void_p
     lib.gsfm_ra_abi_version.restype = C.c_int
     lib.gsfm_ra_last_error.restype = C.c_char_p

@@ -20,12 +20,35 @@ def build():
     subprocess.check_call(["make", "-s", "-C", HERE])
 
 
+def _declare(lib):
+    """argtypes / restypes of oracle/ra_oracle.h (the structs are the C ABI's own: include/gsfm_ra.h)."""
+    pp, lp, op, sp = C.POINTER(capi.Problem), C.POINTER(capi.Loss), C.POINTER(capi.Options), C.POINTER(capi.Summary)
+    dp, u32p, u8p = C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
+    cb = C.CFUNCTYPE(None, C.c_double, dp, C.c_void_p)
+    lib.ra_oracle_loss.argtypes = [lp, C.c_double, dp]
+    lib.ra_oracle_loss.restype = None
+    lib.ra_oracle_gamma_table.argtypes = [C.c_int, C.c_int]
+    lib.ra_oracle_gamma_table.restype = C.c_double
+    lib.ra_oracle_angle_axis_to_matrix.argtypes = [dp, dp]
+    lib.ra_oracle_matrix_to_angle_axis.argtypes = [dp, dp]
+    lib.ra_oracle_whiten.argtypes = [C.c_int, dp, C.c_double, dp]
+    lib.ra_oracle_edge.argtypes = [dp] * 7
+    lib.ra_oracle_eval_edges.argtypes = [pp, lp, dp, dp, dp, dp, dp, C.c_int]
+    lib.ra_oracle_assemble.argtypes = [pp, lp, dp, dp, dp, dp, u32p, u32p, dp, C.c_int]
+    lib.ra_oracle_cost.argtypes = [pp, lp, dp, dp, C.c_int]
+    lib.ra_oracle_solve.argtypes = [pp, op, dp, sp, cb, C.c_void_p]
+    lib.ra_oracle_solve_sigma_consensus.argtypes = [pp, op, C.c_int32, C.c_double, dp, sp, dp]
+    lib.ra_oracle_filter_view_pairs.argtypes = [pp, dp, C.c_double, u8p, dp]
+    lib.loss_cb_type = cb
+    return lib
+
+
 def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             build()
-        _lib = capi.declare(C.CDLL(LIB_PATH), oracle=True)
+        _lib = _declare(C.CDLL(LIB_PATH))
     return _lib
 
 
