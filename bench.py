@@ -36,6 +36,8 @@ WORKLOADS = {
     "syn_10k_1M": dict(views=10000, edges=1000000, covariance=False, loss=("cauchy", 0.05), etype="ANGLE_AXIS"),
     "syn_100k_20M_cov": dict(views=100000, edges=20000000, covariance=True, loss=("magsac3", 1.0), etype="ANGLE_AXIS_COVARIANCE"),
     "piccadilly_like": dict(views=2300, edges=300000, covariance=False, loss=("cauchy", 0.05), etype="ANGLE_AXIS"),
+    # BASELINE configs[1] stand-in (ETH3D terrace needs images + COLMAP): 23 views, near-complete graph
+    "terrace_like": dict(views=23, edges=200, covariance=True, loss=("magsac3", 0.02), etype="ANGLE_AXIS_COVARIANCE"),
     "small": dict(views=500, edges=20000, covariance=False, loss=("cauchy", 0.05), etype="ANGLE_AXIS"),
 }
 

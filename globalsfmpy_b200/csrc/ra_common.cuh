@@ -1,0 +1,251 @@
+// ra_common.cuh -- constants, error plumbing, device-resident scalars, deterministic grid sum, TMA record pipeline
+// Part of libgsfm_ra (one translation unit, see gsfm_ra.cu); reference citations sit next to each kernel.
+#pragma once
+#include <cooperative_groups.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/gsfm_ra.h"
+#include "so3_device.cuh"
+
+using namespace gsfm;
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int kBlock = 256;        // threads per block of every kernel
+constexpr int kWarpsPerBlock = kBlock / 32;
+constexpr uint32_t kSideBit = 0x80000000u;  // he_col bit 31: the ROW view is the j (second) view of the edge
+constexpr int kPartStride = 10;    // per-task partial: diag(6) grad(3) cost(1)
+// The block matrix is stored as CHUNK RECORDS of 32 consecutive half-edges:
+//   { double blk[kBlk][32]; uint32_t col[32]; }   128 B aligned,
+// so 32 lanes still read/write 256 contiguous bytes per block component (coalesced), and K2 can
+// pull a whole record into shared memory with ONE bulk async copy (TMA, cp.async.bulk).
+//   kBlk = 6: symmetric off-diagonal block -S packed (00,01,02,11,12,22) -- every residual that is a function of the
+//             error rotation (types 2..8) is a Laplacian stencil in the body frame;  1664 B per record (52 B / half-edge)
+//   kBlk = 9: general row-major block (QUATERNION_NORM, ROTATION_MAT_FNORM);         2432 B per record (76 B / half-edge)
+template <int kBlk>
+struct Rec {
+  static constexpr int kDoubles = kBlk * 32 + 16;
+  static constexpr int kBytes = kDoubles * 8;
+  static constexpr int kColOffset = kBlk * 32;  // doubles: col[] starts here
+};
+constexpr int kStages = 4;                       // TMA ring depth per warp
+constexpr int spmv_smem_bytes(int blk) { return kWarpsPerBlock * kStages * (blk * 32 + 16) * 8 + kWarpsPerBlock * kStages * 8; }
+
+__device__ __host__ __forceinline__ size_t blk_index(uint64_t h, int k, int rec_doubles) { return (size_t)(h >> 5) * rec_doubles + (size_t)k * 32 + (h & 31); }
+
+thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+}  // namespace
+namespace gsfm_io {
+// bridge for the host-only translation unit gsfm_io.cpp: same thread-local last-error slot
+void set_io_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace gsfm_io
+namespace {
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t err__ = (expr);                                                               \
+    if (err__ != cudaSuccess) {                                                               \
+      set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+      return GSFM_RA_ERR_CUDA;                                                                \
+    }                                                                                         \
+  } while (0)
+
+#define RA_TRY(expr)            \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Scalars living on the device for the whole solve (one cache line group).
+struct DevScalars {
+  // evaluation
+  double cost;          // sum 1/2 rho at the last evaluated point
+  double gmax;          // max |g| (Euclidean gradient) at the last evaluated point
+  double xnorm2;        // |omega|^2 of the last evaluated point
+  // PCG
+  double rz, pAp, alpha, beta, rr, bb;
+  int pcg_iter, pcg_done, pcg_breakdown, pad0;
+  // step
+  double dg, dHd, step2;  // delta.g, delta.H.delta, |delta|^2 (Euclidean step)
+  int bad;                // non-finite detected (1) / a peer GPU did not show up (2)
+  int xseq;               // cross-GPU exchange sequence number (multi-GPU persistent PCG)
+  int bar_seq, pad1;      // grid barrier sequence number of the persistent PCG kernel
+  // %globaltimer stamps of the trust-region batch: start of k_prepare_solve, end of k_apply_step, end of k_node_finalize
+  unsigned long long t_begin, t_linear_end, t_end;
+};
+// What changes from one trust-region batch to the next when the batch is replayed as a CUDA graph: read by the kernels
+// from device memory, refreshed by the graph's first node (a 16-byte H2D copy from pinned host memory).
+struct IterParams {
+  double mu;
+  unsigned seq, pad;
+};
+static_assert(sizeof(DevScalars) % 8 == 0, "DevScalars is copied to the host mailbox in 8-byte words");
+
+// Host mailbox (pinned, mapped into the device): the last kernel of a trust-region batch copies the device scalars here and
+// then publishes the batch's sequence number, so the host learns the outcome by polling its own memory -- no D2H copy
+// operation, no stream synchronisation on the critical path of an iteration.
+struct HostMailbox {
+  DevScalars sc;
+  volatile unsigned seq;
+};
+
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Deterministic grid-wide sum of NV values: block tree -> per-block slot -> the LAST block to
+// arrive adds the slots in a fixed order.  Returns true in the last block (all threads), with the
+// totals in `tot` (valid in thread 0 only).
+template <int NV>
+__device__ bool grid_sum(double (&v)[NV], double* slots, unsigned* counter, double (&tot)[NV]) {
+  __shared__ double sm[NV][kWarpsPerBlock];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double s = warp_sum(v[k]);
+    if (lane == 0) sm[k][warp] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double s = 0.0;
+      for (int w = 0; w < kWarpsPerBlock; ++w) s += sm[k][w];
+      slots[(size_t)blockIdx.x * NV + k] = s;
+    }
+    __threadfence();
+    const unsigned ticket = atomicAdd(counter, 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  // the last block: warp 0 adds the slots, lane l the blocks l, l+32, ... in order, then a butterfly -- a fixed order
+  // whatever block happens to be last, and all loads of a lane are independent (no serial chain of L2 round trips)
+  if (warp == 0) {
+    __threadfence();
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    for (unsigned b = lane; b < gridDim.x; b += 32)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) acc[k] += __ldcg(slots + (size_t)b * NV + k);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) tot[k] = warp_sum(acc[k]);
+    if (lane == 0) *counter = 0u;
+  }
+  return true;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// TMA record pipeline shared by K1 and K2: every warp keeps kStages bulk async copies (cp.async.bulk, one record
+// each, completion on a warp-private mbarrier) in flight.  Bytes in flight are set by the ring depth, not by
+// registers or occupancy.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_bulk(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_bulk_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+
+// L2 residency of the matrix stream (K2): a PCG solve reads the same records once per CG step.  When the stream is somewhat
+// larger than the L2 (104 MB vs 126 MB of L2 shared with everything else at 1M edges) plain LRU keeps almost nothing of a
+// cyclic sweep; loading `keep8` of every 8 records with an evict_last policy and the rest with evict_first pins a fixed
+// fraction of the matrix from one pass to the next and only the remainder streams from HBM (measured at 1M edges,
+// profiles/r01_j_l2_keep.txt: K2 alone 25.9 -> 22.6 us, CG step 33.3 -> 31.9 us with 6 of 8).  keep8 = 0 (streams far larger
+// than the L2, or small enough for LRU to hold them): no hints.  The host picks it from the device's L2 size.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
+struct WarpPipe {
+  double* ring;    // this warp's kStages records in shared memory
+  uint64_t* bars;  // this warp's kStages mbarriers
+  uint32_t pos;    // records consumed since init: ring slot = pos % kStages, phase = (pos / kStages) & 1
+};
+
+template <int kRecBytes>
+__device__ __forceinline__ void pipe_init_bytes(WarpPipe& wp, unsigned char* smem) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  wp.ring = reinterpret_cast<double*>(smem + (size_t)warp * kStages * kRecBytes);
+  wp.bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWarpsPerBlock * kStages * kRecBytes) + warp * kStages;
+  wp.pos = 0;
+  if (lane == 0) {
+    for (int st = 0; st < kStages; ++st) mbar_init(&wp.bars[st], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+}
+template <int kBlk>
+__device__ __forceinline__ void pipe_init(WarpPipe& wp, unsigned char* smem) { pipe_init_bytes<Rec<kBlk>::kBytes>(wp, smem); }
+
+}  // namespace
