@@ -31,12 +31,40 @@ double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::
 int make_dev_loss(const gsfm_ra_loss* in, DevLoss* L) {
   std::memset(L, 0, sizeof(*L));
   if (!in) { L->kind = kLossTrivial; L->scale = 1.0; return 0; }
-  if (in->kind < 0 || in->kind > GSFM_RA_LOSS_MAGSAC9) { set_error("unknown loss kind %d", in->kind); return GSFM_RA_ERR_INVALID; }
+  if (in->kind < 0 || in->kind > GSFM_RA_LOSS_TABULATED) { set_error("unknown loss kind %d", in->kind); return GSFM_RA_ERR_INVALID; }
+  // composition rho(s) = f(g(s)) (ComposedLoss, scripts/loss_functions.py:250-265): g is one of the closed-form kinds
+  const double iscale = (in->inner_scale == 0.0) ? 1.0 : in->inner_scale;
+  if (in->inner_kind != GSFM_RA_LOSS_TRIVIAL || iscale != 1.0) {
+    if (in->inner_kind < 0 || in->inner_kind >= GSFM_RA_LOSS_MAGSAC3) {
+      set_error("inner loss kind %d of a composition has no closed form on the device (tabulate the composed object instead)", in->inner_kind);
+      return GSFM_RA_ERR_UNSUPPORTED;
+    }
+    if (in->kind == GSFM_RA_LOSS_TABULATED) { set_error("a tabulated loss cannot be composed: tabulate the composed object"); return GSFM_RA_ERR_UNSUPPORTED; }
+    if (in->inner_kind != GSFM_RA_LOSS_TRIVIAL && !(in->inner_p[0] > 0.0)) { set_error("inner loss parameter p[0] must be > 0"); return GSFM_RA_ERR_INVALID; }
+    if ((in->inner_kind == GSFM_RA_LOSS_TOLERANT || in->inner_kind == GSFM_RA_LOSS_GEMANMCCLURE) && !(in->inner_p[1] > 0.0)) {
+      set_error("inner loss parameter p[1] must be > 0"); return GSFM_RA_ERR_INVALID;
+    }
+    L->composed = 1; L->inner_kind = in->inner_kind; L->ip0 = in->inner_p[0]; L->ip1 = in->inner_p[1]; L->iscale = iscale;
+    L->isq0 = in->inner_p[0] * in->inner_p[0]; L->iinv_sq0 = 1.0 / L->isq0;
+  }
+  if (in->kind == GSFM_RA_LOSS_TABULATED) {
+    const int M = in->table_per_octave;
+    if (!in->table || in->table_octaves < 1 || M < 1 || M > 4096 || (M & (M - 1)) != 0) {
+      set_error("tabulated loss: table must be non-NULL, octaves >= 1, per_octave a power of two <= 4096"); return GSFM_RA_ERR_INVALID;
+    }
+    int lg = 0;
+    while ((1 << lg) < M) ++lg;
+    L->kind = in->kind; L->flags = in->flags; L->scale = (in->scale == 0.0) ? 1.0 : in->scale;
+    L->tab_min_exp = in->table_min_exp; L->tab_octaves = in->table_octaves; L->tab_log2_per_octave = lg;
+    L->tab_rows = 2 + in->table_octaves * M;
+    L->table = nullptr;  // device copy attached by attach_loss_table
+    return 0;
+  }
   L->kind = in->kind; L->flags = in->flags; L->p0 = in->p[0]; L->p1 = in->p[1];
   L->scale = (in->scale == 0.0) ? 1.0 : in->scale;
   L->sq0 = in->p[0] * in->p[0];
   L->inv_sq0 = 1.0 / L->sq0;
-  const bool needs_p0 = in->kind != GSFM_RA_LOSS_TRIVIAL;
+  const bool needs_p0 = in->kind != GSFM_RA_LOSS_TRIVIAL && in->kind != GSFM_RA_LOSS_TABULATED;
   if (needs_p0 && !(in->p[0] > 0.0)) { set_error("loss parameter p[0] must be > 0"); return GSFM_RA_ERR_INVALID; }
   if ((in->kind == GSFM_RA_LOSS_TOLERANT || in->kind == GSFM_RA_LOSS_GEMANMCCLURE) && !(in->p[1] > 0.0)) {
     set_error("loss parameter p[1] must be > 0"); return GSFM_RA_ERR_INVALID;
@@ -60,6 +88,18 @@ int make_dev_loss(const gsfm_ra_loss* in, DevLoss* L) {
     L->weight_zero = L->one_over_sigma * (std::tgamma(dof) - gk);
     L->expo = nu / 2.0 - 1.5;
   }
+  return 0;
+}
+
+// Device copy of a tabulated loss (rows of rho, rho', rho''); `buf` owns it.
+template <typename Buf>
+int attach_loss_table(const gsfm_ra_loss* in, DevLoss* L, Buf* buf, cudaStream_t st) {
+  if (!in || in->kind != GSFM_RA_LOSS_TABULATED) return 0;
+  const size_t n = 3 * (size_t)L->tab_rows;
+  RA_TRY(buf->alloc(n));
+  CUDA_TRY(cudaMemcpyAsync(buf->p, in->table, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));  // the caller's table may be freed as soon as the call returns
+  L->table = buf->p;
   return 0;
 }
 
@@ -142,7 +182,7 @@ struct StreamHolder {
 // Per-device facts that are expensive to query: cached for the life of the process.
 struct DeviceInfo {
   bool ready = false;
-  int sm_count = 0, coop = 0, occ_k2[2] = {1, 1};  // occ_k2[0]: 6-double records, [1]: 9-double records
+  int sm_count = 0, coop = 0, occ_k2[3] = {1, 1, 1};  // resident blocks of the persistent PCG kernel: [0] 4-, [1] 6-, [2] 9-double records
   int l2_bytes = 0;
 };
 DeviceInfo g_device_info[64];
@@ -232,11 +272,12 @@ struct gsfm_ra_solver {
   uint64_t H = 0;       // half-edges of this shard (2E)
   int rank = 0, world = 1;
   int error_type = 4;
-  int blk = 6;          // doubles per stored off-diagonal block (6: symmetric Laplacian stencil, 9: general)
+  int blk = 6;          // doubles per stored off-diagonal block (4: compact scalar-weight stencil, 6: symmetric Laplacian stencil, 9: general)
   bool scalar_u = false;  // the whitening factor is a scalar multiple of the identity (types 2, 4, 5, 7, 8)
   gsfm_ra_options opt;
   DevLoss loss;
   int64_t launches = 0;
+  int64_t linear_unconverged = 0;  // PCG solves that hit pcg_max_iterations above pcg_rtol
   bool cooperative = true;  // persistent PCG kernel available
   ncclx::Comm comm = nullptr;  // edge-sharded exchange (world > 1)
   // fused exchange: one cudaMalloc'ed block per rank {double y[2][3N]; unsigned flag;}, every peer's block mapped here
@@ -249,6 +290,7 @@ struct gsfm_ra_solver {
   uint32_t n_iso = 0;
   Partition pk1, pk2;  // K1 (edge kernel) and K2 (SpMV / PCG) partitions
   // per half-edge constants, planar
+  DevBuf<double> loss_table;  // device copy of a tabulated loss (GSFM_RA_LOSS_TABULATED)
   DevBuf<double> inrec;  // K1's input records (k_setup_halfedges)
   int ku = 1;            // whitening entries per half-edge in the input records: 1 (scalar) or 6 (upper triangle)
   // edge-order copies for the API kernels
@@ -357,7 +399,7 @@ struct gsfm_ra_solver {
   typedef void (*K1Fn)(const K1Args);
   template <bool JAC, int RES, bool SCAL>
   K1Fn pick_k1_loss() const {
-    const bool plain = loss.scale == 1.0;
+    const bool plain = loss.scale == 1.0 && !loss.composed;
     if (plain && loss.kind == kLossCauchy) return k_edges<JAC, RES, SCAL, kLossCauchy>;
     if (plain && loss.kind == kLossSoftLOne) return k_edges<JAC, RES, SCAL, kLossSoftLOne>;
     if (plain && loss.kind == kLossHuber) return k_edges<JAC, RES, SCAL, kLossHuber>;
@@ -385,11 +427,14 @@ struct gsfm_ra_solver {
     pick_k1(jacobian)<<<pk1.grid, kBlock, k1_smem_bytes(), stream>>>(A);
   }
   void launch_spmv(int b, const double* x4, int check_done) {
-    if (blk == 6)
-      k_spmv<6><<<pk2.grid, kBlock, smem_bytes(), stream>>>(pk2.num_warps, H, pk2.span, pk2.warp_seg_ptr.p, pk2.seg_begin.p, pk2.seg_len.p, val[b].p,
+    if (blk == 4)
+      k_spmv<4><<<pk2.grid, kPcgBlock, smem_bytes(), stream>>>(pk2.num_warps, H, pk2.span, pk2.warp_seg_ptr.p, pk2.seg_begin.p, pk2.seg_len.p, val[b].p,
+                                                            x4, ypart.p, sc.p, check_done, keep8);
+    else if (blk == 6)
+      k_spmv<6><<<pk2.grid, kPcgBlock, smem_bytes(), stream>>>(pk2.num_warps, H, pk2.span, pk2.warp_seg_ptr.p, pk2.seg_begin.p, pk2.seg_len.p, val[b].p,
                                                             x4, ypart.p, sc.p, check_done, keep8);
     else
-      k_spmv<9><<<pk2.grid, kBlock, smem_bytes(), stream>>>(pk2.num_warps, H, pk2.span, pk2.warp_seg_ptr.p, pk2.seg_begin.p, pk2.seg_len.p, val[b].p,
+      k_spmv<9><<<pk2.grid, kPcgBlock, smem_bytes(), stream>>>(pk2.num_warps, H, pk2.span, pk2.warp_seg_ptr.p, pk2.seg_begin.p, pk2.seg_len.p, val[b].p,
                                                             x4, ypart.p, sc.p, check_done, keep8);
   }
 
@@ -512,8 +557,8 @@ struct gsfm_ra_solver {
         P.ip = graph_params ? it_params.p : nullptr;
       }
       void* args[] = {&P};
-      const void* fn = (blk == 6) ? (const void*)k_pcg_persistent<6> : (const void*)k_pcg_persistent<9>;
-      CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(pk2.grid), dim3(kBlock), args, smem_bytes(), stream));
+      const void* fn = (blk == 4) ? (const void*)k_pcg_persistent<4> : (blk == 6) ? (const void*)k_pcg_persistent<6> : (const void*)k_pcg_persistent<9>;
+      CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(pk2.grid), dim3(kPcgBlock), args, smem_bytes(), stream));
       launches += 1;
       return 0;
     }
@@ -564,12 +609,15 @@ int device_info(int device, DeviceInfo** out) {
     CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaDeviceGetAttribute(&d.coop, cudaDevAttrCooperativeLaunch, device));
     CUDA_TRY(cudaDeviceGetAttribute(&d.l2_bytes, cudaDevAttrL2CacheSize, device));
+    CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(4)));
     CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(6)));
     CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(9)));
+    CUDA_TRY(cudaFuncSetAttribute(k_spmv<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(4)));
     CUDA_TRY(cudaFuncSetAttribute(k_spmv<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(6)));
     CUDA_TRY(cudaFuncSetAttribute(k_spmv<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(9)));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2[0], k_pcg_persistent<6>, kBlock, spmv_smem_bytes(6)));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2[1], k_pcg_persistent<9>, kBlock, spmv_smem_bytes(9)));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2[0], k_pcg_persistent<4>, kPcgBlock, spmv_smem_bytes(4)));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2[1], k_pcg_persistent<6>, kPcgBlock, spmv_smem_bytes(6)));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2[2], k_pcg_persistent<9>, kPcgBlock, spmv_smem_bytes(9)));
     // keep freed blocks in the pool: the next solver reuses them
     cudaMemPool_t pool;
     CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -611,14 +659,16 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   s->opt = *options;
   s->rank = rank; s->world = world;
   s->error_type = prob->error_type;
-  s->blk = s->general() ? 9 : 6;
   s->scalar_u = !(prob->error_type == GSFM_RA_ANGLE_AXIS_COVARIANCE || prob->error_type == GSFM_RA_ANGLE_AXIS_COV_INLIERS);
   s->ku = s->scalar_u ? 1 : 6;
+  // scalar-weight angle-axis stencils (types 4, 5, 7, 8) are stored in the compact 4-double form (-DGSFM_RA_NO_COMPACT: 6)
+  s->blk = s->general() ? 9 : (kCompactScalarStencil && s->scalar_u && !s->manifold()) ? 4 : 6;
   RA_TRY(make_dev_loss(&options->loss, &s->loss));
   s->sm_count = di->sm_count;
   CUDA_TRY(cudaStreamCreateWithFlags(&s->stream_holder.s, cudaStreamNonBlocking));
   s->stream = s->stream_holder.s;
   AllocScope alloc_scope(s->stream);
+  RA_TRY(attach_loss_table(&options->loss, &s->loss, &s->loss_table, s->stream));
   for (auto& e : s->ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDefault));
   CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
   lap("context/stream");
@@ -678,22 +728,24 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   s->launches += 6;
 
   // ---- balanced partitions, one per kernel class, sized to exactly one resident wave of that kernel ----
-  const int occ_k2 = di->occ_k2[s->blk == 6 ? 0 : 1];
+  const int occ_k2 = di->occ_k2[s->blk == 4 ? 0 : s->blk == 6 ? 1 : 2];
   s->cooperative = di->coop != 0 && occ_k2 > 0;
+  if (s->opt.linear_solver == GSFM_RA_SOLVER_AUTO)
+    s->opt.linear_solver = (N <= GSFM_RA_AUTO_DENSE_MAX_VIEWS && s->cooperative && world == 1) ? GSFM_RA_SOLVER_DENSE_CHOLESKY : GSFM_RA_SOLVER_PCG;
   // Edge-sharded: the range length and the launch grid are sized from the LARGEST shard (ceil(E_total / world) edges), so
   // every rank launches the same grid even when the shards differ by an edge -- the replicated grid-wide sums then add in
   // the same order on every rank and the replicas stay bit-identical.  (A rank with fewer half-edges leaves its last
   // warps idle.)
   const uint64_t H_sizing = 2 * ((prob->num_edges + (uint64_t)world - 1) / (uint64_t)world);
-  auto make = [&](Partition& P, int blocks_per_sm) -> int {
-    const uint64_t max_warps = (uint64_t)s->sm_count * std::max(1, blocks_per_sm) * kWarpsPerBlock;
+  auto make = [&](Partition& P, int blocks_per_sm, int warps_per_block) -> int {
+    const uint64_t max_warps = (uint64_t)s->sm_count * std::max(1, blocks_per_sm) * warps_per_block;
     uint64_t per = (H_sizing + max_warps - 1) / max_warps;
     per = std::max<uint64_t>(64, (per + 31) / 32 * 32);  // at least 64 half-edges per warp, whole records
     const uint32_t nw = (uint32_t)std::max<uint64_t>(1, (H + per - 1) / per);
     const uint32_t nw_sizing = (uint32_t)std::max<uint64_t>(1, (H_sizing + per - 1) / per);
     P.num_warps = nw; P.span = (uint32_t)per;
     P.num_segs = nw + N;  // upper bound: every range start + every row start opens one segment
-    P.grid = (nw_sizing + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    P.grid = (nw_sizing + warps_per_block - 1) / warps_per_block;
     DevBuf<uint32_t> nseg, cnt;
     RA_TRY(nseg.alloc(nw + 2)); RA_TRY(cnt.alloc(N + 2));
     RA_TRY(P.warp_seg_ptr.alloc(nw + 2)); RA_TRY(P.seg_row.alloc(P.num_segs)); RA_TRY(P.seg_begin.alloc(P.num_segs));
@@ -713,10 +765,10 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
     for (int jac = 0; jac < 2; ++jac) CUDA_TRY(cudaFuncSetAttribute((const void*)s->pick_k1(jac != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, s->k1_smem_bytes()));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_k1, (const void*)s->pick_k1(true), kBlock, s->k1_smem_bytes()));
   }
-  RA_TRY(make(s->pk1, occ_k1));
-  RA_TRY(make(s->pk2, occ_k2));
+  RA_TRY(make(s->pk1, occ_k1, kWarpsPerBlock));
+  RA_TRY(make(s->pk2, std::min(occ_k2, kPcgBlocksPerSM), kPcgWarps));
   // the cooperative grid must be fully resident; node loops are grid-strided so any size works
-  s->pk2.grid = std::min<uint32_t>(s->pk2.grid, (uint32_t)s->sm_count * std::max(1, occ_k2));
+  s->pk2.grid = std::min<uint32_t>(s->pk2.grid, (uint32_t)s->sm_count * std::max(1, std::min(occ_k2, kPcgBlocksPerSM)));
   {
     // L2 residency of the matrix stream: pin what 62 % of the L2 can hold when the stream is larger than that but still
     // comparable to the L2 (GSFM_RA_L2_KEEP=0..7 overrides, 0 disables)
@@ -880,7 +932,7 @@ int iterate(gsfm_ra_solver* s, int max_new_iterations, gsfm_ra_summary* sum) {
   const int64_t launches0 = s->launches;
   const double asm0 = s->ms_assemble, lin0 = s->ms_linear, cost0 = s->ms_cost;
   const uint32_t N = s->N;
-  int succ = 0, unsucc = 0;
+  int succ = 0, unsucc = 0, unconverged = 0;
   int64_t lin_total = 0;
   if (sum) sum->trace_size = 0;
   CUDA_TRY(cudaSetDevice(s->device));
@@ -928,6 +980,7 @@ int iterate(gsfm_ra_solver* s, int max_new_iterations, gsfm_ra_summary* sum) {
     const double lin_res = (s->h_sc->bb > 0.0) ? std::sqrt(s->h_sc->rr / s->h_sc->bb) : 0.0;
     it.linear_iterations = lin_it; it.linear_residual = lin_res;
     lin_total += lin_it;
+    if (o.linear_solver == GSFM_RA_SOLVER_PCG && !breakdown && lin_it >= o.pcg_max_iterations && lin_res > o.pcg_rtol) ++unconverged;
     const double model_change = -s->h_sc->dg - 0.5 * s->h_sc->dHd;
     it.model_cost_change = model_change;
     // `bad` also covers a non-finite candidate evaluation; a non-finite STEP shows up in step2
@@ -992,6 +1045,7 @@ int iterate(gsfm_ra_solver* s, int max_new_iterations, gsfm_ra_summary* sum) {
     sum->num_successful_steps = succ;
     sum->num_unsuccessful_steps = unsucc;
     sum->total_linear_iterations = lin_total;
+    sum->num_linear_unconverged = unconverged;
     sum->initial_cost = s->initial_cost;
     sum->final_cost = s->x_cost;
     sum->ms_setup = s->ms_setup;
@@ -1054,12 +1108,13 @@ void gsfm_ra_default_options(gsfm_ra_options* o) {
   o->min_relative_decrease = 1e-3;
   o->min_lm_diagonal = 1e-6;
   o->max_lm_diagonal = 1e32;
-  o->linear_solver = GSFM_RA_SOLVER_PCG;
+  o->linear_solver = GSFM_RA_SOLVER_AUTO;
   o->pcg_max_iterations = 500;
   o->pcg_rtol = 1e-10;
   o->num_threads = 0;
   o->device = -1;
   o->verbose = 0;
+  o->n_gpus = 0;
 }
 
 int gsfm_ra_solver_create(const gsfm_ra_problem* problem, const gsfm_ra_options* options, gsfm_ra_solver** out) {
@@ -1160,6 +1215,51 @@ int gsfm_ra_solver_edge_range(const gsfm_ra_solver* s, uint64_t* e0, uint64_t* e
 }
 
 void* gsfm_ra_solver_cuda_stream(gsfm_ra_solver* s) { return s ? (void*)s->stream : nullptr; }
+
+int gsfm_ra_solver_info(const gsfm_ra_solver* s, int32_t* out) {
+  if (!s || !out) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
+  out[0] = s->opt.linear_solver;
+  out[1] = s->blk * 8 + 4;
+  out[2] = (int32_t)s->pk2.grid;
+  out[3] = kPcgBlock;
+  out[4] = (int32_t)s->keep8;
+  out[5] = s->world;
+  out[6] = s->graph_state == 1 ? 1 : 0;
+  out[7] = 0;
+  return 0;
+}
+
+int gsfm_ra_measure_stream(uint64_t bytes, int32_t repeats, int32_t device, double* gb_per_s) {
+  if (!gb_per_s || repeats < 1 || bytes < (1u << 20)) { set_error("bad argument (bytes >= 1 MiB, repeats >= 1)"); return GSFM_RA_ERR_INVALID; }
+  int dev = 0;
+  RA_TRY(select_device(device, &dev));
+  DeviceInfo* di = nullptr;
+  RA_TRY(device_info(dev, &di));
+  constexpr int kCB = Chunk<6>::kBytes;  // the chunk size of the symmetric 6-double records
+  const int smem = kPcgWarps * kStages2 * kCB + kPcgWarps * kStages2 * 8;
+  CUDA_TRY(cudaFuncSetAttribute(k_stream_probe<kCB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const uint32_t nchunks = (uint32_t)(bytes / kCB);
+  DevBuf<unsigned char> buf;
+  DevBuf<double> sink;
+  RA_TRY(buf.alloc((size_t)nchunks * kCB));
+  RA_TRY(sink.alloc(8));
+  CUDA_TRY(cudaMemset(buf.p, 0, (size_t)nchunks * kCB));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  const unsigned grid = (unsigned)(di->sm_count * kPcgBlocksPerSM);
+  for (int k = 0; k < 3; ++k) k_stream_probe<kCB><<<grid, kPcgBlock, smem>>>(buf.p, nchunks, sink.p);  // warm: the buffer is now L2 resident if it fits
+  CUDA_TRY(cudaEventRecord(e0));
+  for (int k = 0; k < repeats; ++k) k_stream_probe<kCB><<<grid, kPcgBlock, smem>>>(buf.p, nchunks, sink.p);
+  CUDA_TRY(cudaEventRecord(e1));
+  CUDA_TRY(cudaEventSynchronize(e1));
+  CUDA_TRY(cudaGetLastError());
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *gb_per_s = (double)nchunks * kCB * repeats / (ms * 1e-3) / 1e9;
+  return 0;
+}
 
 int gsfm_ra_solver_time_kernels(gsfm_ra_solver* s, int32_t repeats, double* out_ms) {
   if (!s || !out_ms || repeats < 1) { set_error("bad argument"); return GSFM_RA_ERR_INVALID; }
@@ -1439,7 +1539,8 @@ int gsfm_ra_eval_loss(const gsfm_ra_loss* loss, const double* s_in, uint64_t n, 
   DevLoss L;
   RA_TRY(make_dev_loss(loss, &L));
   if (n == 0) return 0;
-  DevBuf<double> ds, dout;
+  DevBuf<double> ds, dout, dtab;
+  RA_TRY(attach_loss_table(loss, &L, &dtab, nullptr));
   RA_TRY(ds.alloc(n));
   RA_TRY(dout.alloc(3 * n));
   CUDA_TRY(cudaMemcpy(ds.p, s_in, n * sizeof(double), cudaMemcpyHostToDevice));

@@ -35,6 +35,9 @@ constexpr int kPartStride = 10;    // per-task partial: diag(6) grad(3) cost(1)
 //   { double blk[kBlk][32]; uint32_t col[32]; }   128 B aligned,
 // so 32 lanes still read/write 256 contiguous bytes per block component (coalesced), and K2 can
 // pull a whole record into shared memory with ONE bulk async copy (TMA, cp.async.bulk).
+//   kBlk = 4: COMPACT form of the scalar-weight stencil (angle-axis types 4, 5, 7, 8): S = a I + sigma h h^T is a scaled
+//             identity plus a rank-one term, stored as (sigma a, h0, h1, h2) with a > 0 carrying the sign sigma -- the
+//             off-diagonal block is -S;                                                  1152 B per record (36 B / half-edge)
 //   kBlk = 6: symmetric off-diagonal block -S packed (00,01,02,11,12,22) -- every residual that is a function of the
 //             error rotation (types 2..8) is a Laplacian stencil in the body frame;  1664 B per record (52 B / half-edge)
 //   kBlk = 9: general row-major block (QUATERNION_NORM, ROTATION_MAT_FNORM);         2432 B per record (76 B / half-edge)
@@ -44,8 +47,32 @@ struct Rec {
   static constexpr int kBytes = kDoubles * 8;
   static constexpr int kColOffset = kBlk * 32;  // doubles: col[] starts here
 };
-constexpr int kStages = 4;                       // TMA ring depth per warp
-constexpr int spmv_smem_bytes(int blk) { return kWarpsPerBlock * kStages * (blk * 32 + 16) * 8 + kWarpsPerBlock * kStages * 8; }
+#ifdef GSFM_RA_NO_COMPACT
+constexpr bool kCompactScalarStencil = false;  // A/B builds: keep 6-double records for the scalar-weight stencil
+#else
+constexpr bool kCompactScalarStencil = true;
+#endif
+constexpr int kStages = 4;                       // K1: TMA ring depth per warp (one input record per bulk copy)
+// K2-class kernels (k_spmv, k_pcg_persistent).  Measured on B200 (profiles/r02b_*): the TMA unit of an SM retires ~25 bulk
+// copies per microsecond whatever their size, so the matrix stream moves in CHUNKS of several consecutive records per bulk
+// copy (3.3 - 3.5 KB), three chunks in flight per warp; and a grid barrier costs ~3 us with 148 participants against ~4 us
+// with 296, so these kernels run ONE block of 16 warps per SM.  (-DGSFM_RA_PCG_WARPS=8: two blocks of 8 warps, A/B builds.)
+#ifndef GSFM_RA_PCG_WARPS
+#define GSFM_RA_PCG_WARPS 16
+#endif
+constexpr int kPcgWarps = GSFM_RA_PCG_WARPS;
+constexpr int kPcgBlock = kPcgWarps * 32;
+constexpr int kPcgBlocksPerSM = 16 / kPcgWarps;
+constexpr int kMaxWarpsPerBlock = 16;
+constexpr int kStages2 = 3;                      // K2: chunks in flight per warp
+constexpr int chunk_recs(int blk) { return blk == 4 ? 3 : (blk == 6 ? 2 : 1); }   // records per bulk copy
+template <int kBlk>
+struct Chunk {
+  static constexpr int kRecs = chunk_recs(kBlk);
+  static constexpr int kDoubles = kRecs * Rec<kBlk>::kDoubles;
+  static constexpr int kBytes = kDoubles * 8;
+};
+constexpr int spmv_smem_bytes(int blk) { return kPcgWarps * kStages2 * chunk_recs(blk) * (blk * 32 + 16) * 8 + kPcgWarps * kStages2 * 8; }
 
 __device__ __host__ __forceinline__ size_t blk_index(uint64_t h, int k, int rec_doubles) { return (size_t)(h >> 5) * rec_doubles + (size_t)k * 32 + (h & 31); }
 
@@ -135,7 +162,7 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 // totals in `tot` (valid in thread 0 only).
 template <int NV>
 __device__ bool grid_sum(double (&v)[NV], double* slots, unsigned* counter, double (&tot)[NV]) {
-  __shared__ double sm[NV][kWarpsPerBlock];
+  __shared__ double sm[NV][kMaxWarpsPerBlock];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -148,7 +175,7 @@ __device__ bool grid_sum(double (&v)[NV], double* slots, unsigned* counter, doub
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       double s = 0.0;
-      for (int w = 0; w < kWarpsPerBlock; ++w) s += sm[k][w];
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sm[k][w];
       slots[(size_t)blockIdx.x * NV + k] = s;
     }
     __threadfence();
@@ -228,24 +255,25 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
 }
 
 struct WarpPipe {
-  double* ring;    // this warp's kStages records in shared memory
-  uint64_t* bars;  // this warp's kStages mbarriers
-  uint32_t pos;    // records consumed since init: ring slot = pos % kStages, phase = (pos / kStages) & 1
+  double* ring;    // this warp's ring of stages in shared memory
+  uint64_t* bars;  // this warp's mbarriers, one per stage
+  uint32_t pos;    // bulk copies consumed since init: ring slot = pos % stages, phase = (pos / stages) & 1
 };
 
-template <int kRecBytes>
+// Shared memory of a block: [warps][kNumStages][kStageBytes] rings, then [warps][kNumStages] mbarriers.
+template <int kStageBytes, int kNumStages>
 __device__ __forceinline__ void pipe_init_bytes(WarpPipe& wp, unsigned char* smem) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  wp.ring = reinterpret_cast<double*>(smem + (size_t)warp * kStages * kRecBytes);
-  wp.bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWarpsPerBlock * kStages * kRecBytes) + warp * kStages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  wp.ring = reinterpret_cast<double*>(smem + (size_t)warp * kNumStages * kStageBytes);
+  wp.bars = reinterpret_cast<uint64_t*>(smem + (size_t)nwarps * kNumStages * kStageBytes) + warp * kNumStages;
   wp.pos = 0;
   if (lane == 0) {
-    for (int st = 0; st < kStages; ++st) mbar_init(&wp.bars[st], 1);
+    for (int st = 0; st < kNumStages; ++st) mbar_init(&wp.bars[st], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
 }
 template <int kBlk>
-__device__ __forceinline__ void pipe_init(WarpPipe& wp, unsigned char* smem) { pipe_init_bytes<Rec<kBlk>::kBytes>(wp, smem); }
+__device__ __forceinline__ void pipe_init(WarpPipe& wp, unsigned char* smem) { pipe_init_bytes<Chunk<kBlk>::kBytes, kStages2>(wp, smem); }
 
 }  // namespace

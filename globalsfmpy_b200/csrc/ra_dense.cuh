@@ -22,6 +22,12 @@ constexpr int kNB = 32;
 // Entry (r, c) of the stored off-diagonal block of half-edge h (blk = 6: packed symmetric; 9: row-major).
 __device__ __forceinline__ double blk_entry(const double* recs, uint64_t h, int blk, int r, int c) {
   int k;
+  if (blk == 4) {  // compact scalar-weight stencil: -( |c0| delta_rc + sign(c0) h_r h_c )
+    const int rd = blk * 32 + 16;
+    const double c0 = recs[blk_index(h, 0, rd)];
+    const double hh = recs[blk_index(h, 1 + r, rd)] * recs[blk_index(h, 1 + c, rd)];
+    return -((r == c ? fabs(c0) : 0.0) + (signbit(c0) ? -hh : hh));
+  }
   if (blk == 6) { const int a = r < c ? r : c, b2 = r < c ? c : r; k = a * 3 - a * (a - 1) / 2 + (b2 - a); }
   else k = 3 * r + c;
   return recs[blk_index(h, k, blk * 32 + 16)];

@@ -69,6 +69,7 @@ template <bool kWriteBlocks, int kResidual, bool kScalarU, int kLoss>
 // two blocks (16 warps) per SM: three (<= 80 registers) spill and measure 10 % slower (profiles/r01_g_microbench.txt item 5)
 __global__ void __launch_bounds__(kBlock, 2) k_edges(const K1Args A) {
   constexpr int kU = (kScalarU || kResidual == 1) ? 1 : 6;
+  constexpr bool kCompact = kCompactScalarStencil && kScalarU && kResidual == 0;  // 4-double block records (see Rec<4>)
   constexpr int kRD = (4 + kU) * 32 + 32;  // doubles per input record
   constexpr int kRB = kRD * 8;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_edges(const K1Args A) {
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (gw >= A.num_warps) return;
   WarpPipe wp;
-  pipe_init_bytes<kRB>(wp, smem_raw);
+  pipe_init_bytes<kRB, kStages>(wp, smem_raw);
   const uint64_t lo = (uint64_t)gw * A.warp_span, hi = min(A.H, lo + A.warp_span);
   const uint32_t t0 = A.warp_seg_ptr[gw], t1 = A.warp_seg_ptr[gw + 1];
   const uint32_t nrec = (uint32_t)((hi - lo + 31) >> 5);
@@ -140,8 +141,14 @@ __global__ void __launch_bounds__(kBlock, 2) k_edges(const K1Args A) {
       cur[6] = sgn * et.v[0]; cur[7] = sgn * et.v[1]; cur[8] = sgn * et.v[2];
       cur[kAcc - 1] = row_is_j ? 0.0 : 0.5 * et.rho[0];
       if (h < hi) {
+        if (kCompact) {
+          A.val[blk_index(h, 0, Rec<4>::kDoubles)] = et.ca;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) A.val[blk_index(h, k, Rec<6>::kDoubles)] = -et.S[k];
+          for (int k = 0; k < 3; ++k) A.val[blk_index(h, 1 + k, Rec<4>::kDoubles)] = et.h[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) A.val[blk_index(h, k, Rec<6>::kDoubles)] = -et.S[k];
+        }
       }
     } else {
       cur[0] = row_is_j ? 0.0 : 0.5 * et.rho[0];

@@ -98,29 +98,31 @@ template <int kBlk, typename Finish>
 __device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restrict__ recs, uint64_t lo, uint64_t hi, uint32_t t0, uint32_t t1,
                                             const uint32_t* __restrict__ seg_begin, const uint32_t* __restrict__ seg_len, const double* x4,
                                             bool nogather, uint32_t keep8, Finish&& finish) {
-  constexpr int kRD = Rec<kBlk>::kDoubles;
+  constexpr int kRD = Rec<kBlk>::kDoubles, kCR = Chunk<kBlk>::kRecs, kCD = Chunk<kBlk>::kDoubles;
   const int lane = threadIdx.x & 31;
   const uint32_t nrec = (uint32_t)((hi - lo + 31) >> 5);
+  const uint32_t nchunk = (nrec + kCR - 1) / kCR;  // bulk copies of this range: kCR consecutive records each (the last may be short)
   const uint32_t base = wp.pos;
   const double* src = recs + (size_t)(lo >> 5) * kRD;
   uint64_t pol_keep = 0, pol_stream = 0;
   if (keep8) { pol_keep = l2_policy_evict_last(); pol_stream = l2_policy_evict_first(); }
-  const uint32_t rec0 = (uint32_t)(lo >> 5);
-  auto issue = [&](uint32_t c) {
+  const uint32_t chunk0 = (uint32_t)(lo >> 5) / kCR;
+  auto issue = [&](uint32_t k) {
     if (lane == 0) {
-      const uint32_t st = (base + c) % kStages;
-      mbar_expect_tx(&wp.bars[st], Rec<kBlk>::kBytes);
+      const uint32_t st = (base + k) % kStages2;
+      const uint32_t bytes = min((uint32_t)kCR, nrec - k * kCR) * (uint32_t)Rec<kBlk>::kBytes;
+      mbar_expect_tx(&wp.bars[st], bytes);
       if (keep8)
-        tma_load_bulk_hint(wp.ring + (size_t)st * kRD, src + (size_t)c * kRD, Rec<kBlk>::kBytes, &wp.bars[st],
-                           ((rec0 + c) & 7u) < keep8 ? pol_keep : pol_stream);
+        tma_load_bulk_hint(wp.ring + (size_t)st * kCD, src + (size_t)k * kCD, bytes, &wp.bars[st], ((chunk0 + k) & 7u) < keep8 ? pol_keep : pol_stream);
       else
-        tma_load_bulk(wp.ring + (size_t)st * kRD, src + (size_t)c * kRD, Rec<kBlk>::kBytes, &wp.bars[st]);
+        tma_load_bulk(wp.ring + (size_t)st * kCD, src + (size_t)k * kCD, bytes, &wp.bars[st]);
     }
   };
-  auto wait_rec = [&](uint32_t c) -> const double* {
-    const uint32_t p = base + c, st = p % kStages;
-    mbar_wait(&wp.bars[st], (p / kStages) & 1u);
-    return wp.ring + (size_t)st * kRD;
+  // first record of chunk k, once its bulk copy has landed
+  auto wait_chunk = [&](uint32_t k) -> const double* {
+    const uint32_t p = base + k, st = p % kStages2;
+    mbar_wait(&wp.bars[st], (p / kStages2) & 1u);
+    return wp.ring + (size_t)st * kCD;
   };
   auto gather = [&](const double* rec, uint64_t h, double& x0, double& x1, double& x2) {
     uint32_t col = reinterpret_cast<const uint32_t*>(rec + Rec<kBlk>::kColOffset)[lane] & ~kSideBit;
@@ -129,12 +131,12 @@ __device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restri
     const double4 xv = reinterpret_cast<const double4*>(x4)[col];
     x0 = xv.x; x1 = xv.y; x2 = xv.z;
   };
-  for (uint32_t c = 0; c < nrec && c < (uint32_t)kStages; ++c) issue(c);
-  if (nrec == 0 || t0 == t1) { wp.pos = base + nrec; return; }
+  for (uint32_t k = 0; k < nchunk && k < (uint32_t)kStages2; ++k) issue(k);
+  if (nrec == 0 || t0 == t1) { wp.pos = base + nchunk; return; }
   uint32_t t = t0;
   uint64_t sb = seg_begin[t], se = sb + seg_len[t];
   double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-  const double* rec = wait_rec(0);
+  const double* rec = wait_chunk(0);
   double x0, x1, x2;
   gather(rec, lo + lane, x0, x1, x2);
   for (uint32_t c = 0; c < nrec; ++c) {
@@ -142,9 +144,21 @@ __device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restri
     // prefetch the next record's gather
     const double* rec_n = nullptr;
     double n0 = 0.0, n1 = 0.0, n2 = 0.0;
-    if (c + 1 < nrec) { rec_n = wait_rec(c + 1); gather(rec_n, ce + lane, n0, n1, n2); }
+    if (c + 1 < nrec) {
+      rec_n = ((c + 1) % kCR == 0) ? wait_chunk((c + 1) / kCR) : rec + kRD;
+      gather(rec_n, ce + lane, n0, n1, n2);
+    }
     double v0, v1, v2;
-    if (kBlk == 6) {
+    if (kBlk == 4) {
+      // -S x with S = |c0| I + sign(c0) h h^T
+      const double c0 = rec[lane], h0 = rec[32 + lane], h1 = rec[64 + lane], h2 = rec[96 + lane];
+      const double t = h0 * x0 + h1 * x1 + h2 * x2;
+      const double a = fabs(c0);
+      const double st = __longlong_as_double(__double_as_longlong(t) ^ (__double_as_longlong(c0) & (long long)0x8000000000000000ull));
+      v0 = -(a * x0 + st * h0);
+      v1 = -(a * x1 + st * h1);
+      v2 = -(a * x2 + st * h2);
+    } else if (kBlk == 6) {
       const double b0 = rec[lane], b1 = rec[32 + lane], b2 = rec[64 + lane], b3 = rec[96 + lane], b4 = rec[128 + lane], b5 = rec[160 + lane];
       v0 = b0 * x0 + b1 * x1 + b2 * x2;
       v1 = b1 * x0 + b3 * x1 + b4 * x2;
@@ -154,9 +168,11 @@ __device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restri
       v1 = rec[96 + lane] * x0 + rec[128 + lane] * x1 + rec[160 + lane] * x2;
       v2 = rec[192 + lane] * x0 + rec[224 + lane] * x1 + rec[256 + lane] * x2;
     }
-    // this record's slot can be refilled as soon as every lane has read it
-    __syncwarp();
-    if (c + kStages < nrec) issue(c + kStages);
+    // a chunk's stage can be refilled as soon as every lane has read its last record
+    if ((c + 1) % kCR == 0 || c + 1 == nrec) {
+      __syncwarp();
+      if (c / kCR + kStages2 < nchunk) issue(c / kCR + kStages2);
+    }
     while (true) {
       if (h >= sb && h < se) { y0 += v0; y1 += v1; y2 += v2; }
       if (se > ce) break;  // the segment continues in the next record
@@ -170,11 +186,41 @@ __device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restri
     rec = rec_n; x0 = n0; x1 = n1; x2 = n2;
     if (t == t1) break;
   }
-  wp.pos = base + nrec;
+  wp.pos = base + nchunk;
+}
+
+// Measurement aid (gsfm_ra_measure_stream): the K2 ring alone -- every warp pulls its share of `nchunks` chunks of kChunkBytes
+// through the same kStages2-deep bulk-copy pipeline and adds one word per lane and 256 bytes, no gather, no reduction.
+template <int kChunkBytes>
+__global__ void __launch_bounds__(kPcgBlock, kPcgBlocksPerSM) k_stream_probe(const unsigned char* __restrict__ src, uint32_t nchunks, double* sink) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  WarpPipe wp;
+  pipe_init_bytes<kChunkBytes, kStages2>(wp, smem_raw);
+  const int lane = threadIdx.x & 31;
+  const uint32_t nw = (gridDim.x * blockDim.x) >> 5, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t per = (nchunks + nw - 1) / nw, lo = gw * per, n = lo >= nchunks ? 0u : min(per, nchunks - lo);
+  auto issue = [&](uint32_t k) {
+    if (lane == 0 && k < n) {
+      mbar_expect_tx(&wp.bars[k % kStages2], kChunkBytes);
+      tma_load_bulk(reinterpret_cast<unsigned char*>(wp.ring) + (size_t)(k % kStages2) * kChunkBytes, src + (size_t)(lo + k) * kChunkBytes, kChunkBytes,
+                    &wp.bars[k % kStages2]);
+    }
+  };
+  for (uint32_t k = 0; k < (uint32_t)kStages2; ++k) issue(k);
+  double acc = 0.0;
+  for (uint32_t k = 0; k < n; ++k) {
+    mbar_wait(&wp.bars[k % kStages2], (k / kStages2) & 1u);
+    const double* r = wp.ring + (size_t)(k % kStages2) * (kChunkBytes / 8);
+#pragma unroll
+    for (int j = 0; j < kChunkBytes / 256; ++j) acc += r[j * 32 + lane];
+    __syncwarp();
+    issue(k + kStages2);
+  }
+  if (acc == 123.456) sink[0] = acc;
 }
 
 template <int kBlk>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kPcgBlock, kPcgBlocksPerSM)
 k_spmv(uint32_t num_warps, uint64_t H, uint32_t warp_span, const uint32_t* __restrict__ warp_seg_ptr, const uint32_t* __restrict__ task_begin,
        const uint32_t* __restrict__ task_len, const double* __restrict__ recs, const double* __restrict__ x4, double* __restrict__ ypart,
        const DevScalars* sc, int check_done, uint32_t keep8) {
@@ -396,7 +442,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // (Measured alternative, profiles/r01_h: publishing {data | sequence} words and polling all blocks' slots instead of
 // grid.sync is slower -- 296 pollers x 296 slots of dependent L2 round trips.)
 __device__ __forceinline__ void grid_bar_sum2(cg::grid_group& grid, unsigned long long* bar_slots, unsigned& seq, double v0, double v1,
-                                              double* sm_red /*[2*kWarpsPerBlock + 2]*/, double& out0, double& out1) {
+                                              double* sm_red /*[2*kMaxWarpsPerBlock + 2]*/, double& out0, double& out1) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   v0 = warp_sum(v0); v1 = warp_sum(v1);
   if (lane == 0) { sm_red[2 * warp] = v0; sm_red[2 * warp + 1] = v1; }
@@ -405,7 +451,7 @@ __device__ __forceinline__ void grid_bar_sum2(cg::grid_group& grid, unsigned lon
   double* set = reinterpret_cast<double*>(bar_slots) + (size_t)(seq & 1u) * 2 * gridDim.x;
   if (threadIdx.x == 0) {
     double b0 = 0.0, b1 = 0.0;
-    for (int w = 0; w < kWarpsPerBlock; ++w) { b0 += sm_red[2 * w]; b1 += sm_red[2 * w + 1]; }
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { b0 += sm_red[2 * w]; b1 += sm_red[2 * w + 1]; }
     __stcg(set + 2 * (size_t)blockIdx.x, b0); __stcg(set + 2 * (size_t)blockIdx.x + 1, b1);
   }
   grid.sync();
@@ -413,10 +459,10 @@ __device__ __forceinline__ void grid_bar_sum2(cg::grid_group& grid, unsigned lon
     double s0 = 0.0, s1 = 0.0;
     for (unsigned b = lane; b < gridDim.x; b += 32) { s0 += __ldcg(set + 2 * (size_t)b); s1 += __ldcg(set + 2 * (size_t)b + 1); }
     s0 = warp_sum(s0); s1 = warp_sum(s1);
-    if (lane == 0) { sm_red[2 * kWarpsPerBlock] = s0; sm_red[2 * kWarpsPerBlock + 1] = s1; }
+    if (lane == 0) { sm_red[2 * kMaxWarpsPerBlock] = s0; sm_red[2 * kMaxWarpsPerBlock + 1] = s1; }
   }
   __syncthreads();
-  out0 = sm_red[2 * kWarpsPerBlock]; out1 = sm_red[2 * kWarpsPerBlock + 1];
+  out0 = sm_red[2 * kMaxWarpsPerBlock]; out1 = sm_red[2 * kMaxWarpsPerBlock + 1];
 }
 
 // Row i once its off-diagonal sum (y0,y1,y2) is complete: s_i = D_i z_i + y, store, inner products.
@@ -529,12 +575,12 @@ __device__ __forceinline__ void exchange_finish(const PcgParams& P, cg::grid_gro
 }
 
 template <int kBlk>
-__global__ void __launch_bounds__(kBlock) k_pcg_persistent(PcgParams P) {
+__global__ void __launch_bounds__(kPcgBlock, kPcgBlocksPerSM) k_pcg_persistent(PcgParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cg::grid_group grid = cg::this_grid();
   WarpPipe wp;
   pipe_init<kBlk>(wp, smem_raw);
-  __shared__ double sm_red[2 * kWarpsPerBlock + 2];
+  __shared__ double sm_red[2 * kMaxWarpsPerBlock + 2];
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
   unsigned bseq = (unsigned)P.sc->bar_seq;  // barrier sequence number, continues across launches
   double bb;

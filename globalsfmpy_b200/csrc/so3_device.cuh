@@ -16,6 +16,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 
 namespace gsfm {
 
@@ -161,10 +162,18 @@ struct DevLoss {
   double gamma_k;             // upper_incomplete_gamma_of_k
   double weight_zero;         // one_over_sigma * (tgamma((nu-1)/2) - gamma_k)
   double expo;                // nu/2 - 1.5
+  // ComposedLoss (scripts/loss_functions.py:250-265): rho(s) = f(g(s)); the fields above describe f, these g
+  // (a closed-form kind below MAGSAC; composed == 0: g(s) = s)
+  int composed;
+  int inner_kind;
+  double ip0, ip1, iscale, isq0, iinv_sq0;
+  // kLossTabulated: (rho, rho', rho'') of an arbitrary loss object at the knots 0, 2^(min_exp+o) (1 + m / 2^log2_per_octave), ...
+  const double* table;
+  int tab_min_exp, tab_octaves, tab_log2_per_octave, tab_rows;
 };
 
 enum { kLossTrivial = 0, kLossHuber, kLossSoftLOne, kLossCauchy, kLossArctan, kLossTolerant, kLossTukey,
-       kLossLOneHalf, kLossLTwo, kLossGemanMcClure, kLossMagsac3, kLossMagsac4, kLossMagsac9 };
+       kLossLOneHalf, kLossLTwo, kLossGemanMcClure, kLossMagsac3, kLossMagsac4, kLossMagsac9, kLossTabulated };
 
 // stored_gamma_values{nu}[index] = Gamma((nu-1)/2, index/1000), closed forms
 __host__ __device__ inline double gamma_table(int nu, double x) {
@@ -207,50 +216,91 @@ __host__ __device__ inline void magsac_loss(const DevLoss& L, double s_in, doubl
   }
 }
 
-// kKind >= 0 fixes the loss at compile time (the switch folds away); kKind < 0 dispatches on L.kind.
-template <int kKind = -1>
-__host__ __device__ inline void eval_loss(const DevLoss& L, double s, double* out) {
-  switch (kKind < 0 ? L.kind : kKind) {
+// Quintic Hermite interpolation of a tabulated loss (include/gsfm_ra.h, GSFM_RA_LOSS_TABULATED): rho from the polynomial
+// matching (rho, rho', rho'') at the two enclosing knots, rho' and rho'' by differentiating that polynomial.  The knot index
+// comes straight from the exponent and the leading mantissa bits of s.
+__host__ __device__ inline void tabulated_loss(const DevLoss& L, double s, double* out) {
+  const double* T = L.table;
+  if (!(s > 0.0)) { out[0] = T[0]; out[1] = T[1]; out[2] = T[2]; return; }
+#ifdef __CUDA_ARCH__
+  const long long bits = __double_as_longlong(s);
+#else
+  long long bits; memcpy(&bits, &s, 8);
+#endif
+  const int e = (int)((bits >> 52) & 0x7ff) - 1023;
+  const int P = L.tab_log2_per_octave, M = 1 << P;
+  int idx;
+  double s0, h;
+  if (e < L.tab_min_exp) { idx = 0; s0 = 0.0; h = ldexp(1.0, L.tab_min_exp); }
+  else if (e >= L.tab_min_exp + L.tab_octaves) {  // beyond the last knot: linear continuation
+    const double* last = T + 3 * (size_t)(L.tab_rows - 1);
+    const double sl = ldexp(1.0, L.tab_min_exp + L.tab_octaves);
+    out[0] = last[0] + last[1] * (s - sl); out[1] = last[1]; out[2] = 0.0;
+    return;
+  } else {
+    const int m = (int)((bits >> (52 - P)) & (long long)(M - 1));
+    idx = 1 + (e - L.tab_min_exp) * M + m;
+    h = ldexp(1.0, e - P);
+    s0 = ldexp(1.0, e) + m * h;
+  }
+  const double* A = T + 3 * (size_t)idx;
+  const double f0 = A[0], d0 = A[1] * h, c0 = A[2] * h * h, f1 = A[3], d1 = A[4] * h, c1 = A[5] * h * h;
+  const double t = (s - s0) / h, t2 = t * t, t3 = t2 * t, t4 = t3 * t, t5 = t4 * t;
+  const double H0 = 1.0 - 10.0 * t3 + 15.0 * t4 - 6.0 * t5, H1 = t - 6.0 * t3 + 8.0 * t4 - 3.0 * t5, H2 = 0.5 * t2 - 1.5 * t3 + 1.5 * t4 - 0.5 * t5;
+  const double H3 = 10.0 * t3 - 15.0 * t4 + 6.0 * t5, H4 = -4.0 * t3 + 7.0 * t4 - 3.0 * t5, H5 = 0.5 * t3 - t4 + 0.5 * t5;
+  const double G0 = -30.0 * t2 + 60.0 * t3 - 30.0 * t4, G1 = 1.0 - 18.0 * t2 + 32.0 * t3 - 15.0 * t4, G2 = t - 4.5 * t2 + 6.0 * t3 - 2.5 * t4;
+  const double G3 = -G0, G4 = -12.0 * t2 + 28.0 * t3 - 15.0 * t4, G5 = 1.5 * t2 - 4.0 * t3 + 2.5 * t4;
+  const double K0 = -60.0 * t + 180.0 * t2 - 120.0 * t3, K1 = -36.0 * t + 96.0 * t2 - 60.0 * t3, K2 = 1.0 - 9.0 * t + 18.0 * t2 - 10.0 * t3;
+  const double K3 = -K0, K4 = -24.0 * t + 84.0 * t2 - 60.0 * t3, K5 = 3.0 * t - 12.0 * t2 + 10.0 * t3;
+  out[0] = f0 * H0 + d0 * H1 + c0 * H2 + f1 * H3 + d1 * H4 + c1 * H5;
+  out[1] = (f0 * G0 + d0 * G1 + c0 * G2 + f1 * G3 + d1 * G4 + c1 * G5) / h;
+  out[2] = (f0 * K0 + d0 * K1 + c0 * K2 + f1 * K3 + d1 * K4 + c1 * K5) / (h * h);
+}
+
+// The closed-form losses below MAGSAC, parameters passed explicitly (outer and inner function of a composition share it).
+// sq0 = p0^2 and inv_sq0 = 1 / p0^2, rounded exactly as the reference's formulas would compute them.
+__host__ __device__ inline void eval_simple_loss(int kind, double p0, double p1, double sq0, double inv_sq0, double s, double* out) {
+  switch (kind) {
     case kLossTrivial: out[0] = s; out[1] = 1.0; out[2] = 0.0; break;
     case kLossHuber: {
-      const double a = L.p0, b = L.sq0;
+      const double a = p0, b = sq0;
       if (s > b) { const double r = sqrt(s); out[0] = 2.0 * a * r - b; out[1] = fmax(a / r, DBL_MIN); out[2] = -out[1] / (2.0 * s); }
       else { out[0] = s; out[1] = 1.0; out[2] = 0.0; }
       break;
     }
     case kLossSoftLOne: {
-      const double b = L.sq0, c = L.inv_sq0;
+      const double b = sq0, c = inv_sq0;
       const double sum = 1.0 + s * c, tmp = sqrt(sum);
       out[0] = 2.0 * b * (tmp - 1.0); out[1] = fmax(1.0 / tmp, DBL_MIN); out[2] = -(c * out[1]) / (2.0 * sum);
       break;
     }
     case kLossCauchy: {
-      const double b = L.sq0, c = L.inv_sq0;
+      const double b = sq0, c = inv_sq0;
       const double sum = 1.0 + s * c, inv = 1.0 / sum;
       out[0] = b * log(sum); out[1] = fmax(inv, DBL_MIN); out[2] = -c * (inv * inv);
       break;
     }
     case kLossArctan: {
-      const double a = L.p0, b = 1.0 / (a * a);
+      const double a = p0, b = 1.0 / (a * a);
       const double sum = 1.0 + s * s * b, inv = 1.0 / sum;
       out[0] = a * atan2(s, a); out[1] = fmax(inv, DBL_MIN); out[2] = -2.0 * s * b * (inv * inv);
       break;
     }
     case kLossTolerant: {
-      const double a = L.p0, b = L.p1, c = b * log(1.0 + exp(-a / b));
+      const double a = p0, b = p1, c = b * log(1.0 + exp(-a / b));
       const double x = (s - a) / b;
       if (x > 36.7) { out[0] = s - a - c; out[1] = 1.0; out[2] = 0.0; }
       else { const double e_x = exp(x); out[0] = b * log(1.0 + e_x) - c; out[1] = fmax(e_x / (1.0 + e_x), DBL_MIN); out[2] = 0.5 / (b * (1.0 + cosh(x))); }
       break;
     }
     case kLossTukey: {
-      const double a2 = L.p0 * L.p0;
+      const double a2 = p0 * p0;
       if (s <= a2) { const double v = 1.0 - s / a2, v2 = v * v; out[0] = a2 / 6.0 * (1.0 - v2 * v); out[1] = 0.5 * v2; out[2] = -1.0 / a2 * v; }
       else { out[0] = a2 / 6.0; out[1] = 0.0; out[2] = 0.0; }
       break;
     }
     case kLossLOneHalf: {
-      const double a = L.p0, sa = sqrt(a);
+      const double a = p0, sa = sqrt(a);
       out[0] = 2.0 * a * sa * pow(s, 0.25);
       if (s < 0.01) s = 0.01;
       out[1] = 0.5 * pow(a, -1.5) * pow(s, -0.75);
@@ -258,20 +308,41 @@ __host__ __device__ inline void eval_loss(const DevLoss& L, double s, double* ou
       break;
     }
     case kLossLTwo: {
-      const double a2 = L.p0 * L.p0;
+      const double a2 = p0 * p0;
       out[0] = s * s / (a2 * 2.0); out[1] = s / a2; out[2] = 1.0 / a2;
       break;
     }
     case kLossGemanMcClure: {
-      const double a2 = L.p0 * L.p0, sg = L.p1;
+      const double a2 = p0 * p0, sg = p1;
       const double d = s / a2 + sg;
       out[0] = a2 * sg * s / (2.0 * (s + a2 * sg));
       out[1] = (sg * sg) / (2.0 * d * d);
       out[2] = -(sg * sg) / (a2 * d * d * d);
       break;
     }
-    case kLossMagsac3: case kLossMagsac4: case kLossMagsac9: magsac_loss(L, s, out); break;
     default: out[0] = out[1] = out[2] = NAN;
+  }
+}
+
+// kKind >= 0 fixes the loss at compile time (the switch folds away; plain, unscaled, uncomposed losses only -- the host picks
+// such an instantiation only then); kKind < 0 dispatches on L.kind and handles composition.
+template <int kKind = -1>
+__host__ __device__ inline void eval_loss(const DevLoss& L, double s, double* out) {
+  double og[3] = {s, 1.0, 0.0};
+  const bool comp = kKind < 0 && L.composed != 0;
+  if (comp) {
+    eval_simple_loss(L.inner_kind, L.ip0, L.ip1, L.isq0, L.iinv_sq0, s, og);
+    if (L.iscale != 1.0) { og[0] *= L.iscale; og[1] *= L.iscale; og[2] *= L.iscale; }
+    s = og[0];
+  }
+  const int kind = kKind < 0 ? L.kind : kKind;
+  if (kind >= kLossMagsac3 && kind <= kLossMagsac9) magsac_loss(L, s, out);
+  else if (kind == kLossTabulated) tabulated_loss(L, s, out);
+  else eval_simple_loss(kind, L.p0, L.p1, L.sq0, L.inv_sq0, s, out);
+  if (comp) {  // f(g(s)): f' g',  f'' g'^2 + f' g''
+    const double f1 = out[1], f2 = out[2];
+    out[1] = f1 * og[1];
+    out[2] = f2 * og[1] * og[1] + f1 * og[2];
   }
   if (L.scale != 1.0 && L.scale != 0.0) { out[0] *= L.scale; out[1] *= L.scale; out[2] *= L.scale; }
 }
@@ -295,6 +366,10 @@ struct EdgeTerms {
   double S[6];
   double v[3];
   double rho[3];
+  // scalar-weight stencil only (kStencilOnly && kScalarU && kResidual == 0): S = |ca| I + sign(ca) h h^T, the 4-double
+  // form the compact block records store (ca carries the sign of the rank-one term; |ca| > 0 whenever rho' > 0 because
+  // the eigenvalue of Jl^-T Jl^-1 orthogonal to e is (theta/2)^2 / sin^2(theta/2) >= 1)
+  double ca, h[3];
 };
 
 // Ceres Corrector's kappa (zero for every loss with rho'' <= 0).
@@ -340,6 +415,9 @@ __host__ __device__ inline void edge_terms(const Q4& qi, const Q4& qj, const Q4&
     o.S[0] = a + bf0 * f0; o.S[1] = bf0 * f1; o.S[2] = bf0 * f2;
     o.S[3] = a + bf1 * f1; o.S[4] = bf1 * f2; o.S[5] = a + bf2 * f2;
     o.v[0] = rw * f0; o.v[1] = rw * f1; o.v[2] = rw * f2;
+    const double hs = sqrt(fabs(b));
+    o.ca = copysign(a, b);
+    o.h[0] = hs * f0; o.h[1] = hs * f1; o.h[2] = hs * f2;
     return;
   }
   double M[9];                                           // d r / d(left perturbation of E) before the weight

@@ -176,6 +176,13 @@ def read_1dsfm(dataset_directory, with_matches=True):
                 num_verified_matches=_take(m, P, np.int64) if with_matches else None)
 
 
+def measure_stream(nbytes, repeats=20, device=-1):
+    """GB/s of the K2 record stream alone over `nbytes` of device memory (gsfm_ra_measure_stream)."""
+    out = C.c_double(0.0)
+    capi.check(capi.lib().gsfm_ra_measure_stream(int(nbytes), int(repeats), int(device), C.byref(out)))
+    return out.value
+
+
 def _summary(trace_capacity):
     s = capi.Summary()
     trace = (capi.Iteration * max(1, trace_capacity))()
@@ -283,6 +290,13 @@ class Solver:
         out = np.zeros(4)
         capi.check(capi.lib().gsfm_ra_solver_time_kernels(self._h, int(repeats), capi.ptr(out)))
         return dict(k1=out[0], k1c=out[1], spmv=out[2], pcg_iteration=out[3])
+
+    def info(self):
+        """What the solver resolved at build time (gsfm_ra_solver_info)."""
+        out = (C.c_int32 * 8)()
+        capi.check(capi.lib().gsfm_ra_solver_info(self._h, out))
+        return dict(linear_solver=out[0], stored_bytes_per_half_edge=out[1], pcg_grid=out[2], pcg_block=out[3], l2_keep8=out[4],
+                    world=out[5], cuda_graphs=bool(out[6]))
 
     def iterate(self, num_iterations, trace_capacity=0):
         s, trace = _summary(trace_capacity)

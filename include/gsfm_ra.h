@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GSFM_RA_ABI_VERSION 1
+#define GSFM_RA_ABI_VERSION 2
 
 typedef enum {
   GSFM_RA_OK = 0,
@@ -71,16 +71,38 @@ typedef enum {
   GSFM_RA_LOSS_GEMANMCCLURE = 9,  /* :239  p[0]=a p[1]=sigma2                  */
   GSFM_RA_LOSS_MAGSAC3 = 10,      /* :285  p[0]=sigma, flags bit0 = inverse    */
   GSFM_RA_LOSS_MAGSAC4 = 11,      /* :344                                      */
-  GSFM_RA_LOSS_MAGSAC9 = 12       /* :402                                      */
+  GSFM_RA_LOSS_MAGSAC9 = 12,      /* :402                                      */
+  GSFM_RA_LOSS_TABULATED = 13     /* ANY LossFunction object (bind_src/GlobalSfMpy.cpp:33-65 accepts every Python subclass):
+                                     its Evaluate sampled by the host into `table`, see below                          */
 } gsfm_ra_loss_kind;
 
 #define GSFM_RA_LOSS_FLAG_INVERSE 1u
 
+/* A loss is  s -> scale * f(g(s))  (ComposedLoss, loss_functions.py:250-265, and ScaledLoss, :267-281):
+ *   kind/flags/p        the OUTER function f
+ *   inner_*             the INNER function g; a zero-initialised struct has inner_kind = GSFM_RA_LOSS_TRIVIAL and
+ *                       inner_scale 0 (= 1), i.e. g(s) = s: no composition
+ *   scale               ScaledLoss factor applied to the whole (0 = 1)
+ * GSFM_RA_LOSS_TABULATED (as f; g must be trivial): rho, rho', rho'' of an arbitrary loss object sampled by the host at the knots
+ *   s_0 = 0,   s_{1 + o * per_octave + m} = 2^(min_exp + o) * (1 + m / per_octave),   o < octaves, m < per_octave,
+ *   plus the closing knot 2^(min_exp + octaves)  =>  table holds 2 + octaves * per_octave rows of 3 doubles.
+ * The device interpolates rho with the quintic Hermite polynomial of (rho, rho', rho'') at the two enclosing knots and
+ * differentiates that polynomial for rho', rho'' (consistent derivatives); beyond the last knot rho is continued linearly.
+ * per_octave must be a power of two <= 4096.                                                                              */
 typedef struct {
   int32_t kind;     /* gsfm_ra_loss_kind                                            */
   uint32_t flags;   /* GSFM_RA_LOSS_FLAG_*                                          */
   double p[4];      /* parameters, see gsfm_ra_loss_kind                            */
   double scale;     /* ScaledLoss factor 'a' (loss_functions.py:267-281); 1 = none  */
+  int32_t inner_kind;
+  uint32_t inner_flags;
+  double inner_p[4];
+  double inner_scale;
+  const double* table;        /* HOST memory, [2 + table_octaves * table_per_octave][3]; copied by the library */
+  int32_t table_min_exp;
+  int32_t table_octaves;
+  int32_t table_per_octave;
+  int32_t table_reserved;
 } gsfm_ra_loss;
 
 /* One rotation-averaging problem, views densely renumbered 0..num_views-1 by the
@@ -101,9 +123,13 @@ typedef struct {
 } gsfm_ra_problem;
 
 typedef enum {
-  GSFM_RA_SOLVER_PCG = 0,           /* block-Jacobi PCG on the block-3x3 CSR system   */
-  GSFM_RA_SOLVER_DENSE_CHOLESKY = 1 /* on-device dense LL^T, small problems only      */
+  GSFM_RA_SOLVER_PCG = 0,            /* block-Jacobi PCG on the block-3x3 CSR system   */
+  GSFM_RA_SOLVER_DENSE_CHOLESKY = 1, /* on-device dense LL^T, small problems only      */
+  GSFM_RA_SOLVER_AUTO = 2            /* (default) exact dense LL^T -- the role of the reference's SPARSE_NORMAL_CHOLESKY,
+                                        rotation_estimator.cpp:300 -- when num_views <= GSFM_RA_AUTO_DENSE_MAX_VIEWS on one
+                                        cooperative-launch device, PCG otherwise                                          */
 } gsfm_ra_linear_solver;
+#define GSFM_RA_AUTO_DENSE_MAX_VIEWS 1024
 
 /* Trust-region options: the Ceres 1.14 defaults the reference runs with
  * (rotation_estimator.cpp:299-303 overrides only linear solver, 200 iterations,
@@ -125,10 +151,14 @@ typedef struct {
   int32_t pcg_max_iterations;          /* cap per linear solve                      */
   double pcg_rtol;                     /* stop when ||b - Ax|| <= rtol * ||b||      */
   int32_t num_threads;                 /* accepted for API parity (thread_num); unused */
-  int32_t device;                      /* CUDA ordinal; -1 = current device         */
+  int32_t device;                      /* CUDA ordinal of the (first) device; -1 = current device */
   int32_t verbose;                     /* 0 silent, 1 one line per iteration        */
-  int32_t reserved;
+  int32_t n_gpus;                      /* gsfm_ra_solve only: 0 / 1 = one device; W > 1 = shard the edges over devices
+                                          device .. device+W-1 of this process (peer access over NVLink, one host thread per
+                                          device); -1 = every visible device when the problem is large enough
+                                          (>= GSFM_RA_MIN_EDGES_PER_GPU edges per device), else one                        */
 } gsfm_ra_options;
+#define GSFM_RA_MIN_EDGES_PER_GPU 500000
 
 typedef enum {
   GSFM_RA_TERM_NONE = 0,
@@ -179,7 +209,7 @@ typedef struct {
   int32_t trace_size;
   /* sigma-consensus only: outer re-weighting iterations executed and the last mean |w - w_prev| */
   int32_t outer_iterations;
-  int32_t reserved;
+  int32_t num_linear_unconverged; /* PCG solves that stopped at pcg_max_iterations above pcg_rtol (their steps were still used) */
   double last_weight_change;
 } gsfm_ra_summary;
 
@@ -251,6 +281,16 @@ void* gsfm_ra_solver_cuda_stream(gsfm_ra_solver* solver);
  * out_ms[0] K1 fused edge kernel, [1] K1c cost-only edge kernel, [2] K2 block SpMV,
  * [3] one whole PCG iteration (K2 + the three vector kernels).  Does not change solver state. */
 int gsfm_ra_solver_time_kernels(gsfm_ra_solver* solver, int32_t repeats, double* out_ms /*[4]*/);
+
+/* What the solver resolved at build time: out[0] linear solver actually used (gsfm_ra_linear_solver, AUTO resolved),
+ * [1] bytes stored per half-edge of the block matrix (36 compact scalar stencil, 52 symmetric, 76 general),
+ * [2] persistent-kernel grid size, [3] threads per block of the K2-class kernels, [4] L2 keep fraction in eighths,
+ * [5] world size, [6] 1 if trust-region batches replay as CUDA graphs, [7] reserved. */
+int gsfm_ra_solver_info(const gsfm_ra_solver* solver, int32_t* out /*[8]*/);
+/* Measurement aid (roofline denominators): GB/s reached by the K2 record stream alone -- the same per-warp TMA rings pulling
+ * `bytes` of device memory `repeats` times with no arithmetic.  bytes below the L2 size measures the L2 -> SM stream rate,
+ * far above it the HBM stream rate of this access pattern. */
+int gsfm_ra_measure_stream(uint64_t bytes, int32_t repeats, int32_t device, double* gb_per_s);
 
 /* ---- kernel-level entry points (parity tests, profiling) ---------------------*/
 /* Residual dimension of an error type: 4 for QUATERNION_NORM (include/pairwise_rotation_error_quat.hpp:125-150),

@@ -789,7 +789,22 @@ int CheckProblem(const gsfm_ra_problem* p) {
 extern "C" {
 
 void ra_oracle_loss(const gsfm_ra_loss* loss, double s, double* rho3) {
-  BaseLoss(loss, s, rho3);
+  if (loss->inner_kind != GSFM_RA_LOSS_TRIVIAL || (loss->inner_scale != 0.0 && loss->inner_scale != 1.0)) {
+    /* ComposedLoss, scripts/loss_functions.py:250-265: rho(s) = f(g(s)); g may itself be a ScaledLoss */
+    gsfm_ra_loss g;
+    std::memset(&g, 0, sizeof(g));
+    g.kind = loss->inner_kind; g.flags = loss->inner_flags; g.scale = 1.0;
+    for (int k = 0; k < 4; ++k) g.p[k] = loss->inner_p[k];
+    double og[3], of[3];
+    BaseLoss(&g, s, og);
+    if (loss->inner_scale != 0.0 && loss->inner_scale != 1.0) { og[0] *= loss->inner_scale; og[1] *= loss->inner_scale; og[2] *= loss->inner_scale; }
+    BaseLoss(loss, og[0], of);
+    rho3[0] = of[0];
+    rho3[1] = of[1] * og[1];
+    rho3[2] = of[2] * og[1] * og[1] + of[1] * og[2];
+  } else {
+    BaseLoss(loss, s, rho3);
+  }
   /* ScaledLoss, scripts/loss_functions.py:267-281 */
   if (loss->scale != 1.0 && loss->scale != 0.0) { rho3[0] *= loss->scale; rho3[1] *= loss->scale; rho3[2] *= loss->scale; }
 }
@@ -975,7 +990,8 @@ int ra_oracle_solve(const gsfm_ra_problem* p, const gsfm_ra_options* o, double* 
     for (size_t c = 0; c < n; ++c) negg[c] = -L.g[c];
     t = NowMs();
     bool solved = true;
-    if (o->linear_solver == GSFM_RA_SOLVER_DENSE_CHOLESKY) {
+    /* GSFM_RA_SOLVER_AUTO: the exact factorisation for small graphs (the role of SPARSE_NORMAL_CHOLESKY), PCG above */
+    if (o->linear_solver == GSFM_RA_SOLVER_DENSE_CHOLESKY || (o->linear_solver == GSFM_RA_SOLVER_AUTO && N <= GSFM_RA_AUTO_DENSE_MAX_VIEWS)) {
       solved = DenseSolve(S, L, damp.data(), negg.data(), N, delta.data(), nt);
       it.linear_iterations = 1;
     } else {

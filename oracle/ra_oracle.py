@@ -9,7 +9,7 @@ import subprocess
 
 import numpy as np
 
-from globalsfmpy_b200 import _capi as capi
+from globalsfmpy_b200 import _abi as capi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libra_oracle.so")

@@ -37,6 +37,7 @@ def main():
         o.loss = loss
         o.pcg_rtol = 1e-12
         o.pcg_max_iterations = 2000
+        o.linear_solver = capi.SOLVER_PCG   # sharded solves are PCG; keep the single-GPU reference on the same path
         o.device = local
         sh = S.Solver(prob, o, rank=rank, world_size=world)
         sh.connect(dist, fused=fused)

@@ -27,16 +27,26 @@ def test_default_options_match_ceres_defaults():
     capi.lib().gsfm_ra_default_options(C.byref(o))
     p = capi.default_options_py()
     for f, _ in capi.Options._fields_:
-        if f in ("loss", "reserved"):
+        if f == "loss":
             continue
         assert getattr(o, f) == getattr(p, f), f
     assert (o.max_num_iterations, o.function_tolerance, o.gradient_tolerance, o.parameter_tolerance) == (200, 1e-6, 1e-10, 1e-8)
     assert o.initial_trust_region_radius == 1e4 and o.min_relative_decrease == 1e-3 and o.jacobi_scaling == 1
 
 
-def test_struct_sizes_match_header():
-    assert C.sizeof(capi.Loss) == 48 and C.sizeof(capi.Problem) == 64
-    assert C.sizeof(capi.Iteration) == 88
+def test_struct_sizes_match_header(tmp_path):
+    """The ctypes mirror against the C header itself: gcc prints sizeof / a few offsets of every struct of include/gsfm_ra.h."""
+    import subprocess
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gsfm_ra.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %d\\n",'
+                   'sizeof(gsfm_ra_loss),sizeof(gsfm_ra_problem),sizeof(gsfm_ra_options),sizeof(gsfm_ra_iteration),sizeof(gsfm_ra_summary),'
+                   'offsetof(gsfm_ra_loss,table),offsetof(gsfm_ra_options,n_gpus),offsetof(gsfm_ra_summary,num_linear_unconverged),GSFM_RA_ABI_VERSION);return 0;}\n')
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = [int(t) for t in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(capi.Loss), C.sizeof(capi.Problem), C.sizeof(capi.Options), C.sizeof(capi.Iteration), C.sizeof(capi.Summary),
+            capi.Loss.table.offset, capi.Options.n_gpus.offset, capi.Summary.num_linear_unconverged.offset, capi.ABI_VERSION]
+    assert got == want
 
 
 def test_no_cpu_fallback_without_device():

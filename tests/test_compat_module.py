@@ -128,8 +128,30 @@ def test_reference_loss_classes_are_recognised(sfm):
     assert loss_to_struct(lf.MAGSACWeightBasedLoss4(0.02), verify=False).flags == 1      # nu=4 defaults to the inverse weight
     L = loss_to_struct(lf.ScaledLoss(lf.ScaledLoss(lf.CauchyLoss(0.05), 2.0), 1.25), verify=False)
     assert L.kind == capi.LOSS_CAUCHY and L.scale == 2.5
-    with pytest.raises(UnsupportedLoss):
-        loss_to_struct(lf.ComposedLoss(lf.CauchyLoss(0.1), lf.HuberLoss(0.1)), verify=False)
+    # ComposedLoss (loss_functions.py:250-265) of two shipped classes: the native composition f(g(s)), no table
+    L = loss_to_struct(lf.ComposedLoss(lf.ScaledLoss(lf.CauchyLoss(0.1), 3.0), lf.ScaledLoss(lf.HuberLoss(0.2), 0.5)), verify=False)
+    assert (L.kind, L.inner_kind, L.p[0], L.inner_p[0], L.scale, L.inner_scale) == (capi.LOSS_CAUCHY, capi.LOSS_HUBER, 0.1, 0.2, 3.0, 0.5)
+    # the CPU oracle evaluates the same struct: chain rule against the object itself
+    from oracle import ra_oracle as orc
+    obj = lf.ComposedLoss(lf.ScaledLoss(lf.CauchyLoss(0.1), 3.0), lf.ScaledLoss(lf.HuberLoss(0.2), 0.5))
+    for sq in (0.0, 1e-3, 0.039, 0.041, 0.7, 30.0):
+        out = [0.0, 0.0, 0.0]
+        obj.Evaluate(sq, out)
+        assert np.allclose(orc.loss(L, sq)[0], out, rtol=1e-14, atol=1e-300)
+    # anything else -- a user subclass, a deeper nesting -- becomes a table of the object's own Evaluate
+    class LogCosh(sfm.LossFunction):
+        def Evaluate(self, s, out):
+            import math
+            r = math.sqrt(s + 1e-12)
+            out[0] = 2.0 * math.log(math.cosh(r)) if r < 300 else 2.0 * (r - math.log(2.0))
+            out[1] = math.tanh(r) / r
+            out[2] = (r / math.cosh(r) ** 2 - math.tanh(r)) / (2.0 * r ** 3) if r < 300 else -1.0 / (2.0 * r ** 3)
+    T = loss_to_struct(LogCosh(), verify=False)
+    assert T.kind == capi.LOSS_TABULATED and T.table_per_octave == 32 and T.table_octaves == 144
+    tab = np.ctypeslib.as_array(T.table, shape=(2 + 144 * 32, 3))
+    out = [0.0, 0.0, 0.0]
+    LogCosh().Evaluate(2.0 ** -3 * (1 + 5 / 32), out)
+    assert np.array_equal(tab[1 + (-3 + 80) * 32 + 5], out)
     # the reference classes evaluated against OUR module's constants/tables reproduce the golden vectors
     z = np.load(os.path.join(ROOT, "tests", "golden", "loss_golden.npz"))
     out = [0.0, 0.0, 0.0]
@@ -190,5 +212,14 @@ def test_loss_objects_evaluate_on_device(sfm, golden_dir):
 
         def Evaluate(self, s, out):
             out[0], out[1], out[2] = s, 1.0, 0.0
+    # ... by the closed-form mapping; it then runs as a table of its OWN Evaluate (what the reference would call per edge)
+    from globalsfmpy_b200 import _capi as capi, solver
+    T = loss_to_struct(CauchyLoss())
+    assert T.kind == capi.LOSS_TABULATED
+    assert np.allclose(solver.eval_loss(T, [0.0, 0.3, 17.0]), [[0.0, 1, 0], [0.3, 1, 0], [17.0, 1, 0]], rtol=1e-13, atol=1e-10)
+
+    class Kinked(sfm.LossFunction):              # a jump in rho' between knots: a table cannot represent it -> refused, with the error
+        def Evaluate(self, s, out):
+            out[0], out[1], out[2] = (s, 1.0, 0.0) if s < 0.0123 else (0.0123 + 0.1 * (s - 0.0123), 0.1, 0.0)
     with pytest.raises(UnsupportedLoss):
-        loss_to_struct(CauchyLoss())
+        loss_to_struct(Kinked())

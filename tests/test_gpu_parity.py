@@ -204,6 +204,7 @@ def _tight(loss, **kw):
     o.max_num_iterations = 400
     o.pcg_rtol = 1e-12
     o.pcg_max_iterations = 2000
+    o.linear_solver = capi.SOLVER_PCG   # the default (AUTO) would pick the dense factorisation for the small test graphs
     for k, v in kw.items():
         setattr(o, k, v)
     return o
@@ -238,6 +239,7 @@ def test_reference_stopping_rule_trajectory():
     o.loss = CAUCHY
     o.pcg_rtol = 1e-13
     o.pcg_max_iterations = 2000
+    o.linear_solver = capi.SOLVER_PCG
     og, sg, tg = solver.solve(prob, o, g.omega_init, trace_capacity=256)
     o.linear_solver = capi.SOLVER_DENSE_CHOLESKY
     oo, so, to = orc.solve(prob, o, g.omega_init, trace_capacity=256)
@@ -259,7 +261,9 @@ def test_madrid_magsac_reference_path(madrid):
     o.loss = MAGSAC
     o.pcg_rtol = 1e-13
     o.pcg_max_iterations = 5000
+    o.linear_solver = capi.SOLVER_PCG
     og, sg, tg = solver.solve(prob, o, madrid.omega_init, trace_capacity=256)
+    assert sg.num_linear_unconverged == 0
     o.linear_solver = capi.SOLVER_DENSE_CHOLESKY
     oo, so, to = orc.solve(prob, o, madrid.omega_init, trace_capacity=256)
     assert abs(sg.initial_cost - so.initial_cost) <= 1e-12 * so.initial_cost
@@ -281,12 +285,22 @@ def test_dense_cholesky_path_tracks_the_oracle_on_madrid(madrid):
     o.linear_solver = capi.SOLVER_DENSE_CHOLESKY
     og, sg, tg = solver.solve(prob, o, madrid.omega_init, trace_capacity=256)
     oo, so, to = orc.solve(prob, o, madrid.omega_init, trace_capacity=256)
-    for a, b in list(zip(tg, to))[:25]:
-        assert a.step_is_successful == b.step_is_successful
-        assert abs(a.cost - b.cost) <= 1e-7 * abs(b.cost), (a.iteration, a.cost, b.cost)
-    assert abs(sg.final_cost - so.final_cost) <= 2e-4 * so.final_cost
+    # step for step: same accept / reject decisions and costs to 1e-7 for (at least) the first 50 of the ~60 iterations -- the
+    # last few steps sit on the flat end of the staircase where ftol decides and a 1e-12 difference may add an iteration
+    together = 0
+    for a, b in zip(tg, to):
+        if a.step_is_successful != b.step_is_successful or abs(a.cost - b.cost) > 1e-7 * abs(b.cost):
+            break
+        together += 1
+    assert together >= min(50, len(to) - 3), (together, len(tg), len(to))
+    assert abs(sg.final_cost - so.final_cost) <= 1e-6 * so.final_cost
     mean, _ = vg.mean_angular_error(oo, og)
-    assert mean < 5e-3, mean
+    assert mean <= 1e-4, mean      # the north_star bar, on the shipped dataset with the shipped settings
+    # the DEFAULT options take this path by themselves (linear_solver AUTO, 379 views): bit-identical result
+    d = capi.default_options_py()
+    d.loss = MAGSAC
+    od, sd, _ = solver.solve(prob, d, madrid.omega_init)
+    assert np.array_equal(od, og) and sd.num_iterations == sg.num_iterations
     # smooth loss, tight tolerances: the north_star bar with margin
     og, sg, _ = solver.solve(prob, _tight(CAUCHY, linear_solver=capi.SOLVER_DENSE_CHOLESKY), madrid.omega_init)
     oo, so, _ = orc.solve(prob, _tight(CAUCHY, linear_solver=capi.SOLVER_DENSE_CHOLESKY), madrid.omega_init)
@@ -423,6 +437,7 @@ def test_resident_solver_stepwise_equals_one_shot():
     prob = solver.make_problem(g, capi.ANGLE_AXIS)
     o = capi.default_options_py()
     o.loss = CAUCHY
+    o.linear_solver = capi.SOLVER_PCG
     one, s1, _ = solver.solve(prob, o, g.omega_init)
     S = solver.Solver(prob, o)
     S.set_rotations(g.omega_init)
@@ -453,6 +468,7 @@ def test_batch_execution_paths_agree(cfg):
     o = capi.default_options_py()
     o.loss = loss
     o.pcg_rtol = 1e-10
+    o.linear_solver = capi.SOLVER_PCG
     res = {}
     for name, env in (("graph", {}), ("direct", {"GSFM_RA_NO_GRAPH": "1"}), ("unfused", {"GSFM_RA_NO_GRAPH": "1", "GSFM_RA_NO_FUSE": "1"})):
         for k in ("GSFM_RA_NO_GRAPH", "GSFM_RA_NO_FUSE"):
@@ -473,6 +489,49 @@ def test_batch_execution_paths_agree(cfg):
     assert vg.mean_angular_error(om0, om2)[0] < 1e-9
     # and the un-fused run launches more kernels per iteration
     assert s2.kernel_launches > s0.kernel_launches
+
+
+def test_composed_and_tabulated_losses():
+    """ComposedLoss (scripts/loss_functions.py:250-265) runs as the native composition f(g(s)); any other LossFunction object as a
+    table of its own Evaluate.  Both against the oracle, which for the table calls the Python object back once per edge per
+    evaluation exactly as the reference does (bind_src/GlobalSfMpy.cpp:36-59)."""
+    import math
+    from globalsfmpy_b200.losses import loss_to_struct, tabulate_loss
+    g = vg.synthetic_pose_graph(80, 900, seed=41, noise_deg=1.0, outlier_fraction=0.1)
+    prob = solver.make_problem(g, capi.ANGLE_AXIS)
+    # (1) native composition: Cauchy(0.1) o 0.5 * Huber(0.05), scaled by 3
+    L = capi.Loss.compose(capi.Loss.make(capi.LOSS_CAUCHY, 0.1, scale=3.0), capi.Loss.make(capi.LOSS_HUBER, 0.05, scale=0.5))
+    sq = np.concatenate([[0.0], np.exp(np.linspace(np.log(1e-9), np.log(50.0), 400))])
+    assert_close(solver.eval_loss(L, sq), orc.loss(L, sq), 1e-13, "composed loss table")
+    og, sg, _ = solver.solve(prob, _tight(L), g.omega_init)
+    oo, so, _ = orc.solve(prob, _tight(L, linear_solver=capi.SOLVER_DENSE_CHOLESKY), g.omega_init)
+    assert vg.mean_angular_error(oo, og)[0] <= 1e-6 and abs(sg.final_cost - so.final_cost) <= 1e-9 * so.final_cost
+
+    # (2) a hand-written subclass (smooth): tabulated on the host, interpolated on the device
+    class LogCosh:
+        def Evaluate(self, s, out):
+            r = math.sqrt(s + 1e-12) / 0.05
+            out[0] = 0.005 * (math.log(math.cosh(r)) if r < 300 else r - math.log(2.0))
+            out[1] = math.tanh(r) / r
+            out[2] = ((r / math.cosh(r) ** 2 - math.tanh(r)) / (2.0 * r ** 3) if r < 300 else -1.0 / (2.0 * r ** 3)) / 0.0025
+    obj = LogCosh()
+    T = tabulate_loss(obj)          # verifies every cell midpoint against the object on the device
+    assert T._table_error is not None and T._table_error < 1e-7
+    ref = np.array([[0.0] * 3] * len(sq))
+    for k, v in enumerate(sq):
+        obj.Evaluate(float(v), ref[k])
+    assert_close(solver.eval_loss(T, sq), ref, 1e-9, "tabulated loss")
+    og, sg, _ = solver.solve(prob, _tight(T), g.omega_init)
+
+    def cb(v):
+        out = [0.0, 0.0, 0.0]
+        obj.Evaluate(v, out)
+        return out
+    oo, so, _ = orc.solve(prob, _tight(capi.Loss.make(capi.LOSS_TRIVIAL), linear_solver=capi.SOLVER_DENSE_CHOLESKY), g.omega_init, loss_callback=cb)
+    assert vg.mean_angular_error(oo, og)[0] <= 1e-6, vg.mean_angular_error(oo, og)
+    assert abs(sg.final_cost - so.final_cost) <= 1e-8 * so.final_cost
+    # through the object mapping used by the GlobalSfMpy-compatible module
+    assert loss_to_struct(obj).kind == capi.LOSS_TABULATED
 
 
 def test_filter_view_pairs():
@@ -520,3 +579,40 @@ def test_large_graph_properties():
     assert s.final_cost < s.initial_cost
     mean, _ = vg.mean_angular_error(g.omega_gt, om)
     assert np.degrees(mean) < 0.2
+    # ... and WITH the oracle at this size: the whole assembled system at the initial point and the cost at the solution
+    co, go, ho, rpo, colo, valo = orc.assemble(prob, CAUCHY, g.omega_init, num_threads=os.cpu_count())
+    assert abs(c - co) <= 1e-12 * abs(co)
+    assert_close(gr, go, 1e-10, "gradient vs oracle, 1M edges")
+    assert_close(hd, ho, 1e-10, "diagonal blocks vs oracle, 1M edges")
+    assert np.array_equal(rp, rpo) and np.array_equal(col, colo)
+    assert_close(val, valo, 1e-10, "off-diagonal blocks vs oracle, 1M edges")
+    assert abs(solver.cost(prob, CAUCHY, om) - orc.cost(prob, CAUCHY, om, num_threads=os.cpu_count())) <= 1e-12 * s.final_cost
+
+
+def test_baseline_sizes_against_the_oracle():
+    """The other BASELINE-size graphs against the oracle: the Piccadilly stand-in (2.3k views / 300k edges, Cauchy) assembled and
+    SOLVED on both sides; covariance-weighted MAGSAC (the 20M configuration's kernel path) assembled at 1M edges."""
+    ncpu = os.cpu_count()
+    g = vg.synthetic_pose_graph(2300, 300000, seed=56, noise_deg=1.0, outlier_fraction=0.1, init="bfs")
+    prob = solver.make_problem(g, capi.ANGLE_AXIS)
+    c, gr, hd, rp, col, val = solver.assemble(prob, CAUCHY, g.omega_init)
+    co, go, ho, rpo, colo, valo = orc.assemble(prob, CAUCHY, g.omega_init, num_threads=ncpu)
+    assert abs(c - co) <= 1e-12 * abs(co)
+    assert_close(gr, go, 1e-10, "gradient, 300k"); assert_close(hd, ho, 1e-10, "diag, 300k"); assert_close(val, valo, 1e-10, "blocks, 300k")
+    # converged solve, smooth loss, tight on both sides (the oracle with PCG 1e-12: the 6900 x 6900 dense factorisation is not
+    # what limits it, 300k Jets per evaluation are)
+    t = _tight(CAUCHY)
+    t.num_threads = ncpu
+    og, sg, _ = solver.solve(prob, t, g.omega_init)
+    oo, so, _ = orc.solve(prob, t, g.omega_init)
+    mean, mx = vg.mean_angular_error(oo, og)
+    assert mean <= 1e-6, (mean, mx, sg.final_cost, so.final_cost)
+    assert abs(sg.final_cost - so.final_cost) <= 1e-9 * so.final_cost
+    # covariance + MAGSAC at 1M edges / 20k views (the per-edge path of BASELINE configs[4])
+    g = vg.synthetic_pose_graph(20000, 1000000, seed=57, outlier_fraction=0.1, covariance=True, init="bfs")
+    prob = solver.make_problem(g, capi.ANGLE_AXIS_COVARIANCE)
+    L = capi.Loss.make(capi.LOSS_MAGSAC3, 1.0)
+    c, gr, hd, rp, col, val = solver.assemble(prob, L, g.omega_init)
+    co, go, ho, rpo, colo, valo = orc.assemble(prob, L, g.omega_init, num_threads=ncpu)
+    assert abs(c - co) <= 1e-11 * abs(co)
+    assert_close(gr, go, 1e-9, "gradient, cov 1M"); assert_close(hd, ho, 1e-9, "diag, cov 1M"); assert_close(val, valo, 1e-9, "blocks, cov 1M")
