@@ -70,7 +70,7 @@ class Loss(C.Structure):
 class Problem(C.Structure):
     _fields_ = [("num_views", C.c_uint32), ("num_edges", C.c_uint64), ("edge_i", _u32p), ("edge_j", _u32p),
                 ("omega_ij", _dp), ("cov6", _dp), ("edge_weight", _dp), ("error_type", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("total_pair_count", C.c_int32)]
 
 
 class Options(C.Structure):
@@ -99,7 +99,7 @@ class Summary(C.Structure):
                 ("ms_assemble", C.c_double), ("ms_linear", C.c_double), ("ms_cost", C.c_double),
                 ("ms_total", C.c_double), ("kernel_launches", C.c_int64), ("trace", C.POINTER(Iteration)),
                 ("trace_capacity", C.c_int32), ("trace_size", C.c_int32), ("outer_iterations", C.c_int32), ("num_linear_unconverged", C.c_int32),
-                ("last_weight_change", C.c_double)]
+                ("last_weight_change", C.c_double), ("n_gpus_used", C.c_int32), ("reserved", C.c_int32)]
 
 
 def residual_dim(error_type):
@@ -132,6 +132,16 @@ def default_options_py():
     o.verbose = 0
     o.n_gpus = 0
     return o
+
+
+def clone(struct):
+    """A bitwise copy of a ctypes struct (copy.copy refuses structs that hold pointers); Python-side attributes that keep
+    pointed-to buffers alive (a tabulated loss's host table) are carried along."""
+    out = type(struct)()
+    C.memmove(C.byref(out), C.byref(struct), C.sizeof(type(struct)))
+    for k, v in getattr(struct, "__dict__", {}).items():
+        setattr(out, k, v)
+    return out
 
 
 def as_f64(a, shape=None):

@@ -289,13 +289,35 @@ def CalcCovariance(dataset_path):
 
 
 # ------------------------------------------------------------------------------- solver front-ends
-def _flatten(view_pairs, orientations, covariances, error_type):
+def _copy_options(options):
+    """A private copy of a _capi.Options (or the defaults): the caller's object is never written to."""
+    o = _capi.Options()
+    src = options if options is not None else _capi.default_options_py()
+    import ctypes
+    ctypes.memmove(ctypes.byref(o), ctypes.byref(src), ctypes.sizeof(_capi.Options))
+    if options is None:
+        o.n_gpus = -1     # behind the module API a large view graph shards over the box's GPUs by itself (SURVEY 8e)
+    return o
+
+
+def _matched_features(reconstruction, a, b):
+    """get_matched_features(view_id_pair, reconstruction, features).first.size() (rotation_estimator.cpp:260-274): the
+    features of the two views that belong to a common track."""
+    ta, tb = reconstruction._view_tracks.get(a), reconstruction._view_tracks.get(b)
+    return len(ta & tb) if ta and tb else 0
+
+
+def _flatten(view_pairs, orientations, covariances, error_type, reconstruction=None):
     """What rotation_estimator.cpp:228-293 does with the hash maps: skip edges whose endpoints have no initial
-    orientation or (covariance types) no covariance; dense-renumber the views."""
+    orientation or (covariance types) no covariance; dense-renumber the views; per-edge weight #matched/100 for the
+    *_INLIERS types (:260-274)."""
     ids = np.array(sorted(orientations), dtype=np.int64)
     dense = {int(v): k for k, v in enumerate(ids.tolist())}
     needs_cov = error_type in (3, 6, 7, 8)
-    ei, ej, wij, cov6 = [], [], [], []
+    needs_matches = error_type in (5, 6)
+    if needs_matches and reconstruction is None:
+        raise ValueError("ANGLE_AXIS_INLIERS / ANGLE_AXIS_COV_INLIERS weight every edge by its matched features: pass the reconstruction")
+    ei, ej, wij, cov6, weight = [], [], [], [], []
     for (a, b), info in view_pairs.items():
         if a not in dense or b not in dense:
             continue
@@ -306,21 +328,24 @@ def _flatten(view_pairs, orientations, covariances, error_type):
             S = c[0]
             cov6.append([S[0][0], S[1][1], S[2][2], S[0][1], S[0][2], S[1][2]])
         ei.append(dense[a]); ej.append(dense[b]); wij.append(np.asarray(info.rotation_2, dtype=np.float64))
+        if needs_matches:
+            weight.append(_matched_features(reconstruction, a, b) / 100.0)
     omega = np.array([np.asarray(orientations[int(v)], dtype=np.float64) for v in ids.tolist()]).reshape(len(ids), 3)
     return ids, np.array(ei, np.uint32), np.array(ej, np.uint32), np.array(wij).reshape(len(ei), 3), \
-        (np.array(cov6).reshape(len(ei), 6) if needs_cov else None), omega
+        (np.array(cov6).reshape(len(ei), 6) if needs_cov else None), omega, (np.array(weight) if needs_matches else None)
 
 
-def _solve(view_pairs, orientations, loss, error_type, covariances=None, num_threads=1, options=None):
+def _solve(view_pairs, orientations, loss, error_type, covariances=None, num_threads=1, options=None, reconstruction=None):
     error_type = int(error_type)
     if len(orientations) == 0 or len(view_pairs) == 0:
         return False                                  # rotation_estimator.cpp:209-220
-    ids, ei, ej, wij, cov6, omega = _flatten(view_pairs, orientations, covariances, error_type)
+    ids, ei, ej, wij, cov6, omega, weight = _flatten(view_pairs, orientations, covariances, error_type, reconstruction)
     if len(ei) == 0:
         return True
-    prob = _capi.ProblemArrays(len(ids), ei, ej, wij, cov6=cov6, error_type=error_type)
-    o = options or _capi.default_options_py()
-    o.loss = loss_to_struct(loss)
+    prob = _capi.ProblemArrays(len(ids), ei, ej, wij, cov6=cov6, edge_weight=weight, error_type=error_type)
+    o = _copy_options(options)
+    L = loss_to_struct(loss)                          # keeps a tabulated loss's host table alive until the call returns
+    o.loss = L
     o.num_threads = int(num_threads)
     omega, summary, _ = _solver.solve(prob, o, omega)
     for k, v in enumerate(ids.tolist()):
@@ -353,7 +378,7 @@ class NonlinearRotationEstimator(RotationEstimator):
 
     def EstimateRotationsWithCustomizedLossAndCovariance(self, view_pairs, rotations, loss_function, thread_num, covariances,
                                                          rotation_error_type, reconstruction=None):
-        return _solve(view_pairs, rotations, loss_function, rotation_error_type, covariances, thread_num)
+        return _solve(view_pairs, rotations, loss_function, rotation_error_type, covariances, thread_num, reconstruction=reconstruction)
 
 
 class ReconstructionBuilder:
@@ -444,7 +469,7 @@ class GlobalReconstructionEstimator:
         """:463-485: MST initialisation, then EstimateRotationsWithCustomizedLossAndCovariance."""
         self.OrientationsFromMaximumSpanningTree()
         return _solve(self.view_graph_.GetAllEdges(), self.orientations, loss_func, rotation_error_type, covariances,
-                      self.options.num_threads, self.solver_options)
+                      self.options.num_threads, self.solver_options, self.reconstruction_)
 
     def EstimateGlobalRotations(self, loss_func=None, rotation_error_type=RotationErrorType.QUATERNION_COSINE):
         """:440-461 (EstimateGlobalRotationsNonLinear)."""
@@ -458,10 +483,13 @@ class GlobalReconstructionEstimator:
         edges = self.view_graph_.GetAllEdges()
         if len(self.orientations) == 0 or len(edges) == 0:
             return False
-        ids, ei, ej, wij, _, omega = _flatten(edges, self.orientations, None, 4)
+        ids, ei, ej, wij, _, omega, _ = _flatten(edges, self.orientations, None, 4)
         prob = _capi.ProblemArrays(len(ids), ei, ej, wij, error_type=4)
-        o = self.solver_options or _capi.default_options_py()
-        o.loss = loss_to_struct(loss_func)
+        prob.c.total_pair_count = len(edges)       # the reference's stop test averages over view_pairs.size(), skipped pairs included
+        o = _copy_options(self.solver_options)
+        o.n_gpus = 0                               # the re-weighting loop runs on one device
+        L = loss_to_struct(loss_func)
+        o.loss = L
         omega, summary = _solver.solve_sigma_consensus(prob, o, omega, int(iters_num), float(sigma_max))
         for k, v in enumerate(ids.tolist()):
             self.orientations[int(v)] = omega[k].copy()
@@ -469,11 +497,14 @@ class GlobalReconstructionEstimator:
         return True
 
     def FilterRotations(self):
-        """FilterViewPairsFromOrientation with options.rotation_filtering_max_difference_degrees, on the device."""
+        """src/GSfM_global_reconstruction_estimator.cpp:509-524: FilterViewPairsFromOrientation with
+        options.rotation_filtering_max_difference_degrees (on the device), then RemoveDisconnectedViewPairs -- only the largest
+        connected component survives -- and the orientations of the removed views are erased."""
         edges = self.view_graph_.GetAllEdges()
         keys = [k for k in edges if k[0] in self.orientations and k[1] in self.orientations]
-        missing = [k for k in edges if k not in set(keys)]
-        ids, ei, ej, wij, _, omega = _flatten({k: edges[k] for k in keys}, self.orientations, None, 4)
+        keyset = set(keys)
+        missing = [k for k in edges if k not in keyset]
+        ids, ei, ej, wij, _, omega, _ = _flatten({k: edges[k] for k in keys}, self.orientations, None, 4)
         prob = _capi.ProblemArrays(len(ids), ei, ej, wij)
         keep, _ = _solver.filter_view_pairs(prob, omega, self.options.rotation_filtering_max_difference_degrees)
         for k, kp in zip(keys, keep.tolist()):
@@ -481,6 +512,25 @@ class GlobalReconstructionEstimator:
                 self.view_graph_.RemoveEdge(*k)
         for k in missing:
             self.view_graph_.RemoveEdge(*k)
+        # RemoveDisconnectedViewPairs (T/sfm/view_graph/remove_disconnected_view_pairs.cc:48-): keep the largest component
+        left = list(self.view_graph_.GetAllEdges())
+        all_ids = np.array(sorted(self.view_graph_.ViewIds()), dtype=np.int64)
+        if left:
+            ij = np.searchsorted(all_ids, np.array(left, dtype=np.int64))
+            if _on_device():
+                _, vkeep = _solver.filter_initial_view_graph(len(all_ids), ij[:, 0], ij[:, 1], np.ones(len(left), np.int32), 0)
+            else:
+                _, kept_ids = _vg.filter_initial_view_graph(all_ids, np.array(left, dtype=np.int64), np.ones(len(left), np.int64), 0)
+                vkeep = np.isin(all_ids, kept_ids)
+            alive = set(int(v) for v in all_ids[vkeep].tolist())
+        else:
+            alive = set()
+        for v in all_ids.tolist():
+            if int(v) not in alive:
+                self.view_graph_.RemoveView(int(v))
+                self.orientations.pop(int(v), None)
+        for v in [v for v in self.orientations if v not in alive]:
+            del self.orientations[v]
         return True
 
     def _todo(name):  # noqa: N805
@@ -506,6 +556,57 @@ def SetOrientations(orientations, reconstruction):
             continue
         v.orientation = np.asarray(w, dtype=np.float64).copy()
         v.estimated = True
+
+
+class CompareInfo:                               # include/compare_reconstructions.hpp:24-47, bind:387-393
+    def __init__(self):
+        self.rotation_diff_when_align = []
+        self.position_errors = []
+        self.num_3d_points = 0
+        self.common_camera = 0
+        self.num_reconstructed_view = 0
+
+
+def AngularDifference(rotation1, rotation2):
+    """src/compare_reconstructions.cpp:7-16: angle (rad) of R1^T R2."""
+    return float(_vg.angular_difference(np.asarray(rotation1, dtype=np.float64)[None], np.asarray(rotation2, dtype=np.float64)[None])[0])
+
+
+def AlignRotations(gt_rotation, rotation):
+    """src/compare_reconstructions.cpp:149-177: the rotation G (angle-axis, started at 0) minimising
+    sum rho(|gt_i - Log(R_i G)|^2) with rho = CauchyLoss(0.1), applied to `rotation` in place (a list / array of angle-axis
+    vectors).  Host-side metric code: three unknowns, N residual blocks."""
+    out = _vg.align_rotations_robust(np.asarray(gt_rotation, dtype=np.float64), np.asarray(rotation, dtype=np.float64))
+    for k in range(len(rotation)):
+        rotation[k] = out[k]
+    return rotation
+
+
+def FindCommonEstimatedViewsByName(reconstruction1, reconstruction2):
+    """src/compare_reconstructions.cpp:180-195."""
+    by_name = {reconstruction2.View(v).Name(): v for v in reconstruction2.ViewIds()}
+    names = []
+    for v in reconstruction1.ViewIds():
+        name = reconstruction1.View(v).Name()
+        w = by_name.get(name)
+        if w is not None and reconstruction2.View(w).IsEstimated():
+            names.append(name)
+    return names
+
+
+def compare_orientations(common_view_names, reference_reconstruction, reconstruction_to_align, robust_alignment_threshold=0.0):
+    """src/compare_reconstructions.cpp:228-262 (bind:652): gather the rotations of the common views, AlignRotations
+    (robust), per-view AngularDifference."""
+    ref_ids = {reference_reconstruction.View(v).Name(): v for v in reference_reconstruction.ViewIds()}
+    our_ids = {reconstruction_to_align.View(v).Name(): v for v in reconstruction_to_align.ViewIds()}
+    r1 = [np.asarray(reference_reconstruction.View(ref_ids[n]).GetOrientationAsAngleAxis(), dtype=np.float64) for n in common_view_names]
+    r2 = [np.asarray(reconstruction_to_align.View(our_ids[n]).GetOrientationAsAngleAxis(), dtype=np.float64) for n in common_view_names]
+    result = CompareInfo()
+    if r1:
+        AlignRotations(r1, r2)
+        result.rotation_diff_when_align = [AngularDifference(a, b) for a, b in zip(r1, r2)]
+    result.common_camera = len(common_view_names)
+    return result
 
 
 def test_loss_with_input_x(loss_func, x):       # bind:179-183

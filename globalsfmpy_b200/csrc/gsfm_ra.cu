@@ -280,10 +280,11 @@ struct gsfm_ra_solver {
   int64_t linear_unconverged = 0;  // PCG solves that hit pcg_max_iterations above pcg_rtol
   bool cooperative = true;  // persistent PCG kernel available
   ncclx::Comm comm = nullptr;  // edge-sharded exchange (world > 1)
-  // fused exchange: one cudaMalloc'ed block per rank {double y[2][3N]; unsigned flag;}, every peer's block mapped here
-  double* xchg = nullptr;
+  // fused exchange: one cudaMalloc'ed block of LLCell per rank (layout in ra_common.cuh), every peer's block mapped here
+  LLCell* xchg = nullptr;
   void* peer_base[kMaxPeers] = {};
   bool peers_connected = false;
+  bool peers_ipc = false;    // peer_base[] came from cudaIpcOpenMemHandle (closed on destruction), not from in-process peer access
 
   // structure
   DevBuf<uint32_t> he_col, he_row, he_edge, iso;
@@ -341,7 +342,7 @@ struct gsfm_ra_solver {
 
   ~gsfm_ra_solver() {
     if (comm && ncclx::api()) ncclx::api()->CommDestroy(comm);
-    for (int r = 0; r < kMaxPeers; ++r) if (peer_base[r] && r != rank) cudaIpcCloseMemHandle(peer_base[r]);
+    for (int r = 0; r < kMaxPeers; ++r) if (peers_ipc && peer_base[r] && r != rank) cudaIpcCloseMemHandle(peer_base[r]);
     if (xchg) cudaFree(xchg);
     if (h_sc) cudaFreeHost(h_sc);
     if (mailbox) cudaFreeHost(mailbox);
@@ -394,6 +395,9 @@ struct gsfm_ra_solver {
 
   int rec_doubles() const { return blk * 32 + 16; }
   int smem_bytes() const { return spmv_smem_bytes(blk); }
+  // persistent PCG kernel: + the shared-memory copy of z for small graphs (GSFM_RA_NO_SLICE=1 disables it, A/B runs)
+  bool use_slice() const { return N <= (uint32_t)kSliceMaxViews && !std::getenv("GSFM_RA_NO_SLICE"); }
+  int pcg_smem_bytes() const { return spmv_smem_bytes(blk) + (use_slice() ? (int)(24u * N + 16u) : 0); }
   // K1 is specialised on (Jacobian?, residual kind, scalar weight?, loss): the common losses get their own instantiation
   // (no switch, fewer registers), everything else runs the generic one.
   typedef void (*K1Fn)(const K1Args);
@@ -453,8 +457,14 @@ struct gsfm_ra_solver {
     if (!sharded()) {
       k_node_finalize<<<grid_for(N), kBlock, 0, stream>>>(N, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd_p[b], gt_p[b], ediag[b].p, co, 0, tail,
                                                            slots.p, counter.p, sc.p, mb, mseq, publish ? ip_dev : nullptr);
+    } else if (peers_connected && jacobian) {
+      // edge-sharded, fused exchange: the reduction of [Hd | gt | cost] across GPUs happens inside the kernel (peer memory)
+      PeerPtrs pp;
+      for (int r = 0; r < kMaxPeers; ++r) pp.p[r] = (LLCell*)peer_base[r];
+      k_node_finalize_ll<<<grid_for(N), kBlock, 0, stream>>>(N, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd_p[b], gt_p[b], ediag[b].p, slots.p, counter.p,
+                                                              sc.p, mb, mseq, publish ? ip_dev : nullptr, pp, world, rank);
     } else {
-      // edge-sharded: local sums -> ONE all-reduce of [Hd | gt | cost, bad] -> per-view post-processing
+      // edge-sharded, NCCL: local sums -> ONE all-reduce of [Hd | gt | cost, bad] -> per-view post-processing
       k_node_finalize<<<grid_for(N), kBlock, 0, stream>>>(N, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd_p[b], gt_p[b], ediag[b].p, co, 1, tail,
                                                            slots.p, counter.p, sc.p, nullptr, 0u, nullptr);
       if (jacobian) RA_TRY(allreduce(lin[b].p, 9ull * N + 2));
@@ -501,6 +511,7 @@ struct gsfm_ra_solver {
     PcgParams P;
     P.N = N; P.num_warps = pk2.num_warps; P.n_iso = n_iso; P.max_iter = max_iter; P.H = H; P.rtol2 = rtol * rtol;
     P.keep8 = keep8;
+    P.slice_views = use_slice() ? N : 0u;
     P.warp_seg_ptr = pk2.warp_seg_ptr.p; P.seg_row = pk2.seg_row.p; P.seg_begin = pk2.seg_begin.p; P.seg_len = pk2.seg_len.p;
     P.node_seg_ptr = pk2.node_seg_ptr.p; P.iso = iso.p; P.warp_span = pk2.span;
     P.val = val[b].p; P.Dblk = Dblk.p; P.Minv = Minv.p;
@@ -509,10 +520,7 @@ struct gsfm_ra_solver {
     P.fused = 0; P.ip = nullptr; P.cand_q = nullptr; P.cand_JL = nullptr;
     std::memset(&P.prep, 0, sizeof(P.prep)); std::memset(&P.apply, 0, sizeof(P.apply));
     P.world = peers_connected ? world : 1; P.rank = rank;
-    for (int r = 0; r < kMaxPeers; ++r) {
-      P.peer_y[r] = (double*)peer_base[r];
-      P.peer_flag[r] = peer_base[r] ? (unsigned*)((double*)peer_base[r] + 6ull * N) : nullptr;
-    }
+    for (int r = 0; r < kMaxPeers; ++r) P.peer[r] = (LLCell*)peer_base[r];
     return P;
   }
 
@@ -558,7 +566,7 @@ struct gsfm_ra_solver {
       }
       void* args[] = {&P};
       const void* fn = (blk == 4) ? (const void*)k_pcg_persistent<4> : (blk == 6) ? (const void*)k_pcg_persistent<6> : (const void*)k_pcg_persistent<9>;
-      CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(pk2.grid), dim3(kPcgBlock), args, smem_bytes(), stream));
+      CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(pk2.grid), dim3(kPcgBlock), args, pcg_smem_bytes(), stream));
       launches += 1;
       return 0;
     }
@@ -609,15 +617,15 @@ int device_info(int device, DeviceInfo** out) {
     CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaDeviceGetAttribute(&d.coop, cudaDevAttrCooperativeLaunch, device));
     CUDA_TRY(cudaDeviceGetAttribute(&d.l2_bytes, cudaDevAttrL2CacheSize, device));
-    CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(4)));
-    CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(6)));
-    CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(9)));
+    CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(4) + 24 * kSliceMaxViews + 16));
+    CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(6) + 24 * kSliceMaxViews + 16));
+    CUDA_TRY(cudaFuncSetAttribute(k_pcg_persistent<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(9) + 24 * kSliceMaxViews + 16));
     CUDA_TRY(cudaFuncSetAttribute(k_spmv<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(4)));
     CUDA_TRY(cudaFuncSetAttribute(k_spmv<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(6)));
     CUDA_TRY(cudaFuncSetAttribute(k_spmv<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, spmv_smem_bytes(9)));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2[0], k_pcg_persistent<4>, kPcgBlock, spmv_smem_bytes(4)));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2[1], k_pcg_persistent<6>, kPcgBlock, spmv_smem_bytes(6)));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2[2], k_pcg_persistent<9>, kPcgBlock, spmv_smem_bytes(9)));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2[0], k_pcg_persistent<4>, kPcgBlock, spmv_smem_bytes(4) + 24 * kSliceMaxViews + 16));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2[1], k_pcg_persistent<6>, kPcgBlock, spmv_smem_bytes(6) + 24 * kSliceMaxViews + 16));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_k2[2], k_pcg_persistent<9>, kPcgBlock, spmv_smem_bytes(9) + 24 * kSliceMaxViews + 16));
     // keep freed blocks in the pool: the next solver reuses them
     cudaMemPool_t pool;
     CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -886,7 +894,7 @@ int enqueue_batch(gsfm_ra_solver* s, int b, double mu) {
 // back to back -- else as direct launches.  GSFM_RA_NO_GRAPH=1 forces direct launches.
 int run_batch(gsfm_ra_solver* s, int b) {
   if (s->graph_state == 0) {
-    const bool eligible = s->opt.linear_solver == GSFM_RA_SOLVER_PCG && s->cooperative && !s->sharded() && !std::getenv("GSFM_RA_NO_GRAPH");
+    const bool eligible = s->opt.linear_solver == GSFM_RA_SOLVER_PCG && s->cooperative && (!s->sharded() || s->peers_connected) && !std::getenv("GSFM_RA_NO_GRAPH");
     s->graph_state = eligible ? 1 : -1;
   }
   if (s->graph_state == 1 && !s->batch_graph[b]) {
@@ -1046,6 +1054,7 @@ int iterate(gsfm_ra_solver* s, int max_new_iterations, gsfm_ra_summary* sum) {
     sum->num_unsuccessful_steps = unsucc;
     sum->total_linear_iterations = lin_total;
     sum->num_linear_unconverged = unconverged;
+    sum->n_gpus_used = s->world;
     sum->initial_cost = s->initial_cost;
     sum->final_cost = s->x_cost;
     sum->ms_setup = s->ms_setup;
@@ -1055,6 +1064,16 @@ int iterate(gsfm_ra_solver* s, int max_new_iterations, gsfm_ra_summary* sum) {
     sum->ms_total = now_ms() - t_start;
     sum->kernel_launches = s->launches - launches0;
   }
+  return 0;
+}
+
+// The exchange block of a sharded solver: plain cudaMalloc (IPC handles cannot be taken from the async pool), zeroed (tag 0 =
+// "nothing yet": sequence numbers start at 1).
+int alloc_exchange_block(gsfm_ra_solver* s) {
+  if (s->xchg) return 0;
+  const size_t bytes = ll_cells_total(s->N, s->world) * sizeof(LLCell);
+  CUDA_TRY(cudaMalloc(&s->xchg, bytes));
+  CUDA_TRY(cudaMemset(s->xchg, 0, bytes));
   return 0;
 }
 
@@ -1181,11 +1200,7 @@ int gsfm_ra_solver_comm_init(gsfm_ra_solver* s, const uint8_t* id) {
 int gsfm_ra_solver_ipc_export(gsfm_ra_solver* s, uint8_t* handle) {
   if (!s || !handle) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
   CUDA_TRY(cudaSetDevice(s->device));
-  if (!s->xchg) {
-    const size_t bytes = (6ull * s->N + 16) * sizeof(double);
-    CUDA_TRY(cudaMalloc(&s->xchg, bytes));  // plain cudaMalloc: IPC handles cannot be taken from the async pool
-    CUDA_TRY(cudaMemset(s->xchg, 0, bytes));
-  }
+  RA_TRY(alloc_exchange_block(s));
   std::memset(handle, 0, GSFM_RA_IPC_HANDLE_BYTES);
   cudaIpcMemHandle_t h;
   CUDA_TRY(cudaIpcGetMemHandle(&h, s->xchg));
@@ -1205,6 +1220,7 @@ int gsfm_ra_solver_ipc_import(gsfm_ra_solver* s, const uint8_t* handles) {
     CUDA_TRY(cudaIpcOpenMemHandle(&s->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
   }
   s->peers_connected = true;
+  s->peers_ipc = true;
   return 0;
 }
 int gsfm_ra_solver_edge_range(const gsfm_ra_solver* s, uint64_t* e0, uint64_t* e1) {
@@ -1309,9 +1325,102 @@ int gsfm_ra_solver_time_kernels(gsfm_ra_solver* s, int32_t repeats, double* out_
   return 0;
 }
 
+// How many devices a one-shot solve shards over (options.n_gpus, include/gsfm_ra.h).  Multi-GPU needs the PCG path (the dense
+// factorisation is a single-device kernel) and peer access between all the devices; -1 asks for as many devices as keep
+// >= GSFM_RA_MIN_EDGES_PER_GPU edges each (below that the per-step exchange costs more than the pass it saves).
+static int resolve_world(const gsfm_ra_problem* problem, const gsfm_ra_options* options, int* dev0_out) {
+  int want = options->n_gpus;
+  if (want == 0 || want == 1 || !problem) return 1;
+  if (options->linear_solver == GSFM_RA_SOLVER_DENSE_CHOLESKY) return 1;
+  if (options->linear_solver == GSFM_RA_SOLVER_AUTO && problem->num_views <= GSFM_RA_AUTO_DENSE_MAX_VIEWS) return 1;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 2) { cudaGetLastError(); return 1; }
+  int dev0 = options->device;
+  if (dev0 < 0 && cudaGetDevice(&dev0) != cudaSuccess) return 1;
+  const int avail = std::min(ndev - dev0, kMaxPeers);
+  uint64_t min_edges = GSFM_RA_MIN_EDGES_PER_GPU;
+  if (const char* e = std::getenv("GSFM_RA_MIN_EDGES_PER_GPU")) min_edges = std::max<long long>(1, std::atoll(e));  // tests
+  if (want < 0) want = (int)std::min<uint64_t>((uint64_t)avail, problem->num_edges / min_edges);
+  want = std::max(1, std::min(want, avail));
+  for (int a = 0; a < want; ++a)
+    for (int b = 0; b < want; ++b) {
+      int ok = 1;
+      if (a != b && (cudaDeviceCanAccessPeer(&ok, dev0 + a, dev0 + b) != cudaSuccess || !ok)) { cudaGetLastError(); return 1; }
+    }
+  *dev0_out = dev0;
+  return want;
+}
+
+// One process, W devices: one host thread per device, each with its own resident solver on its shard of the edges; the
+// exchange blocks are wired by peer access (no IPC, no NCCL, no host-side hand-shake).  Every thread runs the same
+// trust-region loop on bit-identical replicated scalars, so they take the same decisions without talking to each other.
+static int solve_multi(const gsfm_ra_problem* problem, const gsfm_ra_options* options, int dev0, int W, double* omega_inout,
+                       gsfm_ra_summary* summary) {
+  std::vector<gsfm_ra_solver*> sv(W, nullptr);
+  std::vector<int> rc(W, 0);
+  std::vector<std::string> err(W);
+  auto parallel = [&](auto&& body) {
+    std::vector<std::thread> th;
+    for (int r = 0; r < W; ++r) th.emplace_back([&, r] { rc[r] = body(r); if (rc[r] != 0) err[r] = g_last_error; });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < W; ++r)
+      if (rc[r] != 0 && rc[r] != GSFM_RA_ERR_NUMERIC) { set_error("device %d: %s", dev0 + r, err[r].c_str()); return rc[r]; }
+    return rc[0];
+  };
+  int prev_dev = 0;
+  cudaGetDevice(&prev_dev);
+  struct Cleanup {  // destroys the solvers on their own devices, then puts the caller's current device back
+    std::vector<gsfm_ra_solver*>& v;
+    int restore;
+    ~Cleanup() { for (auto* s : v) if (s) { cudaSetDevice(s->device); delete s; } cudaSetDevice(restore); }
+  } cleanup{sv, prev_dev};
+  int st = parallel([&](int r) -> int {
+    gsfm_ra_options o = *options;
+    o.device = dev0 + r; o.n_gpus = 0;
+    if (r != 0) o.verbose = 0;
+    RA_TRY(build_solver(problem, &o, r, W, &sv[r]));
+    RA_TRY(alloc_exchange_block(sv[r]));
+    for (int q = 0; q < W; ++q) {
+      if (q == r) continue;
+      const cudaError_t e = cudaDeviceEnablePeerAccess(dev0 + q, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", dev0 + r, dev0 + q, cudaGetErrorString(e)); return GSFM_RA_ERR_CUDA; }
+      cudaGetLastError();
+    }
+    return 0;
+  });
+  if (st != 0) { cudaSetDevice(prev_dev); return st; }
+  for (int r = 0; r < W; ++r) {
+    for (int q = 0; q < W; ++q) sv[r]->peer_base[q] = sv[q]->xchg;
+    sv[r]->peers_connected = true;
+  }
+  st = parallel([&](int r) -> int {
+    RA_TRY(gsfm_ra_solver_set_rotations(sv[r], omega_inout));
+    gsfm_ra_summary local;
+    std::memset(&local, 0, sizeof(local));
+    return gsfm_ra_solver_iterate(sv[r], options->max_num_iterations + 1, r == 0 ? summary : &local);
+  });
+  int out = st;
+  if (st == 0 || st == GSFM_RA_ERR_NUMERIC) {
+    const int g = gsfm_ra_solver_get_rotations(sv[0], omega_inout);
+    if (g != 0) out = g;
+  }
+  cudaSetDevice(prev_dev);
+  return out;
+}
+
 int gsfm_ra_solve(const gsfm_ra_problem* problem, const gsfm_ra_options* options, double* omega_inout, gsfm_ra_summary* summary) {
   if (!omega_inout) { set_error("omega_inout is NULL"); return GSFM_RA_ERR_INVALID; }
+  if (!options) { set_error("options is NULL"); return GSFM_RA_ERR_INVALID; }
   const double t0 = now_ms();
+  int dev0 = 0;
+  const int W = resolve_world(problem, options, &dev0);
+  if (W > 1) {
+    RA_TRY(check_problem(problem));
+    if (options->verbose) std::fprintf(stderr, "[gsfm_ra] sharding %llu edges over devices %d..%d\n", (unsigned long long)problem->num_edges, dev0, dev0 + W - 1);
+    const int rc = solve_multi(problem, options, dev0, W, omega_inout, summary);
+    if (summary) summary->ms_total = now_ms() - t0;
+    return rc;
+  }
   TempSolver t;
   RA_TRY(build_solver(problem, options, 0, 1, &t.s));
   RA_TRY(gsfm_ra_solver_set_rotations(t.s, omega_inout));
@@ -1357,17 +1466,20 @@ int gsfm_ra_solve_sigma_consensus(const gsfm_ra_problem* problem, const gsfm_ra_
     s->launches += 3;
     CUDA_TRY(cudaGetLastError());
     RA_TRY(s->fetch_scalars());
-    const double diff = s->h_sc->dg / (double)E;
+    // the reference divides by view_pairs.size(), the pairs it skipped included (rotation_estimator.cpp:419-424)
+    const double diff = s->h_sc->dg / (double)(problem->total_pair_count > 0 ? (uint64_t)problem->total_pair_count : E);
     reset_trust_region(s);
     gsfm_ra_summary s1;
     std::memset(&s1, 0, sizeof(s1));
+    if (total.trace && total.trace_size < total.trace_capacity) { s1.trace = total.trace + total.trace_size; s1.trace_capacity = total.trace_capacity - total.trace_size; }
     rc = gsfm_ra_solver_iterate(s, options->max_num_iterations + 1, &s1);
     if (rc != 0 && rc != GSFM_RA_ERR_NUMERIC) return rc;
     if (it == 0) total.initial_cost = s1.initial_cost;
     total.final_cost = s1.final_cost; total.termination = s1.termination;
     total.num_iterations += s1.num_iterations; total.num_successful_steps += s1.num_successful_steps;
     total.num_unsuccessful_steps += s1.num_unsuccessful_steps; total.total_linear_iterations += s1.total_linear_iterations;
-    total.ms_assemble += s1.ms_assemble; total.ms_linear += s1.ms_linear; total.kernel_launches += s1.kernel_launches + 3;
+    total.ms_assemble += s1.ms_assemble; total.ms_linear += s1.ms_linear; total.ms_cost += s1.ms_cost; total.kernel_launches += s1.kernel_launches + 3;
+    total.trace_size += s1.trace_size; total.num_linear_unconverged += s1.num_linear_unconverged; total.n_gpus_used = 1;
     total.outer_iterations = it + 1;
     total.last_weight_change = diff;
     if (rc != 0 || diff <= 1e-7) break;

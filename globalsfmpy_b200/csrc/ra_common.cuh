@@ -17,6 +17,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gsfm_ra.h"
@@ -72,6 +73,10 @@ struct Chunk {
   static constexpr int kDoubles = kRecs * Rec<kBlk>::kDoubles;
   static constexpr int kBytes = kDoubles * 8;
 };
+// Small graphs: the gathered vector z (24 B per view) is staged in shared memory once per pass and the per-half-edge gather
+// reads it there -- the L1/L2 gather path of an SM retires about one 32 B sector per clock, which at 1M half-edges per pass is
+// as expensive as the matrix stream itself.  kSliceMaxViews * 24 B must fit beside the rings (227 KB per block).
+constexpr int kSliceMaxViews = 2560;
 constexpr int spmv_smem_bytes(int blk) { return kPcgWarps * kStages2 * chunk_recs(blk) * (blk * 32 + 16) * 8 + kPcgWarps * kStages2 * 8; }
 
 __device__ __host__ __forceinline__ size_t blk_index(uint64_t h, int k, int rec_doubles) { return (size_t)(h >> 5) * rec_doubles + (size_t)k * 32 + (h & 31); }
@@ -131,7 +136,8 @@ struct DevScalars {
   double dg, dHd, step2;  // delta.g, delta.H.delta, |delta|^2 (Euclidean step)
   int bad;                // non-finite detected (1) / a peer GPU did not show up (2)
   int xseq;               // cross-GPU exchange sequence number (multi-GPU persistent PCG)
-  int bar_seq, pad1;      // grid barrier sequence number of the persistent PCG kernel
+  int bar_seq;            // grid barrier sequence number of the persistent PCG kernel
+  int eseq;               // cross-GPU exchange sequence number of the per-view sums (one per evaluation)
   // %globaltimer stamps of the trust-region batch: start of k_prepare_solve, end of k_apply_step, end of k_node_finalize
   unsigned long long t_begin, t_linear_end, t_end;
 };
@@ -155,6 +161,61 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
+}
+
+// ------------------------------------------------------------------------------------------
+// Cross-GPU exchange cells (edge-sharded solver).  One double travels as a 16-byte cell {lo32, tag, hi32, tag} written with ONE
+// vector store: each 8-byte half carries its own copy of the sequence tag, 8-byte stores are atomic over NVLink and in L2, so a
+// reader that sees both tags equal to the sequence number it waits for has the value -- no fence, no separate flag, and the
+// producer can push cells into peer memory while it is still computing (the low-latency protocol of NCCL, applied per double).
+// The exchange block of a rank (cudaMalloc, zero-initialised, mapped by every peer over NVLink) holds, double buffered by
+// sequence parity and indexed by SOURCE rank:   cg [2][W][3N]   lin [2][W][9N]   tail [2][W][4]     (cells)
+// ------------------------------------------------------------------------------------------
+struct alignas(16) LLCell { uint32_t lo, t0, hi, t1; };
+constexpr int kMaxPeers = 16;
+struct PeerPtrs { LLCell* p[kMaxPeers]; };
+__host__ __device__ inline size_t ll_cells_total(uint32_t N, int world) { return 2ull * world * (12ull * N + 4); }
+__host__ __device__ inline size_t ll_cg_offset(uint32_t N, int world, unsigned seq, int src) { return ((size_t)(seq & 1u) * world + src) * 3ull * N; }
+__host__ __device__ inline size_t ll_lin_offset(uint32_t N, int world, unsigned seq, int src) { return 2ull * world * 3ull * N + ((size_t)(seq & 1u) * world + src) * 9ull * N; }
+__host__ __device__ inline size_t ll_tail_offset(uint32_t N, int world, unsigned seq, int src) { return 2ull * world * 12ull * N + ((size_t)(seq & 1u) * world + src) * 4ull; }
+__device__ __forceinline__ void ll_store(LLCell* p, double v, uint32_t tag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((uint32_t)b), "r"(tag), "r"((uint32_t)(b >> 32)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ bool ll_try_load(const LLCell* p, uint32_t tag, double& v) {
+  uint32_t a, b, c, d;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+  v = __longlong_as_double((long long)(((unsigned long long)c << 32) | a));
+  return b == tag && d == tag;
+}
+// Spin until the cell carries `tag` (a peer that never shows up: ~4 s, then *bad = 2 instead of a hung GPU).
+__device__ __forceinline__ double ll_wait(const LLCell* p, uint32_t tag, int* bad) {
+  double v;
+  if (ll_try_load(p, tag, v)) return v;
+  const long long t0 = clock64();
+  while (!ll_try_load(p, tag, v)) {
+    if (clock64() - t0 > 8000000000ll) { *bad = 2; return 0.0; }
+  }
+  return v;
+}
+
+// K cells at once: the loads of one poll are issued back to back (one L2 round trip), all tags are then checked together.
+template <int K>
+__device__ __forceinline__ void ll_wait_n(const LLCell* c, uint32_t tag, double (&a)[K], int* bad) {
+  long long t0 = 0;
+  while (true) {
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < K; ++k) ok = ll_try_load(c + k, tag, a[k]) && ok;
+    if (ok) return;
+    if (t0 == 0) t0 = clock64();
+    else if (clock64() - t0 > 8000000000ll) {
+      *bad = 2;
+#pragma unroll
+      for (int k = 0; k < K; ++k) a[k] = 0.0;
+      return;
+    }
+  }
 }
 
 // Deterministic grid-wide sum of NV values: block tree -> per-block slot -> the LAST block to

@@ -309,6 +309,97 @@ __global__ void k_node_finalize(uint32_t N, const uint32_t* __restrict__ node_ta
   }
 }
 
+// Edge-sharded form of k_node_finalize with the cross-GPU reduction INSIDE the kernel (no NCCL call: the trust-region batch
+// stays one CUDA graph).  Per view: the shard-local sums [Hd 6 | gt 3] go out as tagged cells into the exchange block of every
+// rank (LLCell, ra_common.cuh; sequence number = evaluation counter sc->eseq + 1), then the thread waits for the W contributions
+// of its view in its own block, adds them in rank order (bitwise identical everywhere) and post-processes as k_node_finalize
+// does.  The cost and the bad flag travel the same way through the tail cells once this rank's grid-wide sum is complete.
+// Spinning on peers is safe in a plain launch: what a rank waits for is pushed by its peers before THEY wait for anything.
+__global__ void k_node_finalize_ll(uint32_t N, const uint32_t* __restrict__ node_task_ptr, const double* __restrict__ part,
+                                   const double* __restrict__ node_JL, double* __restrict__ Hd, double* __restrict__ gt,
+                                   double* __restrict__ ediag, double* slots, unsigned* counter, DevScalars* sc, HostMailbox* mailbox,
+                                   unsigned mailbox_seq, const IterParams* ip, PeerPtrs peers, int world, int rank) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned eseq = (unsigned)sc->eseq + 1u;
+  int bad = 0;
+  double v[2] = {0.0, 0.0};
+  if (i < N) {
+    double a[kPartStride];
+#pragma unroll
+    for (int k = 0; k < kPartStride; ++k) a[k] = 0.0;
+    for (uint32_t t = node_task_ptr[i]; t < node_task_ptr[i + 1]; ++t) {
+#pragma unroll
+      for (int k = 0; k < kPartStride; ++k) a[k] += part[(size_t)t * kPartStride + k];
+    }
+    v[0] = a[9];
+    for (int r = 0; r < world; ++r) {
+      LLCell* dst = peers.p[r] + ll_lin_offset(N, world, eseq, rank) + 9 * (size_t)i;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) ll_store(dst + k, a[k], eseq);
+    }
+  }
+  // this rank's cost: deterministic grid sum; its last block sends it to everybody
+  double tot[2];
+  if (grid_sum<2>(v, slots, counter, tot) && threadIdx.x == 0) {
+    for (int r = 0; r < world; ++r) {
+      LLCell* dst = peers.p[r] + ll_tail_offset(N, world, eseq, rank);
+      ll_store(dst, tot[0], eseq);
+    }
+  }
+  double gm = 0.0;
+  double w[2] = {0.0, 0.0};
+  if (i < N) {
+    double a[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a[k] = 0.0;
+    const LLCell* mine = peers.p[rank];
+    for (int r = 0; r < world; ++r) {
+      double b9[9];
+      ll_wait_n<9>(mine + ll_lin_offset(N, world, eseq, r) + 9 * (size_t)i, eseq, b9, &bad);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) a[k] += b9[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Hd[6 * (size_t)i + k] = a[k];
+    gt[3 * (size_t)i] = a[6]; gt[3 * (size_t)i + 1] = a[7]; gt[3 * (size_t)i + 2] = a[8];
+    double J[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) J[k] = node_JL[9 * (size_t)i + k];
+    double He[6];
+    congruence(J, a, He);
+    ediag[3 * (size_t)i] = He[0]; ediag[3 * (size_t)i + 1] = He[3]; ediag[3 * (size_t)i + 2] = He[5];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gm = fmax(gm, fabs(J[c] * a[6] + J[3 + c] * a[7] + J[6 + c] * a[8]));
+    if (!(isfinite(a[0]) && isfinite(a[3]) && isfinite(a[5]) && isfinite(a[6]) && isfinite(a[7]) && isfinite(a[8]))) w[0] = 1.0;
+  }
+  if (bad) w[1] = 1.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+  if ((threadIdx.x & 31) == 0 && gm > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(&sc->gmax), (unsigned long long)__double_as_longlong(gm));
+  // second grid-wide sum (its own slots and counter): non-finite flag, lost-peer flag; its last block closes the evaluation
+  double tot2[2];
+  if (grid_sum<2>(w, slots + 2 * (size_t)gridDim.x + 8, counter + 1, tot2) && threadIdx.x == 0) {
+    const LLCell* mine = peers.p[rank];
+    double cost = 0.0;
+    for (int r = 0; r < world; ++r) cost += ll_wait(mine + ll_tail_offset(N, world, eseq, r), eseq, &bad);
+    sc->cost = cost;
+    sc->eseq = (int)eseq;
+    if (tot2[0] != 0.0 || !isfinite(cost)) sc->bad = 1;
+    if (tot2[1] != 0.0 || bad) sc->bad = 2;
+    if (mailbox) {
+      if (ip) mailbox_seq = ip->seq;
+      sc->t_end = gtimer_ns();
+      __threadfence();
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(sc);
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(&mailbox->sc);
+#pragma unroll
+      for (int k = 0; k < (int)(sizeof(DevScalars) / 8); ++k) dst[k] = __ldcg(src + k);
+      __threadfence_system();
+      mailbox->seq = mailbox_seq;
+    }
+  }
+}
+
 // Jacobi scaling, estimated once at the initial point (Ceres: scale_c = 1/(1 + |J_col c|)).
 __global__ void k_jacobi_scale(uint32_t n3, const double* __restrict__ ediag, double* __restrict__ scale, int enabled) {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;

@@ -97,7 +97,8 @@ __global__ void k_prepare_solve(uint32_t N, PrepareArgs A, double* slots, unsign
 template <int kBlk, typename Finish>
 __device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restrict__ recs, uint64_t lo, uint64_t hi, uint32_t t0, uint32_t t1,
                                             const uint32_t* __restrict__ seg_begin, const uint32_t* __restrict__ seg_len, const double* x4,
-                                            bool nogather, uint32_t keep8, Finish&& finish) {
+                                            const double* xs /*shared-memory copy of x, stride 3, or null*/, bool nogather, uint32_t keep8,
+                                            Finish&& finish) {
   constexpr int kRD = Rec<kBlk>::kDoubles, kCR = Chunk<kBlk>::kRecs, kCD = Chunk<kBlk>::kDoubles;
   const int lane = threadIdx.x & 31;
   const uint32_t nrec = (uint32_t)((hi - lo + 31) >> 5);
@@ -128,6 +129,7 @@ __device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restri
     uint32_t col = reinterpret_cast<const uint32_t*>(rec + Rec<kBlk>::kColOffset)[lane] & ~kSideBit;
     if (h >= hi) col = 0;  // padding lanes of the last record
     if (nogather) { x0 = col; x1 = 1.0; x2 = 2.0; return; }  // measurement aid: stream-only ceiling
+    if (xs) { const double* p = xs + 3 * (size_t)col; x0 = p[0]; x1 = p[1]; x2 = p[2]; return; }
     const double4 xv = reinterpret_cast<const double4*>(x4)[col];
     x0 = xv.x; x1 = xv.y; x2 = xv.z;
   };
@@ -232,7 +234,7 @@ k_spmv(uint32_t num_warps, uint64_t H, uint32_t warp_span, const uint32_t* __res
   WarpPipe wp;
   pipe_init<kBlk>(wp, smem_raw);
   const uint64_t lo = (uint64_t)gw * warp_span, hi = min(H, lo + warp_span);
-  spmv_stream<kBlk>(wp, recs, lo, hi, warp_seg_ptr[gw], warp_seg_ptr[gw + 1], task_begin, task_len, x4, check_done == 2, keep8,
+  spmv_stream<kBlk>(wp, recs, lo, hi, warp_seg_ptr[gw], warp_seg_ptr[gw + 1], task_begin, task_len, x4, nullptr, check_done == 2, keep8,
                     [&](uint32_t t, double y0, double y1, double y2) {
                       if (lane == 0) { ypart[3 * (size_t)t] = y0; ypart[3 * (size_t)t + 1] = y1; ypart[3 * (size_t)t + 2] = y2; }
                     });
@@ -399,11 +401,10 @@ __global__ void k_apply_step(uint32_t N, ApplyArgs A, double* slots, unsigned* c
   }
 }
 
-constexpr int kMaxPeers = 16;
-
 struct PcgParams {
   uint32_t N, num_warps, n_iso, warp_span;
   uint32_t keep8;  // records of every 8 loaded with the evict_last L2 policy (0: no cache hints)
+  uint32_t slice_views;  // N when z is staged in shared memory for the gather (N <= kSliceMaxViews), else 0
   int max_iter;
   uint64_t H;
   double rtol2;
@@ -422,12 +423,10 @@ struct PcgParams {
   PrepareArgs prep;
   ApplyArgs apply;
   double *cand_q, *cand_JL;
-  // edge-sharded multi-GPU (world > 1): every rank's exchange block, mapped into this process over NVLink
-  // (CUDA IPC).  Layout of one block: double y[2][3N] (partial matvec, double buffered by step parity) followed
-  // by the rank's sequence flag.  peer_y[rank] / peer_flag[rank] are this rank's own block.
+  // edge-sharded multi-GPU (world > 1): every rank's exchange block (ra_common.cuh, LLCell), mapped into this process over
+  // NVLink (CUDA IPC between processes, peer access inside one).  peer[rank] is this rank's own block.
   int world, rank;
-  double* peer_y[kMaxPeers];
-  unsigned* peer_flag[kMaxPeers];
+  LLCell* peer[kMaxPeers];
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -480,9 +479,11 @@ __device__ __forceinline__ void finish_row(const PcgParams& P, uint32_t row, dou
 // One SpMV pass over this warp's range, s = (Ht + Lam) z.  Accumulates (per lane) gamma = r.z and delta = z.s over
 // the rows this lane finished.
 template <int kBlk>
-__device__ __forceinline__ void spmv_pass(const PcgParams& P, WarpPipe& wp, double& gamma, double& delta, double* ylocal_out = nullptr) {
-  // ylocal_out != null (multi-GPU): only the shard-local off-diagonal row sums are produced, into the exchange
-  // buffer; diagonal and inner products follow after the cross-GPU reduction (exchange_finish).
+__device__ __forceinline__ void spmv_pass(const PcgParams& P, WarpPipe& wp, double& gamma, double& delta, const double* zs, unsigned xseq = 0u) {
+  // xseq != 0 (multi-GPU, exchange step xseq): only the shard-local off-diagonal row sums are produced; the row owner PUSHES
+  // them, tagged with xseq, into the exchange block of every rank (its own included) while the pass is still running;
+  // diagonal and inner products follow once the W contributions of a row have arrived (exchange_finish).
+  const bool push = xseq != 0u;
   const int lane = threadIdx.x & 31;
   const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (gwarp < P.num_warps) {
@@ -510,8 +511,11 @@ __device__ __forceinline__ void spmv_pass(const PcgParams& P, WarpPipe& wp, doub
             my0 += __ldcg(P.ypart + 3 * (size_t)k); my1 += __ldcg(P.ypart + 3 * (size_t)k + 1); my2 += __ldcg(P.ypart + 3 * (size_t)k + 2);
           }
         }
-        if (ylocal_out) {
-          ylocal_out[3 * (size_t)row] = my0; ylocal_out[3 * (size_t)row + 1] = my1; ylocal_out[3 * (size_t)row + 2] = my2;
+        if (push) {
+          for (int r = 0; r < P.world; ++r) {
+            LLCell* dst = P.peer[r] + ll_cg_offset(P.N, P.world, xseq, P.rank) + 3 * (size_t)row;
+            ll_store(dst, my0, xseq); ll_store(dst + 1, my1, xseq); ll_store(dst + 2, my2, xseq);
+          }
         } else {
           finish_row(P, row, my0, my1, my2, gamma, delta);
         }
@@ -519,7 +523,7 @@ __device__ __forceinline__ void spmv_pass(const PcgParams& P, WarpPipe& wp, doub
       nbatch = 0;
       __syncwarp();
     };
-    spmv_stream<kBlk>(wp, P.val, lo, hi, t0, t1, P.seg_begin, P.seg_len, P.z, false, P.keep8, [&](uint32_t t, double y0, double y1, double y2) {
+    spmv_stream<kBlk>(wp, P.val, lo, hi, t0, t1, P.seg_begin, P.seg_len, P.z, zs, false, P.keep8, [&](uint32_t t, double y0, double y1, double y2) {
       const uint32_t rowf = P.seg_row[t];
       if (rowf & kSideBit) {  // continuation of a row owned by an earlier warp
         if (lane == 0) {
@@ -534,44 +538,56 @@ __device__ __forceinline__ void spmv_pass(const PcgParams& P, WarpPipe& wp, doub
     });
     if (nbatch) flush();
   }
-  // views without any half-edge: s_i = D_i z_i  (multi-GPU: their exchange slots stay zero, nothing to do)
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; !ylocal_out && k < P.n_iso; k += gridDim.x * blockDim.x)
-    finish_row(P, P.iso[k], 0.0, 0.0, 0.0, gamma, delta);
+  // views without any half-edge (in this shard): s_i = D_i z_i; multi-GPU: a tagged zero contribution
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n_iso; k += gridDim.x * blockDim.x) {
+    if (push) {
+      for (int r = 0; r < P.world; ++r) {
+        LLCell* dst = P.peer[r] + ll_cg_offset(P.N, P.world, xseq, P.rank) + 3 * (size_t)P.iso[k];
+        ll_store(dst, 0.0, xseq); ll_store(dst + 1, 0.0, xseq); ll_store(dst + 2, 0.0, xseq);
+      }
+    } else {
+      finish_row(P, P.iso[k], 0.0, 0.0, 0.0, gamma, delta);
+    }
+  }
 }
 
-// Fused cross-GPU reduction of the partial matvec, inside the persistent kernel (no NCCL call, no kernel
-// boundary): publish "my partial sums for step `seq` are complete" with a system-scope release, wait for every
-// peer's flag, then every rank adds the partial vectors of ALL ranks in rank order straight out of peer memory
-// over NVLink (bitwise identical result everywhere) and finishes the row: s_i = D_i z_i + sum, inner products.
-// Buffer reuse is safe with two buffers: a rank can only reach step seq+2 after every peer published seq+1,
-// i.e. after every peer finished reading step seq.
-__device__ __forceinline__ void exchange_finish(const PcgParams& P, cg::grid_group& grid, unsigned seq, double& gamma, double& delta) {
-  grid.sync();  // all local row sums of this step are in my exchange buffer
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    __threadfence_system();
-    *((volatile unsigned*)P.peer_flag[P.rank]) = seq;
-  }
-  if (threadIdx.x == 0) {
-    const long long t0 = clock64();
-    for (int r = 0; r < P.world; ++r) {
-      if (r == P.rank) continue;
-      volatile unsigned* f = (volatile unsigned*)P.peer_flag[r];
-      while ((int)(*f - seq) < 0) {
-        if (clock64() - t0 > 8000000000ll) { P.sc->bad = 2; break; }  // ~4 s: a peer died; do not hang the GPU
+// Fused cross-GPU reduction of the partial matvec, inside the persistent kernel: no NCCL call, no kernel boundary, no grid
+// barrier and no fence.  Every rank pushed its row sums as tagged cells into every rank's exchange block during the pass
+// (spmv_pass); here the views are dealt to groups of 4 lanes, lane q of a group waits for the cells of ranks q, q+4, ... in its
+// OWN block (local memory: the peers' stores arrive over NVLink), the group adds them in a fixed order -- bitwise identical on
+// every rank -- and finishes the row: s_i = D_i z_i + sum, inner products.  Two buffers (step parity) suffice: a rank reaches
+// step seq+2 only after it finished step seq+1, which needs every peer's seq+1 cells, which a peer sends only after it finished
+// reading step seq.
+__device__ __forceinline__ void exchange_finish(const PcgParams& P, unsigned seq, double& gamma, double& delta) {
+  constexpr int G = 4;
+  const int lane = threadIdx.x & 31, sub = lane & (G - 1);
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const LLCell* mine = P.peer[P.rank];
+  int bad = 0;
+  for (uint32_t vb = gw * (32 / G); vb < P.N; vb += nwarps * (32 / G)) {
+    const uint32_t i = vb + (uint32_t)(lane / G);
+    double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+    if (i < P.N) {
+      for (int r = sub; r < P.world; r += G) {
+        const LLCell* c = mine + ll_cg_offset(P.N, P.world, seq, r) + 3 * (size_t)i;
+        double a0, a1, a2;
+        long long t0 = 0;
+        while (true) {  // the three loads of a poll are issued together
+          const bool ok0 = ll_try_load(c, seq, a0), ok1 = ll_try_load(c + 1, seq, a1), ok2 = ll_try_load(c + 2, seq, a2);
+          if (ok0 && ok1 && ok2) break;
+          if (t0 == 0) t0 = clock64();
+          else if (clock64() - t0 > 8000000000ll) { bad = 2; a0 = a1 = a2 = 0.0; break; }  // ~4 s: a peer died; do not hang the GPU
+        }
+        y0 += a0; y1 += a1; y2 += a2;
       }
     }
-    __threadfence_system();
-  }
-  __syncthreads();
-  const size_t off = (size_t)(seq & 1u) * 3 * P.N;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.N; i += gridDim.x * blockDim.x) {
-    double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-    for (int r = 0; r < P.world; ++r) {
-      const double* src = P.peer_y[r] + off + 3 * (size_t)i;
-      y0 += __ldcv(src); y1 += __ldcv(src + 1); y2 += __ldcv(src + 2);
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) {
+      y0 += __shfl_xor_sync(0xffffffffu, y0, o); y1 += __shfl_xor_sync(0xffffffffu, y1, o); y2 += __shfl_xor_sync(0xffffffffu, y2, o);
     }
-    finish_row(P, i, y0, y1, y2, gamma, delta);
+    if (i < P.N && sub == 0) finish_row(P, i, y0, y1, y2, gamma, delta);
   }
+  if (bad) P.sc->bad = bad;
 }
 
 template <int kBlk>
@@ -604,18 +620,28 @@ __global__ void __launch_bounds__(kPcgBlock, kPcgBlocksPerSM) k_pcg_persistent(P
   int iter = 0, breakdown = 0;
   const bool multi = P.world > 1;
   unsigned seq = multi ? (unsigned)P.sc->xseq : 0u;  // exchange sequence number, continues across launches
-  double* my_y = multi ? P.peer_y[P.rank] : nullptr;
   while (!done) {
     // ---- phase A: s = (Ht + Lam) z, gamma = r.z, delta = z.s ---------------------------------
     const bool prof = P.prof != nullptr && gtid == 0;
     unsigned long long tA = 0, tB = 0, tC = 0, tE = 0, tF = 0;
     if (prof) tA = gtimer();
     double g_part = 0.0, d_part = 0.0;
-    if (!multi) spmv_pass<kBlk>(P, wp, g_part, d_part);
+    const double* zs = nullptr;
+    if (P.slice_views) {  // stage z (final since the barrier that closed the previous phase) for the gather
+      constexpr int kSliceOffset = kPcgWarps * kStages2 * Chunk<kBlk>::kBytes + kPcgWarps * kStages2 * 8;  // == spmv_smem_bytes(kBlk)
+      double* sl = reinterpret_cast<double*>(smem_raw + kSliceOffset);
+      for (uint32_t i = threadIdx.x; i < P.slice_views; i += blockDim.x) {
+        const double4 zv = reinterpret_cast<const double4*>(P.z)[i];
+        sl[3 * i] = zv.x; sl[3 * i + 1] = zv.y; sl[3 * i + 2] = zv.z;
+      }
+      __syncthreads();
+      zs = sl;
+    }
+    if (!multi) spmv_pass<kBlk>(P, wp, g_part, d_part, zs);
     else {
-      ++seq;
-      spmv_pass<kBlk>(P, wp, g_part, d_part, my_y + (size_t)(seq & 1u) * 3 * P.N);
-      exchange_finish(P, grid, seq, g_part, d_part);
+      if (++seq == 0u) ++seq;  // 0 means "no exchange" in spmv_pass
+      spmv_pass<kBlk>(P, wp, g_part, d_part, zs, seq);
+      exchange_finish(P, seq, g_part, d_part);
     }
     if (prof) tB = gtimer();
     double gamma, delta;

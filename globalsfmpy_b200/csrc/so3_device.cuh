@@ -216,9 +216,9 @@ __host__ __device__ inline void magsac_loss(const DevLoss& L, double s_in, doubl
   }
 }
 
-// Quintic Hermite interpolation of a tabulated loss (include/gsfm_ra.h, GSFM_RA_LOSS_TABULATED): rho from the polynomial
-// matching (rho, rho', rho'') at the two enclosing knots, rho' and rho'' by differentiating that polynomial.  The knot index
-// comes straight from the exponent and the leading mantissa bits of s.
+// Hermite interpolation of a tabulated loss (include/gsfm_ra.h, GSFM_RA_LOSS_TABULATED): rho from the quintic polynomial
+// matching (rho, rho', rho'') at the two enclosing knots, rho' from the cubic matching (rho', rho''), rho'' as the derivative
+// of that cubic.  The knot index comes straight from the exponent and the leading mantissa bits of s.
 __host__ __device__ inline void tabulated_loss(const DevLoss& L, double s, double* out) {
   const double* T = L.table;
   if (!(s > 0.0)) { out[0] = T[0]; out[1] = T[1]; out[2] = T[2]; return; }
@@ -248,13 +248,12 @@ __host__ __device__ inline void tabulated_loss(const DevLoss& L, double s, doubl
   const double t = (s - s0) / h, t2 = t * t, t3 = t2 * t, t4 = t3 * t, t5 = t4 * t;
   const double H0 = 1.0 - 10.0 * t3 + 15.0 * t4 - 6.0 * t5, H1 = t - 6.0 * t3 + 8.0 * t4 - 3.0 * t5, H2 = 0.5 * t2 - 1.5 * t3 + 1.5 * t4 - 0.5 * t5;
   const double H3 = 10.0 * t3 - 15.0 * t4 + 6.0 * t5, H4 = -4.0 * t3 + 7.0 * t4 - 3.0 * t5, H5 = 0.5 * t3 - t4 + 0.5 * t5;
-  const double G0 = -30.0 * t2 + 60.0 * t3 - 30.0 * t4, G1 = 1.0 - 18.0 * t2 + 32.0 * t3 - 15.0 * t4, G2 = t - 4.5 * t2 + 6.0 * t3 - 2.5 * t4;
-  const double G3 = -G0, G4 = -12.0 * t2 + 28.0 * t3 - 15.0 * t4, G5 = 1.5 * t2 - 4.0 * t3 + 2.5 * t4;
-  const double K0 = -60.0 * t + 180.0 * t2 - 120.0 * t3, K1 = -36.0 * t + 96.0 * t2 - 60.0 * t3, K2 = 1.0 - 9.0 * t + 18.0 * t2 - 10.0 * t3;
-  const double K3 = -K0, K4 = -24.0 * t + 84.0 * t2 - 60.0 * t3, K5 = 3.0 * t - 12.0 * t2 + 10.0 * t3;
   out[0] = f0 * H0 + d0 * H1 + c0 * H2 + f1 * H3 + d1 * H4 + c1 * H5;
-  out[1] = (f0 * G0 + d0 * G1 + c0 * G2 + f1 * G3 + d1 * G4 + c1 * G5) / h;
-  out[2] = (f0 * K0 + d0 * K1 + c0 * K2 + f1 * K3 + d1 * K4 + c1 * K5) / (h * h);
+  // rho' from the cubic Hermite polynomial of (rho', rho'') alone and rho'' as its derivative: the step then never depends on
+  // rounding noise in the object's rho values (differences of rho between neighbouring knots can be below its own precision)
+  const double g0 = A[1], g1 = A[4], e0 = A[2] * h, e1 = A[5] * h;
+  out[1] = g0 * (2.0 * t3 - 3.0 * t2 + 1.0) + e0 * (t3 - 2.0 * t2 + t) + g1 * (-2.0 * t3 + 3.0 * t2) + e1 * (t3 - t2);
+  out[2] = (g0 * (6.0 * t2 - 6.0 * t) + e0 * (3.0 * t2 - 4.0 * t + 1.0) + g1 * (-6.0 * t2 + 6.0 * t) + e1 * (3.0 * t2 - 2.0 * t)) / h;
 }
 
 // The closed-form losses below MAGSAC, parameters passed explicitly (outer and inner function of a composition share it).

@@ -404,6 +404,51 @@ def align_rotations(omega_ref, omega):
     return so3_log(R @ G)
 
 
+def align_rotations_robust(omega_ref, omega, loss_width=0.1, max_iterations=500):
+    """AlignRotations of the reference (src/compare_reconstructions.cpp:149-177): G = argmin sum rho(|ref_i - Log(R_i Exp(g))|^2),
+    rho = ceres::CauchyLoss(0.1), g an angle-axis vector started at 0, Levenberg-Marquardt with IRLS weights (three
+    unknowns; forward-difference Jacobian).  Returns omega' with Exp(omega'_i) = Exp(omega_i) Exp(g).  Unlike the chordal
+    alignment above this one is NOT invariant to the branch of the angle-axis vectors, exactly like the reference's."""
+    ref = np.asarray(omega_ref, dtype=np.float64).reshape(-1, 3)
+    R = so3_exp(np.asarray(omega, dtype=np.float64).reshape(-1, 3))
+    b = loss_width * loss_width
+
+    def resid(g):
+        return (ref - so3_log(R @ so3_exp(g))).ravel()
+
+    def cost(r):
+        s = (r.reshape(-1, 3) ** 2).sum(axis=1)
+        return 0.5 * float(np.sum(b * np.log1p(s / b)))
+    g = np.zeros(3)
+    r = resid(g)
+    c = cost(r)
+    lam = 1e-4
+    for _ in range(max_iterations):
+        J = np.empty((len(r), 3))
+        for k in range(3):
+            d = np.zeros(3); d[k] = 1e-7
+            J[:, k] = (resid(g + d) - r) / 1e-7
+        w = np.repeat(1.0 / (1.0 + (r.reshape(-1, 3) ** 2).sum(axis=1) / b), 3)     # rho'
+        H = J.T @ (w[:, None] * J)
+        grad = J.T @ (w * r)
+        if np.abs(grad).max() < 1e-12:
+            break
+        step = np.linalg.solve(H + lam * np.diag(np.maximum(np.diag(H), 1e-12)), -grad)
+        r2 = resid(g + step)
+        c2 = cost(r2)
+        if c2 < c:
+            g, r, lam = g + step, r2, max(lam / 3.0, 1e-12)
+            if c - c2 <= 1e-16 * c or np.linalg.norm(step) < 1e-14:
+                c = c2
+                break
+            c = c2
+        else:
+            lam *= 4.0
+            if lam > 1e12:
+                break
+    return so3_log(R @ so3_exp(g))
+
+
 def angular_difference(omega_a, omega_b):
     """AngularDifference (src/compare_reconstructions.cpp:7-16): angle of R_a^T R_b, radians."""
     Ra, Rb = so3_exp(omega_a), so3_exp(omega_b)

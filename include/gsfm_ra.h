@@ -86,8 +86,9 @@ typedef enum {
  * GSFM_RA_LOSS_TABULATED (as f; g must be trivial): rho, rho', rho'' of an arbitrary loss object sampled by the host at the knots
  *   s_0 = 0,   s_{1 + o * per_octave + m} = 2^(min_exp + o) * (1 + m / per_octave),   o < octaves, m < per_octave,
  *   plus the closing knot 2^(min_exp + octaves)  =>  table holds 2 + octaves * per_octave rows of 3 doubles.
- * The device interpolates rho with the quintic Hermite polynomial of (rho, rho', rho'') at the two enclosing knots and
- * differentiates that polynomial for rho', rho'' (consistent derivatives); beyond the last knot rho is continued linearly.
+ * The device interpolates rho with the quintic Hermite polynomial of (rho, rho', rho'') at the two enclosing knots, rho' with
+ * the cubic Hermite polynomial of (rho', rho'') and rho'' as the derivative of that cubic; beyond the last knot rho is
+ * continued linearly.
  * per_octave must be a power of two <= 4096.                                                                              */
 typedef struct {
   int32_t kind;     /* gsfm_ra_loss_kind                                            */
@@ -119,7 +120,9 @@ typedef struct {
                                 order, src/uncertainty.cpp:200-229) or NULL          */
   const double* edge_weight; /* [E] scalar weight or NULL (=1)                       */
   int32_t error_type;        /* gsfm_ra_error_type                                  */
-  int32_t reserved;
+  int32_t total_pair_count;  /* gsfm_ra_solve_sigma_consensus only: size of the caller's view-pair map INCLUDING the pairs it
+                                skipped (the reference's stop test averages |w - w_prev| over that count,
+                                rotation_estimator.cpp:419-424); 0 = num_edges                                      */
 } gsfm_ra_problem;
 
 typedef enum {
@@ -211,6 +214,8 @@ typedef struct {
   int32_t outer_iterations;
   int32_t num_linear_unconverged; /* PCG solves that stopped at pcg_max_iterations above pcg_rtol (their steps were still used) */
   double last_weight_change;
+  int32_t n_gpus_used;            /* devices the solve ran on (1 unless options.n_gpus asked for more and the problem qualified) */
+  int32_t reserved;
 } gsfm_ra_summary;
 
 typedef struct gsfm_ra_solver gsfm_ra_solver; /* opaque, device-resident problem */
@@ -234,7 +239,8 @@ int gsfm_ra_solve(const gsfm_ra_problem* problem, const gsfm_ra_options* options
  *      (rotation_estimator.cpp:314-457).  Up to iters_num times: per edge w = (C3*2/sigma_max) *
  *      (Gamma_table[round(1000 r^2 / (2 sigma_max^2))] - Gamma_k) from the angular residual r at the current
  *      rotations (weight_zero below DBL_EPSILON), a full trust-region solve of PairwiseRotationError(omega_ij, w)
- *      under options->loss, stop once mean |w - w_prev| <= 1e-7 (checked after the solve, as the reference does).
+ *      under options->loss, stop once mean |w - w_prev| <= 1e-7 (checked after the solve, as the reference does).  The
+ *      caller's trace buffer receives the rows of every inner solve one after the other.
  *      problem->error_type must be GSFM_RA_ANGLE_AXIS; problem->edge_weight is ignored.                        */
 int gsfm_ra_solve_sigma_consensus(const gsfm_ra_problem* problem, const gsfm_ra_options* options, int32_t iters_num,
                                   double sigma_max, double* omega_inout, gsfm_ra_summary* summary);

@@ -22,6 +22,7 @@
 #define GSFM_ROTATION_ESTIMATOR_HPP_
 
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <string>
 #include <type_traits>
@@ -53,6 +54,44 @@ inline gsfm_ra_loss MAGSACWeightBasedLoss(double sigma, bool use_weight_inverse 
   return MakeLoss(kind, sigma, 0.0, use_weight_inverse ? 1u : 0u);
 }
 inline gsfm_ra_loss ScaledLoss(gsfm_ra_loss rho, double a) { rho.scale = (rho.scale == 0.0 ? 1.0 : rho.scale) * a; return rho; }
+// ComposedLoss(f, g): rho(s) = f(g(s))  scripts/loss_functions.py:250-265.  f, g: closed-form losses (g below MAGSAC), neither
+// composed itself; anything deeper goes through TabulatedLoss.
+inline gsfm_ra_loss ComposedLoss(const gsfm_ra_loss& f, const gsfm_ra_loss& g) {
+  gsfm_ra_loss l = f;
+  l.inner_kind = g.kind; l.inner_flags = g.flags; l.inner_scale = (g.scale == 0.0 ? 1.0 : g.scale);
+  for (int k = 0; k < 4; ++k) l.inner_p[k] = g.p[k];
+  return l;
+}
+
+// ANY loss object with the ceres::LossFunction interface -- `void Evaluate(double s, double out[3]) const` -- as a device
+// table (GSFM_RA_LOSS_TABULATED): this is the adapter for the borrowed `ceres::LossFunction*` the reference's estimator takes
+// (include/GSfM_nonlinear_rotation_estimator.hpp:41-49) and for the pybind11 trampoline pyLossFunction
+// (bind_src/GlobalSfMpy.cpp:33-65).  The object is called once per knot (2 + 144 * 32 times) instead of once per edge per
+// evaluation; the table lives in this adapter, which must outlive the solve.
+class TabulatedLoss {
+ public:
+  static constexpr int kMinExp = -80, kOctaves = 144, kPerOctave = 32;
+  template <class LossLike>
+  explicit TabulatedLoss(const LossLike& f) : table_(3 * (size_t)(2 + kOctaves * kPerOctave)) {
+    size_t row = 0;
+    auto put = [&](double s) { f.Evaluate(s, &table_[3 * row]); ++row; };
+    put(0.0);
+    for (int o = 0; o < kOctaves; ++o)
+      for (int m = 0; m < kPerOctave; ++m) put(std::ldexp(1.0 + (double)m / kPerOctave, kMinExp + o));
+    put(std::ldexp(1.0, kMinExp + kOctaves));
+    loss_ = MakeLoss(GSFM_RA_LOSS_TABULATED);
+    loss_.table = table_.data();
+    loss_.table_min_exp = kMinExp; loss_.table_octaves = kOctaves; loss_.table_per_octave = kPerOctave;
+  }
+  TabulatedLoss(const TabulatedLoss&) = delete;
+  TabulatedLoss& operator=(const TabulatedLoss&) = delete;
+  const gsfm_ra_loss& get() const { return loss_; }
+  operator const gsfm_ra_loss&() const { return loss_; }
+
+ private:
+  std::vector<double> table_;
+  gsfm_ra_loss loss_;
+};
 
 // ---- theia::RotationEstimator ------------------------------------------------------------------------------------
 template <class ViewPairs, class Orientations>
@@ -172,7 +211,11 @@ class GSfMNonlinearRotationEstimator : public RotationEstimator<ViewPairs, Orien
 
  private:
   void EnsureOptions() {
-    if (!options_ready_) { gsfm_ra_default_options(&options_); options_ready_ = true; }
+    if (!options_ready_) {
+      gsfm_ra_default_options(&options_);
+      options_.n_gpus = -1;  // behind the plugin API the view graph shards over the box's GPUs by itself once it is large enough
+      options_ready_ = true;
+    }
   }
 
   template <class Covariances, class Matches>
@@ -190,6 +233,7 @@ class GSfMNonlinearRotationEstimator : public RotationEstimator<ViewPairs, Orien
     p.cov6 = f.cov6.empty() ? nullptr : f.cov6.data();
     p.edge_weight = f.weight.empty() ? nullptr : f.weight.data();
     p.error_type = error_type;
+    p.total_pair_count = sigma_iters > 0 && view_pairs.size() < 0x7fffffffu ? static_cast<int32_t>(view_pairs.size()) : 0;
     EnsureOptions();
     gsfm_ra_options o = options_;
     o.loss = loss;

@@ -191,6 +191,28 @@ int main(int argc, char** argv) {
     Check(est.EstimateRotationsWithSigmaConsensus(pairs, &o, gsfm_b200::TrivialLoss(), 1, 5, 0.05), "EstimateRotationsWithSigmaConsensus");
     Check(MeanError(o, gt, n) < 0.5 * M_PI / 180.0 && est.summary().outer_iterations >= 1, "  converges below 0.5 deg");
   }
+  {  // a borrowed ceres::LossFunction-shaped object (what the reference's estimator takes, and what the pybind11 trampoline
+     // pyLossFunction is) through the tabulating adapter, against the closed-form loss of the same formula; and ComposedLoss
+    struct CeresCauchy {  // ceres::CauchyLoss(a): rho = b log(1 + s / b)
+      double b, c;
+      explicit CeresCauchy(double a) : b(a * a), c(1.0 / (a * a)) {}
+      void Evaluate(double s, double* rho) const {
+        const double sum = 1.0 + s * c, inv = 1.0 / sum;
+        rho[0] = b * std::log(sum); rho[1] = inv > 2.2250738585072014e-308 ? inv : 2.2250738585072014e-308; rho[2] = -c * (inv * inv);
+      }
+    } ceres_loss(0.1);
+    gsfm_b200::TabulatedLoss tab(ceres_loss);
+    Orientations o1 = init, o2 = init;
+    Check(est.EstimateRotationsWithCustomizedLossAndCovariance(pairs, &o1, tab, 1, covs, GSFM_RA_ANGLE_AXIS), "TabulatedLoss adapter (any object with Evaluate(s, rho[3]))");
+    Check(est.EstimateRotationsWithCustomizedLossAndCovariance(pairs, &o2, gsfm_b200::CauchyLoss(0.1), 1, covs, GSFM_RA_ANGLE_AXIS), "  closed-form CauchyLoss");
+    const double d = MeanError(o1, o2, n);
+    std::printf("      tabulated vs closed form: mean difference %.3e rad\n", d);
+    Check(d < 1e-6, "  the tabulated object reproduces the closed form to 1e-6 rad");
+    Orientations o3 = init;
+    Check(est.EstimateRotationsWithCustomizedLossAndCovariance(pairs, &o3, gsfm_b200::ComposedLoss(gsfm_b200::CauchyLoss(0.5), gsfm_b200::HuberLoss(0.05)), 1, covs,
+                                                               GSFM_RA_ANGLE_AXIS), "ComposedLoss(Cauchy, Huber)");
+    Check(MeanError(o3, gt, n) < 0.5 * M_PI / 180.0, "  converges below 0.5 deg");
+  }
   {  // the steps before the solve, on the device: initial view-graph filter and spanning-tree initialisation
     ViewPairs vp = pairs;
     vp[{(ViewId)0, (ViewId)1}].num_verified_matches = 5;        // below the threshold: removed (the ring keeps 0 and 1 connected)

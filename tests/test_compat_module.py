@@ -193,7 +193,13 @@ def test_pipeline_call_sequence_on_madrid(sfm, golden_dir, madrid):
     n0 = view_graph.NumEdges()
     est.FilterRotations()
     keep, _ = solver.filter_view_pairs(prob, ref, 15.0)
-    assert view_graph.NumEdges() == int(keep.sum()) < n0
+    # ... followed by RemoveDisconnectedViewPairs: the largest component of what the filter kept, orientations of the rest erased
+    # (src/GSfM_global_reconstruction_estimator.cpp:509-524)
+    kept = np.nonzero(keep)[0]
+    ij = np.stack([madrid.edge_i[kept], madrid.edge_j[kept]], axis=1).astype(np.int64)
+    in_cc, cc_ids = vg.filter_initial_view_graph(np.arange(madrid.num_views), ij, np.ones(len(kept), np.int64), 0)
+    assert view_graph.NumEdges() == int(in_cc.sum()) <= int(keep.sum()) < n0
+    assert set(est.orientations) == set(int(madrid.view_ids[k]) for k in cc_ids) == set(view_graph.ViewIds())
 
 
 @pytest.mark.gpu

@@ -31,6 +31,91 @@ def test_sharded_solver_matches_single_gpu():
         assert v["mean"] < 1e-7, (name, v)
 
 
+@pytest.mark.gpu
+def test_one_process_multi_device_solve():
+    """options.n_gpus behind the C ABI: ONE process, one host thread per device, exchange blocks wired by peer
+    access.  A 4M-edge graph solved on W devices must take the single-GPU trajectory (same iterations, costs to 1e-9) and
+    land within 1e-7 rad of it; n_gpus = -1 engages the devices by itself at this size."""
+    import torch
+    sys.path.insert(0, ROOT)
+    from globalsfmpy_b200 import _capi as capi, solver as S, viewgraph as vg
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    W = 2 if n < 4 else 4
+    g = vg.synthetic_pose_graph(20000, 4000000, seed=9, noise_deg=1.0, outlier_fraction=0.1, init="bfs")
+    prob = S.make_problem(g, capi.ANGLE_AXIS)
+    o = capi.default_options_py()
+    o.loss = capi.Loss.make(capi.LOSS_CAUCHY, 0.05)
+    o.pcg_rtol = 1e-12
+    o.pcg_max_iterations = 2000
+    # both runs converge tightly: on a 4M-edge graph with 10 % outliers the 1e-16 differences of the cross-GPU summation order
+    # grow along the LM trajectory (6.5e-7 relative cost difference mid-way, measured), so minimisers are compared, not paths
+    o.function_tolerance, o.gradient_tolerance, o.parameter_tolerance, o.max_num_iterations = 1e-14, 1e-12, 1e-12, 400
+    o.device = 0
+    om1, s1, t1 = S.solve(prob, o, g.omega_init, trace_capacity=512)
+    assert s1.n_gpus_used == 1
+    o.n_gpus = W
+    omw, sw, tw = S.solve(prob, o, g.omega_init, trace_capacity=512)
+    assert sw.n_gpus_used == W
+    n_same = next((k for k, (a, b) in enumerate(zip(tw, t1)) if abs(a.cost - b.cost) > 1e-9 * abs(b.cost)), min(len(tw), len(t1)))
+    mean, mx = vg.mean_angular_error(om1, omw)
+    print(f"MGPU_INPROC world {W}: iterations {sw.num_iterations} vs {s1.num_iterations} (costs equal to 1e-9 for the first {n_same}), final cost "
+          f"{sw.final_cost:.12e} vs {s1.final_cost:.12e}, mean angular error vs single GPU {mean:.3e} rad (max {mx:.3e}), "
+          f"{s1.ms_total:.1f} ms -> {sw.ms_total:.1f} ms")
+    assert n_same >= 10
+    assert abs(sw.final_cost - s1.final_cost) <= 1e-9 * s1.final_cost
+    assert mean < 1e-7
+    o.n_gpus = -1        # auto: 4M edges / 0.5M per device -> up to 8 devices
+    oma, sa, _ = S.solve(prob, o, g.omega_init)
+    print('MGPU_INPROC auto world', sa.n_gpus_used)
+    assert sa.n_gpus_used == min(n, 8) and vg.mean_angular_error(om1, oma)[0] < 1e-7
+    # small problems stay on one device whatever is asked (dense factorisation path)
+    g2 = vg.synthetic_pose_graph(200, 3000, seed=3)
+    o2 = capi.default_options_py()
+    o2.loss = o.loss
+    o2.n_gpus = W
+    _, s2, _ = S.solve(S.make_problem(g2, capi.ANGLE_AXIS), o2, g2.omega_init)
+    assert s2.n_gpus_used == 1
+
+
+@pytest.mark.gpu
+def test_module_api_uses_several_devices(monkeypatch):
+    """EstimateGlobalRotationsUncertainty of the GlobalSfMpy-compatible module on a graph above the per-device threshold
+    (lowered through the environment so that a dict-based view graph stays small): more than one device, same answer."""
+    import importlib
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "globalsfmpy_b200", "compat"))
+    sfm = importlib.import_module("GlobalSfMpy")
+    from globalsfmpy_b200 import _capi as capi, viewgraph as vg, loss_functions as lf
+    g = vg.synthetic_pose_graph(1500, 40000, seed=21, noise_deg=1.0, outlier_fraction=0.1, covariance=True, init="bfs")
+    graph, covs = sfm.ViewGraph(), sfm.MapEdgesCovariance()
+    for k in range(g.num_edges):
+        info = sfm.TwoViewInfo()
+        info.rotation_2 = g.omega_ij[k].copy()
+        info.num_verified_matches = 100
+        a, b = int(g.edge_i[k]), int(g.edge_j[k])
+        graph.AddEdge(a, b, info)
+        c = g.cov6[k]
+        covs[(a, b)] = (np.array([[c[0], c[3], c[4]], [c[3], c[1], c[5]], [c[4], c[5], c[2]]]), np.zeros(3))
+    res = {}
+    for name, env in (("one", "1000000000"), ("many", "10000")):
+        monkeypatch.setenv("GSFM_RA_MIN_EDGES_PER_GPU", env)
+        est = sfm.GlobalReconstructionEstimator(sfm.ReconstructionEstimatorOptions())
+        est.view_graph_, est.reconstruction_ = graph, sfm.Reconstruction()
+        t = capi.default_options_py()      # converge tightly so that the two runs are comparable at the 1e-7 rad level
+        t.function_tolerance, t.gradient_tolerance, t.parameter_tolerance, t.max_num_iterations = 1e-14, 1e-12, 1e-12, 400
+        t.pcg_rtol, t.pcg_max_iterations, t.n_gpus = 1e-12, 2000, -1
+        est.solver_options = t
+        assert est.EstimateGlobalRotationsUncertainty(lf.SoftLOneLoss(1.0), covs, sfm.RotationErrorType.ANGLE_AXIS_COVARIANCE)
+        res[name] = (np.array([est.orientations[v] for v in range(g.num_views)]), sfm._solve.last_summary.n_gpus_used)
+    assert res["one"][1] == 1 and res["many"][1] == min(n, 4, 8)
+    assert vg.mean_angular_error(res["one"][0], res["many"][0])[0] < 1e-7
+
+
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
     import torch
