@@ -333,6 +333,17 @@ def accuracy_report(S, vg, capi, prob, g, opt, oracle_budget_edges=2500000):
     rep["cost_rel_diff_gpu_vs_oracle_at_same_point"] = abs(c_o - s_b.final_cost) / abs(c_o)
     _, grad_o, _, _, _, _ = orc.assemble(prob, opt.loss, om_t, num_threads=cores)
     rep["oracle_gradient_max_norm_at_gpu_tight_solution"] = float(np.abs(grad_o).max())
+    # converged vs converged (the north_star bar, <= 1e-4 rad): the oracle, started AT the GPU's tight solution with the same
+    # tight tolerances, is allowed to move -- how far it goes is the distance between the two minimisers
+    op = capi.clone(t)
+    op.num_threads = cores
+    op.max_num_iterations = 25
+    t0 = time.perf_counter()
+    om_op, s_op, _ = orc.solve(prob, op, om_t)
+    rep.update({"mean_angular_error_converged_vs_oracle_rad": vg.mean_angular_error(om_op, om_t)[0],
+                "oracle_polish": {"start": "the GPU's tight solution", "lm_iterations": s_op.num_iterations, "initial_cost": s_op.initial_cost,
+                                  "final_cost": s_op.final_cost, "termination": capi.TERMINATION[s_op.termination],
+                                  "seconds": time.perf_counter() - t0}})
     if g.num_edges <= oracle_budget_edges:
         oo = capi.clone(p)
         oo.num_threads = cores
@@ -344,7 +355,12 @@ def accuracy_report(S, vg, capi, prob, g, opt, oracle_budget_edges=2500000):
                                        "1e-12), native loss, all cores",
                     "mean_angular_error_vs_oracle_rad": vg.mean_angular_error(om_o, om_b)[0],
                     "mean_angular_error_exact_pcg_vs_oracle_rad": vg.mean_angular_error(om_o, om_p)[0],
-                    "mean_angular_error_tight_vs_oracle_rad": vg.mean_angular_error(om_o, om_t)[0]})
+                    "mean_angular_error_tight_vs_oracle_rad": vg.mean_angular_error(om_o, om_t)[0],
+                    "mean_angular_error_oracle_default_vs_oracle_converged_rad": vg.mean_angular_error(om_op, om_o)[0],
+                    "note": "Ceres' default stopping rule (relative cost change <= 1e-6) ends a solve well short of the minimiser on this "
+                            "outlier-rich graph: the oracle's own default-tolerance answer sits `..._oracle_default_vs_oracle_converged_rad` "
+                            "from its converged one, so distances to it measure where each run happened to stop, not solver error; "
+                            "`mean_angular_error_converged_vs_oracle_rad` compares minimisers"})
     else:
         rep["oracle_solve"] = f"skipped: {g.num_edges} edges cost the CPU oracle ~{g.num_edges / 1.8e6:.0f} s per LM iteration"
     return rep

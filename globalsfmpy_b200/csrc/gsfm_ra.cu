@@ -289,6 +289,8 @@ struct gsfm_ra_solver {
   // structure
   DevBuf<uint32_t> he_col, he_row, he_edge, iso;
   uint32_t n_iso = 0;
+  ColBlocks cbk = {};    // column blocks of the half-edge order (ra_structure.cuh)
+  bool slice = false;    // the persistent PCG kernel stages a block's slice of z in shared memory
   Partition pk1, pk2;  // K1 (edge kernel) and K2 (SpMV / PCG) partitions
   // per half-edge constants, planar
   DevBuf<double> loss_table;  // device copy of a tabulated loss (GSFM_RA_LOSS_TABULATED)
@@ -396,8 +398,7 @@ struct gsfm_ra_solver {
   int rec_doubles() const { return blk * 32 + 16; }
   int smem_bytes() const { return spmv_smem_bytes(blk); }
   // persistent PCG kernel: + the shared-memory copy of z for small graphs (GSFM_RA_NO_SLICE=1 disables it, A/B runs)
-  bool use_slice() const { return N <= (uint32_t)kSliceMaxViews && !std::getenv("GSFM_RA_NO_SLICE"); }
-  int pcg_smem_bytes() const { return spmv_smem_bytes(blk) + (use_slice() ? (int)(24u * N + 16u) : 0); }
+  int pcg_smem_bytes() const { return spmv_smem_bytes(blk) + (slice ? (int)(24u * cbk.cbsize + 16u) : 0); }
   // K1 is specialised on (Jacobian?, residual kind, scalar weight?, loss): the common losses get their own instantiation
   // (no switch, fewer registers), everything else runs the generic one.
   typedef void (*K1Fn)(const K1Args);
@@ -455,21 +456,21 @@ struct gsfm_ra_solver {
     double* tail = lin[b].p + 9ull * N;
     const int co = jacobian ? 0 : 1;
     if (!sharded()) {
-      k_node_finalize<<<grid_for(N), kBlock, 0, stream>>>(N, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd_p[b], gt_p[b], ediag[b].p, co, 0, tail,
+      k_node_finalize<<<grid_for(N), kBlock, 0, stream>>>(N, cbk.ncb, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd_p[b], gt_p[b], ediag[b].p, co, 0, tail,
                                                            slots.p, counter.p, sc.p, mb, mseq, publish ? ip_dev : nullptr);
     } else if (peers_connected && jacobian) {
       // edge-sharded, fused exchange: the reduction of [Hd | gt | cost] across GPUs happens inside the kernel (peer memory)
       PeerPtrs pp;
       for (int r = 0; r < kMaxPeers; ++r) pp.p[r] = (LLCell*)peer_base[r];
-      k_node_finalize_ll<<<grid_for(N), kBlock, 0, stream>>>(N, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd_p[b], gt_p[b], ediag[b].p, slots.p, counter.p,
+      k_node_finalize_ll<<<grid_for(N), kBlock, 0, stream>>>(N, cbk.ncb, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd_p[b], gt_p[b], ediag[b].p, slots.p, counter.p,
                                                               sc.p, mb, mseq, publish ? ip_dev : nullptr, pp, world, rank);
     } else {
       // edge-sharded, NCCL: local sums -> ONE all-reduce of [Hd | gt | cost, bad] -> per-view post-processing
-      k_node_finalize<<<grid_for(N), kBlock, 0, stream>>>(N, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd_p[b], gt_p[b], ediag[b].p, co, 1, tail,
+      k_node_finalize<<<grid_for(N), kBlock, 0, stream>>>(N, cbk.ncb, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd_p[b], gt_p[b], ediag[b].p, co, 1, tail,
                                                            slots.p, counter.p, sc.p, nullptr, 0u, nullptr);
       if (jacobian) RA_TRY(allreduce(lin[b].p, 9ull * N + 2));
       else RA_TRY(allreduce(tail, 2));
-      k_node_finalize<<<grid_for(N), kBlock, 0, stream>>>(N, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd_p[b], gt_p[b], ediag[b].p, co, 2, tail,
+      k_node_finalize<<<grid_for(N), kBlock, 0, stream>>>(N, cbk.ncb, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd_p[b], gt_p[b], ediag[b].p, co, 2, tail,
                                                            slots.p, counter.p, sc.p, mb, mseq, publish ? ip_dev : nullptr);
       launches += 2;
     }
@@ -482,11 +483,11 @@ struct gsfm_ra_solver {
   int spmv(int b, const double* xin, double* yout, const double* diag_blocks) {
     launch_spmv(b, xin, 0);
     if (!sharded()) {
-      k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, pk2.node_seg_ptr.p, ypart.p, diag_blocks, xin, yout, nullptr, 1, slots.p, counter.p, sc.p);
+      k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, cbk.ncb, pk2.node_seg_ptr.p, ypart.p, diag_blocks, xin, yout, nullptr, 1, slots.p, counter.p, sc.p);
     } else {
-      k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, pk2.node_seg_ptr.p, ypart.p, nullptr, xin, yout, nullptr, 1, slots.p, counter.p, sc.p);
+      k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, cbk.ncb, pk2.node_seg_ptr.p, ypart.p, nullptr, xin, yout, nullptr, 1, slots.p, counter.p, sc.p);
       RA_TRY(allreduce(yout, 3ull * N));
-      k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, pk2.node_seg_ptr.p, ypart.p, diag_blocks, xin, yout, yout, 1, slots.p, counter.p, sc.p);
+      k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, cbk.ncb, pk2.node_seg_ptr.p, ypart.p, diag_blocks, xin, yout, yout, 1, slots.p, counter.p, sc.p);
       launches += 2;
     }
     launches += 2;
@@ -511,7 +512,8 @@ struct gsfm_ra_solver {
     PcgParams P;
     P.N = N; P.num_warps = pk2.num_warps; P.n_iso = n_iso; P.max_iter = max_iter; P.H = H; P.rtol2 = rtol * rtol;
     P.keep8 = keep8;
-    P.slice_views = use_slice() ? N : 0u;
+    P.cbk = cbk;
+    if (!slice) P.cbk.ncb = 0;
     P.warp_seg_ptr = pk2.warp_seg_ptr.p; P.seg_row = pk2.seg_row.p; P.seg_begin = pk2.seg_begin.p; P.seg_len = pk2.seg_len.p;
     P.node_seg_ptr = pk2.node_seg_ptr.p; P.iso = iso.p; P.warp_span = pk2.span;
     P.val = val[b].p; P.Dblk = Dblk.p; P.Minv = Minv.p;
@@ -578,12 +580,12 @@ struct gsfm_ra_solver {
       for (int k = 0; k < poll && enq < max_iter; ++k, ++enq) {
         launch_spmv(b, p.p, 1);
         if (!sharded()) {
-          k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, pk2.node_seg_ptr.p, ypart.p, Dblk.p, p.p, y.p, nullptr, 0, slots.p, counter.p, sc.p);
+          k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, cbk.ncb, pk2.node_seg_ptr.p, ypart.p, Dblk.p, p.p, y.p, nullptr, 0, slots.p, counter.p, sc.p);
         } else {
           // the ONE collective of a CG step: all-reduce of the 3N partial matvec
-          k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, pk2.node_seg_ptr.p, ypart.p, nullptr, p.p, y.p, nullptr, 1, slots.p, counter.p, sc.p);
+          k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, cbk.ncb, pk2.node_seg_ptr.p, ypart.p, nullptr, p.p, y.p, nullptr, 1, slots.p, counter.p, sc.p);
           RA_TRY(allreduce(y.p, 3ull * N));
-          k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, pk2.node_seg_ptr.p, ypart.p, Dblk.p, p.p, y.p, y.p, 0, slots.p, counter.p, sc.p);
+          k_spmv_finish<<<grid_for(N), kBlock, 0, stream>>>(N, cbk.ncb, pk2.node_seg_ptr.p, ypart.p, Dblk.p, p.p, y.p, y.p, 0, slots.p, counter.p, sc.p);
           launches += 2;
         }
         k_pcg_update<<<grid_for(N), kBlock, 0, stream>>>(N, Minv.p, p.p, y.p, x.p, r.p, z.p, rtol2, max_iter, slots.p, counter.p, sc.p);
@@ -706,17 +708,32 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   if (prob->edge_weight) RA_TRY(up64(s->d_weight, prob->edge_weight + e0, E));
   lap("enqueue uploads");
 
-  // ---- half-edges sorted by (row, col): keys -> radix sort -> unpack ----------------------------
+  // ---- half-edges sorted by (column block, row, col): keys -> radix sort -> unpack (ra_structure.cuh) ---------------
+  // column blocks: as few as keep a block's slice of the gathered vector within the shared-memory budget; none (one block,
+  // plain row-major order, gather from L2) beyond kMaxColBlocks * kSliceMaxViews views or with GSFM_RA_NO_SLICE=1
+  {
+    // Measured (profiles/r02_col_blocks.txt): at 10k views / 1M edges four column blocks cut the L2 gather traffic but quadruple
+    // the segments (row sums to reduce, publish and collect) and the CG step goes from 31 to 49 us, K1 from 60 to 69 us -- so
+    // several blocks are an experiment switch (GSFM_RA_COL_BLOCKS=n), and the default is ONE block: graphs of <= kSliceMaxViews
+    // views gather from shared memory, larger ones from L2.
+    uint32_t ncb = 1;
+    if (const char* e = std::getenv("GSFM_RA_COL_BLOCKS")) ncb = (uint32_t)std::min(kMaxColBlocks, std::max(1, std::atoi(e)));
+    if (std::getenv("GSFM_RA_NO_SLICE")) ncb = 1;
+    s->cbk.ncb = ncb;
+    s->cbk.cbsize = (N + ncb - 1) / ncb;
+    s->slice = s->cbk.cbsize <= (uint32_t)kSliceMaxViews && !std::getenv("GSFM_RA_NO_SLICE");
+  }
+  const uint32_t ncb = s->cbk.ncb, cbsize = s->cbk.cbsize, NP = ncb * N;
   DevBuf<int> d_err;
   DevBuf<uint64_t> keys_a, keys_b;
-  DevBuf<uint32_t> vals_a, vals_b, rowptr, flags_ne, flags_iso, nz_rank, iso_rank;
-  RA_TRY(d_err.alloc(4));
-  CUDA_TRY(cudaMemsetAsync(d_err.p, 0, 4 * sizeof(int), st));
+  DevBuf<uint32_t> vals_a, vals_b, pieceptr, flags_ne, flags_iso, nz_rank, iso_rank;
+  RA_TRY(d_err.alloc(4 + kMaxColBlocks + 1));
+  CUDA_TRY(cudaMemsetAsync(d_err.p, 0, (4 + kMaxColBlocks + 1) * sizeof(int), st));
   RA_TRY(keys_a.alloc(H)); RA_TRY(keys_b.alloc(H)); RA_TRY(vals_a.alloc(H)); RA_TRY(vals_b.alloc(H));
-  k_build_keys<<<grid_for(E), kBlock, 0, st>>>(E, N, s->d_ei.p, s->d_ej.p, keys_a.p, vals_a.p, d_err.p);
+  k_build_keys<<<grid_for(E), kBlock, 0, st>>>(E, N, cbsize, s->d_ei.p, s->d_ej.p, keys_a.p, vals_a.p, d_err.p);
   {
     int bits = 1;
-    while (bits < 64 && ((uint64_t)N * N - 1) >> bits) ++bits;
+    while (bits < 64 && ((uint64_t)NP * N - 1) >> bits) ++bits;
     size_t bytes = 0;
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_a.p, keys_b.p, vals_a.p, vals_b.p, (int)H, 0, bits, st));
     DevBuf<unsigned char> tmp;
@@ -725,15 +742,18 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   }
   RA_TRY(s->he_col.alloc(H)); RA_TRY(s->he_row.alloc(H)); RA_TRY(s->he_edge.alloc(H));
   k_unpack_keys<<<grid_for(H), kBlock, 0, st>>>(H, N, keys_b.p, vals_b.p, s->he_row.p, s->he_col.p, s->he_edge.p, d_err.p);
-  RA_TRY(rowptr.alloc(N + 2)); RA_TRY(flags_ne.alloc(N + 2)); RA_TRY(flags_iso.alloc(N + 2)); RA_TRY(nz_rank.alloc(N + 2)); RA_TRY(iso_rank.alloc(N + 2));
-  k_rowptr<<<grid_for(N + 1), kBlock, 0, st>>>(N, H, keys_b.p, rowptr.p);
-  k_row_flags<<<grid_for(N + 1), kBlock, 0, st>>>(N, rowptr.p, flags_ne.p, flags_iso.p);
-  RA_TRY(exclusive_scan(flags_ne.p, nz_rank.p, N + 1, st));
+  RA_TRY(pieceptr.alloc(NP + 2)); RA_TRY(flags_ne.alloc(NP + 2)); RA_TRY(nz_rank.alloc(NP + 2)); RA_TRY(flags_iso.alloc(N + 2)); RA_TRY(iso_rank.alloc(N + 2));
+  k_pieceptr<<<grid_for(NP + 1), kBlock, 0, st>>>(NP, N, H, keys_b.p, pieceptr.p);
+  k_piece_flags<<<grid_for(NP + 1), kBlock, 0, st>>>(NP, pieceptr.p, flags_ne.p);
+  k_iso_flags<<<grid_for(N + 1), kBlock, 0, st>>>(N, ncb, pieceptr.p, flags_iso.p);
+  RA_TRY(exclusive_scan(flags_ne.p, nz_rank.p, NP + 1, st));
   RA_TRY(exclusive_scan(flags_iso.p, iso_rank.p, N + 1, st));
   RA_TRY(s->iso.alloc(N));
   k_iso_fill<<<grid_for(N), kBlock, 0, st>>>(N, flags_iso.p, iso_rank.p, s->iso.p);
   CUDA_TRY(cudaMemcpyAsync(d_err.p + 1, iso_rank.p + N, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));  // n_iso
-  s->launches += 6;
+  for (uint32_t cb = 0; cb <= ncb; ++cb)  // first half-edge of every column block
+    CUDA_TRY(cudaMemcpyAsync(d_err.p + 4 + cb, pieceptr.p + (size_t)cb * N, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  s->launches += 7;
 
   // ---- balanced partitions, one per kernel class, sized to exactly one resident wave of that kernel ----
   const int occ_k2 = di->occ_k2[s->blk == 4 ? 0 : s->blk == 6 ? 1 : 2];
@@ -752,17 +772,18 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
     const uint32_t nw = (uint32_t)std::max<uint64_t>(1, (H + per - 1) / per);
     const uint32_t nw_sizing = (uint32_t)std::max<uint64_t>(1, (H_sizing + per - 1) / per);
     P.num_warps = nw; P.span = (uint32_t)per;
-    P.num_segs = nw + N;  // upper bound: every range start + every row start opens one segment
+    P.num_segs = nw + NP;  // upper bound: every range start + every piece start opens one segment
     P.grid = (nw_sizing + warps_per_block - 1) / warps_per_block;
     DevBuf<uint32_t> nseg, cnt;
-    RA_TRY(nseg.alloc(nw + 2)); RA_TRY(cnt.alloc(N + 2));
+    RA_TRY(nseg.alloc(nw + 2)); RA_TRY(cnt.alloc(NP + 2));
     RA_TRY(P.warp_seg_ptr.alloc(nw + 2)); RA_TRY(P.seg_row.alloc(P.num_segs)); RA_TRY(P.seg_begin.alloc(P.num_segs));
-    RA_TRY(P.seg_len.alloc(P.num_segs)); RA_TRY(P.node_seg_ptr.alloc(N + 2));
-    k_part_count<<<grid_for(nw + 1), kBlock, 0, st>>>(nw, (uint32_t)per, H, s->he_row.p, nz_rank.p, nseg.p);
+    RA_TRY(P.seg_len.alloc(P.num_segs)); RA_TRY(P.node_seg_ptr.alloc(NP + 2));
+    k_part_count<<<grid_for(nw + 1), kBlock, 0, st>>>(nw, (uint32_t)per, H, N, cbsize, s->he_row.p, s->he_col.p, nz_rank.p, nseg.p);
     RA_TRY(exclusive_scan(nseg.p, P.warp_seg_ptr.p, nw + 1, st));
-    k_part_fill<<<grid_for(nw), kBlock, 0, st>>>(nw, (uint32_t)per, H, s->he_row.p, rowptr.p, P.warp_seg_ptr.p, P.seg_row.p, P.seg_begin.p, P.seg_len.p);
-    k_node_seg_count<<<grid_for(N + 1), kBlock, 0, st>>>(N, (uint32_t)per, rowptr.p, cnt.p);
-    RA_TRY(exclusive_scan(cnt.p, P.node_seg_ptr.p, N + 1, st));
+    k_part_fill<<<grid_for(nw), kBlock, 0, st>>>(nw, (uint32_t)per, H, N, cbsize, s->he_row.p, s->he_col.p, pieceptr.p, P.warp_seg_ptr.p, P.seg_row.p, P.seg_begin.p,
+                                                 P.seg_len.p);
+    k_node_seg_count<<<grid_for(NP + 1), kBlock, 0, st>>>(NP, (uint32_t)per, pieceptr.p, cnt.p);
+    RA_TRY(exclusive_scan(cnt.p, P.node_seg_ptr.p, NP + 1, st));
     s->launches += 5;
     return 0;
   };
@@ -840,13 +861,14 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   CUDA_TRY(cudaGetLastError());
   lap("enqueue K0 + allocations");
   // the only synchronisation of the build: input checks and the isolated-view count
-  int h_err[4] = {0, 0, 0, 0};
-  CUDA_TRY(cudaMemcpyAsync(h_err, d_err.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  int h_err[4 + kMaxColBlocks + 1] = {0};
+  CUDA_TRY(cudaMemcpyAsync(h_err, d_err.p, (4 + kMaxColBlocks + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   lap("wait for the device");
   if (h_err[0] == 1) { set_error("an edge is out of range or a self loop"); return GSFM_RA_ERR_INVALID; }
   if (h_err[0] == 2) { set_error("duplicate edge: the same view pair appears twice"); return GSFM_RA_ERR_INVALID; }
   s->n_iso = (uint32_t)h_err[1];
+  for (uint32_t cb = 0; cb <= ncb; ++cb) s->cbk.begin[cb] = (uint32_t)h_err[4 + cb];
   if (options->verbose >= 2) std::fprintf(stderr, "[gsfm_ra] setup total %.2f ms\n", now_ms() - tb0);
   s->ms_setup = s->elapsed_since(s->ev[0]);
   s->radius = options->initial_trust_region_radius;
@@ -1555,7 +1577,22 @@ int gsfm_ra_assemble(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss, c
   if (val || col) {
     RA_TRY(dval.alloc(9 * H));
     RA_TRY(dcol.alloc(H));
-    k_export_blocks<<<grid_for(H), kBlock, 0, s->stream>>>(H, s->blk, s->he_row.p, s->he_col.p, s->val[0].p, s->node_JL[0].p, dval.p, dcol.p);
+    // block-CSR order of the API = (row, col); a column-blocked layout is exported through the sorted permutation
+    DevBuf<uint64_t> ka, kb;
+    DevBuf<uint32_t> ia, ib;
+    const uint32_t* order = nullptr;
+    if (s->cbk.ncb > 1) {
+      RA_TRY(ka.alloc(H)); RA_TRY(kb.alloc(H)); RA_TRY(ia.alloc(H)); RA_TRY(ib.alloc(H));
+      k_rowmajor_keys<<<grid_for(H), kBlock, 0, s->stream>>>(H, N, s->he_row.p, s->he_col.p, ka.p, ia.p);
+      size_t bytes = 0;
+      CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, ka.p, kb.p, ia.p, ib.p, (int)H, 0, 64, s->stream));
+      DevBuf<unsigned char> tmp;
+      RA_TRY(tmp.alloc(bytes + 16));
+      CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, ka.p, kb.p, ia.p, ib.p, (int)H, 0, 64, s->stream));
+      CUDA_TRY(cudaStreamSynchronize(s->stream));  // tmp goes out of scope
+      order = ib.p;
+    }
+    k_export_blocks<<<grid_for(H), kBlock, 0, s->stream>>>(H, s->blk, s->he_row.p, s->he_col.p, s->val[0].p, s->node_JL[0].p, order, dval.p, dcol.p);
     CUDA_TRY(cudaGetLastError());
     if (val) CUDA_TRY(cudaMemcpyAsync(val, dval.p, 9 * H * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     if (col) CUDA_TRY(cudaMemcpyAsync(col, dcol.p, H * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));

@@ -100,9 +100,11 @@ __global__ void k_eval_loss(uint64_t n, const double* __restrict__ s, DevLoss lo
 
 // Tangent -> Euclidean export of the assembled system (API gsfm_ra_assemble).
 __global__ void k_export_blocks(uint64_t H, int blk, const uint32_t* __restrict__ he_row, const uint32_t* __restrict__ he_col, const double* __restrict__ val,
-                                const double* __restrict__ node_JL, double* out_val, uint32_t* out_col) {
-  const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= H) return;
+                                const double* __restrict__ node_JL, const uint32_t* __restrict__ order, double* out_val, uint32_t* out_col) {
+  // output position pos holds half-edge order[pos] (the (row, col)-sorted view of a column-blocked layout), or pos itself
+  const uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= H) return;
+  const uint64_t h = order ? order[pos] : pos;
   const uint32_t row = he_row[h], col = he_col[h] & ~kSideBit;
   double B[9], T[9];
   for (int r = 0; r < 3; ++r)
@@ -112,8 +114,15 @@ __global__ void k_export_blocks(uint64_t H, int blk, const uint32_t* __restrict_
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 3; ++c) T[3 * r + c] = B[3 * r] * Jc[c] + B[3 * r + 1] * Jc[3 + c] + B[3 * r + 2] * Jc[6 + c];
   for (int r = 0; r < 3; ++r)
-    for (int c = 0; c < 3; ++c) out_val[9 * h + 3 * r + c] = Jr[r] * T[c] + Jr[3 + r] * T[3 + c] + Jr[6 + r] * T[6 + c];
-  if (out_col) out_col[h] = col;
+    for (int c = 0; c < 3; ++c) out_val[9 * pos + 3 * r + c] = Jr[r] * T[c] + Jr[3 + r] * T[3 + c] + Jr[6 + r] * T[6 + c];
+  if (out_col) out_col[pos] = col;
+}
+__global__ void k_rowmajor_keys(uint64_t H, uint32_t N, const uint32_t* __restrict__ he_row, const uint32_t* __restrict__ he_col, uint64_t* __restrict__ keys,
+                                uint32_t* __restrict__ idx) {
+  const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  keys[h] = (uint64_t)he_row[h] * N + (he_col[h] & ~kSideBit);
+  idx[h] = (uint32_t)h;
 }
 __global__ void k_export_nodes(uint32_t N, const double* __restrict__ Hd, const double* __restrict__ gt, const double* __restrict__ node_JL,
                                double* hdiag9, double* grad) {

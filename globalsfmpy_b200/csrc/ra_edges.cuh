@@ -159,15 +159,13 @@ __global__ void __launch_bounds__(kBlock, 2) k_edges(const K1Args A) {
         for (int k = 0; k < kAcc; ++k) acc[k] += cur[k];
       }
       if (se > ce) break;  // the segment continues in the next record
-#pragma unroll
-      for (int k = 0; k < kAcc; ++k) acc[k] = warp_sum(acc[k]);
-      if (lane == 0) {
-        if (kWriteBlocks) {
-#pragma unroll
-          for (int k = 0; k < kPartStride; ++k) A.part[(size_t)t * kPartStride + k] = acc[k];
-        } else {
-          A.part[(size_t)t * kPartStride + 9] = acc[0];
-        }
+      if (kWriteBlocks) {  // the ten sums of the segment in one reduce-scatter butterfly; lane 2m ends up with value multi_index16(2m)
+        const double tot = warp_sum_multi16<kAcc>(acc);
+        const int idx = multi_index16(lane);
+        if (!(lane & 1) && idx < kPartStride) A.part[(size_t)t * kPartStride + idx] = tot;
+      } else {
+        const double c = warp_sum(acc[0]);
+        if (lane == 0) A.part[(size_t)t * kPartStride + 9] = c;
       }
 #pragma unroll
       for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
@@ -237,7 +235,7 @@ k_edges_general(uint32_t num_warps, uint64_t H, const uint32_t* __restrict__ war
 // Per view: add the task partials in task order -> tangent diagonal block Hd (packed sym 6),
 // tangent gradient gt; Euclidean gradient g = Jl^T gt (for the gradient tolerance), the Euclidean
 // diagonal diag(Jl^T Hd Jl) (for Jacobi scaling and the LM diagonal), total cost.
-__global__ void k_node_finalize(uint32_t N, const uint32_t* __restrict__ node_task_ptr, const double* __restrict__ part,
+__global__ void k_node_finalize(uint32_t N, uint32_t ncb, const uint32_t* __restrict__ node_task_ptr, const double* __restrict__ part,
                                 const double* __restrict__ node_JL, double* __restrict__ Hd, double* __restrict__ gt,
                                 double* __restrict__ ediag, int cost_only, int stage, double* tail, double* slots, unsigned* counter,
                                 DevScalars* sc, HostMailbox* mailbox, unsigned mailbox_seq, const IterParams* ip) {
@@ -251,13 +249,15 @@ __global__ void k_node_finalize(uint32_t N, const uint32_t* __restrict__ node_ta
 #pragma unroll
     for (int k = 0; k < kPartStride; ++k) a[k] = 0.0;
     if (stage != 2) {
-      for (uint32_t t = node_task_ptr[i]; t < node_task_ptr[i + 1]; ++t) {
-        if (cost_only) a[9] += part[(size_t)t * kPartStride + 9];
-        else {
+      // the row's segments: piece by piece (column block by column block), in segment order -- a fixed summation order
+      for (uint32_t cb = 0; cb < ncb; ++cb)
+        for (uint32_t t = node_task_ptr[cb * N + i]; t < node_task_ptr[cb * N + i + 1]; ++t) {
+          if (cost_only) a[9] += part[(size_t)t * kPartStride + 9];
+          else {
 #pragma unroll
-          for (int k = 0; k < kPartStride; ++k) a[k] += part[(size_t)t * kPartStride + k];
+            for (int k = 0; k < kPartStride; ++k) a[k] += part[(size_t)t * kPartStride + k];
+          }
         }
-      }
       v[0] = a[9];
       if (!cost_only) {
 #pragma unroll
@@ -315,7 +315,7 @@ __global__ void k_node_finalize(uint32_t N, const uint32_t* __restrict__ node_ta
 // of its view in its own block, adds them in rank order (bitwise identical everywhere) and post-processes as k_node_finalize
 // does.  The cost and the bad flag travel the same way through the tail cells once this rank's grid-wide sum is complete.
 // Spinning on peers is safe in a plain launch: what a rank waits for is pushed by its peers before THEY wait for anything.
-__global__ void k_node_finalize_ll(uint32_t N, const uint32_t* __restrict__ node_task_ptr, const double* __restrict__ part,
+__global__ void k_node_finalize_ll(uint32_t N, uint32_t ncb, const uint32_t* __restrict__ node_task_ptr, const double* __restrict__ part,
                                    const double* __restrict__ node_JL, double* __restrict__ Hd, double* __restrict__ gt,
                                    double* __restrict__ ediag, double* slots, unsigned* counter, DevScalars* sc, HostMailbox* mailbox,
                                    unsigned mailbox_seq, const IterParams* ip, PeerPtrs peers, int world, int rank) {
@@ -327,10 +327,11 @@ __global__ void k_node_finalize_ll(uint32_t N, const uint32_t* __restrict__ node
     double a[kPartStride];
 #pragma unroll
     for (int k = 0; k < kPartStride; ++k) a[k] = 0.0;
-    for (uint32_t t = node_task_ptr[i]; t < node_task_ptr[i + 1]; ++t) {
+    for (uint32_t cb = 0; cb < ncb; ++cb)
+      for (uint32_t t = node_task_ptr[cb * N + i]; t < node_task_ptr[cb * N + i + 1]; ++t) {
 #pragma unroll
-      for (int k = 0; k < kPartStride; ++k) a[k] += part[(size_t)t * kPartStride + k];
-    }
+        for (int k = 0; k < kPartStride; ++k) a[k] += part[(size_t)t * kPartStride + k];
+      }
     v[0] = a[9];
     for (int r = 0; r < world; ++r) {
       LLCell* dst = peers.p[r] + ll_lin_offset(N, world, eseq, rank) + 9 * (size_t)i;

@@ -2,6 +2,7 @@
 // Part of libgsfm_ra (one translation unit, see gsfm_ra.cu); reference citations sit next to each kernel.
 #pragma once
 #include "ra_common.cuh"
+#include "ra_structure.cuh"
 #include "ra_edges.cuh"
 namespace {
 
@@ -97,12 +98,17 @@ __global__ void k_prepare_solve(uint32_t N, PrepareArgs A, double* slots, unsign
 template <int kBlk, typename Finish>
 __device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restrict__ recs, uint64_t lo, uint64_t hi, uint32_t t0, uint32_t t1,
                                             const uint32_t* __restrict__ seg_begin, const uint32_t* __restrict__ seg_len, const double* x4,
-                                            const double* xs /*shared-memory copy of x, stride 3, or null*/, bool nogather, uint32_t keep8,
-                                            Finish&& finish) {
+                                            const double* xs /*shared-memory copy of x[xbase ...], stride 3, or null*/, uint32_t xbase, bool nogather,
+                                            uint32_t keep8, Finish&& finish) {
+  // CHUNK-major loop: the kCR records of a bulk copy are consumed together with compile-time indices -- their shared-memory
+  // reads, gathers and products are independent instruction streams (ILP = kCR), the loop / ring / address overhead is paid
+  // once per chunk instead of once per record, and the x gather of chunk k+1 (its columns are in shared memory as soon as
+  // its copy has landed) is issued before chunk k is consumed.  Positions are 32-bit offsets from the start of the range.
   constexpr int kRD = Rec<kBlk>::kDoubles, kCR = Chunk<kBlk>::kRecs, kCD = Chunk<kBlk>::kDoubles;
   const int lane = threadIdx.x & 31;
-  const uint32_t nrec = (uint32_t)((hi - lo + 31) >> 5);
-  const uint32_t nchunk = (nrec + kCR - 1) / kCR;  // bulk copies of this range: kCR consecutive records each (the last may be short)
+  const uint32_t n = (uint32_t)(hi - lo);           // half-edges of this range
+  const uint32_t nrec = (n + 31u) >> 5;
+  const uint32_t nchunk = (nrec + kCR - 1) / kCR;   // bulk copies of this range: kCR consecutive records each (the last may be short)
   const uint32_t base = wp.pos;
   const double* src = recs + (size_t)(lo >> 5) * kRD;
   uint64_t pol_keep = 0, pol_stream = 0;
@@ -125,68 +131,80 @@ __device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restri
     mbar_wait(&wp.bars[st], (p / kStages2) & 1u);
     return wp.ring + (size_t)st * kCD;
   };
-  auto gather = [&](const double* rec, uint64_t h, double& x0, double& x1, double& x2) {
-    uint32_t col = reinterpret_cast<const uint32_t*>(rec + Rec<kBlk>::kColOffset)[lane] & ~kSideBit;
-    if (h >= hi) col = 0;  // padding lanes of the last record
-    if (nogather) { x0 = col; x1 = 1.0; x2 = 2.0; return; }  // measurement aid: stream-only ceiling
-    if (xs) { const double* p = xs + 3 * (size_t)col; x0 = p[0]; x1 = p[1]; x2 = p[2]; return; }
-    const double4 xv = reinterpret_cast<const double4*>(x4)[col];
-    x0 = xv.x; x1 = xv.y; x2 = xv.z;
+  // x[col] of every record of chunk k (records past the end of the range and padding lanes read view 0: never accumulated)
+  auto gather_chunk = [&](const double* ch, uint32_t k, double (&g)[kCR][3]) {
+#pragma unroll
+    for (int j = 0; j < kCR; ++j) {
+      const uint32_t c = k * kCR + j;
+      uint32_t col = xbase;  // padding: any view that is certainly inside the staged slice
+      if (c < nrec) {
+        col = reinterpret_cast<const uint32_t*>(ch + j * kRD + Rec<kBlk>::kColOffset)[lane] & ~kSideBit;
+        if ((c << 5) + (uint32_t)lane >= n) col = xbase;
+      }
+      if (nogather) { g[j][0] = col; g[j][1] = 1.0; g[j][2] = 2.0; }  // measurement aid: stream-only ceiling
+      else if (xs) { const double* p = xs + 3 * (size_t)(col - xbase); g[j][0] = p[0]; g[j][1] = p[1]; g[j][2] = p[2]; }
+      else { const double4 xv = reinterpret_cast<const double4*>(x4)[col]; g[j][0] = xv.x; g[j][1] = xv.y; g[j][2] = xv.z; }
+    }
   };
   for (uint32_t k = 0; k < nchunk && k < (uint32_t)kStages2; ++k) issue(k);
   if (nrec == 0 || t0 == t1) { wp.pos = base + nchunk; return; }
   uint32_t t = t0;
-  uint64_t sb = seg_begin[t], se = sb + seg_len[t];
+  uint32_t sb = (uint32_t)(seg_begin[t] - lo), se = sb + seg_len[t];
   double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-  const double* rec = wait_chunk(0);
-  double x0, x1, x2;
-  gather(rec, lo + lane, x0, x1, x2);
-  for (uint32_t c = 0; c < nrec; ++c) {
-    const uint64_t cb = lo + ((uint64_t)c << 5), ce = cb + 32, h = cb + lane;
-    // prefetch the next record's gather
-    const double* rec_n = nullptr;
-    double n0 = 0.0, n1 = 0.0, n2 = 0.0;
-    if (c + 1 < nrec) {
-      rec_n = ((c + 1) % kCR == 0) ? wait_chunk((c + 1) / kCR) : rec + kRD;
-      gather(rec_n, ce + lane, n0, n1, n2);
+  const double* ch = wait_chunk(0);
+  double g[kCR][3];
+  gather_chunk(ch, 0, g);
+  for (uint32_t k = 0; k < nchunk; ++k) {
+    const double* ch_n = ch;
+    double gn[kCR][3];
+    if (k + 1 < nchunk) { ch_n = wait_chunk(k + 1); gather_chunk(ch_n, k + 1, gn); }
+    double v[kCR][3];
+#pragma unroll
+    for (int j = 0; j < kCR; ++j) {
+      const double* rec = ch + j * kRD;
+      const double x0 = g[j][0], x1 = g[j][1], x2 = g[j][2];
+      if (kBlk == 4) {
+        // -S x with S = |c0| I + sign(c0) h h^T
+        const double c0 = rec[lane], h0 = rec[32 + lane], h1 = rec[64 + lane], h2 = rec[96 + lane];
+        const double tt = h0 * x0 + h1 * x1 + h2 * x2;
+        const double a = fabs(c0);
+        const double st = __longlong_as_double(__double_as_longlong(tt) ^ (__double_as_longlong(c0) & (long long)0x8000000000000000ull));
+        v[j][0] = -(a * x0 + st * h0);
+        v[j][1] = -(a * x1 + st * h1);
+        v[j][2] = -(a * x2 + st * h2);
+      } else if (kBlk == 6) {
+        const double b0 = rec[lane], b1 = rec[32 + lane], b2 = rec[64 + lane], b3 = rec[96 + lane], b4 = rec[128 + lane], b5 = rec[160 + lane];
+        v[j][0] = b0 * x0 + b1 * x1 + b2 * x2;
+        v[j][1] = b1 * x0 + b3 * x1 + b4 * x2;
+        v[j][2] = b2 * x0 + b4 * x1 + b5 * x2;
+      } else {
+        v[j][0] = rec[lane] * x0 + rec[32 + lane] * x1 + rec[64 + lane] * x2;
+        v[j][1] = rec[96 + lane] * x0 + rec[128 + lane] * x1 + rec[160 + lane] * x2;
+        v[j][2] = rec[192 + lane] * x0 + rec[224 + lane] * x1 + rec[256 + lane] * x2;
+      }
     }
-    double v0, v1, v2;
-    if (kBlk == 4) {
-      // -S x with S = |c0| I + sign(c0) h h^T
-      const double c0 = rec[lane], h0 = rec[32 + lane], h1 = rec[64 + lane], h2 = rec[96 + lane];
-      const double t = h0 * x0 + h1 * x1 + h2 * x2;
-      const double a = fabs(c0);
-      const double st = __longlong_as_double(__double_as_longlong(t) ^ (__double_as_longlong(c0) & (long long)0x8000000000000000ull));
-      v0 = -(a * x0 + st * h0);
-      v1 = -(a * x1 + st * h1);
-      v2 = -(a * x2 + st * h2);
-    } else if (kBlk == 6) {
-      const double b0 = rec[lane], b1 = rec[32 + lane], b2 = rec[64 + lane], b3 = rec[96 + lane], b4 = rec[128 + lane], b5 = rec[160 + lane];
-      v0 = b0 * x0 + b1 * x1 + b2 * x2;
-      v1 = b1 * x0 + b3 * x1 + b4 * x2;
-      v2 = b2 * x0 + b4 * x1 + b5 * x2;
-    } else {
-      v0 = rec[lane] * x0 + rec[32 + lane] * x1 + rec[64 + lane] * x2;
-      v1 = rec[96 + lane] * x0 + rec[128 + lane] * x1 + rec[160 + lane] * x2;
-      v2 = rec[192 + lane] * x0 + rec[224 + lane] * x1 + rec[256 + lane] * x2;
+    // the chunk's stage can be refilled as soon as every lane has read it
+    __syncwarp();
+    if (k + kStages2 < nchunk) issue(k + kStages2);
+#pragma unroll
+    for (int j = 0; j < kCR; ++j) {
+      const uint32_t cb = (k * kCR + j) << 5, ce = cb + 32u, h = cb + (uint32_t)lane;
+      if (t != t1 && cb < n) {
+        while (true) {
+          if (h >= sb && h < se) { y0 += v[j][0]; y1 += v[j][1]; y2 += v[j][2]; }
+          if (se > ce) break;  // the segment continues in the next record
+          // lanes 0 / 8 / 16 receive the segment's three sums (component multi_index4(lane))
+          finish(t, warp_sum_multi3(y0, y1, y2));
+          y0 = y1 = y2 = 0.0;
+          if (++t == t1) break;
+          sb = se; se = sb + seg_len[t];
+          if (sb >= ce) break;
+        }
+      }
     }
-    // a chunk's stage can be refilled as soon as every lane has read its last record
-    if ((c + 1) % kCR == 0 || c + 1 == nrec) {
-      __syncwarp();
-      if (c / kCR + kStages2 < nchunk) issue(c / kCR + kStages2);
-    }
-    while (true) {
-      if (h >= sb && h < se) { y0 += v0; y1 += v1; y2 += v2; }
-      if (se > ce) break;  // the segment continues in the next record
-      y0 = warp_sum(y0); y1 = warp_sum(y1); y2 = warp_sum(y2);
-      finish(t, y0, y1, y2);
-      y0 = y1 = y2 = 0.0;
-      if (++t == t1) break;
-      sb = se; se = sb + seg_len[t];
-      if (sb >= ce) break;
-    }
-    rec = rec_n; x0 = n0; x1 = n1; x2 = n2;
-    if (t == t1) break;
+    ch = ch_n;
+#pragma unroll
+    for (int j = 0; j < kCR; ++j) { g[j][0] = gn[j][0]; g[j][1] = gn[j][1]; g[j][2] = gn[j][2]; }
   }
   wp.pos = base + nchunk;
 }
@@ -234,16 +252,16 @@ k_spmv(uint32_t num_warps, uint64_t H, uint32_t warp_span, const uint32_t* __res
   WarpPipe wp;
   pipe_init<kBlk>(wp, smem_raw);
   const uint64_t lo = (uint64_t)gw * warp_span, hi = min(H, lo + warp_span);
-  spmv_stream<kBlk>(wp, recs, lo, hi, warp_seg_ptr[gw], warp_seg_ptr[gw + 1], task_begin, task_len, x4, nullptr, check_done == 2, keep8,
-                    [&](uint32_t t, double y0, double y1, double y2) {
-                      if (lane == 0) { ypart[3 * (size_t)t] = y0; ypart[3 * (size_t)t + 1] = y1; ypart[3 * (size_t)t + 2] = y2; }
+  spmv_stream<kBlk>(wp, recs, lo, hi, warp_seg_ptr[gw], warp_seg_ptr[gw + 1], task_begin, task_len, x4, nullptr, 0u, check_done == 2, keep8,
+                    [&](uint32_t t, double ysum) {
+                      if ((lane & 7) == 0 && lane < 24) ypart[3 * (size_t)t + multi_index4(lane)] = ysum;
                     });
 }
 
 // y_i = Dblk_i x_i + sum of the row's task partials (+ shard-local only: the diagonal part is
 // added after the cross-GPU reduction).  mode 0: write y, reduce p.y -> alpha (PCG step 1).
 // mode 1: y only.
-__global__ void k_spmv_finish(uint32_t N, const uint32_t* __restrict__ node_task_ptr, const double* __restrict__ ypart,
+__global__ void k_spmv_finish(uint32_t N, uint32_t ncb, const uint32_t* __restrict__ node_task_ptr, const double* __restrict__ ypart,
                               const double* __restrict__ Dblk, const double* __restrict__ x, double* y, const double* ysum,
                               int mode, double* slots, unsigned* counter, DevScalars* sc) {
   // ysum != null: the off-diagonal part was already summed (and all-reduced across GPUs) into ysum
@@ -256,9 +274,10 @@ __global__ void k_spmv_finish(uint32_t N, const uint32_t* __restrict__ node_task
     if (Dblk) sym_mul_vec(Dblk + 6 * (size_t)i, xi, yi);
     if (ysum) { yi[0] += ysum[3 * (size_t)i]; yi[1] += ysum[3 * (size_t)i + 1]; yi[2] += ysum[3 * (size_t)i + 2]; }
     else
-      for (uint32_t t = node_task_ptr[i]; t < node_task_ptr[i + 1]; ++t) {
-        yi[0] += ypart[3 * (size_t)t]; yi[1] += ypart[3 * (size_t)t + 1]; yi[2] += ypart[3 * (size_t)t + 2];
-      }
+      for (uint32_t cb = 0; cb < ncb; ++cb)
+        for (uint32_t t = node_task_ptr[cb * N + i]; t < node_task_ptr[cb * N + i + 1]; ++t) {
+          yi[0] += ypart[3 * (size_t)t]; yi[1] += ypart[3 * (size_t)t + 1]; yi[2] += ypart[3 * (size_t)t + 2];
+        }
     y[3 * (size_t)i] = yi[0]; y[3 * (size_t)i + 1] = yi[1]; y[3 * (size_t)i + 2] = yi[2];
     v[0] = xi[0] * yi[0] + xi[1] * yi[1] + xi[2] * yi[2];
   }
@@ -404,7 +423,7 @@ __global__ void k_apply_step(uint32_t N, ApplyArgs A, double* slots, unsigned* c
 struct PcgParams {
   uint32_t N, num_warps, n_iso, warp_span;
   uint32_t keep8;  // records of every 8 loaded with the evict_last L2 policy (0: no cache hints)
-  uint32_t slice_views;  // N when z is staged in shared memory for the gather (N <= kSliceMaxViews), else 0
+  ColBlocks cbk;         // column blocks of the half-edge order; cbk.ncb = 0: no shared-memory staging of z
   int max_iter;
   uint64_t H;
   double rtol2;
@@ -479,7 +498,8 @@ __device__ __forceinline__ void finish_row(const PcgParams& P, uint32_t row, dou
 // One SpMV pass over this warp's range, s = (Ht + Lam) z.  Accumulates (per lane) gamma = r.z and delta = z.s over
 // the rows this lane finished.
 template <int kBlk>
-__device__ __forceinline__ void spmv_pass(const PcgParams& P, WarpPipe& wp, double& gamma, double& delta, const double* zs, unsigned xseq = 0u) {
+__device__ __forceinline__ void spmv_pass(const PcgParams& P, WarpPipe& wp, double& gamma, double& delta, const double* zs, uint32_t zbase,
+                                          unsigned xseq = 0u) {
   // xseq != 0 (multi-GPU, exchange step xseq): only the shard-local off-diagonal row sums are produced; the row owner PUSHES
   // them, tagged with xseq, into the exchange block of every rank (its own included) while the pass is still running;
   // diagonal and inner products follow once the W contributions of a row have arrived (exchange_finish).
@@ -488,55 +508,65 @@ __device__ __forceinline__ void spmv_pass(const PcgParams& P, WarpPipe& wp, doub
   const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (gwarp < P.num_warps) {
     const uint64_t lo = (uint64_t)gwarp * P.warp_span, hi = min(P.H, lo + P.warp_span);
-    // Rows are finished by a STATIC owner -- the warp holding the row's first segment -- so every
-    // sum has a fixed order and a fixed place (bit-reproducible).  A continuation segment (always the
-    // first segment of a warp's range) is published at once by lane 0: parts + fence + counter.
-    // Owned segments are parked one per lane and completed as a batch, so the wait / load latencies
-    // of up to 32 rows overlap instead of serialising while the record stream drains.  The owner
-    // spins on the row counter; the warps it waits for publish first thing in their pass and the
-    // cooperative launch keeps every block resident, so the wait cannot deadlock.
+    // Rows are finished by a STATIC owner -- the warp holding the row's first segment (first non-empty column block, first
+    // range) -- so every sum has a fixed order and a fixed place (bit-reproducible).  Every segment's sum goes to ypart[t];
+    // a segment that is not its row's first one also counts itself in on the row's counter.  Only when its whole range is
+    // streamed does a warp turn to the rows it owns: it waits for the row's other segments, adds all of them in segment
+    // order and finishes the row.  Nothing is waited for before everything a warp owes others is published, and the
+    // cooperative launch keeps every block resident, so the waits cannot deadlock.
     const uint32_t t0 = P.warp_seg_ptr[gwarp], t1 = P.warp_seg_ptr[gwarp + 1];
-    double my0 = 0.0, my1 = 0.0, my2 = 0.0;
-    uint32_t my_t = 0, nbatch = 0;
-    auto flush = [&]() {
-      if ((uint32_t)lane < nbatch) {
-        const uint32_t row = P.seg_row[my_t] & ~kSideBit;
-        const uint32_t s0 = P.node_seg_ptr[row], s1 = P.node_seg_ptr[row + 1];
-        if (s1 - s0 > 1) {
-          volatile unsigned* cnt = P.row_cnt + row;
-          while (*cnt != s1 - s0 - 1) { }
+    const uint32_t ncb = P.cbk.ncb ? P.cbk.ncb : 1u;
+    spmv_stream<kBlk>(wp, P.val, lo, hi, t0, t1, P.seg_begin, P.seg_len, P.z, zs, zbase, false, P.keep8, [&](uint32_t t, double ysum) {
+      if ((lane & 7) == 0 && lane < 24) __stcg(P.ypart + 3 * (size_t)t + multi_index4(lane), ysum);
+      if (ncb == 1u) {
+        // one column block: the only segment of a range that is not its row's first is the range's FIRST segment (the row began
+        // in an earlier range) -- publish it at once, its owner is about to need it
+        const uint32_t rowf = P.seg_row[t];
+        if (rowf & kSideBit) {
           __threadfence();
-          *cnt = 0u;
-          for (uint32_t k = s0 + 1; k < s1; ++k) {
-            my0 += __ldcg(P.ypart + 3 * (size_t)k); my1 += __ldcg(P.ypart + 3 * (size_t)k + 1); my2 += __ldcg(P.ypart + 3 * (size_t)k + 2);
-          }
-        }
-        if (push) {
-          for (int r = 0; r < P.world; ++r) {
-            LLCell* dst = P.peer[r] + ll_cg_offset(P.N, P.world, xseq, P.rank) + 3 * (size_t)row;
-            ll_store(dst, my0, xseq); ll_store(dst + 1, my1, xseq); ll_store(dst + 2, my2, xseq);
-          }
-        } else {
-          finish_row(P, row, my0, my1, my2, gamma, delta);
+          __syncwarp();
+          if (lane == 0) { __threadfence(); atomicAdd(P.row_cnt + (rowf & ~kSideBit), 1u); }
         }
       }
-      nbatch = 0;
-      __syncwarp();
-    };
-    spmv_stream<kBlk>(wp, P.val, lo, hi, t0, t1, P.seg_begin, P.seg_len, P.z, zs, false, P.keep8, [&](uint32_t t, double y0, double y1, double y2) {
-      const uint32_t rowf = P.seg_row[t];
-      if (rowf & kSideBit) {  // continuation of a row owned by an earlier warp
-        if (lane == 0) {
-          __stcg(P.ypart + 3 * (size_t)t, y0); __stcg(P.ypart + 3 * (size_t)t + 1, y1); __stcg(P.ypart + 3 * (size_t)t + 2, y2);
-          __threadfence();
-          atomicAdd(P.row_cnt + (rowf & ~kSideBit), 1u);
-        }
-        return;
-      }
-      if ((uint32_t)lane == nbatch) { my0 = y0; my1 = y1; my2 = y2; my_t = t; }
-      if (++nbatch == 32) flush();
     });
-    if (nbatch) flush();
+    if (ncb > 1u) {
+      // several column blocks: a range holds many such segments; ONE fence for the whole range, then every one of them counts
+      // itself in on its row's counter (lanes in parallel) -- a fence per segment would stall the stream every ~50 half-edges
+      __threadfence();
+      __syncwarp();
+      __threadfence();
+      for (uint32_t t = t0 + (uint32_t)lane; t < t1; t += 32u) {
+        const uint32_t rowf = P.seg_row[t];
+        if (rowf & kSideBit) atomicAdd(P.row_cnt + (rowf & ~kSideBit), 1u);
+      }
+    }
+    __syncwarp();
+    for (uint32_t t = t0 + (uint32_t)lane; t < t1; t += 32u) {
+      const uint32_t rowf = P.seg_row[t];
+      if (rowf & kSideBit) continue;
+      const uint32_t row = rowf;
+      uint32_t nseg = 0;
+      for (uint32_t cb = 0; cb < ncb; ++cb) nseg += P.node_seg_ptr[cb * P.N + row + 1] - P.node_seg_ptr[cb * P.N + row];
+      if (nseg > 1) {
+        volatile unsigned* cnt = P.row_cnt + row;
+        while (*cnt != nseg - 1) { }
+        __threadfence();
+        *cnt = 0u;
+      }
+      double my0 = 0.0, my1 = 0.0, my2 = 0.0;
+      for (uint32_t cb = 0; cb < ncb; ++cb)
+        for (uint32_t k = P.node_seg_ptr[cb * P.N + row]; k < P.node_seg_ptr[cb * P.N + row + 1]; ++k) {
+          my0 += __ldcg(P.ypart + 3 * (size_t)k); my1 += __ldcg(P.ypart + 3 * (size_t)k + 1); my2 += __ldcg(P.ypart + 3 * (size_t)k + 2);
+        }
+      if (push) {
+        for (int r = 0; r < P.world; ++r) {
+          LLCell* dst = P.peer[r] + ll_cg_offset(P.N, P.world, xseq, P.rank) + 3 * (size_t)row;
+          ll_store(dst, my0, xseq); ll_store(dst + 1, my1, xseq); ll_store(dst + 2, my2, xseq);
+        }
+      } else {
+        finish_row(P, row, my0, my1, my2, gamma, delta);
+      }
+    }
   }
   // views without any half-edge (in this shard): s_i = D_i z_i; multi-GPU: a tagged zero contribution
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n_iso; k += gridDim.x * blockDim.x) {
@@ -627,20 +657,33 @@ __global__ void __launch_bounds__(kPcgBlock, kPcgBlocksPerSM) k_pcg_persistent(P
     if (prof) tA = gtimer();
     double g_part = 0.0, d_part = 0.0;
     const double* zs = nullptr;
-    if (P.slice_views) {  // stage z (final since the barrier that closed the previous phase) for the gather
-      constexpr int kSliceOffset = kPcgWarps * kStages2 * Chunk<kBlk>::kBytes + kPcgWarps * kStages2 * 8;  // == spmv_smem_bytes(kBlk)
-      double* sl = reinterpret_cast<double*>(smem_raw + kSliceOffset);
-      for (uint32_t i = threadIdx.x; i < P.slice_views; i += blockDim.x) {
-        const double4 zv = reinterpret_cast<const double4*>(P.z)[i];
-        sl[3 * i] = zv.x; sl[3 * i + 1] = zv.y; sl[3 * i + 2] = zv.z;
+    uint32_t zbase = 0;
+    if (P.cbk.ncb) {
+      // stage the slice of z this CTA's half-edges gather from (z is final since the barrier that closed the previous
+      // phase): possible when the CTA's whole range lies inside ONE column block -- all but at most ncb - 1 CTAs
+      const uint64_t wpb = blockDim.x >> 5;
+      const uint64_t lo_cta = (uint64_t)blockIdx.x * wpb * P.warp_span, hi_cta = min(P.H, lo_cta + wpb * P.warp_span);
+      int cb = -1;
+      if (lo_cta < P.H)
+        for (uint32_t c = 0; c < P.cbk.ncb; ++c)
+          if ((uint64_t)P.cbk.begin[c] <= lo_cta && hi_cta <= (uint64_t)P.cbk.begin[c + 1]) cb = (int)c;
+      if (cb >= 0) {
+        constexpr int kSliceOffset = kPcgWarps * kStages2 * Chunk<kBlk>::kBytes + kPcgWarps * kStages2 * 8;  // == spmv_smem_bytes(kBlk)
+        double* sl = reinterpret_cast<double*>(smem_raw + kSliceOffset);
+        zbase = (uint32_t)cb * P.cbk.cbsize;
+        const uint32_t nv = min(P.cbk.cbsize, P.N - zbase);
+        for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) {
+          const double4 zv = reinterpret_cast<const double4*>(P.z)[zbase + i];
+          sl[3 * i] = zv.x; sl[3 * i + 1] = zv.y; sl[3 * i + 2] = zv.z;
+        }
+        __syncthreads();
+        zs = sl;
       }
-      __syncthreads();
-      zs = sl;
     }
-    if (!multi) spmv_pass<kBlk>(P, wp, g_part, d_part, zs);
+    if (!multi) spmv_pass<kBlk>(P, wp, g_part, d_part, zs, zbase);
     else {
       if (++seq == 0u) ++seq;  // 0 means "no exchange" in spmv_pass
-      spmv_pass<kBlk>(P, wp, g_part, d_part, zs, seq);
+      spmv_pass<kBlk>(P, wp, g_part, d_part, zs, zbase, seq);
       exchange_finish(P, seq, g_part, d_part);
     }
     if (prof) tB = gtimer();

@@ -35,17 +35,32 @@ __global__ void k_setup_halfedges(uint64_t H, int ku, const uint32_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------
-// Structure build on the device (one-time per problem): half-edge keys -> radix sort -> rows,
-// row pointers, duplicate / range checks, balanced warp partitions and their segments.
+// Structure build on the device (one-time per problem): half-edge keys -> radix sort -> pieces,
+// piece pointers, duplicate / range checks, balanced warp partitions and their segments.
+//
+// COLUMN BLOCKS.  The views are cut into ncb blocks of cbsize consecutive views and the half-edges are sorted by
+// (column block of col, row, col).  A PIECE is the run of half-edges of one row inside one column block; piece id
+// p = cb * N + row, so everything that used to be "per row" in the partition machinery is "per piece" and a row's pieces are
+// p = row, N + row, 2N + row, ...  Why: the per-half-edge gather x[col] of the SpMV moves 32 B per half-edge through the L2,
+// as much as the matrix stream itself; with the columns of a CTA's range confined to one block, that block's slice of x
+// (<= kSliceMaxViews * 24 B) is staged in shared memory once per pass and the gather never leaves the SM.  ncb = 1 (graphs of
+// more than kMaxColBlocks * kSliceMaxViews views, where the matrix stream is HBM-bound anyway) is the plain (row, col) order.
 // ------------------------------------------------------------------------------------------
-__global__ void k_build_keys(uint64_t E, uint32_t N, const uint32_t* __restrict__ ei, const uint32_t* __restrict__ ej, uint64_t* __restrict__ keys,
-                             uint32_t* __restrict__ vals, int* err) {
+constexpr int kMaxColBlocks = 8;
+struct ColBlocks {
+  uint32_t ncb, cbsize;                     // column block of view v: v / cbsize
+  uint32_t begin[kMaxColBlocks + 1];        // first half-edge of every block (begin[ncb] = H)
+};
+__device__ __host__ __forceinline__ uint32_t piece_of(uint32_t row, uint32_t col, uint32_t N, uint32_t cbsize) { return (col / cbsize) * N + row; }
+
+__global__ void k_build_keys(uint64_t E, uint32_t N, uint32_t cbsize, const uint32_t* __restrict__ ei, const uint32_t* __restrict__ ej,
+                             uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int* err) {
   const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= E) return;
   uint32_t i = ei[k], j = ej[k];
   if (i >= N || j >= N || i == j) { atomicMax(err, 1); i = 0; j = (N > 1) ? 1 : 0; }
-  keys[2 * k] = (uint64_t)i * N + j;     vals[2 * k] = (uint32_t)k;
-  keys[2 * k + 1] = (uint64_t)j * N + i; vals[2 * k + 1] = (uint32_t)k | kSideBit;
+  keys[2 * k] = (uint64_t)piece_of(i, j, N, cbsize) * N + j;     vals[2 * k] = (uint32_t)k;
+  keys[2 * k + 1] = (uint64_t)piece_of(j, i, N, cbsize) * N + i; vals[2 * k + 1] = (uint32_t)k | kSideBit;
 }
 __global__ void k_unpack_keys(uint64_t H, uint32_t N, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t* __restrict__ he_row,
                               uint32_t* __restrict__ he_col, uint32_t* __restrict__ he_edge, int* err) {
@@ -53,63 +68,78 @@ __global__ void k_unpack_keys(uint64_t H, uint32_t N, const uint64_t* __restrict
   if (h >= H) return;
   const uint64_t key = keys[h];
   const uint32_t v = vals[h];
-  he_row[h] = (uint32_t)(key / N);
+  he_row[h] = (uint32_t)((key / N) % N);
   he_col[h] = (uint32_t)(key % N) | (v & kSideBit);
   he_edge[h] = v & ~kSideBit;
   if (h > 0 && keys[h - 1] == key) atomicMax(err, 2);  // the same view pair twice
 }
-__global__ void k_rowptr(uint32_t N, uint64_t H, const uint64_t* __restrict__ keys, uint32_t* __restrict__ rowptr) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r > N) return;
-  const uint64_t target = (uint64_t)r * N;
+// pieceptr[p] = first half-edge of piece p, p = 0 .. NP (NP = ncb * N pieces)
+__global__ void k_pieceptr(uint32_t NP, uint32_t N, uint64_t H, const uint64_t* __restrict__ keys, uint32_t* __restrict__ pieceptr) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > NP) return;
+  const uint64_t target = (uint64_t)p * N;
   uint64_t lo = 0, hi = H;
   while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (keys[mid] < target) lo = mid + 1; else hi = mid; }
-  rowptr[r] = (uint32_t)lo;
+  pieceptr[p] = (uint32_t)lo;
 }
-__global__ void k_row_flags(uint32_t N, const uint32_t* __restrict__ rowptr, uint32_t* __restrict__ nonempty, uint32_t* __restrict__ isoflag) {
+__global__ void k_piece_flags(uint32_t NP, const uint32_t* __restrict__ pieceptr, uint32_t* __restrict__ nonempty) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > NP) return;
+  nonempty[p] = (p < NP && pieceptr[p + 1] > pieceptr[p]) ? 1u : 0u;
+}
+// views without any half-edge (in this shard): every piece of the row is empty
+__global__ void k_iso_flags(uint32_t N, uint32_t ncb, const uint32_t* __restrict__ pieceptr, uint32_t* __restrict__ isoflag) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r > N) return;
-  const uint32_t ne = (r < N && rowptr[r + 1] > rowptr[r]) ? 1u : 0u;
-  nonempty[r] = ne;
-  isoflag[r] = (r < N) ? 1u - ne : 0u;
+  uint32_t any = 0;
+  if (r < N)
+    for (uint32_t cb = 0; cb < ncb; ++cb) any |= (pieceptr[cb * N + r + 1] > pieceptr[cb * N + r]) ? 1u : 0u;
+  isoflag[r] = (r < N) ? 1u - any : 0u;
 }
 __global__ void k_iso_fill(uint32_t N, const uint32_t* __restrict__ isoflag, const uint32_t* __restrict__ iso_rank, uint32_t* __restrict__ iso) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < N && isoflag[r]) iso[iso_rank[r]] = r;
 }
-__global__ void k_part_count(uint32_t nw, uint32_t per, uint64_t H, const uint32_t* __restrict__ he_row, const uint32_t* __restrict__ nz_rank,
-                             uint32_t* __restrict__ nseg) {
+__global__ void k_part_count(uint32_t nw, uint32_t per, uint64_t H, uint32_t N, uint32_t cbsize, const uint32_t* __restrict__ he_row,
+                             const uint32_t* __restrict__ he_col, const uint32_t* __restrict__ nz_rank, uint32_t* __restrict__ nseg) {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w > nw) return;
   if (w == nw) { nseg[w] = 0; return; }
   const uint64_t lo = (uint64_t)w * per, hi = min(H, lo + per);
-  nseg[w] = nz_rank[he_row[hi - 1]] - nz_rank[he_row[lo]] + 1;
+  const uint32_t p0 = piece_of(he_row[lo], he_col[lo] & ~kSideBit, N, cbsize), p1 = piece_of(he_row[hi - 1], he_col[hi - 1] & ~kSideBit, N, cbsize);
+  nseg[w] = nz_rank[p1] - nz_rank[p0] + 1;  // non-empty pieces met by the range = its segments
 }
-__global__ void k_part_fill(uint32_t nw, uint32_t per, uint64_t H, const uint32_t* __restrict__ he_row, const uint32_t* __restrict__ rowptr,
-                            const uint32_t* __restrict__ warp_seg_ptr, uint32_t* __restrict__ seg_row, uint32_t* __restrict__ seg_begin,
-                            uint32_t* __restrict__ seg_len) {
+__global__ void k_part_fill(uint32_t nw, uint32_t per, uint64_t H, uint32_t N, uint32_t cbsize, const uint32_t* __restrict__ he_row,
+                            const uint32_t* __restrict__ he_col, const uint32_t* __restrict__ pieceptr, const uint32_t* __restrict__ warp_seg_ptr,
+                            uint32_t* __restrict__ seg_row, uint32_t* __restrict__ seg_begin, uint32_t* __restrict__ seg_len) {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= nw) return;
   const uint64_t lo = (uint64_t)w * per, hi = min(H, lo + per);
   uint32_t t = warp_seg_ptr[w];
   uint64_t h = lo;
-  uint32_t r = he_row[lo];
+  uint32_t p = piece_of(he_row[lo], he_col[lo] & ~kSideBit, N, cbsize);
   while (h < hi) {
-    while (rowptr[r + 1] <= h) ++r;
-    const uint64_t end = min(hi, (uint64_t)rowptr[r + 1]);
-    seg_row[t] = r | ((h > rowptr[r]) ? kSideBit : 0u);  // bit 31: continuation of a row begun in an earlier range
+    while (pieceptr[p + 1] <= h) ++p;
+    const uint64_t end = min(hi, (uint64_t)pieceptr[p + 1]);
+    const uint32_t row = p % N, cb = p / N;
+    // bit 31: NOT the first segment of its row -- the piece began in an earlier range, or the row has half-edges in an
+    // earlier column block.  The warp that holds a row's first segment owns the row (it adds the pieces and finishes it).
+    bool later = h > pieceptr[p];
+    for (uint32_t c = 0; c < cb && !later; ++c) later = pieceptr[c * N + row + 1] > pieceptr[c * N + row];
+    seg_row[t] = row | (later ? kSideBit : 0u);
     seg_begin[t] = (uint32_t)h;
     seg_len[t] = (uint32_t)(end - h);
     ++t;
     h = end;
   }
 }
-__global__ void k_node_seg_count(uint32_t N, uint32_t per, const uint32_t* __restrict__ rowptr, uint32_t* __restrict__ cnt) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r > N) return;
+// segments per piece (the ranges it spans); their exclusive scan, node_seg_ptr[p], is the id of the piece's first segment
+__global__ void k_node_seg_count(uint32_t NP, uint32_t per, const uint32_t* __restrict__ pieceptr, uint32_t* __restrict__ cnt) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > NP) return;
   uint32_t c = 0;
-  if (r < N && rowptr[r + 1] > rowptr[r]) c = (rowptr[r + 1] - 1) / per - rowptr[r] / per + 1;
-  cnt[r] = c;
+  if (p < NP && pieceptr[p + 1] > pieceptr[p]) c = (pieceptr[p + 1] - 1) / per - pieceptr[p] / per + 1;
+  cnt[p] = c;
 }
 
 // Column indices live inside the chunk records of both block buffers (written once).

@@ -22,6 +22,36 @@ namespace gsfm {
 
 struct Q4 { double w, x, y, z; };
 
+// Reciprocal / reciprocal square root for NORMAL, finite, non-zero arguments (every call site guarantees it): the hardware
+// seed (MUFU.RCP64H / RSQ64H, ~20 bits) and two Newton steps -- 5 / 7 straight-line instructions with a result within one ulp,
+// instead of the IEEE division / square root sequences with their special-case branches (~25 instructions and a slow-path
+// call each; K1 is bound by instruction issue, profiles/r02a_k_edges_20M_dynamic_mix.txt).  Host builds use the exact operations.
+__host__ __device__ __forceinline__ double fast_rcp(double x) {
+#ifdef __CUDA_ARCH__
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+#else
+  return 1.0 / x;
+#endif
+}
+__host__ __device__ __forceinline__ double fast_rsqrt(double x) {
+#ifdef __CUDA_ARCH__
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  return fma(y, e, y);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
 __host__ __device__ inline Q4 qmul(const Q4& a, const Q4& b) {
   Q4 r;
   r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
@@ -63,10 +93,10 @@ __host__ __device__ inline void quat_log(Q4 q, double* e, double* theta2_out, do
   const double s2 = q.x * q.x + q.y * q.y + q.z * q.z;
   double k = 2.0, theta2 = 0.0, c = 1.0 / 12.0;
   if (s2 > 1e-280) {
-    const double s = sqrt(s2);
+    const double s = s2 * fast_rsqrt(s2);
     const double theta = 2.0 * atan2(s, q.w);
     // one reciprocal serves theta/s, 1/theta^2 and w/(2 theta s): 1/theta = s inv, 1/s = theta inv
-    const double inv = 1.0 / (theta * s);
+    const double inv = fast_rcp(theta * s);
     const double it = s * inv, is = theta * inv;
     k = theta * is;
     theta2 = theta * theta;
@@ -189,19 +219,25 @@ __host__ __device__ inline double pow_expo(double b, int nu) {
   return b * b * b;
 }
 
+// kNu = 3 / 4 / 9 fixes the degrees of freedom at compile time (the table and the power fold away); 0 reads L.nu
+template <int kNu = 0>
 __host__ __device__ inline void magsac_loss(const DevLoss& L, double s_in, double* rho) {
+  const int nu = kNu ? kNu : L.nu;
   double sr = s_in;
   bool zero_derivative = false;
   if (sr > L.clamp_s) { sr = L.clamp_s; zero_derivative = true; }
   double xr = rint(1000.0 * sr / L.sq_sigma_max_2);  // Python round(): half to even
   if ((double)L.table_size < xr) xr = (double)L.table_size;
   double s = xr * L.sq_sigma_max_2 / 1000.0;
-  const double weight = L.one_over_sigma * (gamma_table(L.nu, xr / 1000.0) - L.gamma_k);
+  // s / (2 sigma^2) == xr / 1000 up to one rounding: ONE exponential serves the table value (nu = 3: exp(-x)), rho' and rho''
+  // (the reference evaluates three; the arguments differ by an ulp, the values by 1e-16 relative); only when s is floored at
+  // 1e-7 for rho'' does that term need its own
   const double ex = exp(-s / L.sq_sigma_max_2);
-  const double wd = -L.Ctd * pow_expo(s / L.sq_sigma_max_2, L.nu) * ex / (2.0 * L.cubed_sigma);
-  if (s < 1e-7) s = 1e-7;
-  const double wdd = 2.0 * L.Ctd * pow_expo(s / L.sq_sigma_max_2, L.nu) * (1.0 / L.sq_sigma - ((double)L.nu - 3.0) / s) *
-                     exp(-s / L.sq_sigma_max_2) / (8.0 * L.cubed_sigma);
+  const double weight = L.one_over_sigma * ((nu == 3 ? ex : gamma_table(nu, xr / 1000.0)) - L.gamma_k);
+  const double wd = -L.Ctd * pow_expo(s / L.sq_sigma_max_2, nu) * ex / (2.0 * L.cubed_sigma);
+  double ex2 = ex;
+  if (s < 1e-7) { s = 1e-7; ex2 = exp(-s / L.sq_sigma_max_2); }
+  const double wdd = 2.0 * L.Ctd * pow_expo(s / L.sq_sigma_max_2, nu) * (1.0 / L.sq_sigma - ((double)nu - 3.0) / s) * ex2 / (8.0 * L.cubed_sigma);
   if (L.flags & 1u) {
     rho[0] = 1.0 / weight;
     rho[1] = -1.0 / (weight * weight) * wd;
@@ -269,13 +305,13 @@ __host__ __device__ inline void eval_simple_loss(int kind, double p0, double p1,
     }
     case kLossSoftLOne: {
       const double b = sq0, c = inv_sq0;
-      const double sum = 1.0 + s * c, tmp = sqrt(sum);
-      out[0] = 2.0 * b * (tmp - 1.0); out[1] = fmax(1.0 / tmp, DBL_MIN); out[2] = -(c * out[1]) / (2.0 * sum);
+      const double sum = 1.0 + s * c, rt = fast_rsqrt(sum), tmp = sum * rt;   // sum >= 1
+      out[0] = 2.0 * b * (tmp - 1.0); out[1] = fmax(rt, DBL_MIN); out[2] = -(c * out[1]) * (0.5 * rt * rt);
       break;
     }
     case kLossCauchy: {
       const double b = sq0, c = inv_sq0;
-      const double sum = 1.0 + s * c, inv = 1.0 / sum;
+      const double sum = 1.0 + s * c, inv = fast_rcp(sum);   // sum >= 1
       out[0] = b * log(sum); out[1] = fmax(inv, DBL_MIN); out[2] = -c * (inv * inv);
       break;
     }
@@ -335,7 +371,8 @@ __host__ __device__ inline void eval_loss(const DevLoss& L, double s, double* ou
     s = og[0];
   }
   const int kind = kKind < 0 ? L.kind : kKind;
-  if (kind >= kLossMagsac3 && kind <= kLossMagsac9) magsac_loss(L, s, out);
+  if (kKind == kLossMagsac3) magsac_loss<3>(L, s, out);
+  else if (kind >= kLossMagsac3 && kind <= kLossMagsac9) magsac_loss<0>(L, s, out);
   else if (kind == kLossTabulated) tabulated_loss(L, s, out);
   else eval_simple_loss(kind, L.p0, L.p1, L.sq0, L.inv_sq0, s, out);
   if (comp) {  // f(g(s)): f' g',  f'' g'^2 + f' g''
@@ -414,7 +451,8 @@ __host__ __device__ inline void edge_terms(const Q4& qi, const Q4& qj, const Q4&
     o.S[0] = a + bf0 * f0; o.S[1] = bf0 * f1; o.S[2] = bf0 * f2;
     o.S[3] = a + bf1 * f1; o.S[4] = bf1 * f2; o.S[5] = a + bf2 * f2;
     o.v[0] = rw * f0; o.v[1] = rw * f1; o.v[2] = rw * f2;
-    const double hs = sqrt(fabs(b));
+    const double ab = fabs(b);
+    const double hs = ab > 1e-290 ? ab * fast_rsqrt(ab) : 0.0;
     o.ca = copysign(a, b);
     o.h[0] = hs * f0; o.h[1] = hs * f1; o.h[2] = hs * f2;
     return;

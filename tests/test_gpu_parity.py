@@ -529,7 +529,7 @@ def test_composed_and_tabulated_losses():
     for k, v in enumerate(sq):
         obj.Evaluate(float(v), ref[k])
     dev = solver.eval_loss(T, sq)
-    assert_close(dev[:, :2], ref[:, :2], 1e-9, "tabulated loss: rho, rho'")
+    assert_close(dev[:, :2], ref[:, :2], 1e-8, "tabulated loss: rho, rho'")
     assert_close(dev[:, 2], ref[:, 2], 1e-5, "tabulated loss: rho''")
     og, sg, _ = solver.solve(prob, _tight(T), g.omega_init)
 
