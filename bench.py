@@ -48,7 +48,7 @@ WORKLOADS = {
     "syn_100k_20M_cov": dict(views=100000, edges=20000000, covariance=True, loss=("magsac3", 1.0), etype="ANGLE_AXIS_COVARIANCE"),
     "piccadilly_like": dict(views=2300, edges=300000, covariance=False, loss=("cauchy", 0.05), etype="ANGLE_AXIS"),
     # BASELINE configs[1] stand-in (ETH3D terrace needs images + COLMAP): 23 views, near-complete graph
-    "terrace_like": dict(views=23, edges=200, covariance=True, loss=("magsac3", 0.02), etype="ANGLE_AXIS_COVARIANCE"),
+    "terrace_like": dict(views=23, edges=200, covariance=True, loss=("magsac3", 1.0), etype="ANGLE_AXIS_COVARIANCE"),
     # experiment only (profiles/kernel_times.py): 1M edges on few enough views for the shared-memory gather
     "syn_2500_1M": dict(views=2500, edges=1000000, covariance=False, loss=("cauchy", 0.05), etype="ANGLE_AXIS"),
     "small": dict(views=500, edges=20000, covariance=False, loss=("cauchy", 0.05), etype="ANGLE_AXIS"),
@@ -331,6 +331,9 @@ def accuracy_report(S, vg, capi, prob, g, opt, oracle_budget_edges=2500000):
     c_o = orc.cost(prob, opt.loss, om_b, num_threads=cores)
     rep["oracle_cost_at_gpu_solution"] = c_o
     rep["cost_rel_diff_gpu_vs_oracle_at_same_point"] = abs(c_o - s_b.final_cost) / abs(c_o)
+    if g.num_edges > oracle_budget_edges:
+        rep["oracle_solve"] = f"skipped: {g.num_edges} edges cost the CPU oracle ~{g.num_edges / 1.8e6:.0f} s per LM iteration"
+        return rep
     _, grad_o, _, _, _, _ = orc.assemble(prob, opt.loss, om_t, num_threads=cores)
     rep["oracle_gradient_max_norm_at_gpu_tight_solution"] = float(np.abs(grad_o).max())
     # converged vs converged (the north_star bar, <= 1e-4 rad): the oracle, started AT the GPU's tight solution with the same
@@ -344,7 +347,7 @@ def accuracy_report(S, vg, capi, prob, g, opt, oracle_budget_edges=2500000):
                 "oracle_polish": {"start": "the GPU's tight solution", "lm_iterations": s_op.num_iterations, "initial_cost": s_op.initial_cost,
                                   "final_cost": s_op.final_cost, "termination": capi.TERMINATION[s_op.termination],
                                   "seconds": time.perf_counter() - t0}})
-    if g.num_edges <= oracle_budget_edges:
+    if True:
         oo = capi.clone(p)
         oo.num_threads = cores
         t0 = time.perf_counter()
@@ -361,8 +364,6 @@ def accuracy_report(S, vg, capi, prob, g, opt, oracle_budget_edges=2500000):
                             "outlier-rich graph: the oracle's own default-tolerance answer sits `..._oracle_default_vs_oracle_converged_rad` "
                             "from its converged one, so distances to it measure where each run happened to stop, not solver error; "
                             "`mean_angular_error_converged_vs_oracle_rad` compares minimisers"})
-    else:
-        rep["oracle_solve"] = f"skipped: {g.num_edges} edges cost the CPU oracle ~{g.num_edges / 1.8e6:.0f} s per LM iteration"
     return rep
 
 

@@ -155,6 +155,8 @@ __device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restri
   double g[kCR][3];
   gather_chunk(ch, 0, g);
   for (uint32_t k = 0; k < nchunk; ++k) {
+    // the next chunk's gather goes out first and completes under this chunk's products and bookkeeping (measured, r02j: issuing
+    // it after the products is neutral at 1M edges / L2 resident and 6 % slower at 20M edges / HBM resident)
     const double* ch_n = ch;
     double gn[kCR][3];
     if (k + 1 < nchunk) { ch_n = wait_chunk(k + 1); gather_chunk(ch_n, k + 1, gn); }
