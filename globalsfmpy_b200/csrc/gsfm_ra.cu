@@ -355,6 +355,13 @@ struct gsfm_ra_solver {
   }
 
   bool sharded() const { return world > 1; }
+  // exchange mode (ra_common.cuh): direct up to 2 ranks, owner-reduce above; GSFM_RA_EXCHANGE=owner / direct forces one (tests)
+  bool owner_mode() const {
+    const char* e = std::getenv("GSFM_RA_EXCHANGE");
+    if (e && std::strcmp(e, "owner") == 0) return world > 1;
+    if (e && std::strcmp(e, "direct") == 0) return false;
+    return world > 2;
+  }
   // QUATERNION_COSINE: parameters live on the manifold (left-multiplicative update, local coordinates delta = phi/2)
   bool manifold() const { return error_type <= GSFM_RA_QUATERNION_COSINE; }
   bool general() const { return error_type < GSFM_RA_QUATERNION_COSINE; }  // two-block residuals, 9-double records
@@ -463,7 +470,7 @@ struct gsfm_ra_solver {
       PeerPtrs pp;
       for (int r = 0; r < kMaxPeers; ++r) pp.p[r] = (LLCell*)peer_base[r];
       k_node_finalize_ll<<<grid_for(N), kBlock, 0, stream>>>(N, cbk.ncb, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd_p[b], gt_p[b], ediag[b].p, slots.p, counter.p,
-                                                              sc.p, mb, mseq, publish ? ip_dev : nullptr, pp, world, rank);
+                                                              sc.p, mb, mseq, publish ? ip_dev : nullptr, pp, world, rank, owner_mode() ? 1 : 0);
     } else {
       // edge-sharded, NCCL: local sums -> ONE all-reduce of [Hd | gt | cost, bad] -> per-view post-processing
       k_node_finalize<<<grid_for(N), kBlock, 0, stream>>>(N, cbk.ncb, pk1.node_seg_ptr.p, part.p, node_JL[b].p, Hd_p[b], gt_p[b], ediag[b].p, co, 1, tail,
@@ -522,6 +529,7 @@ struct gsfm_ra_solver {
     P.fused = 0; P.ip = nullptr; P.cand_q = nullptr; P.cand_JL = nullptr;
     std::memset(&P.prep, 0, sizeof(P.prep)); std::memset(&P.apply, 0, sizeof(P.apply));
     P.world = peers_connected ? world : 1; P.rank = rank;
+    P.owner_mode = owner_mode() ? 1 : 0;
     for (int r = 0; r < kMaxPeers; ++r) P.peer[r] = (LLCell*)peer_base[r];
     return P;
   }
@@ -1378,6 +1386,7 @@ static int resolve_world(const gsfm_ra_problem* problem, const gsfm_ra_options* 
 // trust-region loop on bit-identical replicated scalars, so they take the same decisions without talking to each other.
 static int solve_multi(const gsfm_ra_problem* problem, const gsfm_ra_options* options, int dev0, int W, double* omega_inout,
                        gsfm_ra_summary* summary) {
+  const double t_enter = now_ms();
   std::vector<gsfm_ra_solver*> sv(W, nullptr);
   std::vector<int> rc(W, 0);
   std::vector<std::string> err(W);
@@ -1415,6 +1424,7 @@ static int solve_multi(const gsfm_ra_problem* problem, const gsfm_ra_options* op
     for (int q = 0; q < W; ++q) sv[r]->peer_base[q] = sv[q]->xchg;
     sv[r]->peers_connected = true;
   }
+  const double t_built = now_ms();
   st = parallel([&](int r) -> int {
     RA_TRY(gsfm_ra_solver_set_rotations(sv[r], omega_inout));
     gsfm_ra_summary local;
@@ -1422,10 +1432,14 @@ static int solve_multi(const gsfm_ra_problem* problem, const gsfm_ra_options* op
     return gsfm_ra_solver_iterate(sv[r], options->max_num_iterations + 1, r == 0 ? summary : &local);
   });
   int out = st;
+  const double t_solved = now_ms();
   if (st == 0 || st == GSFM_RA_ERR_NUMERIC) {
     const int g = gsfm_ra_solver_get_rotations(sv[0], omega_inout);
     if (g != 0) out = g;
   }
+  if (options->verbose)
+    std::fprintf(stderr, "[gsfm_ra] %d devices: build + connect %.2f ms, solve %.2f ms (%d iterations)\n", W, t_built - t_enter, t_solved - t_built,
+                 summary ? summary->num_iterations : -1);
   cudaSetDevice(prev_dev);
   return out;
 }

@@ -228,12 +228,20 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 // reader that sees both tags equal to the sequence number it waits for has the value -- no fence, no separate flag, and the
 // producer can push cells into peer memory while it is still computing (the low-latency protocol of NCCL, applied per double).
 // The exchange block of a rank (cudaMalloc, zero-initialised, mapped by every peer over NVLink) holds, double buffered by
-// sequence parity and indexed by SOURCE rank:   cg [2][W][3N]   lin [2][W][9N]   tail [2][W][4]     (cells)
+// sequence parity and indexed by SOURCE rank:   cg [2][W][3N]   lin [2][W][9N]   tail [2][W][4]   and the REDUCED values of the
+// owner mode   cgred [2][3N]   linred [2][9N]     (cells).
+// Two exchange modes.  DIRECT (W <= 2): every rank pushes its contribution for every view to every rank, every rank adds the W
+// contributions itself -- one NVLink hop, W x the stores.  OWNER (W > 2): view i belongs to rank i % W; contributions go to the
+// owner only, the owner adds them in rank order and pushes the sum to every rank -- two hops, but 2N instead of W N cell groups
+// per rank, which is what counts once N W is large (100k views on 8 GPUs: 4x fewer NVLink writes).  Either way every rank ends
+// up with bitwise the same sums.
 // ------------------------------------------------------------------------------------------
 struct alignas(16) LLCell { uint32_t lo, t0, hi, t1; };
 constexpr int kMaxPeers = 16;
 struct PeerPtrs { LLCell* p[kMaxPeers]; };
-__host__ __device__ inline size_t ll_cells_total(uint32_t N, int world) { return 2ull * world * (12ull * N + 4); }
+__host__ __device__ inline size_t ll_cells_total(uint32_t N, int world) { return 2ull * world * (12ull * N + 4) + 2ull * 12ull * N; }
+__host__ __device__ inline size_t ll_cgred_offset(uint32_t N, int world, unsigned seq) { return 2ull * world * (12ull * N + 4) + (size_t)(seq & 1u) * 3ull * N; }
+__host__ __device__ inline size_t ll_linred_offset(uint32_t N, int world, unsigned seq) { return 2ull * world * (12ull * N + 4) + 2ull * 3ull * N + (size_t)(seq & 1u) * 9ull * N; }
 __host__ __device__ inline size_t ll_cg_offset(uint32_t N, int world, unsigned seq, int src) { return ((size_t)(seq & 1u) * world + src) * 3ull * N; }
 __host__ __device__ inline size_t ll_lin_offset(uint32_t N, int world, unsigned seq, int src) { return 2ull * world * 3ull * N + ((size_t)(seq & 1u) * world + src) * 9ull * N; }
 __host__ __device__ inline size_t ll_tail_offset(uint32_t N, int world, unsigned seq, int src) { return 2ull * world * 12ull * N + ((size_t)(seq & 1u) * world + src) * 4ull; }

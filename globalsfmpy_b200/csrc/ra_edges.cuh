@@ -318,7 +318,7 @@ __global__ void k_node_finalize(uint32_t N, uint32_t ncb, const uint32_t* __rest
 __global__ void k_node_finalize_ll(uint32_t N, uint32_t ncb, const uint32_t* __restrict__ node_task_ptr, const double* __restrict__ part,
                                    const double* __restrict__ node_JL, double* __restrict__ Hd, double* __restrict__ gt,
                                    double* __restrict__ ediag, double* slots, unsigned* counter, DevScalars* sc, HostMailbox* mailbox,
-                                   unsigned mailbox_seq, const IterParams* ip, PeerPtrs peers, int world, int rank) {
+                                   unsigned mailbox_seq, const IterParams* ip, PeerPtrs peers, int world, int rank, int owner_mode) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned eseq = (unsigned)sc->eseq + 1u;
   int bad = 0;
@@ -333,10 +333,27 @@ __global__ void k_node_finalize_ll(uint32_t N, uint32_t ncb, const uint32_t* __r
         for (int k = 0; k < kPartStride; ++k) a[k] += part[(size_t)t * kPartStride + k];
       }
     v[0] = a[9];
-    for (int r = 0; r < world; ++r) {
+    const int r0 = owner_mode ? (int)(i % (uint32_t)world) : 0, r1 = owner_mode ? r0 + 1 : world;
+    for (int r = r0; r < r1; ++r) {
       LLCell* dst = peers.p[r] + ll_lin_offset(N, world, eseq, rank) + 9 * (size_t)i;
 #pragma unroll
       for (int k = 0; k < 9; ++k) ll_store(dst + k, a[k], eseq);
+    }
+    if (owner_mode && r0 == rank) {  // this rank owns view i: add the W contributions in rank order, push the sums to everybody
+      double t[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) t[k] = 0.0;
+      for (int r = 0; r < world; ++r) {
+        double b9[9];
+        ll_wait_n<9>(peers.p[rank] + ll_lin_offset(N, world, eseq, r) + 9 * (size_t)i, eseq, b9, &bad);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) t[k] += b9[k];
+      }
+      for (int r = 0; r < world; ++r) {
+        LLCell* dst = peers.p[r] + ll_linred_offset(N, world, eseq) + 9 * (size_t)i;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) ll_store(dst + k, t[k], eseq);
+      }
     }
   }
   // this rank's cost: deterministic grid sum; its last block sends it to everybody
@@ -354,11 +371,15 @@ __global__ void k_node_finalize_ll(uint32_t N, uint32_t ncb, const uint32_t* __r
 #pragma unroll
     for (int k = 0; k < 9; ++k) a[k] = 0.0;
     const LLCell* mine = peers.p[rank];
-    for (int r = 0; r < world; ++r) {
-      double b9[9];
-      ll_wait_n<9>(mine + ll_lin_offset(N, world, eseq, r) + 9 * (size_t)i, eseq, b9, &bad);
+    if (owner_mode) {
+      ll_wait_n<9>(mine + ll_linred_offset(N, world, eseq) + 9 * (size_t)i, eseq, a, &bad);
+    } else {
+      for (int r = 0; r < world; ++r) {
+        double b9[9];
+        ll_wait_n<9>(mine + ll_lin_offset(N, world, eseq, r) + 9 * (size_t)i, eseq, b9, &bad);
 #pragma unroll
-      for (int k = 0; k < 9; ++k) a[k] += b9[k];
+        for (int k = 0; k < 9; ++k) a[k] += b9[k];
+      }
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) Hd[6 * (size_t)i + k] = a[k];

@@ -447,6 +447,7 @@ struct PcgParams {
   // edge-sharded multi-GPU (world > 1): every rank's exchange block (ra_common.cuh, LLCell), mapped into this process over
   // NVLink (CUDA IPC between processes, peer access inside one).  peer[rank] is this rank's own block.
   int world, rank;
+  int owner_mode;  // exchange mode (ra_common.cuh): 0 direct, 1 owner-reduce
   LLCell* peer[kMaxPeers];
 };
 
@@ -561,7 +562,8 @@ __device__ __forceinline__ void spmv_pass(const PcgParams& P, WarpPipe& wp, doub
           my0 += __ldcg(P.ypart + 3 * (size_t)k); my1 += __ldcg(P.ypart + 3 * (size_t)k + 1); my2 += __ldcg(P.ypart + 3 * (size_t)k + 2);
         }
       if (push) {
-        for (int r = 0; r < P.world; ++r) {
+        const int r0 = P.owner_mode ? (int)(row % (uint32_t)P.world) : 0, r1 = P.owner_mode ? r0 + 1 : P.world;
+        for (int r = r0; r < r1; ++r) {
           LLCell* dst = P.peer[r] + ll_cg_offset(P.N, P.world, xseq, P.rank) + 3 * (size_t)row;
           ll_store(dst, my0, xseq); ll_store(dst + 1, my1, xseq); ll_store(dst + 2, my2, xseq);
         }
@@ -573,8 +575,10 @@ __device__ __forceinline__ void spmv_pass(const PcgParams& P, WarpPipe& wp, doub
   // views without any half-edge (in this shard): s_i = D_i z_i; multi-GPU: a tagged zero contribution
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n_iso; k += gridDim.x * blockDim.x) {
     if (push) {
-      for (int r = 0; r < P.world; ++r) {
-        LLCell* dst = P.peer[r] + ll_cg_offset(P.N, P.world, xseq, P.rank) + 3 * (size_t)P.iso[k];
+      const uint32_t row = P.iso[k];
+      const int r0 = P.owner_mode ? (int)(row % (uint32_t)P.world) : 0, r1 = P.owner_mode ? r0 + 1 : P.world;
+      for (int r = r0; r < r1; ++r) {
+        LLCell* dst = P.peer[r] + ll_cg_offset(P.N, P.world, xseq, P.rank) + 3 * (size_t)row;
         ll_store(dst, 0.0, xseq); ll_store(dst + 1, 0.0, xseq); ll_store(dst + 2, 0.0, xseq);
       }
     } else {
@@ -596,8 +600,12 @@ __device__ __forceinline__ void exchange_finish(const PcgParams& P, unsigned seq
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const LLCell* mine = P.peer[P.rank];
   int bad = 0;
-  for (uint32_t vb = gw * (32 / G); vb < P.N; vb += nwarps * (32 / G)) {
-    const uint32_t i = vb + (uint32_t)(lane / G);
+  const uint32_t W = (uint32_t)P.world;
+  // owner mode: only the views of this rank (i % W == rank) are reduced here, then pushed to everybody; all views follow below
+  const uint32_t nloop = P.owner_mode ? (P.N + W - 1) / W : P.N;
+  for (uint32_t vb = gw * (32 / G); vb < nloop; vb += nwarps * (32 / G)) {
+    const uint32_t k = vb + (uint32_t)(lane / G);
+    const uint32_t i = P.owner_mode ? (uint32_t)P.rank + W * k : k;
     double y0 = 0.0, y1 = 0.0, y2 = 0.0;
     if (i < P.N) {
       for (int r = sub; r < P.world; r += G) {
@@ -617,7 +625,23 @@ __device__ __forceinline__ void exchange_finish(const PcgParams& P, unsigned seq
     for (int o = 1; o < G; o <<= 1) {
       y0 += __shfl_xor_sync(0xffffffffu, y0, o); y1 += __shfl_xor_sync(0xffffffffu, y1, o); y2 += __shfl_xor_sync(0xffffffffu, y2, o);
     }
-    if (i < P.N && sub == 0) finish_row(P, i, y0, y1, y2, gamma, delta);
+    if (P.owner_mode) {
+      if (i < P.N)
+        for (int r = sub; r < P.world; r += G) {  // the group's lanes share the W destinations
+          LLCell* dst = P.peer[r] + ll_cgred_offset(P.N, P.world, seq) + 3 * (size_t)i;
+          ll_store(dst, y0, seq); ll_store(dst + 1, y1, seq); ll_store(dst + 2, y2, seq);
+        }
+    } else if (i < P.N && sub == 0) {
+      finish_row(P, i, y0, y1, y2, gamma, delta);
+    }
+  }
+  if (P.owner_mode) {
+    // every view: its reduced sums arrive from its owner
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.N; i += gridDim.x * blockDim.x) {
+      double a[3];
+      ll_wait_n<3>(mine + ll_cgred_offset(P.N, P.world, seq) + 3 * (size_t)i, seq, a, &bad);
+      finish_row(P, i, a[0], a[1], a[2], gamma, delta);
+    }
   }
   if (bad) P.sc->bad = bad;
 }
