@@ -104,6 +104,7 @@ int attach_loss_table(const gsfm_ra_loss* in, DevLoss* L, Buf* buf, cudaStream_t
 }
 
 bool type_needs_cov(int t) { return t == 3 || t == 6 || t == 7 || t == 8; }
+bool type_is_position(int t) { return t == GSFM_RA_POSITION_BASELINE; }
 
 int check_problem(const gsfm_ra_problem* p) {
   if (!p) { set_error("problem is NULL"); return GSFM_RA_ERR_INVALID; }
@@ -111,6 +112,11 @@ int check_problem(const gsfm_ra_problem* p) {
   if (!p->edge_i || !p->edge_j || !p->omega_ij) { set_error("edge arrays are NULL"); return GSFM_RA_ERR_INVALID; }
   if (p->num_views >= kSideBit) { set_error("too many views"); return GSFM_RA_ERR_INVALID; }
   if (p->num_edges >= (1ull << 31)) { set_error("too many edges for 32-bit half-edge offsets"); return GSFM_RA_ERR_UNSUPPORTED; }
+  if (type_is_position(p->error_type)) {
+    if (!p->orientation) { set_error("GSFM_RA_POSITION_BASELINE needs the global orientations"); return GSFM_RA_ERR_INVALID; }
+    if (p->fixed_view >= (int64_t)p->num_views) { set_error("fixed_view %lld out of range", (long long)p->fixed_view); return GSFM_RA_ERR_INVALID; }
+    return 0;
+  }
   if (p->error_type < GSFM_RA_QUATERNION_NORM || p->error_type > GSFM_RA_ANGLE_AXIS_COVNORM) { set_error("unknown error_type %d", p->error_type); return GSFM_RA_ERR_INVALID; }
   if (type_needs_cov(p->error_type) && !p->cov6) { set_error("error_type %d needs cov6", p->error_type); return GSFM_RA_ERR_INVALID; }
   return 0;
@@ -298,7 +304,8 @@ struct gsfm_ra_solver {
   int ku = 1;            // whitening entries per half-edge in the input records: 1 (scalar) or 6 (upper triangle)
   // edge-order copies for the API kernels
   DevBuf<uint32_t> d_ei, d_ej;
-  DevBuf<double> d_omega_ij, d_cov6, d_weight;
+  DevBuf<double> d_omega_ij, d_cov6, d_weight, d_orient;  // d_orient: translation averaging, the global orientations [N][3]
+  uint32_t fixed_view = kNoFixedView;                     // translation averaging: the view held constant
   // linearisation, double buffered: [cur] is the accepted point, [cur^1] the candidate
   DevBuf<double> omega[2], node_q[2], node_JL[2], val[2], ediag[2];
   // lin[b] = [Hd 6N | gt 3N | cost, bad]: everything one evaluation sums over edges, contiguous so the
@@ -364,6 +371,8 @@ struct gsfm_ra_solver {
   }
   // QUATERNION_COSINE: parameters live on the manifold (left-multiplicative update, local coordinates delta = phi/2)
   bool manifold() const { return error_type <= GSFM_RA_QUATERNION_COSINE; }
+  bool position() const { return type_is_position(error_type); }   // translation averaging: Euclidean 3-vectors, D = I
+  int param_kind() const { return position() ? 2 : (manifold() ? 1 : 0); }  // node_prep_view / apply_view
   bool general() const { return error_type < GSFM_RA_QUATERNION_COSINE; }  // two-block residuals, 9-double records
   int allreduce(double* buf, size_t count) {
     if (!comm) { set_error("sharded solver used before gsfm_ra_solver_comm_init"); return GSFM_RA_ERR_INVALID; }
@@ -420,6 +429,7 @@ struct gsfm_ra_solver {
   }
   K1Fn pick_k1(bool jacobian) const {
     if (manifold()) return jacobian ? pick_k1_loss<true, 1, true>() : pick_k1_loss<false, 1, true>();
+    if (position()) return jacobian ? pick_k1_loss<true, 2, true>() : pick_k1_loss<false, 2, true>();
     if (scalar_u) return jacobian ? pick_k1_loss<true, 0, true>() : pick_k1_loss<false, 0, true>();
     return jacobian ? pick_k1_loss<true, 0, false>() : pick_k1_loss<false, 0, false>();
   }
@@ -435,7 +445,7 @@ struct gsfm_ra_solver {
     K1Args A;
     A.num_warps = pk1.num_warps; A.warp_span = pk1.span; A.H = H;
     A.warp_seg_ptr = pk1.warp_seg_ptr.p; A.seg_begin = pk1.seg_begin.p; A.seg_len = pk1.seg_len.p;
-    A.inrec = inrec.p; A.node_q = node_q[b].p; A.val = val_out; A.part = part.p; A.loss = loss;
+    A.inrec = inrec.p; A.node_q = node_q[b].p; A.val = val_out; A.part = part.p; A.loss = loss; A.fixed = fixed_view;
     pick_k1(jacobian)<<<pk1.grid, kBlock, k1_smem_bytes(), stream>>>(A);
   }
   void launch_spmv(int b, const double* x4, int check_done) {
@@ -456,7 +466,7 @@ struct gsfm_ra_solver {
     const IterParams* ip_dev = graph_params ? it_params.p : nullptr;  // graph replay: the sequence number comes from device memory
     const unsigned mseq = (publish && !graph_params) ? ++mailbox_seq : 0u;
     if (!prepped) {
-      k_node_prep<<<grid_for(N), kBlock, 0, stream>>>(N, omega[b].p, node_q[b].p, node_JL[b].p, slots.p, counter.p, sc.p, manifold() ? 1 : 0);
+      k_node_prep<<<grid_for(N), kBlock, 0, stream>>>(N, omega[b].p, node_q[b].p, node_JL[b].p, slots.p, counter.p, sc.p, param_kind());
       launches += 1;
     }
     launch_edges(b, jacobian, val[b].p);
@@ -512,7 +522,7 @@ struct gsfm_ra_solver {
   ApplyArgs apply_args(int b, int c) {
     ApplyArgs A;
     A.node_JL = node_JL[b].p; A.xt = x.p; A.bvec = bvec.p; A.res = r.p; A.Dblk = Dblk.p; A.Hd = Hd_p[b]; A.gt = gt_p[b]; A.omega = omega[b].p;
-    A.cand = omega[c].p; A.delta_out = delta.p; A.manifold = manifold() ? 1 : 0;
+    A.cand = omega[c].p; A.delta_out = delta.p; A.manifold = param_kind();
     return A;
   }
   PcgParams pcg_params(int b, double rtol, int max_iter) {
@@ -680,7 +690,8 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   s->scalar_u = !(prob->error_type == GSFM_RA_ANGLE_AXIS_COVARIANCE || prob->error_type == GSFM_RA_ANGLE_AXIS_COV_INLIERS);
   s->ku = s->scalar_u ? 1 : 6;
   // scalar-weight angle-axis stencils (types 4, 5, 7, 8) are stored in the compact 4-double form (-DGSFM_RA_NO_COMPACT: 6)
-  s->blk = s->general() ? 9 : (kCompactScalarStencil && s->scalar_u && !s->manifold()) ? 4 : 6;
+  s->blk = s->general() ? 9 : (kCompactScalarStencil && s->scalar_u && !s->manifold() && !s->position()) ? 4 : 6;
+  if (s->position() && prob->fixed_view >= 0) s->fixed_view = (uint32_t)prob->fixed_view;
   RA_TRY(make_dev_loss(&options->loss, &s->loss));
   s->sm_count = di->sm_count;
   CUDA_TRY(cudaStreamCreateWithFlags(&s->stream_holder.s, cudaStreamNonBlocking));
@@ -714,6 +725,7 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
   RA_TRY(up64(s->d_omega_ij, prob->omega_ij + 3 * e0, 3 * E));
   if (prob->cov6) RA_TRY(up64(s->d_cov6, prob->cov6 + 6 * e0, 6 * E));
   if (prob->edge_weight) RA_TRY(up64(s->d_weight, prob->edge_weight + e0, E));
+  if (s->position()) RA_TRY(up64(s->d_orient, prob->orientation, 3ull * N));
   lap("enqueue uploads");
 
   // ---- half-edges sorted by (column block, row, col): keys -> radix sort -> unpack (ra_structure.cuh) ---------------
@@ -824,7 +836,7 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
     CUDA_TRY(cudaMemsetAsync(s->inrec.p + (nrec_in - 1) * rd, 0, rd * 8, st));  // lanes past H in the last record
   }
   k_setup_halfedges<<<grid_for(H), kBlock, 0, st>>>(H, s->ku, s->he_edge.p, s->he_row.p, s->he_col.p, s->d_omega_ij.p, s->d_cov6.p, s->d_weight.p,
-                                                    prob->error_type, s->inrec.p);
+                                                    prob->error_type, s->inrec.p, s->d_ei.p, s->d_orient.p);
   s->launches += 1;
   const size_t nrec = (size_t)((H + 31) / 32);
   for (int b = 0; b < 2; ++b) {
@@ -1540,7 +1552,7 @@ int gsfm_ra_eval_edges(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss,
   if (jac_i) RA_TRY(dji.alloc(3 * d * E));
   if (jac_j) RA_TRY(djj.alloc(3 * d * E));
   if (rho) RA_TRY(drho.alloc(3 * E));
-  k_node_prep<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->omega[0].p, s->node_q[0].p, s->node_JL[0].p, s->slots.p, s->counter.p, s->sc.p, s->manifold() ? 1 : 0);
+  k_node_prep<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->omega[0].p, s->node_q[0].p, s->node_JL[0].p, s->slots.p, s->counter.p, s->sc.p, s->param_kind());
   if (s->error_type == GSFM_RA_QUATERNION_NORM)
     k_eval_edges_general<0><<<grid_for(E), kBlock, 0, s->stream>>>(E, s->d_ei.p, s->d_ej.p, s->d_omega_ij.p, s->d_weight.p, s->node_q[0].p, s->node_JL[0].p,
                                                                    s->loss, dr.p, dji.p, djj.p, drho.p);
@@ -1549,7 +1561,7 @@ int gsfm_ra_eval_edges(const gsfm_ra_problem* problem, const gsfm_ra_loss* loss,
                                                                    s->loss, dr.p, dji.p, djj.p, drho.p);
   else
     k_eval_edges<<<grid_for(E), kBlock, 0, s->stream>>>(E, s->d_ei.p, s->d_ej.p, s->d_omega_ij.p, s->d_cov6.p, s->d_weight.p, s->error_type,
-                                                        s->node_q[0].p, s->node_JL[0].p, s->loss, dr.p, dji.p, djj.p, drho.p);
+                                                        s->node_q[0].p, s->node_JL[0].p, s->loss, dr.p, dji.p, djj.p, drho.p, s->d_orient.p);
   CUDA_TRY(cudaGetLastError());
   if (r) CUDA_TRY(cudaMemcpyAsync(r, dr.p, d * E * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   if (jac_i) CUDA_TRY(cudaMemcpyAsync(jac_i, dji.p, 3 * d * E * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -1728,7 +1740,7 @@ int gsfm_ra_filter_view_pairs(const gsfm_ra_problem* problem, const double* omeg
   RA_TRY(dk.alloc(E));
   RA_TRY(da.alloc(E));
   const double thr = max_degrees * M_PI / 180.0;
-  k_node_prep<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->omega[0].p, s->node_q[0].p, s->node_JL[0].p, s->slots.p, s->counter.p, s->sc.p, s->manifold() ? 1 : 0);
+  k_node_prep<<<grid_for(s->N), kBlock, 0, s->stream>>>(s->N, s->omega[0].p, s->node_q[0].p, s->node_JL[0].p, s->slots.p, s->counter.p, s->sc.p, s->param_kind());
   k_filter_pairs<<<grid_for(E), kBlock, 0, s->stream>>>(E, s->d_ei.p, s->d_ej.p, s->d_omega_ij.p, s->node_q[0].p, thr * thr, dk.p, da.p);
   CUDA_TRY(cudaGetLastError());
   if (keep) CUDA_TRY(cudaMemcpyAsync(keep, dk.p, E, cudaMemcpyDeviceToHost, s->stream));

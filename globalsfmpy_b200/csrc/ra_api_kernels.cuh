@@ -10,18 +10,21 @@ namespace {
 // AutoDiffCostFunction::Evaluate + LossFunction::Evaluate return in the reference.
 __global__ void k_eval_edges(uint64_t E, const uint32_t* __restrict__ ei, const uint32_t* __restrict__ ej, const double* __restrict__ omega_ij,
                              const double* __restrict__ cov6, const double* __restrict__ weight, int error_type, const double* __restrict__ node_q,
-                             const double* __restrict__ node_JL, DevLoss loss, double* r, double* Ji, double* Jj, double* rho) {
+                             const double* __restrict__ node_JL, DevLoss loss, double* r, double* Ji, double* Jj, double* rho,
+                             const double* __restrict__ orientation = nullptr) {
   const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= E) return;
   const uint32_t i = ei[k], j = ej[k];
   const double4 a = reinterpret_cast<const double4*>(node_q)[i], b = reinterpret_cast<const double4*>(node_q)[j];
   const Q4 qi{a.x, a.y, a.z, a.w}, qj{b.x, b.y, b.z, b.w};
-  const Q4 qm = aa_to_quat(omega_ij[3 * k], omega_ij[3 * k + 1], omega_ij[3 * k + 2]);
+  const Q4 qm = orientation ? rotated_translation(orientation + 3 * (size_t)i, omega_ij + 3 * k)
+                            : aa_to_quat(omega_ij[3 * k], omega_ij[3 * k + 1], omega_ij[3 * k + 2]);
   double c6[6] = {0, 0, 0, 0, 0, 0}, u[6];
   if (cov6) for (int t = 0; t < 6; ++t) c6[t] = cov6[6 * k + t];
   whiten(error_type, c6, weight ? weight[k] : 1.0, u);
   EdgeTerms et;
   if (error_type == 2) edge_terms<true, 1>(qi, qj, qm, u, loss, et);
+  else if (orientation) edge_terms<true, 2>(qi, qj, qm, u, loss, et);
   else edge_terms<true, 0>(qi, qj, qm, u, loss, et);
   if (r) for (int t = 0; t < 3; ++t) r[3 * k + t] = et.r[t];
   if (rho) for (int t = 0; t < 3; ++t) rho[3 * k + t] = et.rho[t];

@@ -66,6 +66,18 @@ constexpr int kPcgBlock = kPcgWarps * 32;
 constexpr int kPcgBlocksPerSM = 16 / kPcgWarps;
 constexpr int kMaxWarpsPerBlock = 16;
 constexpr int kStages2 = 3;                      // K2: chunks in flight per warp
+// K2 loop form for the compact 4-double records: record-major (one record per iteration) or chunk-major (the records of a bulk
+// copy unrolled together); A/B builds with -DGSFM_RA_K2_CHUNK_MAJOR4.
+#ifdef GSFM_RA_K2_CHUNK_MAJOR4
+constexpr bool kRecordMajor4 = false;
+#else
+constexpr bool kRecordMajor4 = true;
+#endif
+#ifdef GSFM_RA_NO_WRAP_PREFETCH
+constexpr bool kWrapPrefetch = false;   // A/B builds: no wrap-around prefetch of the matrix stream across the CG step's barriers
+#else
+constexpr bool kWrapPrefetch = true;
+#endif
 constexpr int chunk_recs(int blk) { return blk == 4 ? 3 : (blk == 6 ? 2 : 1); }   // records per bulk copy
 template <int kBlk>
 struct Chunk {
@@ -386,6 +398,7 @@ struct WarpPipe {
   double* ring;    // this warp's ring of stages in shared memory
   uint64_t* bars;  // this warp's mbarriers, one per stage
   uint32_t pos;    // bulk copies consumed since init: ring slot = pos % stages, phase = (pos / stages) & 1
+  uint32_t primed; // bulk copies of the NEXT pass already in flight (wrap-around prefetch of the persistent PCG kernel)
 };
 
 // Shared memory of a block: [warps][kNumStages][kStageBytes] rings, then [warps][kNumStages] mbarriers.
@@ -395,6 +408,7 @@ __device__ __forceinline__ void pipe_init_bytes(WarpPipe& wp, unsigned char* sme
   wp.ring = reinterpret_cast<double*>(smem + (size_t)warp * kNumStages * kStageBytes);
   wp.bars = reinterpret_cast<uint64_t*>(smem + (size_t)nwarps * kNumStages * kStageBytes) + warp * kNumStages;
   wp.pos = 0;
+  wp.primed = 0;
   if (lane == 0) {
     for (int st = 0; st < kNumStages; ++st) mbar_init(&wp.bars[st], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

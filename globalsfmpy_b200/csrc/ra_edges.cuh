@@ -13,11 +13,19 @@ namespace {
 // per-view body of k_node_prep; returns the view's contribution to |x|^2
 __device__ __forceinline__ double node_prep_view(uint32_t i, const double* w3, double* __restrict__ node_q, double* __restrict__ node_JL, int manifold) {
   const double wx = w3[0], wy = w3[1], wz = w3[2];
+  if (manifold == 2) {
+    // translation averaging: the parameters are camera positions (Euclidean, D = I); the position rides in the x,y,z slots
+    // of the 32 B per-view sector the edge kernel gathers
+    reinterpret_cast<double4*>(node_q)[i] = make_double4(0.0, wx, wy, wz);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) node_JL[9 * (size_t)i + t] = (t == 0 || t == 4 || t == 8) ? 1.0 : 0.0;
+    return wx * wx + wy * wy + wz * wz;
+  }
   const Q4 q = aa_to_quat(wx, wy, wz);
   reinterpret_cast<double4*>(node_q)[i] = make_double4(q.w, q.x, q.y, q.z);
   double J[9];
   double xn;
-  if (manifold) {
+  if (manifold == 1) {
     double R[9];
     quat_to_mat(q, R);
 #pragma unroll
@@ -63,7 +71,9 @@ struct K1Args {
   const double *inrec, *node_q;
   double *val, *part;
   DevLoss loss;
+  uint32_t fixed;  // translation averaging: the view held constant (kNoFixedView: none)
 };
+constexpr uint32_t kNoFixedView = 0xffffffffu;
 
 template <bool kWriteBlocks, int kResidual, bool kScalarU, int kLoss>
 // two blocks (16 warps) per SM: three (<= 80 registers) spill and measure 10 % slower (profiles/r01_g_microbench.txt item 5)
@@ -124,6 +134,15 @@ __global__ void __launch_bounds__(kBlock, 2) k_edges(const K1Args A) {
     if (c + 1 < nrec) { rec_n = wait_rec(c + 1); gather(rec_n, ce + lane, cf_n, qrow_n, qcol_n); }
     const bool row_is_j = (cf & kSideBit) != 0;
     const Q4 qm{rec[lane], rec[32 + lane], rec[64 + lane], rec[96 + lane]};
+    // translation averaging holds ONE view constant (position_estimator.cpp:121-122 SetParameterBlockConstant): its gradient is
+    // dropped and every off-diagonal block that touches it is stored as zero, so the step of that view is exactly zero and
+    // the other views see the reduced system Ceres solves (their diagonal blocks keep the edge's contribution)
+    bool fix_row = false, fix_any = false;
+    if (kResidual == 2 && A.fixed != kNoFixedView) {
+      const uint32_t rowv = reinterpret_cast<const uint32_t*>(rec + (4 + kU) * 32)[32 + lane];
+      fix_row = rowv == A.fixed;
+      fix_any = fix_row || (cf & ~kSideBit) == A.fixed;
+    }
     double u[6];
 #pragma unroll
     for (int k = 0; k < kU; ++k) u[k] = rec[(4 + k) * 32 + lane];
@@ -140,6 +159,13 @@ __global__ void __launch_bounds__(kBlock, 2) k_edges(const K1Args A) {
       for (int k = 0; k < 6; ++k) cur[k] = et.S[k];
       cur[6] = sgn * et.v[0]; cur[7] = sgn * et.v[1]; cur[8] = sgn * et.v[2];
       cur[kAcc - 1] = row_is_j ? 0.0 : 0.5 * et.rho[0];
+      if (kResidual == 2) {
+        if (fix_row) cur[6] = cur[7] = cur[8] = 0.0;
+        if (fix_any) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) et.S[k] = 0.0;   // cur[] already holds the diagonal contribution
+        }
+      }
       if (h < hi) {
         if (kCompact) {
           A.val[blk_index(h, 0, Rec<4>::kDoubles)] = et.ca;

@@ -99,7 +99,7 @@ template <int kBlk, typename Finish>
 __device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restrict__ recs, uint64_t lo, uint64_t hi, uint32_t t0, uint32_t t1,
                                             const uint32_t* __restrict__ seg_begin, const uint32_t* __restrict__ seg_len, const double* x4,
                                             const double* xs /*shared-memory copy of x[xbase ...], stride 3, or null*/, uint32_t xbase, bool nogather,
-                                            uint32_t keep8, Finish&& finish) {
+                                            uint32_t keep8, Finish&& finish, bool wrap = false, bool stop_after_priming = false) {
   // CHUNK-major loop: the kCR records of a bulk copy are consumed together with compile-time indices -- their shared-memory
   // reads, gathers and products are independent instruction streams (ILP = kCR), the loop / ring / address overhead is paid
   // once per chunk instead of once per record, and the x gather of chunk k+1 (its columns are in shared memory as soon as
@@ -114,15 +114,22 @@ __device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restri
   uint64_t pol_keep = 0, pol_stream = 0;
   if (keep8) { pol_keep = l2_policy_evict_last(); pol_stream = l2_policy_evict_first(); }
   const uint32_t chunk0 = (uint32_t)(lo >> 5) / kCR;
+  // WRAP-AROUND PREFETCH (persistent PCG kernel): every pass streams the same range, and the matrix does not depend on the
+  // vector being multiplied -- so when the last chunks of a pass have been consumed their ring stages are refilled with the
+  // FIRST chunks of the next pass.  Those copies land while the block sits in the two grid barriers and the vector phase of the
+  // CG step (the ring of an SM holds ~166 KB: a third of the whole matrix at 1M edges), and the next pass starts on data that
+  // is already in shared memory.  Chunk index k >= nchunk means chunk k - nchunk of the next pass; ring positions keep counting.
+  const bool wrap_ok = wrap && nchunk >= (uint32_t)kStages2;
   auto issue = [&](uint32_t k) {
     if (lane == 0) {
       const uint32_t st = (base + k) % kStages2;
-      const uint32_t bytes = min((uint32_t)kCR, nrec - k * kCR) * (uint32_t)Rec<kBlk>::kBytes;
+      const uint32_t kk = k < nchunk ? k : k - nchunk;
+      const uint32_t bytes = min((uint32_t)kCR, nrec - kk * kCR) * (uint32_t)Rec<kBlk>::kBytes;
       mbar_expect_tx(&wp.bars[st], bytes);
       if (keep8)
-        tma_load_bulk_hint(wp.ring + (size_t)st * kCD, src + (size_t)k * kCD, bytes, &wp.bars[st], ((chunk0 + k) & 7u) < keep8 ? pol_keep : pol_stream);
+        tma_load_bulk_hint(wp.ring + (size_t)st * kCD, src + (size_t)kk * kCD, bytes, &wp.bars[st], ((chunk0 + kk) & 7u) < keep8 ? pol_keep : pol_stream);
       else
-        tma_load_bulk(wp.ring + (size_t)st * kCD, src + (size_t)k * kCD, bytes, &wp.bars[st]);
+        tma_load_bulk(wp.ring + (size_t)st * kCD, src + (size_t)kk * kCD, bytes, &wp.bars[st]);
     }
   };
   // first record of chunk k, once its bulk copy has landed
@@ -146,11 +153,61 @@ __device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restri
       else { const double4 xv = reinterpret_cast<const double4*>(x4)[col]; g[j][0] = xv.x; g[j][1] = xv.y; g[j][2] = xv.z; }
     }
   };
-  for (uint32_t k = 0; k < nchunk && k < (uint32_t)kStages2; ++k) issue(k);
+  for (uint32_t k = wp.primed; k < nchunk && k < (uint32_t)kStages2; ++k) issue(k);  // wp.primed of them went out at the end of the previous pass
+  wp.primed = 0;
+  if (stop_after_priming) { wp.primed = min(nchunk, (uint32_t)kStages2); return; }
   if (nrec == 0 || t0 == t1) { wp.pos = base + nchunk; return; }
   uint32_t t = t0;
   uint32_t sb = (uint32_t)(seg_begin[t] - lo), se = sb + seg_len[t];
   double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+  if (kBlk == 4 && kRecordMajor4) {
+    // RECORD-major loop for the compact records: one record per iteration, the gather of record c+1 issued before record c is
+    // consumed.  Measured (profiles/r02_col_blocks.txt): on the L2-resident 1M-edge matrix this form is ~2 us per pass faster
+    // than the chunk-major one below (fewer live registers in the persistent kernel, gathers spread more evenly), which in turn
+    // is 10 % faster on the HBM-resident 20M-edge matrix (6-double records).
+    auto gather1 = [&](const double* rec, uint32_t c, double& x0, double& x1, double& x2) {
+      uint32_t col = reinterpret_cast<const uint32_t*>(rec + Rec<kBlk>::kColOffset)[lane] & ~kSideBit;
+      if ((c << 5) + (uint32_t)lane >= n) col = xbase;  // padding lanes of the last record
+      if (nogather) { x0 = col; x1 = 1.0; x2 = 2.0; }
+      else if (xs) { const double* p = xs + 3 * (size_t)(col - xbase); x0 = p[0]; x1 = p[1]; x2 = p[2]; }
+      else { const double4 xv = reinterpret_cast<const double4*>(x4)[col]; x0 = xv.x; x1 = xv.y; x2 = xv.z; }
+    };
+    const double* rec = wait_chunk(0);
+    double x0, x1, x2;
+    gather1(rec, 0, x0, x1, x2);
+    for (uint32_t c = 0; c < nrec; ++c) {
+      const uint32_t cb = c << 5, ce = cb + 32u, h = cb + (uint32_t)lane;
+      const double* rec_n = rec;
+      double n0 = 0.0, n1 = 0.0, n2 = 0.0;
+      if (c + 1 < nrec) {
+        rec_n = ((c + 1) % kCR == 0) ? wait_chunk((c + 1) / kCR) : rec + kRD;
+        gather1(rec_n, c + 1, n0, n1, n2);
+      }
+      const double c0 = rec[lane], h0 = rec[32 + lane], h1 = rec[64 + lane], h2 = rec[96 + lane];
+      const double tt = h0 * x0 + h1 * x1 + h2 * x2;
+      const double a = fabs(c0);
+      const double st = __longlong_as_double(__double_as_longlong(tt) ^ (__double_as_longlong(c0) & (long long)0x8000000000000000ull));
+      const double v0 = -(a * x0 + st * h0), v1 = -(a * x1 + st * h1), v2 = -(a * x2 + st * h2);
+      if ((c + 1) % kCR == 0 || c + 1 == nrec) {  // a chunk's stage can be refilled as soon as every lane has read its last record
+        __syncwarp();
+        if (c / kCR + kStages2 < nchunk || wrap_ok) issue(c / kCR + kStages2);
+      }
+      while (true) {
+        if (h >= sb && h < se) { y0 += v0; y1 += v1; y2 += v2; }
+        if (se > ce) break;  // the segment continues in the next record
+        finish(t, warp_sum_multi3(y0, y1, y2));
+        y0 = y1 = y2 = 0.0;
+        if (++t == t1) break;
+        sb = se; se = sb + seg_len[t];
+        if (sb >= ce) break;
+      }
+      rec = rec_n; x0 = n0; x1 = n1; x2 = n2;
+      if (t == t1) break;
+    }
+    wp.pos = base + nchunk;
+    wp.primed = wrap_ok ? (uint32_t)kStages2 : 0u;
+    return;
+  }
   const double* ch = wait_chunk(0);
   double g[kCR][3];
   gather_chunk(ch, 0, g);
@@ -187,7 +244,7 @@ __device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restri
     }
     // the chunk's stage can be refilled as soon as every lane has read it
     __syncwarp();
-    if (k + kStages2 < nchunk) issue(k + kStages2);
+    if (k + kStages2 < nchunk || wrap_ok) issue(k + kStages2);
 #pragma unroll
     for (int j = 0; j < kCR; ++j) {
       const uint32_t cb = (k * kCR + j) << 5, ce = cb + 32u, h = cb + (uint32_t)lane;
@@ -209,6 +266,17 @@ __device__ __forceinline__ void spmv_stream(WarpPipe& wp, const double* __restri
     for (int j = 0; j < kCR; ++j) { g[j][0] = gn[j][0]; g[j][1] = gn[j][1]; g[j][2] = gn[j][2]; }
   }
   wp.pos = base + nchunk;
+  wp.primed = wrap_ok ? (uint32_t)kStages2 : 0u;
+}
+
+// Wait for the bulk copies a wrap-around prefetch left in flight (a block must not exit with copies into its shared memory pending).
+__device__ __forceinline__ void spmv_drain(WarpPipe& wp) {
+  for (uint32_t k = 0; k < wp.primed; ++k) {
+    const uint32_t p = wp.pos + k;
+    mbar_wait(&wp.bars[p % kStages2], (p / kStages2) & 1u);
+  }
+  wp.pos += wp.primed;
+  wp.primed = 0;
 }
 
 // Measurement aid (gsfm_ra_measure_stream): the K2 ring alone -- every warp pulls its share of `nchunks` chunks of kChunkBytes
@@ -377,7 +445,7 @@ __device__ __forceinline__ void apply_view(uint32_t i, const ApplyArgs& A, doubl
 #pragma unroll
   for (int c = 0; c < 3; ++c) d[c] = Ji[3 * c] * t0 + Ji[3 * c + 1] * t1 + Ji[3 * c + 2] * t2;
   w3[0] = w3[1] = w3[2] = 0.0;
-  if (A.manifold) {
+  if (A.manifold == 1) {
     // x (+) delta = [sin|d| d/|d|, cos|d|] (x) x, a left rotation by 2 delta = R xt, i.e. R <- R Exp(xt); the state stays
     // an angle-axis vector (principal branch of the product quaternion).  |step| in the ambient quaternion space =
     // 2 sin(|delta| / 2) per view, |delta| = |xt| / 2.
@@ -498,6 +566,15 @@ __device__ __forceinline__ void finish_row(const PcgParams& P, uint32_t row, dou
   delta += zi[0] * y0 + zi[1] * y1 + zi[2] * y2;
 }
 
+// Put the first chunks of this warp's range in flight (before the prologue's barrier: they land under it).
+template <int kBlk>
+__device__ __forceinline__ void spmv_prime(const PcgParams& P, WarpPipe& wp) {
+  const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (!kWrapPrefetch || gwarp >= P.num_warps) return;
+  const uint64_t lo = (uint64_t)gwarp * P.warp_span, hi = min(P.H, lo + P.warp_span);
+  spmv_stream<kBlk>(wp, P.val, lo, hi, 0u, 0u, P.seg_begin, P.seg_len, P.z, nullptr, 0u, false, P.keep8, [](uint32_t, double) {}, false, true);
+}
+
 // One SpMV pass over this warp's range, s = (Ht + Lam) z.  Accumulates (per lane) gamma = r.z and delta = z.s over
 // the rows this lane finished.
 template <int kBlk>
@@ -531,7 +608,7 @@ __device__ __forceinline__ void spmv_pass(const PcgParams& P, WarpPipe& wp, doub
           if (lane == 0) { __threadfence(); atomicAdd(P.row_cnt + (rowf & ~kSideBit), 1u); }
         }
       }
-    });
+    }, kWrapPrefetch);
     if (ncb > 1u) {
       // several column blocks: a range holds many such segments; ONE fence for the whole range, then every one of them counts
       // itself in on its row's counter (lanes in parallel) -- a fence per segment would stall the stream every ~50 half-edges
@@ -657,6 +734,7 @@ __global__ void __launch_bounds__(kPcgBlock, kPcgBlocksPerSM) k_pcg_persistent(P
   unsigned bseq = (unsigned)P.sc->bar_seq;  // barrier sequence number, continues across launches
   double bb;
   bool done;
+  spmv_prime<kBlk>(P, wp);
   if (P.fused) {
     // ---- prologue (k_prepare_solve): LM damping in the tangent frame, block-Jacobi inverse, x = 0, r = b, z = p = M^-1 b
     if (gtid == 0) { P.sc->t_begin = gtimer_ns(); P.sc->bad = 0; }
@@ -765,6 +843,7 @@ __global__ void __launch_bounds__(kPcgBlock, kPcgBlocksPerSM) k_pcg_persistent(P
     ++iter;
     if (rr <= P.rtol2 * bb || iter >= P.max_iter || !isfinite(rr)) done = true;
   }
+  spmv_drain(wp);
   if (gtid == 0) {
     P.sc->xseq = (int)seq;
     P.sc->bar_seq = (int)bseq;

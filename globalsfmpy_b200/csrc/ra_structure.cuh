@@ -16,11 +16,15 @@ __device__ __host__ __forceinline__ int in_rec_doubles(int ku) { return (4 + ku)
 
 __global__ void k_setup_halfedges(uint64_t H, int ku, const uint32_t* __restrict__ he_edge, const uint32_t* __restrict__ he_row,
                                   const uint32_t* __restrict__ he_col, const double* __restrict__ omega_ij, const double* __restrict__ cov6,
-                                  const double* __restrict__ weight, int error_type, double* __restrict__ inrec) {
+                                  const double* __restrict__ weight, int error_type, double* __restrict__ inrec,
+                                  const uint32_t* __restrict__ ei = nullptr, const double* __restrict__ orientation = nullptr) {
   const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= H) return;
   const uint64_t k = he_edge[h];
-  const Q4 q = aa_to_quat(omega_ij[3 * k], omega_ij[3 * k + 1], omega_ij[3 * k + 2]);
+  // translation averaging (orientation != null): the measurement slot carries the pair's translation direction rotated into
+  // the global frame by the FIRST view's orientation (position_estimator.cpp:271-272), omega_ij holds TwoViewInfo::position_2
+  const Q4 q = orientation ? rotated_translation(orientation + 3 * (size_t)ei[k], omega_ij + 3 * k)
+                           : aa_to_quat(omega_ij[3 * k], omega_ij[3 * k + 1], omega_ij[3 * k + 2]);
   double* rec = inrec + (size_t)(h >> 5) * in_rec_doubles(ku);
   const int lane = (int)(h & 31);
   rec[lane] = q.w; rec[32 + lane] = q.x; rec[64 + lane] = q.y; rec[96 + lane] = q.z;

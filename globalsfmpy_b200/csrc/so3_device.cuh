@@ -85,6 +85,14 @@ __host__ __device__ inline void quat_to_mat(const Q4& q, double* R) {
   R[6] = 2.0 * (xz - wy);       R[7] = 2.0 * (yz + wx);       R[8] = 1.0 - 2.0 * (xx + yy);
 }
 
+// GetRotatedTranslation (src/GSfM_nonlinear_position_estimator.cpp:36-44): R(omega)^T t, the relative translation of a view
+// pair rotated into the global frame by the first view's orientation.  Returned in the x,y,z slots of a Q4 (w = 0).
+__host__ __device__ inline Q4 rotated_translation(const double* omega, const double* t) {
+  double R[9];
+  quat_to_mat(aa_to_quat(omega[0], omega[1], omega[2]), R);
+  return Q4{0.0, R[0] * t[0] + R[3] * t[1] + R[6] * t[2], R[1] * t[0] + R[4] * t[1] + R[7] * t[2], R[2] * t[0] + R[5] * t[1] + R[8] * t[2]};
+}
+
 // Log of a unit quaternion as a rotation vector with angle in [0, pi] (ceres QuaternionToAngleAxis),
 // also returning c(theta) of Jl^-1(e) = I - [e]x/2 + c [e]x^2,
 //   c = 1/theta^2 - cot(theta/2)/(2 theta),  cot(theta/2) = w/|v| (no trigonometry needed).
@@ -428,8 +436,50 @@ __host__ __device__ inline double triggs_kappa(double s, const double* rho) {
 //   B^T B = w^2 ((1 - g theta^2) I + g f f^T),   u = B^T r = w^2 f,
 //   S = rho' w^2 ((1 - g theta^2) I + (g - kappa w^2) f f^T),   v = rho' w^2 f
 // -- no rotation matrix, no 3x3 products.
+// kResidual = 2: TRANSLATION averaging (src/GSfM_nonlinear_position_estimator.cpp:252-296 with
+//                theia::PairwiseTranslationError, T/sfm/global_pose_estimation/pairwise_translation_error.h:62-88).  The "views"
+//                are camera positions c (Euclidean parameters, carried in the x,y,z slots of the Q4 arguments), the measurement
+//                is the unit direction t_ij (in the x,y,z slots of qij) and
+//                    r = w (d / |d| - t_ij),  d = c_j - c_i,  |d| := 1 when |d| < 1e-12 (the reference's kNormTolerance branch:
+//                    the norm becomes the CONSTANT 1, so the Jacobian is w I there)
+//                    d r / d c_j = +B,  d r / d c_i = -B,  B = (w / |d|) (I - u u^T),  u = d / |d|    (B symmetric)
+//                -- again a Laplacian stencil: S = rho' (B^T B - kappa ub ub^T), ub = B^T r, v = rho' ub.
+template <bool kNeedJacobian, int kLoss, bool kStencilOnly>
+__host__ __device__ inline void translation_terms(const Q4& ci, const Q4& cj, const Q4& tij, double w, const DevLoss& L, EdgeTerms& o) {
+  const double d0 = cj.x - ci.x, d1 = cj.y - ci.y, d2 = cj.z - ci.z;
+  double n = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+  const bool tiny = n < 1e-12;
+  if (tiny) n = 1.0;
+  const double u0 = d0 / n, u1 = d1 / n, u2 = d2 / n;
+  o.r[0] = w * (u0 - tij.x); o.r[1] = w * (u1 - tij.y); o.r[2] = w * (u2 - tij.z);
+  const double s = o.r[0] * o.r[0] + o.r[1] * o.r[1] + o.r[2] * o.r[2];
+  eval_loss<kLoss>(L, s, o.rho);
+  if (!kNeedJacobian) return;
+  const double a = w / n, p = tiny ? 0.0 : a;   // B = a I - p u u^T
+  double B[6];                                  // symmetric, packed 00 01 02 11 12 22
+  B[0] = a - p * u0 * u0; B[1] = -p * u0 * u1; B[2] = -p * u0 * u2;
+  B[3] = a - p * u1 * u1; B[4] = -p * u1 * u2; B[5] = a - p * u2 * u2;
+  if (!kStencilOnly) {
+    o.B[0] = B[0]; o.B[1] = B[1]; o.B[2] = B[2]; o.B[3] = B[1]; o.B[4] = B[3]; o.B[5] = B[4]; o.B[6] = B[2]; o.B[7] = B[4]; o.B[8] = B[5];
+  }
+  const double ub0 = B[0] * o.r[0] + B[1] * o.r[1] + B[2] * o.r[2];
+  const double ub1 = B[1] * o.r[0] + B[3] * o.r[1] + B[4] * o.r[2];
+  const double ub2 = B[2] * o.r[0] + B[4] * o.r[1] + B[5] * o.r[2];
+  const double kappa = triggs_kappa(s, o.rho);
+  const double rho1 = o.rho[1];
+  // B^T B = B B (symmetric)
+  o.S[0] = rho1 * (B[0] * B[0] + B[1] * B[1] + B[2] * B[2] - kappa * ub0 * ub0);
+  o.S[1] = rho1 * (B[0] * B[1] + B[1] * B[3] + B[2] * B[4] - kappa * ub0 * ub1);
+  o.S[2] = rho1 * (B[0] * B[2] + B[1] * B[4] + B[2] * B[5] - kappa * ub0 * ub2);
+  o.S[3] = rho1 * (B[1] * B[1] + B[3] * B[3] + B[4] * B[4] - kappa * ub1 * ub1);
+  o.S[4] = rho1 * (B[1] * B[2] + B[3] * B[4] + B[4] * B[5] - kappa * ub1 * ub2);
+  o.S[5] = rho1 * (B[2] * B[2] + B[4] * B[4] + B[5] * B[5] - kappa * ub2 * ub2);
+  o.v[0] = rho1 * ub0; o.v[1] = rho1 * ub1; o.v[2] = rho1 * ub2;
+}
+
 template <bool kNeedJacobian, int kResidual = 0, bool kScalarU = false, int kLoss = -1, bool kStencilOnly = false>
 __host__ __device__ inline void edge_terms(const Q4& qi, const Q4& qj, const Q4& qij, const double* U, const DevLoss& L, EdgeTerms& o) {
+  if (kResidual == 2) { translation_terms<kNeedJacobian, kLoss, kStencilOnly>(qi, qj, qij, U[0], L, o); return; }
   const Q4 qE = qmul(qmul(qj, qconj(qi)), qconj(qij));  // error rotation R_j R_i^T R_ij^T
   if (kNeedJacobian && kStencilOnly && kScalarU && kResidual == 0) {
     double e[3], theta2, c;

@@ -218,7 +218,11 @@ def _eigen_rot(q):
 
 
 def _general_residual(etype, qa, qb, qrel):
-    """include/pairwise_rotation_error_quat.hpp:125-150 (QuatFNorm) and :169-196 (RotFNorm), restated with numpy."""
+    """include/pairwise_rotation_error_quat.hpp:82-106 (Quat), :125-150 (QuatFNorm) and :169-196 (RotFNorm), restated with numpy."""
+    if etype == capi.QUATERNION_COSINE:
+        # hpp:82-106: delta_q = q_rel * conj(q_b * conj(q_a)); residual = weight * 2 * delta_q.vec()
+        conj = lambda q: np.concatenate([-q[:3], q[3:]])
+        return 2.0 * _qmul_xyzw(qrel, conj(_qmul_xyzw(qb, conj(qa))))[:3]
     if etype == capi.QUATERNION_NORM:
         est = _qmul_xyzw(qrel, qa)
         b = -qb if qb[1] < 0 else qb
@@ -227,9 +231,10 @@ def _general_residual(etype, qa, qb, qrel):
     return (_eigen_rot(qrel) @ _eigen_rot(qa) - _eigen_rot(qb)).reshape(-1, order="F")  # Eigen linear index = column-major
 
 
-@pytest.mark.parametrize("etype", [capi.QUATERNION_NORM, capi.ROTATION_MAT_FNORM])
+@pytest.mark.parametrize("etype", [capi.QUATERNION_COSINE, capi.QUATERNION_NORM, capi.ROTATION_MAT_FNORM])
 def test_general_residual_types(etype):
-    """The oracle's jet evaluation of the 4- and 9-dimensional functors against a numpy restatement of the reference formulas,
+    """The oracle's jet evaluation of the three quaternion-parameter functors (3-, 4- and 9-dimensional residuals; hpp:82-106,
+    :125-150, :169-196) against a numpy restatement of the reference formulas,
     and its local-coordinate Jacobians against finite differences through EigenQuaternionParameterization::Plus
     (x (+) d = [sin|d| d/|d|, cos|d|] (x) x)."""
     g = vg.synthetic_pose_graph(12, 40, seed=3, noise_deg=5.0, outlier_fraction=0.2)
