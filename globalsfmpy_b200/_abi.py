@@ -4,7 +4,7 @@ CUDA product library)."""
 import ctypes as C
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 COMM_ID_BYTES = 128
 IPC_HANDLE_BYTES = 128
 
@@ -15,6 +15,8 @@ OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NUMERIC = 0, -1, 
 QUATERNION_NORM, ROTATION_MAT_FNORM, QUATERNION_COSINE = 0, 1, 2
 ANGLE_AXIS_COVARIANCE, ANGLE_AXIS, ANGLE_AXIS_INLIERS = 3, 4, 5
 ANGLE_AXIS_COV_INLIERS, ANGLE_AXIS_COVTRACE, ANGLE_AXIS_COVNORM = 6, 7, 8
+# translation averaging through the same solver (include/gsfm_pa.h): theia::PositionErrorType::BASELINE
+POSITION_BASELINE = 16
 
 # gsfm_ra_loss_kind
 (LOSS_TRIVIAL, LOSS_HUBER, LOSS_SOFTLONE, LOSS_CAUCHY, LOSS_ARCTAN, LOSS_TOLERANT, LOSS_TUKEY,
@@ -25,6 +27,7 @@ SOLVER_PCG, SOLVER_DENSE_CHOLESKY, SOLVER_AUTO = 0, 1, 2
 AUTO_DENSE_MAX_VIEWS = 1024
 MIN_EDGES_PER_GPU = 500000
 
+TERMINATION_FAILURE = 7
 TERMINATION = {0: "NONE", 1: "FUNCTION_TOLERANCE", 2: "GRADIENT_TOLERANCE", 3: "PARAMETER_TOLERANCE",
                4: "MAX_ITERATIONS", 5: "MIN_RADIUS", 6: "INVALID_STEPS", 7: "FAILURE"}
 
@@ -70,7 +73,18 @@ class Loss(C.Structure):
 class Problem(C.Structure):
     _fields_ = [("num_views", C.c_uint32), ("num_edges", C.c_uint64), ("edge_i", _u32p), ("edge_j", _u32p),
                 ("omega_ij", _dp), ("cov6", _dp), ("edge_weight", _dp), ("error_type", C.c_int32),
-                ("total_pair_count", C.c_int32)]
+                ("total_pair_count", C.c_int32), ("orientation", _dp), ("fixed_view", C.c_int64)]
+
+
+class PositionProblem(C.Structure):
+    """gsfm_pa_problem (include/gsfm_pa.h)."""
+    _fields_ = [("num_views", C.c_uint32), ("num_edges", C.c_uint64), ("edge_i", _u32p), ("edge_j", _u32p),
+                ("position_2", _dp), ("orientation", _dp), ("edge_weight", _dp), ("fixed_view", C.c_int64),
+                ("error_type", C.c_int32), ("reserved", C.c_int32)]
+
+
+# gsfm_pa_error_type == theia::PositionErrorType (include/pairwise_translation_error_covariance.hpp:47-51)
+PA_BASELINE, PA_COVARIANCE = 0, 1
 
 
 class Options(C.Structure):
@@ -159,7 +173,7 @@ class ProblemArrays:
     """Owns contiguous numpy arrays and the gsfm_ra_problem that points at them."""
 
     def __init__(self, num_views, edge_i, edge_j, omega_ij, cov6=None, edge_weight=None,
-                 error_type=ANGLE_AXIS):
+                 error_type=ANGLE_AXIS, orientation=None, fixed_view=-1):
         self.edge_i = np.ascontiguousarray(edge_i, dtype=np.uint32)
         self.edge_j = np.ascontiguousarray(edge_j, dtype=np.uint32)
         E = len(self.edge_i)
@@ -178,6 +192,11 @@ class ProblemArrays:
         p.cov6 = ptr(self.cov6)
         p.edge_weight = ptr(self.edge_weight)
         p.error_type = self.error_type
+        # translation averaging (POSITION_BASELINE): omega_ij holds position_2, plus the global orientations and the fixed view
+        self.orientation = None if orientation is None else as_f64(orientation, (self.num_views, 3))
+        self.fixed_view = int(fixed_view)
+        p.orientation = ptr(self.orientation)
+        p.fixed_view = self.fixed_view
         self.c = p
 
 

@@ -68,10 +68,18 @@ def declare(lib):
     lib.gsfm_ra_write_covariance_rot.argtypes = [C.c_char_p, C.c_uint64, _u32p, _u32p, _dp, _dp]
     lib.gsfm_ra_read_1dsfm.argtypes = [C.c_char_p, PP(C.c_uint32), PP(C.c_uint64), PP(_u32p), PP(_dp), PP(C.c_uint64), PP(_u32p), PP(_u32p),
                                        PP(_dp), PP(_dp), PP(_i32p)]
+    # include/gsfm_pa.h (translation averaging)
+    qp = C.POINTER(PositionProblem)
+    lib.gsfm_pa_default_options.argtypes = [op]
+    lib.gsfm_pa_default_options.restype = None
+    lib.gsfm_pa_as_ra_problem.argtypes = [qp, pp]
+    lib.gsfm_pa_solve.argtypes = [qp, op, _dp, sp]
+    lib.gsfm_pa_eval_edges.argtypes = [qp, lp, _dp, _dp, _dp, _dp, _dp, C.c_int32]
+    lib.gsfm_pa_cost.argtypes = [qp, lp, _dp, _dp, C.c_int32]
     return lib
 
 
-# every symbol include/gsfm_ra.h declares (checked by the CPU test-suite)
+# every symbol include/gsfm_ra.h and include/gsfm_pa.h declare (checked by the CPU test-suite)
 EXPORTED_SYMBOLS = [
     "gsfm_ra_abi_version", "gsfm_ra_last_error", "gsfm_ra_device_count", "gsfm_ra_default_options",
     "gsfm_ra_solve", "gsfm_ra_solve_sigma_consensus", "gsfm_ra_solver_create", "gsfm_ra_solver_create_sharded", "gsfm_ra_solver_destroy",
@@ -81,6 +89,7 @@ EXPORTED_SYMBOLS = [
     "gsfm_ra_spmv", "gsfm_ra_pcg", "gsfm_ra_eval_loss", "gsfm_ra_filter_view_pairs", "gsfm_ra_residual_dim",
     "gsfm_ra_filter_initial_view_graph", "gsfm_ra_init_orientations_mst",
     "gsfm_ra_free", "gsfm_ra_read_covariance_rot", "gsfm_ra_write_covariance_rot", "gsfm_ra_read_1dsfm",
+    "gsfm_pa_default_options", "gsfm_pa_as_ra_problem", "gsfm_pa_solve", "gsfm_pa_eval_edges", "gsfm_pa_cost",
 ]
 
 _lib = None

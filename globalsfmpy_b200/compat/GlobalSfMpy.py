@@ -10,8 +10,10 @@ and argument meaning: options + `load_1DSFM_config`, `Rec
 `GlobalReconstructionEstimator.FilterInitialViewGraphAndCalibrateCameras / EstimateGlobalRotationsUncertainty /
 EstimateGlobalRotations / OrientationsFromMaximumSpanningTree / FilterRotations / orientations`, `SetOrientations`,
 `LossFunction`, `RotationEstimator`, `NonlinearRotationEstimator`, `RotationErrorType`, the MAGSAC gamma constants.
-Steps 4-9 of the pipeline (translations, positions, triangulation, bundle adjustment, file writers) are the rest of
-TheiaSfM and are out of scope: they raise NotImplementedError naming the reference function.
+Step 7 (`EstimatePosition`: robust translation averaging, src/GSfM_nonlinear_position_estimator.cpp) runs on the same device
+solver through include/gsfm_pa.h and fills `.positions`.  The remaining steps (pairwise-translation refinement, triangulation,
+bundle adjustment, file writers) are the rest of TheiaSfM and are out of scope: they raise NotImplementedError naming the
+reference function.
 """
 import enum
 import math
@@ -45,7 +47,7 @@ class RotationErrorType(enum.IntEnum):          # include/pairwise_rotation_erro
     ANGLE_AXIS_COVNORM = 8
 
 
-class PositionErrorType(enum.IntEnum):
+class PositionErrorType(enum.IntEnum):           # include/pairwise_translation_error_covariance.hpp:47-51; bind:441-443 exports BASELINE only
     BASELINE = 0
 
 
@@ -533,14 +535,55 @@ class GlobalReconstructionEstimator:
             del self.orientations[v]
         return True
 
+    def EstimatePosition(self, loss_func, error_type=PositionErrorType.BASELINE):
+        """bind:564-579 -> EstimatePositionNonLinear (src/GSfM_global_reconstruction_estimator.cpp:605-617) ->
+        GSfMNonlinearPositionEstimator::EstimatePositions(view_pairs, orientations_, &positions_, error_type, loss_func)
+        (src/GSfM_nonlinear_position_estimator.cpp:151-234) on the device through gsfm_pa_solve: camera-to-camera constraints
+        only (position_estimation_min_num_tracks_per_view = 0 in flags_1dsfm.yaml), every camera starts at the origin, one view
+        is held constant (the reference: positions->begin() of a hash map; here the smallest estimated view id -- the choice
+        moves the solution by a global translation only)."""
+        edges = self.view_graph_.GetAllEdges()
+        if len(edges) == 0 or len(self.orientations) == 0:
+            return False                                  # position_estimator.cpp:159-164
+        constrained = set()
+        for a, b in edges:
+            constrained.add(a); constrained.add(b)
+        ids = np.array(sorted(v for v in self.orientations if v in constrained), dtype=np.int64)   # InitializeRandomPositions :236-257
+        if len(ids) == 0:
+            return False
+        dense = {int(v): k for k, v in enumerate(ids.tolist())}
+        ei, ej, p2 = [], [], []
+        for (a, b), info in edges.items():
+            if a in dense and b in dense:                 # :307-312
+                ei.append(dense[a]); ej.append(dense[b]); p2.append(np.asarray(info.position_2, dtype=np.float64))
+        orient = np.array([np.asarray(self.orientations[int(v)], dtype=np.float64) for v in ids.tolist()]).reshape(len(ids), 3)
+        x = np.zeros((len(ids), 3))
+        if ei:
+            from globalsfmpy_b200 import positions as _pos
+            prob = _pos.PositionProblemArrays(len(ids), np.array(ei, np.uint32), np.array(ej, np.uint32), np.array(p2).reshape(len(ei), 3), orient,
+                                              fixed_view=0, error_type=int(error_type))
+            o = _pos.default_options()                    # Ceres defaults, max_num_iterations 400
+            if self.solver_options is not None:
+                o = _copy_options(self.solver_options)
+            else:
+                o.n_gpus = -1
+            L = loss_to_struct(loss_func)
+            o.loss = L
+            o.num_threads = int(self.options.num_threads)
+            x, summary, _ = _pos.solve(prob, o)
+            _solve.last_summary = summary
+            if summary.termination == _capi.TERMINATION_FAILURE:
+                return False                              # summary.IsSolutionUsable()
+        self.positions = {int(v): x[k].copy() for k, v in enumerate(ids.tolist())}
+        return True
+
     def _todo(name):  # noqa: N805
         def f(self, *a, **k):
-            raise NotImplementedError(f"{name}: pipeline steps after rotation averaging are TheiaSfM's (out of scope here)")
+            raise NotImplementedError(f"{name}: this pipeline step is TheiaSfM's (out of scope here: SURVEY section 2)")
         return f
 
     OptimizePairwiseTranslations = _todo("OptimizePairwiseTranslations")
     FilterRelativeTranslation = _todo("FilterRelativeTranslation")
-    EstimatePosition = _todo("EstimatePosition")
     EstimateStructure = _todo("EstimateStructure")
     BundleAdjustCameraPositionsAndPoints = _todo("BundleAdjustCameraPositionsAndPoints")
     BundleAdjustmentAndRemoveOutlierPoints = _todo("BundleAdjustmentAndRemoveOutlierPoints")

@@ -1749,6 +1749,48 @@ int gsfm_ra_filter_view_pairs(const gsfm_ra_problem* problem, const double* omeg
   return 0;
 }
 
+// ---- translation averaging (include/gsfm_pa.h): the same solver on error type GSFM_RA_POSITION_BASELINE ------------------
+void gsfm_pa_default_options(gsfm_ra_options* o) {
+  if (!o) return;
+  gsfm_ra_default_options(o);
+  o->max_num_iterations = 400;           // NonlinearPositionEstimator::Options::max_num_iterations
+  o->loss.kind = GSFM_RA_LOSS_HUBER;     // new ceres::HuberLoss(options_.robust_loss_width), position_estimator.cpp:330
+  o->loss.p[0] = 0.1;
+}
+
+int gsfm_pa_as_ra_problem(const gsfm_pa_problem* p, gsfm_ra_problem* out) {
+  if (!p || !out) { set_error("NULL argument"); return GSFM_RA_ERR_INVALID; }
+  if (p->error_type != GSFM_PA_BASELINE && p->error_type != GSFM_PA_COVARIANCE) { set_error("unknown position error type %d", p->error_type); return GSFM_RA_ERR_INVALID; }
+  if (!p->position_2 || !p->orientation) { set_error("position_2 / orientation is NULL"); return GSFM_RA_ERR_INVALID; }
+  std::memset(out, 0, sizeof(*out));
+  out->num_views = p->num_views; out->num_edges = p->num_edges;
+  out->edge_i = p->edge_i; out->edge_j = p->edge_j;
+  out->omega_ij = p->position_2; out->edge_weight = p->edge_weight;
+  out->error_type = GSFM_RA_POSITION_BASELINE;
+  out->orientation = p->orientation;
+  out->fixed_view = p->fixed_view;
+  return 0;
+}
+
+int gsfm_pa_solve(const gsfm_pa_problem* problem, const gsfm_ra_options* options, double* positions_inout, gsfm_ra_summary* summary) {
+  gsfm_ra_problem q;
+  RA_TRY(gsfm_pa_as_ra_problem(problem, &q));
+  return gsfm_ra_solve(&q, options, positions_inout, summary);
+}
+
+int gsfm_pa_eval_edges(const gsfm_pa_problem* problem, const gsfm_ra_loss* loss, const double* positions, double* r, double* jac_i, double* jac_j,
+                       double* rho, int32_t device) {
+  gsfm_ra_problem q;
+  RA_TRY(gsfm_pa_as_ra_problem(problem, &q));
+  return gsfm_ra_eval_edges(&q, loss, positions, r, jac_i, jac_j, rho, device);
+}
+
+int gsfm_pa_cost(const gsfm_pa_problem* problem, const gsfm_ra_loss* loss, const double* positions, double* cost, int32_t device) {
+  gsfm_ra_problem q;
+  RA_TRY(gsfm_pa_as_ra_problem(problem, &q));
+  return gsfm_ra_cost(&q, loss, positions, cost, device);
+}
+
 }  // extern "C"
 
 #include "gsfm_graph.cuh"

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "../../include/gsfm_ra.h"
+#include "../../include/gsfm_pa.h"
 #include "so3_device.cuh"
 
 using namespace gsfm;

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GSFM_RA_ABI_VERSION 2
+#define GSFM_RA_ABI_VERSION 3
 
 typedef enum {
   GSFM_RA_OK = 0,
@@ -54,7 +54,12 @@ typedef enum {
   GSFM_RA_ANGLE_AXIS_INLIERS = 5,     /* U = edge_weight * I           :260-264 (weight = #matches/100 from the host) */
   GSFM_RA_ANGLE_AXIS_COV_INLIERS = 6, /* U = Lt * edge_weight          :265-274 */
   GSFM_RA_ANGLE_AXIS_COVTRACE = 7,    /* U = sqrt(1/trace(1e8 Sigma)) I :275-282 */
-  GSFM_RA_ANGLE_AXIS_COVNORM = 8      /* U = sqrt(1/||1e8 Sigma||_F) I  :283-288 */
+  GSFM_RA_ANGLE_AXIS_COVNORM = 8,     /* U = sqrt(1/||1e8 Sigma||_F) I  :283-288 */
+  /* Translation averaging (the boundary for it is include/gsfm_pa.h): the "views" are camera POSITIONS,
+   * residual theia::PairwiseTranslationError, PositionErrorType::BASELINE
+   * (src/GSfM_nonlinear_position_estimator.cpp:252-296).  The same solver, layouts and kernels; gsfm_ra_problem carries
+   * position_2 in omega_ij plus the two extra fields at its end.                                                      */
+  GSFM_RA_POSITION_BASELINE = 16
 } gsfm_ra_error_type;
 
 /* Robust losses of scripts/loss_functions.py (formulas at the cited lines). */
@@ -123,6 +128,10 @@ typedef struct {
   int32_t total_pair_count;  /* gsfm_ra_solve_sigma_consensus only: size of the caller's view-pair map INCLUDING the pairs it
                                 skipped (the reference's stop test averages |w - w_prev| over that count,
                                 rotation_estimator.cpp:419-424); 0 = num_edges                                      */
+  /* GSFM_RA_POSITION_BASELINE only (ignored otherwise; ABI v3): */
+  const double* orientation; /* [N][3] global orientations (angle-axis): an edge's direction is R(orientation[edge_i])^T * omega_ij[k],
+                                omega_ij[k] = TwoViewInfo::position_2 (position_estimator.cpp:36-44, 271-272)           */
+  int64_t fixed_view;        /* the view whose position is held constant (position_estimator.cpp:121-122), < 0 = none  */
 } gsfm_ra_problem;
 
 typedef enum {

@@ -256,6 +256,31 @@ void QuatPlusJacobian(const double* x, double* J /*4x3 row-major*/) {
 }
 /* one quaternion edge through jets; Jacobians returned in the 3-dim LOCAL (tangent) coordinates Ceres optimises in:
  * J_local = J_ambient(dim x 4) * PlusJacobian(4x3).  type selects the functor (0: QuatFNorm, 1: RotFNorm, 2: Quat). */
+/* theia::PairwiseTranslationError::operator()
+ * (thirdparty/TheiaSfM/src/theia/sfm/global_pose_estimation/pairwise_translation_error.h:62-88), as AutoDiffCostFunction
+ * <PairwiseTranslationError, 3, 3, 3> runs it: below kNormTolerance the norm is REPLACED by the constant T(1.0), so the dual
+ * part of the norm (0 * inf = NaN at coincident positions) is discarded with it.                                        */
+template <typename T>
+void TranslationResidual(const T* position1, const T* position2, const double* translation_direction, double weight, T* residuals) {
+  const double kNormTolerance = 1e-12;
+  T translation[3];
+  translation[0] = position2[0] - position1[0];
+  translation[1] = position2[1] - position1[1];
+  translation[2] = position2[2] - position1[2];
+  T norm = sqrt(translation[0] * translation[0] + translation[1] * translation[1] + translation[2] * translation[2]);
+  if (val(norm) < kNormTolerance) norm = T(1.0);
+  residuals[0] = T(weight) * (translation[0] / norm - T(translation_direction[0]));
+  residuals[1] = T(weight) * (translation[1] / norm - T(translation_direction[1]));
+  residuals[2] = T(weight) * (translation[2] / norm - T(translation_direction[2]));
+}
+
+/* GetRotatedTranslation, src/GSfM_nonlinear_position_estimator.cpp:36-44: rotation.transpose() * translation */
+void RotatedTranslation(const double* orientation, const double* translation, double* out) {
+  Mat3<double> R;
+  AngleAxisToMatrix(orientation, &R);
+  for (int c = 0; c < 3; ++c) out[c] = R.m[0][c] * translation[0] + R.m[1][c] * translation[1] + R.m[2][c] * translation[2];
+}
+
 int ResidualDim(int type) { return type == GSFM_RA_QUATERNION_NORM ? 4 : (type == GSFM_RA_ROTATION_MAT_FNORM ? 9 : 3); }
 void QuatEdge(int type, const double* qa, const double* qb, const double* qrel, double weight, double* r, double* Ji, double* Jj) {
   Jet a[4], b[4], res[9];
@@ -455,7 +480,8 @@ bool TypeNeedsCov(int type) {
   return type == GSFM_RA_ANGLE_AXIS_COVARIANCE || type == GSFM_RA_ANGLE_AXIS_COV_INLIERS ||
          type == GSFM_RA_ANGLE_AXIS_COVTRACE || type == GSFM_RA_ANGLE_AXIS_COVNORM;
 }
-bool TypeSupported(int type) { return type >= GSFM_RA_QUATERNION_NORM && type <= GSFM_RA_ANGLE_AXIS_COVNORM; }
+bool IsPosition(const gsfm_ra_problem* p) { return p->error_type == GSFM_RA_POSITION_BASELINE; }
+bool TypeSupported(int type) { return (type >= GSFM_RA_QUATERNION_NORM && type <= GSFM_RA_ANGLE_AXIS_COVNORM) || type == GSFM_RA_POSITION_BASELINE; }
 bool IsQuat(const gsfm_ra_problem* p) { return p->error_type <= GSFM_RA_QUATERNION_COSINE; }
 
 void EdgeU(const gsfm_ra_problem* p, uint64_t k, double* U) {
@@ -489,6 +515,24 @@ void EvalEdgeRaw(const gsfm_ra_problem* p, uint64_t k, const double* omega, Edge
     const double w = p->edge_weight ? p->edge_weight[k] : 1.0;  /* cost_weight = 1.0, rotation_estimator.cpp:125 */
     QuatEdge(p->error_type, omega + 4 * (size_t)p->edge_i[k], omega + 4 * (size_t)p->edge_j[k], qrel, w, out->r, jac ? out->Ji : nullptr,
              jac ? out->Jj : nullptr);
+    return;
+  }
+  if (IsPosition(p)) {
+    /* translation averaging: `omega` holds camera positions, omega_ij holds TwoViewInfo::position_2
+     * (src/GSfM_nonlinear_position_estimator.cpp:298-343, weight 1.0 at :320) */
+    double dir[3];
+    RotatedTranslation(p->orientation + 3 * (size_t)p->edge_i[k], p->omega_ij + 3 * k, dir);
+    const double w = p->edge_weight ? p->edge_weight[k] : 1.0;
+    const double* c1 = omega + 3 * (size_t)p->edge_i[k];
+    const double* c2 = omega + 3 * (size_t)p->edge_j[k];
+    if (!jac) { TranslationResidual<double>(c1, c2, dir, w, out->r); return; }
+    Jet a[3], b[3], res[3];
+    for (int q = 0; q < 3; ++q) { a[q] = Jet(c1[q]); a[q].v[q] = 1.0; b[q] = Jet(c2[q]); b[q].v[3 + q] = 1.0; }
+    TranslationResidual<Jet>(a, b, dir, w, res);
+    for (int q = 0; q < 3; ++q) {
+      out->r[q] = res[q].a;
+      for (int c = 0; c < 3; ++c) { out->Ji[3 * q + c] = res[q].v[c]; out->Jj[3 * q + c] = res[q].v[3 + c]; }
+    }
     return;
   }
   double U[9];
@@ -650,6 +694,17 @@ int Linearize(const gsfm_ra_problem* p, const LossEval& loss, const double* omeg
       }
     }
   }
+  if (IsPosition(p) && p->fixed_view >= 0) {
+    /* problem_->SetParameterBlockConstant (position_estimator.cpp:121-122): Ceres drops the block from the program.  On the full
+     * structure the same reduced system results from a zero gradient for that view and zero off-diagonal blocks in its row
+     * and column -- its step is then exactly zero and nobody else sees it (its own diagonal block only keeps the system
+     * non-singular); the diagonal blocks of its neighbours keep the edges' contributions, as in the reduced program.      */
+    const size_t f = (size_t)p->fixed_view;
+    for (int a = 0; a < 3; ++a) L->g[3 * f + a] = 0.0;
+    for (uint64_t k = 0; k < E; ++k)
+      if (p->edge_i[k] == f || p->edge_j[k] == f)
+        for (int q = 0; q < 9; ++q) { L->hoff[9 * S.slot_ij[k] + q] = 0.0; L->hoff[9 * S.slot_ji[k] + q] = 0.0; }
+  }
   return 0;
 }
 
@@ -777,6 +832,7 @@ double NowMs() {
 int CheckProblem(const gsfm_ra_problem* p) {
   if (!p || !p->edge_i || !p->edge_j || !p->omega_ij) return GSFM_RA_ERR_INVALID;
   if (!TypeSupported(p->error_type)) return GSFM_RA_ERR_UNSUPPORTED;
+  if (IsPosition(p) && (!p->orientation || p->fixed_view >= (int64_t)p->num_views)) return GSFM_RA_ERR_INVALID;
   if (TypeNeedsCov(p->error_type) && !p->cov6) return GSFM_RA_ERR_INVALID;
   for (uint64_t k = 0; k < p->num_edges; ++k)
     if (p->edge_i[k] >= p->num_views || p->edge_j[k] >= p->num_views || p->edge_i[k] == p->edge_j[k]) return GSFM_RA_ERR_INVALID;

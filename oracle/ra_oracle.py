@@ -169,3 +169,9 @@ def filter_view_pairs(prob, omega, max_degrees):
                                            capi.ptr(keep, C.c_uint8), _p(ang))
     assert rc == 0, rc
     return keep.astype(bool), ang
+
+
+def position_problem(pp):
+    """The gsfm_ra_problem (error type POSITION_BASELINE) of a globalsfmpy_b200.positions.PositionProblemArrays: every oracle
+    entry point above takes it, with positions in place of omega (translation averaging)."""
+    return pp.as_rotation_solver_problem()

@@ -12,6 +12,7 @@
 #include <unistd.h>
 #include <unordered_map>
 
+#include "../../include/gsfm_position_estimator.hpp"
 #include "../../include/gsfm_rotation_estimator.hpp"
 
 namespace {
@@ -29,7 +30,7 @@ struct Matrix3d {                                 // stand-in for Eigen::Matrix3
   double operator()(int r, int c) const { return m[3 * r + c]; }
   double& operator()(int r, int c) { return m[3 * r + c]; }
 };
-struct TwoViewInfo { Vector3d rotation_2; int num_verified_matches = 0; };  // T/sfm/twoview_info.h:54-98
+struct TwoViewInfo { Vector3d rotation_2, position_2; int num_verified_matches = 0; };  // T/sfm/twoview_info.h:54-98
 typedef std::unordered_map<ViewIdPair, TwoViewInfo, PairHash> ViewPairs;
 typedef std::unordered_map<ViewId, Vector3d> Orientations;
 typedef std::unordered_map<ViewIdPair, std::pair<Matrix3d, Vector3d>, PairHash> CovarianceMap;
@@ -92,8 +93,9 @@ int main(int argc, char** argv) {
   std::mt19937 rng(56);  // the seed of Theia's rotation tests
   std::uniform_real_distribution<double> uni(-1.0, 1.0);
   std::normal_distribution<double> gauss(0.0, 1.0);
-  Orientations gt, init;
+  Orientations gt, init, cam;  // cam: ground-truth camera positions (translation averaging)
   for (int k = 0; k < n; ++k) { Vector3d w; for (int t = 0; t < 3; ++t) w[t] = 0.2 * uni(rng) * 3.0; gt[k] = w; }
+  for (int k = 0; k < n; ++k) { Vector3d c; for (int t = 0; t < 3; ++t) c[t] = 10.0 * uni(rng); cam[k] = c; }
   ViewPairs pairs;
   CovarianceMap covs;
   auto add = [&](ViewId a, ViewId b) {
@@ -105,6 +107,13 @@ int main(int argc, char** argv) {
     Vector3d noise; for (int t = 0; t < 3; ++t) noise[t] = gauss(rng) * (1.0 * M_PI / 180.0) / std::sqrt(3.0);
     Exp(noise, N); Mul(N, Rab, Rn);
     TwoViewInfo info; info.rotation_2 = Log(Rn); info.num_verified_matches = 100;
+    {  // position_2 = R_a (c_b - c_a) / |c_b - c_a| with half a degree of noise (T/sfm/twoview_info.h: position of camera 2 in frame 1)
+      double d[3], nn = 0;
+      for (int t = 0; t < 3; ++t) { d[t] = cam[b][t] - cam[a][t]; nn += d[t] * d[t]; }
+      for (int t = 0; t < 3; ++t) d[t] = d[t] / std::sqrt(nn) + gauss(rng) * (0.5 * M_PI / 180.0);
+      nn = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      for (int r = 0; r < 3; ++r) info.position_2[r] = (Ra[3 * r] * d[0] + Ra[3 * r + 1] * d[1] + Ra[3 * r + 2] * d[2]) / nn;
+    }
     pairs[{a, b}] = info;
     Matrix3d S; S.m[0] = S.m[4] = S.m[8] = 1e-8 * (0.5 + std::fabs(uni(rng)));  // isotropic-ish covariance, 1e8 Sigma ~ 1
     covs[{a, b}] = {S, Vector3d()};
@@ -147,6 +156,12 @@ int main(int argc, char** argv) {
     Check(same, "  covariances survive the round trip bit for bit (upper triangle mirrored)");
     Check(!gsfm_b200::ReadCovariance(dir + "/nowhere", &back, &err) && err.find("cannot open") != std::string::npos, "  a missing file fails loudly");
     if (system(("rm -rf " + dir).c_str()) != 0) std::printf("      (could not remove %s)\n", dir.c_str());
+  }
+  typedef gsfm_b200::GSfMNonlinearPositionEstimator<ViewPairs, Orientations> PosEstimator;
+  if (expect_no_device) {
+    PosEstimator pe;
+    Orientations c;
+    Check(!pe.EstimatePositions(pairs, gt, &c) && pe.last_error().find("no CUDA device") != std::string::npos, "no CUDA device: EstimatePositions fails loudly");
   }
   if (expect_no_device) {
     Orientations o = init;
@@ -229,6 +244,43 @@ int main(int argc, char** argv) {
     std::printf("      spanning-tree initialisation: mean error vs ground truth %.3f deg\n", e * 180 / M_PI);
     Check(e < 10.0 * M_PI / 180.0, "  initialisation is consistent with the measurements");
     Check(base->EstimateRotations(vp, &o) && MeanError(o, gt, n) < 0.5 * M_PI / 180.0, "  and the solve converges from it");
+  }
+  {  // translation averaging behind theia::PositionEstimator (include/gsfm_position_estimator.hpp)
+    PosEstimator pe;
+    gsfm_b200::PositionEstimator<ViewPairs, Orientations>* pbase = &pe;
+    Orientations none, c;
+    ViewPairs nopairs;
+    Check(!pbase->EstimatePositions(nopairs, gt, &c) && !pbase->EstimatePositions(pairs, none, &c), "EstimatePositions returns false for empty inputs");
+    Check(pbase->EstimatePositions(pairs, gt, &c), "EstimatePositions (Huber 0.1, BASELINE, every camera starts at the origin)");
+    Check(c.size() == (size_t)n && pe.fixed_view() == 0, "  a position for every oriented view; the smallest id is the constant one");
+    Check(c.at(0)[0] == 0.0 && c.at(0)[1] == 0.0 && c.at(0)[2] == 0.0, "  the constant view stays at the origin");
+    // the gauge left is translation (fixed by view 0) and SCALE: compare after the least-squares scale about view 0
+    auto mean_err = [&](const Orientations& est_c) {
+      double num = 0, den = 0;
+      for (int k = 1; k < n; ++k)
+        for (int t = 0; t < 3; ++t) { const double g = cam[k][t] - cam[0][t]; num += g * est_c.at(k)[t]; den += est_c.at(k)[t] * est_c.at(k)[t]; }
+      const double sc = num / den;
+      double e = 0;
+      for (int k = 1; k < n; ++k) {
+        double d2 = 0;
+        for (int t = 0; t < 3; ++t) { const double d = sc * est_c.at(k)[t] - (cam[k][t] - cam[0][t]); d2 += d * d; }
+        e += std::sqrt(d2);
+      }
+      return e / (n - 1);
+    };
+    const double e = mean_err(c);
+    std::printf("      mean position error vs ground truth (scene of +-10): %.4f, %d iterations, cost %.6g -> %.6g\n", e, pe.summary().num_iterations,
+                pe.summary().initial_cost, pe.summary().final_cost);
+    Check(e < 0.3 && pe.summary().final_cost < 0.01 * pe.summary().initial_cost, "  recovers the camera positions up to the similarity gauge");
+    Orientations c2;
+    Check(pe.EstimatePositions(pairs, gt, &c2, gsfm_b200::PositionErrorType::BASELINE, gsfm_b200::CauchyLoss(0.1)) && mean_err(c2) < 0.3,
+          "EstimatePositions with a customized loss (Cauchy 0.1)");
+    Orientations fewer = gt; fewer.erase(9);
+    Orientations c3;
+    Check(pe.EstimatePositions(pairs, fewer, &c3) && c3.size() == (size_t)n - 1 && c3.count(9) == 0, "  a view without orientation gets no position and its pairs are skipped");
+    PosEstimator::Options po; po.min_num_points_per_view = 10;
+    PosEstimator pt(po);
+    Check(!pt.EstimatePositions(pairs, gt, &c3) && !pt.last_error().empty(), "  point-to-camera constraints are declined loudly");
   }
   std::printf("%s\n", g_failed ? "FAILED" : "ALL OK");
   return g_failed ? 1 : 0;

@@ -13,8 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_exports_every_declared_symbol():
-    header = open(os.path.join(ROOT, "include", "gsfm_ra.h")).read()
-    declared = set(re.findall(r"\b(gsfm_ra_[a-z_0-9]+)\s*\(", header))
+    header = open(os.path.join(ROOT, "include", "gsfm_ra.h")).read() + open(os.path.join(ROOT, "include", "gsfm_pa.h")).read()
+    declared = set(re.findall(r"\b(gsfm_[rp]a_[a-z_0-9]+)\s*\(", header))
     assert declared == set(capi.EXPORTED_SYMBOLS), declared ^ set(capi.EXPORTED_SYMBOLS)
     lib = capi.lib()
     for name in declared:
@@ -38,14 +38,16 @@ def test_struct_sizes_match_header(tmp_path):
     """The ctypes mirror against the C header itself: gcc prints sizeof / a few offsets of every struct of include/gsfm_ra.h."""
     import subprocess
     src = tmp_path / "sizes.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gsfm_ra.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %d\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gsfm_pa.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %d %zu %zu %zu\\n",'
                    'sizeof(gsfm_ra_loss),sizeof(gsfm_ra_problem),sizeof(gsfm_ra_options),sizeof(gsfm_ra_iteration),sizeof(gsfm_ra_summary),'
-                   'offsetof(gsfm_ra_loss,table),offsetof(gsfm_ra_options,n_gpus),offsetof(gsfm_ra_summary,num_linear_unconverged),GSFM_RA_ABI_VERSION);return 0;}\n')
+                   'offsetof(gsfm_ra_loss,table),offsetof(gsfm_ra_options,n_gpus),offsetof(gsfm_ra_summary,num_linear_unconverged),GSFM_RA_ABI_VERSION,'
+                   'offsetof(gsfm_ra_problem,fixed_view),sizeof(gsfm_pa_problem),offsetof(gsfm_pa_problem,error_type));return 0;}\n')
     exe = tmp_path / "sizes"
     subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
     got = [int(t) for t in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(capi.Loss), C.sizeof(capi.Problem), C.sizeof(capi.Options), C.sizeof(capi.Iteration), C.sizeof(capi.Summary),
-            capi.Loss.table.offset, capi.Options.n_gpus.offset, capi.Summary.num_linear_unconverged.offset, capi.ABI_VERSION]
+            capi.Loss.table.offset, capi.Options.n_gpus.offset, capi.Summary.num_linear_unconverged.offset, capi.ABI_VERSION,
+            capi.Problem.fixed_view.offset, C.sizeof(capi.PositionProblem), capi.PositionProblem.error_type.offset]
     assert got == want
 
 

@@ -31,9 +31,10 @@ def _graph_from_fixture(sfm, golden_dir):
         if vid not in cc:
             recon.RemoveView(vid)
     rot2 = vg.egs_to_rotation_2(z["edge_R"])
-    for (a, b), w, n in zip(z["edge_ij"].tolist(), rot2, z["num_verified_matches"].tolist()):
+    for (a, b), w, n, t in zip(z["edge_ij"].tolist(), rot2, z["num_verified_matches"].tolist(), z["edge_t"]):
         info = sfm.TwoViewInfo()
         info.rotation_2 = w
+        info.position_2 = np.array([1.0, -1.0, -1.0]) * t      # bundler_to_theia * t, T/io/read_1dsfm.cc:331-335
         info.num_verified_matches = n
         graph.AddEdge(a, b, info)
     for (a, b), c in zip(z["cov_ij"].tolist(), z["cov6"]):
@@ -200,6 +201,44 @@ def test_pipeline_call_sequence_on_madrid(sfm, golden_dir, madrid):
     in_cc, cc_ids = vg.filter_initial_view_graph(np.arange(madrid.num_views), ij, np.ones(len(kept), np.int64), 0)
     assert view_graph.NumEdges() == int(in_cc.sum()) <= int(keep.sum()) < n0
     assert set(est.orientations) == set(int(madrid.view_ids[k]) for k in cc_ids) == set(view_graph.ViewIds())
+
+
+@pytest.mark.gpu
+def test_estimate_position_on_madrid(sfm, golden_dir, madrid):
+    """scripts/sfm_pipeline.py:82-83, step 7: reconstruction_estimator.EstimatePosition(loss_func_position, position_error_type)
+    after the rotation averaging of step 3, on the shipped dataset (379 views: the exact dense factorisation, the role of the
+    reference's SPARSE_NORMAL_CHOLESKY below 1000 cameras); compared with the CPU oracle on the same flattened inputs."""
+    from globalsfmpy_b200 import _capi as capi, loss_functions as lf, positions as P
+    from oracle import ra_oracle as orc
+    recon, graph, covs = _graph_from_fixture(sfm, golden_dir)
+    options = sfm.ReconstructionBuilderOptions()
+    builder = sfm.ReconstructionBuilder(options, recon, graph)
+    builder.CheckView()
+    est = sfm.GlobalReconstructionEstimator(options.reconstruction_estimator_options)
+    est.FilterInitialViewGraphAndCalibrateCameras(builder.get_view_graph(), builder.get_reconstruction())
+    assert est.EstimateGlobalRotationsUncertainty(lf.MAGSACWeightBasedLoss(0.02), covs, sfm.RotationErrorType.ANGLE_AXIS_COVARIANCE)
+    assert est.EstimatePosition(lf.HuberLoss(0.1), sfm.PositionErrorType.BASELINE)
+    ids = sorted(est.orientations)
+    assert sorted(est.positions) == ids and len(ids) == 379
+    assert not np.asarray(est.positions[ids[0]]).any()                 # the constant view stays at the origin
+    x = np.array([est.positions[v] for v in ids])
+    assert np.isfinite(x).all() and np.abs(x).max() > 0
+    # the oracle on the same inputs
+    dense = {v: k for k, v in enumerate(ids)}
+    edges = est.get_view_graph().GetAllEdges()
+    ei = np.array([dense[a] for a, b in edges], np.uint32)
+    ej = np.array([dense[b] for a, b in edges], np.uint32)
+    p2 = np.array([edges[k].position_2 for k in edges])
+    orient = np.array([est.orientations[v] for v in ids])
+    pp = P.PositionProblemArrays(len(ids), ei, ej, p2, orient, fixed_view=0)
+    o = P.default_options()
+    o.linear_solver = capi.SOLVER_DENSE_CHOLESKY
+    xo, so, _ = orc.solve(pp.as_rotation_solver_problem(), o, np.zeros((len(ids), 3)))
+    s = sfm._solve.last_summary
+    print(f"Madrid positions: {s.num_iterations} iterations (oracle {so.num_iterations}), cost {s.initial_cost:.6g} -> {s.final_cost:.9g} (oracle {so.final_cost:.9g})")
+    assert abs(s.initial_cost - so.initial_cost) <= 1e-9 * so.initial_cost
+    assert abs(s.final_cost - so.final_cost) <= 1e-6 * so.final_cost
+    assert np.abs(x - xo).max() <= 1e-5 * np.abs(xo).max()
 
 
 @pytest.mark.gpu
