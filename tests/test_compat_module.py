@@ -189,6 +189,14 @@ def test_pipeline_call_sequence_on_madrid(sfm, golden_dir, madrid):
     # the module hands the edges over in hash-map order; the solver sorts half-edges itself, so the result is the same
     ref, s, _ = solver.solve(prob, o, init_dev)
     assert np.array_equal(got, ref)
+    # ... and the module's DEFAULT options (AUTO -> the exact dense factorisation at 379 views, the role of the reference's
+    # SPARSE_NORMAL_CHOLESKY) against the CPU oracle's exact-solve trajectory: the north_star bar on the shipped dataset
+    from oracle import ra_oracle as orc
+    assert s.num_linear_unconverged == 0
+    om_o, s_o, _ = orc.solve(prob, o, init_dev)
+    err, _ = vg.mean_angular_error(om_o, got)
+    assert err <= 1e-4, err
+    assert abs(s.final_cost - s_o.final_cost) <= 1e-5 * s_o.final_cost
     # step 4 of the pipeline: the rotation filter (15 degrees in flags_1dsfm.yaml) on the device
     est.options.rotation_filtering_max_difference_degrees = 15.0
     n0 = view_graph.NumEdges()
