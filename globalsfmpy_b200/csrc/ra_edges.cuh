@@ -104,15 +104,19 @@ __global__ void __launch_bounds__(kBlock, 2) k_edges(const K1Args A) {
     mbar_wait(&wp.bars[st], (c / kStages) & 1u);
     return wp.ring + (size_t)st * kRD;
   };
-  auto gather = [&](const double* rec, uint64_t h, uint32_t& cf, Q4& qrow, Q4& qcol) {
+  // the two endpoint sectors of a half-edge, already in EDGE order (view i, view j): the side is resolved on the two indices,
+  // not by selecting between eight doubles afterwards
+  auto gather = [&](const double* rec, uint64_t h, uint32_t& cf, Q4& qi, Q4& qj) {
     const uint32_t* idx = reinterpret_cast<const uint32_t*>(rec + (4 + kU) * 32);
     cf = idx[lane];
     uint32_t row = idx[32 + lane];
     if (h >= hi) { cf = 0; row = 0; }  // padding lanes of the last record
-    const double4 a = reinterpret_cast<const double4*>(A.node_q)[row];
-    const double4 b = reinterpret_cast<const double4*>(A.node_q)[cf & ~kSideBit];
-    qrow = Q4{a.x, a.y, a.z, a.w};
-    qcol = Q4{b.x, b.y, b.z, b.w};
+    const uint32_t col = cf & ~kSideBit;
+    const bool rj = (cf & kSideBit) != 0;
+    const double4 a = reinterpret_cast<const double4*>(A.node_q)[rj ? col : row];
+    const double4 b = reinterpret_cast<const double4*>(A.node_q)[rj ? row : col];
+    qi = Q4{a.x, a.y, a.z, a.w};
+    qj = Q4{b.x, b.y, b.z, b.w};
   };
   for (uint32_t c = 0; c < nrec && c < (uint32_t)kStages; ++c) issue(c);
   if (nrec == 0 || t0 == t1) return;
@@ -124,14 +128,14 @@ __global__ void __launch_bounds__(kBlock, 2) k_edges(const K1Args A) {
   for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
   const double* rec = wait_rec(0);
   uint32_t cf;
-  Q4 qrow, qcol;
-  gather(rec, lo + lane, cf, qrow, qcol);
+  Q4 qi, qj;
+  gather(rec, lo + lane, cf, qi, qj);
   for (uint32_t c = 0; c < nrec; ++c) {
     const uint64_t cb = lo + ((uint64_t)c << 5), ce = cb + 32, h = cb + lane;
     const double* rec_n = nullptr;
     uint32_t cf_n = 0;
-    Q4 qrow_n{1, 0, 0, 0}, qcol_n{1, 0, 0, 0};
-    if (c + 1 < nrec) { rec_n = wait_rec(c + 1); gather(rec_n, ce + lane, cf_n, qrow_n, qcol_n); }
+    Q4 qi_n{1, 0, 0, 0}, qj_n{1, 0, 0, 0};
+    if (c + 1 < nrec) { rec_n = wait_rec(c + 1); gather(rec_n, ce + lane, cf_n, qi_n, qj_n); }
     const bool row_is_j = (cf & kSideBit) != 0;
     const Q4 qm{rec[lane], rec[32 + lane], rec[64 + lane], rec[96 + lane]};
     // translation averaging holds ONE view constant (position_estimator.cpp:121-122 SetParameterBlockConstant): its gradient is
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_edges(const K1Args A) {
     __syncwarp();
     if (c + kStages < nrec) issue(c + kStages);
     EdgeTerms et;
-    edge_terms<kWriteBlocks, kResidual, kScalarU, kLoss, true>(row_is_j ? qcol : qrow, row_is_j ? qrow : qcol, qm, u, A.loss, et);
+    edge_terms<kWriteBlocks, kResidual, kScalarU, kLoss, true>(qi, qj, qm, u, A.loss, et);  // (q_i, q_j): see gather
     double cur[kAcc];
     if (kWriteBlocks) {
       // both rows of the edge: diag += S, block(row, col) = -S; gradient: +v in row j, -v in row i; cost once, in row i
@@ -167,13 +171,16 @@ __global__ void __launch_bounds__(kBlock, 2) k_edges(const K1Args A) {
         }
       }
       if (h < hi) {
+        // lo is a multiple of 32: record (lo >> 5) + c, word `lane` of each component row
         if (kCompact) {
-          A.val[blk_index(h, 0, Rec<4>::kDoubles)] = et.ca;
+          double* out = A.val + ((size_t)(lo >> 5) + c) * Rec<4>::kDoubles + lane;
+          out[0] = et.ca;
 #pragma unroll
-          for (int k = 0; k < 3; ++k) A.val[blk_index(h, 1 + k, Rec<4>::kDoubles)] = et.h[k];
+          for (int k = 0; k < 3; ++k) out[(1 + k) * 32] = et.h[k];
         } else {
+          double* out = A.val + ((size_t)(lo >> 5) + c) * Rec<6>::kDoubles + lane;
 #pragma unroll
-          for (int k = 0; k < 6; ++k) A.val[blk_index(h, k, Rec<6>::kDoubles)] = -et.S[k];
+          for (int k = 0; k < 6; ++k) out[k * 32] = -et.S[k];
         }
       }
     } else {
@@ -199,7 +206,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_edges(const K1Args A) {
       sb = se; se = sb + A.seg_len[t];
       if (sb >= ce) break;
     }
-    rec = rec_n; cf = cf_n; qrow = qrow_n; qcol = qcol_n;
+    rec = rec_n; cf = cf_n; qi = qi_n; qj = qj_n;
     if (t == t1) break;
   }
 }
