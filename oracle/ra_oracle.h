@@ -11,7 +11,11 @@
  *     theia/sfm/global_pose_estimation/pairwise_rotation_error_test.cc:87-139,
  *   - every robust loss against the unmodified scripts/loss_functions.py executed in
  *     the build container (tests/golden/make_loss_golden.py -> loss_golden.npz),
- *   - the MAGSAC gamma tables against include/gamma_values.cpp (sampled golden).
+ *   - the MAGSAC gamma tables against include/gamma_values.cpp (sampled golden),
+ *   - the translation residual (GSFM_RA_POSITION_BASELINE problems: theia::PairwiseTranslationError under
+ *     src/GSfM_nonlinear_position_estimator.cpp:87-343) against the four known-answer cases of
+ *     theia/sfm/global_pose_estimation/pairwise_translation_error_test.cc:69-127 and a numpy / finite-difference
+ *     restatement of its Jacobian (tests/test_positions.py).
  * The trust-region loop restates Ceres Solver 1.14.0 (README.md:21, not vendored) from
  * its published algorithm: converged-solution parity vs. a Ceres binary is UNPINNED.
  */
@@ -46,7 +50,11 @@ void ra_oracle_edge(const double* wi, const double* wj, const double* wij, const
                     double* r, double* Ji, double* Jj);
 
 /* All edges: r [E][d], Ji/Jj [E][d][3], rho [E][3], d = the residual dimension of the error type (3; 4 for QUATERNION_NORM,
- * 9 for ROTATION_MAT_FNORM); any output may be NULL. */
+ * 9 for ROTATION_MAT_FNORM); any output may be NULL.
+ * Every entry point below also takes a TRANSLATION problem (error_type GSFM_RA_POSITION_BASELINE, include/gsfm_pa.h):
+ * `omega` then holds camera positions [N][3], problem->omega_ij the pairs' position_2, problem->orientation the global
+ * orientations, and problem->fixed_view the parameter block held constant (its gradient and the off-diagonal blocks that
+ * touch it are zero in the assembled system -- the reduced program Ceres solves). */
 int ra_oracle_eval_edges(const gsfm_ra_problem* p, const gsfm_ra_loss* loss, const double* omega,
                          double* r, double* Ji, double* Jj, double* rho, int num_threads);
 
