@@ -177,3 +177,63 @@ def test_edge_sharding_sums_with_gloo():
         for s in range(rp[a], rp[a + 1]):
             yref[a] += val[s] @ x[col[s]]
     assert np.allclose(y, yref, rtol=1e-12, atol=1e-12 * np.abs(yref).max())
+
+
+def _gloo_worker_positions(rank, world, port, q):
+    """Translation averaging, edge sharded: every shard zeroes the constant view's gradient and the off-diagonal blocks that
+    touch it on its own pairs, so the all-reduced system is the reduced system of the whole problem."""
+    import torch.distributed as dist
+    import torch
+    sys.path.insert(0, ROOT)
+    from globalsfmpy_b200 import _abi as capi, positions as P
+    from oracle import ra_oracle as orc
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = P.synthetic_position_graph(50, 400, seed=23)
+    L = capi.Loss.make(capi.LOSS_HUBER, 0.1)
+    E = 400
+    e0, e1 = E * rank // world, E * (rank + 1) // world
+    shard = P.PositionProblemArrays(50, d["edge_i"][e0:e1], d["edge_j"][e0:e1], d["position_2"][e0:e1], d["orientation"],
+                                    fixed_view=7).as_rotation_solver_problem()
+    x = d["positions_gt"] + 0.3
+    cost, grad, hd, rp, col, val = orc.assemble(shard, L, x)
+    v = np.random.default_rng(2).normal(size=(50, 3))
+    y = np.zeros((50, 3))
+    for a in range(50):
+        for s_ in range(rp[a], rp[a + 1]):
+            y[a] += val[s_] @ v[col[s_]]
+    buf = torch.from_numpy(np.concatenate([hd.ravel(), grad.ravel(), [cost], y.ravel()]))
+    dist.all_reduce(buf)
+    if rank == 0:
+        q.put(buf.numpy().copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_position_sharding_sums_with_gloo():
+    import torch.multiprocessing as mp
+    sys.path.insert(0, ROOT)
+    from globalsfmpy_b200 import _abi as capi, positions as P
+    from oracle import ra_oracle as orc
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker_positions, args=(r, 2, 29547, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    buf = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    d = P.synthetic_position_graph(50, 400, seed=23)
+    L = capi.Loss.make(capi.LOSS_HUBER, 0.1)
+    full = P.PositionProblemArrays(50, d["edge_i"], d["edge_j"], d["position_2"], d["orientation"], fixed_view=7).as_rotation_solver_problem()
+    x = d["positions_gt"] + 0.3
+    cost, grad, hd, rp, col, val = orc.assemble(full, L, x)
+    v = np.random.default_rng(2).normal(size=(50, 3))
+    y = np.zeros((50, 3))
+    for a in range(50):
+        for s_ in range(rp[a], rp[a + 1]):
+            y[a] += val[s_] @ v[col[s_]]
+    ref = np.concatenate([hd.ravel(), grad.ravel(), [cost], y.ravel()])
+    assert np.allclose(buf, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+    assert not grad[7].any() and not y[7].any()      # the constant view: no gradient, no coupling
