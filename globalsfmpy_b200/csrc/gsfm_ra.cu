@@ -8,12 +8,16 @@
 // Data layout.  The view graph is stored as HALF-EDGES: every edge (i,j)
 // appears once in row i and once in row j, sorted by (row, col); a row's half-edges are
 // contiguous, so per-view sums (diagonal block, gradient) are segmented reductions over a
-// contiguous range and need no atomics.  Rows are cut into TASKS of <= kTaskLen half-edges; one
-// warp owns one task, lanes stride the task with fully coalesced planar (SoA) loads.  The
-// normal-equation matrix lives in the LEFT TANGENT frame (see so3_device.cuh): H = D^T Ht D with
-// D = blockdiag(Jl(omega_i)), so the per-edge kernel never touches the per-view Jl factors; the
+// contiguous range and need no atomics.  The half-edge array is cut into equal contiguous RANGES,
+// one per resident warp of the kernel that walks it, and every range at row boundaries into
+// SEGMENTS; records of 32 half-edges are planar (SoA) and travel by bulk async copy (TMA).  The
+// normal-equation matrix lives in the BODY tangent frame (see so3_device.cuh): H = D^T Ht D with
+// D = blockdiag(Jr(omega_i)), so the per-edge kernel never touches the per-view factors; the
 // Euclidean (angle-axis) Levenberg-Marquardt of Ceres is reproduced exactly by transforming the
 // LM diagonal per view.
+//
+// The same solver runs robust TRANSLATION averaging (include/gsfm_pa.h; reference
+// src/GSfM_nonlinear_position_estimator.cpp): error type GSFM_RA_POSITION_BASELINE, D = I.
 #include "ra_common.cuh"
 #include "ra_structure.cuh"
 #include "ra_edges.cuh"
