@@ -153,6 +153,19 @@ def test_position_problem_is_checked_before_the_device():
     assert capi.lib().gsfm_pa_as_ra_problem(C.byref(pp.c), C.byref(q)) == capi.ERR_INVALID
 
 
+def test_no_cpu_fallback_for_positions():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    d, pp, rp = _problem(8, 20)
+    with pytest.raises(capi.GsfmError) as e:
+        P.solve(pp, P.default_options())
+    assert e.value.code == capi.ERR_NO_DEVICE
+    with pytest.raises(capi.GsfmError) as e:
+        P.eval_edges(pp, HUBER, np.zeros((8, 3)))
+    assert e.value.code == capi.ERR_NO_DEVICE
+
+
 # ------------------------------------------------------------------------------------------------ GPU: the CUDA path
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,p1,p2,direction,weight", KNOWN)
