@@ -92,11 +92,21 @@ __global__ void __launch_bounds__(kBlock, 2) k_edges(const K1Args A) {
   const uint32_t t0 = A.warp_seg_ptr[gw], t1 = A.warp_seg_ptr[gw + 1];
   const uint32_t nrec = (uint32_t)((hi - lo + 31) >> 5);
   const double* src = A.inrec + (size_t)(lo >> 5) * kRD;
+  // The input records are read ONCE per evaluation (96 MB at 1M edges): loaded with the evict_first L2 policy they do not push
+  // out the block records this kernel writes (72 MB), which the persistent PCG kernel streams right afterwards.
+  // (-DGSFM_RA_K1_NO_HINT: plain loads, A/B builds.)
+#ifndef GSFM_RA_K1_NO_HINT
+  const uint64_t pol_once = l2_policy_evict_first();
+#endif
   auto issue = [&](uint32_t c) {
     if (lane == 0) {
       const uint32_t st = c % kStages;
       mbar_expect_tx(&wp.bars[st], kRB);
+#ifndef GSFM_RA_K1_NO_HINT
+      tma_load_bulk_hint(wp.ring + (size_t)st * kRD, src + (size_t)c * kRD, kRB, &wp.bars[st], pol_once);
+#else
       tma_load_bulk(wp.ring + (size_t)st * kRD, src + (size_t)c * kRD, kRB, &wp.bars[st]);
+#endif
     }
   };
   auto wait_rec = [&](uint32_t c) -> const double* {
