@@ -719,17 +719,42 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
     CUDA_TRY(cudaMemcpyAsync(d.p, src, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     return 0;
   };
-  auto up64 = [&](DevBuf<double>& d, const double* src, size_t n) -> int {
-    RA_TRY(d.alloc(n));
-    CUDA_TRY(cudaMemcpyAsync(d.p, src, n * sizeof(double), cudaMemcpyHostToDevice, st));
-    return 0;
-  };
   RA_TRY(up32(s->d_ei, prob->edge_i + e0, E));
   RA_TRY(up32(s->d_ej, prob->edge_j + e0, E));
-  RA_TRY(up64(s->d_omega_ij, prob->omega_ij + 3 * e0, 3 * E));
-  if (prob->cov6) RA_TRY(up64(s->d_cov6, prob->cov6 + 6 * e0, 6 * E));
-  if (prob->edge_weight) RA_TRY(up64(s->d_weight, prob->edge_weight + e0, E));
-  if (s->position()) RA_TRY(up64(s->d_orient, prob->orientation, 3ull * N));
+  // The structure build below needs only the two index arrays.  The per-edge PAYLOAD (measurements, covariances, weights: 24 to
+  // 80 bytes per edge against 8 of indices) is uploaded on a second stream while the keys are sorted and the partitions built;
+  // K0, its first reader, waits for it.  (GSFM_RA_NO_COPY_STREAM=1: everything on the solver's stream, A/B runs.)
+  struct CopyStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t ready = nullptr, done = nullptr;
+    ~CopyStream() {
+      if (s) cudaStreamSynchronize(s);
+      if (ready) cudaEventDestroy(ready);
+      if (done) cudaEventDestroy(done);
+      if (s) cudaStreamDestroy(s);
+    }
+  } cs;
+  const bool overlap_upload = std::getenv("GSFM_RA_NO_COPY_STREAM") == nullptr;
+  cudaStream_t up = st;
+  if (overlap_upload) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&cs.s, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&cs.ready, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&cs.done, cudaEventDisableTiming));
+    up = cs.s;
+  }
+  RA_TRY(s->d_omega_ij.alloc(3 * E));
+  if (prob->cov6) RA_TRY(s->d_cov6.alloc(6 * E));
+  if (prob->edge_weight) RA_TRY(s->d_weight.alloc(E));
+  if (s->position()) RA_TRY(s->d_orient.alloc(3ull * N));
+  if (overlap_upload) {  // the buffers come from the pool in the order of the solver's stream
+    CUDA_TRY(cudaEventRecord(cs.ready, st));
+    CUDA_TRY(cudaStreamWaitEvent(up, cs.ready, 0));
+  }
+  CUDA_TRY(cudaMemcpyAsync(s->d_omega_ij.p, prob->omega_ij + 3 * e0, 3 * E * sizeof(double), cudaMemcpyHostToDevice, up));
+  if (prob->cov6) CUDA_TRY(cudaMemcpyAsync(s->d_cov6.p, prob->cov6 + 6 * e0, 6 * E * sizeof(double), cudaMemcpyHostToDevice, up));
+  if (prob->edge_weight) CUDA_TRY(cudaMemcpyAsync(s->d_weight.p, prob->edge_weight + e0, E * sizeof(double), cudaMemcpyHostToDevice, up));
+  if (s->position()) CUDA_TRY(cudaMemcpyAsync(s->d_orient.p, prob->orientation, 3ull * N * sizeof(double), cudaMemcpyHostToDevice, up));
+  if (overlap_upload) CUDA_TRY(cudaEventRecord(cs.done, up));
   lap("enqueue uploads");
 
   // ---- half-edges sorted by (column block, row, col): keys -> radix sort -> unpack (ra_structure.cuh) ---------------
@@ -839,6 +864,7 @@ int build_solver(const gsfm_ra_problem* prob, const gsfm_ra_options* options, in
     RA_TRY(s->inrec.alloc(nrec_in * rd));
     CUDA_TRY(cudaMemsetAsync(s->inrec.p + (nrec_in - 1) * rd, 0, rd * 8, st));  // lanes past H in the last record
   }
+  if (overlap_upload) CUDA_TRY(cudaStreamWaitEvent(st, cs.done, 0));  // the payload is on the device from here on
   k_setup_halfedges<<<grid_for(H), kBlock, 0, st>>>(H, s->ku, s->he_edge.p, s->he_row.p, s->he_col.p, s->d_omega_ij.p, s->d_cov6.p, s->d_weight.p,
                                                     prob->error_type, s->inrec.p, s->d_ei.p, s->d_orient.p);
   s->launches += 1;
